@@ -1,0 +1,217 @@
+/*
+ * empc_b200.h — C ABI of the B200-native SbFDDP hot path (drop-in for eagle-mpc's solver path).
+ *
+ * Everything that crosses this boundary is plain-old-data: fixed-size structs, pointers and sizes.
+ * No C++ types, no torch types, no exceptions.  The host-side mirror of eagle-mpc's C++ surfaces
+ * (Trajectory / Stage / factories / SolverSbFDDP / MPC controllers, see eagle-mpc_b200/host/) flattens a
+ * problem into an `empc_problem_desc_t` and drives the CUDA kernels through the functions below.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the eagle-mpc tree):
+ *   empc_create            SolverSbFDDP::SolverSbFDDP(problem, squashing)        src/sbfddp.cpp:5-38 (+ barrierInit :169-190)
+ *   empc_set_x0            crocoddyl::ShootingProblem::set_x0                     examples/python/mpc.py:50
+ *   empc_set_candidate     crocoddyl::SolverAbstract::setCandidate                src/sbfddp.cpp:199
+ *   empc_set_params        set_convergence_init / solve(maxiter)                  include/eagle_mpc/sbfddp.hpp:43-52
+ *   empc_update_costs      {Carrot,Rail,Weighted}Mpc::updateProblem               src/mpc-controllers/carrot-mpc.cpp:298-401
+ *   empc_solve             SolverSbFDDP::solve                                    src/sbfddp.cpp:192-226
+ *   empc_get_*             get_xs/get_us/get_K/get_k/get_cost/get_iter, getSquashControls  src/sbfddp.cpp:487
+ *   empc_phase_*           computeDirection / tryStep (tile-level parity hooks)   src/sbfddp.cpp:244,264
+ *
+ * Conventions (Crocoddyl 1.x / Pinocchio 2.x, restated in DESIGN.md):
+ *   x = [q ; v],  q = [p(3), quat xyzw(4), theta(na)],  v = [v_lin(3), omega(3) (body frame), theta_dot(na)]
+ *   nq = 7+na, nv = 6+na, nx = nq+nv, ndx = 2 nv, nu = n_rotors + na.
+ *   All matrices are row-major doubles.
+ */
+#ifndef EMPC_B200_H
+#define EMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMPC_MAX_JOINTS 8   /* free-flyer + up to 7 revolute joints */
+#define EMPC_MAX_FRAMES 16
+#define EMPC_MAX_ROTORS 8
+#define EMPC_MAX_NU 16
+#define EMPC_N_ALPHAS 10    /* line-search step lengths 2^0 .. 2^-9 (crocoddyl SolverDDP ctor) */
+
+/* status codes */
+enum {
+  EMPC_OK = 0,
+  EMPC_ERR_INVALID = 1,  /* bad argument / unsupported problem */
+  EMPC_ERR_CUDA = 2,     /* CUDA runtime error (see empc_last_error) */
+  EMPC_ERR_UNSUPPORTED = 3
+};
+
+/* cost (residual) types — src/factory/cost.cpp:38-168 */
+enum {
+  EMPC_COST_STATE = 0,
+  EMPC_COST_CONTROL = 1,
+  EMPC_COST_FRAME_PLACEMENT = 2,
+  EMPC_COST_FRAME_ROTATION = 3,
+  EMPC_COST_FRAME_VELOCITY = 4,
+  EMPC_COST_FRAME_TRANSLATION = 5,
+  EMPC_COST_SQUASH_BARRIER = 6 /* the "barrier" cost SolverSbFDDP adds, src/sbfddp.cpp:169-190 */
+};
+
+/* activation types — src/factory/activation.cpp:34-101 */
+enum {
+  EMPC_ACT_QUAD = 0,
+  EMPC_ACT_WEIGHTED_QUAD = 1,
+  EMPC_ACT_QUAD_BARRIER = 2,
+  EMPC_ACT_WEIGHTED_QUAD_BARRIER = 3
+};
+
+/* Rigid-body tree: joint 0 is the free-flyer (Pinocchio "root_joint"), joints 1.. are revolute. */
+typedef struct empc_robot {
+  int32_t n_joints;                       /* 1 + number of arm joints */
+  int32_t n_frames;                       /* operational frames referenced by costs */
+  int32_t parent[EMPC_MAX_JOINTS];        /* parent joint index, -1 for joint 0 */
+  double jplace_R[EMPC_MAX_JOINTS][9];    /* joint placement in the parent joint frame (rotation) */
+  double jplace_p[EMPC_MAX_JOINTS][3];    /* ... translation */
+  double axis[EMPC_MAX_JOINTS][3];        /* revolute axis, unit, joint frame (unused for joint 0) */
+  double mass[EMPC_MAX_JOINTS];           /* body inertia attached to joint i, expressed in joint frame */
+  double com[EMPC_MAX_JOINTS][3];
+  double inertia[EMPC_MAX_JOINTS][9];     /* rotational inertia about the COM, 3x3 */
+  double gravity[3];                      /* world linear gravity, (0,0,-9.81) */
+  int32_t frame_joint[EMPC_MAX_FRAMES];   /* joint each frame hangs on */
+  double frame_R[EMPC_MAX_FRAMES][9];     /* frame placement in that joint's frame */
+  double frame_p[EMPC_MAX_FRAMES][3];
+} empc_robot_t;
+
+/* One cost term of a CostModelSum.  Offsets index `pool` (doubles); -1 = absent.
+ * Reference layouts: STATE nx | CONTROL nu | FRAME_PLACEMENT R(9)+p(3) | FRAME_ROTATION R(9) |
+ * FRAME_VELOCITY lin(3)+ang(3) | FRAME_TRANSLATION p(3) | SQUASH_BARRIER none.
+ * Activation vectors (weights / lower / upper bound) have the residual's dimension. */
+typedef struct empc_cost {
+  int32_t type;
+  int32_t activation;
+  int32_t frame;
+  int32_t active;
+  double weight;
+  int32_t ref_off;
+  int32_t w_off;
+  int32_t lb_off;
+  int32_t ub_off;
+} empc_cost_t;
+
+/* Flat shooting problem.  A "cost set" is one CostModelSum (costs already in the order the reference
+ * iterates them: std::map<std::string,...> => sorted by name).  node_costset has n_node_maps*(T+1)
+ * entries; entry [m*(T+1)+t] is the cost set of node t (t = T is the terminal node) under map m. */
+typedef struct empc_problem_desc {
+  empc_robot_t robot;
+  int32_t n_rotors;
+  int32_t use_squash;                       /* 1: ActuationSquashingModel (required by the solver) */
+  double tau_f[6 * EMPC_MAX_ROTORS];        /* 6 x n_rotors, row-major (src/multicopter-base-params.cpp:67-78) */
+  double u_lb[EMPC_MAX_NU];
+  double u_ub[EMPC_MAX_NU];
+  double dt;                                /* seconds */
+  int32_t T;                                /* number of running nodes */
+  int32_t n_costsets;
+  int32_t n_costs;
+  int32_t n_pool;
+  int32_t n_node_maps;
+  const int32_t* costset_begin;             /* n_costsets+1 */
+  const empc_cost_t* costs;                 /* n_costs */
+  const double* pool;                       /* n_pool */
+  const int32_t* node_costset;              /* n_node_maps*(T+1) */
+} empc_problem_desc_t;
+
+/* Solver constants: eagle-mpc's (src/sbfddp.cpp:5-29) and crocoddyl SolverDDP/FDDP defaults. */
+typedef struct empc_solver_params {
+  int32_t maxiter;          /* solve(maxiter), default 100 */
+  int32_t stop_gap_norm;    /* fork policy knob: 0 = max_t ||fs_t||_inf, 1 = sum_t ||fs_t||_1 */
+  int32_t squash_quirk;     /* oracle only: emulate us_squash = "last calc on the data"  */
+  int32_t reserved;
+  double convergence_init;  /* 1e-2 */
+  double convergence_stop;  /* 1e-3 */
+  double convergence_mult;  /* 1e-1 */
+  double smooth_init;       /* 0.1 */
+  double smooth_mult;       /* 0.5 */
+  double barrier_weight;    /* 1e-3 */
+  double reg_init;          /* 1e-9 */
+  double reg_min;           /* 1e-9 */
+  double reg_max;           /* 1e9 */
+  double reg_factor;        /* 10 */
+  double th_acceptstep;     /* 0.1 */
+  double th_acceptnegstep;  /* 2 */
+  double th_grad;           /* 1e-12 */
+  double th_gaptol;         /* 1e-16 */
+  double th_stepdec;        /* 0.5 */
+  double th_stepinc;        /* 0.01 */
+  double th_stop_gaps;      /* 1.0 */
+} empc_solver_params_t;
+
+/* Fills `p` with the reference defaults listed above. */
+void empc_default_params(empc_solver_params_t* p);
+
+/* Derived dimensions of a problem. */
+typedef struct empc_dims {
+  int32_t nq, nv, nx, ndx, nu, T, batch;
+  int32_t tile;       /* doubles per node tile: Fx|Fu|Lxx|Lxu|Luu|Lx|Lu, padded to an even count */
+} empc_dims_t;
+
+typedef struct empc_solver empc_solver_t; /* opaque handle: owns all device memory */
+
+/* ---- lifetime ---- */
+int empc_create(const empc_problem_desc_t* desc, int32_t batch, int32_t device, empc_solver_t** out);
+int empc_destroy(empc_solver_t* h);
+const char* empc_last_error(void);
+int empc_get_dims(const empc_solver_t* h, empc_dims_t* out);
+
+/* ---- inputs (host pointers, copied; caller keeps ownership) ---- */
+int empc_set_x0(empc_solver_t* h, const double* x0 /* batch*nx */);
+/* xs: batch*(T+1)*nx or NULL (=> state.zero()); us: batch*T*nu or NULL (=> 0). */
+int empc_set_candidate(empc_solver_t* h, const double* xs, const double* us, int32_t is_feasible);
+int empc_set_params(empc_solver_t* h, const empc_solver_params_t* p);
+/* per-OCP node map selection, batch entries in [0,n_node_maps); NULL => all 0 */
+int empc_set_node_maps(empc_solver_t* h, const int32_t* ocp_map);
+/* MPC retargeting: overwrite `n` cost records starting at `first_cost` and `n_pool` doubles at `pool_off`. */
+int empc_update_costs(empc_solver_t* h, int32_t first_cost, int32_t n, const empc_cost_t* costs,
+                      int32_t pool_off, int32_t n_pool, const double* pool);
+int empc_update_node_costsets(empc_solver_t* h, const int32_t* node_costset /* n_node_maps*(T+1) */);
+
+/* ---- the hot path ---- */
+/* Full SbFDDP solve of the whole batch (squash-smoothing schedule, FDDP passes, DDP clean-up). */
+int empc_solve(empc_solver_t* h);
+/* Same, but inputs (x0, warm start) are already device-resident from a previous set_* / solve:
+ * restarts every OCP from its stored x0 and initial candidate (used by bench.py's `value` leg). */
+int empc_reset(empc_solver_t* h);
+
+/* ---- outputs (host pointers) ---- */
+int empc_get_xs(const empc_solver_t* h, double* xs /* batch*(T+1)*nx */);
+int empc_get_us(const empc_solver_t* h, double* us /* batch*T*nu */);
+int empc_get_us_squash(const empc_solver_t* h, double* us_squash /* batch*T*nu */);
+int empc_get_K(const empc_solver_t* h, double* K /* batch*T*nu*ndx */);
+int empc_get_k(const empc_solver_t* h, double* k /* batch*T*nu */);
+int empc_get_cost(const empc_solver_t* h, double* cost /* batch */);
+int empc_get_iters(const empc_solver_t* h, int32_t* iters /* batch: iter_ as left by solve() */);
+int empc_get_stop(const empc_solver_t* h, double* stop /* batch */);
+int empc_get_feasible(const empc_solver_t* h, int32_t* feasible /* batch */);
+int empc_get_reg(const empc_solver_t* h, double* xreg /* batch */);
+/* total inner iterations executed by the last solve, summed over the batch (the benchmark's work unit) */
+int empc_get_total_iterations(const empc_solver_t* h, int64_t* total);
+/* number of kernel launches issued by the last solve and device time (ms) spent per kernel family:
+ * [0]=calc_diff [1]=backward [2]=rollout [3]=decide */
+int empc_get_launch_stats(const empc_solver_t* h, int64_t* launches, double* ms_by_kernel /* 4 or NULL */);
+int empc_enable_kernel_timing(empc_solver_t* h, int32_t on);
+
+/* ---- tile-level parity hooks (one phase on the current candidate of every OCP) ---- */
+int empc_phase_calc_diff(empc_solver_t* h, double smooth);      /* calc + calcDiff + gaps */
+int empc_phase_backward(empc_solver_t* h, double xreg, int32_t is_feasible, int32_t* ok /* batch */);
+int empc_phase_rollout(empc_solver_t* h, double smooth, int32_t is_feasible, int32_t ddp);
+int empc_get_tiles(const empc_solver_t* h, double* tiles /* batch*(T+1)*tile */);
+int empc_get_xnext(const empc_solver_t* h, double* xnext /* batch*(T+1)*nx (row T unused) */);
+int empc_get_node_cost(const empc_solver_t* h, double* c /* batch*(T+1) */);
+int empc_get_gaps(const empc_solver_t* h, double* fs /* batch*(T+1)*ndx */);
+int empc_get_Vx(const empc_solver_t* h, double* Vx /* batch*(T+1)*ndx */);
+int empc_get_Vxx_fs(const empc_solver_t* h, double* g /* batch*(T+1)*ndx */);
+int empc_get_dgdq(const empc_solver_t* h, double* dgdq /* batch*2 */);
+int empc_get_trial(const empc_solver_t* h, int32_t alpha_index, double* xs_try, double* us_try,
+                   double* cost_try /* batch */, double* dv /* batch */, int32_t* ok /* batch */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMPC_B200_H */

@@ -1,0 +1,682 @@
+// oracle_model.hpp — TEST INFRASTRUCTURE ONLY (CPU oracle; parity unpinned, see oracle_math.hpp header).
+//
+// Per-node action model of eagle-mpc's shooting problems, restated from the Crocoddyl 1.x / Pinocchio 2.x chain the
+// reference instantiates (src/factory/diff-action.cpp:31-35, src/factory/int-action.cpp:26, src/trajectory.cpp:47-52):
+//   IntegratedActionModelEuler            crocoddyl/core/integrator/euler.hxx           (calc / calcDiff)
+//   DifferentialActionModelFreeFwdDynamics crocoddyl/multibody/actions/free-fwddyn.hxx
+//   ActuationSquashingModel + SquashingModelSmoothSat + ActuationModelMultiCopterBase
+//   CostModelSum / CostModelResidual / Activation* / Residual{State,Control,Frame*}
+//   StateMultibody (integrate / diff / Jdiff / Jintegrate / JintegrateTransport)
+//   pinocchio::aba, pinocchio::computeABADerivatives, frame kinematics
+#pragma once
+#include <vector>
+
+#include "../include/empc_b200.h"
+#include "oracle_math.hpp"
+
+namespace orc {
+
+constexpr int MAXJ = EMPC_MAX_JOINTS;
+constexpr int MAXV = 6 + MAXJ - 1;
+constexpr int MAXQ = MAXV + 1;
+constexpr int MAXX = MAXQ + MAXV;
+constexpr int MAXDX = 2 * MAXV;
+constexpr int MAXU = EMPC_MAX_NU;
+
+struct Model {
+  const empc_problem_desc_t* d = nullptr;
+  int nj = 0, na = 0, nq = 0, nv = 0, nx = 0, ndx = 0, nu = 0, nr = 0, tile = 0;
+  int col0[MAXJ];          // first velocity column of joint i
+  int ncol[MAXJ];          // 6 for the free-flyer, 1 for revolute
+  int joint_of_col[MAXV];  // joint owning velocity column c
+  bool anc[MAXJ][MAXJ];    // anc[j][k]: joint j is an ancestor of k, or k itself
+  SE3 jplace[MAXJ];
+  double Y[MAXJ][36];
+  SE3 fplace[EMPC_MAX_FRAMES];
+  double a0[6];            // -gravity as a spatial acceleration
+  double dt = 0;
+  // tile offsets
+  int oFx, oFu, oLxx, oLxu, oLuu, oLx, oLu;
+
+  void init(const empc_problem_desc_t* desc) {
+    d = desc;
+    const empc_robot_t& r = d->robot;
+    nj = r.n_joints; na = nj - 1; nq = 7 + na; nv = 6 + na; nx = nq + nv; ndx = 2 * nv;
+    nr = d->n_rotors; nu = nr + na; dt = d->dt;
+    for (int i = 0; i < nj; ++i) {
+      col0[i] = (i == 0) ? 0 : 5 + i;
+      ncol[i] = (i == 0) ? 6 : 1;
+      std::memcpy(jplace[i].R, r.jplace_R[i], sizeof(double) * 9);
+      std::memcpy(jplace[i].p, r.jplace_p[i], sizeof(double) * 3);
+      inertia_matrix(r.mass[i], r.com[i], r.inertia[i], Y[i]);
+    }
+    for (int c = 0; c < nv; ++c) joint_of_col[c] = (c < 6) ? 0 : c - 5;
+    for (int j = 0; j < nj; ++j)
+      for (int k = 0; k < nj; ++k) {
+        bool a = false;
+        for (int m = k; m >= 0; m = r.parent[m]) if (m == j) { a = true; break; }
+        anc[j][k] = a;
+      }
+    for (int f = 0; f < r.n_frames; ++f) {
+      std::memcpy(fplace[f].R, r.frame_R[f], sizeof(double) * 9);
+      std::memcpy(fplace[f].p, r.frame_p[f], sizeof(double) * 3);
+    }
+    for (int i = 0; i < 3; ++i) { a0[i] = -r.gravity[i]; a0[3 + i] = 0; }
+    oFx = 0; oFu = oFx + ndx * ndx; oLxx = oFu + ndx * nu; oLxu = oLxx + ndx * ndx; oLuu = oLxu + ndx * nu;
+    oLx = oLuu + nu * nu; oLu = oLx + ndx;
+    tile = oLu + nu; tile += tile & 1;
+  }
+};
+
+// ---- StateMultibody (crocoddyl/multibody/states/multibody.hxx) -----------------------------------------------------
+inline void state_zero(const Model& m, double* x) {
+  for (int i = 0; i < m.nx; ++i) x[i] = 0;
+  x[6] = 1;
+}
+inline void q_to_se3(const double* q, SE3& M) {
+  quat_to_R(q + 3, M.R);
+  M.p[0] = q[0]; M.p[1] = q[1]; M.p[2] = q[2];
+}
+// pinocchio::integrate on SE3 x R^na (special-euclidean.hpp integrate_impl) ; v += dv
+inline void state_integrate(const Model& m, const double* x, const double* dx, double* out) {
+  SE3 M0, E, M1;
+  q_to_se3(x, M0);
+  exp6(dx, E);
+  se3_mul(M0, E, M1);
+  double quat[4];
+  R_to_quat(M1.R, quat);
+  const double dotp = quat[0] * x[3] + quat[1] * x[4] + quat[2] * x[5] + quat[3] * x[6];
+  if (dotp < 0) for (int i = 0; i < 4; ++i) quat[i] = -quat[i];
+  const double n2 = quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3];
+  const double alpha = (3 - n2) / 2;  // quaternion::firstOrderNormalize
+  double o[MAXX];
+  o[0] = M1.p[0]; o[1] = M1.p[1]; o[2] = M1.p[2];
+  for (int i = 0; i < 4; ++i) o[3 + i] = quat[i] * alpha;
+  for (int i = 0; i < m.na; ++i) o[7 + i] = x[7 + i] + dx[6 + i];
+  for (int i = 0; i < m.nv; ++i) o[m.nq + i] = x[m.nq + i] + dx[m.nv + i];
+  std::memcpy(out, o, sizeof(double) * m.nx);
+}
+// dx = x1 (-) x0
+inline void state_diff(const Model& m, const double* x0, const double* x1, double* dx) {
+  SE3 M0, M1, D;
+  q_to_se3(x0, M0); q_to_se3(x1, M1);
+  se3_inv_mul(M0, M1, D);
+  log6(D, dx);
+  for (int i = 0; i < m.na; ++i) dx[6 + i] = x1[7 + i] - x0[7 + i];
+  for (int i = 0; i < m.nv; ++i) dx[m.nv + i] = x1[m.nq + i] - x0[m.nq + i];
+}
+
+// ---- per-node scratch (the crocoddyl "data" objects) ------------------------------------------------------------------
+struct Work {
+  double x[MAXX], u[MAXU];
+  double s[MAXU], ds[MAXU];   // squashed control and ds/du
+  double tau[MAXV];
+  SE3 liMi[MAXJ], oMi[MAXJ];
+  double v[MAXJ][6];          // local joint spatial velocities
+  double agf[MAXJ][6];        // local spatial accelerations incl. gravity field (data.a_gf)
+  double a[MAXV];             // joint accelerations
+  double dx[MAXDX];
+  double xnext[MAXX];
+  double cost;
+  // world-frame quantities of calcDiff
+  double J[6][MAXV];
+  double ov[MAXJ][6], oa[MAXJ][6];
+  double Minv[MAXV * MAXV];
+};
+
+struct SolverCtx {  // the pieces of solver state the node model depends on
+  double smooth;         // SquashingModelSmoothSat::smooth_
+  double barrier_weight; // weight of the "barrier" cost (1e-3)
+};
+
+// pinocchio::aba (algorithm/aba.hxx), local-frame three-pass recursion, SURVEY.md B.8
+inline void aba(const Model& m, const double* q, const double* vq, const double* tau, Work& w) {
+  const empc_robot_t& r = m.d->robot;
+  double Ia[MAXJ][36], pA[MAXJ][6], uu[MAXV];
+  double U[MAXJ][6], Dinv[MAXJ], UDinv[MAXJ][6];
+  for (int i = 0; i < m.nv; ++i) uu[i] = tau[i];
+  // pass 1
+  for (int i = 0; i < m.nj; ++i) {
+    if (i == 0) {
+      q_to_se3(q, w.liMi[0]);
+      w.oMi[0] = w.liMi[0];
+      for (int k = 0; k < 6; ++k) w.v[0][k] = vq[k];
+      for (int k = 0; k < 6; ++k) w.agf[0][k] = 0;  // c = v x vJ = 0 for the root
+    } else {
+      const double th = q[6 + i];  // q[7 + (i-1)]
+      double ax[3] = {r.axis[i][0] * th, r.axis[i][1] * th, r.axis[i][2] * th};
+      SE3 Mj; exp3(ax, Mj.R); Mj.p[0] = Mj.p[1] = Mj.p[2] = 0;
+      se3_mul(m.jplace[i], Mj, w.liMi[i]);
+      se3_mul(w.oMi[r.parent[i]], w.liMi[i], w.oMi[i]);
+      double vJ[6] = {0, 0, 0, r.axis[i][0] * vq[5 + i], r.axis[i][1] * vq[5 + i], r.axis[i][2] * vq[5 + i]};
+      double vp[6]; actinv_motion(w.liMi[i], w.v[r.parent[i]], vp);
+      for (int k = 0; k < 6; ++k) w.v[i][k] = vJ[k] + vp[k];
+      cross_mm(w.v[i], vJ, w.agf[i]);
+    }
+    std::memcpy(Ia[i], m.Y[i], sizeof(double) * 36);
+    double h[6]; mat6_vec(m.Y[i], w.v[i], h);
+    cross_mf(w.v[i], h, pA[i]);
+  }
+  // pass 2
+  double LL[36];  // Cholesky factor of the root articulated inertia
+  for (int i = m.nj - 1; i >= 0; --i) {
+    if (i == 0) {
+      for (int k = 0; k < 6; ++k) uu[k] -= pA[0][k];
+      std::memcpy(LL, Ia[0], sizeof(LL));
+      llt_inplace(LL, 6);
+    } else {
+      const double S[6] = {0, 0, 0, r.axis[i][0], r.axis[i][1], r.axis[i][2]};
+      const int c = m.col0[i];
+      uu[c] -= dot6(S, pA[i]);
+      mat6_vec(Ia[i], S, U[i]);
+      Dinv[i] = 1.0 / dot6(S, U[i]);
+      for (int k = 0; k < 6; ++k) UDinv[i][k] = U[i][k] * Dinv[i];
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) Ia[i][6 * a + b] -= UDinv[i][a] * U[i][b];
+      double pa[6], Iac[6];
+      mat6_vec(Ia[i], w.agf[i], Iac);
+      for (int k = 0; k < 6; ++k) pa[k] = pA[i][k] + Iac[k] + UDinv[i][k] * uu[c];
+      double X[36], Ip[36], fp[6];
+      force_action_matrix(w.liMi[i], X);
+      congruence6(X, Ia[i], Ip);
+      const int p = r.parent[i];
+      for (int k = 0; k < 36; ++k) Ia[p][k] += Ip[k];
+      act_force(w.liMi[i], pa, fp);
+      for (int k = 0; k < 6; ++k) pA[p][k] += fp[k];
+    }
+  }
+  // pass 3
+  for (int i = 0; i < m.nj; ++i) {
+    if (i == 0) {
+      double g[6]; actinv_motion(w.oMi[0], m.a0, g);
+      for (int k = 0; k < 6; ++k) w.agf[0][k] += g[k];
+      double rhs[6];
+      for (int k = 0; k < 6; ++k) rhs[k] = uu[k];
+      llt_solve(LL, 6, rhs, 1);  // Dinv * u
+      for (int k = 0; k < 6; ++k) { w.a[k] = rhs[k] - w.agf[0][k]; }  // UDinv = I for the free-flyer
+      for (int k = 0; k < 6; ++k) w.agf[0][k] += w.a[k];
+    } else {
+      double ap[6]; actinv_motion(w.liMi[i], w.agf[r.parent[i]], ap);
+      for (int k = 0; k < 6; ++k) w.agf[i][k] += ap[k];
+      const int c = m.col0[i];
+      w.a[c] = Dinv[i] * uu[c] - dot6(UDinv[i], w.agf[i]);
+      for (int k = 0; k < 3; ++k) w.agf[i][3 + k] += r.axis[i][k] * w.a[c];
+    }
+  }
+}
+
+// Recursive Newton-Euler (local frame), used only by tests as an independent check of aba / derivatives.
+inline void rnea(const Model& m, const double* q, const double* vq, const double* aq, double* tau) {
+  const empc_robot_t& r = m.d->robot;
+  SE3 liMi[MAXJ], oMi[MAXJ];
+  double v[MAXJ][6], a[MAXJ][6], f[MAXJ][6];
+  for (int i = 0; i < m.nj; ++i) {
+    if (i == 0) {
+      q_to_se3(q, liMi[0]); oMi[0] = liMi[0];
+      for (int k = 0; k < 6; ++k) v[0][k] = vq[k];
+      double g[6]; actinv_motion(oMi[0], m.a0, g);
+      for (int k = 0; k < 6; ++k) a[0][k] = g[k] + aq[k];
+    } else {
+      const double th = q[6 + i];
+      double ax[3] = {r.axis[i][0] * th, r.axis[i][1] * th, r.axis[i][2] * th};
+      SE3 Mj; exp3(ax, Mj.R); Mj.p[0] = Mj.p[1] = Mj.p[2] = 0;
+      se3_mul(m.jplace[i], Mj, liMi[i]);
+      se3_mul(oMi[r.parent[i]], liMi[i], oMi[i]);
+      double vJ[6] = {0, 0, 0, r.axis[i][0] * vq[5 + i], r.axis[i][1] * vq[5 + i], r.axis[i][2] * vq[5 + i]};
+      double vp[6], ap[6], c[6];
+      actinv_motion(liMi[i], v[r.parent[i]], vp);
+      for (int k = 0; k < 6; ++k) v[i][k] = vJ[k] + vp[k];
+      cross_mm(v[i], vJ, c);
+      actinv_motion(liMi[i], a[r.parent[i]], ap);
+      for (int k = 0; k < 6; ++k) a[i][k] = ap[k] + c[k];
+      for (int k = 0; k < 3; ++k) a[i][3 + k] += r.axis[i][k] * aq[5 + i];
+    }
+    double h[6], Ya[6], vh[6];
+    mat6_vec(m.Y[i], v[i], h); mat6_vec(m.Y[i], a[i], Ya); cross_mf(v[i], h, vh);
+    for (int k = 0; k < 6; ++k) f[i][k] = Ya[k] + vh[k];
+  }
+  for (int i = m.nj - 1; i >= 0; --i) {
+    if (i == 0) {
+      for (int k = 0; k < 6; ++k) tau[k] = f[0][k];
+    } else {
+      tau[5 + i] = r.axis[i][0] * f[i][3] + r.axis[i][1] * f[i][4] + r.axis[i][2] * f[i][5];
+      double fp[6]; act_force(liMi[i], f[i], fp);
+      for (int k = 0; k < 6; ++k) f[r.parent[i]][k] += fp[k];
+    }
+  }
+}
+
+// ---- activations (crocoddyl/core/activations/*.hpp) ------------------------------------------------------------------
+// returns a_value; fills Ar, Arr (diagonal).  w/lb/ub may be null depending on the type.
+inline double activation(int type, int n, const double* r, const double* w, const double* lb, const double* ub,
+                         double* Ar, double* Arr) {
+  double val = 0;
+  switch (type) {
+    case EMPC_ACT_QUAD:
+      for (int i = 0; i < n; ++i) { val += r[i] * r[i]; Ar[i] = r[i]; Arr[i] = 1; }
+      return 0.5 * val;
+    case EMPC_ACT_WEIGHTED_QUAD:
+      for (int i = 0; i < n; ++i) { const double wr = w[i] * r[i]; val += r[i] * wr; Ar[i] = wr; Arr[i] = w[i]; }
+      return 0.5 * val;
+    case EMPC_ACT_QUAD_BARRIER: {
+      double sl = 0, su = 0;
+      for (int i = 0; i < n; ++i) {
+        const double dl = r[i] - lb[i], du = r[i] - ub[i];
+        const double l = dl < 0 ? dl : 0.0, uu = du > 0 ? du : 0.0;
+        sl += l * l; su += uu * uu;
+        Ar[i] = l + uu;
+        Arr[i] = (dl <= 0) ? 1.0 : ((du >= 0) ? 1.0 : 0.0);
+      }
+      return 0.5 * sl + 0.5 * su;
+    }
+    case EMPC_ACT_WEIGHTED_QUAD_BARRIER: {
+      // weighted-quadratic-barrier.hpp: value and gradient use (w r)^2, the Hessian uses w (as upstream)
+      double sl = 0, su = 0;
+      for (int i = 0; i < n; ++i) {
+        const double dl = r[i] - lb[i], du = r[i] - ub[i];
+        const double l = (dl < 0 ? dl : 0.0) * w[i], uu = (du > 0 ? du : 0.0) * w[i];
+        sl += l * l; su += uu * uu;
+        Ar[i] = (l + uu) * w[i];
+        Arr[i] = (dl <= 0) ? w[i] : ((du >= 0) ? w[i] : 0.0);
+      }
+      return 0.5 * sl + 0.5 * su;
+    }
+  }
+  return 0;
+}
+
+struct CostEval {  // residual + activation of one cost, kept between calc and calcDiff
+  double r[MAXDX], Ar[MAXDX], Arr[MAXDX];
+  SE3 rMf;  // frame placement / rotation error
+};
+
+inline int residual_dim(const Model& m, int type) {
+  switch (type) {
+    case EMPC_COST_STATE: return m.ndx;
+    case EMPC_COST_CONTROL: return m.nu;
+    case EMPC_COST_SQUASH_BARRIER: return m.nu;
+    case EMPC_COST_FRAME_PLACEMENT: return 6;
+    case EMPC_COST_FRAME_VELOCITY: return 6;
+    default: return 3;
+  }
+}
+
+inline void frame_placement(const Model& m, const Work& w, int f, SE3& oMf) {
+  se3_mul(w.oMi[m.d->robot.frame_joint[f]], m.fplace[f], oMf);
+}
+
+// residual value + activation; returns the activation value
+inline double cost_calc(const Model& m, const SolverCtx& ctx, const empc_cost_t& c, const Work& w, CostEval& e) {
+  const double* pool = m.d->pool;
+  const double* ref = c.ref_off >= 0 ? pool + c.ref_off : nullptr;
+  const double* aw = c.w_off >= 0 ? pool + c.w_off : nullptr;
+  const double* lb = c.lb_off >= 0 ? pool + c.lb_off : nullptr;
+  const double* ub = c.ub_off >= 0 ? pool + c.ub_off : nullptr;
+  const int n = residual_dim(m, c.type);
+  switch (c.type) {
+    case EMPC_COST_STATE: state_diff(m, ref, w.x, e.r); break;
+    case EMPC_COST_CONTROL: for (int i = 0; i < n; ++i) e.r[i] = w.u[i] - ref[i]; break;
+    case EMPC_COST_SQUASH_BARRIER: {
+      // src/sbfddp.cpp:22-24,169-190,464-477: WeightedQuadraticBarrier(bounds(s_lb,s_ub,beta=1), 1/(smooth (ub-lb))^2)
+      double bw[MAXU], blb[MAXU], bub[MAXU];
+      for (int i = 0; i < n; ++i) {
+        const double aux = ctx.smooth * (m.d->u_ub[i] - m.d->u_lb[i]);
+        bw[i] = 1.0 / (aux * aux);
+        const double mid = 0.5 * (m.d->u_lb[i] + m.d->u_ub[i]), dd = 0.5 * (m.d->u_ub[i] - m.d->u_lb[i]);
+        blb[i] = mid - 1.0 * dd; bub[i] = mid + 1.0 * dd;  // crocoddyl::ActivationBounds ctor with beta = 1
+        e.r[i] = w.u[i];
+      }
+      return activation(EMPC_ACT_WEIGHTED_QUAD_BARRIER, n, e.r, bw, blb, bub, e.Ar, e.Arr);
+    }
+    case EMPC_COST_FRAME_PLACEMENT: {
+      SE3 Mref, oMf; std::memcpy(Mref.R, ref, 72); std::memcpy(Mref.p, ref + 9, 24);
+      frame_placement(m, w, c.frame, oMf);
+      se3_inv_mul(Mref, oMf, e.rMf);
+      log6(e.rMf, e.r);
+    } break;
+    case EMPC_COST_FRAME_ROTATION: {
+      SE3 oMf; frame_placement(m, w, c.frame, oMf);
+      matTmul3(ref, oMf.R, e.rMf.R);
+      double th; log3(e.rMf.R, e.r, th);
+    } break;
+    case EMPC_COST_FRAME_TRANSLATION: {
+      SE3 oMf; frame_placement(m, w, c.frame, oMf);
+      for (int i = 0; i < 3; ++i) e.r[i] = oMf.p[i] - ref[i];
+    } break;
+    case EMPC_COST_FRAME_VELOCITY: {
+      double vf[6]; actinv_motion(m.fplace[c.frame], w.v[m.d->robot.frame_joint[c.frame]], vf);
+      for (int i = 0; i < 6; ++i) e.r[i] = vf[i] - ref[i];
+    } break;
+  }
+  return activation(c.activation, n, e.r, aw, lb, ub, e.Ar, e.Arr);
+}
+
+// IntegratedActionModelEuler::calc — fills w (xnext, cost, and everything calcDiff reuses)
+inline void node_calc(const Model& m, const SolverCtx& ctx, int costset, const double* x, const double* u, Work& w,
+                      std::vector<CostEval>* evals = nullptr) {
+  const empc_problem_desc_t& d = *m.d;
+  std::memcpy(w.x, x, sizeof(double) * m.nx);
+  for (int i = 0; i < m.nu; ++i) w.u[i] = u ? u[i] : 0.0;  // calc(data,x) == calc(data,x,unone_=0), SURVEY B.7
+  // squashing (crocoddyl/core/actuation/squashing/smooth-sat.hpp)
+  for (int i = 0; i < m.nu; ++i) {
+    if (d.use_squash) {
+      const double dd = (d.u_ub[i] - d.u_lb[i]) * ctx.smooth, a = dd * dd;
+      const double l = w.u[i] - d.u_lb[i], h = w.u[i] - d.u_ub[i];
+      w.s[i] = 0.5 * (std::sqrt(l * l + a) - std::sqrt(h * h + a) + d.u_lb[i] + d.u_ub[i]);
+    } else {
+      w.s[i] = w.u[i];
+    }
+  }
+  // ActuationModelMultiCopterBase: tau = [tau_f s_rotors ; s_arm]
+  for (int i = 0; i < 6; ++i) {
+    double t = 0;
+    for (int j = 0; j < m.nr; ++j) t += d.tau_f[i * m.nr + j] * w.s[j];
+    w.tau[i] = t;
+  }
+  for (int i = 0; i < m.na; ++i) w.tau[6 + i] = w.s[m.nr + i];
+  aba(m, x, x + m.nq, w.tau, w);
+  // semi-implicit Euler (euler.hxx calc)
+  const double dt = m.dt, dt2 = dt * dt;
+  for (int i = 0; i < m.nv; ++i) {
+    w.dx[i] = x[m.nq + i] * dt + w.a[i] * dt2;
+    w.dx[m.nv + i] = w.a[i] * dt;
+  }
+  state_integrate(m, x, w.dx, w.xnext);
+  // CostModelSum::calc, costs in name order
+  double cost = 0;
+  const int c0 = d.costset_begin[costset], c1 = d.costset_begin[costset + 1];
+  if (evals) evals->resize(c1 - c0);
+  CostEval tmp;
+  for (int c = c0; c < c1; ++c) {
+    if (!d.costs[c].active) continue;
+    CostEval& e = evals ? (*evals)[c - c0] : tmp;
+    cost += d.costs[c].weight * cost_calc(m, ctx, d.costs[c], w, e);
+  }
+  w.cost = dt * cost;
+}
+
+// world Jacobian columns, velocities/accelerations, M^-1, d(ddq)/d(q,v,tau).  aq (nv x nv), av, Minv in w.Minv.
+inline void aba_derivatives(const Model& m, Work& w, double* a_q, double* a_v) {
+  const empc_robot_t& r = m.d->robot;
+  const int nv = m.nv;
+  double oY[MAXJ][36], Bm[MAXJ][36], F[MAXJ][6];
+  for (int i = 0; i < m.nj; ++i) {
+    // world Jacobian columns
+    if (i == 0) {
+      double X[36]; motion_action_matrix(w.oMi[0], X);
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) w.J[a][b] = X[6 * a + b];
+    } else {
+      const double S[6] = {0, 0, 0, r.axis[i][0], r.axis[i][1], r.axis[i][2]};
+      double Jc[6]; act_motion(w.oMi[i], S, Jc);
+      for (int a = 0; a < 6; ++a) w.J[a][m.col0[i]] = Jc[a];
+    }
+    act_motion(w.oMi[i], w.v[i], w.ov[i]);
+    act_motion(w.oMi[i], w.agf[i], w.oa[i]);
+    double X[36]; force_action_matrix(w.oMi[i], X);
+    congruence6(X, m.Y[i], oY[i]);
+    double h[6], Ya[6], vh[6];
+    mat6_vec(oY[i], w.ov[i], h); mat6_vec(oY[i], w.oa[i], Ya); cross_mf(w.ov[i], h, vh);
+    for (int k = 0; k < 6; ++k) F[i][k] = Ya[k] + vh[k];
+    // B_i = crf(v) Y - Y crm(v) + Hx(h)   (DESIGN.md "RNEA derivatives")
+    double Sv[9], Sw[9]; skew3(w.ov[i], Sv); skew3(w.ov[i] + 3, Sw);
+    double crf[36], crm[36];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        crf[6 * a + b] = Sw[3 * a + b]; crf[6 * a + 3 + b] = 0;
+        crf[6 * (3 + a) + b] = Sv[3 * a + b]; crf[6 * (3 + a) + 3 + b] = Sw[3 * a + b];
+        crm[6 * a + b] = Sw[3 * a + b]; crm[6 * a + 3 + b] = Sv[3 * a + b];
+        crm[6 * (3 + a) + b] = 0; crm[6 * (3 + a) + 3 + b] = Sw[3 * a + b];
+      }
+    double Shf[9], Shn[9]; skew3(h, Shf); skew3(h + 3, Shn);
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b < 6; ++b) {
+        double s1 = 0, s2 = 0;
+        for (int k = 0; k < 6; ++k) { s1 += crf[6 * a + k] * oY[i][6 * k + b]; s2 += oY[i][6 * a + k] * crm[6 * k + b]; }
+        Bm[i][6 * a + b] = s1 - s2;
+      }
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        Bm[i][6 * a + 3 + b] -= Shf[3 * a + b];
+        Bm[i][6 * (3 + a) + b] -= Shf[3 * a + b];
+        Bm[i][6 * (3 + a) + 3 + b] -= Shn[3 * a + b];
+      }
+  }
+  // backward accumulation: composite inertia, composite B, subtree force
+  for (int i = m.nj - 1; i > 0; --i) {
+    const int p = r.parent[i];
+    for (int k = 0; k < 36; ++k) { oY[p][k] += oY[i][k]; Bm[p][k] += Bm[i][k]; }
+    for (int k = 0; k < 6; ++k) F[p][k] += F[i][k];
+  }
+  // YJ_c = Ycrb_j J_c ; BtJ_c = Bcrb_j^T J_c
+  double YJ[MAXV][6], BtJ[MAXV][6], Jc[MAXV][6];
+  for (int c = 0; c < nv; ++c) {
+    const int j = m.joint_of_col[c];
+    for (int a = 0; a < 6; ++a) Jc[c][a] = w.J[a][c];
+    mat6_vec(oY[j], Jc[c], YJ[c]);
+    mat6T_vec(Bm[j], Jc[c], BtJ[c]);
+  }
+  // joint-space inertia
+  double M[MAXV * MAXV];
+  for (int cj = 0; cj < nv; ++cj)
+    for (int ck = 0; ck < nv; ++ck) {
+      const int j = m.joint_of_col[cj], k = m.joint_of_col[ck];
+      double val = 0;
+      if (m.anc[j][k]) val = dot6(Jc[cj], YJ[ck]);
+      else if (m.anc[k][j]) val = dot6(Jc[ck], YJ[cj]);
+      M[cj * nv + ck] = val;
+    }
+  // RNEA partial derivatives
+  double dq[MAXV * MAXV], dv[MAXV * MAXV];
+  const double zero6[6] = {0, 0, 0, 0, 0, 0};
+  for (int ck = 0; ck < nv; ++ck) {
+    const int k = m.joint_of_col[ck], pk = r.parent[k];
+    const double* s = Jc[ck];
+    const double* vp = pk >= 0 ? w.ov[pk] : zero6;
+    const double* ap = pk >= 0 ? w.oa[pk] : m.a0;
+    double dVdq[6], dAdq[6], dAdv[6], t6[6], vsum[6];
+    cross_mm(vp, s, dVdq);
+    cross_mm(ap, s, dAdq); cross_mm(vp, dVdq, t6);
+    for (int a = 0; a < 6; ++a) { dAdq[a] += t6[a]; vsum[a] = vp[a] + w.ov[k][a]; }
+    cross_mm(vsum, s, dAdv);
+    double P[6], Fq[6], Fv[6], t1[6], t2[6];
+    mat6_vec(oY[k], dAdq, t1); mat6_vec(Bm[k], dVdq, t2);
+    for (int a = 0; a < 6; ++a) P[a] = t1[a] + t2[a];
+    cross_mf(s, F[k], t1);
+    for (int a = 0; a < 6; ++a) Fq[a] = P[a] + t1[a];
+    mat6_vec(oY[k], dAdv, t1); mat6_vec(Bm[k], s, t2);
+    for (int a = 0; a < 6; ++a) Fv[a] = t1[a] + t2[a];
+    for (int cj = 0; cj < nv; ++cj) {
+      const int j = m.joint_of_col[cj];
+      double vq_ = 0, vv_ = 0;
+      if (j == k) { vq_ = dot6(Jc[cj], P); vv_ = dot6(Jc[cj], Fv); }
+      else if (m.anc[j][k]) { vq_ = dot6(Jc[cj], Fq); vv_ = dot6(Jc[cj], Fv); }
+      else if (m.anc[k][j]) {
+        vq_ = dot6(YJ[cj], dAdq) + dot6(BtJ[cj], dVdq);
+        vv_ = dot6(YJ[cj], dAdv) + dot6(BtJ[cj], s);
+      }
+      dq[cj * nv + ck] = vq_; dv[cj * nv + ck] = vv_;
+    }
+  }
+  // Minv by Cholesky; ddq_dq = -Minv dtau_dq etc. (computeABADerivatives)
+  double L[MAXV * MAXV];
+  std::memcpy(L, M, sizeof(double) * nv * nv);
+  llt_inplace(L, nv);
+  for (int i = 0; i < nv; ++i)
+    for (int j = 0; j < nv; ++j) w.Minv[i * nv + j] = (i == j) ? 1.0 : 0.0;
+  llt_solve(L, nv, w.Minv, nv);
+  for (int i = 0; i < nv; ++i)
+    for (int j = 0; j < nv; ++j) {
+      double sq = 0, sv = 0;
+      for (int k = 0; k < nv; ++k) { sq += w.Minv[i * nv + k] * dq[k * nv + j]; sv += w.Minv[i * nv + k] * dv[k * nv + j]; }
+      a_q[i * nv + j] = -sq; a_v[i * nv + j] = -sv;
+    }
+}
+
+// local frame Jacobian (6 x nv) of frame f: fJ = Ad(oMf^-1) J restricted to supporting columns
+inline void frame_jacobian(const Model& m, const Work& w, int f, const SE3& oMf, double fJ[6][MAXV]) {
+  const int j = m.d->robot.frame_joint[f];
+  for (int c = 0; c < m.nv; ++c) {
+    if (m.anc[m.joint_of_col[c]][j]) {
+      double col[6] = {w.J[0][c], w.J[1][c], w.J[2][c], w.J[3][c], w.J[4][c], w.J[5][c]}, o[6];
+      actinv_motion(oMf, col, o);
+      for (int a = 0; a < 6; ++a) fJ[a][c] = o[a];
+    } else {
+      for (int a = 0; a < 6; ++a) fJ[a][c] = 0;
+    }
+  }
+}
+
+// IntegratedActionModelEuler::calcDiff.  `tile` receives Fx|Fu|Lxx|Lxu|Luu|Lx|Lu (Model::o* offsets).
+// Must follow node_calc on the same (x,u) — crocoddyl's convention.
+inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Work& w, std::vector<CostEval>& evals,
+                           double* tile) {
+  const empc_problem_desc_t& d = *m.d;
+  const int nv = m.nv, ndx = m.ndx, nu = m.nu, nr = m.nr;
+  const double dt = m.dt, dt2 = dt * dt;
+  for (int i = 0; i < m.tile; ++i) tile[i] = 0;
+  double* Fx = tile + m.oFx; double* Fu = tile + m.oFu; double* Lxx = tile + m.oLxx;
+  double* Luu = tile + m.oLuu; double* Lx = tile + m.oLx; double* Lu = tile + m.oLu;
+  // squashing derivative
+  for (int i = 0; i < nu; ++i) {
+    if (d.use_squash) {
+      const double dd = (d.u_ub[i] - d.u_lb[i]) * ctx.smooth, a = dd * dd;
+      const double l = w.u[i] - d.u_lb[i], h = w.u[i] - d.u_ub[i];
+      w.ds[i] = 0.5 * ((1.0 / std::sqrt(a + l * l)) * l - (1.0 / std::sqrt(a + h * h)) * h);
+    } else {
+      w.ds[i] = 1.0;
+    }
+  }
+  double a_q[MAXV * MAXV], a_v[MAXV * MAXV], a_u[MAXV * MAXU];
+  aba_derivatives(m, w, a_q, a_v);
+  // Fu_cont = Minv * (A diag(ds)),  A = [tau_f 0; 0 I]
+  for (int i = 0; i < nv; ++i)
+    for (int j = 0; j < nu; ++j) {
+      double s = 0;
+      if (j < nr) { for (int k = 0; k < 6; ++k) s += w.Minv[i * nv + k] * (d.tau_f[k * nr + j] * w.ds[j]); }
+      else s = w.Minv[i * nv + 6 + (j - nr)] * w.ds[j];
+      a_u[i * nu + j] = s;
+    }
+  // Euler: discrete Jacobians before the Lie-group transport
+  for (int i = 0; i < nv; ++i) {
+    for (int j = 0; j < nv; ++j) {
+      Fx[i * ndx + j] = a_q[i * nv + j] * dt2;
+      Fx[i * ndx + nv + j] = a_v[i * nv + j] * dt2;
+      Fx[(nv + i) * ndx + j] = a_q[i * nv + j] * dt;
+      Fx[(nv + i) * ndx + nv + j] = a_v[i * nv + j] * dt;
+    }
+    Fx[i * ndx + nv + i] += dt;
+    for (int j = 0; j < nu; ++j) { Fu[i * nu + j] = dt2 * a_u[i * nu + j]; Fu[(nv + i) * nu + j] = dt * a_u[i * nu + j]; }
+  }
+  // JintegrateTransport(x,dx,.,second): rows 0..5 <- Jexp6(dx[0:6]) * rows 0..5
+  double Je[36]; Jexp6(w.dx, Je);
+  {
+    double tmp[6][MAXDX];
+    for (int a = 0; a < 6; ++a)
+      for (int c = 0; c < ndx; ++c) {
+        double s = 0;
+        for (int k = 0; k < 6; ++k) s += Je[6 * a + k] * Fx[k * ndx + c];
+        tmp[a][c] = s;
+      }
+    for (int a = 0; a < 6; ++a) for (int c = 0; c < ndx; ++c) Fx[a * ndx + c] = tmp[a][c];
+    for (int a = 0; a < 6; ++a)
+      for (int c = 0; c < nu; ++c) {
+        double s = 0;
+        for (int k = 0; k < 6; ++k) s += Je[6 * a + k] * Fu[k * nu + c];
+        tmp[a][c] = s;
+      }
+    for (int a = 0; a < 6; ++a) for (int c = 0; c < nu; ++c) Fu[a * nu + c] = tmp[a][c];
+  }
+  // Jintegrate(x,dx,first,addto): += blockdiag(Ad(exp6(dx)^-1), I)
+  {
+    SE3 E; exp6(w.dx, E);
+    double Xs[36]; force_action_matrix(E, Xs);  // Ad(E^-1) = (X*)^T
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) Fx[a * ndx + b] += Xs[6 * b + a];
+    for (int i = 6; i < ndx; ++i) Fx[i * ndx + i] += 1.0;
+  }
+  // ---- cost derivatives (CostModelSum::calcDiff, Gauss-Newton) ----
+  const int c0 = d.costset_begin[costset], c1 = d.costset_begin[costset + 1];
+  for (int c = c0; c < c1; ++c) {
+    const empc_cost_t& cs = d.costs[c];
+    if (!cs.active) continue;
+    const CostEval& e = evals[c - c0];
+    const double wt = cs.weight;
+    switch (cs.type) {
+      case EMPC_COST_STATE: {
+        // Rx = Jdiff(xref, x, second) = blockdiag(Jlog6(Mref^-1 M), I)
+        SE3 Mref, Mx, D; q_to_se3(d.pool + cs.ref_off, Mref); q_to_se3(w.x, Mx); se3_inv_mul(Mref, Mx, D);
+        double Jl[36]; Jlog6(D, Jl);
+        for (int i = 0; i < 6; ++i) {
+          double s = 0;
+          for (int k = 0; k < 6; ++k) s += Jl[6 * k + i] * e.Ar[k];
+          Lx[i] += wt * s;
+          for (int j = 0; j < 6; ++j) {
+            double h = 0;
+            for (int k = 0; k < 6; ++k) h += Jl[6 * k + i] * (e.Arr[k] * Jl[6 * k + j]);
+            Lxx[i * ndx + j] += wt * h;
+          }
+        }
+        for (int i = 6; i < ndx; ++i) { Lx[i] += wt * e.Ar[i]; Lxx[i * ndx + i] += wt * e.Arr[i]; }
+      } break;
+      case EMPC_COST_CONTROL:
+      case EMPC_COST_SQUASH_BARRIER:
+        for (int i = 0; i < nu; ++i) { Lu[i] += wt * e.Ar[i]; Luu[i * nu + i] += wt * e.Arr[i]; }
+        break;
+      default: {
+        // frame costs: Rx = [Rq (nr x nv), Rv (nr x nv)]
+        const int f = cs.frame, n = residual_dim(m, cs.type);
+        SE3 oMf; frame_placement(m, w, f, oMf);
+        double fJ[6][MAXV]; frame_jacobian(m, w, f, oMf, fJ);
+        double Rx[6][MAXDX];
+        for (int a = 0; a < 6; ++a) for (int b = 0; b < ndx; ++b) Rx[a][b] = 0;
+        int ncols = nv;
+        if (cs.type == EMPC_COST_FRAME_PLACEMENT) {
+          double Jl[36]; Jlog6(e.rMf, Jl);
+          for (int a = 0; a < 6; ++a)
+            for (int b = 0; b < nv; ++b) {
+              double s = 0;
+              for (int k = 0; k < 6; ++k) s += Jl[6 * a + k] * fJ[k][b];
+              Rx[a][b] = s;
+            }
+        } else if (cs.type == EMPC_COST_FRAME_ROTATION) {
+          double wv[3], th, Jl[9]; log3(e.rMf.R, wv, th); Jlog3(th, wv, Jl);
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < nv; ++b) Rx[a][b] = Jl[3 * a] * fJ[3][b] + Jl[3 * a + 1] * fJ[4][b] + Jl[3 * a + 2] * fJ[5][b];
+        } else if (cs.type == EMPC_COST_FRAME_TRANSLATION) {
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < nv; ++b)
+              Rx[a][b] = oMf.R[3 * a] * fJ[0][b] + oMf.R[3 * a + 1] * fJ[1][b] + oMf.R[3 * a + 2] * fJ[2][b];
+        } else {  // FRAME_VELOCITY, LOCAL: dv_f/dq_c = oMf.actInv(ov_parent(c) x J_c), dv_f/dv = fJ
+          const int jf = d.robot.frame_joint[f];
+          for (int b = 0; b < nv; ++b) {
+            const int k = m.joint_of_col[b], pk = d.robot.parent[k];
+            if (m.anc[k][jf] && pk >= 0) {
+              double col[6] = {w.J[0][b], w.J[1][b], w.J[2][b], w.J[3][b], w.J[4][b], w.J[5][b]}, cr[6], o[6];
+              cross_mm(w.ov[pk], col, cr); actinv_motion(oMf, cr, o);
+              for (int a = 0; a < 6; ++a) Rx[a][b] = o[a];
+            }
+            for (int a = 0; a < 6; ++a) Rx[a][nv + b] = fJ[a][b];
+          }
+          ncols = ndx;
+        }
+        for (int i = 0; i < ncols; ++i) {
+          double s = 0;
+          for (int k = 0; k < n; ++k) s += Rx[k][i] * e.Ar[k];
+          Lx[i] += wt * s;
+          for (int j = 0; j < ncols; ++j) {
+            double h = 0;
+            for (int k = 0; k < n; ++k) h += Rx[k][i] * (e.Arr[k] * Rx[k][j]);
+            Lxx[i * ndx + j] += wt * h;
+          }
+        }
+      } break;
+    }
+  }
+  // Euler scales the cost derivatives by dt (Lxu stays zero: no cost couples x and u)
+  for (int i = 0; i < ndx * ndx; ++i) Lxx[i] *= dt;
+  for (int i = 0; i < nu * nu; ++i) Luu[i] *= dt;
+  for (int i = 0; i < ndx; ++i) Lx[i] *= dt;
+  for (int i = 0; i < nu; ++i) Lu[i] *= dt;
+}
+
+}  // namespace orc

@@ -1,0 +1,172 @@
+"""ctypes binding of oracle/liboracle.so — the CPU checker.  Test infrastructure only."""
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+abi = importlib.import_module("eagle-mpc_b200.abi")
+dp = abi.as_double_p
+
+
+def _load():
+    path = os.path.join(ROOT, "oracle", "liboracle.so")
+    src = [os.path.join(ROOT, "oracle", f) for f in ("oracle.cpp", "oracle_model.hpp", "oracle_math.hpp")]
+    if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in src):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    lib = C.CDLL(path)
+    lib.orc_create.restype = C.c_void_p
+    lib.orc_create.argtypes = [C.POINTER(abi.ProblemDesc)]
+    lib.orc_destroy.argtypes = [C.c_void_p]
+    lib.orc_get.argtypes = [C.c_void_p, C.c_char_p, abi.c_double_p]
+    lib.orc_phase_calc_diff.argtypes = [C.c_void_p, C.c_double]
+    lib.orc_phase_backward.argtypes = [C.c_void_p, C.c_double, C.c_int]
+    lib.orc_phase_rollout.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
+    lib.orc_node_eval.argtypes = [C.c_void_p, C.c_int, C.c_double] + [abi.c_double_p] * 6
+    return lib
+
+
+lib = _load()
+
+
+def default_params():
+    p = abi.SolverParams()
+    lib.orc_default_params(C.byref(p))
+    return p
+
+
+class Oracle:
+    def __init__(self, holder):
+        self.h = holder
+        self.p = C.c_void_p(lib.orc_create(C.byref(holder.desc)))
+        d = (C.c_int32 * 7)()
+        lib.orc_dims(self.p, d)
+        self.nq, self.nv, self.nx, self.ndx, self.nu, self.T, self.tile = list(d)
+
+    def __del__(self):
+        if getattr(self, "p", None):
+            lib.orc_destroy(self.p)
+            self.p = None
+
+    def set_params(self, p):
+        lib.orc_set_params(self.p, C.byref(p))
+
+    def set_x0(self, x0):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        lib.orc_set_x0(self.p, dp(x0))
+
+    def set_candidate(self, xs=None, us=None, feasible=False):
+        xs = None if xs is None else np.ascontiguousarray(xs, dtype=np.float64)
+        us = None if us is None else np.ascontiguousarray(us, dtype=np.float64)
+        lib.orc_set_candidate(self.p, None if xs is None else dp(xs), None if us is None else dp(us), int(feasible))
+
+    def solve(self, xs=None, us=None, feasible=False):
+        xs = None if xs is None else np.ascontiguousarray(xs, dtype=np.float64)
+        us = None if us is None else np.ascontiguousarray(us, dtype=np.float64)
+        lib.orc_solve(self.p, None if xs is None else dp(xs), None if us is None else dp(us), int(feasible))
+
+    def get(self, name):
+        T, nx, ndx, nu = self.T, self.nx, self.ndx, self.nu
+        shapes = {
+            "xs": (T + 1, nx), "us": (T, nu), "xs_try": (T + 1, nx), "us_try": (T, nu), "us_squash": (T, nu),
+            "K": (T, nu, ndx), "k": (T, nu), "Vx": (T + 1, ndx), "Vxx": (T + 1, ndx, ndx), "fs": (T + 1, ndx),
+            "tiles": (T + 1, self.tile), "xnext": (T + 1, nx), "node_cost": (T + 1,), "cost": (1,),
+            "cost_try": (1,), "stop": (1,), "xreg": (1,), "dgdq": (2,), "dv": (1,), "iter": (1,), "feasible": (1,),
+        }
+        out = np.zeros(shapes[name])
+        rc = lib.orc_get(self.p, name.encode(), dp(out))
+        assert rc == 0, name
+        return out if out.size > 1 else out.reshape(-1)[0]
+
+    def phase_calc_diff(self, smooth):
+        lib.orc_phase_calc_diff(self.p, smooth)
+
+    def phase_backward(self, xreg, feasible):
+        return lib.orc_phase_backward(self.p, xreg, int(feasible))
+
+    def phase_rollout(self, smooth, feasible, ddp, alpha_index):
+        return lib.orc_phase_rollout(self.p, smooth, int(feasible), int(ddp), alpha_index)
+
+    def node_eval(self, costset, smooth, x, u, diff=True):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+        xnext = np.zeros(self.nx)
+        cost = np.zeros(1)
+        s = np.zeros(self.nu)
+        tile = np.zeros(self.tile) if diff else None
+        lib.orc_node_eval(self.p, costset, smooth, dp(x), None if u is None else dp(u), dp(xnext), dp(cost), dp(s),
+                          None if tile is None else dp(tile))
+        return xnext, cost[0], s, tile
+
+    def integrate(self, x, dx):
+        x = np.ascontiguousarray(x, dtype=np.float64); dx = np.ascontiguousarray(dx, dtype=np.float64)
+        out = np.zeros(self.nx)
+        lib.orc_state_integrate(self.p, dp(x), dp(dx), dp(out))
+        return out
+
+    def diff(self, x0, x1):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64); x1 = np.ascontiguousarray(x1, dtype=np.float64)
+        out = np.zeros(self.ndx)
+        lib.orc_state_diff(self.p, dp(x0), dp(x1), dp(out))
+        return out
+
+    def aba(self, q, v, tau):
+        q, v, tau = (np.ascontiguousarray(a, dtype=np.float64) for a in (q, v, tau))
+        a = np.zeros(self.nv)
+        lib.orc_aba(self.p, dp(q), dp(v), dp(tau), dp(a))
+        return a
+
+    def rnea(self, q, v, a):
+        q, v, a = (np.ascontiguousarray(z, dtype=np.float64) for z in (q, v, a))
+        tau = np.zeros(self.nv)
+        lib.orc_rnea(self.p, dp(q), dp(v), dp(a), dp(tau))
+        return tau
+
+    def aba_derivatives(self, q, v, tau):
+        q, v, tau = (np.ascontiguousarray(z, dtype=np.float64) for z in (q, v, tau))
+        nv = self.nv
+        a = np.zeros(nv); aq = np.zeros((nv, nv)); av = np.zeros((nv, nv)); Minv = np.zeros((nv, nv))
+        lib.orc_aba_derivatives(self.p, dp(q), dp(v), dp(tau), dp(a), dp(aq), dp(av), dp(Minv))
+        return a, aq, av, Minv
+
+
+def exp6(nu):
+    nu = np.ascontiguousarray(nu, dtype=np.float64); R = np.zeros((3, 3)); p = np.zeros(3)
+    lib.orc_exp6(dp(nu), dp(R), dp(p)); return R, p
+
+
+def log6(R, p):
+    R = np.ascontiguousarray(R, dtype=np.float64); p = np.ascontiguousarray(p, dtype=np.float64); nu = np.zeros(6)
+    lib.orc_log6(dp(R), dp(p), dp(nu)); return nu
+
+
+def Jlog6(R, p):
+    R = np.ascontiguousarray(R, dtype=np.float64); p = np.ascontiguousarray(p, dtype=np.float64); J = np.zeros((6, 6))
+    lib.orc_Jlog6(dp(R), dp(p), dp(J)); return J
+
+
+def Jexp6(nu):
+    nu = np.ascontiguousarray(nu, dtype=np.float64); J = np.zeros((6, 6))
+    lib.orc_Jexp6(dp(nu), dp(J)); return J
+
+
+def exp3(w):
+    w = np.ascontiguousarray(w, dtype=np.float64); R = np.zeros((3, 3)); lib.orc_exp3(dp(w), dp(R)); return R
+
+
+def log3(R):
+    R = np.ascontiguousarray(R, dtype=np.float64); w = np.zeros(3); lib.orc_log3(dp(R), dp(w)); return w
+
+
+def Jlog3(R):
+    R = np.ascontiguousarray(R, dtype=np.float64); J = np.zeros((3, 3)); lib.orc_Jlog3(dp(R), dp(J)); return J
+
+
+def quat_to_R(q):
+    q = np.ascontiguousarray(q, dtype=np.float64); R = np.zeros((3, 3)); lib.orc_quat_to_R(dp(q), dp(R)); return R
+
+
+def R_to_quat(R):
+    R = np.ascontiguousarray(R, dtype=np.float64); q = np.zeros(4); lib.orc_R_to_quat(dp(R), dp(q)); return q
