@@ -1,0 +1,758 @@
+// node.cuh — per-node action model on the device (one thread evaluates one shooting node), FP64, sm_100a.
+//
+// Replaces, for the model chain eagle-mpc instantiates (src/factory/diff-action.cpp:31-35, src/factory/int-action.cpp:26,
+// src/trajectory.cpp:47-52), the per-node work crocoddyl does inside ShootingProblem::calc / calcDiff:
+//   IntegratedActionModelEuler::calc/calcDiff  ->  DifferentialActionModelFreeFwdDynamics::calc/calcDiff
+//   -> ActuationSquashingModel (SquashingModelSmoothSat + ActuationModelMultiCopterBase), pinocchio::aba,
+//      pinocchio::computeABADerivatives, CostModelSum over CostModelResidual{State,Control,Frame*} with
+//      Activation{Quad,WeightedQuad,QuadraticBarrier,WeightedQuadraticBarrier}   
+// Invoked from the reference at src/sbfddp.cpp:244,332 (computeDirection -> calcDiff) and :264,:437 (rollout calc).
+//
+// The robot is a free-flyer base + a serial chain of NA revolute joints (all eagle-mpc platforms); template
+// parameters make every loop bound a compile-time constant.
+#pragma once
+#include "../../include/empc_b200.h"
+#include "spatial.cuh"
+
+namespace empc {
+
+struct DevModel {
+  int nj, na, nq, nv, nx, ndx, nu, nr, T, tile, use_squash, n_frames;
+  int oFx, oFu, oLxx, oLxu, oLuu, oLx, oLu, pad_;
+  double dt;
+  double jR[EMPC_MAX_JOINTS][9], jp[EMPC_MAX_JOINTS][3], axis[EMPC_MAX_JOINTS][3];
+  double Y[EMPC_MAX_JOINTS][36];  // body spatial inertia in the joint frame
+  double a0[6];                   // -gravity (spatial)
+  int frame_joint[EMPC_MAX_FRAMES];
+  double fR[EMPC_MAX_FRAMES][9], fp[EMPC_MAX_FRAMES][3];
+  double tau_f[6 * EMPC_MAX_ROTORS], u_lb[EMPC_MAX_NU], u_ub[EMPC_MAX_NU];
+  double bar_lb[EMPC_MAX_NU], bar_ub[EMPC_MAX_NU];  // crocoddyl::ActivationBounds(u_lb,u_ub,beta=1)
+  double barrier_weight;
+};
+
+struct CostTables {
+  const empc_cost_t* costs;
+  const double* pool;
+  const int* costset_begin;
+};
+
+template <int NA_, int NR_>
+struct Dim {
+  static constexpr int NA = NA_, NR = NR_, NJ = NA + 1, NV = 6 + NA, NQ = 7 + NA, NX = NQ + NV, NDX = 2 * NV,
+                       NU = NR + NA;
+  static constexpr int oFx = 0, oFu = oFx + NDX * NDX, oLxx = oFu + NDX * NU, oLxu = oLxx + NDX * NDX,
+                       oLuu = oLxu + NDX * NU, oLx = oLuu + NU * NU, oLu = oLx + NDX, TILE0 = oLu + NU,
+                       TILE = TILE0 + (TILE0 & 1);
+};
+
+// kinematic / dynamic quantities left by calc and reused by calcDiff (crocoddyl's "data")
+template <class D>
+struct NodeData {
+  SE3 oM[D::NJ];
+  SE3 li[D::NJ];
+  double v[D::NJ][6];
+  double agf[D::NJ][6];
+  double a[D::NV];
+  double dx[D::NDX];
+  double s[D::NU];
+};
+
+// ---- StateMultibody ------------------------------------------------------------------------------------------------
+EMPC_DI void q_to_se3(const double* q, SE3& M) {
+  quat_to_R(q + 3, M.R);
+  M.p[0] = q[0]; M.p[1] = q[1]; M.p[2] = q[2];
+}
+template <class D>
+EMPC_DI void state_integrate(const double* x, const double* dx, double* out) {
+  SE3 M0, E, M1;
+  q_to_se3(x, M0);
+  exp6(dx, E);
+  se3_mul(M0, E, M1);
+  double quat[4];
+  R_to_quat(M1.R, quat);
+  const double dotp = quat[0] * x[3] + quat[1] * x[4] + quat[2] * x[5] + quat[3] * x[6];
+  if (dotp < 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) quat[i] = -quat[i];
+  }
+  const double n2 = quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3];
+  const double alpha = (3 - n2) / 2;
+  double o[D::NX];
+  o[0] = M1.p[0]; o[1] = M1.p[1]; o[2] = M1.p[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[3 + i] = quat[i] * alpha;
+#pragma unroll
+  for (int i = 0; i < D::NA; ++i) o[7 + i] = x[7 + i] + dx[6 + i];
+#pragma unroll
+  for (int i = 0; i < D::NV; ++i) o[D::NQ + i] = x[D::NQ + i] + dx[D::NV + i];
+#pragma unroll
+  for (int i = 0; i < D::NX; ++i) out[i] = o[i];
+}
+template <class D>
+EMPC_DI void state_diff(const double* x0, const double* x1, double* dx) {
+  SE3 M0, M1, Dm;
+  q_to_se3(x0, M0); q_to_se3(x1, M1);
+  se3_inv_mul(M0, M1, Dm);
+  log6(Dm, dx);
+#pragma unroll
+  for (int i = 0; i < D::NA; ++i) dx[6 + i] = x1[7 + i] - x0[7 + i];
+#pragma unroll
+  for (int i = 0; i < D::NV; ++i) dx[D::NV + i] = x1[D::NQ + i] - x0[D::NQ + i];
+}
+
+// ---- activations ----------------------------------------------------------------------------------------------------
+template <int N>
+EMPC_DI double activation(int type, const double* r, const double* w, const double* lb, const double* ub, double* Ar,
+                          double* Arr) {
+  double val = 0;
+  if (type == EMPC_ACT_QUAD) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { val += r[i] * r[i]; Ar[i] = r[i]; Arr[i] = 1; }
+    return 0.5 * val;
+  } else if (type == EMPC_ACT_WEIGHTED_QUAD) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const double wr = w[i] * r[i]; val += r[i] * wr; Ar[i] = wr; Arr[i] = w[i]; }
+    return 0.5 * val;
+  } else if (type == EMPC_ACT_QUAD_BARRIER) {
+    double sl = 0, su = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double dl = r[i] - lb[i], du = r[i] - ub[i];
+      const double l = dl < 0 ? dl : 0.0, uu = du > 0 ? du : 0.0;
+      sl += l * l; su += uu * uu;
+      Ar[i] = l + uu;
+      Arr[i] = (dl <= 0) ? 1.0 : ((du >= 0) ? 1.0 : 0.0);
+    }
+    return 0.5 * sl + 0.5 * su;
+  } else {
+    double sl = 0, su = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double dl = r[i] - lb[i], du = r[i] - ub[i];
+      const double l = (dl < 0 ? dl : 0.0) * w[i], uu = (du > 0 ? du : 0.0) * w[i];
+      sl += l * l; su += uu * uu;
+      Ar[i] = (l + uu) * w[i];
+      Arr[i] = (dl <= 0) ? w[i] : ((du >= 0) ? w[i] : 0.0);
+    }
+    return 0.5 * sl + 0.5 * su;
+  }
+}
+
+template <class D>
+EMPC_DI void frame_placement(const DevModel& M, const NodeData<D>& nd, int f, SE3& oMf) {
+  SE3 fM;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) fM.R[i] = M.fR[f][i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) fM.p[i] = M.fp[f][i];
+  const int j = M.frame_joint[f];
+  SE3 oMj = nd.oM[0];
+#pragma unroll
+  for (int i = 1; i < D::NJ; ++i)
+    if (i == j) oMj = nd.oM[i];
+  se3_mul(oMj, fM, oMf);
+}
+
+// residual + activation of one cost.  r/Ar/Arr sized NDX.  rMf receives the SE3 error of placement/rotation costs.
+template <class D>
+EMPC_DI double cost_eval(const DevModel& M, const CostTables& C, const empc_cost_t& c, double smooth, const double* x,
+                         const double* u, const NodeData<D>& nd, double* r, double* Ar, double* Arr, SE3& rMf) {
+  const double* ref = C.pool + c.ref_off;
+  const double* aw = C.pool + c.w_off;
+  const double* lb = C.pool + c.lb_off;
+  const double* ub = C.pool + c.ub_off;
+  switch (c.type) {
+    case EMPC_COST_STATE: {
+      double xr[D::NX];
+#pragma unroll
+      for (int i = 0; i < D::NX; ++i) xr[i] = ref[i];
+      state_diff<D>(xr, x, r);
+      return activation<D::NDX>(c.activation, r, aw, lb, ub, Ar, Arr);
+    }
+    case EMPC_COST_CONTROL: {
+#pragma unroll
+      for (int i = 0; i < D::NU; ++i) r[i] = u[i] - ref[i];
+      return activation<D::NU>(c.activation, r, aw, lb, ub, Ar, Arr);
+    }
+    case EMPC_COST_SQUASH_BARRIER: {
+      double bw[D::NU];
+#pragma unroll
+      for (int i = 0; i < D::NU; ++i) {
+        const double aux = smooth * (M.u_ub[i] - M.u_lb[i]);
+        bw[i] = 1.0 / (aux * aux);
+        r[i] = u[i];
+      }
+      return activation<D::NU>(EMPC_ACT_WEIGHTED_QUAD_BARRIER, r, bw, M.bar_lb, M.bar_ub, Ar, Arr);
+    }
+    case EMPC_COST_FRAME_PLACEMENT: {
+      SE3 Mref, oMf;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Mref.R[i] = ref[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Mref.p[i] = ref[9 + i];
+      frame_placement<D>(M, nd, c.frame, oMf);
+      se3_inv_mul(Mref, oMf, rMf);
+      log6(rMf, r);
+      return activation<6>(c.activation, r, aw, lb, ub, Ar, Arr);
+    }
+    case EMPC_COST_FRAME_ROTATION: {
+      SE3 oMf; frame_placement<D>(M, nd, c.frame, oMf);
+      double Rr[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rr[i] = ref[i];
+      matTmul3(Rr, oMf.R, rMf.R);
+      double th; log3(rMf.R, r, th);
+      return activation<3>(c.activation, r, aw, lb, ub, Ar, Arr);
+    }
+    case EMPC_COST_FRAME_TRANSLATION: {
+      SE3 oMf; frame_placement<D>(M, nd, c.frame, oMf);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) r[i] = oMf.p[i] - ref[i];
+      return activation<3>(c.activation, r, aw, lb, ub, Ar, Arr);
+    }
+    default: {  // EMPC_COST_FRAME_VELOCITY (LOCAL)
+      const int f = c.frame, j = M.frame_joint[f];
+      SE3 fM;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) fM.R[i] = M.fR[f][i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) fM.p[i] = M.fp[f][i];
+      double vj[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) vj[k] = nd.v[0][k];
+#pragma unroll
+      for (int i = 1; i < D::NJ; ++i)
+        if (i == j) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) vj[k] = nd.v[i][k];
+        }
+      double vf[6]; actinv_motion(fM, vj, vf);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) r[i] = vf[i] - ref[i];
+      return activation<6>(c.activation, r, aw, lb, ub, Ar, Arr);
+    }
+  }
+}
+
+// SquashingModelSmoothSat::calc
+template <class D>
+EMPC_DI void squash(const DevModel& M, double smooth, const double* u, double* s) {
+#pragma unroll
+  for (int i = 0; i < D::NU; ++i) {
+    if (M.use_squash) {
+      const double lbv = M.u_lb[i], ubv = M.u_ub[i];
+      const double dd = (ubv - lbv) * smooth, a = dd * dd;
+      const double l = u[i] - lbv, h = u[i] - ubv;
+      s[i] = 0.5 * (sqrt(l * l + a) - sqrt(h * h + a) + lbv + ubv);
+    } else {
+      s[i] = u[i];
+    }
+  }
+}
+
+// pinocchio::aba for free-flyer + serial revolute chain (local-frame three-pass recursion)
+template <class D>
+EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData<D>& nd) {
+  constexpr int NJ = D::NJ, NV = D::NV;
+  double Ia[NJ][36], pA[NJ][6], uu[NV];
+  double U[NJ][6], Dinv[NJ], UDinv[NJ][6];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) uu[i] = tau[i];
+  const double* vq = x + D::NQ;
+  // pass 1
+  q_to_se3(x, nd.li[0]);
+  nd.oM[0] = nd.li[0];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { nd.v[0][k] = vq[k]; nd.agf[0][k] = 0; }
+#pragma unroll 1
+  for (int i = 1; i < NJ; ++i) {
+    const double th = x[6 + i];
+    double ax[3] = {M.axis[i][0] * th, M.axis[i][1] * th, M.axis[i][2] * th};
+    SE3 Mj; exp3(ax, Mj.R); Mj.p[0] = Mj.p[1] = Mj.p[2] = 0;
+    SE3 Jp;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Jp.R[k] = M.jR[i][k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Jp.p[k] = M.jp[i][k];
+    se3_mul(Jp, Mj, nd.li[i]);
+    se3_mul(nd.oM[i - 1], nd.li[i], nd.oM[i]);
+    double vJ[6] = {0, 0, 0, M.axis[i][0] * vq[5 + i], M.axis[i][1] * vq[5 + i], M.axis[i][2] * vq[5 + i]};
+    double vp[6]; actinv_motion(nd.li[i], nd.v[i - 1], vp);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) nd.v[i][k] = vJ[k] + vp[k];
+    cross_mm(nd.v[i], vJ, nd.agf[i]);
+  }
+#pragma unroll 1
+  for (int i = 0; i < NJ; ++i) {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) Ia[i][k] = M.Y[i][k];
+    double h[6]; mat6_vec(Ia[i], nd.v[i], h);
+    cross_mf(nd.v[i], h, pA[i]);
+  }
+  // pass 2
+#pragma unroll 1
+  for (int i = NJ - 1; i >= 1; --i) {
+    const double S[6] = {0, 0, 0, M.axis[i][0], M.axis[i][1], M.axis[i][2]};
+    const int c = 5 + i;
+    uu[c] -= dot6(S, pA[i]);
+    mat6_vec(Ia[i], S, U[i]);
+    Dinv[i] = 1.0 / dot6(S, U[i]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) UDinv[i][k] = U[i][k] * Dinv[i];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 6; ++b) Ia[i][6 * a + b] -= UDinv[i][a] * U[i][b];
+    double pa[6], Iac[6];
+    mat6_vec(Ia[i], nd.agf[i], Iac);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pa[k] = pA[i][k] + Iac[k] + UDinv[i][k] * uu[c];
+    double X[36], Ip[36], fp[6];
+    force_action_matrix(nd.li[i], X);
+    congruence6(X, Ia[i], Ip);
+#pragma unroll
+    for (int k = 0; k < 36; ++k) Ia[i - 1][k] += Ip[k];
+    act_force(nd.li[i], pa, fp);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pA[i - 1][k] += fp[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) uu[k] -= pA[0][k];
+  llt_inplace<6>(Ia[0]);
+  // pass 3
+  {
+    double g[6]; actinv_motion(nd.oM[0], M.a0, g);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) nd.agf[0][k] += g[k];
+    double rhs[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rhs[k] = uu[k];
+    llt_solve_vec<6>(Ia[0], rhs, 1);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { nd.a[k] = rhs[k] - nd.agf[0][k]; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) nd.agf[0][k] += nd.a[k];
+  }
+#pragma unroll 1
+  for (int i = 1; i < NJ; ++i) {
+    double ap[6]; actinv_motion(nd.li[i], nd.agf[i - 1], ap);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) nd.agf[i][k] += ap[k];
+    const int c = 5 + i;
+    nd.a[c] = Dinv[i] * uu[c] - dot6(UDinv[i], nd.agf[i]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nd.agf[i][3 + k] += M.axis[i][k] * nd.a[c];
+  }
+}
+
+// IntegratedActionModelEuler::calc.  u == nullptr => terminal convention u = 0.
+template <class D>
+EMPC_DI void node_calc(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x,
+                       const double* u, NodeData<D>& nd, double* xnext, double& cost) {
+  squash<D>(M, smooth, u, nd.s);
+  double tau[D::NV];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double t = 0;
+#pragma unroll
+    for (int j = 0; j < D::NR; ++j) t += M.tau_f[i * D::NR + j] * nd.s[j];
+    tau[i] = t;
+  }
+#pragma unroll
+  for (int i = 0; i < D::NA; ++i) tau[6 + i] = nd.s[D::NR + i];
+  aba<D>(M, x, tau, nd);
+  const double dt = M.dt, dt2 = dt * dt;
+#pragma unroll
+  for (int i = 0; i < D::NV; ++i) {
+    nd.dx[i] = x[D::NQ + i] * dt + nd.a[i] * dt2;
+    nd.dx[D::NV + i] = nd.a[i] * dt;
+  }
+  state_integrate<D>(x, nd.dx, xnext);
+  double csum = 0;
+  const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
+  for (int c = c0; c < c1; ++c) {
+    const empc_cost_t cs = C.costs[c];
+    if (!cs.active) continue;
+    double r[D::NDX], Ar[D::NDX], Arr[D::NDX];
+    SE3 rMf;
+    csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
+  }
+  cost = dt * csum;
+}
+
+// world-frame RNEA-derivative recursion + Minv (DESIGN.md "ABA derivatives"); outputs a_q, a_v (NV x NV), Minv, Jc.
+template <class D>
+EMPC_DI void aba_derivatives(const DevModel& M, const NodeData<D>& nd, double (*Jc)[6], double (*ov)[6], double* a_q,
+                             double* a_v, double* Minv) {
+  constexpr int NJ = D::NJ, NV = D::NV;
+  double oY[NJ][36], Bm[NJ][36], F[NJ][6], oa[NJ][6];
+#pragma unroll 1
+  for (int i = 0; i < NJ; ++i) {
+    if (i == 0) {
+      // motion action matrix columns of oM0: X = [[R, px R],[0,R]]
+      double S[9], SR[9]; skew3(nd.oM[0].p, S); matmul3(S, nd.oM[0].R, SR);
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          Jc[b][a] = nd.oM[0].R[3 * a + b]; Jc[b][3 + a] = 0;
+          Jc[3 + b][a] = SR[3 * a + b]; Jc[3 + b][3 + a] = nd.oM[0].R[3 * a + b];
+        }
+      }
+    } else {
+      const double S[6] = {0, 0, 0, M.axis[i][0], M.axis[i][1], M.axis[i][2]};
+      act_motion(nd.oM[i], S, Jc[5 + i]);
+    }
+    act_motion(nd.oM[i], nd.v[i], ov[i]);
+    act_motion(nd.oM[i], nd.agf[i], oa[i]);
+    double X[36]; force_action_matrix(nd.oM[i], X);
+    double Yl[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) Yl[k] = M.Y[i][k];
+    congruence6(X, Yl, oY[i]);
+    double h[6], Ya[6], vh[6];
+    mat6_vec(oY[i], ov[i], h); mat6_vec(oY[i], oa[i], Ya); cross_mf(ov[i], h, vh);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) F[i][k] = Ya[k] + vh[k];
+    // B_i = crf(v) Y - Y crm(v) + Hx(h)
+    double Sv[9], Sw[9]; skew3(ov[i], Sv); skew3(ov[i] + 3, Sw);
+    double Shf[9], Shn[9]; skew3(h, Shf); skew3(h + 3, Shn);
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        // crf = [[Sw,0],[Sv,Sw]], crm = [[Sw,Sv],[0,Sw]]
+        double s1 = 0, s2 = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double crf_ak, crm_kb;
+          if (a < 3) crf_ak = (k < 3) ? Sw[3 * a + k] : 0.0;
+          else crf_ak = (k < 3) ? Sv[3 * (a - 3) + k] : Sw[3 * (a - 3) + (k - 3)];
+          if (k < 3) crm_kb = (b < 3) ? Sw[3 * k + b] : Sv[3 * k + (b - 3)];
+          else crm_kb = (b < 3) ? 0.0 : Sw[3 * (k - 3) + (b - 3)];
+          s1 += crf_ak * oY[i][6 * k + b];
+          s2 += oY[i][6 * a + k] * crm_kb;
+        }
+        double hx = 0;
+        if (a < 3 && b >= 3) hx = Shf[3 * a + (b - 3)];
+        else if (a >= 3 && b < 3) hx = Shf[3 * (a - 3) + b];
+        else if (a >= 3 && b >= 3) hx = Shn[3 * (a - 3) + (b - 3)];
+        Bm[i][6 * a + b] = s1 - s2 - hx;
+      }
+  }
+#pragma unroll 1
+  for (int i = NJ - 1; i > 0; --i) {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) { oY[i - 1][k] += oY[i][k]; Bm[i - 1][k] += Bm[i][k]; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) F[i - 1][k] += F[i][k];
+  }
+  double YJ[NV][6], BtJ[NV][6];
+#pragma unroll 1
+  for (int c = 0; c < NV; ++c) {
+    const int j = (c < 6) ? 0 : c - 5;
+    mat6_vec(oY[j], Jc[c], YJ[c]);
+    mat6T_vec(Bm[j], Jc[c], BtJ[c]);
+  }
+  double Mm[NV * NV];
+#pragma unroll 1
+  for (int cj = 0; cj < NV; ++cj)
+#pragma unroll 1
+    for (int ck = cj; ck < NV; ++ck) {
+      const double val = dot6(Jc[cj], YJ[ck]);  // serial chain: joint(cj) <= joint(ck)
+      Mm[cj * NV + ck] = val; Mm[ck * NV + cj] = val;
+    }
+  double* dq = a_q; double* dv = a_v;
+#pragma unroll 1
+  for (int ck = 0; ck < NV; ++ck) {
+    const int k = (ck < 6) ? 0 : ck - 5;
+    const double* s = Jc[ck];
+    double vp[6], ap[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { vp[a] = (k > 0) ? ov[k > 0 ? k - 1 : 0][a] : 0.0; ap[a] = (k > 0) ? oa[k > 0 ? k - 1 : 0][a] : M.a0[a]; }
+    double dVdq[6], dAdq[6], dAdv[6], t6[6], vsum[6];
+    cross_mm(vp, s, dVdq);
+    cross_mm(ap, s, dAdq); cross_mm(vp, dVdq, t6);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { dAdq[a] += t6[a]; vsum[a] = vp[a] + ov[k][a]; }
+    cross_mm(vsum, s, dAdv);
+    double P[6], Fq[6], Fv[6], t1[6], t2[6];
+    mat6_vec(oY[k], dAdq, t1); mat6_vec(Bm[k], dVdq, t2);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) P[a] = t1[a] + t2[a];
+    cross_mf(s, F[k], t1);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) Fq[a] = P[a] + t1[a];
+    mat6_vec(oY[k], dAdv, t1); mat6_vec(Bm[k], s, t2);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) Fv[a] = t1[a] + t2[a];
+#pragma unroll 1
+    for (int cj = 0; cj < NV; ++cj) {
+      const int j = (cj < 6) ? 0 : cj - 5;
+      double vq_, vv_;
+      if (j == k) { vq_ = dot6(Jc[cj], P); vv_ = dot6(Jc[cj], Fv); }
+      else if (j < k) { vq_ = dot6(Jc[cj], Fq); vv_ = dot6(Jc[cj], Fv); }
+      else { vq_ = dot6(YJ[cj], dAdq) + dot6(BtJ[cj], dVdq); vv_ = dot6(YJ[cj], dAdv) + dot6(BtJ[cj], s); }
+      dq[cj * NV + ck] = vq_; dv[cj * NV + ck] = vv_;
+    }
+  }
+  llt_inplace<NV>(Mm);
+#pragma unroll 1
+  for (int i = 0; i < NV; ++i)
+#pragma unroll 1
+    for (int j = 0; j < NV; ++j) Minv[i * NV + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+  for (int c = 0; c < NV; ++c) llt_solve_vec<NV>(Mm, Minv + c, NV);
+  // a_q = -Minv dq, a_v = -Minv dv, column by column in place
+#pragma unroll 1
+  for (int j = 0; j < NV; ++j) {
+    double cq[NV], cv[NV];
+#pragma unroll 1
+    for (int i = 0; i < NV; ++i) {
+      double sq = 0, sv = 0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) { sq += Minv[i * NV + k] * dq[k * NV + j]; sv += Minv[i * NV + k] * dv[k * NV + j]; }
+      cq[i] = -sq; cv[i] = -sv;
+    }
+#pragma unroll 1
+    for (int i = 0; i < NV; ++i) { a_q[i * NV + j] = cq[i]; a_v[i * NV + j] = cv[i]; }
+  }
+}
+
+// IntegratedActionModelEuler::calcDiff: writes the node tile Fx|Fu|Lxx|Lxu|Luu|Lx|Lu to `tile` (global memory).
+// Must follow node_calc on the same (x,u,nd).
+template <class D>
+EMPC_DI void node_calc_diff(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x,
+                            const double* u, const NodeData<D>& nd, double* __restrict__ tile) {
+  constexpr int NV = D::NV, NDX = D::NDX, NU = D::NU, NR = D::NR, NJ = D::NJ;
+  const double dt = M.dt, dt2 = dt * dt;
+  double ds[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    if (M.use_squash) {
+      const double lbv = M.u_lb[i], ubv = M.u_ub[i];
+      const double dd = (ubv - lbv) * smooth, a = dd * dd;
+      const double l = u[i] - lbv, h = u[i] - ubv;
+      ds[i] = 0.5 * ((1.0 / sqrt(a + l * l)) * l - (1.0 / sqrt(a + h * h)) * h);
+    } else {
+      ds[i] = 1.0;
+    }
+  }
+  double Jc[NV][6], ov[NJ][6];
+  double a_q[NV * NV], a_v[NV * NV], Minv[NV * NV];
+  aba_derivatives<D>(M, nd, Jc, ov, a_q, a_v, Minv);
+
+  double* Fx = tile + D::oFx; double* Fu = tile + D::oFu;
+  // Lie-group transport pieces
+  double JeA[9], JeQ[9]; Jexp6_blocks(nd.dx, JeA, JeQ);
+  SE3 E; exp6(nd.dx, E);
+  double Xs[36]; force_action_matrix(E, Xs);  // Ad(E^-1) = (X*)^T
+  // rows 0..5 of Fx/Fu need the transport; build them in registers
+  {
+    double top[6][NDX];
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll 1
+      for (int j = 0; j < NV; ++j) { top[i][j] = a_q[i * NV + j] * dt2; top[i][NV + j] = a_v[i * NV + j] * dt2; }
+      top[i][NV + i] += dt;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll 1
+      for (int c = 0; c < NDX; ++c) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          // Je = [[A,Q],[0,A]]
+          double je;
+          if (a < 3) je = (k < 3) ? JeA[3 * a + k] : JeQ[3 * a + (k - 3)];
+          else je = (k < 3) ? 0.0 : JeA[3 * (a - 3) + (k - 3)];
+          s += je * top[k][c];
+        }
+        if (c < 6) s += Xs[6 * c + a];
+        Fx[a * NDX + c] = s;
+      }
+  }
+#pragma unroll 1
+  for (int i = 6; i < NV; ++i) {
+#pragma unroll 1
+    for (int j = 0; j < NV; ++j) {
+      Fx[i * NDX + j] = a_q[i * NV + j] * dt2 + ((i == j) ? 1.0 : 0.0);
+      Fx[i * NDX + NV + j] = a_v[i * NV + j] * dt2 + ((i == j) ? dt : 0.0);
+    }
+  }
+#pragma unroll 1
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll 1
+    for (int j = 0; j < NV; ++j) {
+      Fx[(NV + i) * NDX + j] = a_q[i * NV + j] * dt;
+      Fx[(NV + i) * NDX + NV + j] = a_v[i * NV + j] * dt + ((i == j) ? 1.0 : 0.0);
+    }
+  }
+  // Fu = [dt^2; dt] * Minv * A diag(ds), rows 0..5 transported
+  {
+    double top[6][NU];
+#pragma unroll 1
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll 1
+      for (int j = 0; j < NU; ++j) {
+        double s;
+        if (j < NR) {
+          s = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += Minv[i * NV + k] * (M.tau_f[k * NR + j] * ds[j]);
+        } else {
+          s = Minv[i * NV + 6 + (j - NR)] * ds[j];
+        }
+        if (i < 6) top[i][j] = dt2 * s; else Fu[i * NU + j] = dt2 * s;
+        Fu[(NV + i) * NU + j] = dt * s;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll 1
+      for (int c = 0; c < NU; ++c) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double je;
+          if (a < 3) je = (k < 3) ? JeA[3 * a + k] : JeQ[3 * a + (k - 3)];
+          else je = (k < 3) ? 0.0 : JeA[3 * (a - 3) + (k - 3)];
+          s += je * top[k][c];
+        }
+        Fu[a * NU + c] = s;
+      }
+  }
+  // ---- cost derivatives ----
+  double Lxx[NDX * NDX], Lx[NDX], Lu[NU], Luud[NU];
+#pragma unroll 1
+  for (int i = 0; i < NDX * NDX; ++i) Lxx[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NDX; ++i) Lx[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NU; ++i) { Lu[i] = 0; Luud[i] = 0; }
+  const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
+  for (int c = c0; c < c1; ++c) {
+    const empc_cost_t cs = C.costs[c];
+    if (!cs.active) continue;
+    double r[NDX], Ar[NDX], Arr[NDX];
+    SE3 rMf;
+    cost_eval<D>(M, C, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
+    const double wt = cs.weight;
+    if (cs.type == EMPC_COST_STATE) {
+      SE3 Mref, Mx, Dm;
+      double xr[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) xr[i] = C.pool[cs.ref_off + i];
+      q_to_se3(xr, Mref); q_to_se3(x, Mx); se3_inv_mul(Mref, Mx, Dm);
+      double Jl[36]; Jlog6(Dm, Jl);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += Jl[6 * k + i] * Ar[k];
+        Lx[i] += wt * s;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          double h = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) h += Jl[6 * k + i] * (Arr[k] * Jl[6 * k + j]);
+          Lxx[i * NDX + j] += wt * h;
+        }
+      }
+#pragma unroll 1
+      for (int i = 6; i < NDX; ++i) { Lx[i] += wt * Ar[i]; Lxx[i * NDX + i] += wt * Arr[i]; }
+    } else if (cs.type == EMPC_COST_CONTROL || cs.type == EMPC_COST_SQUASH_BARRIER) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) { Lu[i] += wt * Ar[i]; Luud[i] += wt * Arr[i]; }
+    } else {
+      const int f = cs.frame, jf = M.frame_joint[f];
+      SE3 oMf; frame_placement<D>(M, nd, f, oMf);
+      double fJ[6][NV];
+#pragma unroll 1
+      for (int cc = 0; cc < NV; ++cc) {
+        const int jc = (cc < 6) ? 0 : cc - 5;
+        double o[6];
+        actinv_motion(oMf, Jc[cc], o);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) fJ[a][cc] = (jc <= jf) ? o[a] : 0.0;
+      }
+      double Rx[6][NDX];
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll 1
+        for (int b = 0; b < NDX; ++b) Rx[a][b] = 0;
+      int n = 3;
+      bool full = false;
+      if (cs.type == EMPC_COST_FRAME_PLACEMENT) {
+        n = 6;
+        double Jl[36]; Jlog6(rMf, Jl);
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll 1
+          for (int b = 0; b < NV; ++b) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s += Jl[6 * a + k] * fJ[k][b];
+            Rx[a][b] = s;
+          }
+      } else if (cs.type == EMPC_COST_FRAME_ROTATION) {
+        double wv[3], th, Jl[9]; log3(rMf.R, wv, th); Jlog3(th, wv, Jl);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll 1
+          for (int b = 0; b < NV; ++b) Rx[a][b] = Jl[3 * a] * fJ[3][b] + Jl[3 * a + 1] * fJ[4][b] + Jl[3 * a + 2] * fJ[5][b];
+      } else if (cs.type == EMPC_COST_FRAME_TRANSLATION) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll 1
+          for (int b = 0; b < NV; ++b)
+            Rx[a][b] = oMf.R[3 * a] * fJ[0][b] + oMf.R[3 * a + 1] * fJ[1][b] + oMf.R[3 * a + 2] * fJ[2][b];
+      } else {  // FRAME_VELOCITY
+        n = 6; full = true;
+#pragma unroll 1
+        for (int b = 6; b < NV; ++b) {  // base columns have no parent body: zero
+          const int k = b - 5;
+          if (k <= jf) {
+            double cr[6], o[6];
+            cross_mm(ov[k - 1], Jc[b], cr); actinv_motion(oMf, cr, o);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) Rx[a][b] = o[a];
+          }
+        }
+#pragma unroll 1
+        for (int b = 0; b < NV; ++b)
+#pragma unroll
+          for (int a = 0; a < 6; ++a) Rx[a][NV + b] = fJ[a][b];
+      }
+      const int ncols = full ? NDX : NV;
+      for (int i = 0; i < ncols; ++i) {
+        double s = 0;
+        for (int k = 0; k < n; ++k) s += Rx[k][i] * Ar[k];
+        Lx[i] += wt * s;
+        for (int j = 0; j < ncols; ++j) {
+          double h = 0;
+          for (int k = 0; k < n; ++k) h += Rx[k][i] * (Arr[k] * Rx[k][j]);
+          Lxx[i * NDX + j] += wt * h;
+        }
+      }
+    }
+  }
+  double* gLxx = tile + D::oLxx; double* gLxu = tile + D::oLxu; double* gLuu = tile + D::oLuu;
+  double* gLx = tile + D::oLx; double* gLu = tile + D::oLu;
+#pragma unroll 1
+  for (int i = 0; i < NDX * NDX; ++i) gLxx[i] = Lxx[i] * dt;
+#pragma unroll 1
+  for (int i = 0; i < NDX * NU; ++i) gLxu[i] = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < NU; ++i)
+#pragma unroll 1
+    for (int j = 0; j < NU; ++j) gLuu[i * NU + j] = (i == j) ? Luud[i] * dt : 0.0;
+#pragma unroll
+  for (int i = 0; i < NDX; ++i) gLx[i] = Lx[i] * dt;
+#pragma unroll
+  for (int i = 0; i < NU; ++i) gLu[i] = Lu[i] * dt;
+  if (D::TILE != D::TILE0) tile[D::TILE0] = 0.0;
+}
+
+}  // namespace empc

@@ -1,0 +1,535 @@
+// solver.cu — C-ABI implementation (include/empc_b200.h): device memory ownership, kernel launches, batch iteration loop.
+//
+// Host-side control flow mirrors SolverSbFDDP::solve (src/sbfddp.cpp:192-226) for a whole batch at once: every OCP
+// carries its own state machine on the device (kernels.cuh: OcpState), the host only loops
+//   calc_diff -> backward -> rollout -> decide
+// until no OCP is active.  No CPU fallback: every entry point fails with EMPC_ERR_CUDA if the device is unusable.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace empc;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail(EMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+struct empc_solver {
+  int device = 0, B = 0, T = 0;
+  int na = 0, nr = 0, nq = 0, nv = 0, nx = 0, ndx = 0, nu = 0, tile = 0;
+  int n_costs = 0, n_pool = 0, n_node_maps = 0;
+  empc_solver_params_t P;
+  DevModel hmodel;
+  Buffers bf;
+  std::vector<void*> allocs;
+  // device copies that need host-side access
+  DevModel* d_model = nullptr;
+  empc_cost_t* d_costs = nullptr;
+  double* d_pool = nullptr;
+  int* d_costset_begin = nullptr;
+  int* d_node_costset = nullptr;
+  int* d_ocp_map = nullptr;
+  double* d_x0 = nullptr;
+  double *d_xs_init = nullptr, *d_us_init = nullptr;
+  int init_feasible = 0;
+  cudaStream_t stream = nullptr;
+  int* h_active = nullptr;  // pinned
+  // stats
+  long long launches = 0, total_iterations = 0;
+  int timing = 0;
+  double ms_by_kernel[4] = {0, 0, 0, 0};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+template <class Tp>
+static cudaError_t dalloc(empc_solver* h, Tp** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(Tp));
+  if (e == cudaSuccess) { h->allocs.push_back(*p); e = cudaMemsetAsync(*p, 0, n * sizeof(Tp), h->stream); }
+  return e;
+}
+
+// ---- (NA, NR) dispatch: one instantiation per eagle-mpc platform family ---------------------------------------------
+#define EMPC_DISPATCH(h, CALL)                                               \
+  do {                                                                       \
+    if ((h)->na == 0 && (h)->nr == 4) { using D = Dim<0, 4>; CALL; }         \
+    else if ((h)->na == 0 && (h)->nr == 6) { using D = Dim<0, 6>; CALL; }    \
+    else if ((h)->na == 2 && (h)->nr == 6) { using D = Dim<2, 6>; CALL; }    \
+    else if ((h)->na == 3 && (h)->nr == 6) { using D = Dim<3, 6>; CALL; }    \
+    else if ((h)->na == 5 && (h)->nr == 6) { using D = Dim<5, 6>; CALL; }    \
+    else return fail(EMPC_ERR_UNSUPPORTED, "unsupported (arm joints, rotors) combination");                \
+  } while (0)
+
+static bool supported(int na, int nr) {
+  return (na == 0 && nr == 4) || (na == 0 && nr == 6) || (na == 2 && nr == 6) || (na == 3 && nr == 6) || (na == 5 && nr == 6);
+}
+
+static void inertia_matrix(double m, const double* c, const double* Ic, double* Y) {
+  const double S[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0};
+  double SS[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) SS[3 * i + j] = S[3 * i] * S[j] + S[3 * i + 1] * S[3 + j] + S[3 * i + 2] * S[6 + j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      Y[6 * i + j] = (i == j) ? m : 0.0;
+      Y[6 * i + 3 + j] = -m * S[3 * i + j];
+      Y[6 * (3 + i) + j] = m * S[3 * i + j];
+      Y[6 * (3 + i) + 3 + j] = Ic[3 * i + j] - m * SS[3 * i + j];
+    }
+}
+
+extern "C" {
+
+const char* empc_last_error(void) { return g_last_error.c_str(); }
+
+void empc_default_params(empc_solver_params_t* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->maxiter = 100; p->stop_gap_norm = 0; p->squash_quirk = 0;
+  p->convergence_init = 1e-2; p->convergence_stop = 1e-3; p->convergence_mult = 1e-1;
+  p->smooth_init = 0.1; p->smooth_mult = 0.5; p->barrier_weight = 1e-3;
+  p->reg_init = 1e-9; p->reg_min = 1e-9; p->reg_max = 1e9; p->reg_factor = 10;
+  p->th_acceptstep = 0.1; p->th_acceptnegstep = 2; p->th_grad = 1e-12; p->th_gaptol = 1e-16;
+  p->th_stepdec = 0.5; p->th_stepinc = 0.01; p->th_stop_gaps = 1.0;
+}
+
+int empc_destroy(empc_solver_t* h) {
+  if (!h) return EMPC_OK;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_active) cudaFreeHost(h->h_active);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return EMPC_OK;
+}
+
+int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, empc_solver_t** out) {
+  if (!d || !out || batch <= 0) return fail(EMPC_ERR_INVALID, "null argument or batch <= 0");
+  const empc_robot_t& r = d->robot;
+  if (r.n_joints < 1 || r.n_joints > EMPC_MAX_JOINTS) return fail(EMPC_ERR_INVALID, "bad joint count");
+  for (int i = 1; i < r.n_joints; ++i)
+    if (r.parent[i] != i - 1) return fail(EMPC_ERR_UNSUPPORTED, "device path supports serial-chain arms only");
+  if (!supported(r.n_joints - 1, d->n_rotors)) return fail(EMPC_ERR_UNSUPPORTED, "unsupported (arm joints, rotors) combination");
+  if (d->T < 1 || d->n_node_maps < 1) return fail(EMPC_ERR_INVALID, "bad horizon / node maps");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(EMPC_ERR_CUDA, "no such CUDA device");
+  CK(cudaSetDevice(device));
+
+  empc_solver* h = new empc_solver();
+  h->device = device; h->B = batch; h->T = d->T;
+  h->na = r.n_joints - 1; h->nr = d->n_rotors;
+  h->nq = 7 + h->na; h->nv = 6 + h->na; h->nx = h->nq + h->nv; h->ndx = 2 * h->nv; h->nu = h->nr + h->na;
+  empc_default_params(&h->P);
+  h->n_costs = d->n_costs; h->n_pool = d->n_pool; h->n_node_maps = d->n_node_maps;
+
+  DevModel& M = h->hmodel;
+  std::memset(&M, 0, sizeof(M));
+  M.nj = r.n_joints; M.na = h->na; M.nq = h->nq; M.nv = h->nv; M.nx = h->nx; M.ndx = h->ndx; M.nu = h->nu; M.nr = h->nr;
+  M.T = d->T; M.use_squash = d->use_squash; M.n_frames = r.n_frames; M.dt = d->dt;
+  const int ndx = h->ndx, nu = h->nu;
+  M.oFx = 0; M.oFu = ndx * ndx; M.oLxx = M.oFu + ndx * nu; M.oLxu = M.oLxx + ndx * ndx; M.oLuu = M.oLxu + ndx * nu;
+  M.oLx = M.oLuu + nu * nu; M.oLu = M.oLx + ndx;
+  M.tile = M.oLu + nu; M.tile += M.tile & 1;
+  h->tile = M.tile;
+  for (int i = 0; i < r.n_joints; ++i) {
+    std::memcpy(M.jR[i], r.jplace_R[i], 72); std::memcpy(M.jp[i], r.jplace_p[i], 24); std::memcpy(M.axis[i], r.axis[i], 24);
+    inertia_matrix(r.mass[i], r.com[i], r.inertia[i], M.Y[i]);
+  }
+  for (int i = 0; i < 3; ++i) { M.a0[i] = -r.gravity[i]; M.a0[3 + i] = 0; }
+  for (int f = 0; f < r.n_frames; ++f) {
+    M.frame_joint[f] = r.frame_joint[f];
+    std::memcpy(M.fR[f], r.frame_R[f], 72); std::memcpy(M.fp[f], r.frame_p[f], 24);
+  }
+  std::memcpy(M.tau_f, d->tau_f, sizeof(double) * 6 * h->nr);
+  for (int i = 0; i < nu; ++i) {
+    M.u_lb[i] = d->u_lb[i]; M.u_ub[i] = d->u_ub[i];
+    const double mid = 0.5 * (d->u_lb[i] + d->u_ub[i]), dd = 0.5 * (d->u_ub[i] - d->u_lb[i]);
+    M.bar_lb[i] = mid - 1.0 * dd; M.bar_ub[i] = mid + 1.0 * dd;  // crocoddyl::ActivationBounds ctor, beta = 1
+  }
+  M.barrier_weight = h->P.barrier_weight;
+
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return fail(EMPC_ERR_CUDA, cudaGetErrorString(e)); }
+#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); empc_destroy(h); return fail(EMPC_ERR_CUDA, m_); } } while (0)
+  const size_t B = batch, T = d->T, T1 = T + 1, nx = h->nx, tile = h->tile;
+  CKH(cudaMallocHost((void**)&h->h_active, sizeof(int)));
+  for (auto& ev : h->ev) CKH(cudaEventCreate(&ev));
+  CKH(dalloc(h, &h->d_model, 1));
+  CKH(dalloc(h, &h->d_costs, (size_t)std::max(1, d->n_costs)));
+  CKH(dalloc(h, &h->d_pool, (size_t)std::max(1, d->n_pool)));
+  CKH(dalloc(h, &h->d_costset_begin, (size_t)d->n_costsets + 1));
+  CKH(dalloc(h, &h->d_node_costset, (size_t)d->n_node_maps * T1));
+  CKH(dalloc(h, &h->d_ocp_map, B));
+  CKH(dalloc(h, &h->d_x0, B * nx));
+  CKH(dalloc(h, &h->d_xs_init, B * T1 * nx));
+  CKH(dalloc(h, &h->d_us_init, B * T * nu));
+  Buffers& bf = h->bf;
+  std::memset(&bf, 0, sizeof(bf));
+  bf.B = batch; bf.T = d->T;
+  CKH(dalloc(h, &bf.st, B));
+  CKH(dalloc(h, &bf.xs, B * T1 * nx));
+  CKH(dalloc(h, &bf.us, B * T * nu));
+  CKH(dalloc(h, &bf.xs_try0, B * nx));
+  CKH(dalloc(h, &bf.tiles, B * T1 * tile));
+  CKH(dalloc(h, &bf.xnext, B * T1 * nx));
+  CKH(dalloc(h, &bf.node_cost, B * T1));
+  CKH(dalloc(h, &bf.fs, B * T1 * ndx));
+  CKH(dalloc(h, &bf.gap_inf, B * T1));
+  CKH(dalloc(h, &bf.gap_l1, B * T1));
+  CKH(dalloc(h, &bf.K, B * T * nu * ndx));
+  CKH(dalloc(h, &bf.k, B * T * nu));
+  CKH(dalloc(h, &bf.Vx, B * T1 * ndx));
+  CKH(dalloc(h, &bf.g, B * T1 * ndx));
+  CKH(dalloc(h, &bf.nodesc, B * T1 * 4));
+  CKH(dalloc(h, &bf.xs_try, (size_t)EMPC_N_ALPHAS * B * T1 * nx));
+  CKH(dalloc(h, &bf.us_try, (size_t)EMPC_N_ALPHAS * B * T * nu));
+  CKH(dalloc(h, &bf.cost_try, B * EMPC_N_ALPHAS));
+  CKH(dalloc(h, &bf.dv, B * EMPC_N_ALPHAS));
+  CKH(dalloc(h, &bf.ok, B * EMPC_N_ALPHAS));
+  CKH(dalloc(h, &bf.us_squash, B * T * nu));
+  CKH(dalloc(h, &bf.n_active, 1));
+  bf.model = h->d_model; bf.ct.costs = h->d_costs; bf.ct.pool = h->d_pool; bf.ct.costset_begin = h->d_costset_begin;
+  bf.node_costset = h->d_node_costset; bf.ocp_map = h->d_ocp_map; bf.x0 = h->d_x0;
+  CKH(cudaMemcpyAsync(h->d_model, &M, sizeof(M), cudaMemcpyHostToDevice, h->stream));
+  if (d->n_costs) CKH(cudaMemcpyAsync(h->d_costs, d->costs, sizeof(empc_cost_t) * d->n_costs, cudaMemcpyHostToDevice, h->stream));
+  if (d->n_pool) CKH(cudaMemcpyAsync(h->d_pool, d->pool, sizeof(double) * d->n_pool, cudaMemcpyHostToDevice, h->stream));
+  CKH(cudaMemcpyAsync(h->d_costset_begin, d->costset_begin, sizeof(int) * (d->n_costsets + 1), cudaMemcpyHostToDevice, h->stream));
+  CKH(cudaMemcpyAsync(h->d_node_costset, d->node_costset, sizeof(int) * d->n_node_maps * T1, cudaMemcpyHostToDevice, h->stream));
+  CKH(cudaStreamSynchronize(h->stream));
+  // default x0 / candidate: state.zero()
+  {
+    std::vector<double> x0(B * nx, 0.0);
+    for (size_t b = 0; b < B; ++b) x0[b * nx + 6] = 1.0;
+    CKH(cudaMemcpy(h->d_x0, x0.data(), sizeof(double) * x0.size(), cudaMemcpyHostToDevice));
+  }
+  *out = h;
+  int rc = empc_set_candidate(h, nullptr, nullptr, 0);
+  if (rc != EMPC_OK) { empc_destroy(h); *out = nullptr; return rc; }
+  return EMPC_OK;
+}
+
+int empc_get_dims(const empc_solver_t* h, empc_dims_t* o) {
+  if (!h || !o) return fail(EMPC_ERR_INVALID, "null");
+  o->nq = h->nq; o->nv = h->nv; o->nx = h->nx; o->ndx = h->ndx; o->nu = h->nu; o->T = h->T; o->batch = h->B; o->tile = h->tile;
+  return EMPC_OK;
+}
+
+int empc_set_x0(empc_solver_t* h, const double* x0) {
+  if (!h || !x0) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_x0, x0, sizeof(double) * h->B * h->nx, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
+
+static int load_candidate(empc_solver* h) {
+  const size_t nxs = (size_t)h->B * (h->T + 1) * h->nx, nus = (size_t)h->B * h->T * h->nu;
+  CK(cudaMemcpyAsync(h->bf.xs, h->d_xs_init, sizeof(double) * nxs, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->bf.us, h->d_us_init, sizeof(double) * nus, cudaMemcpyDeviceToDevice, h->stream));
+  return EMPC_OK;
+}
+
+int empc_set_candidate(empc_solver_t* h, const double* xs, const double* us, int32_t is_feasible) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  const size_t nxs = (size_t)h->B * (h->T + 1) * h->nx, nus = (size_t)h->B * h->T * h->nu;
+  if (xs) CK(cudaMemcpyAsync(h->d_xs_init, xs, sizeof(double) * nxs, cudaMemcpyHostToDevice, h->stream));
+  else {
+    std::vector<double> z(nxs, 0.0);
+    for (size_t n = 0; n < nxs / h->nx; ++n) z[n * h->nx + 6] = 1.0;
+    CK(cudaMemcpy(h->d_xs_init, z.data(), sizeof(double) * nxs, cudaMemcpyHostToDevice));
+  }
+  if (us) CK(cudaMemcpyAsync(h->d_us_init, us, sizeof(double) * nus, cudaMemcpyHostToDevice, h->stream));
+  else CK(cudaMemsetAsync(h->d_us_init, 0, sizeof(double) * nus, h->stream));
+  h->init_feasible = is_feasible ? 1 : 0;
+  int rc = load_candidate(h);
+  if (rc) return rc;
+  init_state_kernel<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->bf, h->P, h->init_feasible, h->nx);
+  override_state_kernel<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->bf, 0.0, h->init_feasible, 0);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
+
+int empc_set_params(empc_solver_t* h, const empc_solver_params_t* p) {
+  if (!h || !p) return fail(EMPC_ERR_INVALID, "null");
+  if (p->maxiter < 1) return fail(EMPC_ERR_INVALID, "maxiter < 1");
+  h->P = *p;
+  h->hmodel.barrier_weight = p->barrier_weight;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(h->d_model, &h->hmodel, sizeof(DevModel), cudaMemcpyHostToDevice));
+  return EMPC_OK;
+}
+
+int empc_set_node_maps(empc_solver_t* h, const int32_t* m) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  if (m) {
+    for (int b = 0; b < h->B; ++b) if (m[b] < 0 || m[b] >= h->n_node_maps) return fail(EMPC_ERR_INVALID, "node map out of range");
+    CK(cudaMemcpy(h->d_ocp_map, m, sizeof(int) * h->B, cudaMemcpyHostToDevice));
+  } else CK(cudaMemset(h->d_ocp_map, 0, sizeof(int) * h->B));
+  return EMPC_OK;
+}
+
+int empc_update_costs(empc_solver_t* h, int32_t first, int32_t n, const empc_cost_t* costs, int32_t pool_off, int32_t n_pool, const double* pool) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  if (n < 0 || first < 0 || first + n > h->n_costs || n_pool < 0 || pool_off < 0 || pool_off + n_pool > h->n_pool)
+    return fail(EMPC_ERR_INVALID, "cost / pool range out of bounds");
+  CK(cudaSetDevice(h->device));
+  if (n) CK(cudaMemcpyAsync(h->d_costs + first, costs, sizeof(empc_cost_t) * n, cudaMemcpyHostToDevice, h->stream));
+  if (n_pool) CK(cudaMemcpyAsync(h->d_pool + pool_off, pool, sizeof(double) * n_pool, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
+
+int empc_update_node_costsets(empc_solver_t* h, const int32_t* nc) {
+  if (!h || !nc) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(h->d_node_costset, nc, sizeof(int) * h->n_node_maps * (h->T + 1), cudaMemcpyHostToDevice));
+  return EMPC_OK;
+}
+
+}  // extern "C"
+
+// ---- launches -------------------------------------------------------------------------------------------------------
+template <class D>
+static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth) {
+  const int n = h->B * (h->T + 1);
+  calc_diff_kernel<D><<<(n + 127) / 128, 128, 0, h->stream>>>(h->bf, force, smooth);
+  h->launches++;
+  return cudaGetLastError();
+}
+template <class D>
+static cudaError_t launch_backward(empc_solver* h, int force) {
+  constexpr int WARPS = 4;
+  const size_t smem = sizeof(double) * BwSmem<D>::TOTAL * WARPS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(backward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  BwParams P{h->P.reg_max, h->P.reg_factor, h->P.th_gaptol, force};
+  backward_kernel<D><<<(h->B + WARPS - 1) / WARPS, WARPS * 32, smem, h->stream>>>(h->bf, P);
+  h->launches++;
+  return cudaGetLastError();
+}
+template <class D>
+static cudaError_t launch_rollout(empc_solver* h, int force, int feasible, int ddp, double smooth) {
+  const int n = h->B * EMPC_N_ALPHAS;
+  RoParams P{force, feasible, ddp, smooth};
+  rollout_kernel<D><<<(n + 63) / 64, 64, 0, h->stream>>>(h->bf, P);
+  h->launches++;
+  return cudaGetLastError();
+}
+template <class D>
+static cudaError_t launch_decide(empc_solver* h) {
+  DecideParams dp{h->P};
+  decide_kernel<D><<<h->B, 128, 0, h->stream>>>(h->bf, dp);
+  h->launches++;
+  return cudaGetLastError();
+}
+template <class D>
+static cudaError_t launch_squash_out(empc_solver* h) {
+  const int n = h->B * h->T;
+  squash_out_kernel<D><<<(n + 127) / 128, 128, 0, h->stream>>>(h->bf);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+template <class D>
+static int solve_impl(empc_solver* h) {
+  if (D::TILE != h->tile) return fail(EMPC_ERR_INVALID, "tile size mismatch");
+  h->launches = 0; h->total_iterations = 0;
+  for (double& m : h->ms_by_kernel) m = 0;
+  init_state_kernel<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->bf, h->P, h->init_feasible, h->nx);
+  h->launches++;
+  CK(cudaGetLastError());
+  // upper bound on batch iterations: every pass of every phase can use maxiter iterations
+  int passes = 1;
+  for (double c = h->P.convergence_init; c >= h->P.convergence_stop && passes < 64; c *= h->P.convergence_mult) passes++;
+  const long long max_loops = (long long)passes * h->P.maxiter + 8;
+  for (long long it = 0; it < max_loops; ++it) {
+    if (h->timing) CK(cudaEventRecord(h->ev[0], h->stream));
+    CK(launch_calc_diff<D>(h, 0, 0.0));
+    if (h->timing) CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(launch_backward<D>(h, 0));
+    if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(launch_rollout<D>(h, 0, 0, 0, 0.0));
+    if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaMemsetAsync(h->bf.n_active, 0, sizeof(int), h->stream));
+    CK(launch_decide<D>(h));
+    if (h->timing) CK(cudaEventRecord(h->ev[4], h->stream));
+    CK(cudaMemcpyAsync(h->h_active, h->bf.n_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->timing) {
+      for (int k = 0; k < 4; ++k) { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1])); h->ms_by_kernel[k] += ms; }
+    }
+    if (const char* tr = std::getenv("EMPC_TRACE_OCP")) {
+      const int b = std::atoi(tr);
+      if (b >= 0 && b < h->B) {
+        OcpState s;
+        CK(cudaMemcpy(&s, h->bf.st + b, sizeof(s), cudaMemcpyDeviceToHost));
+        std::printf("[gpu ph%d] loop=%lld it=%d cost=%.15e prev=%.15e step=%g xreg=%g feas=%d wasf=%d stop=%.6e gap=%.6e acc=%d dg=%.6e dq=%.6e smooth=%g tot=%d\n",
+                    s.phase, it, s.iter, s.cost, s.cost_prev, s.steplength, s.xreg, s.is_feasible, s.was_feasible, s.stop, s.gap_inf, s.accepted, s.dg, s.dq, s.smooth, s.total_iters);
+      }
+    }
+    if (*h->h_active == 0) break;
+  }
+  CK(launch_squash_out<D>(h));
+  // total inner iterations over the batch
+  std::vector<OcpState> st(h->B);
+  CK(cudaMemcpyAsync(st.data(), h->bf.st, sizeof(OcpState) * h->B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  long long tot = 0;
+  for (const OcpState& s : st) tot += s.total_iters;
+  h->total_iterations = tot;
+  return EMPC_OK;
+}
+
+extern "C" {
+
+int empc_solve(empc_solver_t* h) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  EMPC_DISPATCH(h, return solve_impl<D>(h));
+  return EMPC_OK;
+}
+
+int empc_reset(empc_solver_t* h) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  int rc = load_candidate(h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
+
+// ---- outputs ---------------------------------------------------------------------------------------------------------
+static int d2h(const empc_solver* h, void* dst, const void* src, size_t bytes) {
+  if (!h || !dst) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
+int empc_get_xs(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.xs, sizeof(double) * h->B * (h->T + 1) * h->nx); }
+int empc_get_us(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.us, sizeof(double) * h->B * h->T * h->nu); }
+int empc_get_us_squash(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.us_squash, sizeof(double) * h->B * h->T * h->nu); }
+int empc_get_K(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.K, sizeof(double) * h->B * h->T * h->nu * h->ndx); }
+int empc_get_k(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.k, sizeof(double) * h->B * h->T * h->nu); }
+int empc_get_tiles(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.tiles, sizeof(double) * h->B * (h->T + 1) * h->tile); }
+int empc_get_xnext(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.xnext, sizeof(double) * h->B * (h->T + 1) * h->nx); }
+int empc_get_node_cost(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.node_cost, sizeof(double) * h->B * (h->T + 1)); }
+int empc_get_gaps(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.fs, sizeof(double) * h->B * (h->T + 1) * h->ndx); }
+int empc_get_Vx(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.Vx, sizeof(double) * h->B * (h->T + 1) * h->ndx); }
+int empc_get_Vxx_fs(const empc_solver_t* h, double* o) { return d2h(h, o, h->bf.g, sizeof(double) * h->B * (h->T + 1) * h->ndx); }
+
+static int get_states(const empc_solver* h, std::vector<OcpState>& st) {
+  st.resize(h->B);
+  return d2h(h, st.data(), h->bf.st, sizeof(OcpState) * h->B);
+}
+int empc_get_cost(const empc_solver_t* h, double* o) {
+  std::vector<OcpState> st; int rc = get_states(h, st); if (rc) return rc;
+  for (int b = 0; b < h->B; ++b) o[b] = st[b].cost;
+  return EMPC_OK;
+}
+int empc_get_iters(const empc_solver_t* h, int32_t* o) {
+  std::vector<OcpState> st; int rc = get_states(h, st); if (rc) return rc;
+  for (int b = 0; b < h->B; ++b) o[b] = st[b].iters_out;
+  return EMPC_OK;
+}
+int empc_get_stop(const empc_solver_t* h, double* o) {
+  std::vector<OcpState> st; int rc = get_states(h, st); if (rc) return rc;
+  for (int b = 0; b < h->B; ++b) o[b] = st[b].stop;
+  return EMPC_OK;
+}
+int empc_get_feasible(const empc_solver_t* h, int32_t* o) {
+  std::vector<OcpState> st; int rc = get_states(h, st); if (rc) return rc;
+  for (int b = 0; b < h->B; ++b) o[b] = st[b].is_feasible;
+  return EMPC_OK;
+}
+int empc_get_reg(const empc_solver_t* h, double* o) {
+  std::vector<OcpState> st; int rc = get_states(h, st); if (rc) return rc;
+  for (int b = 0; b < h->B; ++b) o[b] = st[b].xreg;
+  return EMPC_OK;
+}
+int empc_get_dgdq(const empc_solver_t* h, double* o) {
+  std::vector<OcpState> st; int rc = get_states(h, st); if (rc) return rc;
+  for (int b = 0; b < h->B; ++b) { o[2 * b] = st[b].dg; o[2 * b + 1] = st[b].dq; }
+  return EMPC_OK;
+}
+int empc_get_total_iterations(const empc_solver_t* h, int64_t* total) {
+  if (!h || !total) return fail(EMPC_ERR_INVALID, "null");
+  *total = h->total_iterations;
+  return EMPC_OK;
+}
+int empc_get_launch_stats(const empc_solver_t* h, int64_t* launches, double* ms) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  if (launches) *launches = h->launches;
+  if (ms) for (int k = 0; k < 4; ++k) ms[k] = h->ms_by_kernel[k];
+  return EMPC_OK;
+}
+int empc_enable_kernel_timing(empc_solver_t* h, int32_t on) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  h->timing = on ? 1 : 0;
+  return EMPC_OK;
+}
+
+// ---- tile-level parity hooks ---------------------------------------------------------------------------------------
+int empc_phase_calc_diff(empc_solver_t* h, double smooth) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  EMPC_DISPATCH(h, CK(launch_calc_diff<D>(h, 1, smooth)));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
+int empc_phase_backward(empc_solver_t* h, double xreg, int32_t is_feasible, int32_t* ok) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  override_state_kernel<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->bf, xreg, is_feasible, 1);
+  CK(cudaGetLastError());
+  EMPC_DISPATCH(h, CK(launch_backward<D>(h, 1)));
+  CK(cudaStreamSynchronize(h->stream));
+  if (ok) {
+    std::vector<OcpState> st; int rc = get_states(h, st); if (rc) return rc;
+    for (int b = 0; b < h->B; ++b) ok[b] = st[b].bw_fail ? 0 : 1;
+  }
+  return EMPC_OK;
+}
+int empc_phase_rollout(empc_solver_t* h, double smooth, int32_t is_feasible, int32_t ddp) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  CK(cudaSetDevice(h->device));
+  EMPC_DISPATCH(h, CK(launch_rollout<D>(h, 1, is_feasible, ddp, smooth)));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
+int empc_get_trial(const empc_solver_t* h, int32_t ai, double* xs_try, double* us_try, double* cost_try, double* dv, int32_t* ok) {
+  if (!h || ai < 0 || ai >= EMPC_N_ALPHAS) return fail(EMPC_ERR_INVALID, "bad alpha index");
+  const size_t B = h->B, T1 = h->T + 1;
+  int rc;
+  if (xs_try && (rc = d2h(h, xs_try, h->bf.xs_try + (size_t)ai * B * T1 * h->nx, sizeof(double) * B * T1 * h->nx))) return rc;
+  if (us_try && (rc = d2h(h, us_try, h->bf.us_try + (size_t)ai * B * h->T * h->nu, sizeof(double) * B * h->T * h->nu))) return rc;
+  std::vector<double> c(B * EMPC_N_ALPHAS), d(B * EMPC_N_ALPHAS);
+  std::vector<int> o(B * EMPC_N_ALPHAS);
+  if ((rc = d2h(h, c.data(), h->bf.cost_try, sizeof(double) * c.size()))) return rc;
+  if ((rc = d2h(h, d.data(), h->bf.dv, sizeof(double) * d.size()))) return rc;
+  if ((rc = d2h(h, o.data(), h->bf.ok, sizeof(int) * o.size()))) return rc;
+  for (size_t b = 0; b < B; ++b) {
+    if (cost_try) cost_try[b] = c[b * EMPC_N_ALPHAS + ai];
+    if (dv) dv[b] = d[b * EMPC_N_ALPHAS + ai];
+    if (ok) ok[b] = o[b * EMPC_N_ALPHAS + ai];
+  }
+  return EMPC_OK;
+}
+
+}  // extern "C"

@@ -21,6 +21,7 @@
 //   increase/decreaseRegularization}, SolverFDDP::{forwardPass,updateExpectedImprovement,expectedImprovement}.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -44,7 +45,9 @@ struct Solver {
   std::vector<std::vector<CostEval>> evals;
   bool is_feasible = false, was_feasible = false;
   double cost = 0, cost_prev = 0, cost_try = 0, xreg = 0, ureg = 0, steplength = 1, dV = 0, dVexp = 0;
-  double dg = 0, dq = 0, dv = 0, d0 = 0, d1 = 0, stop = 0, th_stop = 0, smooth = 0.1, convergence = 0;
+  double dg = 0, dq = 0, dv = 0, d0 = 0, d1 = 0, stop = 0, th_stop = 0, convergence = 0;
+  double smooth = 0.1;        // SolverSbFDDP::smooth_ (the schedule variable)
+  double smooth_model = 0.1;  // what squashingUpdate()/barrierUpdate() last pushed into the models
   int iter = 0;
   long total_iters = 0;
   double alphas[EMPC_N_ALPHAS];
@@ -72,7 +75,7 @@ struct Solver {
     set_candidate(nullptr, nullptr, false);
   }
   int costset_of(int t) const { return node_costset[(size_t)node_map * (T + 1) + t]; }
-  SolverCtx ctx() const { return SolverCtx{smooth, P.barrier_weight}; }
+  SolverCtx ctx() const { return SolverCtx{smooth_model, P.barrier_weight}; }
 
   // SolverAbstract::setCandidate (crocoddyl/core/solver-base.cpp)
   void set_candidate(const double* xs_in, const double* us_in, bool feasible) {
@@ -370,6 +373,12 @@ struct Solver {
   bool stopping_test() const { return stop < th_stop && gap_norm() < P.th_stop_gaps; }   // StopTestGaps
   bool stopping_test_feasible() const { return was_feasible && stop < th_stop; }
 
+  void trace(const char* ph) const {
+    static const char* on = std::getenv("ORC_TRACE");
+    if (!on) return;
+    std::printf("[orc %s] it=%d cost=%.15e prev=%.15e step=%g xreg=%g feas=%d wasf=%d stop=%.6e gap=%.6e dV=%.6e dVexp=%.6e d0=%.6e d1=%.6e smooth=%g\n",
+                ph, iter, cost, cost_prev, steplength, xreg, (int)is_feasible, (int)was_feasible, stop, gap_norm(), dV, dVexp, d0, d1, smooth_model);
+  }
   // src/sbfddp.cpp:228-315
   bool solve_fddp(int maxiter, bool feasible_arg, double reginit) {
     is_feasible = feasible_arg;
@@ -416,6 +425,7 @@ struct Solver {
         if (xreg == P.reg_max) return false;
       }
       stopping_criteria();
+      trace("fddp");
       if (stopping_test()) return true;
     }
     iter = iter >= maxiter ? maxiter - 1 : iter;
@@ -458,6 +468,7 @@ struct Solver {
         if (xreg == P.reg_max) return false;
       }
       stopping_criteria();
+      trace("ddp");
       if (stopping_test_feasible()) return true;
     }
     iter = iter >= maxiter ? maxiter - 1 : iter;
@@ -471,7 +482,7 @@ struct Solver {
     convergence = P.convergence_init;
     total_iters = 0;
     while (convergence >= P.convergence_stop) {
-      // squashingUpdate / barrierUpdate: both are functions of `smooth`, read through ctx()
+      smooth_model = smooth;  // squashingUpdate() + barrierUpdate() (src/sbfddp.cpp:206-207,462-477)
       th_stop = convergence;
       solve_fddp(maxiter, false, P.reg_init);
       smooth *= P.smooth_mult;
@@ -484,9 +495,9 @@ struct Solver {
     }
     iter = (int)total_iters - 1;
     // fillSquashedOutputs.  The node data were last evaluated with the smoothing of the final pass (set_smooth is not
-    // called again after the loop), i.e. smooth/smooth_mult.  Default: s(us[t]); squash_quirk: whatever the last calc
-    // on node t left.
-    const double last_smooth = smooth / P.smooth_mult;
+    // called again after the loop; the DDP clean-up phase therefore also runs with it).  Default: s(us[t]);
+    // squash_quirk: whatever the last calc on node t left.
+    const double last_smooth = smooth_model;
     for (int t = 0; t < T; ++t)
       for (int i = 0; i < m.nu; ++i) {
         if (P.squash_quirk) { us_squash[(size_t)t * m.nu + i] = work[t].s[i]; continue; }
@@ -547,7 +558,7 @@ void orc_solve(void* h, const double* xs_in, const double* us_in, int feasible) 
 // ---- phase hooks mirroring empc_phase_* ----
 void orc_phase_calc_diff(void* h, double smooth) {
   Solver* s = (Solver*)h;
-  s->smooth = smooth; s->iter = 0;
+  s->smooth = s->smooth_model = smooth; s->iter = 0;
   s->calc_diff();
 }
 int orc_phase_backward(void* h, double xreg, int feasible) {
@@ -559,7 +570,7 @@ int orc_phase_backward(void* h, double xreg, int feasible) {
 }
 int orc_phase_rollout(void* h, double smooth, int feasible, int ddp, int alpha_index) {
   Solver* s = (Solver*)h;
-  s->smooth = smooth; s->is_feasible = feasible != 0;
+  s->smooth = s->smooth_model = smooth; s->is_feasible = feasible != 0;
   const double a = s->alphas[alpha_index];
   bool ok;
   if (ddp) ok = s->forward_pass_ddp(a);
