@@ -1,0 +1,288 @@
+#!/usr/bin/env python3
+"""bench.py — SbFDDP OCP-iterations/sec on synthetic batches of the reference's named problems (BASELINE.json).
+
+A "step" is one complete batched SbFDDP solve (every OCP of the batch to its own stopping decision) of
+  hexacopter370_flying_arm_3 / displacement.yaml, dt 20 ms, Euler, squash, T = 400, B = 4096 OCPs per GPU,
+  x0_b = YAML initial state + 0.05*U(-1,1) noise (seed 2024+b), zero initial guess, maxiter 100  (SURVEY.md §8d config 2).
+`value`  = OCP-iterations executed by all ranks / device time, inputs already resident in HBM.
+`e2e`    = the same through the C ABI with host buffers: x0 copied H2D, xs/us/cost/iters copied D2H inside the timed region.
+`--impl reference` times the CPU restatement (oracle/) on all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SbFDDP OCP-iterations/sec"
+UNIT = "OCP-iterations/s"
+WORKLOAD = "hexacopter370_flying_arm_3_displacement"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="OCPs per GPU")
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="OCPs in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_problem(name):
+    host = importlib.import_module("eagle-mpc_b200.host")
+    wl = importlib.import_module("eagle-mpc_b200.workloads")
+    yaml, dt, seed0 = wl.CONFIGS[name]
+    tr = host.Trajectory(yaml)
+    fp = tr.createProblem(dt)
+    return tr, fp, wl, seed0, dt
+
+
+def oracle_binding():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob  # test infrastructure: only used for the CPU baseline legs
+    return ob
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.t = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.strip().split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the in-repo restatement (oracle/) on all host threads; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tr, fp, wl, seed0, dt = load_problem(args.workload)
+    ob = oracle_binding()
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample or max(cores, 8 * cores)
+    n = min(n, 512)
+    x0 = wl.noisy_x0(fp.x0, n, seed0)
+    for _ in range(max(args.warmup, 0)):
+        ob.solve_batch(fp, x0[:cores], cores)
+    tot_it, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        sec, it, _c = ob.solve_batch(fp, x0, cores)
+        tot_it += int(it.sum()); tot_s += sec
+    v = tot_it / tot_s
+    sample = f"{n} OCPs of {args.workload} (B=4096 workload, seeds {seed0}..{seed0 + n - 1}) per step, {cores} threads"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": args.workload, "T": fp.T, "dt_ms": dt, "batch_per_step": n,
+                      "note": "CPU restatement of the reference algorithm (oracle/), not Crocoddyl itself"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    tr, fp, wl, seed0, dt = load_problem(args.workload)
+    B = args.batch
+    nx, nu, ndx, T = fp.nx, fp.nu, fp.ndx, fp.T
+    # weak scaling: every rank solves its own B OCPs (seeds continue across ranks); no collective on the solver path
+    x0 = wl.noisy_x0(fp.x0, B, seed0, first=rank * B)
+    solver = capi.BatchSolver(fp, B, device=local_rank)
+    solver.set_x0(x0)
+    solver.set_candidate(None, None, False)
+    solver.enable_kernel_timing(True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # pinned host buffers for the e2e leg
+    x0_pin = torch.from_numpy(x0.copy()).pin_memory()
+    xs_pin = torch.empty((B, T + 1, nx), dtype=torch.float64).pin_memory()
+    us_pin = torch.empty((B, T, nu), dtype=torch.float64).pin_memory()
+    cost_pin = torch.empty((B,), dtype=torch.float64).pin_memory()
+    iters_pin = torch.empty((B,), dtype=torch.int32).pin_memory()
+
+    def step_resident():
+        solver.reset()
+        solver.solve()
+        return solver.total_iterations()
+
+    def step_e2e():
+        solver.set_x0_ptr(x0_pin.data_ptr())
+        solver.set_candidate(None, None, False)
+        solver.solve()
+        solver.get_into("xs", xs_pin.data_ptr())
+        solver.get_into("us", us_pin.data_ptr())
+        solver.get_into("cost", cost_pin.data_ptr())
+        solver.get_into("iters", iters_pin.data_ptr())
+        return solver.total_iterations()
+
+    for _ in range(args.warmup):
+        step_resident()
+    # ---- timed region: device-resident inputs ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    iters = 0
+    dev_ms = 0.0
+    launches = 0
+    ms_k = np.zeros(4)
+    units_k = np.zeros(4, dtype=np.int64)
+    for _ in range(args.steps):
+        iters += step_resident()
+        ms, units = solver.solve_stats()
+        dev_ms += ms
+        n_l, mk = solver.launch_stats()
+        launches += n_l; ms_k += mk; units_k += units
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- e2e: host buffers through the C ABI ----
+    step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    iters_e2e = 0
+    for _ in range(args.steps):
+        iters_e2e += step_e2e()
+    barrier()
+    wall_e2e = time.perf_counter() - t1
+    h2d = x0_pin.numel() * 8
+    d2h = (xs_pin.numel() + us_pin.numel() + cost_pin.numel()) * 8 + iters_pin.numel() * 4
+
+    # max over ranks of the time, sum over ranks of the work
+    stats = torch.tensor([wall, wall_e2e, dev_ms], dtype=torch.float64, device="cuda")
+    work = torch.tensor([iters, iters_e2e, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    wall, wall_e2e, dev_ms = stats.tolist()
+    iters_all, iters_e2e_all, launches_all = work.tolist()
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        # roofline of the dominant kernel: algorithmic bytes (SURVEY.md §8d split per kernel family) / its device time
+        D = 2 * ndx * ndx + 2 * ndx * nu + nu * nu + ndx + nu
+        bytes_node = {
+            "calc_diff": 8 * ((nx + nu) + (D + nx + 1)),
+            "backward": 8 * ((D + ndx) + (nu * ndx + nu + ndx + ndx * ndx)),
+            "rollout": 8 * ((nx + nu + nu * ndx + nu + ndx) + (nx + nu + 1)),  # one trial (the sequential reference's usual case)
+        }
+        names = ["calc_diff", "backward", "rollout", "decide"]
+        dom = int(np.argmax(ms_k[:3]))
+        n_launch = max(1, (launches - 2 * args.steps) // 4)  # launches of each kernel family on this rank
+        ach = bytes_node[names[dom]] * float(units_k[dom]) * T / (ms_k[dom] * 1e-3) / 1e9
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        roofline = {"bound": "hbm", "kernel": names[dom] + "_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_kind": peak_kind,
+                    "algorithmic_bytes_per_node": bytes_node[names[dom]],
+                    "avg_launch_ms": float(ms_k[dom] / n_launch),
+                    "share_of_step": {n: float(ms_k[i] / ms_k.sum()) for i, n in enumerate(names)},
+                    "ms_by_kernel_per_step": {n: float(ms_k[i] / args.steps) for i, n in enumerate(names)}}
+        out = {"metric": METRIC, "value": iters_all / wall, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": args.workload, "T": T, "dt_ms": dt, "batch_per_gpu": B, "maxiter": 100,
+                          "nx": nx, "ndx": ndx, "nu": nu, "x0": f"YAML initial state + 0.05*U(-1,1), seeds {seed0}+b",
+                          "l2": "inputs_larger_than_L2 (node tiles: %.1f GB per GPU)" % (B * (T + 1) * fp.tile * 8 / 1e9),
+                          "iterations_per_step": iters_all / args.steps, "device_ms_per_step": dev_ms / args.steps},
+               "clocks": clocks,
+               "e2e": {"value": iters_e2e_all / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": 1e3 * wall_e2e / args.steps},
+               "gpu_launches": int(launches_all), "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            ob = oracle_binding()
+            cores = os.cpu_count() or 1
+            n = args.cpu_sample or min(512, 12 * cores)
+            sec, it, _c = ob.solve_batch(fp, x0[:n], cores)
+            out["cpu_baseline"] = {"value": float(it.sum() / sec), "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"first {n} OCPs of the same batch, {cores} host threads, {sec:.1f} s; CPU restatement (oracle/), not Crocoddyl itself"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

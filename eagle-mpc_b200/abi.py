@@ -111,22 +111,8 @@ def as_int32_p(a):
     return a.ctypes.data_as(c_int32_p)
 
 
-class DescHolder:
-    """Owns the numpy arrays a ProblemDesc points to (keeps them alive)."""
-
-    def __init__(self, desc, costset_begin, costs, pool, node_costset):
-        self.desc = desc
-        self.costset_begin = np.ascontiguousarray(costset_begin, dtype=np.int32)
-        self.costs = costs  # ctypes array of Cost
-        self.pool = np.ascontiguousarray(pool, dtype=np.float64)
-        self.node_costset = np.ascontiguousarray(node_costset, dtype=np.int32)
-        desc.costset_begin = as_int32_p(self.costset_begin)
-        desc.costs = C.cast(self.costs, C.POINTER(Cost))
-        desc.pool = as_double_p(self.pool)
-        desc.node_costset = as_int32_p(self.node_costset)
-        desc.n_costsets = len(self.costset_begin) - 1
-        desc.n_costs = len(self.costs)
-        desc.n_pool = len(self.pool)
+class DescView:
+    """Dimension helpers over a ProblemDesc (`self.desc`)."""
 
     @property
     def na(self):
@@ -173,3 +159,21 @@ class DescHolder:
         o["Lx"] = o["Luu"] + nu * nu
         o["Lu"] = o["Lx"] + ndx
         return o
+
+
+class DescHolder(DescView):
+    """Owns the numpy arrays a ProblemDesc points to (keeps them alive)."""
+
+    def __init__(self, desc, costset_begin, costs, pool, node_costset):
+        self.desc = desc
+        self.costset_begin = np.ascontiguousarray(costset_begin, dtype=np.int32)
+        self.costs = costs  # ctypes array of Cost
+        self.pool = np.ascontiguousarray(pool, dtype=np.float64)
+        self.node_costset = np.ascontiguousarray(node_costset, dtype=np.int32)
+        desc.costset_begin = as_int32_p(self.costset_begin)
+        desc.costs = C.cast(self.costs, C.POINTER(Cost))
+        desc.pool = as_double_p(self.pool)
+        desc.node_costset = as_int32_p(self.node_costset)
+        desc.n_costsets = len(self.costset_begin) - 1
+        desc.n_costs = len(self.costs)
+        desc.n_pool = len(self.pool)

@@ -44,6 +44,7 @@ def lib():
         L.empc_get_total_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.empc_get_launch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), abi.c_double_p]
         L.empc_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
+        L.empc_get_solve_stats.argtypes = [C.c_void_p, abi.c_double_p, C.POINTER(C.c_int64)]
         L.empc_phase_calc_diff.argtypes = [C.c_void_p, C.c_double]
         L.empc_phase_backward.argtypes = [C.c_void_p, C.c_double, C.c_int32, abi.c_int32_p]
         L.empc_phase_rollout.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32]
@@ -160,6 +161,22 @@ class BatchSolver:
         ms = np.zeros(4)
         _ck(lib().empc_get_launch_stats(self.h, C.byref(n), abi.as_double_p(ms)))
         return n.value, ms
+
+    def solve_stats(self):
+        """(device ms of the last solve, OCPs processed per kernel family summed over launches)"""
+        ms = np.zeros(1)
+        units = (C.c_int64 * 4)()
+        _ck(lib().empc_get_solve_stats(self.h, abi.as_double_p(ms), units))
+        return float(ms[0]), np.array(list(units), dtype=np.int64)
+
+    def get_into(self, name, ptr):
+        """empc_get_<name> into a caller-owned host buffer (e.g. pinned memory); ptr is an integer address"""
+        fn = getattr(lib(), "empc_get_" + name)
+        _ck(fn(self.h, C.cast(ptr, fn.argtypes[1])))
+
+    def set_x0_ptr(self, ptr):
+        """host pointer (e.g. pinned) to batch*nx doubles"""
+        _ck(lib().empc_set_x0(self.h, C.cast(ptr, abi.c_double_p)))
 
     # ---- phase hooks ----
     def phase_calc_diff(self, smooth):

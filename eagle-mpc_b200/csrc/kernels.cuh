@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(128) decide_kernel(Buffers bf, DecideParams dp
           }
         }
       }
-      if (st.phase != PHASE_DONE) atomicAdd(bf.n_active, 1);
+      if (st.phase != PHASE_DONE) { atomicAdd(bf.n_active, 1); if (st.recalc) atomicAdd(bf.n_active + 1, 1); }
       bf.st[b] = st;
     }
     s_acc = acc; s_last = last;
@@ -686,6 +686,13 @@ __global__ void squash_out_kernel(Buffers bf) {
   squash<D>(M, bf.st[b].smooth, u, s);
 #pragma unroll
   for (int i = 0; i < D::NU; ++i) bf.us_squash[(size_t)n * D::NU + i] = s[i];
+}
+
+// SolverAbstract::setCandidate with empty warm starts: xs[t] = state.zero(), us[t] = 0
+__global__ void zero_candidate_kernel(double* xs, size_t n_states, int nx) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_states * (size_t)nx) return;
+  xs[i] = ((int)(i % nx) == 6) ? 1.0 : 0.0;
 }
 
 __global__ void override_state_kernel(Buffers bf, double xreg, int is_feasible, int set_xreg) {

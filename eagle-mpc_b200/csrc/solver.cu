@@ -47,7 +47,10 @@ struct empc_solver {
   long long launches = 0, total_iterations = 0;
   int timing = 0;
   double ms_by_kernel[4] = {0, 0, 0, 0};
+  long long units_by_kernel[4] = {0, 0, 0, 0};  // OCPs processed by each kernel family, summed over launches
+  double solve_ms = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_solve[2] = {nullptr, nullptr};
 };
 
 template <class Tp>
@@ -106,6 +109,7 @@ int empc_destroy(empc_solver_t* h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_active) cudaFreeHost(h->h_active);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_solve) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return EMPC_OK;
@@ -161,8 +165,9 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   if (e != cudaSuccess) { delete h; return fail(EMPC_ERR_CUDA, cudaGetErrorString(e)); }
 #define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); empc_destroy(h); return fail(EMPC_ERR_CUDA, m_); } } while (0)
   const size_t B = batch, T = d->T, T1 = T + 1, nx = h->nx, tile = h->tile;
-  CKH(cudaMallocHost((void**)&h->h_active, sizeof(int)));
+  CKH(cudaMallocHost((void**)&h->h_active, 2 * sizeof(int)));
   for (auto& ev : h->ev) CKH(cudaEventCreate(&ev));
+  for (auto& ev : h->ev_solve) CKH(cudaEventCreate(&ev));
   CKH(dalloc(h, &h->d_model, 1));
   CKH(dalloc(h, &h->d_costs, (size_t)std::max(1, d->n_costs)));
   CKH(dalloc(h, &h->d_pool, (size_t)std::max(1, d->n_pool)));
@@ -196,7 +201,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   CKH(dalloc(h, &bf.dv, B * EMPC_N_ALPHAS));
   CKH(dalloc(h, &bf.ok, B * EMPC_N_ALPHAS));
   CKH(dalloc(h, &bf.us_squash, B * T * nu));
-  CKH(dalloc(h, &bf.n_active, 1));
+  CKH(dalloc(h, &bf.n_active, 2));
   bf.model = h->d_model; bf.ct.costs = h->d_costs; bf.ct.pool = h->d_pool; bf.ct.costset_begin = h->d_costset_begin;
   bf.node_costset = h->d_node_costset; bf.ocp_map = h->d_ocp_map; bf.x0 = h->d_x0;
   CKH(cudaMemcpyAsync(h->d_model, &M, sizeof(M), cudaMemcpyHostToDevice, h->stream));
@@ -244,9 +249,8 @@ int empc_set_candidate(empc_solver_t* h, const double* xs, const double* us, int
   const size_t nxs = (size_t)h->B * (h->T + 1) * h->nx, nus = (size_t)h->B * h->T * h->nu;
   if (xs) CK(cudaMemcpyAsync(h->d_xs_init, xs, sizeof(double) * nxs, cudaMemcpyHostToDevice, h->stream));
   else {
-    std::vector<double> z(nxs, 0.0);
-    for (size_t n = 0; n < nxs / h->nx; ++n) z[n * h->nx + 6] = 1.0;
-    CK(cudaMemcpy(h->d_xs_init, z.data(), sizeof(double) * nxs, cudaMemcpyHostToDevice));
+    zero_candidate_kernel<<<(unsigned)((nxs + 255) / 256), 256, 0, h->stream>>>(h->d_xs_init, nxs / h->nx, h->nx);
+    CK(cudaGetLastError());
   }
   if (us) CK(cudaMemcpyAsync(h->d_us_init, us, sizeof(double) * nus, cudaMemcpyHostToDevice, h->stream));
   else CK(cudaMemsetAsync(h->d_us_init, 0, sizeof(double) * nus, h->stream));
@@ -351,6 +355,9 @@ static int solve_impl(empc_solver* h) {
   if (D::TILE != h->tile) return fail(EMPC_ERR_INVALID, "tile size mismatch");
   h->launches = 0; h->total_iterations = 0;
   for (double& m : h->ms_by_kernel) m = 0;
+  for (long long& u : h->units_by_kernel) u = 0;
+  CK(cudaEventRecord(h->ev_solve[0], h->stream));
+  long long n_act = h->B, n_recalc = h->B;  // OCPs entering the next loop iteration
   init_state_kernel<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->bf, h->P, h->init_feasible, h->nx);
   h->launches++;
   CK(cudaGetLastError());
@@ -366,11 +373,13 @@ static int solve_impl(empc_solver* h) {
     if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
     CK(launch_rollout<D>(h, 0, 0, 0, 0.0));
     if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(cudaMemsetAsync(h->bf.n_active, 0, sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->bf.n_active, 0, 2 * sizeof(int), h->stream));
     CK(launch_decide<D>(h));
     if (h->timing) CK(cudaEventRecord(h->ev[4], h->stream));
-    CK(cudaMemcpyAsync(h->h_active, h->bf.n_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_active, h->bf.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->units_by_kernel[0] += n_recalc; h->units_by_kernel[1] += n_act; h->units_by_kernel[2] += n_act; h->units_by_kernel[3] += n_act;
+    n_act = h->h_active[0]; n_recalc = h->h_active[1];
     if (h->timing) {
       for (int k = 0; k < 4; ++k) { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1])); h->ms_by_kernel[k] += ms; }
     }
@@ -386,6 +395,7 @@ static int solve_impl(empc_solver* h) {
     if (*h->h_active == 0) break;
   }
   CK(launch_squash_out<D>(h));
+  CK(cudaEventRecord(h->ev_solve[1], h->stream));
   // total inner iterations over the batch
   std::vector<OcpState> st(h->B);
   CK(cudaMemcpyAsync(st.data(), h->bf.st, sizeof(OcpState) * h->B, cudaMemcpyDeviceToHost, h->stream));
@@ -393,6 +403,7 @@ static int solve_impl(empc_solver* h) {
   long long tot = 0;
   for (const OcpState& s : st) tot += s.total_iters;
   h->total_iterations = tot;
+  { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev_solve[0], h->ev_solve[1])); h->solve_ms = ms; }
   return EMPC_OK;
 }
 
@@ -477,6 +488,12 @@ int empc_get_launch_stats(const empc_solver_t* h, int64_t* launches, double* ms)
   if (!h) return fail(EMPC_ERR_INVALID, "null");
   if (launches) *launches = h->launches;
   if (ms) for (int k = 0; k < 4; ++k) ms[k] = h->ms_by_kernel[k];
+  return EMPC_OK;
+}
+int empc_get_solve_stats(const empc_solver_t* h, double* solve_ms, int64_t* units_by_kernel) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  if (solve_ms) *solve_ms = h->solve_ms;
+  if (units_by_kernel) for (int k = 0; k < 4; ++k) units_by_kernel[k] = h->units_by_kernel[k];
   return EMPC_OK;
 }
 int empc_enable_kernel_timing(empc_solver_t* h, int32_t on) {

@@ -1,0 +1,122 @@
+// host_capi.cpp — plain-C access to the host-side mirror (for the Python front-end / tests; no compute here).
+#include <cstring>
+#include <string>
+
+#include "eagle_mpc.hpp"
+
+using namespace eagle_mpc;
+
+static thread_local std::string g_err;
+#define GUARD(body, failret)            \
+  try { body }                          \
+  catch (const std::exception& e) { g_err = e.what(); return failret; }
+
+struct HostTrajectory { std::shared_ptr<Trajectory> traj; };
+struct HostFlat { std::shared_ptr<ShootingProblem> problem; FlatProblem flat; };
+struct HostSolver { std::shared_ptr<Trajectory> traj; std::shared_ptr<ShootingProblem> problem; std::unique_ptr<SolverSbFDDP> solver; };
+
+extern "C" {
+
+const char* empc_host_last_error(void) { return g_err.c_str(); }
+void empc_host_set_dirs(const char* yaml_dir, const char* robot_dir) {
+  if (yaml_dir) set_yaml_dir(yaml_dir);
+  if (robot_dir) set_robot_data_dir(robot_dir);
+}
+
+// ParserYaml -> "key\tvalue\n" dump (caller frees with empc_host_free_str)
+char* empc_host_parse_yaml(const char* path) {
+  GUARD({
+    ParserYaml p(getYamlPath(path));
+    std::string out;
+    for (auto& kv : p.get_params()) out += kv.first + "\t" + kv.second + "\n";
+    char* c = new char[out.size() + 1];
+    std::memcpy(c, out.c_str(), out.size() + 1);
+    return c;
+  }, nullptr)
+}
+void empc_host_free_str(char* s) { delete[] s; }
+
+void* empc_host_trajectory_create(const char* yaml_path) {
+  GUARD({
+    auto t = Trajectory::create();
+    t->autoSetup(getYamlPath(yaml_path));
+    return new HostTrajectory{t};
+  }, nullptr)
+}
+void empc_host_trajectory_free(void* t) { delete (HostTrajectory*)t; }
+int empc_host_trajectory_info(void* t, int32_t* out /* nq nv nu n_stages duration n_rotors */) {
+  auto& tr = ((HostTrajectory*)t)->traj;
+  out[0] = tr->get_robot_model()->nq; out[1] = tr->get_robot_model()->nv; out[2] = (int)tr->get_actuation_nu();
+  out[3] = (int)tr->get_stages().size(); out[4] = (int)tr->get_duration(); out[5] = (int)tr->get_platform_params()->n_rotors_;
+  return 0;
+}
+int empc_host_trajectory_platform(void* t, double* tau_f /* 6*n_rotors */, double* u_lb, double* u_ub) {
+  auto& pf = ((HostTrajectory*)t)->traj->get_platform_params();
+  std::copy(pf->tau_f_.begin(), pf->tau_f_.end(), tau_f);
+  std::copy(pf->u_lb.begin(), pf->u_lb.end(), u_lb);
+  std::copy(pf->u_ub.begin(), pf->u_ub.end(), u_ub);
+  return 0;
+}
+
+// createProblem + (optionally) SolverSbFDDP::barrierInit + flatten.  Returns a handle owning the POD description.
+void* empc_host_flatten(void* t, int32_t dt_ms, int32_t squash, const char* integrator, int32_t add_barrier) {
+  GUARD({
+    auto& tr = ((HostTrajectory*)t)->traj;
+    auto* hf = new HostFlat();
+    hf->problem = tr->createProblem((std::size_t)dt_ms, squash != 0, integrator);
+    if (add_barrier) sbfddp_barrier_init(*hf->problem, tr->get_squash()->get_ns(), 1e-3);
+    flatten_problem(*hf->problem, hf->flat);
+    return hf;
+  }, nullptr)
+}
+void empc_host_flat_free(void* f) { delete (HostFlat*)f; }
+const empc_problem_desc_t* empc_host_flat_desc(void* f) { return &((HostFlat*)f)->flat.desc; }
+int empc_host_flat_x0(void* f, double* x0) {
+  auto& p = ((HostFlat*)f)->problem;
+  std::copy(p->x0.begin(), p->x0.end(), x0);
+  return 0;
+}
+// names of the costs of cost set `s`, "\n"-separated, in evaluation order
+char* empc_host_flat_cost_names(void* f, int32_t s) {
+  auto* hf = (HostFlat*)f;
+  std::string out;
+  std::vector<std::string> names(hf->flat.slots[s].size());
+  const int base = hf->flat.costset_begin[s];
+  for (auto& kv : hf->flat.slots[s]) names[kv.second.cost_index - base] = kv.first;
+  for (auto& n : names) out += n + "\n";
+  char* c = new char[out.size() + 1];
+  std::memcpy(c, out.c_str(), out.size() + 1);
+  return c;
+}
+
+// ---- SolverSbFDDP facade (needs a GPU) ----
+void* empc_host_solver_create(void* t, int32_t dt_ms, int32_t squash, const char* integrator, int32_t batch, int32_t device) {
+  GUARD({
+    auto& tr = ((HostTrajectory*)t)->traj;
+    auto* hs = new HostSolver();
+    hs->traj = tr;
+    hs->problem = tr->createProblem((std::size_t)dt_ms, squash != 0, integrator);
+    hs->solver.reset(new SolverSbFDDP(hs->problem, tr->get_squash(), batch, device));
+    return hs;
+  }, nullptr)
+}
+void empc_host_solver_free(void* s) { delete (HostSolver*)s; }
+empc_solver_t* empc_host_solver_handle(void* s) { return ((HostSolver*)s)->solver->handle(); }
+int empc_host_solver_set_convergence_init(void* s, double c) { ((HostSolver*)s)->solver->set_convergence_init(c); return 0; }
+// solve([], [], maxiter) — the reference driver's call (examples/python/trajectory.py:26)
+int empc_host_solver_solve(void* s, int32_t maxiter) {
+  GUARD({ ((HostSolver*)s)->solver->solve({}, {}, (std::size_t)maxiter); return 0; }, 1)
+}
+int empc_host_solver_solve_batch(void* s, const double* x0, const double* xs, const double* us, int32_t maxiter) {
+  GUARD({ ((HostSolver*)s)->solver->solveBatch(x0, xs, us, (std::size_t)maxiter); return 0; }, 1)
+}
+int empc_host_solver_result(void* s, double* xs, double* us, double* us_squash, double* cost, int32_t* iter, int32_t* feasible) {
+  auto& sv = ((HostSolver*)s)->solver;
+  const auto& X = sv->get_xs(); const auto& U = sv->get_us(); const auto& S = sv->getSquashControls();
+  for (std::size_t t = 0; t < X.size(); ++t) std::copy(X[t].begin(), X[t].end(), xs + t * X[t].size());
+  for (std::size_t t = 0; t < U.size(); ++t) { std::copy(U[t].begin(), U[t].end(), us + t * U[t].size()); std::copy(S[t].begin(), S[t].end(), us_squash + t * S[t].size()); }
+  *cost = sv->get_cost(); *iter = (int)sv->get_iter(); *feasible = sv->get_is_feasible() ? 1 : 0;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+// sbfddp.cpp — SolverSbFDDP facade: same constructor / solve / setCandidate / getters as the reference
+// (include/eagle_mpc/sbfddp.hpp:39-52, src/sbfddp.cpp), with the whole iteration running in CUDA behind the C ABI.
+#include <cstring>
+
+#include "eagle_mpc.hpp"
+
+namespace eagle_mpc {
+
+static void ck(int rc, const char* what) {
+  if (rc != EMPC_OK) throw std::runtime_error(std::string(what) + ": " + empc_last_error());
+}
+
+SolverSbFDDP::SolverSbFDDP(const std::shared_ptr<ShootingProblem>& problem,
+                           const std::shared_ptr<SquashingModelSmoothSat>& squashing_model, int batch, int device)
+    : problem_(problem), squashing_model_(squashing_model), batch_(batch), device_(device) {
+  empc_default_params(&params_);
+  barrierInit();
+  flatten_problem(*problem_, flat_);
+  ck(empc_create(&flat_.desc, batch_, device_, &handle_), "empc_create");
+  const std::size_t T = problem_->get_T();
+  const std::size_t nx = (std::size_t)problem_->state->get_nx(), nu = squashing_model_->get_ns(), ndx = (std::size_t)problem_->state->get_ndx();
+  xs_.assign(T + 1, problem_->state->zero());
+  us_.assign(T, VectorXd(nu, 0.0));
+  us_squash_.assign(T, VectorXd(nu, 0.0));
+  k_.assign(T, VectorXd(nu, 0.0));
+  K_.assign(T, std::vector<double>(nu * ndx, 0.0));
+  syncX0();
+}
+
+SolverSbFDDP::~SolverSbFDDP() { if (handle_) empc_destroy(handle_); }
+
+// src/sbfddp.cpp:169-190: add the "barrier" cost (weight 1e-3) to every running model that does not have it yet.
+// One shared cost object; its activation weights follow the smoothing schedule on the device.
+void sbfddp_barrier_init(ShootingProblem& problem, std::size_t ns, double barrier_weight) {
+  auto barrier = std::make_shared<CostModelResidual>();
+  barrier->type = CostModelTypes::CostModelSquashBarrier;
+  barrier->activation.type = ActivationModelTypes::ActivationModelWeightedQuadraticBarrier;
+  barrier->activation.nr = ns;
+  for (auto& m : problem.runningModels) {
+    auto& costs = m->costs->get_costs();
+    if (costs.find("barrier") == costs.end()) m->costs->addCost("barrier", barrier, barrier_weight);
+  }
+}
+void SolverSbFDDP::barrierInit() { sbfddp_barrier_init(*problem_, squashing_model_->get_ns(), params_.barrier_weight); }
+
+void SolverSbFDDP::syncX0() {
+  const std::size_t nx = problem_->x0.size();
+  std::vector<double> x0((std::size_t)batch_ * nx);
+  for (int b = 0; b < batch_; ++b) std::copy(problem_->x0.begin(), problem_->x0.end(), x0.begin() + (std::size_t)b * nx);
+  ck(empc_set_x0(handle_, x0.data()), "empc_set_x0");
+}
+
+void SolverSbFDDP::pushCosts(int first, int n) {
+  ck(empc_update_costs(handle_, first, n, flat_.costs.data() + first, 0, (int)flat_.pool.size(), flat_.pool.data()), "empc_update_costs");
+}
+void SolverSbFDDP::pushAllCosts() { pushCosts(0, (int)flat_.costs.size()); }
+
+void SolverSbFDDP::setCandidate(const std::vector<VectorXd>& xs_warm, const std::vector<VectorXd>& us_warm, bool is_feasible) {
+  const std::size_t T = problem_->get_T(), nx = (std::size_t)problem_->state->get_nx(), nu = squashing_model_->get_ns();
+  std::vector<double> xs, us;
+  if (!xs_warm.empty()) {
+    if (xs_warm.size() != T + 1)
+      throw std::invalid_argument("Warm start state has wrong dimension, got " + std::to_string(xs_warm.size()) + " expecting " + std::to_string(T + 1));
+    xs.resize((std::size_t)batch_ * (T + 1) * nx);
+    for (int b = 0; b < batch_; ++b)
+      for (std::size_t t = 0; t <= T; ++t) std::copy(xs_warm[t].begin(), xs_warm[t].end(), xs.begin() + ((std::size_t)b * (T + 1) + t) * nx);
+  }
+  if (!us_warm.empty()) {
+    if (us_warm.size() != T)
+      throw std::invalid_argument("Warm start control has wrong dimension, got " + std::to_string(us_warm.size()) + " expecting " + std::to_string(T));
+    us.resize((std::size_t)batch_ * T * nu);
+    for (int b = 0; b < batch_; ++b)
+      for (std::size_t t = 0; t < T; ++t) std::copy(us_warm[t].begin(), us_warm[t].end(), us.begin() + ((std::size_t)b * T + t) * nu);
+  }
+  ck(empc_set_candidate(handle_, xs.empty() ? nullptr : xs.data(), us.empty() ? nullptr : us.data(), is_feasible ? 1 : 0), "empc_set_candidate");
+}
+
+void SolverSbFDDP::fetch(bool with_gains) {
+  const std::size_t T = problem_->get_T(), nx = (std::size_t)problem_->state->get_nx(), nu = squashing_model_->get_ns(),
+                    ndx = (std::size_t)problem_->state->get_ndx(), B = (std::size_t)batch_;
+  std::vector<double> buf(B * (T + 1) * nx);
+  ck(empc_get_xs(handle_, buf.data()), "empc_get_xs");
+  for (std::size_t t = 0; t <= T; ++t) xs_[t].assign(buf.begin() + t * nx, buf.begin() + (t + 1) * nx);
+  buf.resize(B * T * nu);
+  ck(empc_get_us(handle_, buf.data()), "empc_get_us");
+  for (std::size_t t = 0; t < T; ++t) us_[t].assign(buf.begin() + t * nu, buf.begin() + (t + 1) * nu);
+  ck(empc_get_us_squash(handle_, buf.data()), "empc_get_us_squash");
+  for (std::size_t t = 0; t < T; ++t) us_squash_[t].assign(buf.begin() + t * nu, buf.begin() + (t + 1) * nu);
+  if (with_gains) {
+    ck(empc_get_k(handle_, buf.data()), "empc_get_k");
+    for (std::size_t t = 0; t < T; ++t) k_[t].assign(buf.begin() + t * nu, buf.begin() + (t + 1) * nu);
+    buf.resize(B * T * nu * ndx);
+    ck(empc_get_K(handle_, buf.data()), "empc_get_K");
+    for (std::size_t t = 0; t < T; ++t) K_[t].assign(buf.begin() + t * nu * ndx, buf.begin() + (t + 1) * nu * ndx);
+  }
+  std::vector<double> c(B), s(B);
+  std::vector<int32_t> it(B), fe(B);
+  ck(empc_get_cost(handle_, c.data()), "empc_get_cost");
+  ck(empc_get_stop(handle_, s.data()), "empc_get_stop");
+  ck(empc_get_iters(handle_, it.data()), "empc_get_iters");
+  ck(empc_get_feasible(handle_, fe.data()), "empc_get_feasible");
+  cost_ = c[0]; stop_ = s[0]; iter_ = (std::size_t)it[0]; is_feasible_ = fe[0] != 0;
+}
+
+bool SolverSbFDDP::solve(const std::vector<VectorXd>& init_xs, const std::vector<VectorXd>& init_us, std::size_t maxiter,
+                         bool is_feasible, double /*regInit: ignored, src/sbfddp.cpp:196 vs :210*/) {
+  syncX0();
+  setCandidate(init_xs, init_us, is_feasible);
+  params_.maxiter = (int)maxiter;
+  ck(empc_set_params(handle_, &params_), "empc_set_params");
+  ck(empc_solve(handle_), "empc_solve");
+  fetch(true);
+  return true;  // the reference always returns true (src/sbfddp.cpp:225)
+}
+
+bool SolverSbFDDP::solveWarm(std::size_t maxiter) {
+  syncX0();
+  params_.maxiter = (int)maxiter;
+  ck(empc_set_params(handle_, &params_), "empc_set_params");
+  ck(empc_solve(handle_), "empc_solve");
+  fetch(false);
+  return true;
+}
+
+bool SolverSbFDDP::solveBatch(const double* x0, const double* xs, const double* us, std::size_t maxiter, bool is_feasible) {
+  if (x0) ck(empc_set_x0(handle_, x0), "empc_set_x0");
+  ck(empc_set_candidate(handle_, xs, us, is_feasible ? 1 : 0), "empc_set_candidate");
+  params_.maxiter = (int)maxiter;
+  ck(empc_set_params(handle_, &params_), "empc_set_params");
+  ck(empc_solve(handle_), "empc_solve");
+  fetch(false);
+  return true;
+}
+
+}  // namespace eagle_mpc

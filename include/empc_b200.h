@@ -196,6 +196,9 @@ int empc_get_total_iterations(const empc_solver_t* h, int64_t* total);
  * [0]=calc_diff [1]=backward [2]=rollout [3]=decide */
 int empc_get_launch_stats(const empc_solver_t* h, int64_t* launches, double* ms_by_kernel /* 4 or NULL */);
 int empc_enable_kernel_timing(empc_solver_t* h, int32_t on);
+/* device time of the last empc_solve (CUDA events on the solver's stream) and, per kernel family, the number of OCPs
+ * each launch processed summed over the launches (x T = node-iterations) */
+int empc_get_solve_stats(const empc_solver_t* h, double* solve_ms, int64_t* units_by_kernel /* 4 or NULL */);
 
 /* ---- tile-level parity hooks (one phase on the current candidate of every OCP) ---- */
 int empc_phase_calc_diff(empc_solver_t* h, double smooth);      /* calc + calcDiff + gaps */

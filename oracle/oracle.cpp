@@ -23,7 +23,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "oracle_model.hpp"
@@ -606,6 +609,36 @@ int orc_get(void* h, const char* name, double* out) {
   else if (n == "feasible") out[0] = s->is_feasible ? 1.0 : 0.0;
   else return 1;
   return 0;
+}
+
+// Solves `n` OCPs of the same problem (different x0, zero initial guess) on `nthreads` host threads, one OCP per
+// thread at a time — the execution model of the reference (single-threaded solver) replicated across cores.
+// Returns wall seconds; iters_out[i] = iterations executed by OCP i (iter_+1), cost_out[i] its final cost.
+double orc_solve_batch(const empc_problem_desc_t* d, const empc_solver_params_t* p, const double* x0, int n, int nthreads,
+                       int32_t* iters_out, double* cost_out) {
+  if (nthreads < 1) nthreads = 1;
+  std::vector<Solver*> solvers(nthreads);
+  for (int t = 0; t < nthreads; ++t) { solvers[t] = new Solver(); solvers[t]->P = *p; solvers[t]->init(d); }
+  const int nx = solvers[0]->m.nx;
+  std::atomic<int> next(0);
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([&, t]() {
+      Solver* s = solvers[t];
+      for (;;) {
+        const int i = next.fetch_add(1);
+        if (i >= n) break;
+        std::memcpy(s->x0.data(), x0 + (size_t)i * nx, sizeof(double) * nx);
+        s->solve(nullptr, nullptr, s->P.maxiter, false);
+        if (iters_out) iters_out[i] = s->iter + 1;
+        if (cost_out) cost_out[i] = s->cost;
+      }
+    });
+  for (auto& x : th) x.join();
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (Solver* s : solvers) delete s;
+  return sec;
 }
 
 // ---- math unit-test exports ----

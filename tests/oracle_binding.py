@@ -25,6 +25,9 @@ def _load():
     lib.orc_phase_backward.argtypes = [C.c_void_p, C.c_double, C.c_int]
     lib.orc_phase_rollout.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
     lib.orc_node_eval.argtypes = [C.c_void_p, C.c_int, C.c_double] + [abi.c_double_p] * 6
+    lib.orc_solve_batch.restype = C.c_double
+    lib.orc_solve_batch.argtypes = [C.POINTER(abi.ProblemDesc), C.POINTER(abi.SolverParams), abi.c_double_p, C.c_int, C.c_int,
+                                    abi.c_int32_p, abi.c_double_p]
     return lib
 
 
@@ -35,6 +38,16 @@ def default_params():
     p = abi.SolverParams()
     lib.orc_default_params(C.byref(p))
     return p
+
+
+def solve_batch(holder, x0, nthreads=1, params=None):
+    """(seconds, iterations per OCP, final costs) of the CPU oracle over a batch of initial states."""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n = x0.shape[0]
+    p = params or default_params()
+    iters = np.zeros(n, dtype=np.int32); cost = np.zeros(n)
+    sec = lib.orc_solve_batch(C.byref(holder.desc), C.byref(p), dp(x0), n, nthreads, abi.as_int32_p(iters), dp(cost))
+    return sec, iters, cost
 
 
 class Oracle:
