@@ -10,7 +10,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libempc_b200.so")
+LIB_PATH = os.environ.get("EMPC_LIB", os.path.join(_HERE, "lib", "libempc_b200.so"))
 _lib = None
 
 

@@ -47,8 +47,11 @@ struct Buffers {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef EMPC_CD_MINB
+#define EMPC_CD_MINB 4
+#endif
 template <class D>
-__global__ void __launch_bounds__(128) calc_diff_kernel(Buffers bf, int force, double force_smooth) {
+__global__ void __launch_bounds__(128, EMPC_CD_MINB) calc_diff_kernel(Buffers bf, int force, double force_smooth) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int T1 = bf.T + 1;
   if (n >= bf.B * T1) return;
@@ -114,320 +117,7 @@ __global__ void __launch_bounds__(128) calc_diff_kernel(Buffers bf, int force, d
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Warp-cooperative small dense products on shared memory.  C (M x N, ld ldc) (+)= opA(A) (M x K) * B (K x N).
-// TA: A is stored K x M (use A^T).  Each lane owns RT x CT register tiles, accumulating over k in ascending order
-// (the same summation order as the scalar reference loops).
-template <int M_, int N_, int K_, int RT, int CT, bool TA, bool ACC, bool NEG>
-EMPC_DI void warp_mm(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda,
-                     const double* __restrict__ Bm, int ldb, int lane) {
-  constexpr int TM = (M_ + RT - 1) / RT, TN = (N_ + CT - 1) / CT;
-  for (int tile = lane; tile < TM * TN; tile += 32) {
-    const int i0 = (tile / TN) * RT, j0 = (tile % TN) * CT;
-    double acc[RT][CT];
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
-#pragma unroll
-      for (int c = 0; c < CT; ++c) acc[r][c] = 0.0;
-#pragma unroll 2
-    for (int k = 0; k < K_; ++k) {
-      double a[RT], bv[CT];
-#pragma unroll
-      for (int r = 0; r < RT; ++r) a[r] = (i0 + r < M_) ? (TA ? A[k * lda + i0 + r] : A[(i0 + r) * lda + k]) : 0.0;
-#pragma unroll
-      for (int c = 0; c < CT; ++c) bv[c] = (j0 + c < N_) ? Bm[k * ldb + j0 + c] : 0.0;
-#pragma unroll
-      for (int r = 0; r < RT; ++r)
-#pragma unroll
-        for (int c = 0; c < CT; ++c) acc[r][c] += a[r] * bv[c];
-    }
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
-#pragma unroll
-      for (int c = 0; c < CT; ++c)
-        if (i0 + r < M_ && j0 + c < N_) {
-          double* p = &C[(i0 + r) * ldc + j0 + c];
-          if (ACC) *p = NEG ? (*p - acc[r][c]) : (*p + acc[r][c]);
-          else *p = NEG ? -acc[r][c] : acc[r][c];
-        }
-  }
-}
-
-template <class D>
-struct BwSmem {
-  static constexpr int NDX = D::NDX, NU = D::NU;
-  // per-warp layout (doubles)
-  static constexpr int oTile = 0;
-  static constexpr int oV = oTile + D::TILE;         // Vxx' (NDX x NDX)
-  static constexpr int oFxTV = oV + NDX * NDX;        // Fx^T Vxx'  (later: Vxx_t scratch)
-  static constexpr int oFuTV = oFxTV + NDX * NDX;     // Fu^T Vxx'
-  static constexpr int oK = oFuTV + NU * NDX;         // K (NU x NDX)
-  static constexpr int oVx = oK + NU * NDX;           // Vx' (NDX)
-  static constexpr int oVec = oVx + NDX;              // k(NU) Quuk(NU) fs(NDX) g(NDX) tmp(NDX)
-  static constexpr int TOTAL0 = oVec + 2 * NU + 3 * NDX;
-  static constexpr int TOTAL = TOTAL0 + (TOTAL0 & 1);
-};
-
-struct BwParams {
-  double reg_max, reg_factor, th_gaptol;
-  int force;          // phase hook: single attempt, take xreg / is_feasible from state as they are, no prologue
-};
-
-template <class D>
-__global__ void __launch_bounds__(128) backward_kernel(Buffers bf, BwParams P) {
-  constexpr int NDX = D::NDX, NU = D::NU, NX = D::NX;
-  using S = BwSmem<D>;
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int b = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (b >= bf.B) return;
-  double* sm = smem + (size_t)wib * S::TOTAL;
-  OcpState st = bf.st[b];
-  if (!P.force && st.phase == PHASE_DONE) return;
-  const int T = bf.T, T1 = T + 1;
-  const size_t nb = (size_t)b * T1;
-
-  // ---- prologue: SolverDDP::calcDiff tail — cost_ = sum of node costs (in node order), feasibility from the gaps ----
-  if (!P.force && st.recalc) {
-    double* tmp = sm;  // reuse the per-warp region as staging, in chunks
-    double c = 0;
-    for (int base = 0; base < T1; base += S::TOTAL) {
-      const int cnt = min(S::TOTAL, T1 - base);
-      for (int t = lane; t < cnt; t += 32) tmp[t] = bf.node_cost[nb + base + t];
-      __syncwarp();
-      if (lane == 0) for (int t = 0; t < cnt; ++t) c += tmp[t];
-      __syncwarp();
-    }
-    st.cost = __shfl_sync(0xffffffffu, c, 0);
-    if (!st.is_feasible) {
-      double gi = 0, g1 = 0; int has_nan = 0;
-      for (int t = lane; t < T1; t += 32) { const double a = bf.gap_inf[nb + t]; if (isnan(a)) has_nan = 1; gi = fmax(gi, a); g1 += bf.gap_l1[nb + t]; }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { gi = fmax(gi, __shfl_xor_sync(0xffffffffu, gi, o)); g1 += __shfl_xor_sync(0xffffffffu, g1, o); has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o); }
-      st.gap_inf = has_nan ? nan("") : gi; st.gap_l1 = g1;
-      st.is_feasible = (!has_nan && gi < P.th_gaptol) ? 1 : 0;
-    } else if (!st.was_feasible) {
-      st.gap_inf = 0; st.gap_l1 = 0;
-    }
-    __syncwarp();
-  }
-  const int feasible = st.is_feasible;
-
-  double* tile = sm + S::oTile;
-  double* V = sm + S::oV;
-  double* FxTV = sm + S::oFxTV;
-  double* FuTV = sm + S::oFuTV;
-  double* Kt = sm + S::oK;
-  double* Vxp = sm + S::oVx;
-  double* kv = sm + S::oVec;
-  double* Quuk = kv + NU;
-  double* fsv = Quuk + NU;
-  double* gv = fsv + NDX;
-  double* tmpv = gv + NDX;
-  double* Fx = tile + D::oFx; double* Fu = tile + D::oFu; double* Qxx = tile + D::oLxx; double* Qxu = tile + D::oLxu;
-  double* Quu = tile + D::oLuu; double* Qx = tile + D::oLx; double* Qu = tile + D::oLu;
-
-  int failed;
-  while (true) {
-    failed = 0;
-    const double xreg = st.xreg;
-    // terminal node: Vxx = Lxx + xreg I ; Vx = Lx (+ Vxx fs)
-    {
-      const double* tg = bf.tiles + (nb + T) * D::TILE;
-      for (int i = lane; i < NDX * NDX; i += 32) V[i] = tg[D::oLxx + i];
-      for (int i = lane; i < NDX; i += 32) { Vxp[i] = tg[D::oLx + i]; fsv[i] = bf.fs[(nb + T) * NDX + i]; }
-      __syncwarp();
-      for (int i = lane; i < NDX; i += 32) V[i * NDX + i] += xreg;
-      __syncwarp();
-      for (int i = lane; i < NDX; i += 32) {
-        double s = 0;
-        for (int j = 0; j < NDX; ++j) s += V[i * NDX + j] * fsv[j];
-        gv[i] = s;
-      }
-      __syncwarp();
-      if (!feasible) for (int i = lane; i < NDX; i += 32) Vxp[i] += gv[i];
-      __syncwarp();
-      // per-node scalars: [Qu.k, k.Quuk, Vx.fs, fs.Vxx fs]
-      double a = 0, c = 0;
-      for (int i = lane; i < NDX; i += 32) { a += Vxp[i] * fsv[i]; c += fsv[i] * gv[i]; }
-      // ordered (sequential) dot products keep the reference summation order
-      if (lane == 0) {
-        double s0 = 0, s1 = 0;
-        for (int i = 0; i < NDX; ++i) { s0 += Vxp[i] * fsv[i]; s1 += fsv[i] * gv[i]; }
-        double* ns = bf.nodesc + (nb + T) * 4;
-        ns[0] = 0; ns[1] = 0; ns[2] = s0; ns[3] = s1;
-      }
-      (void)a; (void)c;
-      for (int i = lane; i < NDX; i += 32) { bf.Vx[(nb + T) * NDX + i] = Vxp[i]; bf.g[(nb + T) * NDX + i] = gv[i]; }
-      __syncwarp();
-    }
-    for (int t = T - 1; t >= 0; --t) {
-      // stage the node tile in shared memory (coalesced)
-      {
-        const double2* tg = reinterpret_cast<const double2*>(bf.tiles + (nb + t) * D::TILE);
-        double2* ts = reinterpret_cast<double2*>(tile);
-        for (int i = lane; i < D::TILE / 2; i += 32) ts[i] = tg[i];
-        for (int i = lane; i < NDX; i += 32) fsv[i] = bf.fs[(nb + t) * NDX + i];
-      }
-      __syncwarp();
-      // FxTV = Fx^T V ; FuTV = Fu^T V
-      warp_mm<NDX, NDX, NDX, 3, 3, true, false, false>(FxTV, NDX, Fx, NDX, V, NDX, lane);
-      warp_mm<NU, NDX, NDX, 3, 3, true, false, false>(FuTV, NDX, Fu, NU, V, NDX, lane);
-      // Qx += Fx^T Vx' ; Qu += Fu^T Vx'
-      for (int i = lane; i < NDX + NU; i += 32) {
-        double s = 0;
-        if (i < NDX) { for (int l = 0; l < NDX; ++l) s += Fx[l * NDX + i] * Vxp[l]; Qx[i] += s; }
-        else { const int ii = i - NDX; for (int l = 0; l < NDX; ++l) s += Fu[l * NU + ii] * Vxp[l]; Qu[ii] += s; }
-      }
-      __syncwarp();
-      // Qxx += FxTV Fx ; Qxu += FxTV Fu ; Quu += FuTV Fu (+ ureg)
-      warp_mm<NDX, NDX, NDX, 3, 3, false, true, false>(Qxx, NDX, FxTV, NDX, Fx, NDX, lane);
-      warp_mm<NDX, NU, NDX, 3, 3, false, true, false>(Qxu, NU, FxTV, NDX, Fu, NU, lane);
-      warp_mm<NU, NU, NDX, 3, 3, false, true, false>(Quu, NU, FuTV, NDX, Fu, NU, lane);
-      __syncwarp();
-      for (int i = lane; i < NU; i += 32) Quu[i * NU + i] += xreg;
-      __syncwarp();
-      // Quuk needs the un-factorised Quu: keep a copy of Quu in FuTV (free from here on)
-      double* L = FuTV;
-      for (int i = lane; i < NU * NU; i += 32) L[i] = Quu[i];
-      __syncwarp();
-      // Cholesky (right-looking; subtraction order equals the scalar left-looking loop)
-      for (int j = 0; j < NU; ++j) {
-        const double djj = L[j * NU + j];
-        if (!(djj > 0.0)) failed = 1;
-        const double d = sqrt(djj);
-        __syncwarp();
-        if (lane == 0) L[j * NU + j] = d;
-        for (int i = j + 1 + lane; i < NU; i += 32) L[i * NU + j] = L[i * NU + j] / d;
-        __syncwarp();
-        const int rem = NU - j - 1;
-        for (int idx = lane; idx < rem * rem; idx += 32) {
-          const int i = j + 1 + idx / rem, kk = j + 1 + idx % rem;
-          if (kk <= i) L[i * NU + kk] -= L[i * NU + j] * L[kk * NU + j];
-        }
-        __syncwarp();
-      }
-      if (failed) break;
-      // K = Quu^-1 Qxu^T (one right-hand side per lane), k = Quu^-1 Qu
-      for (int c = lane; c < NDX + 1; c += 32) {
-        double rhs[NU];
-        if (c < NDX) {
-#pragma unroll
-          for (int i = 0; i < NU; ++i) rhs[i] = Qxu[c * NU + i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < NU; ++i) rhs[i] = Qu[i];
-        }
-#pragma unroll
-        for (int i = 0; i < NU; ++i) {
-          double s = rhs[i];
-#pragma unroll
-          for (int kk = 0; kk < i; ++kk) s -= L[i * NU + kk] * rhs[kk];
-          rhs[i] = s / L[i * NU + i];
-        }
-#pragma unroll
-        for (int i = NU - 1; i >= 0; --i) {
-          double s = rhs[i];
-#pragma unroll
-          for (int kk = i + 1; kk < NU; ++kk) s -= L[kk * NU + i] * rhs[kk];
-          rhs[i] = s / L[i * NU + i];
-        }
-        if (c < NDX) {
-#pragma unroll
-          for (int i = 0; i < NU; ++i) Kt[i * NDX + c] = rhs[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < NU; ++i) kv[i] = rhs[i];
-        }
-      }
-      __syncwarp();
-      // Quuk = Quu k
-      for (int i = lane; i < NU; i += 32) {
-        double s = 0;
-        for (int j = 0; j < NU; ++j) s += Quu[i * NU + j] * kv[j];
-        Quuk[i] = s;
-      }
-      __syncwarp();
-      // Vx = Qx + K^T Quuk - 2 K^T Qu ; Vxx = Qxx - Qxu K
-      for (int i = lane; i < NDX; i += 32) {
-        double s1 = 0, s2 = 0;
-        for (int j = 0; j < NU; ++j) { s1 += Kt[j * NDX + i] * Quuk[j]; s2 += Kt[j * NDX + i] * Qu[j]; }
-        tmpv[i] = Qx[i] + s1 - 2 * s2;
-      }
-      warp_mm<NDX, NDX, NU, 3, 3, false, true, true>(Qxx, NDX, Qxu, NU, Kt, NDX, lane);
-      __syncwarp();
-      // symmetrise + xreg -> V
-      for (int idx = lane; idx < NDX * NDX; idx += 32) {
-        const int i = idx / NDX, j = idx - i * NDX;
-        const int lo = i < j ? i : j, hi = i < j ? j : i;
-        double a = 0.5 * (Qxx[lo * NDX + hi] + Qxx[hi * NDX + lo]);
-        if (i == j) a += xreg;
-        V[idx] = a;
-      }
-      __syncwarp();
-      for (int i = lane; i < NDX; i += 32) {
-        double s = 0;
-        for (int j = 0; j < NDX; ++j) s += V[i * NDX + j] * fsv[j];
-        gv[i] = s;
-      }
-      __syncwarp();
-      for (int i = lane; i < NDX; i += 32) Vxp[i] = feasible ? tmpv[i] : (tmpv[i] + gv[i]);
-      __syncwarp();
-      // NaN guard ("backward_error")
-      {
-        int bad = 0;
-        for (int i = lane; i < NDX * NDX; i += 32) if (isnan(V[i])) bad = 1;
-        for (int i = lane; i < NDX; i += 32) if (isnan(Vxp[i])) bad = 1;
-        if (__any_sync(0xffffffffu, bad)) { failed = 1; break; }
-      }
-      // outputs
-      {
-        double* Kg = bf.K + ((size_t)b * T + t) * NU * NDX;
-        for (int i = lane; i < NU * NDX; i += 32) Kg[i] = Kt[i];
-        double* kg = bf.k + ((size_t)b * T + t) * NU;
-        for (int i = lane; i < NU; i += 32) kg[i] = kv[i];
-        for (int i = lane; i < NDX; i += 32) { bf.Vx[(nb + t) * NDX + i] = Vxp[i]; bf.g[(nb + t) * NDX + i] = gv[i]; }
-        if (lane == 0) {
-          double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-          for (int i = 0; i < NU; ++i) { s0 += Qu[i] * kv[i]; s1 += kv[i] * Quuk[i]; }
-          for (int i = 0; i < NDX; ++i) { s2 += Vxp[i] * fsv[i]; s3 += fsv[i] * gv[i]; }
-          double* ns = bf.nodesc + (nb + t) * 4;
-          ns[0] = s0; ns[1] = s1; ns[2] = s2; ns[3] = s3;
-        }
-      }
-      __syncwarp();
-    }
-    failed = __any_sync(0xffffffffu, failed);
-    if (!failed || P.force) break;
-    // computeDirection threw: recalcDiff = false; increaseRegularization(); give up at reg_max (src/sbfddp.cpp:245-253)
-    st.xreg *= P.reg_factor;
-    if (st.xreg > P.reg_max) st.xreg = P.reg_max;
-    if (st.xreg == P.reg_max) break;
-  }
-  st.bw_fail = failed ? 1 : 0;
-  // SolverFDDP::updateExpectedImprovement / expectedImprovementDDP: ordered sums over the nodes
-  if (!failed) {
-    double* tmp = sm;
-    double dg = 0, dq = 0, dg0 = 0, dq0 = 0;
-    if (!feasible && lane == 0) { dg -= bf.nodesc[(nb + T) * 4 + 2]; dq += bf.nodesc[(nb + T) * 4 + 3]; }
-    constexpr int CH = S::TOTAL / 4;
-    for (int base = 0; base < T; base += CH) {
-      const int cnt = min(CH, T - base);
-      for (int i = lane; i < cnt * 4; i += 32) tmp[i] = bf.nodesc[(nb + base) * 4 + i];
-      __syncwarp();
-      if (lane == 0) {
-        for (int t = 0; t < cnt; ++t) {
-          dg += tmp[t * 4 + 0]; dq -= tmp[t * 4 + 1];
-          dg0 += tmp[t * 4 + 0]; dq0 -= tmp[t * 4 + 1];
-          if (!feasible) { dg -= tmp[t * 4 + 2]; dq += tmp[t * 4 + 3]; }
-        }
-      }
-      __syncwarp();
-    }
-    if (lane == 0) { st.dg = dg; st.dq = dq; st.dg0 = dg0; st.dq0 = dq0; }
-  }
-  if (lane == 0) bf.st[b] = st;
-}
+#include "backward.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------------
 struct RoParams {
@@ -436,7 +126,7 @@ struct RoParams {
 };
 
 template <class D>
-__global__ void __launch_bounds__(128) rollout_kernel(Buffers bf, RoParams P) {
+__global__ void __launch_bounds__(32, 9) rollout_kernel(Buffers bf, RoParams P) {
   constexpr int NX = D::NX, NDX = D::NDX, NU = D::NU;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= bf.B * EMPC_N_ALPHAS) return;

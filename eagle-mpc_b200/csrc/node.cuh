@@ -22,6 +22,7 @@ struct DevModel {
   double dt;
   double jR[EMPC_MAX_JOINTS][9], jp[EMPC_MAX_JOINTS][3], axis[EMPC_MAX_JOINTS][3];
   double Y[EMPC_MAX_JOINTS][36];  // body spatial inertia in the joint frame
+  double mass[EMPC_MAX_JOINTS], com[EMPC_MAX_JOINTS][3], Ic[EMPC_MAX_JOINTS][9];  // same, as (m, c, I_c)
   double a0[6];                   // -gravity (spatial)
   int frame_joint[EMPC_MAX_FRAMES];
   double fR[EMPC_MAX_FRAMES][9], fp[EMPC_MAX_FRAMES][3];
@@ -250,16 +251,30 @@ EMPC_DI void squash(const DevModel& M, double smooth, const double* u, double* s
   }
 }
 
-// pinocchio::aba for free-flyer + serial revolute chain (local-frame three-pass recursion)
+// Rigid-body inertia (m, c, I_c) applied to a motion: [f;n] = Y [v;w]  (pinocchio::InertiaTpl::__mult__)
+EMPC_DI void inertia_apply(double m, const double* c, const double* Ic, const double* v, double* o) {
+  double cxw[3], f[3], Iw[3], cxf[3];
+  cross3(c, v + 3, cxw);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) f[i] = m * (v[i] - cxw[i]);
+  matvec3(Ic, v + 3, Iw);
+  cross3(c, f, cxf);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { o[i] = f[i]; o[3 + i] = Iw[i] + cxf[i]; }
+}
+
+// pinocchio::aba for free-flyer + serial revolute chain (local-frame three-pass recursion).
+// The backward pass carries ONE articulated inertia (the contribution of the subtree, expressed in the current joint
+// frame) instead of one per joint, so the working set stays in registers.
 template <class D>
 EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData<D>& nd) {
   constexpr int NJ = D::NJ, NV = D::NV;
-  double Ia[NJ][36], pA[NJ][6], uu[NV];
-  double U[NJ][6], Dinv[NJ], UDinv[NJ][6];
+  double uu[NV];
+  double Dinv[NJ], UDinv[NJ][6];
 #pragma unroll
   for (int i = 0; i < NV; ++i) uu[i] = tau[i];
   const double* vq = x + D::NQ;
-  // pass 1
+  // pass 1: placements, velocities, bias accelerations
   q_to_se3(x, nd.li[0]);
   nd.oM[0] = nd.li[0];
 #pragma unroll
@@ -282,43 +297,105 @@ EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData
     for (int k = 0; k < 6; ++k) nd.v[i][k] = vJ[k] + vp[k];
     cross_mm(nd.v[i], vJ, nd.agf[i]);
   }
-#pragma unroll 1
-  for (int i = 0; i < NJ; ++i) {
+  // pass 2: tip to base with ONE running articulated inertia, kept as 3x3 blocks Ia = [[A, B],[B^T, C]] and moved to
+  // the parent frame with the block form of X* Ia X*^T (X* = [[R,0],[[p]x R, R]]):
+  //   A' = R A R^T,  B' = R B R^T - A'[p]x,  C' = R C R^T + [p]x B' - (R B R^T)^T [p]x
+  double A[9], Bk[9], C[9], pA[6];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) Ia[i][k] = M.Y[i][k];
-    double h[6]; mat6_vec(Ia[i], nd.v[i], h);
-    cross_mf(nd.v[i], h, pA[i]);
-  }
-  // pass 2
+  for (int k = 0; k < 9; ++k) { A[k] = 0.0; Bk[k] = 0.0; C[k] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) pA[k] = 0.0;
 #pragma unroll 1
   for (int i = NJ - 1; i >= 1; --i) {
-    const double S[6] = {0, 0, 0, M.axis[i][0], M.axis[i][1], M.axis[i][2]};
+    {  // Ia += Y_i ; pA += v x* (Y v)
+      double h[6], vh[6];
+      inertia_apply(M.mass[i], M.com[i], M.Ic[i], nd.v[i], h);
+      cross_mf(nd.v[i], h, vh);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          A[3 * a + b] += M.Y[i][6 * a + b]; Bk[3 * a + b] += M.Y[i][6 * a + 3 + b]; C[3 * a + b] += M.Y[i][6 * (3 + a) + 3 + b];
+        }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) pA[k] += vh[k];
+    }
+    const double ax[3] = {M.axis[i][0], M.axis[i][1], M.axis[i][2]};
     const int c = 5 + i;
-    uu[c] -= dot6(S, pA[i]);
-    mat6_vec(Ia[i], S, U[i]);
-    Dinv[i] = 1.0 / dot6(S, U[i]);
+    uu[c] -= ax[0] * pA[3] + ax[1] * pA[4] + ax[2] * pA[5];
+    double U[6];  // U = Ia S, S = [0; ax]
+    matvec3(Bk, ax, U); matvec3(C, ax, U + 3);
+    Dinv[i] = 1.0 / dot3(ax, U + 3);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) UDinv[i][k] = U[i][k] * Dinv[i];
+    for (int k = 0; k < 6; ++k) UDinv[i][k] = U[k] * Dinv[i];
 #pragma unroll
-    for (int a = 0; a < 6; ++a)
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int b = 0; b < 6; ++b) Ia[i][6 * a + b] -= UDinv[i][a] * U[i][b];
-    double pa[6], Iac[6];
-    mat6_vec(Ia[i], nd.agf[i], Iac);
+      for (int b = 0; b < 3; ++b) {
+        A[3 * a + b] -= UDinv[i][a] * U[b];
+        Bk[3 * a + b] -= UDinv[i][a] * U[3 + b];
+        C[3 * a + b] -= UDinv[i][3 + a] * U[3 + b];
+      }
+    double pa[6];
+    {  // pa = pA + Ia c_i + UDinv u_i
+      const double* cv = nd.agf[i];
+      double t1[3], t2[3], t3[3], t4[3];
+      matvec3(A, cv, t1); matvec3(Bk, cv + 3, t2); matTvec3(Bk, cv, t3); matvec3(C, cv + 3, t4);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) pa[k] = pA[i][k] + Iac[k] + UDinv[i][k] * uu[c];
-    double X[36], Ip[36], fp[6];
-    force_action_matrix(nd.li[i], X);
-    congruence6(X, Ia[i], Ip);
+      for (int k = 0; k < 3; ++k) {
+        pa[k] = pA[k] + t1[k] + t2[k] + UDinv[i][k] * uu[c];
+        pa[3 + k] = pA[3 + k] + t3[k] + t4[k] + UDinv[i][3 + k] * uu[c];
+      }
+    }
+    {  // carry to the parent frame
+      const double* R = nd.li[i].R; const double* p = nd.li[i].p;
+      double T1[9], An[9], Bt[9], Cn[9], P[9];
+      matmul3(R, A, T1);
 #pragma unroll
-    for (int k = 0; k < 36; ++k) Ia[i - 1][k] += Ip[k];
-    act_force(nd.li[i], pa, fp);
+      for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) pA[i - 1][k] += fp[k];
+        for (int b = 0; b < 3; ++b) An[3 * a + b] = T1[3 * a] * R[3 * b] + T1[3 * a + 1] * R[3 * b + 1] + T1[3 * a + 2] * R[3 * b + 2];
+      matmul3(R, Bk, T1);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Bt[3 * a + b] = T1[3 * a] * R[3 * b] + T1[3 * a + 1] * R[3 * b + 1] + T1[3 * a + 2] * R[3 * b + 2];
+      matmul3(R, C, T1);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Cn[3 * a + b] = T1[3 * a] * R[3 * b] + T1[3 * a + 1] * R[3 * b + 1] + T1[3 * a + 2] * R[3 * b + 2];
+      skew3(p, P);
+      double AP[9], Bn[9], PB[9], BtP[9];
+      matmul3(An, P, AP);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Bn[k] = Bt[k] - AP[k];
+      matmul3(P, Bn, PB);
+      matTmul3(Bt, P, BtP);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { A[k] = An[k]; Bk[k] = Bn[k]; C[k] = Cn[k] + PB[k] - BtP[k]; }
+      act_force(nd.li[i], pa, pA);
+    }
   }
+  double Ia[36];
+  {  // root (free-flyer): Ia0 = Y_0 + children, D = Ia0
+    double h[6], vh[6];
+    inertia_apply(M.mass[0], M.com[0], M.Ic[0], nd.v[0], h);
+    cross_mf(nd.v[0], h, vh);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) uu[k] -= pA[0][k];
-  llt_inplace<6>(Ia[0]);
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        Ia[6 * a + b] = A[3 * a + b] + M.Y[0][6 * a + b];
+        Ia[6 * a + 3 + b] = Bk[3 * a + b] + M.Y[0][6 * a + 3 + b];
+        Ia[6 * (3 + a) + b] = Bk[3 * b + a] + M.Y[0][6 * (3 + a) + b];
+        Ia[6 * (3 + a) + 3 + b] = C[3 * a + b] + M.Y[0][6 * (3 + a) + 3 + b];
+      }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) uu[k] -= pA[k] + vh[k];
+  }
+  double Iinv[6];
+  llt_inplace_inv<6>(Ia, Iinv);
   // pass 3
   {
     double g[6]; actinv_motion(nd.oM[0], M.a0, g);
@@ -327,7 +404,7 @@ EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData
     double rhs[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) rhs[k] = uu[k];
-    llt_solve_vec<6>(Ia[0], rhs, 1);
+    llt_solve_vec_inv<6>(Ia, Iinv, rhs, 1);
 #pragma unroll
     for (int k = 0; k < 6; ++k) { nd.a[k] = rhs[k] - nd.agf[0][k]; }
 #pragma unroll
@@ -380,12 +457,15 @@ EMPC_DI void node_calc(const DevModel& M, const CostTables& C, int costset, doub
   cost = dt * csum;
 }
 
-// world-frame RNEA-derivative recursion + Minv (DESIGN.md "ABA derivatives"); outputs a_q, a_v (NV x NV), Minv, Jc.
+// world-frame RNEA-derivative recursion + Minv (DESIGN.md "ABA derivatives"); outputs a_q, a_v (NV x NV), Minv, Jc, ov.
+// Tip-to-base sweep with running composite quantities of the subtree: rigid-body inertia Ycrb (m, m c, I_o: 13
+// numbers), subtree force Fcrb, and the composite "B" operator, which reduces to a momentum vector hf and one 3x3
+// block G because  B_i = crf(v_i) Y_i - Y_i crm(v_i) + Hx(h_i) = [[0, -2[hf_i]x],[0, G_i]].
 template <class D>
 EMPC_DI void aba_derivatives(const DevModel& M, const NodeData<D>& nd, double (*Jc)[6], double (*ov)[6], double* a_q,
                              double* a_v, double* Minv) {
-  constexpr int NJ = D::NJ, NV = D::NV;
-  double oY[NJ][36], Bm[NJ][36], F[NJ][6], oa[NJ][6];
+  constexpr int NJ = D::NJ, NV = D::NV, NA = D::NA;
+  double oa[NJ][6];
 #pragma unroll 1
   for (int i = 0; i < NJ; ++i) {
     if (i == 0) {
@@ -405,104 +485,121 @@ EMPC_DI void aba_derivatives(const DevModel& M, const NodeData<D>& nd, double (*
     }
     act_motion(nd.oM[i], nd.v[i], ov[i]);
     act_motion(nd.oM[i], nd.agf[i], oa[i]);
-    double X[36]; force_action_matrix(nd.oM[i], X);
-    double Yl[36];
-#pragma unroll
-    for (int k = 0; k < 36; ++k) Yl[k] = M.Y[i][k];
-    congruence6(X, Yl, oY[i]);
-    double h[6], Ya[6], vh[6];
-    mat6_vec(oY[i], ov[i], h); mat6_vec(oY[i], oa[i], Ya); cross_mf(ov[i], h, vh);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) F[i][k] = Ya[k] + vh[k];
-    // B_i = crf(v) Y - Y crm(v) + Hx(h)
-    double Sv[9], Sw[9]; skew3(ov[i], Sv); skew3(ov[i] + 3, Sw);
-    double Shf[9], Shn[9]; skew3(h, Shf); skew3(h + 3, Shn);
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int b = 0; b < 6; ++b) {
-        // crf = [[Sw,0],[Sv,Sw]], crm = [[Sw,Sv],[0,Sw]]
-        double s1 = 0, s2 = 0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          double crf_ak, crm_kb;
-          if (a < 3) crf_ak = (k < 3) ? Sw[3 * a + k] : 0.0;
-          else crf_ak = (k < 3) ? Sv[3 * (a - 3) + k] : Sw[3 * (a - 3) + (k - 3)];
-          if (k < 3) crm_kb = (b < 3) ? Sw[3 * k + b] : Sv[3 * k + (b - 3)];
-          else crm_kb = (b < 3) ? 0.0 : Sw[3 * (k - 3) + (b - 3)];
-          s1 += crf_ak * oY[i][6 * k + b];
-          s2 += oY[i][6 * a + k] * crm_kb;
-        }
-        double hx = 0;
-        if (a < 3 && b >= 3) hx = Shf[3 * a + (b - 3)];
-        else if (a >= 3 && b < 3) hx = Shf[3 * (a - 3) + b];
-        else if (a >= 3 && b >= 3) hx = Shn[3 * (a - 3) + (b - 3)];
-        Bm[i][6 * a + b] = s1 - s2 - hx;
-      }
   }
-#pragma unroll 1
-  for (int i = NJ - 1; i > 0; --i) {
+  double cm = 0, cmc[3] = {0, 0, 0}, cIo[9], chf[3] = {0, 0, 0}, cG[9], cF[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int k = 0; k < 36; ++k) { oY[i - 1][k] += oY[i][k]; Bm[i - 1][k] += Bm[i][k]; }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) F[i - 1][k] += F[i][k];
-  }
-  double YJ[NV][6], BtJ[NV][6];
-#pragma unroll 1
-  for (int c = 0; c < NV; ++c) {
-    const int j = (c < 6) ? 0 : c - 5;
-    mat6_vec(oY[j], Jc[c], YJ[c]);
-    mat6T_vec(Bm[j], Jc[c], BtJ[c]);
-  }
+  for (int i = 0; i < 9; ++i) { cIo[i] = 0; cG[i] = 0; }
+  double YJa[NA > 0 ? NA : 1][6], BtJa[NA > 0 ? NA : 1][3];
   double Mm[NV * NV];
-#pragma unroll 1
-  for (int cj = 0; cj < NV; ++cj)
-#pragma unroll 1
-    for (int ck = cj; ck < NV; ++ck) {
-      const double val = dot6(Jc[cj], YJ[ck]);  // serial chain: joint(cj) <= joint(ck)
-      Mm[cj * NV + ck] = val; Mm[ck * NV + cj] = val;
-    }
   double* dq = a_q; double* dv = a_v;
+  // Ycrb u  and  Bcrb u  with the running composites
+  auto Yc = [&](const double* u, double* o) {
+    double t1[3], t2[3], t3[3];
+    cross3(cmc, u + 3, t1); cross3(cmc, u, t2); matvec3(cIo, u + 3, t3);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o[i] = cm * u[i] - t1[i]; o[3 + i] = t2[i] + t3[i]; }
+  };
+  auto Bc = [&](const double* u, double* o) {
+    double t1[3], t2[3];
+    cross3(chf, u + 3, t1); matvec3(cG, u + 3, t2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o[i] = -2.0 * t1[i]; o[3 + i] = t2[i]; }
+  };
 #pragma unroll 1
-  for (int ck = 0; ck < NV; ++ck) {
-    const int k = (ck < 6) ? 0 : ck - 5;
-    const double* s = Jc[ck];
-    double vp[6], ap[6];
+  for (int k = NJ - 1; k >= 0; --k) {
+    {  // add body k to the composites
+      const SE3& oMk = nd.oM[k];
+      double cw[3]; matvec3(oMk.R, M.com[k], cw);
 #pragma unroll
-    for (int a = 0; a < 6; ++a) { vp[a] = (k > 0) ? ov[k > 0 ? k - 1 : 0][a] : 0.0; ap[a] = (k > 0) ? oa[k > 0 ? k - 1 : 0][a] : M.a0[a]; }
-    double dVdq[6], dAdq[6], dAdv[6], t6[6], vsum[6];
-    cross_mm(vp, s, dVdq);
-    cross_mm(ap, s, dAdq); cross_mm(vp, dVdq, t6);
+      for (int i = 0; i < 3; ++i) cw[i] += oMk.p[i];
+      double RI[9], Iw[9];
+      matmul3(oMk.R, M.Ic[k], RI);
 #pragma unroll
-    for (int a = 0; a < 6; ++a) { dAdq[a] += t6[a]; vsum[a] = vp[a] + ov[k][a]; }
-    cross_mm(vsum, s, dAdv);
-    double P[6], Fq[6], Fv[6], t1[6], t2[6];
-    mat6_vec(oY[k], dAdq, t1); mat6_vec(Bm[k], dVdq, t2);
+      for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int a = 0; a < 6; ++a) P[a] = t1[a] + t2[a];
-    cross_mf(s, F[k], t1);
+        for (int j = 0; j < 3; ++j) Iw[3 * i + j] = RI[3 * i] * oMk.R[3 * j] + RI[3 * i + 1] * oMk.R[3 * j + 1] + RI[3 * i + 2] * oMk.R[3 * j + 2];
+      const double m = M.mass[k];
+      double h[6], Ya[6], vh[6];
+      inertia_apply(m, cw, Iw, ov[k], h); inertia_apply(m, cw, Iw, oa[k], Ya); cross_mf(ov[k], h, vh);
+      const double c2 = dot3(cw, cw);
+      double Io[9], mc[3] = {m * cw[0], m * cw[1], m * cw[2]};
 #pragma unroll
-    for (int a = 0; a < 6; ++a) Fq[a] = P[a] + t1[a];
-    mat6_vec(oY[k], dAdv, t1); mat6_vec(Bm[k], s, t2);
+      for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int a = 0; a < 6; ++a) Fv[a] = t1[a] + t2[a];
+        for (int j = 0; j < 3; ++j) Io[3 * i + j] = Iw[3 * i + j] + m * (((i == j) ? c2 : 0.0) - cw[i] * cw[j]);
+      const double* vl = ov[k]; const double* w = ov[k] + 3;
+      double Sw[9], A1[9], Shn[9]; skew3(w, Sw); matmul3(Sw, Io, A1); skew3(h + 3, Shn);
+      const double vm = dot3(vl, mc);
+      cm += m;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { cmc[i] += mc[i]; chf[i] += h[i]; }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cF[i] += Ya[i] + vh[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          cIo[3 * i + j] += Io[3 * i + j];
+          cG[3 * i + j] += A1[3 * i + j] + A1[3 * j + i] - (mc[i] * vl[j] + vl[i] * mc[j]) + ((i == j) ? 2.0 * vm : 0.0) - Shn[3 * i + j];
+        }
+    }
+    const int c_begin = (k == 0) ? 0 : 5 + k, c_end = (k == 0) ? 6 : 6 + k;
 #pragma unroll 1
-    for (int cj = 0; cj < NV; ++cj) {
-      const int j = (cj < 6) ? 0 : cj - 5;
-      double vq_, vv_;
-      if (j == k) { vq_ = dot6(Jc[cj], P); vv_ = dot6(Jc[cj], Fv); }
-      else if (j < k) { vq_ = dot6(Jc[cj], Fq); vv_ = dot6(Jc[cj], Fv); }
-      else { vq_ = dot6(YJ[cj], dAdq) + dot6(BtJ[cj], dVdq); vv_ = dot6(YJ[cj], dAdv) + dot6(BtJ[cj], s); }
-      dq[cj * NV + ck] = vq_; dv[cj * NV + ck] = vv_;
+    for (int ck = c_begin; ck < c_end; ++ck) {
+      const double* s = Jc[ck];
+      double vp[6], ap[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { vp[a] = (k > 0) ? ov[k > 0 ? k - 1 : 0][a] : 0.0; ap[a] = (k > 0) ? oa[k > 0 ? k - 1 : 0][a] : M.a0[a]; }
+      double dVdq[6], dAdq[6], dAdv[6], t6[6], vsum[6];
+      cross_mm(vp, s, dVdq);
+      cross_mm(ap, s, dAdq); cross_mm(vp, dVdq, t6);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { dAdq[a] += t6[a]; vsum[a] = vp[a] + ov[k][a]; }
+      cross_mm(vsum, s, dAdv);
+      double P[6], Fq[6], Fv[6], YJ[6], t1[6], t2[6];
+      Yc(dAdq, t1); Bc(dVdq, t2);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) P[a] = t1[a] + t2[a];
+      cross_mf(s, cF, t1);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) Fq[a] = P[a] + t1[a];
+      Yc(dAdv, t1); Bc(s, t2);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) Fv[a] = t1[a] + t2[a];
+      Yc(s, YJ);
+      if (k > 0) {
+        double c1[3], c2v[3];
+        cross3(chf, s, c1);  // 2 hf x s_v + G^T s_w
+#pragma unroll
+        for (int i = 0; i < 3; ++i) c2v[i] = cG[i] * s[3] + cG[3 + i] * s[4] + cG[6 + i] * s[5];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) YJa[k - 1][i] = YJ[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) BtJa[k - 1][i] = 2.0 * c1[i] + c2v[i];
+      }
+#pragma unroll 1
+      for (int cj = 0; cj < NV; ++cj) {
+        double vq_, vv_;
+        if (cj < c_begin) { vq_ = dot6(Jc[cj], Fq); vv_ = dot6(Jc[cj], Fv); }
+        else if (cj < c_end) { vq_ = dot6(Jc[cj], P); vv_ = dot6(Jc[cj], Fv); }
+        else {
+          const double* yj = YJa[cj - 6]; const double* bj = BtJa[cj - 6];
+          vq_ = dot6(yj, dAdq) + (bj[0] * dVdq[3] + bj[1] * dVdq[4] + bj[2] * dVdq[5]);
+          vv_ = dot6(yj, dAdv) + (bj[0] * s[3] + bj[1] * s[4] + bj[2] * s[5]);
+        }
+        dq[cj * NV + ck] = vq_; dv[cj * NV + ck] = vv_;
+        if (cj <= ck) { const double mv = dot6(Jc[cj], YJ); Mm[cj * NV + ck] = mv; Mm[ck * NV + cj] = mv; }
+      }
     }
   }
-  llt_inplace<NV>(Mm);
+  double Minvd[NV];
+  llt_inplace_inv<NV>(Mm, Minvd);
 #pragma unroll 1
   for (int i = 0; i < NV; ++i)
 #pragma unroll 1
     for (int j = 0; j < NV; ++j) Minv[i * NV + j] = (i == j) ? 1.0 : 0.0;
 #pragma unroll 1
-  for (int c = 0; c < NV; ++c) llt_solve_vec<NV>(Mm, Minv + c, NV);
+  for (int c = 0; c < NV; ++c) llt_solve_vec_inv<NV>(Mm, Minvd, Minv + c, NV);
   // a_q = -Minv dq, a_v = -Minv dv, column by column in place
 #pragma unroll 1
   for (int j = 0; j < NV; ++j) {

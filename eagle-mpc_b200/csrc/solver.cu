@@ -147,6 +147,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   for (int i = 0; i < r.n_joints; ++i) {
     std::memcpy(M.jR[i], r.jplace_R[i], 72); std::memcpy(M.jp[i], r.jplace_p[i], 24); std::memcpy(M.axis[i], r.axis[i], 24);
     inertia_matrix(r.mass[i], r.com[i], r.inertia[i], M.Y[i]);
+    M.mass[i] = r.mass[i]; std::memcpy(M.com[i], r.com[i], 24); std::memcpy(M.Ic[i], r.inertia[i], 72);
   }
   for (int i = 0; i < 3; ++i) { M.a0[i] = -r.gravity[i]; M.a0[3 + i] = 0; }
   for (int f = 0; f < r.n_frames; ++f) {
@@ -314,16 +315,18 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth) {
 }
 template <class D>
 static cudaError_t launch_backward(empc_solver* h, int force) {
-  constexpr int WARPS = 4;
-  const size_t smem = sizeof(double) * BwSmem<D>::TOTAL * WARPS;
+  using S = BwCfg<D>;
+  const size_t smem = sizeof(double) * S::TOTAL;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(backward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(backward_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
   BwParams P{h->P.reg_max, h->P.reg_factor, h->P.th_gaptol, force};
-  backward_kernel<D><<<(h->B + WARPS - 1) / WARPS, WARPS * 32, smem, h->stream>>>(h->bf, P);
+  backward_kernel<D><<<h->B, S::THREADS, smem, h->stream>>>(h->bf, P);
   h->launches++;
   return cudaGetLastError();
 }
@@ -331,7 +334,8 @@ template <class D>
 static cudaError_t launch_rollout(empc_solver* h, int force, int feasible, int ddp, double smooth) {
   const int n = h->B * EMPC_N_ALPHAS;
   RoParams P{force, feasible, ddp, smooth};
-  rollout_kernel<D><<<(n + 63) / 64, 64, 0, h->stream>>>(h->bf, P);
+  // one warp per block, >= 9 resident blocks per SM: 4096 OCPs x 10 step lengths = 1280 warps fit in a single wave
+  rollout_kernel<D><<<(n + 31) / 32, 32, 0, h->stream>>>(h->bf, P);
   h->launches++;
   return cudaGetLastError();
 }

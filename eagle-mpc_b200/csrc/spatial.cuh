@@ -409,6 +409,48 @@ EMPC_DI bool llt_inplace(double* A) {
   }
   return ok;
 }
+// Cholesky that also returns the reciprocals of the diagonal, and substitution that multiplies by them: keeps the long
+// FP64 division sequences (~30 dependent instructions each) out of the substitution chains.
+template <int N>
+EMPC_DI bool llt_inplace_inv(double* A, double* dinv) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double d = A[j * N + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= A[j * N + k] * A[j * N + k];
+    if (!(d > 0.0)) ok = false;
+    d = sqrt(d);
+    A[j * N + j] = d;
+    const double inv = 1.0 / d;
+    dinv[j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      double s = A[i * N + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= A[i * N + k] * A[j * N + k];
+      A[i * N + j] = s * inv;
+    }
+  }
+  return ok;
+}
+template <int N>
+EMPC_DI void llt_solve_vec_inv(const double* L, const double* dinv, double* b, int stride) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = b[i * stride];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[i * N + k] * b[k * stride];
+    b[i * stride] = s * dinv[i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double s = b[i * stride];
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) s -= L[k * N + i] * b[k * stride];
+    b[i * stride] = s * dinv[i];
+  }
+}
 // solve L L^T x = b for one right-hand side (strided), in place
 template <int N>
 EMPC_DI void llt_solve_vec(const double* L, double* b, int stride) {

@@ -11,8 +11,8 @@ abi = importlib.import_module("eagle-mpc_b200.abi")
 dp = abi.as_double_p
 
 
-def _load():
-    path = os.path.join(ROOT, "oracle", "liboracle.so")
+def _load(name="liboracle.so"):
+    path = os.path.join(ROOT, "oracle", name)
     src = [os.path.join(ROOT, "oracle", f) for f in ("oracle.cpp", "oracle_model.hpp", "oracle_math.hpp")]
     if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in src):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
@@ -32,6 +32,15 @@ def _load():
 
 
 lib = _load()
+_lib_nofma = None
+
+
+def lib_nofma():
+    """The same oracle compiled with -ffp-contract=off (conditioning yardstick)."""
+    global _lib_nofma
+    if _lib_nofma is None:
+        _lib_nofma = _load("liboracle_nofma.so")
+    return _lib_nofma
 
 
 def default_params():
@@ -51,34 +60,35 @@ def solve_batch(holder, x0, nthreads=1, params=None):
 
 
 class Oracle:
-    def __init__(self, holder):
+    def __init__(self, holder, nofma=False):
         self.h = holder
-        self.p = C.c_void_p(lib.orc_create(C.byref(holder.desc)))
+        self.lib = lib_nofma() if nofma else lib
+        self.p = C.c_void_p(self.lib.orc_create(C.byref(holder.desc)))
         d = (C.c_int32 * 7)()
-        lib.orc_dims(self.p, d)
+        self.lib.orc_dims(self.p, d)
         self.nq, self.nv, self.nx, self.ndx, self.nu, self.T, self.tile = list(d)
 
     def __del__(self):
         if getattr(self, "p", None):
-            lib.orc_destroy(self.p)
+            self.lib.orc_destroy(self.p)
             self.p = None
 
     def set_params(self, p):
-        lib.orc_set_params(self.p, C.byref(p))
+        self.lib.orc_set_params(self.p, C.byref(p))
 
     def set_x0(self, x0):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
-        lib.orc_set_x0(self.p, dp(x0))
+        self.lib.orc_set_x0(self.p, dp(x0))
 
     def set_candidate(self, xs=None, us=None, feasible=False):
         xs = None if xs is None else np.ascontiguousarray(xs, dtype=np.float64)
         us = None if us is None else np.ascontiguousarray(us, dtype=np.float64)
-        lib.orc_set_candidate(self.p, None if xs is None else dp(xs), None if us is None else dp(us), int(feasible))
+        self.lib.orc_set_candidate(self.p, None if xs is None else dp(xs), None if us is None else dp(us), int(feasible))
 
     def solve(self, xs=None, us=None, feasible=False):
         xs = None if xs is None else np.ascontiguousarray(xs, dtype=np.float64)
         us = None if us is None else np.ascontiguousarray(us, dtype=np.float64)
-        lib.orc_solve(self.p, None if xs is None else dp(xs), None if us is None else dp(us), int(feasible))
+        self.lib.orc_solve(self.p, None if xs is None else dp(xs), None if us is None else dp(us), int(feasible))
 
     def get(self, name):
         T, nx, ndx, nu = self.T, self.nx, self.ndx, self.nu
@@ -89,18 +99,18 @@ class Oracle:
             "cost_try": (1,), "stop": (1,), "xreg": (1,), "dgdq": (2,), "dv": (1,), "iter": (1,), "feasible": (1,),
         }
         out = np.zeros(shapes[name])
-        rc = lib.orc_get(self.p, name.encode(), dp(out))
+        rc = self.lib.orc_get(self.p, name.encode(), dp(out))
         assert rc == 0, name
         return out if out.size > 1 else out.reshape(-1)[0]
 
     def phase_calc_diff(self, smooth):
-        lib.orc_phase_calc_diff(self.p, smooth)
+        self.lib.orc_phase_calc_diff(self.p, smooth)
 
     def phase_backward(self, xreg, feasible):
-        return lib.orc_phase_backward(self.p, xreg, int(feasible))
+        return self.lib.orc_phase_backward(self.p, xreg, int(feasible))
 
     def phase_rollout(self, smooth, feasible, ddp, alpha_index):
-        return lib.orc_phase_rollout(self.p, smooth, int(feasible), int(ddp), alpha_index)
+        return self.lib.orc_phase_rollout(self.p, smooth, int(feasible), int(ddp), alpha_index)
 
     def node_eval(self, costset, smooth, x, u, diff=True):
         x = np.ascontiguousarray(x, dtype=np.float64)
@@ -109,39 +119,39 @@ class Oracle:
         cost = np.zeros(1)
         s = np.zeros(self.nu)
         tile = np.zeros(self.tile) if diff else None
-        lib.orc_node_eval(self.p, costset, smooth, dp(x), None if u is None else dp(u), dp(xnext), dp(cost), dp(s),
+        self.lib.orc_node_eval(self.p, costset, smooth, dp(x), None if u is None else dp(u), dp(xnext), dp(cost), dp(s),
                           None if tile is None else dp(tile))
         return xnext, cost[0], s, tile
 
     def integrate(self, x, dx):
         x = np.ascontiguousarray(x, dtype=np.float64); dx = np.ascontiguousarray(dx, dtype=np.float64)
         out = np.zeros(self.nx)
-        lib.orc_state_integrate(self.p, dp(x), dp(dx), dp(out))
+        self.lib.orc_state_integrate(self.p, dp(x), dp(dx), dp(out))
         return out
 
     def diff(self, x0, x1):
         x0 = np.ascontiguousarray(x0, dtype=np.float64); x1 = np.ascontiguousarray(x1, dtype=np.float64)
         out = np.zeros(self.ndx)
-        lib.orc_state_diff(self.p, dp(x0), dp(x1), dp(out))
+        self.lib.orc_state_diff(self.p, dp(x0), dp(x1), dp(out))
         return out
 
     def aba(self, q, v, tau):
         q, v, tau = (np.ascontiguousarray(a, dtype=np.float64) for a in (q, v, tau))
         a = np.zeros(self.nv)
-        lib.orc_aba(self.p, dp(q), dp(v), dp(tau), dp(a))
+        self.lib.orc_aba(self.p, dp(q), dp(v), dp(tau), dp(a))
         return a
 
     def rnea(self, q, v, a):
         q, v, a = (np.ascontiguousarray(z, dtype=np.float64) for z in (q, v, a))
         tau = np.zeros(self.nv)
-        lib.orc_rnea(self.p, dp(q), dp(v), dp(a), dp(tau))
+        self.lib.orc_rnea(self.p, dp(q), dp(v), dp(a), dp(tau))
         return tau
 
     def aba_derivatives(self, q, v, tau):
         q, v, tau = (np.ascontiguousarray(z, dtype=np.float64) for z in (q, v, tau))
         nv = self.nv
         a = np.zeros(nv); aq = np.zeros((nv, nv)); av = np.zeros((nv, nv)); Minv = np.zeros((nv, nv))
-        lib.orc_aba_derivatives(self.p, dp(q), dp(v), dp(tau), dp(a), dp(aq), dp(av), dp(Minv))
+        self.lib.orc_aba_derivatives(self.p, dp(q), dp(v), dp(tau), dp(a), dp(aq), dp(av), dp(Minv))
         return a, aq, av, Minv
 
 
