@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BwCfg<D>::THREADS, BwCfg<D>::MIN_BLOCKS) backw
   __shared__ int s_flag;
   __shared__ double s_red[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x;
+  const int b = bf.b0 + blockIdx.x;
   OcpState st = bf.st[b];
   if (!P.force && st.phase == PHASE_DONE) return;
   const int T = bf.T, T1 = T + 1;

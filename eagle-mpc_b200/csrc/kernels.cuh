@@ -32,6 +32,7 @@ struct Buffers {
   const int* node_costset;
   const int* ocp_map;
   int B, T;
+  int b0, nb;  // OCP window [b0, b0+nb) this launch works on (batch groups pipelined on separate streams)
   // per-OCP
   OcpState* st;
   const double* x0;
@@ -52,9 +53,10 @@ struct Buffers {
 #endif
 template <class D>
 __global__ void __launch_bounds__(128, EMPC_CD_MINB) calc_diff_kernel(Buffers bf, int force, double force_smooth) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nl = blockIdx.x * blockDim.x + threadIdx.x;
   const int T1 = bf.T + 1;
-  if (n >= bf.B * T1) return;
+  if (nl >= bf.nb * T1) return;
+  const int n = bf.b0 * T1 + nl;
   const int b = n / T1, t = n - b * T1;
   const OcpState st = bf.st[b];
   if (!force && (st.phase == PHASE_DONE || !st.recalc)) return;
@@ -128,8 +130,9 @@ struct RoParams {
 template <class D>
 __global__ void __launch_bounds__(32, 9) rollout_kernel(Buffers bf, RoParams P) {
   constexpr int NX = D::NX, NDX = D::NDX, NU = D::NU;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= bf.B * EMPC_N_ALPHAS) return;
+  const int nl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nl >= bf.nb * EMPC_N_ALPHAS) return;
+  const int n = bf.b0 * EMPC_N_ALPHAS + nl;
   const int b = n / EMPC_N_ALPHAS, ai = n - b * EMPC_N_ALPHAS;
   const OcpState st = bf.st[b];
   if (!P.force && (st.phase == PHASE_DONE || st.bw_fail)) return;
@@ -256,7 +259,7 @@ __device__ __forceinline__ void end_inner_solve(OcpState& st, const empc_solver_
 template <class D>
 __global__ void __launch_bounds__(128) decide_kernel(Buffers bf, DecideParams dp) {
   constexpr int NX = D::NX, NU = D::NU;
-  const int b = blockIdx.x;
+  const int b = bf.b0 + blockIdx.x;
   __shared__ int s_acc, s_last;
   const empc_solver_params_t& P = dp.P;
   const int T = bf.T, T1 = T + 1;
@@ -376,6 +379,58 @@ __global__ void squash_out_kernel(Buffers bf) {
   squash<D>(M, bf.st[b].smooth, u, s);
 #pragma unroll
   for (int i = 0; i < D::NU; ++i) bf.us_squash[(size_t)n * D::NU + i] = s[i];
+}
+
+// RK4 plant of the closed-loop drivers (bindings/python/eagle_mpc/utils/simulator.py:7-29: IntegratedActionModelRK4 over
+// DifferentialActionModelFreeFwdDynamics with the plain multicopter actuation, no costs).  One thread per instance.
+template <class D>
+__global__ void plant_rk4_kernel(const DevModel* Mp, const double* __restrict__ xin, const double* __restrict__ uin, double dt,
+                                 double* __restrict__ xout, int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const DevModel& M = *Mp;
+  double x[D::NX], u[D::NU], tau[D::NV];
+#pragma unroll
+  for (int i = 0; i < D::NX; ++i) x[i] = xin[(size_t)b * D::NX + i];
+#pragma unroll
+  for (int i = 0; i < D::NU; ++i) u[i] = uin[(size_t)b * D::NU + i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double t = 0;
+#pragma unroll
+    for (int j = 0; j < D::NR; ++j) t += M.tau_f[i * D::NR + j] * u[j];
+    tau[i] = t;
+  }
+#pragma unroll
+  for (int i = 0; i < D::NA; ++i) tau[6 + i] = u[D::NR + i];
+  const double c[4] = {0.0, 0.5, 0.5, 1.0}, wgt[4] = {1.0, 2.0, 2.0, 1.0};
+  double ksum[D::NDX], kprev[D::NDX];
+#pragma unroll
+  for (int i = 0; i < D::NDX; ++i) { ksum[i] = 0; kprev[i] = 0; }
+#pragma unroll 1
+  for (int s = 0; s < 4; ++s) {
+    double y[D::NX], dxs[D::NDX];
+#pragma unroll
+    for (int i = 0; i < D::NDX; ++i) dxs[i] = dt * c[s] * kprev[i];
+    if (s == 0) {
+#pragma unroll
+      for (int i = 0; i < D::NX; ++i) y[i] = x[i];
+    } else {
+      state_integrate<D>(x, dxs, y);
+    }
+    NodeData<D> nd;
+    aba<D>(M, y, tau, nd);
+#pragma unroll
+    for (int i = 0; i < D::NV; ++i) { kprev[i] = y[D::NQ + i]; kprev[D::NV + i] = nd.a[i]; }
+#pragma unroll
+    for (int i = 0; i < D::NDX; ++i) ksum[i] += wgt[s] * kprev[i];
+  }
+  double dx[D::NDX], xn[D::NX];
+#pragma unroll
+  for (int i = 0; i < D::NDX; ++i) dx[i] = ksum[i] * (dt / 6.0);
+  state_integrate<D>(x, dx, xn);
+#pragma unroll
+  for (int i = 0; i < D::NX; ++i) xout[(size_t)b * D::NX + i] = xn[i];
 }
 
 // SolverAbstract::setCandidate with empty warm starts: xs[t] = state.zero(), us[t] = 0

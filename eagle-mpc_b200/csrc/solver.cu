@@ -42,7 +42,11 @@ struct empc_solver {
   double *d_xs_init = nullptr, *d_us_init = nullptr;
   int init_feasible = 0;
   cudaStream_t stream = nullptr;
-  int* h_active = nullptr;  // pinned
+  int* h_active = nullptr;  // pinned: [group][slot][2]
+  static constexpr int MAXG = 4;
+  int n_groups = 1;
+  cudaStream_t gstream[MAXG] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_it[MAXG][2] = {}, ev_skew[MAXG] = {}, ev_init = nullptr, ev_gdone[MAXG] = {};
   // stats
   long long launches = 0, total_iterations = 0;
   int timing = 0;
@@ -110,6 +114,13 @@ int empc_destroy(empc_solver_t* h) {
   if (h->h_active) cudaFreeHost(h->h_active);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_solve) if (e) cudaEventDestroy(e);
+  for (int g = 0; g < empc_solver::MAXG; ++g) {
+    if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
+    for (auto& e : h->ev_it[g]) if (e) cudaEventDestroy(e);
+    if (h->ev_skew[g]) cudaEventDestroy(h->ev_skew[g]);
+    if (h->ev_gdone[g]) cudaEventDestroy(h->ev_gdone[g]);
+  }
+  if (h->ev_init) cudaEventDestroy(h->ev_init);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return EMPC_OK;
@@ -166,7 +177,18 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   if (e != cudaSuccess) { delete h; return fail(EMPC_ERR_CUDA, cudaGetErrorString(e)); }
 #define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); empc_destroy(h); return fail(EMPC_ERR_CUDA, m_); } } while (0)
   const size_t B = batch, T = d->T, T1 = T + 1, nx = h->nx, tile = h->tile;
-  CKH(cudaMallocHost((void**)&h->h_active, 2 * sizeof(int)));
+  CKH(cudaMallocHost((void**)&h->h_active, empc_solver::MAXG * 2 * 2 * sizeof(int)));
+  for (int g = 0; g < empc_solver::MAXG; ++g) {
+    CKH(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+    for (auto& e : h->ev_it[g]) CKH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_skew[g], cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_gdone[g], cudaEventDisableTiming));
+  }
+  CKH(cudaEventCreateWithFlags(&h->ev_init, cudaEventDisableTiming));
+  // batch groups: the rollout is latency-bound (one wave), calc_diff/backward are throughput-bound; skewed groups on
+  // separate streams let one group's rollout overlap the others' calc_diff + backward
+  h->n_groups = 1;  // measured on B200: grouping does not pay at B=4096 (profiles/), kept as an opt-in (EMPC_GROUPS)
+  if (const char* e = std::getenv("EMPC_GROUPS")) h->n_groups = std::max(1, std::min((int)empc_solver::MAXG, std::atoi(e)));
   for (auto& ev : h->ev) CKH(cudaEventCreate(&ev));
   for (auto& ev : h->ev_solve) CKH(cudaEventCreate(&ev));
   CKH(dalloc(h, &h->d_model, 1));
@@ -180,7 +202,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   CKH(dalloc(h, &h->d_us_init, B * T * nu));
   Buffers& bf = h->bf;
   std::memset(&bf, 0, sizeof(bf));
-  bf.B = batch; bf.T = d->T;
+  bf.B = batch; bf.T = d->T; bf.b0 = 0; bf.nb = batch;
   CKH(dalloc(h, &bf.st, B));
   CKH(dalloc(h, &bf.xs, B * T1 * nx));
   CKH(dalloc(h, &bf.us, B * T * nu));
@@ -202,7 +224,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   CKH(dalloc(h, &bf.dv, B * EMPC_N_ALPHAS));
   CKH(dalloc(h, &bf.ok, B * EMPC_N_ALPHAS));
   CKH(dalloc(h, &bf.us_squash, B * T * nu));
-  CKH(dalloc(h, &bf.n_active, 2));
+  CKH(dalloc(h, &bf.n_active, 2 * empc_solver::MAXG));
   bf.model = h->d_model; bf.ct.costs = h->d_costs; bf.ct.pool = h->d_pool; bf.ct.costset_begin = h->d_costset_begin;
   bf.node_costset = h->d_node_costset; bf.ocp_map = h->d_ocp_map; bf.x0 = h->d_x0;
   CKH(cudaMemcpyAsync(h->d_model, &M, sizeof(M), cudaMemcpyHostToDevice, h->stream));
@@ -307,14 +329,18 @@ int empc_update_node_costsets(empc_solver_t* h, const int32_t* nc) {
 
 // ---- launches -------------------------------------------------------------------------------------------------------
 template <class D>
-static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth) {
-  const int n = h->B * (h->T + 1);
-  calc_diff_kernel<D><<<(n + 127) / 128, 128, 0, h->stream>>>(h->bf, force, smooth);
+static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, const Buffers* gb = nullptr, cudaStream_t st = nullptr) {
+  const Buffers& bf = gb ? *gb : h->bf;
+  if (!st) st = h->stream;
+  const int n = bf.nb * (h->T + 1);
+  calc_diff_kernel<D><<<(n + 127) / 128, 128, 0, st>>>(bf, force, smooth);
   h->launches++;
   return cudaGetLastError();
 }
 template <class D>
-static cudaError_t launch_backward(empc_solver* h, int force) {
+static cudaError_t launch_backward(empc_solver* h, int force, const Buffers* gb = nullptr, cudaStream_t st = nullptr) {
+  const Buffers& bf = gb ? *gb : h->bf;
+  if (!st) st = h->stream;
   using S = BwCfg<D>;
   const size_t smem = sizeof(double) * S::TOTAL;
   static bool attr_set = false;
@@ -326,23 +352,28 @@ static cudaError_t launch_backward(empc_solver* h, int force) {
     attr_set = true;
   }
   BwParams P{h->P.reg_max, h->P.reg_factor, h->P.th_gaptol, force};
-  backward_kernel<D><<<h->B, S::THREADS, smem, h->stream>>>(h->bf, P);
+  backward_kernel<D><<<bf.nb, S::THREADS, smem, st>>>(bf, P);
   h->launches++;
   return cudaGetLastError();
 }
 template <class D>
-static cudaError_t launch_rollout(empc_solver* h, int force, int feasible, int ddp, double smooth) {
-  const int n = h->B * EMPC_N_ALPHAS;
+static cudaError_t launch_rollout(empc_solver* h, int force, int feasible, int ddp, double smooth, const Buffers* gb = nullptr,
+                                  cudaStream_t st = nullptr) {
+  const Buffers& bf = gb ? *gb : h->bf;
+  if (!st) st = h->stream;
+  const int n = bf.nb * EMPC_N_ALPHAS;
   RoParams P{force, feasible, ddp, smooth};
   // one warp per block, >= 9 resident blocks per SM: 4096 OCPs x 10 step lengths = 1280 warps fit in a single wave
-  rollout_kernel<D><<<(n + 31) / 32, 32, 0, h->stream>>>(h->bf, P);
+  rollout_kernel<D><<<(n + 31) / 32, 32, 0, st>>>(bf, P);
   h->launches++;
   return cudaGetLastError();
 }
 template <class D>
-static cudaError_t launch_decide(empc_solver* h) {
+static cudaError_t launch_decide(empc_solver* h, const Buffers* gb = nullptr, cudaStream_t st = nullptr) {
+  const Buffers& bf = gb ? *gb : h->bf;
+  if (!st) st = h->stream;
   DecideParams dp{h->P};
-  decide_kernel<D><<<h->B, 128, 0, h->stream>>>(h->bf, dp);
+  decide_kernel<D><<<bf.nb, 128, 0, st>>>(bf, dp);
   h->launches++;
   return cudaGetLastError();
 }
@@ -369,34 +400,88 @@ static int solve_impl(empc_solver* h) {
   int passes = 1;
   for (double c = h->P.convergence_init; c >= h->P.convergence_stop && passes < 64; c *= h->P.convergence_mult) passes++;
   const long long max_loops = (long long)passes * h->P.maxiter + 8;
-  for (long long it = 0; it < max_loops; ++it) {
-    if (h->timing) CK(cudaEventRecord(h->ev[0], h->stream));
-    CK(launch_calc_diff<D>(h, 0, 0.0));
-    if (h->timing) CK(cudaEventRecord(h->ev[1], h->stream));
-    CK(launch_backward<D>(h, 0));
-    if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
-    CK(launch_rollout<D>(h, 0, 0, 0, 0.0));
-    if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(cudaMemsetAsync(h->bf.n_active, 0, 2 * sizeof(int), h->stream));
-    CK(launch_decide<D>(h));
-    if (h->timing) CK(cudaEventRecord(h->ev[4], h->stream));
-    CK(cudaMemcpyAsync(h->h_active, h->bf.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->units_by_kernel[0] += n_recalc; h->units_by_kernel[1] += n_act; h->units_by_kernel[2] += n_act; h->units_by_kernel[3] += n_act;
-    n_act = h->h_active[0]; n_recalc = h->h_active[1];
-    if (h->timing) {
-      for (int k = 0; k < 4; ++k) { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1])); h->ms_by_kernel[k] += ms; }
+  const bool trace = std::getenv("EMPC_TRACE_OCP") != nullptr;
+  if (h->timing || trace || h->n_groups == 1) {
+    // serial schedule with per-kernel CUDA-event timing (used for the roofline numbers and for tracing)
+    for (long long it = 0; it < max_loops; ++it) {
+      if (h->timing) CK(cudaEventRecord(h->ev[0], h->stream));
+      CK(launch_calc_diff<D>(h, 0, 0.0));
+      if (h->timing) CK(cudaEventRecord(h->ev[1], h->stream));
+      CK(launch_backward<D>(h, 0));
+      if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
+      CK(launch_rollout<D>(h, 0, 0, 0, 0.0));
+      if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
+      CK(cudaMemsetAsync(h->bf.n_active, 0, 2 * sizeof(int), h->stream));
+      CK(launch_decide<D>(h));
+      if (h->timing) CK(cudaEventRecord(h->ev[4], h->stream));
+      CK(cudaMemcpyAsync(h->h_active, h->bf.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      h->units_by_kernel[0] += n_recalc; h->units_by_kernel[1] += n_act; h->units_by_kernel[2] += n_act; h->units_by_kernel[3] += n_act;
+      n_act = h->h_active[0]; n_recalc = h->h_active[1];
+      if (h->timing) {
+        for (int k = 0; k < 4; ++k) { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1])); h->ms_by_kernel[k] += ms; }
+      }
+      if (trace) {
+        const int b = std::atoi(std::getenv("EMPC_TRACE_OCP"));
+        if (b >= 0 && b < h->B) {
+          OcpState s;
+          CK(cudaMemcpy(&s, h->bf.st + b, sizeof(s), cudaMemcpyDeviceToHost));
+          std::printf("[gpu ph%d] loop=%lld it=%d cost=%.15e prev=%.15e step=%g xreg=%g feas=%d wasf=%d stop=%.6e gap=%.6e acc=%d dg=%.6e dq=%.6e smooth=%g tot=%d\n",
+                      s.phase, it, s.iter, s.cost, s.cost_prev, s.steplength, s.xreg, s.is_feasible, s.was_feasible, s.stop, s.gap_inf, s.accepted, s.dg, s.dq, s.smooth, s.total_iters);
+        }
+      }
+      if (*h->h_active == 0) break;
     }
-    if (const char* tr = std::getenv("EMPC_TRACE_OCP")) {
-      const int b = std::atoi(tr);
-      if (b >= 0 && b < h->B) {
-        OcpState s;
-        CK(cudaMemcpy(&s, h->bf.st + b, sizeof(s), cudaMemcpyDeviceToHost));
-        std::printf("[gpu ph%d] loop=%lld it=%d cost=%.15e prev=%.15e step=%g xreg=%g feas=%d wasf=%d stop=%.6e gap=%.6e acc=%d dg=%.6e dq=%.6e smooth=%g tot=%d\n",
-                    s.phase, it, s.iter, s.cost, s.cost_prev, s.steplength, s.xreg, s.is_feasible, s.was_feasible, s.stop, s.gap_inf, s.accepted, s.dg, s.dq, s.smooth, s.total_iters);
+  } else {
+    // pipelined schedule: G batch groups on their own streams, started one backward pass apart
+    const int G = h->n_groups;
+    Buffers gb[empc_solver::MAXG];
+    bool alive[empc_solver::MAXG];
+    long long g_act[empc_solver::MAXG], g_recalc[empc_solver::MAXG];
+    CK(cudaEventRecord(h->ev_init, h->stream));
+    for (int g = 0; g < G; ++g) {
+      gb[g] = h->bf;
+      gb[g].b0 = (int)((long long)h->B * g / G);
+      gb[g].nb = (int)((long long)h->B * (g + 1) / G) - gb[g].b0;
+      gb[g].n_active = h->bf.n_active + 2 * g;
+      alive[g] = gb[g].nb > 0;
+      g_act[g] = g_recalc[g] = gb[g].nb;
+      CK(cudaStreamWaitEvent(h->gstream[g], h->ev_init, 0));
+    }
+    for (long long it = 0; it < max_loops + 1; ++it) {
+      bool any = false;
+      const int slot = (int)(it & 1);
+      for (int g = 0; g < G; ++g) {
+        if (!alive[g]) continue;
+        any = true;
+        cudaStream_t st = h->gstream[g];
+        if (it == 0 && g > 0) CK(cudaStreamWaitEvent(st, h->ev_skew[g - 1], 0));
+        CK(launch_calc_diff<D>(h, 0, 0.0, &gb[g], st));
+        CK(launch_backward<D>(h, 0, &gb[g], st));
+        if (it == 0) CK(cudaEventRecord(h->ev_skew[g], st));
+        CK(launch_rollout<D>(h, 0, 0, 0, 0.0, &gb[g], st));
+        CK(cudaMemsetAsync(gb[g].n_active, 0, 2 * sizeof(int), st));
+        CK(launch_decide<D>(h, &gb[g], st));
+        CK(cudaMemcpyAsync(h->h_active + (g * 2 + slot) * 2, gb[g].n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(h->ev_it[g][slot], st));
+      }
+      if (!any) break;
+      if (it >= 1) {  // lagged termination check: look at the counters of the previous batch-iteration
+        const int ps = (int)((it - 1) & 1);
+        for (int g = 0; g < G; ++g) {
+          if (!alive[g]) continue;
+          CK(cudaEventSynchronize(h->ev_it[g][ps]));
+          const int* c = h->h_active + (g * 2 + ps) * 2;
+          h->units_by_kernel[0] += g_recalc[g]; h->units_by_kernel[1] += g_act[g]; h->units_by_kernel[2] += g_act[g]; h->units_by_kernel[3] += g_act[g];
+          g_act[g] = c[0]; g_recalc[g] = c[1];
+          if (c[0] == 0) alive[g] = false;  // the iteration already queued for this group is a no-op (every OCP exits early)
+        }
       }
     }
-    if (*h->h_active == 0) break;
+    for (int g = 0; g < G; ++g) {
+      CK(cudaEventRecord(h->ev_gdone[g], h->gstream[g]));
+      CK(cudaStreamWaitEvent(h->stream, h->ev_gdone[g], 0));
+    }
   }
   CK(launch_squash_out<D>(h));
   CK(cudaEventRecord(h->ev_solve[1], h->stream));
@@ -503,6 +588,30 @@ int empc_get_solve_stats(const empc_solver_t* h, double* solve_ms, int64_t* unit
 int empc_enable_kernel_timing(empc_solver_t* h, int32_t on) {
   if (!h) return fail(EMPC_ERR_INVALID, "null");
   h->timing = on ? 1 : 0;
+  return EMPC_OK;
+}
+
+}  // extern "C"
+
+// ---- plant (closed-loop drivers) ----
+template <class D>
+static int plant_impl(empc_solver* h, const double* x, const double* u, double dt, double* xnext, int n) {
+  double *dx_ = nullptr, *du_ = nullptr, *dxn_ = nullptr;
+  CK(cudaMalloc(&dx_, sizeof(double) * n * h->nx)); CK(cudaMalloc(&du_, sizeof(double) * n * h->nu)); CK(cudaMalloc(&dxn_, sizeof(double) * n * h->nx));
+  CK(cudaMemcpyAsync(dx_, x, sizeof(double) * n * h->nx, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(du_, u, sizeof(double) * n * h->nu, cudaMemcpyHostToDevice, h->stream));
+  plant_rk4_kernel<D><<<(n + 63) / 64, 64, 0, h->stream>>>(h->d_model, dx_, du_, dt, dxn_, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(xnext, dxn_, sizeof(double) * n * h->nx, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(dx_); cudaFree(du_); cudaFree(dxn_);
+  return EMPC_OK;
+}
+extern "C" {
+int empc_plant_step(empc_solver_t* h, const double* x, const double* u, double dt, double* xnext, int32_t n) {
+  if (!h || !x || !u || !xnext || n <= 0) return fail(EMPC_ERR_INVALID, "null / bad count");
+  CK(cudaSetDevice(h->device));
+  EMPC_DISPATCH(h, return plant_impl<D>(h, x, u, dt, xnext, n));
   return EMPC_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <string>
 
 #include "eagle_mpc.hpp"
+#include "mpc.hpp"
 
 using namespace eagle_mpc;
 
@@ -10,6 +11,8 @@ static thread_local std::string g_err;
 #define GUARD(body, failret)            \
   try { body }                          \
   catch (const std::exception& e) { g_err = e.what(); return failret; }
+#define GUARD_BEGIN try {
+#define GUARD_END(failret) } catch (const std::exception& e) { g_err = e.what(); return failret; }
 
 struct HostTrajectory { std::shared_ptr<Trajectory> traj; };
 struct HostFlat { std::shared_ptr<ShootingProblem> problem; FlatProblem flat; };
@@ -116,6 +119,73 @@ int empc_host_solver_result(void* s, double* xs, double* us, double* us_squash, 
   for (std::size_t t = 0; t < X.size(); ++t) std::copy(X[t].begin(), X[t].end(), xs + t * X[t].size());
   for (std::size_t t = 0; t < U.size(); ++t) { std::copy(U[t].begin(), U[t].end(), us + t * U[t].size()); std::copy(S[t].begin(), S[t].end(), us_squash + t * S[t].size()); }
   *cost = sv->get_cost(); *iter = (int)sv->get_iter(); *feasible = sv->get_is_feasible() ? 1 : 0;
+  return 0;
+}
+
+// ---- CarrotMpc (src/mpc-controllers/carrot-mpc.cpp) ----
+struct HostCarrot { std::shared_ptr<Trajectory> traj; std::unique_ptr<CarrotMpc> mpc; };
+
+void* empc_host_carrot_create(void* t, const double* state_ref, int32_t n_ref, int32_t dt_ref, const char* yaml_path, int32_t create_solver) {
+  GUARD_BEGIN
+  auto& tr = ((HostTrajectory*)t)->traj;
+  const std::size_t nx = (std::size_t)tr->get_robot_state()->get_nx();
+  std::vector<VectorXd> ref((std::size_t)n_ref);
+  for (int i = 0; i < n_ref; ++i) ref[(std::size_t)i].assign(state_ref + (std::size_t)i * nx, state_ref + (std::size_t)(i + 1) * nx);
+  auto* hc = new HostCarrot();
+  hc->traj = tr;
+  hc->mpc.reset(new CarrotMpc(tr, ref, (std::size_t)dt_ref, getYamlPath(yaml_path), create_solver != 0));
+  return hc;
+  GUARD_END(nullptr)
+}
+void empc_host_carrot_free(void* m) { delete (HostCarrot*)m; }
+int empc_host_carrot_info(void* m, int32_t* out /* knots dt iters n_costs n_pool */) {
+  auto& c = ((HostCarrot*)m)->mpc;
+  out[0] = (int)c->get_knots(); out[1] = (int)c->get_dt(); out[2] = (int)c->get_iters();
+  out[3] = (int)c->flat().costs.size(); out[4] = (int)c->flat().pool.size();
+  return 0;
+}
+const empc_problem_desc_t* empc_host_carrot_desc(void* m) { return &((HostCarrot*)m)->mpc->flat().desc; }
+empc_solver_t* empc_host_carrot_handle(void* m) {
+  auto& s = ((HostCarrot*)m)->mpc->get_solver();
+  return s ? s->handle() : nullptr;
+}
+int empc_host_carrot_update(void* m, int32_t t_ms) {
+  GUARD({ ((HostCarrot*)m)->mpc->updateProblem((std::size_t)t_ms); return 0; }, 1)
+}
+// current cost records / pool (after updateProblem), for the tests' oracle
+int empc_host_carrot_costs(void* m, empc_cost_t* costs, double* pool) {
+  FlatProblem& f = ((HostCarrot*)m)->mpc->flat();
+  std::copy(f.costs.begin(), f.costs.end(), costs);
+  std::copy(f.pool.begin(), f.pool.end(), pool);
+  return 0;
+}
+// problem.x0 = x0 ; solver.solve(xs, us, maxiter) with explicit warm start (NULL xs => warm start from the previous solution)
+int empc_host_carrot_solve(void* m, const double* x0, const double* xs, const double* us, int32_t maxiter, double convergence_init) {
+  GUARD_BEGIN
+  auto& c = ((HostCarrot*)m)->mpc;
+  auto& sv = c->get_solver();
+  if (!sv) throw std::runtime_error("CarrotMpc was created without a solver");
+  const std::size_t nx = (std::size_t)c->get_robot_state()->get_nx(), T = c->get_problem()->get_T(), nu = c->get_squash()->get_ns();
+  c->get_problem()->set_x0(VectorXd(x0, x0 + nx));
+  sv->set_convergence_init(convergence_init);
+  if (xs && us) {
+    std::vector<VectorXd> X(T + 1);
+    std::vector<VectorXd> U(T);
+    for (std::size_t t = 0; t <= T; ++t) X[t].assign(xs + t * nx, xs + (t + 1) * nx);
+    for (std::size_t t = 0; t < T; ++t) U[t].assign(us + t * nu, us + (t + 1) * nu);
+    sv->solve(X, U, (std::size_t)maxiter);
+  } else {
+    sv->solveWarm((std::size_t)maxiter);
+  }
+  return 0;
+  GUARD_END(1)
+}
+int empc_host_carrot_result(void* m, double* xs, double* us, double* us_squash, double* cost, int32_t* iter) {
+  auto& sv = ((HostCarrot*)m)->mpc->get_solver();
+  const auto& X = sv->get_xs(); const auto& U = sv->get_us(); const auto& S = sv->getSquashControls();
+  for (std::size_t t = 0; t < X.size(); ++t) std::copy(X[t].begin(), X[t].end(), xs + t * X[t].size());
+  for (std::size_t t = 0; t < U.size(); ++t) { std::copy(U[t].begin(), U[t].end(), us + t * U[t].size()); std::copy(S[t].begin(), S[t].end(), us_squash + t * S[t].size()); }
+  *cost = sv->get_cost(); *iter = (int)sv->get_iter();
   return 0;
 }
 

@@ -1,1 +1,218 @@
+// mpc.cpp — MpcAbstract + CarrotMpc (src/mpc-base.cpp, src/mpc-controllers/carrot-mpc.cpp), bug-compatible where the
+// reference's behaviour is observable: integer-division interpolation (piecewise-constant
+// reference), t_stages clamped to >= dt, carrot_tail never deactivated, dimension checks that never throw.
+#include <algorithm>
+
 #include "mpc.hpp"
+
+namespace eagle_mpc {
+
+MpcAbstract::MpcAbstract(const std::string& yaml_path) {
+  ParserYaml parser(yaml_path);
+  params_server_ = std::make_shared<ParamsServer>(parser.get_params());
+  initializeRobotObjects();
+  loadParams();
+  int_models_.reserve(params_.knots);
+}
+
+void MpcAbstract::initializeRobotObjects() {
+  robot_model_path_ = getUrdfPath(params_server_->getParam<std::string>("robot/urdf"));
+  robot_model_ = buildModelFromUrdf(robot_model_path_);
+  platform_params_ = std::make_shared<MultiCopterBaseParams>();
+  platform_params_->autoSetup("robot/platform/", params_server_, robot_model_);
+  robot_state_ = std::make_shared<StateMultibody>();
+  robot_state_->pinocchio = robot_model_;
+  nu_ = platform_params_->n_rotors_ + (std::size_t)(robot_model_->nv - 6);
+  squash_ = std::make_shared<SquashingModelSmoothSat>();
+  squash_->u_lb = platform_params_->u_lb; squash_->u_ub = platform_params_->u_ub; squash_->ns = nu_;
+}
+
+void MpcAbstract::loadParams() {
+  const std::string p = "mpc_controller/";
+  params_.integrator_type = params_server_->getParam<std::string>(p + "integration_method");
+  if (params_.integrator_type != "IntegratedActionModelEuler" && params_.integrator_type != "IntegratedActionModelRK4")
+    throw std::out_of_range("map::at");
+  params_.knots = (std::size_t)params_server_->getParam<int>(p + "knots");
+  params_.iters = (std::size_t)params_server_->getParam<int>(p + "iters");
+  params_.dt = (std::size_t)params_server_->getParam<int>(p + "dt");
+  const std::string solver = params_server_->getParam<std::string>(p + "solver");
+  if (solver == "SolverSbFDDP") params_.solver_type = SolverTypes::SolverSbFDDP;
+  else if (solver == "SolverBoxFDDP") params_.solver_type = SolverTypes::SolverBoxFDDP;
+  else if (solver == "SolverBoxDDP") params_.solver_type = SolverTypes::SolverBoxDDP;
+  else throw std::out_of_range("map::at");
+  try { params_.callback = params_server_->getParam<bool>(p + "callback"); }
+  catch (const std::exception&) { params_.callback = false; }
+}
+
+// ---- CarrotMpc --------------------------------------------------------------------------------------------------------
+CarrotMpc::CarrotMpc(const std::shared_ptr<Trajectory>& trajectory, const std::vector<VectorXd>& state_ref, std::size_t dt_ref,
+                     const std::string& yaml_path, bool create_solver)
+    : MpcAbstract(yaml_path), trajectory_(trajectory) {
+  defer_solver_ = !create_solver;
+  state_ref_ = state_ref;
+  for (std::size_t i = 0; i < state_ref_.size(); ++i) t_ref_.push_back(dt_ref * i);
+  loadCostParams();
+  const auto& stages = trajectory_->get_stages();
+  t_stages_.reserve(stages.size() + 1);
+  t_stages_.push_back(0);
+  for (std::size_t i = 1; i < stages.size(); ++i) {
+    const std::size_t duration = stages[i - 1]->get_duration() <= params_.dt ? params_.dt : stages[i - 1]->get_duration();
+    t_stages_.push_back(t_stages_.back() + duration);
+  }
+  const std::size_t duration = stages.back()->get_duration() <= params_.dt ? params_.dt : stages.back()->get_duration();
+  t_stages_.push_back(t_stages_.back() + duration);
+  createProblem();
+  update_vars_.state_ref = robot_state_->zero();
+}
+
+void CarrotMpc::loadCostParams() {
+  auto dbl = [&](const char* key, double def) {
+    try { return params_server_->getParam<double>(std::string("mpc_controller/") + key); }
+    catch (const std::exception&) { return def; }
+  };
+  auto vec = [&](const char* key, std::size_t n) {
+    try { return converter<VectorXd>::convert(params_server_->getParam<std::string>(std::string("mpc_controller/") + key)); }
+    catch (const std::exception&) { return VectorXd(n, 1.0); }
+  };
+  const std::size_t ndx = (std::size_t)robot_state_->get_ndx();
+  carrot_weight_ = dbl("carrot_weight", 10.0);
+  carrot_tail_weight_ = dbl("carrot_tail_weight", 5.0);
+  carrot_tail_act_weights_ = vec("carrot_tail_act_weights", ndx);
+  control_reg_weight_ = dbl("carrot_control_reg_weight", 1e-2);
+  control_reg_act_weights_ = vec("carrot_control_reg_act_weights", nu_);
+  state_reg_weight_ = dbl("carrot_state_reg_weight", 1e-3);
+  state_ref_act_weights_ = vec("carrot_state_ref_act_weights", ndx);
+  state_limits_weight_ = dbl("carrot_state_limits_weight", 100);
+  state_limits_act_weights_ = vec("carrot_state_limits_act_weights", ndx);
+  // mandatory (no try/catch in the reference, :162-171); the size checks there construct an exception without throwing
+  state_limits_l_bound_ = converter<VectorXd>::convert(params_server_->getParam<std::string>("mpc_controller/carrot_state_limits_l_bound"));
+  state_limits_u_bound_ = converter<VectorXd>::convert(params_server_->getParam<std::string>("mpc_controller/carrot_state_limits_u_bound"));
+  for (const VectorXd* v : {&carrot_tail_act_weights_, &state_ref_act_weights_, &state_limits_act_weights_, &state_limits_l_bound_, &state_limits_u_bound_})
+    if (v->size() != ndx) throw std::runtime_error("CarrotMPC: a state-sized parameter vector has dimension " + std::to_string(v->size()) +
+                                                   ", should be " + std::to_string(ndx) + " (the reference would read out of bounds here)");
+  if (control_reg_act_weights_.size() != nu_) throw std::runtime_error("CarrotMPC: control regularization weights have the wrong dimension");
+}
+
+std::shared_ptr<CostModelSum> CarrotMpc::createCosts() const {
+  auto costs = std::make_shared<CostModelSum>();
+  const std::size_t ndx = (std::size_t)robot_state_->get_ndx();
+  auto state_cost = [&](ActivationModelTypes t, const VectorXd& w) {
+    auto c = std::make_shared<CostModelResidual>();
+    c->type = CostModelTypes::CostModelState;
+    c->activation.type = t; c->activation.nr = ndx; c->activation.weights = w;
+    c->reference = robot_state_->zero();
+    return c;
+  };
+  costs->addCost("state_reg", state_cost(ActivationModelTypes::ActivationModelWeightedQuad, state_ref_act_weights_), state_reg_weight_, true);
+  auto control = std::make_shared<CostModelResidual>();
+  control->type = CostModelTypes::CostModelControl;
+  control->activation.type = ActivationModelTypes::ActivationModelWeightedQuad; control->activation.nr = nu_;
+  control->activation.weights = control_reg_act_weights_;
+  control->reference.assign(nu_, 0.0);
+  costs->addCost("control_reg", control, control_reg_weight_, true);
+  auto limits = state_cost(ActivationModelTypes::ActivationModelWeightedQuadraticBarrier, state_limits_act_weights_);
+  limits->activation.lb = state_limits_l_bound_; limits->activation.ub = state_limits_u_bound_;
+  for (std::size_t i = 0; i < ndx; ++i) {  // crocoddyl::ActivationBounds(lb, ub, 1)
+    const double m = 0.5 * (limits->activation.lb[i] + limits->activation.ub[i]), d = 0.5 * (limits->activation.ub[i] - limits->activation.lb[i]);
+    limits->activation.lb[i] = m - 1.0 * d; limits->activation.ub[i] = m + 1.0 * d;
+  }
+  costs->addCost("state_limits", limits, state_limits_weight_, true);
+  costs->addCost("carrot_state", state_cost(ActivationModelTypes::ActivationModelQuad, VectorXd()), carrot_weight_, false);
+  costs->addCost("carrot_tail", state_cost(ActivationModelTypes::ActivationModelWeightedQuad, carrot_tail_act_weights_), carrot_tail_weight_, false);
+  return costs;
+}
+
+void CarrotMpc::createProblem() {
+  if (trajectory_->get_has_contact()) throw std::runtime_error("Carrot with contact has not been implemented");
+  if (params_.solver_type != SolverTypes::SolverSbFDDP)
+    throw std::runtime_error("only SolverSbFDDP is part of the B200 hot path (SolverBoxFDDP/BoxDDP: SURVEY.md §8f rank 4)");
+  if (params_.integrator_type != "IntegratedActionModelEuler")
+    throw std::runtime_error("IntegratedActionModelRK4 is not part of the B200 hot path yet");
+  for (std::size_t i = 0; i < params_.knots; ++i) {
+    auto iam = std::make_shared<ActionModel>();
+    iam->costs = createCosts();  // one model per knot (:195-225)
+    iam->dt = double(params_.dt) / 1000.;
+    iam->squash = true;
+    iam->u_lb = platform_params_->u_lb; iam->u_ub = platform_params_->u_ub;
+    int_models_.push_back(iam);
+  }
+  problem_ = std::make_shared<ShootingProblem>();
+  problem_->x0 = robot_state_->zero();
+  problem_->runningModels.assign(int_models_.begin(), int_models_.end() - 1);
+  problem_->terminalModel = int_models_.back();
+  problem_->state = robot_state_;
+  problem_->platform = platform_params_;
+  if (!defer_solver_) attachSolver();
+  else {
+    sbfddp_barrier_init(*problem_, squash_->get_ns(), 1e-3);
+    flatten_problem(*problem_, flat_local_);
+  }
+}
+
+void CarrotMpc::attachSolver() {
+  if (!solver_) solver_ = std::make_shared<SolverSbFDDP>(problem_, squash_, 1, 0);
+}
+
+FlatProblem& CarrotMpc::flat() { return solver_ ? solver_->flat() : flat_local_; }
+
+void CarrotMpc::computeActiveStage(std::size_t t) {
+  update_vars_.idx_stage = std::size_t(std::upper_bound(t_stages_.begin(), t_stages_.end(), t) - t_stages_.begin()) - 1;
+}
+
+void CarrotMpc::computeStateReference(std::size_t time) {
+  update_vars_.idx_state = std::size_t(std::upper_bound(t_ref_.begin(), t_ref_.end(), time) - t_ref_.begin());
+  const std::size_t nq = (std::size_t)robot_state_->get_nq();
+  if (update_vars_.idx_state >= state_ref_.size()) {
+    update_vars_.state_ref = robot_state_->zero();
+    std::copy(state_ref_.back().begin(), state_ref_.back().begin() + (long)nq, update_vars_.state_ref.begin());
+  } else {
+    // alpha = (time - t_ref[i-1]) / (t_ref[i] - t_ref[i-1]) in integer arithmetic == 0  (:391-392): piecewise constant
+    update_vars_.state_ref = state_ref_[update_vars_.idx_state - 1];
+  }
+}
+
+// copy one cost item of knot `knot` into the flat tables and remember the dirty range
+void CarrotMpc::syncCost(std::size_t knot, const std::string& name) {
+  FlatProblem& fl = flat();
+  const int set = fl.node_costset[knot];
+  const FlatProblem::Slot& sl = fl.slots[set].at(name);
+  fill_cost_record(*int_models_[knot]->costs->get_costs().at(name), fl.costs[sl.cost_index], fl.pool.data());
+  dirty_lo_ = std::min(dirty_lo_, sl.cost_index); dirty_hi_ = std::max(dirty_hi_, sl.cost_index);
+}
+
+void CarrotMpc::updateFreeCosts(std::size_t idx) {
+  auto& costs = int_models_[idx]->costs->get_costs();
+  const auto& stages = trajectory_->get_stages();
+  if (update_vars_.idx_stage < stages.size()) {
+    if (!stages[update_vars_.idx_stage]->get_is_transition() || (idx == int_models_.size() - 1)) {
+      costs.at("carrot_state")->active = true;
+      computeStateReference(update_vars_.node_time);
+      costs.at("carrot_state")->cost->reference = update_vars_.state_ref;
+    } else {
+      costs.at("carrot_state")->active = false;
+    }
+    syncCost(idx, "carrot_state");
+  } else {
+    costs.at("carrot_state")->active = false;
+    costs.at("carrot_tail")->active = true;
+    computeStateReference(update_vars_.node_time);
+    costs.at("carrot_tail")->cost->reference = update_vars_.state_ref;
+    syncCost(idx, "carrot_state");
+    syncCost(idx, "carrot_tail");
+  }
+}
+
+void CarrotMpc::updateProblem(const std::size_t& current_time) {
+  computeActiveStage(current_time);
+  update_vars_.idx_last_stage = update_vars_.idx_stage;
+  dirty_lo_ = 1 << 30; dirty_hi_ = -1;
+  for (std::size_t i = 0; i < int_models_.size(); ++i) {
+    update_vars_.node_time = current_time + i * params_.dt;
+    computeActiveStage(update_vars_.node_time);
+    updateFreeCosts(i);
+    update_vars_.idx_last_stage = update_vars_.idx_stage;
+  }
+  if (solver_ && dirty_hi_ >= dirty_lo_) solver_->pushCosts(dirty_lo_, dirty_hi_ - dirty_lo_ + 1);
+}
+
+}  // namespace eagle_mpc

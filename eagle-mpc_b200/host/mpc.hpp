@@ -1,2 +1,88 @@
+// mpc.hpp — MPC controllers on top of the B200 SbFDDP path (host-side mirror of include/eagle_mpc/mpc-base.hpp and
+// include/eagle_mpc/mpc-controllers/carrot-mpc.hpp).  updateProblem() edits the per-knot cost tables exactly like the
+// reference (src/mpc-controllers/carrot-mpc.cpp:298-401) and pushes only the changed records to the device through
+// empc_update_costs.
 #pragma once
 #include "eagle_mpc.hpp"
+
+namespace eagle_mpc {
+
+enum class SolverTypes { SolverSbFDDP, SolverBoxFDDP, SolverBoxDDP };
+
+struct MpcParams {
+  std::string integrator_type;
+  std::size_t knots = 0, iters = 0, dt = 0;
+  SolverTypes solver_type = SolverTypes::SolverSbFDDP;
+  bool callback = false;
+};
+
+class MpcAbstract {
+ public:
+  explicit MpcAbstract(const std::string& yaml_path);
+  virtual ~MpcAbstract() {}
+  virtual void createProblem() = 0;
+  virtual void updateProblem(const std::size_t& current_time) = 0;
+
+  const std::shared_ptr<RobotModel>& get_robot_model() const { return robot_model_; }
+  const std::string& get_robot_model_path() const { return robot_model_path_; }
+  const std::shared_ptr<MultiCopterBaseParams>& get_platform_params() const { return platform_params_; }
+  const std::shared_ptr<StateMultibody>& get_robot_state() const { return robot_state_; }
+  const std::shared_ptr<SquashingModelSmoothSat>& get_squash() const { return squash_; }
+  const std::vector<std::shared_ptr<ActionModel>>& get_int_models() const { return int_models_; }
+  const std::shared_ptr<ShootingProblem>& get_problem() const { return problem_; }
+  const std::shared_ptr<SolverSbFDDP>& get_solver() const { return solver_; }
+  const std::size_t& get_dt() const { return params_.dt; }
+  const std::size_t& get_knots() const { return params_.knots; }
+  const std::size_t& get_iters() const { return params_.iters; }
+
+ protected:
+  void initializeRobotObjects();
+  void loadParams();
+  std::shared_ptr<ParamsServer> params_server_;
+  std::shared_ptr<RobotModel> robot_model_;
+  std::string robot_model_path_;
+  std::shared_ptr<MultiCopterBaseParams> platform_params_;
+  std::shared_ptr<StateMultibody> robot_state_;
+  std::shared_ptr<SquashingModelSmoothSat> squash_;
+  std::size_t nu_ = 0;
+  MpcParams params_;
+  std::vector<std::shared_ptr<ActionModel>> int_models_;
+  std::shared_ptr<ShootingProblem> problem_;
+  std::shared_ptr<SolverSbFDDP> solver_;
+  bool defer_solver_ = false;  // tests flatten the problem on machines without a GPU
+};
+
+class CarrotMpc : public MpcAbstract {
+ public:
+  CarrotMpc(const std::shared_ptr<Trajectory>& trajectory, const std::vector<VectorXd>& state_ref, std::size_t dt_ref,
+            const std::string& yaml_path, bool create_solver = true);
+  void createProblem() override;
+  void updateProblem(const std::size_t& current_time) override;
+  void attachSolver();  // builds the SolverSbFDDP (needs a GPU)
+  const std::shared_ptr<Trajectory>& get_trajectory() const { return trajectory_; }
+  const std::vector<VectorXd>& get_state_ref() const { return state_ref_; }
+  const std::vector<std::size_t>& get_t_stages() const { return t_stages_; }
+  const std::vector<std::size_t>& get_t_ref() const { return t_ref_; }
+  // the flattened problem (kept in sync by updateProblem): for the solver, and for the tests' oracle
+  FlatProblem& flat();
+
+ private:
+  void loadCostParams();
+  std::shared_ptr<CostModelSum> createCosts() const;
+  void computeActiveStage(std::size_t t);
+  void updateFreeCosts(std::size_t idx);
+  void computeStateReference(std::size_t time);
+  void syncCost(std::size_t knot, const std::string& name);
+
+  std::shared_ptr<Trajectory> trajectory_;
+  std::vector<VectorXd> state_ref_;
+  std::vector<std::size_t> t_ref_, t_stages_;
+  double carrot_weight_ = 10, carrot_tail_weight_ = 5, control_reg_weight_ = 1e-2, state_reg_weight_ = 1e-3, state_limits_weight_ = 100;
+  VectorXd carrot_tail_act_weights_, control_reg_act_weights_, state_ref_act_weights_, state_limits_act_weights_,
+      state_limits_l_bound_, state_limits_u_bound_;
+  struct { std::size_t node_time = 0, idx_stage = 0, idx_last_stage = 0, idx_state = 0; VectorXd state_ref; } update_vars_;
+  FlatProblem flat_local_;  // used when no solver is attached
+  int dirty_lo_ = 1 << 30, dirty_hi_ = -1;
+};
+
+}  // namespace eagle_mpc

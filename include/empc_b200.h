@@ -179,6 +179,10 @@ int empc_solve(empc_solver_t* h);
  * restarts every OCP from its stored x0 and initial candidate (used by bench.py's `value` leg). */
 int empc_reset(empc_solver_t* h);
 
+/* RK4 plant step of the closed-loop drivers (bindings/python/eagle_mpc/utils/simulator.py:24-29): n independent
+ * instances, x (n*nx), u (n*nu, thrusts and joint torques actually applied), dt in seconds; host pointers. */
+int empc_plant_step(empc_solver_t* h, const double* x, const double* u, double dt, double* xnext, int32_t n);
+
 /* ---- outputs (host pointers) ---- */
 int empc_get_xs(const empc_solver_t* h, double* xs /* batch*(T+1)*nx */);
 int empc_get_us(const empc_solver_t* h, double* us /* batch*T*nu */);

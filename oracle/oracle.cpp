@@ -641,6 +641,34 @@ double orc_solve_batch(const empc_problem_desc_t* d, const empc_solver_params_t*
   return sec;
 }
 
+// RK4 plant (bindings/python/eagle_mpc/utils/simulator.py:7-29; crocoddyl 1.x IntegratedActionModelRK4::calc) with the
+// plain multicopter actuation: tau = [tau_f u_rotors ; u_arm]
+void orc_plant_step(void* h, const double* x, const double* u, double dt, double* xnext) {
+  Solver* s = (Solver*)h;
+  const orc::Model& m = s->m;
+  double tau[orc::MAXV];
+  for (int i = 0; i < 6; ++i) {
+    double t = 0;
+    for (int j = 0; j < m.nr; ++j) t += s->desc.tau_f[i * m.nr + j] * u[j];
+    tau[i] = t;
+  }
+  for (int i = 0; i < m.na; ++i) tau[6 + i] = u[m.nr + i];
+  const double c[4] = {0.0, 0.5, 0.5, 1.0}, wgt[4] = {1.0, 2.0, 2.0, 1.0};
+  double ksum[orc::MAXDX] = {0}, kprev[orc::MAXDX] = {0}, y[orc::MAXX], dxs[orc::MAXDX];
+  for (int st = 0; st < 4; ++st) {
+    for (int i = 0; i < m.ndx; ++i) dxs[i] = dt * c[st] * kprev[i];
+    if (st == 0) std::memcpy(y, x, sizeof(double) * m.nx);
+    else orc::state_integrate(m, x, dxs, y);
+    orc::Work w;
+    orc::aba(m, y, y + m.nq, tau, w);
+    for (int i = 0; i < m.nv; ++i) { kprev[i] = y[m.nq + i]; kprev[m.nv + i] = w.a[i]; }
+    for (int i = 0; i < m.ndx; ++i) ksum[i] += wgt[st] * kprev[i];
+  }
+  double dx[orc::MAXDX];
+  for (int i = 0; i < m.ndx; ++i) dx[i] = ksum[i] * (dt / 6.0);
+  orc::state_integrate(m, x, dx, xnext);
+}
+
 // ---- math unit-test exports ----
 void orc_exp6(const double* nu, double* R, double* p) { orc::SE3 M; orc::exp6(nu, M); std::memcpy(R, M.R, 72); std::memcpy(p, M.p, 24); }
 void orc_log6(const double* R, const double* p, double* nu) { orc::SE3 M; std::memcpy(M.R, R, 72); std::memcpy(M.p, p, 24); orc::log6(M, nu); }

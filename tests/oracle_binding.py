@@ -193,3 +193,41 @@ def quat_to_R(q):
 
 def R_to_quat(R):
     R = np.ascontiguousarray(R, dtype=np.float64); q = np.zeros(4); lib.orc_R_to_quat(dp(R), dp(q)); return q
+
+
+def oracle_closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, record=False):
+    """CPU twin of eagle-mpc_b200.mpc.closed_loop: same host-side CarrotMpc retargeting (created without a solver),
+    oracle solves and oracle RK4 plant."""
+    import time
+    T = mpc.knots - 1
+    o = Oracle(mpc)
+    lib.orc_update_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Cost), C.c_int, C.c_int, abi.c_double_p]
+    lib.orc_plant_step.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, C.c_double, abi.c_double_p]
+
+    def push():
+        costs, pool = mpc.cost_tables()
+        lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), dp(pool))
+
+    p = default_params()
+    mpc.updateProblem(0); push()
+    p.maxiter = 100; p.convergence_init = 1e-2
+    o.set_params(p); o.set_x0(x_start); o.solve(xs_traj[:T + 1], us_traj[:T])
+    p.maxiter = mpc.iters; p.convergence_init = 1e-3
+    o.set_params(p)
+    x = np.array(x_start, dtype=np.float64)
+    lat, states, controls, iters = [], [x.copy()], [], []
+    t = 0
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        mpc.updateProblem(int(t)); push()
+        o.set_x0(x)
+        o.solve(o.get("xs"), o.get("us"))
+        lat.append(time.perf_counter() - t0)
+        u = o.get("us_squash")[0].copy()
+        xn = np.zeros_like(x)
+        lib.orc_plant_step(o.p, dp(np.ascontiguousarray(x)), dp(np.ascontiguousarray(u)), dt_sim_ms / 1000.0, dp(xn))
+        x = xn
+        t += dt_sim_ms
+        if record:
+            states.append(x.copy()); controls.append(u); iters.append(int(o.get("iter")))
+    return np.array(lat), np.array(states), np.array(controls), iters
