@@ -10,7 +10,7 @@ CU_OBJ := $(PKG)/csrc/solver.o
 
 all: $(LIB) oracle
 
-$(PKG)/csrc/solver.o: $(PKG)/csrc/solver.cu $(PKG)/csrc/kernels.cuh $(PKG)/csrc/node.cuh $(PKG)/csrc/spatial.cuh include/empc_b200.h
+$(PKG)/csrc/solver.o: $(PKG)/csrc/solver.cu $(wildcard $(PKG)/csrc/*.cuh) include/empc_b200.h
 	$(NVCC) $(CUFLAGS) -c -o $@ $<
 
 $(PKG)/host/%.o: $(PKG)/host/%.cpp $(PKG)/host/eagle_mpc.hpp $(PKG)/host/mpc.hpp include/empc_b200.h

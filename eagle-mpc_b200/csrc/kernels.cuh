@@ -22,7 +22,8 @@ struct OcpState {
   double dg0, dq0;     // DDP expected improvement (src/sbfddp.cpp:395-408)
   double gap_inf, gap_l1;
   int phase, iter, total_iters, is_feasible, was_feasible, recalc, bw_fail, iters_out;
-  int accepted, pad_;
+  int accepted;
+  int pending;  // every stage-A step length was rejected: stage B of the line search has to run (rollout.cuh)
 };
 
 struct Buffers {
@@ -122,104 +123,12 @@ __global__ void __launch_bounds__(128, EMPC_CD_MINB) calc_diff_kernel(Buffers bf
 #include "backward.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------------
-struct RoParams {
-  int force, force_feasible, force_ddp;
-  double force_smooth;
-};
-
-template <class D>
-__global__ void __launch_bounds__(32, 9) rollout_kernel(Buffers bf, RoParams P) {
-  constexpr int NX = D::NX, NDX = D::NDX, NU = D::NU;
-  const int nl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (nl >= bf.nb * EMPC_N_ALPHAS) return;
-  const int n = bf.b0 * EMPC_N_ALPHAS + nl;
-  const int b = n / EMPC_N_ALPHAS, ai = n - b * EMPC_N_ALPHAS;
-  const OcpState st = bf.st[b];
-  if (!P.force && (st.phase == PHASE_DONE || st.bw_fail)) return;
-  const int ddp = P.force ? P.force_ddp : (st.phase == PHASE_DDP);
-  const int feasible = P.force ? P.force_feasible : st.is_feasible;
-  const double smooth = P.force ? P.force_smooth : st.smooth;
-  const double alpha = 1.0 / (double)(1 << ai);
-  const DevModel& M = *bf.model;
-  const int T = bf.T, T1 = T + 1;
-  const size_t nb = (size_t)b * T1;
-  const size_t trial = (size_t)ai * bf.B + b;
-  double* xs_try = bf.xs_try + trial * T1 * NX;
-  double* us_try = bf.us_try + trial * T * NU;
-  const bool plain = ddp || feasible || ai == 0;
-
-  double xn[NX];  // running state (xnext)
-  if (ddp) {
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xn[i] = bf.xs_try0[(size_t)b * NX + i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xn[i] = bf.x0[(size_t)b * NX + i];
-  }
-  double cost_try = 0, dv = 0;
-  int ok = 1;
-  for (int t = 0; t <= T; ++t) {
-    double xt[NX];
-    if (plain) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) xt[i] = xn[i];
-    } else {
-      double gap[NDX];
-#pragma unroll
-      for (int i = 0; i < NDX; ++i) gap[i] = bf.fs[(nb + t) * NDX + i] * (alpha - 1);
-      state_integrate<D>(xn, gap, xt);
-    }
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xs_try[(size_t)t * NX + i] = xt[i];
-    double x0t[NX], dx[NDX];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) x0t[i] = bf.xs[(nb + t) * NX + i];
-    state_diff<D>(x0t, xt, dx);
-    if (!ddp && !feasible) {
-      // dv -= fs . Vxx diff(xs_try, xs)  ==  + (Vxx fs) . diff(xs, xs_try)   (Vxx symmetric)
-      double s = 0;
-#pragma unroll
-      for (int i = 0; i < NDX; ++i) s += bf.g[(nb + t) * NDX + i] * dx[i];
-      dv += s;
-    }
-    double u[NU];
-    const int costset = bf.node_costset[bf.ocp_map[b] * T1 + t];
-    NodeData<D> nd;
-    double c;
-    if (t < T) {
-      const double* Kg = bf.K + ((size_t)b * T + t) * NU * NDX;
-      const double* kg = bf.k + ((size_t)b * T + t) * NU;
-      const double* ug = bf.us + ((size_t)b * T + t) * NU;
-#pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        double kd = 0;
-#pragma unroll
-        for (int j = 0; j < NDX; ++j) kd += Kg[i * NDX + j] * dx[j];
-        u[i] = ug[i] - kg[i] * alpha - kd;
-        us_try[(size_t)t * NU + i] = u[i];
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < NU; ++i) u[i] = 0.0;
-    }
-    node_calc<D>(M, bf.ct, costset, smooth, xt, u, nd, xn, c);
-    cost_try += c;
-    if (isnan(cost_try)) { ok = 0; break; }
-    if (t < T) {
-      bool bad = false;
-#pragma unroll
-      for (int i = 0; i < NX; ++i) bad |= isnan(xn[i]);
-      if (bad) { ok = 0; break; }
-    }
-  }
-  bf.cost_try[n] = cost_try;
-  bf.dv[n] = dv;
-  bf.ok[n] = ok;
-}
+#include "rollout.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------------
 struct DecideParams {
   empc_solver_params_t P;
+  int stage;  // 0: after rollout stage A (step lengths [0, RO_WIDTH_A)); 1: after stage B, pending OCPs only
 };
 
 __device__ __forceinline__ void increase_reg(OcpState& st, const empc_solver_params_t& P) {
@@ -266,13 +175,16 @@ __global__ void __launch_bounds__(128) decide_kernel(Buffers bf, DecideParams dp
   if (threadIdx.x == 0) {
     OcpState st = bf.st[b];
     int acc = -1, last = -1;
-    if (st.phase != PHASE_DONE) {
+    const int n_begin = dp.stage == 0 ? 0 : RO_WIDTH_A, n_end = dp.stage == 0 ? RO_WIDTH_A : EMPC_N_ALPHAS;
+    const bool mine = st.phase != PHASE_DONE && (dp.stage == 0 || st.pending);
+    if (mine) {
+      if (dp.stage == 1) { st.pending = 0; atomicSub(bf.n_active, 1); }  // re-counted below if still active
       if (st.bw_fail) {
         st.bw_fail = 0;
         end_inner_solve(st, P);  // computeDirection gave up at reg_max: the inner solve returns false
       } else {
         const int ddp = st.phase == PHASE_DDP;
-        for (int n = 0; n < EMPC_N_ALPHAS; ++n) {
+        for (int n = n_begin; n < n_end; ++n) {
           st.steplength = 1.0 / (double)(1 << n);
           last = n;
           if (!bf.ok[b * EMPC_N_ALPHAS + n]) continue;  // "forward_error": try the next step length
@@ -299,6 +211,14 @@ __global__ void __launch_bounds__(128) decide_kernel(Buffers bf, DecideParams dp
             acc = n;
             break;
           }
+        }
+        if (acc < 0 && n_end < EMPC_N_ALPHAS) {
+          // none of the stage-A step lengths passed: the smaller ones are evaluated by rollout stage B, then decide again
+          st.pending = 1;
+          atomicAdd(bf.n_active, 1);
+          bf.st[b] = st;
+          s_acc = -1; s_last = -1;
+          goto decided;
         }
         st.recalc = acc >= 0 ? 1 : 0;
         st.accepted = acc;
@@ -328,6 +248,7 @@ __global__ void __launch_bounds__(128) decide_kernel(Buffers bf, DecideParams dp
       bf.st[b] = st;
     }
     s_acc = acc; s_last = last;
+  decided:;
   }
   __syncthreads();
   const int acc = s_acc, last = s_last;
@@ -357,7 +278,7 @@ __global__ void init_state_kernel(Buffers bf, empc_solver_params_t P, int is_fea
   st.xreg = P.reg_init; st.cost = 0; st.cost_prev = bf.st[b].cost_prev; st.stop = 0; st.steplength = 1;
   st.dg = st.dq = st.dg0 = st.dq0 = 0; st.gap_inf = 0; st.gap_l1 = 0;
   st.iter = 0; st.total_iters = 0; st.is_feasible = 0; st.was_feasible = 0; st.recalc = 1; st.bw_fail = 0;
-  st.iters_out = 0; st.accepted = -1; st.pad_ = 0;
+  st.iters_out = 0; st.accepted = -1; st.pending = 0;
   (void)is_feasible_arg;  // solveFDDP(maxiter, false, ...) overrides the caller's flag (src/sbfddp.cpp:210,230)
   if (P.convergence_init >= P.convergence_stop) st.phase = PHASE_FDDP;
   else { st.phase = is_feasible_arg ? PHASE_DONE : PHASE_DDP; st.is_feasible = is_feasible_arg; }
@@ -446,6 +367,7 @@ __global__ void override_state_kernel(Buffers bf, double xreg, int is_feasible, 
   if (set_xreg) bf.st[b].xreg = xreg;
   bf.st[b].is_feasible = is_feasible;
   bf.st[b].bw_fail = 0;
+  bf.st[b].pending = 0;
 }
 
 }  // namespace empc

@@ -50,7 +50,7 @@ struct Dim {
 template <class D>
 struct NodeData {
   SE3 oM[D::NJ];
-  SE3 li[D::NJ];
+  double liR[D::NJ][9];  // rotation of the joint placement in the parent frame (its translation is the constant jp)
   double v[D::NJ][6];
   double agf[D::NJ][6];
   double a[D::NV];
@@ -244,7 +244,7 @@ EMPC_DI void squash(const DevModel& M, double smooth, const double* u, double* s
       const double lbv = M.u_lb[i], ubv = M.u_ub[i];
       const double dd = (ubv - lbv) * smooth, a = dd * dd;
       const double l = u[i] - lbv, h = u[i] - ubv;
-      s[i] = 0.5 * (sqrt(l * l + a) - sqrt(h * h + a) + lbv + ubv);
+      s[i] = 0.5 * (sqrt_nr(l * l + a) - sqrt_nr(h * h + a) + lbv + ubv);
     } else {
       s[i] = u[i];
     }
@@ -263,40 +263,53 @@ EMPC_DI void inertia_apply(double m, const double* c, const double* Ic, const do
   for (int i = 0; i < 3; ++i) { o[i] = f[i]; o[3 + i] = Iw[i] + cxf[i]; }
 }
 
-// pinocchio::aba for free-flyer + serial revolute chain (local-frame three-pass recursion).
-// The backward pass carries ONE articulated inertia (the contribution of the subtree, expressed in the current joint
-// frame) instead of one per joint, so the working set stays in registers.
-template <class D>
-EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData<D>& nd) {
-  constexpr int NJ = D::NJ, NV = D::NV;
-  double uu[NV];
-  double Dinv[NJ], UDinv[NJ][6];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) uu[i] = tau[i];
+// pinocchio::aba for free-flyer + serial revolute chain (local-frame three-pass recursion), split in two:
+//   aba_kinematics  pass 1: placements, velocities, bias accelerations  (everything the costs need)
+//   aba_dynamics    pass 2 + 3: articulated inertias tip to base, accelerations base to tip
+// so that callers can evaluate the costs in between and let the world placements die before the register-hungry
+// backward sweep.  The backward pass carries ONE articulated inertia (the contribution of the subtree, expressed in the
+// current joint frame) instead of one per joint.  The translation of a joint placement li[i] is the model constant
+// jp[i] (the revolute joint transform has no translation), so only the rotations are kept.
+// FULL: unroll the joint loops completely, so that every NodeData / model access has a static index (registers and
+// constant-bank operands instead of local memory); used where the register budget allows it.
+template <class D, bool FULL = false>
+EMPC_DI void aba_kinematics(const DevModel& M, const double* x, NodeData<D>& nd) {
+  constexpr int NJ = D::NJ;
+  constexpr int UNR = FULL ? NJ : 1;
   const double* vq = x + D::NQ;
-  // pass 1: placements, velocities, bias accelerations
-  q_to_se3(x, nd.li[0]);
-  nd.oM[0] = nd.li[0];
+  q_to_se3(x, nd.oM[0]);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) nd.liR[0][k] = nd.oM[0].R[k];
 #pragma unroll
   for (int k = 0; k < 6; ++k) { nd.v[0][k] = vq[k]; nd.agf[0][k] = 0; }
-#pragma unroll 1
+#pragma unroll UNR
   for (int i = 1; i < NJ; ++i) {
     const double th = x[6 + i];
     double ax[3] = {M.axis[i][0] * th, M.axis[i][1] * th, M.axis[i][2] * th};
-    SE3 Mj; exp3(ax, Mj.R); Mj.p[0] = Mj.p[1] = Mj.p[2] = 0;
-    SE3 Jp;
+    double Rj[9]; exp3(ax, Rj);
+    matmul3(M.jR[i], Rj, nd.liR[i]);
+    SE3 li;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Jp.R[k] = M.jR[i][k];
+    for (int k = 0; k < 9; ++k) li.R[k] = nd.liR[i][k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) Jp.p[k] = M.jp[i][k];
-    se3_mul(Jp, Mj, nd.li[i]);
-    se3_mul(nd.oM[i - 1], nd.li[i], nd.oM[i]);
+    for (int k = 0; k < 3; ++k) li.p[k] = M.jp[i][k];
+    se3_mul(nd.oM[i - 1], li, nd.oM[i]);
     double vJ[6] = {0, 0, 0, M.axis[i][0] * vq[5 + i], M.axis[i][1] * vq[5 + i], M.axis[i][2] * vq[5 + i]};
-    double vp[6]; actinv_motion(nd.li[i], nd.v[i - 1], vp);
+    double vp[6]; actinv_motion(li, nd.v[i - 1], vp);
 #pragma unroll
     for (int k = 0; k < 6; ++k) nd.v[i][k] = vJ[k] + vp[k];
     cross_mm(nd.v[i], vJ, nd.agf[i]);
   }
+}
+
+template <class D, bool FULL = false>
+EMPC_DI void aba_dynamics(const DevModel& M, const double* tau, NodeData<D>& nd) {
+  constexpr int NJ = D::NJ, NV = D::NV;
+  constexpr int UNR = FULL ? NJ : 1;
+  double uu[NV];
+  double Dinv[NJ], UDinv[NJ][6];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) uu[i] = tau[i];
   // pass 2: tip to base with ONE running articulated inertia, kept as 3x3 blocks Ia = [[A, B],[B^T, C]] and moved to
   // the parent frame with the block form of X* Ia X*^T (X* = [[R,0],[[p]x R, R]]):
   //   A' = R A R^T,  B' = R B R^T - A'[p]x,  C' = R C R^T + [p]x B' - (R B R^T)^T [p]x
@@ -305,7 +318,7 @@ EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData
   for (int k = 0; k < 9; ++k) { A[k] = 0.0; Bk[k] = 0.0; C[k] = 0.0; }
 #pragma unroll
   for (int k = 0; k < 6; ++k) pA[k] = 0.0;
-#pragma unroll 1
+#pragma unroll UNR
   for (int i = NJ - 1; i >= 1; --i) {
     {  // Ia += Y_i ; pA += v x* (Y v)
       double h[6], vh[6];
@@ -325,7 +338,7 @@ EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData
     uu[c] -= ax[0] * pA[3] + ax[1] * pA[4] + ax[2] * pA[5];
     double U[6];  // U = Ia S, S = [0; ax]
     matvec3(Bk, ax, U); matvec3(C, ax, U + 3);
-    Dinv[i] = 1.0 / dot3(ax, U + 3);
+    Dinv[i] = rcp_nr(dot3(ax, U + 3));
 #pragma unroll
     for (int k = 0; k < 6; ++k) UDinv[i][k] = U[k] * Dinv[i];
 #pragma unroll
@@ -348,7 +361,12 @@ EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData
       }
     }
     {  // carry to the parent frame
-      const double* R = nd.li[i].R; const double* p = nd.li[i].p;
+      SE3 li;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) li.R[k] = nd.liR[i][k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) li.p[k] = M.jp[i][k];
+      const double* R = li.R; const double* p = li.p;
       double T1[9], An[9], Bt[9], Cn[9], P[9];
       matmul3(R, A, T1);
 #pragma unroll
@@ -374,7 +392,7 @@ EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData
       matTmul3(Bt, P, BtP);
 #pragma unroll
       for (int k = 0; k < 9; ++k) { A[k] = An[k]; Bk[k] = Bn[k]; C[k] = Cn[k] + PB[k] - BtP[k]; }
-      act_force(nd.li[i], pa, pA);
+      act_force(li, pa, pA);
     }
   }
   double Ia[36];
@@ -398,7 +416,14 @@ EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData
   llt_inplace_inv<6>(Ia, Iinv);
   // pass 3
   {
-    double g[6]; actinv_motion(nd.oM[0], M.a0, g);
+    double g[6];
+    {  // gravity in the base frame: oM[0]^-1 acting on a0 = (-gravity, 0); oM[0].R is liR[0]
+      SE3 o0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) o0.R[k] = nd.liR[0][k];
+      o0.p[0] = o0.p[1] = o0.p[2] = 0.0;  // a0 has no angular part, so the translation does not enter
+      actinv_motion(o0, M.a0, g);
+    }
 #pragma unroll
     for (int k = 0; k < 6; ++k) nd.agf[0][k] += g[k];
     double rhs[6];
@@ -410,9 +435,14 @@ EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData
 #pragma unroll
     for (int k = 0; k < 6; ++k) nd.agf[0][k] += nd.a[k];
   }
-#pragma unroll 1
+#pragma unroll UNR
   for (int i = 1; i < NJ; ++i) {
-    double ap[6]; actinv_motion(nd.li[i], nd.agf[i - 1], ap);
+    SE3 li;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) li.R[k] = nd.liR[i][k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) li.p[k] = M.jp[i][k];
+    double ap[6]; actinv_motion(li, nd.agf[i - 1], ap);
 #pragma unroll
     for (int k = 0; k < 6; ++k) nd.agf[i][k] += ap[k];
     const int c = 5 + i;
@@ -422,8 +452,14 @@ EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData
   }
 }
 
+template <class D, bool FULL = false>
+EMPC_DI void aba(const DevModel& M, const double* x, const double* tau, NodeData<D>& nd) {
+  aba_kinematics<D, FULL>(M, x, nd);
+  aba_dynamics<D, FULL>(M, tau, nd);
+}
+
 // IntegratedActionModelEuler::calc.  u == nullptr => terminal convention u = 0.
-template <class D>
+template <class D, bool FULL = false>
 EMPC_DI void node_calc(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x,
                        const double* u, NodeData<D>& nd, double* xnext, double& cost) {
   squash<D>(M, smooth, u, nd.s);
@@ -437,14 +473,9 @@ EMPC_DI void node_calc(const DevModel& M, const CostTables& C, int costset, doub
   }
 #pragma unroll
   for (int i = 0; i < D::NA; ++i) tau[6 + i] = nd.s[D::NR + i];
-  aba<D>(M, x, tau, nd);
-  const double dt = M.dt, dt2 = dt * dt;
-#pragma unroll
-  for (int i = 0; i < D::NV; ++i) {
-    nd.dx[i] = x[D::NQ + i] * dt + nd.a[i] * dt2;
-    nd.dx[D::NV + i] = nd.a[i] * dt;
-  }
-  state_integrate<D>(x, nd.dx, xnext);
+  aba_kinematics<D, FULL>(M, x, nd);
+  // costs depend on (x, u) and the kinematics only: evaluated before the dynamics sweep so that the world placements
+  // need not stay live across it
   double csum = 0;
   const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
   for (int c = c0; c < c1; ++c) {
@@ -454,6 +485,14 @@ EMPC_DI void node_calc(const DevModel& M, const CostTables& C, int costset, doub
     SE3 rMf;
     csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
   }
+  aba_dynamics<D, FULL>(M, tau, nd);
+  const double dt = M.dt, dt2 = dt * dt;
+#pragma unroll
+  for (int i = 0; i < D::NV; ++i) {
+    nd.dx[i] = x[D::NQ + i] * dt + nd.a[i] * dt2;
+    nd.dx[D::NV + i] = nd.a[i] * dt;
+  }
+  state_integrate<D>(x, nd.dx, xnext);
   cost = dt * csum;
 }
 
@@ -630,7 +669,7 @@ EMPC_DI void node_calc_diff(const DevModel& M, const CostTables& C, int costset,
       const double lbv = M.u_lb[i], ubv = M.u_ub[i];
       const double dd = (ubv - lbv) * smooth, a = dd * dd;
       const double l = u[i] - lbv, h = u[i] - ubv;
-      ds[i] = 0.5 * ((1.0 / sqrt(a + l * l)) * l - (1.0 / sqrt(a + h * h)) * h);
+      ds[i] = 0.5 * (rsqrt_nr(a + l * l) * l - rsqrt_nr(a + h * h) * h);
     } else {
       ds[i] = 1.0;
     }

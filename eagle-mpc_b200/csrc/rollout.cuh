@@ -1,0 +1,205 @@
+// rollout.cuh — nonlinear forward rollouts of the line search, all EMPC_N_ALPHAS step lengths of an OCP concurrently
+// (included from kernels.cuh inside namespace empc).
+//
+// Replaces crocoddyl::SolverFDDP::forwardPass / SolverSbFDDP::forwardPassDDP as called by tryStep / tryStepDDP
+// (src/sbfddp.cpp:264, :410-460).  The reference tries the step lengths one after the other and stops at the first
+// accepted one; the trials are independent, so the device evaluates all of them at once and decide_kernel picks the
+// first accepted in the reference's order.
+//
+// Speculation width: a launch evaluates W consecutive step lengths per OCP.  Stage A (W = 4: alpha = 1 .. 1/8) runs for
+// every active OCP; stage B (the remaining 1/16 .. 1/512) only for the OCPs whose stage-A trials were all rejected
+// (decide_kernel flags them `pending`), which is rare — so the common case costs 4 rollouts per OCP instead of 10 and one
+// warp per SM sub-partition with the full register file, not 10 trials squeezed into 168 registers.
+//
+// Mapping: one warp = 32/W OCPs x W step lengths, one lane per trial, sequential in t.  The chain
+// x_t -> u_t -> ABA -> x_{t+1} is latency-bound, so the kernel is organised around per-node latency:
+//   * the per-node inputs shared by the 10 trials of an OCP (xs, us, k, fs, Vxx.fs, K: 235 doubles for flying_arm_3) are
+//     fetched one node ahead with cp.async into a double-buffered shared-memory stage (coalesced, read once per OCP
+//     instead of once per trial) and read back as shared-memory broadcasts;
+//   * the robot model comes in as a __grid_constant__ kernel parameter: with the joint loops fully unrolled every model
+//     access is a constant-bank operand and the kinematic chain stays in registers (no local-memory NodeData);
+//   * each lane streams its own xs_try / us_try rows straight from registers (L2 merges the partial sectors).
+#pragma once
+
+struct RoParams {
+  int force, force_feasible, force_ddp;
+  double force_smooth;
+  int a_begin;  // first step-length index of this launch (0: stage A, RO_WIDTH_A: stage B)
+};
+
+constexpr int RO_WIDTH_A = 4;  // step lengths tried by stage A (alpha index 0..3); stage B covers the rest
+
+template <class D, int W>
+struct RoCfg {
+  static constexpr int NX = D::NX, NDX = D::NDX, NU = D::NU;
+  static constexpr int OCPS = 32 / W;  // OCPs per warp
+  // stage of one OCP and one node (doubles).  16-byte aligned members first (NDX and NU*NDX are even).
+  static constexpr int oK = 0, oFs = oK + NU * NDX, oG = oFs + NDX, oXs = oG + NDX, oUs = oXs + NX, oKk = oUs + NU,
+                       STAGE0 = oKk + NU, STAGE = STAGE0 + (STAGE0 & 1);
+  static constexpr int SMEM_DOUBLES = 2 * OCPS * STAGE;
+};
+
+EMPC_DI void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+EMPC_DI void cp_async16(double* smem_dst, const double* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+EMPC_DI void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+EMPC_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <class D, int W>
+__global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, const __grid_constant__ DevModel M) {
+  constexpr int NX = D::NX, NDX = D::NDX, NU = D::NU;
+  using S = RoCfg<D, W>;
+  extern __shared__ __align__(16) double ro_sm[];
+  const int lane = threadIdx.x;
+  const int o = lane / W;                              // OCP slot of this lane
+  const int j = lane - o * W;                          // position among the lanes of the slot
+  const int ai = P.a_begin + j;                        // step-length index of this lane (>= EMPC_N_ALPHAS: idle lane)
+  const int bl = blockIdx.x * S::OCPS + o;             // OCP of this lane, relative to the window
+  const int T = bf.T, T1 = T + 1;
+  const bool has_ocp = bl < bf.nb;
+  const int b = bf.b0 + (has_ocp ? bl : 0);
+
+  bool slot_on = has_ocp;                              // the OCP takes part in this launch (all its lanes agree)
+  int ddp = 0, feasible = 0;
+  double smooth = 0.0;
+  {
+    const OcpState st = bf.st[b];
+    if (!P.force && (st.phase == PHASE_DONE || st.bw_fail || (P.a_begin > 0 && !st.pending))) slot_on = false;
+    ddp = P.force ? P.force_ddp : (st.phase == PHASE_DDP);
+    feasible = P.force ? P.force_feasible : st.is_feasible;
+    smooth = P.force ? P.force_smooth : st.smooth;
+  }
+  if (__ballot_sync(0xffffffffu, slot_on) == 0) return;
+  const bool mine = slot_on && ai < EMPC_N_ALPHAS;     // this lane owns a trial
+  bool active = mine;
+
+  const double alpha = 1.0 / (double)(1 << (ai < EMPC_N_ALPHAS ? ai : 0));
+  const bool plain = ddp || feasible || ai == 0;
+  const int* costsets = bf.node_costset + (size_t)bf.ocp_map[b] * T1;
+  const size_t trial = (size_t)(ai < EMPC_N_ALPHAS ? ai : 0) * bf.B + b;
+  double* xs_try = bf.xs_try + trial * T1 * NX;
+  double* us_try = bf.us_try + trial * T * NU;
+
+  // Asynchronous fetch of node t: the W lanes of a slot copy their own OCP's record (K | fs | g | xs | us | k) in
+  // interleaved 16-byte (8-byte where the row length is odd) pieces; no loop over slots, constant offsets only.
+  double* my_stage = ro_sm + (size_t)o * S::STAGE;
+  auto prefetch = [&](int t, int buf) {
+    if (slot_on) {
+      double* dst = my_stage + (size_t)buf * S::OCPS * S::STAGE;
+      const size_t node = (size_t)b * T1 + t;
+      const double* fs = bf.fs + node * NDX;
+      const double* g = bf.g + node * NDX;
+      const double* xs = bf.xs + node * NX;
+#pragma unroll
+      for (int c = 0; c < (NDX / 2 + W - 1) / W; ++c) {
+        const int i = j + c * W;
+        if (i < NDX / 2) { cp_async16(dst + S::oFs + 2 * i, fs + 2 * i); cp_async16(dst + S::oG + 2 * i, g + 2 * i); }
+      }
+#pragma unroll
+      for (int c = 0; c < (NX + W - 1) / W; ++c) {
+        const int i = j + c * W;
+        if (i < NX) cp_async8(dst + S::oXs + i, xs + i);
+      }
+      if (t < T) {
+        const size_t nodeu = (size_t)b * T + t;
+        const double* Kg = bf.K + nodeu * NU * NDX;
+        const double* us = bf.us + nodeu * NU;
+        const double* kg = bf.k + nodeu * NU;
+#pragma unroll
+        for (int c = 0; c < (NU * NDX / 2 + W - 1) / W; ++c) {
+          const int i = j + c * W;
+          if (i < NU * NDX / 2) cp_async16(dst + S::oK + 2 * i, Kg + 2 * i);
+        }
+#pragma unroll
+        for (int c = 0; c < (NU + W - 1) / W; ++c) {
+          const int i = j + c * W;
+          if (i < NU) { cp_async8(dst + S::oUs + i, us + i); cp_async8(dst + S::oKk + i, kg + i); }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  double xn[NX];  // running state (xnext of the previous node)
+  {
+    const double* src = ddp ? (bf.xs_try0 + (size_t)b * NX) : (bf.x0 + (size_t)b * NX);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xn[i] = src[i];
+  }
+  double cost_try = 0, dv = 0;
+  int ok = 1;
+
+  prefetch(0, 0);
+  for (int t = 0; t <= T; ++t) {
+    if (t < T) { prefetch(t + 1, (t + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncwarp();
+    const double* in = my_stage + (size_t)(t & 1) * S::OCPS * S::STAGE;
+    if (active) {
+      double xt[NX];
+      if (plain) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xt[i] = xn[i];
+      } else {
+        double gap[NDX];
+#pragma unroll
+        for (int i = 0; i < NDX; ++i) gap[i] = in[S::oFs + i] * (alpha - 1);
+        state_integrate<D>(xn, gap, xt);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xs_try[(size_t)t * NX + i] = xt[i];
+      double dx[NDX];
+      {
+        double x0t[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x0t[i] = in[S::oXs + i];
+        state_diff<D>(x0t, xt, dx);
+      }
+      if (!ddp && !feasible) {
+        // dv -= fs . Vxx diff(xs_try, xs)  ==  + (Vxx fs) . diff(xs, xs_try)   (Vxx symmetric)
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < NDX; ++i) s += in[S::oG + i] * dx[i];
+        dv += s;
+      }
+      double u[NU];
+      if (t < T) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double kd = 0;
+#pragma unroll
+          for (int jj = 0; jj < NDX; ++jj) kd += in[S::oK + i * NDX + jj] * dx[jj];
+          u[i] = in[S::oUs + i] - in[S::oKk + i] * alpha - kd;
+          us_try[(size_t)t * NU + i] = u[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = 0.0;
+      }
+      NodeData<D> nd;
+      double c;
+      node_calc<D, true>(M, bf.ct, costsets[t], smooth, xt, u, nd, xn, c);
+      cost_try += c;
+      bool bad = isnan(cost_try);
+      if (t < T) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) bad |= isnan(xn[i]);
+      }
+      if (bad) { ok = 0; active = false; }  // "forward_error": this step length is skipped by decide_kernel
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0) break;  // every trial of this warp hit a forward error
+    __syncwarp();  // this node's shared-memory reads are done before the next prefetch overwrites the other buffer
+  }
+  cp_async_wait<0>();
+  if (mine) {
+    const size_t n = (size_t)b * EMPC_N_ALPHAS + ai;
+    bf.cost_try[n] = cost_try;
+    bf.dv[n] = dv;
+    bf.ok[n] = ok;
+  }
+}

@@ -356,23 +356,38 @@ static cudaError_t launch_backward(empc_solver* h, int force, const Buffers* gb 
   h->launches++;
   return cudaGetLastError();
 }
-template <class D>
-static cudaError_t launch_rollout(empc_solver* h, int force, int feasible, int ddp, double smooth, const Buffers* gb = nullptr,
-                                  cudaStream_t st = nullptr) {
-  const Buffers& bf = gb ? *gb : h->bf;
-  if (!st) st = h->stream;
-  const int n = bf.nb * EMPC_N_ALPHAS;
-  RoParams P{force, feasible, ddp, smooth};
-  // one warp per block, >= 9 resident blocks per SM: 4096 OCPs x 10 step lengths = 1280 warps fit in a single wave
-  rollout_kernel<D><<<(n + 31) / 32, 32, 0, st>>>(bf, P);
+template <class D, int W>
+static cudaError_t launch_rollout_w(empc_solver* h, const RoParams& P, const Buffers& bf, cudaStream_t st) {
+  using S = RoCfg<D, W>;
+  const size_t smem = sizeof(double) * S::SMEM_DOUBLES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rollout_kernel<D, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rollout_kernel<D, W>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  // one warp per block = 32/W OCPs x W step lengths
+  rollout_kernel<D, W><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
   h->launches++;
   return cudaGetLastError();
 }
+// stage 0: step lengths [0, RO_WIDTH_A) of every active OCP; stage 1: the remaining ones, pending OCPs only
 template <class D>
-static cudaError_t launch_decide(empc_solver* h, const Buffers* gb = nullptr, cudaStream_t st = nullptr) {
+static cudaError_t launch_rollout(empc_solver* h, int stage, int force, int feasible, int ddp, double smooth, const Buffers* gb = nullptr,
+                                  cudaStream_t st = nullptr) {
   const Buffers& bf = gb ? *gb : h->bf;
   if (!st) st = h->stream;
-  DecideParams dp{h->P};
+  RoParams P{force, feasible, ddp, smooth, stage == 0 ? 0 : RO_WIDTH_A};
+  if (stage == 0) return launch_rollout_w<D, RO_WIDTH_A>(h, P, bf, st);
+  return launch_rollout_w<D, 8>(h, P, bf, st);
+}
+template <class D>
+static cudaError_t launch_decide(empc_solver* h, int stage, const Buffers* gb = nullptr, cudaStream_t st = nullptr) {
+  const Buffers& bf = gb ? *gb : h->bf;
+  if (!st) st = h->stream;
+  DecideParams dp{h->P, stage};
   decide_kernel<D><<<bf.nb, 128, 0, st>>>(bf, dp);
   h->launches++;
   return cudaGetLastError();
@@ -409,10 +424,13 @@ static int solve_impl(empc_solver* h) {
       if (h->timing) CK(cudaEventRecord(h->ev[1], h->stream));
       CK(launch_backward<D>(h, 0));
       if (h->timing) CK(cudaEventRecord(h->ev[2], h->stream));
-      CK(launch_rollout<D>(h, 0, 0, 0, 0.0));
+      CK(launch_rollout<D>(h, 0, 0, 0, 0, 0.0));
       if (h->timing) CK(cudaEventRecord(h->ev[3], h->stream));
       CK(cudaMemsetAsync(h->bf.n_active, 0, 2 * sizeof(int), h->stream));
-      CK(launch_decide<D>(h));
+      CK(launch_decide<D>(h, 0));
+      // stage B of the line search: no-ops unless some OCP rejected every stage-A step length
+      CK(launch_rollout<D>(h, 1, 0, 0, 0, 0.0));
+      CK(launch_decide<D>(h, 1));
       if (h->timing) CK(cudaEventRecord(h->ev[4], h->stream));
       CK(cudaMemcpyAsync(h->h_active, h->bf.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
@@ -459,9 +477,11 @@ static int solve_impl(empc_solver* h) {
         CK(launch_calc_diff<D>(h, 0, 0.0, &gb[g], st));
         CK(launch_backward<D>(h, 0, &gb[g], st));
         if (it == 0) CK(cudaEventRecord(h->ev_skew[g], st));
-        CK(launch_rollout<D>(h, 0, 0, 0, 0.0, &gb[g], st));
+        CK(launch_rollout<D>(h, 0, 0, 0, 0, 0.0, &gb[g], st));
         CK(cudaMemsetAsync(gb[g].n_active, 0, 2 * sizeof(int), st));
-        CK(launch_decide<D>(h, &gb[g], st));
+        CK(launch_decide<D>(h, 0, &gb[g], st));
+        CK(launch_rollout<D>(h, 1, 0, 0, 0, 0.0, &gb[g], st));
+        CK(launch_decide<D>(h, 1, &gb[g], st));
         CK(cudaMemcpyAsync(h->h_active + (g * 2 + slot) * 2, gb[g].n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(h->ev_it[g][slot], st));
       }
@@ -639,7 +659,8 @@ int empc_phase_backward(empc_solver_t* h, double xreg, int32_t is_feasible, int3
 int empc_phase_rollout(empc_solver_t* h, double smooth, int32_t is_feasible, int32_t ddp) {
   if (!h) return fail(EMPC_ERR_INVALID, "null");
   CK(cudaSetDevice(h->device));
-  EMPC_DISPATCH(h, CK(launch_rollout<D>(h, 1, is_feasible, ddp, smooth)));
+  EMPC_DISPATCH(h, CK(launch_rollout<D>(h, 0, 1, is_feasible, ddp, smooth)));
+  EMPC_DISPATCH(h, CK(launch_rollout<D>(h, 1, 1, is_feasible, ddp, smooth)));
   CK(cudaStreamSynchronize(h->stream));
   return EMPC_OK;
 }

@@ -18,6 +18,35 @@ struct SE3 {
   double p[3];
 };
 
+// ---- branch-free reciprocal square root / square root / reciprocal --------------------------------------------------
+// The library sqrt() and 1/x expand to a MUFU seed, Newton steps AND a branch to a slow path for denormal / huge
+// operands (BSSY/BSYNC + a call): ~25 instructions and a fetch bubble each, ~80 times per node.  The quantities that
+// go through these helpers (squashing radicands, Cholesky pivots, articulated joint inertias) are positive normal
+// numbers, so the MUFU seed (2^-22 relative) plus two Newton steps (-> rounding level, <= 2 ulp) is enough; the
+// deviation from the correctly rounded value is ~1e-16 relative, far below the 1e-9 parity bar.
+EMPC_DI double rsqrt_nr(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double h = 0.5 * x;
+  r = r * fma(-h * r, r, 1.5);
+  r = r * fma(-h * r, r, 1.5);
+  return r;
+}
+// sqrt(x) for x >= 0 (0 -> 0, negative -> NaN like sqrt)
+EMPC_DI double sqrt_nr(double x) {
+  const double r = rsqrt_nr(x);
+  double s = x * r;
+  s = fma(fma(-s, s, x), 0.5 * r, s);
+  return x == 0.0 ? 0.0 : s;
+}
+EMPC_DI double rcp_nr(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
 EMPC_DI void cross3(const double* a, const double* b, double* o) {
   const double x = a[1] * b[2] - a[2] * b[1];
   const double y = a[2] * b[0] - a[0] * b[2];
@@ -420,9 +449,8 @@ EMPC_DI bool llt_inplace_inv(double* A, double* dinv) {
 #pragma unroll
     for (int k = 0; k < j; ++k) d -= A[j * N + k] * A[j * N + k];
     if (!(d > 0.0)) ok = false;
-    d = sqrt(d);
-    A[j * N + j] = d;
-    const double inv = 1.0 / d;
+    const double inv = rsqrt_nr(d);  // NaN for d < 0, inf for d == 0: both poison the factor like sqrt()/division would
+    A[j * N + j] = d * inv;
     dinv[j] = inv;
 #pragma unroll
     for (int i = j + 1; i < N; ++i) {
