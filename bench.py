@@ -289,7 +289,7 @@ def main():
         }
         names = ["calc_diff", "backward", "rollout", "decide"]
         dom = int(np.argmax(ms_k[:3]))
-        n_launch = max(1, (launches_serial - 2) // 6)  # batch-iterations of the instrumented step (6 launches each)
+        n_launch = max(1, (launches_serial - 2) // 7)  # batch-iterations of the instrumented step (7 launches each)
         ach = bytes_node[names[dom]] * float(units_k[dom]) * T / (ms_k[dom] * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
         roofline = {"bound": "hbm", "kernel": names[dom] + "_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",

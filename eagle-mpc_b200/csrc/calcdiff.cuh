@@ -1,0 +1,718 @@
+// calcdiff.cuh — calc + calcDiff of every shooting node of every OCP, as two kernels (included from kernels.cuh inside
+// namespace empc).
+//
+// Replaces, per node, crocoddyl::ShootingProblem::calc/calcDiff -> IntegratedActionModelEuler::calc/calcDiff ->
+// DifferentialActionModelFreeFwdDynamics -> pinocchio::aba / computeABADerivatives + CostModelSum derivatives, and the
+// gap computation of SolverDDP::calcDiff (reference call sites: src/sbfddp.cpp:244, :332).
+//
+// Why two kernels.  The work of a node splits into a SERIAL part (squashing, ABA, Lie-group maps, residuals: chains of
+// small 3x3 / 6-vector operations that do not parallelise inside a node) and a COLUMN-PARALLEL part (the NV columns of
+// d tau/dq, d tau/dv, M^-1, the NDX x NDX / NDX x NU Jacobian and Hessian blocks).  A thread-per-node kernel needs the
+// whole ~9 KB matrix working set per thread (local memory, thrashing L1/L2: profiles/r1_baseline.md); a
+// lanes-per-node kernel would repeat the serial part on every lane.  So:
+//   node_calc_kernel  thread per node   serial part; writes xnext, cost, gaps and a 344-double "packet" per node
+//                                        (world placements / velocities / accelerations, composite-rigid-body sweep,
+//                                        squashing slopes, Lie transport blocks, state/control cost summaries)
+//   node_diff_kernel  16 lanes per node  column-parallel part out of shared memory; writes the node tile
+//                                        Fx|Fu|Lxx|Lxu|Luu|Lx|Lu with contiguous half-warp stores.
+// The packet is stored AoSoA in groups of 8 nodes ([group][field][8]): the producer's warp (32 consecutive nodes) writes
+// full 64-byte runs per field, and the consumer's block (8 nodes) reads one contiguous chunk.
+#pragma once
+
+template <class D>
+struct Pk {
+  static constexpr int NJ = D::NJ, NV = D::NV, NDX = D::NDX, NU = D::NU;
+  static constexpr int oOM = 0;                       // NJ x (R 9, p 3)      world placements of the joints
+  static constexpr int oOV = oOM + 12 * NJ;           // NJ x 6               world velocities
+  static constexpr int oOA = oOV + 6 * NJ;            // NJ x 6               world accelerations (with gravity)
+  static constexpr int oCOMP = oOA + 6 * NJ;          // NJ x 31              composites after adding body k:
+  static constexpr int cM = 0, cMC = 1, cIO = 4, cHF = 13, cG = 16, cF = 25, COMP = 31;  //   m | m c | I_o | hf | G | F
+  static constexpr int oDS = oCOMP + COMP * NJ;       // NU                   squashing slopes ds/du
+  static constexpr int oJE = oDS + NU;                // JeA 9 | JeQ 9 | E.R 9 | E.p 3
+  static constexpr int oLX = oJE + 30;                // NDX                  sum over state costs of w Rx^T Ar
+  static constexpr int oLXXB = oLX + NDX;             // 36                   ... of w Rx^T Arr Rx, base 6x6 block
+  static constexpr int oLXXD = oLXXB + 36;            // NDX-6                ... diagonal of the remaining rows
+  static constexpr int oLU = oLXXD + NDX - 6;         // NU
+  static constexpr int oLUUD = oLU + NU;              // NU                   diagonal of Luu
+  static constexpr int oFLAG = oLUUD + NU;            // 1                    node has frame costs (0/1)
+  static constexpr int SIZE = oFLAG + 1;
+  static constexpr int GROUP = 8;
+  static constexpr int STRIDE = SIZE | 1;             // per-node stride in shared memory (odd: spreads banks)
+};
+
+template <class D>
+EMPC_DI size_t pk_index(size_t n, int f) { return (n / Pk<D>::GROUP) * (size_t)(Pk<D>::SIZE * Pk<D>::GROUP) + (size_t)f * Pk<D>::GROUP + (n % Pk<D>::GROUP); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel A: serial part, one thread per node.
+template <class D>
+__global__ void __launch_bounds__(128, 2) node_calc_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
+  constexpr int NJ = D::NJ, NV = D::NV, NDX = D::NDX, NU = D::NU, NX = D::NX, NR = D::NR;
+  using P = Pk<D>;
+  const int nl = blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = bf.T + 1;
+  if (nl >= bf.nb * T1) return;
+  const size_t n = (size_t)bf.b0 * T1 + nl;
+  const int b = (int)(n / T1), t = (int)(n - (size_t)b * T1);
+  const OcpState st = bf.st[b];
+  if (!force && (st.phase == PHASE_DONE || !st.recalc)) return;
+  const double smooth = force ? force_smooth : st.smooth;
+  double* pk = bf.packets + pk_index<D>(n, 0);  // field f of this node: pk[f * GROUP]
+  auto put = [&](int f, double v) { pk[(size_t)f * P::GROUP] = v; };
+
+  double x[NX], u[NU];
+  const double* xg = bf.xs + n * NX;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = xg[i];
+  if (t < bf.T) {
+    const double* ug = bf.us + ((size_t)b * bf.T + t) * NU;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = ug[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = 0.0;  // calc(data,x) == calc(data,x,0), SURVEY B.7
+  }
+  const int costset = bf.node_costset[bf.ocp_map[b] * T1 + t];
+
+  // squashing + thrust map (ActuationSquashingModel)
+  NodeData<D> nd;
+  squash<D>(M, smooth, u, nd.s);
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    double ds = 1.0;
+    if (M.use_squash) {
+      const double lbv = M.u_lb[i], ubv = M.u_ub[i];
+      const double dd = (ubv - lbv) * smooth, a = dd * dd;
+      const double l = u[i] - lbv, h = u[i] - ubv;
+      ds = 0.5 * (rsqrt_nr(a + l * l) * l - rsqrt_nr(a + h * h) * h);
+    }
+    put(P::oDS + i, ds);
+  }
+  double tau[NV];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) s += M.tau_f[i * NR + j] * nd.s[j];
+    tau[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < D::NA; ++i) tau[6 + i] = nd.s[NR + i];
+
+  aba_kinematics<D, true>(M, x, nd);
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) put(P::oOM + 12 * i + k, nd.oM[i].R[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) put(P::oOM + 12 * i + 9 + k, nd.oM[i].p[k]);
+  }
+
+  // costs: value, and the derivative summaries of the state / control type costs (frame costs are left to kernel B)
+  double csum = 0;
+  {
+    double Lx[NDX], LxxB[36], LxxD[NDX - 6], Lu[NU], Luud[NU];
+#pragma unroll
+    for (int i = 0; i < NDX; ++i) Lx[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) LxxB[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NDX - 6; ++i) LxxD[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) { Lu[i] = 0; Luud[i] = 0; }
+    double flag = 0.0;
+    const int c0 = bf.ct.costset_begin[costset], c1 = bf.ct.costset_begin[costset + 1];
+    for (int c = c0; c < c1; ++c) {
+      const empc_cost_t cs = bf.ct.costs[c];
+      if (!cs.active) continue;
+      double r[NDX], Ar[NDX], Arr[NDX];
+      SE3 rMf;
+      const double wt = cs.weight;
+      csum += wt * cost_eval<D>(M, bf.ct, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
+      if (cs.type == EMPC_COST_STATE) {
+        SE3 Mref, Mx, Dm;
+        double xr[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) xr[i] = bf.ct.pool[cs.ref_off + i];
+        q_to_se3(xr, Mref); q_to_se3(x, Mx); se3_inv_mul(Mref, Mx, Dm);
+        double Jl[36]; Jlog6(Dm, Jl);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          double s = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += Jl[6 * k + i] * Ar[k];
+          Lx[i] += wt * s;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            double h = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) h += Jl[6 * k + i] * (Arr[k] * Jl[6 * k + j]);
+            LxxB[6 * i + j] += wt * h;
+          }
+        }
+#pragma unroll
+        for (int i = 6; i < NDX; ++i) { Lx[i] += wt * Ar[i]; LxxD[i - 6] += wt * Arr[i]; }
+      } else if (cs.type == EMPC_COST_CONTROL || cs.type == EMPC_COST_SQUASH_BARRIER) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) { Lu[i] += wt * Ar[i]; Luud[i] += wt * Arr[i]; }
+      } else {
+        flag = 1.0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NDX; ++i) put(P::oLX + i, Lx[i]);
+#pragma unroll
+    for (int i = 0; i < 36; ++i) put(P::oLXXB + i, LxxB[i]);
+#pragma unroll
+    for (int i = 0; i < NDX - 6; ++i) put(P::oLXXD + i, LxxD[i]);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) { put(P::oLU + i, Lu[i]); put(P::oLUUD + i, Luud[i]); }
+    put(P::oFLAG, flag);
+  }
+  bf.node_cost[n] = M.dt * csum;
+
+  // forward dynamics + semi-implicit Euler
+  aba_dynamics<D, true>(M, tau, nd);
+  double xn[NX];
+  {
+    const double dt = M.dt, dt2 = dt * dt;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      nd.dx[i] = x[D::NQ + i] * dt + nd.a[i] * dt2;
+      nd.dx[NV + i] = nd.a[i] * dt;
+    }
+    state_integrate<D>(x, nd.dx, xn);
+    double* xng = bf.xnext + n * NX;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xng[i] = xn[i];
+    // Lie-group transport pieces of Fx / Fu
+    double JeA[9], JeQ[9]; Jexp6_blocks(nd.dx, JeA, JeQ);
+    SE3 E; exp6(nd.dx, E);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { put(P::oJE + k, JeA[k]); put(P::oJE + 9 + k, JeQ[k]); put(P::oJE + 18 + k, E.R[k]); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) put(P::oJE + 27 + k, E.p[k]);
+  }
+
+  // world-frame velocities / accelerations and the tip-to-base composite sweep (DESIGN.md "ABA derivatives")
+  {
+    double cm = 0, cmc[3] = {0, 0, 0}, cIo[9], chf[3] = {0, 0, 0}, cG[9], cF[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { cIo[i] = 0; cG[i] = 0; }
+#pragma unroll
+    for (int k = NJ - 1; k >= 0; --k) {
+      const SE3& oMk = nd.oM[k];
+      double ov[6], oa[6];
+      act_motion(oMk, nd.v[k], ov);
+      act_motion(oMk, nd.agf[k], oa);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { put(P::oOV + 6 * k + i, ov[i]); put(P::oOA + 6 * k + i, oa[i]); }
+      double cw[3]; matvec3(oMk.R, M.com[k], cw);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) cw[i] += oMk.p[i];
+      double RI[9], Iw[9];
+      matmul3(oMk.R, M.Ic[k], RI);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Iw[3 * i + j] = RI[3 * i] * oMk.R[3 * j] + RI[3 * i + 1] * oMk.R[3 * j + 1] + RI[3 * i + 2] * oMk.R[3 * j + 2];
+      const double m = M.mass[k];
+      double h[6], Ya[6], vh[6];
+      inertia_apply(m, cw, Iw, ov, h); inertia_apply(m, cw, Iw, oa, Ya); cross_mf(ov, h, vh);
+      const double c2 = dot3(cw, cw);
+      double Io[9], mc[3] = {m * cw[0], m * cw[1], m * cw[2]};
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Io[3 * i + j] = Iw[3 * i + j] + m * (((i == j) ? c2 : 0.0) - cw[i] * cw[j]);
+      const double* vl = ov; const double* w = ov + 3;
+      double Sw[9], A1[9], Shn[9]; skew3(w, Sw); matmul3(Sw, Io, A1); skew3(h + 3, Shn);
+      const double vm = dot3(vl, mc);
+      cm += m;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { cmc[i] += mc[i]; chf[i] += h[i]; }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cF[i] += Ya[i] + vh[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          cIo[3 * i + j] += Io[3 * i + j];
+          cG[3 * i + j] += A1[3 * i + j] + A1[3 * j + i] - (mc[i] * vl[j] + vl[i] * mc[j]) + ((i == j) ? 2.0 * vm : 0.0) - Shn[3 * i + j];
+        }
+      const int o = P::oCOMP + P::COMP * k;
+      put(o + P::cM, cm);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { put(o + P::cMC + i, cmc[i]); put(o + P::cHF + i, chf[i]); }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { put(o + P::cIO + i, cIo[i]); put(o + P::cG + i, cG[i]); }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) put(o + P::cF + i, cF[i]);
+    }
+  }
+
+  // gaps (SolverDDP::calcDiff): fs[0] = x0 (-) xs[0], fs[t+1] = xnext_t (-) xs[t+1]
+  if (!st.is_feasible) {
+    if (t < bf.T) {
+      double x1[NX], f[NDX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x1[i] = xg[NX + i];
+      state_diff<D>(x1, xn, f);
+      double gi = 0, g1 = 0;
+#pragma unroll
+      for (int i = 0; i < NDX; ++i) { bf.fs[(n + 1) * NDX + i] = f[i]; const double a = fabs(f[i]); gi = fmax(gi, a); g1 += a; if (isnan(a)) gi = a; }
+      bf.gap_inf[n + 1] = gi; bf.gap_l1[n + 1] = g1;
+    }
+    if (t == 0) {
+      double xx[NX], f[NDX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xx[i] = bf.x0[(size_t)b * NX + i];
+      state_diff<D>(x, xx, f);
+      double gi = 0, g1 = 0;
+#pragma unroll
+      for (int i = 0; i < NDX; ++i) { bf.fs[n * NDX + i] = f[i]; const double a = fabs(f[i]); gi = fmax(gi, a); g1 += a; if (isnan(a)) gi = a; }
+      bf.gap_inf[n] = gi; bf.gap_l1[n] = g1;
+    }
+  } else if (!st.was_feasible) {
+    if (t < bf.T) {
+#pragma unroll
+      for (int i = 0; i < NDX; ++i) bf.fs[(n + 1) * NDX + i] = 0.0;
+      bf.gap_inf[n + 1] = 0; bf.gap_l1[n + 1] = 0;
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int i = 0; i < NDX; ++i) bf.fs[n * NDX + i] = 0.0;
+      bf.gap_inf[n] = 0; bf.gap_l1[n] = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel B: column-parallel part, 16 lanes per node, 8 nodes per block.
+template <class D>
+struct DiffCfg {
+  static constexpr int NJ = D::NJ, NV = D::NV, NDX = D::NDX, NU = D::NU, NA = D::NA;
+  static constexpr int NODES = Pk<D>::GROUP, LANES = 16, THREADS = NODES * LANES;
+  // per-node work area (doubles)
+  static constexpr int wJc = 0;                          // NV x 6   world motion axes
+  static constexpr int wYJa = wJc + 6 * NV;              // NA x 6   Ycrb_j J_j of the arm joints
+  static constexpr int wBtJa = wYJa + 6 * (NA > 0 ? NA : 1);  // NA x 3
+  static constexpr int wDq = wBtJa + 3 * (NA > 0 ? NA : 1);   // NV x NV  d tau/dq  -> a_q
+  static constexpr int wDv = wDq + NV * NV;              // NV x NV  d tau/dv  -> a_v
+  static constexpr int wMm = wDv + NV * NV;              // NV x NV  joint-space inertia
+  static constexpr int wMinv = wMm + NV * NV;            // NV x NV
+  static constexpr int wLxx = wDq;                       // NDX x NDX cost Hessian accumulator, aliases Dq|Dv|Mm|Minv (4 NV^2)
+  static constexpr int wTop = wMinv + NV * NV;           // 6 x NDX  untransported top rows of Fx ; later fJ (6 x NV)
+  static constexpr int wRx = wTop + 6 * NDX;             // 6 x NDX  residual Jacobian of one frame cost
+  static constexpr int wVec = wRx + 6 * NDX;             // Lx accumulator (NDX)
+  static constexpr int WORK0 = wVec + NDX;
+  static constexpr int WORK = WORK0 | 1;
+  static constexpr int SMEM_DOUBLES = NODES * (Pk<D>::STRIDE + WORK);
+};
+
+template <class D>
+__global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
+  constexpr int NJ = D::NJ, NV = D::NV, NDX = D::NDX, NU = D::NU, NR = D::NR;
+  using P = Pk<D>;
+  using W = DiffCfg<D>;
+  extern __shared__ __align__(16) double cd_sm[];
+  const int tid = threadIdx.x;
+  const int T1 = bf.T + 1;
+  const size_t n_first = (size_t)bf.b0 * T1, n_end = n_first + (size_t)bf.nb * T1;
+  // groups are aligned on multiples of 8 nodes in the global node index
+  const size_t g0 = n_first / P::GROUP;
+  const size_t grp = g0 + blockIdx.x;
+  const size_t nbase = grp * P::GROUP;
+
+  // ---- cooperative load of the 8 packets (one contiguous chunk), transposed to node-major in shared memory ----
+  {
+    const double* src = bf.packets + grp * (size_t)(P::SIZE * P::GROUP);
+    for (int e = tid; e < P::SIZE * P::GROUP; e += W::THREADS) {
+      const int f = e / P::GROUP, i = e - f * P::GROUP;
+      const size_t n = nbase + i;
+      bool on = n >= n_first && n < n_end;
+      if (on) {
+        const int b = (int)(n / T1);
+        const OcpState* sp = bf.st + b;
+        on = force || (sp->phase != PHASE_DONE && sp->recalc);
+      }
+      if (on) cd_sm[i * P::STRIDE + f] = src[e];
+    }
+  }
+  __syncthreads();
+
+  const int node = tid / W::LANES, l = tid % W::LANES;
+  const unsigned hm = 0xFFFFu << (16 * ((tid & 31) >> 4));  // the half-warp working on this node
+  const size_t n = nbase + node;
+  if (n < n_first || n >= n_end) return;
+  const int b = (int)(n / T1), t = (int)(n - (size_t)b * T1);
+  const OcpState st = bf.st[b];
+  if (!force && (st.phase == PHASE_DONE || !st.recalc)) return;
+  const double smooth = force ? force_smooth : st.smooth;
+  const double* pk = cd_sm + node * P::STRIDE;
+  double* wk = cd_sm + W::NODES * P::STRIDE + node * W::WORK;
+  double* tile = bf.tiles + n * D::TILE;
+  const double dt = M.dt, dt2 = dt * dt;
+
+  // ---- B1: world motion axes Jc (lane = column) ----
+  if (l < NV) {
+    double s[6];
+    if (l < 6) {
+      const double* R = pk + P::oOM; const double* p = R + 9;
+      if (l < 3) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s[a] = R[3 * a + l]; s[3 + a] = 0.0; }
+      } else {
+        const int c = l - 3;
+        const double r0 = R[c], r1 = R[3 + c], r2 = R[6 + c];  // column c of R
+        s[0] = p[1] * r2 - p[2] * r1; s[1] = p[2] * r0 - p[0] * r2; s[2] = p[0] * r1 - p[1] * r0;
+        s[3] = r0; s[4] = r1; s[5] = r2;
+      }
+    } else {
+      const int i = l - 5;
+      SE3 oMi;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) oMi.R[k] = pk[P::oOM + 12 * i + k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) oMi.p[k] = pk[P::oOM + 12 * i + 9 + k];
+      const double S[6] = {0, 0, 0, M.axis[i][0], M.axis[i][1], M.axis[i][2]};
+      act_motion(oMi, S, s);
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) wk[W::wJc + 6 * l + a] = s[a];
+  }
+  __syncwarp(hm);
+
+  // ---- B2: columns of d tau/dq, d tau/dv and of the joint-space inertia (lane = column ck) ----
+  {
+    const int ck = l < NV ? l : NV - 1;  // surplus lanes shadow the last column (results discarded)
+    const int k = ck < 6 ? 0 : ck - 5;
+    const int c_begin = (k == 0) ? 0 : 5 + k, c_end = (k == 0) ? 6 : 6 + k;
+    const double* cp = pk + P::oCOMP + P::COMP * k;
+    const double cm = cp[P::cM];
+    double cmc[3], chf[3], cIo[9], cG[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { cmc[i] = cp[P::cMC + i]; chf[i] = cp[P::cHF + i]; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { cIo[i] = cp[P::cIO + i]; cG[i] = cp[P::cG + i]; }
+    auto Yc = [&](const double* uu, double* o) {
+      double t1[3], t2[3], t3[3];
+      cross3(cmc, uu + 3, t1); cross3(cmc, uu, t2); matvec3(cIo, uu + 3, t3);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { o[i] = cm * uu[i] - t1[i]; o[3 + i] = t2[i] + t3[i]; }
+    };
+    auto Bc = [&](const double* uu, double* o) {
+      double t1[3], t2[3];
+      cross3(chf, uu + 3, t1); matvec3(cG, uu + 3, t2);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { o[i] = -2.0 * t1[i]; o[3 + i] = t2[i]; }
+    };
+    double s[6], vp[6], ap[6], ovk[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      s[a] = wk[W::wJc + 6 * ck + a];
+      vp[a] = (k > 0) ? pk[P::oOV + 6 * (k > 0 ? k - 1 : 0) + a] : 0.0;
+      ap[a] = (k > 0) ? pk[P::oOA + 6 * (k > 0 ? k - 1 : 0) + a] : M.a0[a];
+      ovk[a] = pk[P::oOV + 6 * k + a];
+    }
+    double dVdq[6], dAdq[6], dAdv[6], t6[6], vsum[6];
+    cross_mm(vp, s, dVdq);
+    cross_mm(ap, s, dAdq); cross_mm(vp, dVdq, t6);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { dAdq[a] += t6[a]; vsum[a] = vp[a] + ovk[a]; }
+    cross_mm(vsum, s, dAdv);
+    double Pq[6], Fq[6], Fv[6], YJ[6], t1[6], t2[6], cF[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) cF[a] = cp[P::cF + a];
+    Yc(dAdq, t1); Bc(dVdq, t2);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) Pq[a] = t1[a] + t2[a];
+    cross_mf(s, cF, t1);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) Fq[a] = Pq[a] + t1[a];
+    Yc(dAdv, t1); Bc(s, t2);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) Fv[a] = t1[a] + t2[a];
+    Yc(s, YJ);
+    if (k > 0 && l < NV) {
+      double c1[3], c2v[3];
+      cross3(chf, s, c1);  // 2 hf x s_v + G^T s_w
+#pragma unroll
+      for (int i = 0; i < 3; ++i) c2v[i] = cG[i] * s[3] + cG[3 + i] * s[4] + cG[6 + i] * s[5];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) wk[W::wYJa + 6 * (k - 1) + i] = YJ[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) wk[W::wBtJa + 3 * (k - 1) + i] = 2.0 * c1[i] + c2v[i];
+    }
+    __syncwarp(hm);
+    if (l < NV) {
+#pragma unroll 1
+      for (int cj = 0; cj < NV; ++cj) {
+        double vq_, vv_;
+        if (cj < c_end) {
+          double jc[6];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) jc[a] = wk[W::wJc + 6 * cj + a];
+          vq_ = (cj < c_begin) ? dot6(jc, Fq) : dot6(jc, Pq);
+          vv_ = dot6(jc, Fv);
+          if (cj <= ck) { const double mv = dot6(jc, YJ); wk[W::wMm + cj * NV + ck] = mv; wk[W::wMm + ck * NV + cj] = mv; }
+        } else {
+          const double* yj = wk + W::wYJa + 6 * (cj - 6); const double* bj = wk + W::wBtJa + 3 * (cj - 6);
+          vq_ = dot6(yj, dAdq) + (bj[0] * dVdq[3] + bj[1] * dVdq[4] + bj[2] * dVdq[5]);
+          vv_ = dot6(yj, dAdv) + (bj[0] * s[3] + bj[1] * s[4] + bj[2] * s[5]);
+        }
+        wk[W::wDq + cj * NV + ck] = vq_; wk[W::wDv + cj * NV + ck] = vv_;
+      }
+    }
+  }
+  __syncwarp(hm);
+
+  // ---- B3: Cholesky of the joint-space inertia (every lane, in registers) and one column of M^-1 per lane ----
+  {
+    double L[NV * NV], Linv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) L[i * NV + j] = wk[W::wMm + i * NV + j];
+    llt_inplace_inv<NV>(L, Linv);
+    double e[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) e[i] = (i == l) ? 1.0 : 0.0;
+    llt_solve_vec_inv<NV>(L, Linv, e, 1);
+    if (l < NV) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) wk[W::wMinv + i * NV + l] = e[i];
+    }
+  }
+  __syncwarp(hm);
+
+  // ---- B4: a_q = -M^-1 dtau/dq, a_v = -M^-1 dtau/dv, lane = column, in place ----
+  if (l < NV) {
+    double cq[NV], cv[NV], rq[NV], rv[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { cq[k] = wk[W::wDq + k * NV + l]; cv[k] = wk[W::wDv + k * NV + l]; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double sq = 0, sv = 0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) { const double mi = wk[W::wMinv + i * NV + k]; sq += mi * cq[k]; sv += mi * cv[k]; }
+      rq[i] = -sq; rv[i] = -sv;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { wk[W::wDq + i * NV + l] = rq[i]; wk[W::wDv + i * NV + l] = rv[i]; }
+  }
+  __syncwarp(hm);
+  const double* aq = wk + W::wDq; const double* av = wk + W::wDv;
+
+  // ---- B5: Fx.  Rows 6.. are scaled copies; rows 0..5 go through the Lie-group transport ----
+  const double* JeA = pk + P::oJE; const double* JeQ = JeA + 9;
+  {
+    double* Fx = tile + D::oFx;
+    for (int e = 6 * NDX + l; e < NDX * NDX; e += W::LANES) {
+      const int i = e / NDX, j = e - i * NDX;
+      double v;
+      if (i < NV) v = (j < NV) ? aq[i * NV + j] * dt2 + ((i == j) ? 1.0 : 0.0) : av[i * NV + (j - NV)] * dt2 + ((i == j - NV) ? dt : 0.0);
+      else { const int ii = i - NV; v = (j < NV) ? aq[ii * NV + j] * dt : av[ii * NV + (j - NV)] * dt + ((ii == j - NV) ? 1.0 : 0.0); }
+      Fx[e] = v;
+    }
+    // Ad(E^-1) = (X*)^T of E = exp(dx): column c (< 6), row a:  Xs[6 c + a]
+    SE3 E;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) E.R[k] = pk[P::oJE + 18 + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) E.p[k] = pk[P::oJE + 27 + k];
+    double Xs[36]; force_action_matrix(E, Xs);
+    for (int c = l; c < NDX; c += W::LANES) {
+      double top[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) top[k] = ((c < NV) ? aq[k * NV + c] : av[k * NV + (c - NV)]) * dt2 + ((c == NV + k) ? dt : 0.0);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double je;  // Je = [[A,Q],[0,A]]
+          if (a < 3) je = (k < 3) ? JeA[3 * a + k] : JeQ[3 * a + (k - 3)];
+          else je = (k < 3) ? 0.0 : JeA[3 * (a - 3) + (k - 3)];
+          s += je * top[k];
+        }
+        if (c < 6) {
+          double xs_ = 0.0;
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) xs_ = (cc == c) ? Xs[6 * cc + a] : xs_;
+          s += xs_;
+        }
+        wk[W::wTop + a * NDX + c] = s;
+      }
+    }
+    __syncwarp(hm);
+    for (int e = l; e < 6 * NDX; e += W::LANES) Fx[e] = wk[W::wTop + e];
+  }
+
+  // ---- B6: Fu = [dt^2; dt] M^-1 A diag(ds), rows 0..5 transported; lane = column ----
+  {
+    double* Fu = tile + D::oFu;
+    const double* Minv = wk + W::wMinv;
+    __syncwarp(hm);
+    for (int j = l; j < NU; j += W::LANES) {
+      const double dsj = pk[P::oDS + j];
+      double top[6];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        double s;
+        if (j < NR) {
+          s = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += Minv[i * NV + k] * (M.tau_f[k * NR + j] * dsj);
+        } else {
+          s = Minv[i * NV + 6 + (j - NR)] * dsj;
+        }
+        if (i < 6) top[i] = dt2 * s; else Fu[i * NU + j] = dt2 * s;
+        Fu[(NV + i) * NU + j] = dt * s;
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double je;
+          if (a < 3) je = (k < 3) ? JeA[3 * a + k] : JeQ[3 * a + (k - 3)];
+          else je = (k < 3) ? 0.0 : JeA[3 * (a - 3) + (k - 3)];
+          s += je * top[k];
+        }
+        Fu[a * NU + j] = s;
+      }
+    }
+  }
+  __syncwarp(hm);  // Minv, a_q, a_v are dead from here on: their area becomes the Lxx accumulator
+
+  // ---- B7: cost derivatives ----
+  {
+    double* Lxx = wk + W::wLxx;
+    double* Lxv = wk + W::wVec;
+    for (int e = l; e < NDX * NDX; e += W::LANES) {
+      const int i = e / NDX, j = e - i * NDX;
+      double v = 0.0;
+      if (i < 6 && j < 6) v = pk[P::oLXXB + 6 * i + j];
+      else if (i == j) v = pk[P::oLXXD + i - 6];
+      Lxx[e] = v;
+    }
+    for (int i = l; i < NDX; i += W::LANES) Lxv[i] = pk[P::oLX + i];
+    __syncwarp(hm);
+    if (pk[P::oFLAG] != 0.0) {
+      // frame costs: residual / activation on every lane (serial), Jacobian columns and Hessian entries across lanes
+      NodeData<D> nd;  // only oM and v are used by the frame costs
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) nd.oM[i].R[k] = pk[P::oOM + 12 * i + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) nd.oM[i].p[k] = pk[P::oOM + 12 * i + 9 + k];
+        double ov[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ov[k] = pk[P::oOV + 6 * i + k];
+        actinv_motion(nd.oM[i], ov, nd.v[i]);
+      }
+      const int costset = bf.node_costset[bf.ocp_map[b] * T1 + t];
+      const int c0 = bf.ct.costset_begin[costset], c1 = bf.ct.costset_begin[costset + 1];
+      double* fJ = wk + W::wTop;   // 6 x NV
+      double* Rx = wk + W::wRx;    // 6 x NDX
+      for (int c = c0; c < c1; ++c) {
+        const empc_cost_t cs = bf.ct.costs[c];
+        if (!cs.active) continue;
+        if (cs.type == EMPC_COST_STATE || cs.type == EMPC_COST_CONTROL || cs.type == EMPC_COST_SQUASH_BARRIER) continue;
+        double r[NDX], Ar[NDX], Arr[NDX];
+        SE3 rMf;
+        cost_eval<D>(M, bf.ct, cs, smooth, nullptr, nullptr, nd, r, Ar, Arr, rMf);
+        const double wt = cs.weight;
+        const int f = cs.frame, jf = M.frame_joint[f];
+        SE3 oMf; frame_placement<D>(M, nd, f, oMf);
+        for (int e = l; e < 6 * NDX; e += W::LANES) Rx[e] = 0.0;
+        if (l < NV) {  // frame Jacobian column (LOCAL)
+          const int jc = (l < 6) ? 0 : l - 5;
+          double jcw[6], o[6];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) jcw[a] = wk[W::wJc + 6 * l + a];
+          actinv_motion(oMf, jcw, o);
+#pragma unroll
+          for (int a = 0; a < 6; ++a) fJ[a * NV + l] = (jc <= jf) ? o[a] : 0.0;
+        }
+        __syncwarp(hm);
+        int nres = 3;
+        bool full = false;
+        if (cs.type == EMPC_COST_FRAME_PLACEMENT) {
+          nres = 6;
+          double Jl[36]; Jlog6(rMf, Jl);
+          if (l < NV) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+              double s = 0;
+#pragma unroll
+              for (int k = 0; k < 6; ++k) s += Jl[6 * a + k] * fJ[k * NV + l];
+              Rx[a * NDX + l] = s;
+            }
+          }
+        } else if (cs.type == EMPC_COST_FRAME_ROTATION) {
+          double wv[3], th, Jl[9]; log3(rMf.R, wv, th); Jlog3(th, wv, Jl);
+          if (l < NV) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) Rx[a * NDX + l] = Jl[3 * a] * fJ[3 * NV + l] + Jl[3 * a + 1] * fJ[4 * NV + l] + Jl[3 * a + 2] * fJ[5 * NV + l];
+          }
+        } else if (cs.type == EMPC_COST_FRAME_TRANSLATION) {
+          if (l < NV) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+              Rx[a * NDX + l] = oMf.R[3 * a] * fJ[0 * NV + l] + oMf.R[3 * a + 1] * fJ[1 * NV + l] + oMf.R[3 * a + 2] * fJ[2 * NV + l];
+          }
+        } else {  // FRAME_VELOCITY
+          nres = 6; full = true;
+          if (l < NV) {
+            if (l >= 6) {  // base columns have no parent body: zero
+              const int kk = l - 5;
+              if (kk <= jf) {
+                double ovp[6], jcw[6], cr[6], o[6];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) { ovp[a] = pk[P::oOV + 6 * (kk - 1) + a]; jcw[a] = wk[W::wJc + 6 * l + a]; }
+                cross_mm(ovp, jcw, cr); actinv_motion(oMf, cr, o);
+#pragma unroll
+                for (int a = 0; a < 6; ++a) Rx[a * NDX + l] = o[a];
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) Rx[a * NDX + NV + l] = fJ[a * NV + l];
+          }
+        }
+        __syncwarp(hm);
+        const int ncols = full ? NDX : NV;
+        double wA[6], wAr[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { wA[k] = (k < nres) ? Arr[k] : 0.0; wAr[k] = (k < nres) ? Ar[k] : 0.0; }
+        for (int j = l; j < ncols; j += W::LANES) {
+          double rj[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) rj[k] = Rx[k * NDX + j];
+          double s = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += rj[k] * wAr[k];
+          Lxv[j] += wt * s;
+#pragma unroll 1
+          for (int i = 0; i < ncols; ++i) {
+            double h = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) h += Rx[k * NDX + i] * (wA[k] * rj[k]);
+            Lxx[i * NDX + j] += wt * h;
+          }
+        }
+        __syncwarp(hm);
+      }
+    }
+    double* gLxx = tile + D::oLxx; double* gLxu = tile + D::oLxu; double* gLuu = tile + D::oLuu;
+    double* gLx = tile + D::oLx; double* gLu = tile + D::oLu;
+    for (int e = l; e < NDX * NDX; e += W::LANES) gLxx[e] = Lxx[e] * dt;
+    for (int e = l; e < NDX * NU; e += W::LANES) gLxu[e] = 0.0;
+    for (int e = l; e < NU * NU; e += W::LANES) { const int i = e / NU, j = e - i * NU; gLuu[e] = (i == j) ? pk[P::oLUUD + i] * dt : 0.0; }
+    for (int i = l; i < NDX; i += W::LANES) gLx[i] = Lxv[i] * dt;
+    for (int i = l; i < NU; i += W::LANES) gLu[i] = pk[P::oLU + i] * dt;
+    if (D::TILE != D::TILE0 && l == 0) tile[D::TILE0] = 0.0;
+  }
+}

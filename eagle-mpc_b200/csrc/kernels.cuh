@@ -1,6 +1,7 @@
 // kernels.cuh — the four kernel families of the batched SbFDDP iteration (FP64, sm_100a).
 //
-//   calc_diff_kernel  thread per (OCP, node): calc + calcDiff + gaps            (src/sbfddp.cpp:244,332 -> SolverDDP::calcDiff)
+//   node_calc_kernel  thread per (OCP, node): calc + gaps + serial half of calcDiff  (src/sbfddp.cpp:244,332 -> SolverDDP::calcDiff)
+//   node_diff_kernel  16 lanes per (OCP, node): column-parallel half of calcDiff, writes the node tiles
 //   backward_kernel   warp per OCP: Riccati sweep, Quu LLT, gains, expected-improvement sums, regularisation retry
 //                                                                              (SolverDDP::backwardPass/computeGains, :245-253)
 //   rollout_kernel    thread per (OCP, step length): all 10 alphas concurrently (SolverFDDP::forwardPass, :416-460)
@@ -40,6 +41,7 @@ struct Buffers {
   double* xs; double* us;
   double* xs_try0;
   // per node
+  double* packets;  // calcdiff.cuh: per-node hand-over from node_calc_kernel to node_diff_kernel (AoSoA, groups of 8)
   double* tiles; double* xnext; double* node_cost; double* fs; double* gap_inf; double* gap_l1;
   double* K; double* k; double* Vx; double* g; double* nodesc;
   // trials
@@ -49,76 +51,7 @@ struct Buffers {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
-#ifndef EMPC_CD_MINB
-#define EMPC_CD_MINB 4
-#endif
-template <class D>
-__global__ void __launch_bounds__(128, EMPC_CD_MINB) calc_diff_kernel(Buffers bf, int force, double force_smooth) {
-  const int nl = blockIdx.x * blockDim.x + threadIdx.x;
-  const int T1 = bf.T + 1;
-  if (nl >= bf.nb * T1) return;
-  const int n = bf.b0 * T1 + nl;
-  const int b = n / T1, t = n - b * T1;
-  const OcpState st = bf.st[b];
-  if (!force && (st.phase == PHASE_DONE || !st.recalc)) return;
-  const double smooth = force ? force_smooth : st.smooth;
-  const DevModel& M = *bf.model;
-  double x[D::NX], u[D::NU];
-  const double* xg = bf.xs + (size_t)n * D::NX;
-#pragma unroll
-  for (int i = 0; i < D::NX; ++i) x[i] = xg[i];
-  if (t < bf.T) {
-    const double* ug = bf.us + ((size_t)b * bf.T + t) * D::NU;
-#pragma unroll
-    for (int i = 0; i < D::NU; ++i) u[i] = ug[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < D::NU; ++i) u[i] = 0.0;  // calc(data,x) == calc(data,x,0), SURVEY B.7
-  }
-  const int costset = bf.node_costset[bf.ocp_map[b] * T1 + t];
-  NodeData<D> nd;
-  double xn[D::NX], cost;
-  node_calc<D>(M, bf.ct, costset, smooth, x, u, nd, xn, cost);
-  double* xng = bf.xnext + (size_t)n * D::NX;
-#pragma unroll
-  for (int i = 0; i < D::NX; ++i) xng[i] = xn[i];
-  bf.node_cost[n] = cost;
-  node_calc_diff<D>(M, bf.ct, costset, smooth, x, u, nd, bf.tiles + (size_t)n * D::TILE);
-  // gaps (SolverDDP::calcDiff): fs[0] = x0 (-) xs[0], fs[t+1] = xnext_t (-) xs[t+1]
-  if (!st.is_feasible) {
-    if (t < bf.T) {
-      double x1[D::NX], f[D::NDX];
-#pragma unroll
-      for (int i = 0; i < D::NX; ++i) x1[i] = xg[D::NX + i];
-      state_diff<D>(x1, xn, f);
-      double gi = 0, g1 = 0;
-#pragma unroll
-      for (int i = 0; i < D::NDX; ++i) { bf.fs[(size_t)(n + 1) * D::NDX + i] = f[i]; const double a = fabs(f[i]); gi = fmax(gi, a); g1 += a; if (isnan(a)) gi = a; }
-      bf.gap_inf[n + 1] = gi; bf.gap_l1[n + 1] = g1;
-    }
-    if (t == 0) {
-      double xx[D::NX], f[D::NDX];
-#pragma unroll
-      for (int i = 0; i < D::NX; ++i) xx[i] = bf.x0[(size_t)b * D::NX + i];
-      state_diff<D>(x, xx, f);
-      double gi = 0, g1 = 0;
-#pragma unroll
-      for (int i = 0; i < D::NDX; ++i) { bf.fs[(size_t)n * D::NDX + i] = f[i]; const double a = fabs(f[i]); gi = fmax(gi, a); g1 += a; if (isnan(a)) gi = a; }
-      bf.gap_inf[n] = gi; bf.gap_l1[n] = g1;
-    }
-  } else if (!st.was_feasible) {
-    if (t < bf.T) {
-#pragma unroll
-      for (int i = 0; i < D::NDX; ++i) bf.fs[(size_t)(n + 1) * D::NDX + i] = 0.0;
-      bf.gap_inf[n + 1] = 0; bf.gap_l1[n + 1] = 0;
-    }
-    if (t == 0) {
-#pragma unroll
-      for (int i = 0; i < D::NDX; ++i) bf.fs[(size_t)n * D::NDX + i] = 0.0;
-      bf.gap_inf[n] = 0; bf.gap_l1[n] = 0;
-    }
-  }
-}
+#include "calcdiff.cuh"
 
 #include "backward.cuh"
 

@@ -136,8 +136,10 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
   int ok = 1;
 
   prefetch(0, 0);
+  int costset_next = costsets[0];
   for (int t = 0; t <= T; ++t) {
-    if (t < T) { prefetch(t + 1, (t + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    const int costset = costset_next;
+    if (t < T) { prefetch(t + 1, (t + 1) & 1); costset_next = costsets[t + 1]; cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncwarp();
     const double* in = my_stage + (size_t)(t & 1) * S::OCPS * S::STAGE;
     if (active) {
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
       }
       NodeData<D> nd;
       double c;
-      node_calc<D, true>(M, bf.ct, costsets[t], smooth, xt, u, nd, xn, c);
+      node_calc<D, true>(M, bf.ct, costset, smooth, xt, u, nd, xn, c);
       cost_try += c;
       bool bad = isnan(cost_try);
       if (t < T) {

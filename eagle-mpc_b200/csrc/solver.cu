@@ -75,6 +75,13 @@ static cudaError_t dalloc(empc_solver* h, Tp** p, size_t n) {
     else return fail(EMPC_ERR_UNSUPPORTED, "unsupported (arm joints, rotors) combination");                \
   } while (0)
 
+static int packet_doubles(int na, int nr) {
+  int out = 0;
+#define EMPC_PK(NA_, NR_) if (na == NA_ && nr == NR_) out = Pk<Dim<NA_, NR_>>::SIZE;
+  EMPC_PK(0, 4) EMPC_PK(0, 6) EMPC_PK(2, 6) EMPC_PK(3, 6) EMPC_PK(5, 6)
+#undef EMPC_PK
+  return out;
+}
 static bool supported(int na, int nr) {
   return (na == 0 && nr == 4) || (na == 0 && nr == 6) || (na == 2 && nr == 6) || (na == 3 && nr == 6) || (na == 5 && nr == 6);
 }
@@ -208,6 +215,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   CKH(dalloc(h, &bf.us, B * T * nu));
   CKH(dalloc(h, &bf.xs_try0, B * nx));
   CKH(dalloc(h, &bf.tiles, B * T1 * tile));
+  CKH(dalloc(h, &bf.packets, (B * T1 + 7) / 8 * 8 * (size_t)packet_doubles(h->na, h->nr)));
   CKH(dalloc(h, &bf.xnext, B * T1 * nx));
   CKH(dalloc(h, &bf.node_cost, B * T1));
   CKH(dalloc(h, &bf.fs, B * T1 * ndx));
@@ -332,8 +340,25 @@ template <class D>
 static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, const Buffers* gb = nullptr, cudaStream_t st = nullptr) {
   const Buffers& bf = gb ? *gb : h->bf;
   if (!st) st = h->stream;
-  const int n = bf.nb * (h->T + 1);
-  calc_diff_kernel<D><<<(n + 127) / 128, 128, 0, st>>>(bf, force, smooth);
+  const int T1 = h->T + 1;
+  const long long n = (long long)bf.nb * T1;
+  node_calc_kernel<D><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bf, force, smooth, h->hmodel);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  using W = DiffCfg<D>;
+  const size_t smem = sizeof(double) * W::SMEM_DOUBLES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(node_diff_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(node_diff_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const long long n_first = (long long)bf.b0 * T1, n_last = n_first + n - 1;
+  const long long groups = n_last / Pk<D>::GROUP - n_first / Pk<D>::GROUP + 1;
+  node_diff_kernel<D><<<(unsigned)groups, W::THREADS, smem, st>>>(bf, force, smooth, h->hmodel);
   h->launches++;
   return cudaGetLastError();
 }

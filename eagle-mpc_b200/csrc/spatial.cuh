@@ -89,9 +89,9 @@ EMPC_DI void skew3(const double* v, double* S) {
 // A = sin t/t, B = (1-cos t)/t^2, C = (t-sin t)/t^3
 EMPC_DI void so3_coef(double t2, double t, double& A, double& B, double& C) {
   if (t < EMPC_SERIES_BELOW) {
-    A = 1 + t2 * (-1.0 / 6 + t2 * (1.0 / 120 + t2 * (-1.0 / 5040 + t2 * (1.0 / 362880 - t2 / 39916800))));
-    B = 0.5 + t2 * (-1.0 / 24 + t2 * (1.0 / 720 + t2 * (-1.0 / 40320 + t2 * (1.0 / 3628800 - t2 / 479001600))));
-    C = 1.0 / 6 + t2 * (-1.0 / 120 + t2 * (1.0 / 5040 + t2 * (-1.0 / 362880 + t2 * (1.0 / 39916800 - t2 / 6227020800.0))));
+    A = 1 + t2 * (-1.0 / 6 + t2 * (1.0 / 120 + t2 * (-1.0 / 5040 + t2 * (1.0 / 362880 - t2 * (1.0 / 39916800)))));
+    B = 0.5 + t2 * (-1.0 / 24 + t2 * (1.0 / 720 + t2 * (-1.0 / 40320 + t2 * (1.0 / 3628800 - t2 * (1.0 / 479001600)))));
+    C = 1.0 / 6 + t2 * (-1.0 / 120 + t2 * (1.0 / 5040 + t2 * (-1.0 / 362880 + t2 * (1.0 / 39916800 - t2 * (1.0 / 6227020800.0)))));
   } else {
     double st, ct; sincos(t, &st, &ct);
     A = st / t; B = (1 - ct) / t2; C = (t - st) / (t2 * t);
@@ -115,8 +115,8 @@ EMPC_DI void log_coef(double t, double& alpha, double& beta, double& bdot) {
 // c2 = (t^2+2cos t-2)/(2t^4), c3 = (2t-3sin t+t cos t)/(2t^5)
 EMPC_DI void q_coef(double t2, double t, double& c2, double& c3) {
   if (t < EMPC_SERIES_BELOW) {
-    c2 = 1.0 / 24 + t2 * (-1.0 / 720 + t2 * (1.0 / 40320 + t2 * (-1.0 / 3628800 + t2 / 479001600)));
-    c3 = 1.0 / 120 + t2 * (-1.0 / 2520 + t2 * (1.0 / 120960 + t2 * (-1.0 / 9979200 + t2 / 1245404160.0)));
+    c2 = 1.0 / 24 + t2 * (-1.0 / 720 + t2 * (1.0 / 40320 + t2 * (-1.0 / 3628800 + t2 * (1.0 / 479001600))));
+    c3 = 1.0 / 120 + t2 * (-1.0 / 2520 + t2 * (1.0 / 120960 + t2 * (-1.0 / 9979200 + t2 * (1.0 / 1245404160.0))));
   } else {
     double st, ct; sincos(t, &st, &ct);
     const double t4 = t2 * t2;
