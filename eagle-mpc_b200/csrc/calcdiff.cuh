@@ -299,19 +299,23 @@ struct DiffCfg {
   static constexpr int wBtJa = wYJa + 6 * (NA > 0 ? NA : 1);  // NA x 3
   static constexpr int wDq = wBtJa + 3 * (NA > 0 ? NA : 1);   // NV x NV  d tau/dq  -> a_q
   static constexpr int wDv = wDq + NV * NV;              // NV x NV  d tau/dv  -> a_v
-  static constexpr int wMm = wDv + NV * NV;              // NV x NV  joint-space inertia
+  static constexpr int wMm = wDv + NV * NV;              // NV x NV  joint-space inertia -> its Cholesky factor
   static constexpr int wMinv = wMm + NV * NV;            // NV x NV
-  static constexpr int wLxx = wDq;                       // NDX x NDX cost Hessian accumulator, aliases Dq|Dv|Mm|Minv (4 NV^2)
-  static constexpr int wTop = wMinv + NV * NV;           // 6 x NDX  untransported top rows of Fx ; later fJ (6 x NV)
-  static constexpr int wRx = wTop + 6 * NDX;             // 6 x NDX  residual Jacobian of one frame cost
-  static constexpr int wVec = wRx + 6 * NDX;             // Lx accumulator (NDX)
+  static constexpr int wLxx = wDq;                       // NDX x NDX cost Hessian accumulator (frame costs only), aliases Dq|Dv|Mm|Minv
+  static constexpr int wLinv = wMinv + NV * NV;          // NV       reciprocal Cholesky pivots
+  static constexpr int wFJ = wLinv + NV;                 // 6 x NV   LOCAL frame Jacobian of one frame cost
+  static constexpr int wVec = wFJ + 6 * NV;              // Lx accumulator (NDX)
   static constexpr int WORK0 = wVec + NDX;
   static constexpr int WORK = WORK0 | 1;
-  static constexpr int SMEM_DOUBLES = NODES * (Pk<D>::STRIDE + WORK);
+  // the residual Jacobian of a frame cost (6 x NDX) reuses the packet's composite area, dead after phase B2
+  static constexpr int RX_IN_PACKET = (6 * NDX <= Pk<D>::COMP * NJ) ? 1 : 0;
+  static constexpr int wRx = WORK;                       // used when the composite area is too small (short arms)
+  static constexpr int WORK_TOTAL = WORK + (RX_IN_PACKET ? 0 : 6 * NDX + 1);
+  static constexpr int SMEM_DOUBLES = NODES * (Pk<D>::STRIDE + WORK_TOTAL);
 };
 
 template <class D>
-__global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
+__global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
   constexpr int NJ = D::NJ, NV = D::NV, NDX = D::NDX, NU = D::NU, NR = D::NR;
   using P = Pk<D>;
   using W = DiffCfg<D>;
@@ -324,20 +328,25 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffe
   const size_t grp = g0 + blockIdx.x;
   const size_t nbase = grp * P::GROUP;
 
-  // ---- cooperative load of the 8 packets (one contiguous chunk), transposed to node-major in shared memory ----
+  // ---- cooperative load of the 8 packets (one contiguous chunk), transposed to node-major in shared memory.  Thread tid
+  // always handles node tid % 8 (THREADS is a multiple of 8), so the activity test is done once; the copies are 8-byte
+  // cp.async's fired back to back and awaited together. ----
   {
     const double* src = bf.packets + grp * (size_t)(P::SIZE * P::GROUP);
-    for (int e = tid; e < P::SIZE * P::GROUP; e += W::THREADS) {
-      const int f = e / P::GROUP, i = e - f * P::GROUP;
-      const size_t n = nbase + i;
-      bool on = n >= n_first && n < n_end;
-      if (on) {
-        const int b = (int)(n / T1);
-        const OcpState* sp = bf.st + b;
-        on = force || (sp->phase != PHASE_DONE && sp->recalc);
-      }
-      if (on) cd_sm[i * P::STRIDE + f] = src[e];
+    const int i = tid % P::GROUP;
+    const size_t nn = nbase + i;
+    bool on = nn >= n_first && nn < n_end;
+    if (on) {
+      const OcpState* sp = bf.st + (int)(nn / T1);
+      on = force || (sp->phase != PHASE_DONE && sp->recalc);
     }
+    if (on) {
+      double* dst = cd_sm + i * P::STRIDE;
+#pragma unroll 4
+      for (int e = tid; e < P::SIZE * P::GROUP; e += W::THREADS) cp_async8(dst + e / P::GROUP, src + e);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
   }
   __syncthreads();
 
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffe
   if (!force && (st.phase == PHASE_DONE || !st.recalc)) return;
   const double smooth = force ? force_smooth : st.smooth;
   const double* pk = cd_sm + node * P::STRIDE;
-  double* wk = cd_sm + W::NODES * P::STRIDE + node * W::WORK;
+  double* wk = cd_sm + W::NODES * P::STRIDE + node * W::WORK_TOTAL;
   double* tile = bf.tiles + n * D::TILE;
   const double dt = M.dt, dt2 = dt * dt;
 
@@ -467,21 +476,51 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffe
   }
   __syncwarp(hm);
 
-  // ---- B3: Cholesky of the joint-space inertia (every lane, in registers) and one column of M^-1 per lane ----
+  // ---- B3: Cholesky of the joint-space inertia in shared memory (lane = row, left-looking, same subtraction order as
+  // llt_inplace_inv) and one column of M^-1 per lane ----
   {
-    double L[NV * NV], Linv[NV];
+    double* Lm = wk + W::wMm;
+    double* Linv = wk + W::wLinv;
+    double row[NV];  // this lane's row of L (entries k < j are final when column j is processed)
+    const int i = l < NV ? l : NV - 1;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+    for (int k = 0; k < NV; ++k) row[k] = Lm[i * NV + k];
 #pragma unroll
-      for (int j = 0; j <= i; ++j) L[i * NV + j] = wk[W::wMm + i * NV + j];
-    llt_inplace_inv<NV>(L, Linv);
+    for (int j = 0; j < NV; ++j) {
+      // pivot: every lane computes it from row j (broadcast reads), so no extra hand-over is needed
+      double d = Lm[j * NV + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) { const double ljk = Lm[j * NV + k]; d -= ljk * ljk; }
+      const double inv = rsqrt_nr(d);
+      double sij = row[j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) sij -= row[k] * Lm[j * NV + k];
+      sij = (i == j) ? d * inv : sij * inv;
+      row[j] = sij;
+      __syncwarp(hm);
+      if (l < NV && i >= j) Lm[i * NV + j] = sij;
+      if (l == j) Linv[j] = inv;
+      __syncwarp(hm);
+    }
+    // column l of M^-1: L y = e_l, L^T x = y
     double e[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) e[i] = (i == l) ? 1.0 : 0.0;
-    llt_solve_vec_inv<NV>(L, Linv, e, 1);
+    for (int r = 0; r < NV; ++r) {
+      double sacc = (r == l) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; ++k) sacc -= Lm[r * NV + k] * e[k];
+      e[r] = sacc * Linv[r];
+    }
+#pragma unroll
+    for (int r = NV - 1; r >= 0; --r) {
+      double sacc = e[r];
+#pragma unroll
+      for (int k = r + 1; k < NV; ++k) sacc -= Lm[k * NV + r] * e[k];
+      e[r] = sacc * Linv[r];
+    }
     if (l < NV) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) wk[W::wMinv + i * NV + l] = e[i];
+      for (int r = 0; r < NV; ++r) wk[W::wMinv + r * NV + l] = e[r];
     }
   }
   __syncwarp(hm);
@@ -542,11 +581,9 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffe
           for (int cc = 0; cc < 6; ++cc) xs_ = (cc == c) ? Xs[6 * cc + a] : xs_;
           s += xs_;
         }
-        wk[W::wTop + a * NDX + c] = s;
+        Fx[a * NDX + c] = s;
       }
     }
-    __syncwarp(hm);
-    for (int e = l; e < 6 * NDX; e += W::LANES) Fx[e] = wk[W::wTop + e];
   }
 
   // ---- B6: Fu = [dt^2; dt] M^-1 A diag(ds), rows 0..5 transported; lane = column ----
@@ -588,18 +625,31 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffe
 
   // ---- B7: cost derivatives ----
   {
-    double* Lxx = wk + W::wLxx;
-    double* Lxv = wk + W::wVec;
-    for (int e = l; e < NDX * NDX; e += W::LANES) {
-      const int i = e / NDX, j = e - i * NDX;
-      double v = 0.0;
-      if (i < 6 && j < 6) v = pk[P::oLXXB + 6 * i + j];
-      else if (i == j) v = pk[P::oLXXD + i - 6];
-      Lxx[e] = v;
-    }
-    for (int i = l; i < NDX; i += W::LANES) Lxv[i] = pk[P::oLX + i];
-    __syncwarp(hm);
-    if (pk[P::oFLAG] != 0.0) {
+    double* gLxx = tile + D::oLxx; double* gLxu = tile + D::oLxu; double* gLuu = tile + D::oLuu;
+    double* gLx = tile + D::oLx; double* gLu = tile + D::oLu;
+    static_assert(D::oLxx % 2 == 0 && D::oLxu % 2 == 0 && NDX % 2 == 0, "double2 stores need even offsets");
+    // Lxu = 0, Luu diagonal, Lu: the same for every node
+    for (int e = l; e < NDX * NU / 2; e += W::LANES) reinterpret_cast<double2*>(gLxu)[e] = make_double2(0.0, 0.0);
+    for (int e = l; e < NU * NU; e += W::LANES) { const int i = e / NU, j = e - i * NU; gLuu[e] = (i == j) ? pk[P::oLUUD + i] * dt : 0.0; }
+    for (int i = l; i < NU; i += W::LANES) gLu[i] = pk[P::oLU + i] * dt;
+    if (D::TILE != D::TILE0 && l == 0) tile[D::TILE0] = 0.0;
+    auto lxx_state = [&](int i, int j) -> double {  // state-cost part: 6x6 block + diagonal
+      if (i < 6 && j < 6) return pk[P::oLXXB + 6 * i + j];
+      if (i == j) return pk[P::oLXXD + i - 6];
+      return 0.0;
+    };
+    if (pk[P::oFLAG] == 0.0) {
+      for (int e2 = l; e2 < NDX * NDX / 2; e2 += W::LANES) {
+        const int e = 2 * e2, i = e / NDX, j = e - i * NDX;
+        reinterpret_cast<double2*>(gLxx)[e2] = make_double2(lxx_state(i, j) * dt, lxx_state(i, j + 1) * dt);
+      }
+      for (int i = l; i < NDX; i += W::LANES) gLx[i] = pk[P::oLX + i] * dt;
+    } else {
+      double* Lxx = wk + W::wLxx;
+      double* Lxv = wk + W::wVec;
+      for (int e = l; e < NDX * NDX; e += W::LANES) { const int i = e / NDX; Lxx[e] = lxx_state(i, e - i * NDX); }
+      for (int i = l; i < NDX; i += W::LANES) Lxv[i] = pk[P::oLX + i];
+      __syncwarp(hm);
       // frame costs: residual / activation on every lane (serial), Jacobian columns and Hessian entries across lanes
       NodeData<D> nd;  // only oM and v are used by the frame costs
 #pragma unroll
@@ -615,8 +665,8 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffe
       }
       const int costset = bf.node_costset[bf.ocp_map[b] * T1 + t];
       const int c0 = bf.ct.costset_begin[costset], c1 = bf.ct.costset_begin[costset + 1];
-      double* fJ = wk + W::wTop;   // 6 x NV
-      double* Rx = wk + W::wRx;    // 6 x NDX
+      double* fJ = wk + W::wFJ;   // 6 x NV
+      double* Rx = W::RX_IN_PACKET ? const_cast<double*>(pk) + P::oCOMP : wk + W::wRx;  // 6 x NDX
       for (int c = c0; c < c1; ++c) {
         const empc_cost_t cs = bf.ct.costs[c];
         if (!cs.active) continue;
@@ -646,10 +696,10 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffe
           if (l < NV) {
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
-              double s = 0;
+              double sacc = 0;
 #pragma unroll
-              for (int k = 0; k < 6; ++k) s += Jl[6 * a + k] * fJ[k * NV + l];
-              Rx[a * NDX + l] = s;
+              for (int k = 0; k < 6; ++k) sacc += Jl[6 * a + k] * fJ[k * NV + l];
+              Rx[a * NDX + l] = sacc;
             }
           }
         } else if (cs.type == EMPC_COST_FRAME_ROTATION) {
@@ -691,10 +741,10 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffe
           double rj[6];
 #pragma unroll
           for (int k = 0; k < 6; ++k) rj[k] = Rx[k * NDX + j];
-          double s = 0;
+          double sacc = 0;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) s += rj[k] * wAr[k];
-          Lxv[j] += wt * s;
+          for (int k = 0; k < 6; ++k) sacc += rj[k] * wAr[k];
+          Lxv[j] += wt * sacc;
 #pragma unroll 1
           for (int i = 0; i < ncols; ++i) {
             double h = 0;
@@ -705,14 +755,9 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 3) node_diff_kernel(Buffe
         }
         __syncwarp(hm);
       }
+      for (int e2 = l; e2 < NDX * NDX / 2; e2 += W::LANES)
+        reinterpret_cast<double2*>(gLxx)[e2] = make_double2(Lxx[2 * e2] * dt, Lxx[2 * e2 + 1] * dt);
+      for (int i = l; i < NDX; i += W::LANES) gLx[i] = Lxv[i] * dt;
     }
-    double* gLxx = tile + D::oLxx; double* gLxu = tile + D::oLxu; double* gLuu = tile + D::oLuu;
-    double* gLx = tile + D::oLx; double* gLu = tile + D::oLu;
-    for (int e = l; e < NDX * NDX; e += W::LANES) gLxx[e] = Lxx[e] * dt;
-    for (int e = l; e < NDX * NU; e += W::LANES) gLxu[e] = 0.0;
-    for (int e = l; e < NU * NU; e += W::LANES) { const int i = e / NU, j = e - i * NU; gLuu[e] = (i == j) ? pk[P::oLUUD + i] * dt : 0.0; }
-    for (int i = l; i < NDX; i += W::LANES) gLx[i] = Lxv[i] * dt;
-    for (int i = l; i < NU; i += W::LANES) gLu[i] = pk[P::oLU + i] * dt;
-    if (D::TILE != D::TILE0 && l == 0) tile[D::TILE0] = 0.0;
   }
 }

@@ -39,18 +39,6 @@ struct RoCfg {
   static constexpr int SMEM_DOUBLES = 2 * OCPS * STAGE;
 };
 
-EMPC_DI void cp_async8(double* smem_dst, const double* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
-}
-EMPC_DI void cp_async16(double* smem_dst, const double* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
-}
-EMPC_DI void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-EMPC_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 template <class D, int W>
 __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, const __grid_constant__ DevModel M) {
   constexpr int NX = D::NX, NDX = D::NDX, NU = D::NU;

@@ -18,6 +18,19 @@ struct SE3 {
   double p[3];
 };
 
+// ---- cp.async (LDGSTS): asynchronous global -> shared copies, awaited per commit group ---------------------------------
+EMPC_DI void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+EMPC_DI void cp_async16(double* smem_dst, const double* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+EMPC_DI void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+EMPC_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // ---- branch-free reciprocal square root / square root / reciprocal --------------------------------------------------
 // The library sqrt() and 1/x expand to a MUFU seed, Newton steps AND a branch to a slow path for denormal / huge
 // operands (BSSY/BSYNC + a call): ~25 instructions and a fetch bubble each, ~80 times per node.  The quantities that

@@ -5,7 +5,15 @@ import csv, collections, io, re, subprocess, sys
 rep, sass, pat = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(out)))
+allrows = list(csv.reader(io.StringIO(out)))
+# the source page of a multi-kernel report is a concatenation of sections, each starting with a "Kernel Name" row
+secs = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"]
+kpat = sys.argv[5] if len(sys.argv) > 5 else None
+pick = secs[0]
+if kpat:
+    pick = [i for i in secs if kpat in allrows[i][1]][0]
+end = min([i for i in secs if i > pick] + [len(allrows)])
+rows = allrows[pick:end]
 hdr = rows[1]
 iS, iE, iN = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('# Samples')
 stall_cols = {h: i for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h}
