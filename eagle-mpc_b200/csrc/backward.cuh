@@ -1,33 +1,59 @@
-// backward.cuh — Riccati backward pass, one thread block per OCP (included from kernels.cuh inside namespace empc).
+// backward.cuh — Riccati backward pass, ONE WARP per OCP, dense products on the FP64 tensor cores (DMMA).
+// (included from kernels.cuh inside namespace empc)
 //
 // Replaces crocoddyl::SolverDDP::backwardPass + computeGains and the regularisation retry loop of
 // SolverSbFDDP::solveFDDP/solveDDP (src/sbfddp.cpp:242-255, :330-343), plus SolverFDDP::updateExpectedImprovement /
 // SolverSbFDDP::expectedImprovementDDP (src/sbfddp.cpp:256, :395-408).
 //
-// Layout: the node tile (Fx|Fu|Lxx|Lxu|Luu|Lx|Lu) is staged in shared memory and turned in place into
-// Qxx|Qxu|Quu|Qx|Qu; Vxx' (the value Hessian of the next node) stays resident in shared memory for the whole sweep.
-// The next node's tile is prefetched from HBM into registers while the current node is processed.  Dense products
-// use 2x3 register tiles per thread and accumulate over k in ascending order (the reference's summation order).
+// Per node (n = ndx, m = nu):  FxTV = Fx^T V', FuTV = Fu^T V', Qxx = Lxx + FxTV Fx, Qxu = Lxu + FxTV Fu,
+// Quu = Luu + FuTV Fu + ureg I, Qx = Lx + Fx^T Vx', Qu = Lu + Fu^T Vx', LLT(Quu), K = Quu^-1 Qxu^T, k = Quu^-1 Qu,
+// Vx = Qx + K^T Quu k - 2 K^T Qu (+ Vxx fs), Vxx = sym(Qxx - Qxu K) + xreg I.
+//
+// The six dense products are the only GEMM-shaped work on the SbFDDP path (18x18x18 for flying_arm_3).  They run as
+// mma.sync.m8n8k4.f64 (SASS DMMA) on 8x8 tiles with zero-padded operands in shared memory: one DMMA replaces 8 DFMA
+// warp-instructions and needs two 8-byte fragment loads instead of ~7 (measured: the FP64 tensor rate equals the vector
+// rate on B200, so the gain is issue slots and shared-memory bandwidth, not FLOPs; profiles/r1_baseline.md).
+// Leading dimensions are chosen per operand role so that every fragment load is bank-conflict free:
+//   LDB = 24  (= 8 mod 16)  operands read as B (k x n, row k) or as transposed A:   Fx, Fu, V', K
+//   LDA = 20  (= 4 mod 16)  operands read as row-major A (row i, 4 consecutive k):   FxTV, FuTV, Qxu
+// Everything else (Cholesky of Quu, triangular solves, vector updates, ordered reductions) is warp-cooperative out of
+// shared memory with __syncwarp only: no block-level barrier anywhere on the sweep.  The next node's Fx / Fu arrive by
+// cp.async while the current node is being factorised; its cost blocks are prefetched into registers.
 #pragma once
 
 template <class D>
 struct BwCfg {
-  static constexpr int NDX = D::NDX, NU = D::NU;
-  static constexpr int THREADS = (NDX <= 18) ? 64 : 128;
-#ifndef EMPC_BW_MINB
-#define EMPC_BW_MINB 8
-#endif
-  static constexpr int MIN_BLOCKS = (NDX <= 18) ? EMPC_BW_MINB : EMPC_BW_MINB / 2;  // caps registers at 128/thread so shared memory, not registers, bounds occupancy
-  static constexpr int oTile = 0;
-  static constexpr int oV = oTile + D::TILE;          // Vxx' (NDX x NDX)
-  static constexpr int oFxTV = oV + NDX * NDX;         // Fx^T Vxx'
-  static constexpr int oFuTV = oFxTV + NDX * NDX;      // Fu^T Vxx'  (later: Cholesky factor of Quu)
-  static constexpr int oK = oFuTV + NU * NDX;          // K (NU x NDX)
-  static constexpr int oVx = oK + NU * NDX;            // Vx' (NDX)
-  static constexpr int oVec = oVx + NDX;               // k(NU) Quuk(NU) fs(NDX) g(NDX) tmp(NDX)
-  static constexpr int TOTAL0 = oVec + 2 * NU + 3 * NDX;
+  static constexpr int n = D::NDX, m = D::NU;
+  static constexpr int NT = (n + 7) / 8, MT = (m + 7) / 8;      // 8-wide tiles over n, m
+  static constexpr int KN = (n + 3) / 4, KM = (m + 3) / 4;      // 4-deep k-steps over n, m
+  static constexpr int NP = 8 * NT, MP = 8 * MT, KNP = 4 * KN, KMP = 4 * KM;
+  static constexpr int LDB = 24;
+  static constexpr int lda_for(int k) { return k <= 20 ? 20 : 36; }
+  static constexpr int LDA = lda_for(KNP);                       // FxTV, FuTV
+  static constexpr int LDQ = 20;                                 // Qxu (k extent KMP <= 16)
+  static_assert(NP <= LDB && MP <= LDB && KMP <= LDQ, "operand wider than its leading dimension");
+  static constexpr int ROWS_K = (KNP > NP ? KNP : NP);
+  static constexpr int oFx = 0;                                  // KNP x LDB
+  static constexpr int oFu = oFx + KNP * LDB;                    // KNP x LDB
+  static constexpr int oV = oFu + KNP * LDB;                     // ROWS_K x LDB   Vxx' (symmetric)
+  static constexpr int oQxx = oV + ROWS_K * LDB;                 // NP x LDB       Lxx -> Qxx -> Qxx - Qxu K
+  static constexpr int oQxu = oQxx + NP * LDB;                   // NP x LDQ       Lxu -> Qxu
+  static constexpr int oQuu = oQxu + NP * LDQ;                   // MP x LDQ       Luu -> Quu
+  static constexpr int oFxTV = oQuu + MP * LDQ;                  // NP x LDA
+  static constexpr int oFuTV = oFxTV + NP * LDA;                 // MP x LDA
+  static constexpr int oK = oFuTV + MP * LDA;                    // KMP x LDB      gains K (m x n)
+  static constexpr int oL = oK + KMP * LDB;                      // m x m Cholesky factor of Quu, then m reciprocal pivots
+  static constexpr int oVec = oL + m * m + m + ((m * m + m) & 1);
+  static constexpr int vQx = 0, vQu = vQx + NP, vVx = vQu + MP, vFs = vVx + NP, vG = vFs + NP, vKv = vG + NP,
+                       vQuuk = vKv + MP, vTmp = vQuuk + MP, VEC = vTmp + NP;
+  static constexpr int TOTAL0 = oVec + VEC;
   static constexpr int TOTAL = TOTAL0 + (TOTAL0 & 1);
-  static constexpr int PREF = (D::TILE / 2 + THREADS - 1) / THREADS;  // double2 registers per thread for the prefetch
+  // register prefetch of the cost blocks Lxx | Lxu | Luu | Lx | Lu (contiguous in the tile) + fs
+  static constexpr int LBLK = n * n + n * m + m * m + n + m;
+  static constexpr int PREF = (LBLK + 31) / 32;
+#ifndef EMPC_BW_WARPS_PER_SM
+#define EMPC_BW_WARPS_PER_SM 6
+#endif
 };
 
 struct BwParams {
@@ -35,57 +61,66 @@ struct BwParams {
   int force;  // phase hook: single attempt, xreg / is_feasible taken from the state as they are, no prologue
 };
 
-// C (M x N, ld ldc) (+/-)= opA(A) (M x K) * B (K x N) over threads [tid, tid+nth, ...]; TA: A stored K x M.
-template <int M_, int N_, int K_, int RT, int CT, bool TA, bool ACC, bool NEG>
-EMPC_DI void cta_mm(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda, const double* __restrict__ Bm,
-                    int ldb, int tid, int nth) {
-  constexpr int TM = (M_ + RT - 1) / RT, TN = (N_ + CT - 1) / CT;
-  for (int tile = tid; tile < TM * TN; tile += nth) {
-    const int i0 = (tile / TN) * RT, j0 = (tile % TN) * CT;
-    double acc[RT][CT];
+EMPC_DI void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// acc[i][j] (+)= op(A) B over KS k-steps.  Fragment coordinates: r = lane >> 2, c = lane & 3.
+//   AT  : A is stored k-major (A(i,k) = Ab[k * lda + i]), else row-major (A(i,k) = Ab[i * lda + k])
+//   NEG : accumulate -A B
+template <int MT_, int NT_, int KS_, bool AT, bool NEG>
+EMPC_DI void warp_mm(double (&acc)[MT_][NT_][2], const double* __restrict__ Ab, int lda, const double* __restrict__ Bb, int ldb, int r, int c) {
 #pragma unroll
-    for (int r = 0; r < RT; ++r)
+  for (int ks = 0; ks < KS_; ++ks) {
+    double a[MT_], b[NT_];
 #pragma unroll
-      for (int c = 0; c < CT; ++c) acc[r][c] = 0.0;
-    // clamp the ragged edge instead of branching inside the k loop (the clamped lanes' results are discarded)
-    int ia[RT], jb[CT];
-#pragma unroll
-    for (int r = 0; r < RT; ++r) ia[r] = (i0 + r < M_) ? i0 + r : M_ - 1;
-#pragma unroll
-    for (int c = 0; c < CT; ++c) jb[c] = (j0 + c < N_) ? j0 + c : N_ - 1;
-#pragma unroll 6
-    for (int k = 0; k < K_; ++k) {
-      double a[RT], bv[CT];
-#pragma unroll
-      for (int r = 0; r < RT; ++r) a[r] = TA ? A[k * lda + ia[r]] : A[ia[r] * lda + k];
-#pragma unroll
-      for (int c = 0; c < CT; ++c) bv[c] = Bm[k * ldb + jb[c]];
-#pragma unroll
-      for (int r = 0; r < RT; ++r)
-#pragma unroll
-        for (int c = 0; c < CT; ++c) acc[r][c] += a[r] * bv[c];
+    for (int i = 0; i < MT_; ++i) {
+      const double v = AT ? Ab[(4 * ks + c) * lda + 8 * i + r] : Ab[(8 * i + r) * lda + 4 * ks + c];
+      a[i] = NEG ? -v : v;
     }
 #pragma unroll
-    for (int r = 0; r < RT; ++r)
+    for (int j = 0; j < NT_; ++j) b[j] = Bb[(4 * ks + c) * ldb + 8 * j + r];
 #pragma unroll
-      for (int c = 0; c < CT; ++c)
-        if (i0 + r < M_ && j0 + c < N_) {
-          double* p = &C[(i0 + r) * ldc + j0 + c];
-          if (ACC) *p = NEG ? (*p - acc[r][c]) : (*p + acc[r][c]);
-          else *p = NEG ? -acc[r][c] : acc[r][c];
-        }
+    for (int i = 0; i < MT_; ++i)
+#pragma unroll
+      for (int j = 0; j < NT_; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
+}
+template <int MT_, int NT_>
+EMPC_DI void acc_zero(double (&acc)[MT_][NT_][2]) {
+#pragma unroll
+  for (int i = 0; i < MT_; ++i)
+#pragma unroll
+    for (int j = 0; j < NT_; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+}
+// C tile (i, j): lane holds C[8 i + r][8 j + 2 c], C[8 i + r][8 j + 2 c + 1]
+template <int MT_, int NT_>
+EMPC_DI void acc_load(double (&acc)[MT_][NT_][2], const double* Cb, int ldc, int r, int c) {
+#pragma unroll
+  for (int i = 0; i < MT_; ++i)
+#pragma unroll
+    for (int j = 0; j < NT_; ++j) {
+      const double2 v = *reinterpret_cast<const double2*>(Cb + (8 * i + r) * ldc + 8 * j + 2 * c);
+      acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+    }
+}
+// columns >= ncols are not stored (the padded tail of a narrow leading dimension)
+template <int MT_, int NT_>
+EMPC_DI void acc_store(const double (&acc)[MT_][NT_][2], double* Cb, int ldc, int ncols, int r, int c) {
+#pragma unroll
+  for (int i = 0; i < MT_; ++i)
+#pragma unroll
+    for (int j = 0; j < NT_; ++j)
+      if (8 * j + 2 * c < ncols) *reinterpret_cast<double2*>(Cb + (8 * i + r) * ldc + 8 * j + 2 * c) = make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
 template <class D>
-__global__ void __launch_bounds__(BwCfg<D>::THREADS, BwCfg<D>::MIN_BLOCKS) backward_kernel(Buffers bf, BwParams P) {
-  constexpr int NDX = D::NDX, NU = D::NU;
+__global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buffers bf, BwParams P) {
   using S = BwCfg<D>;
-  constexpr int NT = S::THREADS;
-  extern __shared__ double sm[];
-  __shared__ int s_flag;
-  __shared__ double s_red[4];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int n = S::n, m = S::m, LDB = S::LDB, LDA = S::LDA, LDQ = S::LDQ;
+  extern __shared__ __align__(16) double bw_sm[];
+  double* sm = bw_sm;
+  const int lane = threadIdx.x, fr = lane >> 2, fc = lane & 3;
   const int b = bf.b0 + blockIdx.x;
   OcpState st = bf.st[b];
   if (!P.force && st.phase == PHASE_DONE) return;
@@ -94,268 +129,305 @@ __global__ void __launch_bounds__(BwCfg<D>::THREADS, BwCfg<D>::MIN_BLOCKS) backw
 
   // ---- prologue: tail of SolverDDP::calcDiff — cost_ = sum of node costs in node order, feasibility from the gaps ----
   if (!P.force && st.recalc) {
-    double c = 0;
+    double cst = 0;
     for (int base = 0; base < T1; base += S::TOTAL) {
       const int cnt = min(S::TOTAL, T1 - base);
-      for (int t = tid; t < cnt; t += NT) sm[t] = bf.node_cost[nb + base + t];
-      __syncthreads();
-      if (tid == 0) for (int t = 0; t < cnt; ++t) c += sm[t];
-      __syncthreads();
+      for (int t = lane; t < cnt; t += 32) sm[t] = bf.node_cost[nb + base + t];
+      __syncwarp();
+      if (lane == 0) for (int t = 0; t < cnt; ++t) cst += sm[t];
+      __syncwarp();
     }
-    if (tid == 0) s_red[0] = c;
+    st.cost = __shfl_sync(0xffffffffu, cst, 0);
     if (!st.is_feasible) {
       double gi = 0, g1 = 0; int has_nan = 0;
-      for (int t = tid; t < T1; t += NT) { const double a = bf.gap_inf[nb + t]; if (isnan(a)) has_nan = 1; gi = fmax(gi, a); g1 += bf.gap_l1[nb + t]; }
+      for (int t = lane; t < T1; t += 32) { const double a = bf.gap_inf[nb + t]; if (isnan(a)) has_nan = 1; gi = fmax(gi, a); g1 += bf.gap_l1[nb + t]; }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { gi = fmax(gi, __shfl_xor_sync(0xffffffffu, gi, o)); g1 += __shfl_xor_sync(0xffffffffu, g1, o); has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o); }
-      double* red = sm;  // [warp][3]
-      if (lane == 0) { red[warp * 3] = gi; red[warp * 3 + 1] = g1; red[warp * 3 + 2] = has_nan ? 1.0 : 0.0; }
-      __syncthreads();
-      if (tid == 0) {
-        double a = 0, l = 0, n = 0;
-        for (int w = 0; w < NT / 32; ++w) { a = fmax(a, red[w * 3]); l += red[w * 3 + 1]; n += red[w * 3 + 2]; }
-        s_red[1] = a; s_red[2] = l; s_red[3] = n;
-      }
-    }
-    __syncthreads();
-    st.cost = s_red[0];
-    if (!st.is_feasible) {
-      const bool has_nan = s_red[3] != 0.0;
-      st.gap_inf = has_nan ? nan("") : s_red[1]; st.gap_l1 = s_red[2];
-      st.is_feasible = (!has_nan && s_red[1] < P.th_gaptol) ? 1 : 0;
+      st.gap_inf = has_nan ? nan("") : gi; st.gap_l1 = g1;
+      st.is_feasible = (!has_nan && gi < P.th_gaptol) ? 1 : 0;
     } else if (!st.was_feasible) {
       st.gap_inf = 0; st.gap_l1 = 0;
     }
-    __syncthreads();
   }
   const int feasible = st.is_feasible;
 
-  double* tile = sm + S::oTile;
-  double* V = sm + S::oV;
-  double* FxTV = sm + S::oFxTV;
-  double* FuTV = sm + S::oFuTV;
-  double* Kt = sm + S::oK;
-  double* Vxp = sm + S::oVx;
-  double* kv = sm + S::oVec;
-  double* Quuk = kv + NU;
-  double* fsv = Quuk + NU;
-  double* gv = fsv + NDX;
-  double* tmpv = gv + NDX;
-  double* Fx = tile + D::oFx; double* Fu = tile + D::oFu; double* Qxx = tile + D::oLxx; double* Qxu = tile + D::oLxu;
-  double* Quu = tile + D::oLuu; double* Qx = tile + D::oLx; double* Qu = tile + D::oLu;
-  double2* tile2 = reinterpret_cast<double2*>(tile);
+  double* sFx = sm + S::oFx; double* sFu = sm + S::oFu; double* sV = sm + S::oV; double* sQxx = sm + S::oQxx;
+  double* sQxu = sm + S::oQxu; double* sQuu = sm + S::oQuu; double* sFxTV = sm + S::oFxTV; double* sFuTV = sm + S::oFuTV;
+  double* sK = sm + S::oK; double* sL = sm + S::oL; double* sLinv = sL + m * m;
+  double* vec = sm + S::oVec;
+  double* Qx = vec + S::vQx; double* Qu = vec + S::vQu; double* Vxp = vec + S::vVx; double* fsv = vec + S::vFs;
+  double* gv = vec + S::vG; double* kv = vec + S::vKv; double* Quuk = vec + S::vQuuk; double* tmpv = vec + S::vTmp;
+
+  // asynchronous fetch of Fx (16-byte pieces, n even) and Fu (8-byte pieces) of node t into their padded layouts
+  auto fetch_F = [&](int t) {
+    const double* tg = bf.tiles + (nb + t) * D::TILE;
+    for (int e = lane; e < n * n / 2; e += 32) { const int i = e / (n / 2), cc = e - i * (n / 2); cp_async16(sFx + i * LDB + 2 * cc, tg + D::oFx + 2 * e); }
+    for (int e = lane; e < n * m; e += 32) { const int i = e / m, j = e - i * m; cp_async8(sFu + i * LDB + j, tg + D::oFu + e); }
+    cp_async_commit();
+  };
+  // cost blocks of node t: HBM -> registers (issued early) -> shared memory (at the end of the previous node)
+  auto load_L = [&](int t, double (&pre)[S::PREF], double& pre_fs) {
+    const double* tg = bf.tiles + (nb + t) * D::TILE + D::oLxx;
+#pragma unroll
+    for (int q = 0; q < S::PREF; ++q) { const int e = lane + 32 * q; pre[q] = (e < S::LBLK) ? tg[e] : 0.0; }
+    pre_fs = (lane < n) ? bf.fs[(nb + t) * n + lane] : 0.0;
+  };
+  auto store_L = [&](const double (&pre)[S::PREF], double pre_fs) {
+#pragma unroll
+    for (int q = 0; q < S::PREF; ++q) {
+      int e = lane + 32 * q;
+      if (e < n * n) { const int i = e / n; sQxx[i * LDB + (e - i * n)] = pre[q]; continue; }
+      e -= n * n;
+      if (e < n * m) { const int i = e / m; sQxu[i * LDQ + (e - i * m)] = pre[q]; continue; }
+      e -= n * m;
+      if (e < m * m) { const int i = e / m; sQuu[i * LDQ + (e - i * m)] = pre[q]; continue; }
+      e -= m * m;
+      if (e < n) { Qx[e] = pre[q]; continue; }
+      e -= n;
+      if (e < m) Qu[e] = pre[q];
+    }
+    if (lane < n) fsv[lane] = pre_fs;
+  };
 
   int failed;
   while (true) {
     failed = 0;
-    if (tid == 0) s_flag = 0;
     const double xreg = st.xreg;
+    // zero everything: the padding of every DMMA operand must be (and then stays) zero
+    for (int i = lane; i < S::TOTAL; i += 32) sm[i] = 0.0;
+    __syncwarp();
     // ---- terminal node: Vxx = Lxx + xreg I ; Vx = Lx (+ Vxx fs) ----
     {
       const double* tg = bf.tiles + (nb + T) * D::TILE;
-      for (int i = tid; i < NDX * NDX; i += NT) V[i] = tg[D::oLxx + i] + ((i / NDX == i % NDX) ? xreg : 0.0);
-      for (int i = tid; i < NDX; i += NT) { Vxp[i] = tg[D::oLx + i]; fsv[i] = bf.fs[(nb + T) * NDX + i]; }
-      __syncthreads();
-      for (int i = tid; i < NDX; i += NT) {
+      for (int e = lane; e < n * n; e += 32) { const int i = e / n, j = e - i * n; sV[i * LDB + j] = tg[D::oLxx + e] + ((i == j) ? xreg : 0.0); }
+      if (lane < n) { Vxp[lane] = tg[D::oLx + lane]; fsv[lane] = bf.fs[(nb + T) * n + lane]; }
+      __syncwarp();
+      if (lane < n) {
         double s = 0;
-        for (int j = 0; j < NDX; ++j) s += V[i * NDX + j] * fsv[j];
-        gv[i] = s;
+#pragma unroll 6
+        for (int j = 0; j < n; ++j) s += sV[lane * LDB + j] * fsv[j];
+        gv[lane] = s;
+        if (!feasible) Vxp[lane] += s;
       }
-      __syncthreads();
-      if (!feasible) for (int i = tid; i < NDX; i += NT) Vxp[i] += gv[i];
-      __syncthreads();
-      if (tid == 0) {
+      __syncwarp();
+      if (lane == 0) {
         double s0 = 0, s1 = 0;
-        for (int i = 0; i < NDX; ++i) { s0 += Vxp[i] * fsv[i]; s1 += fsv[i] * gv[i]; }
+        for (int i = 0; i < n; ++i) { s0 += Vxp[i] * fsv[i]; s1 += fsv[i] * gv[i]; }
         double* ns = bf.nodesc + (nb + T) * 4;
         ns[0] = 0; ns[1] = 0; ns[2] = s0; ns[3] = s1;
       }
-      for (int i = tid; i < NDX; i += NT) { bf.Vx[(nb + T) * NDX + i] = Vxp[i]; bf.g[(nb + T) * NDX + i] = gv[i]; }
-      __syncthreads();
-      // first running tile straight into shared memory
-      const double2* tg2 = reinterpret_cast<const double2*>(bf.tiles + (nb + T - 1) * D::TILE);
-      for (int i = tid; i < D::TILE / 2; i += NT) tile2[i] = tg2[i];
-      for (int i = tid; i < NDX; i += NT) fsv[i] = bf.fs[(nb + T - 1) * NDX + i];
-      __syncthreads();
+      if (lane < n) { bf.Vx[(nb + T) * n + lane] = Vxp[lane]; bf.g[(nb + T) * n + lane] = gv[lane]; }
+      fetch_F(T - 1);
+      double pre[S::PREF], pre_fs;
+      load_L(T - 1, pre, pre_fs);
+      __syncwarp();
+      store_L(pre, pre_fs);
     }
     for (int t = T - 1; t >= 0; --t) {
-      // prefetch the next node's tile (t-1) into registers; it lands in shared memory at the end of this step
-      double2 pre[S::PREF];
-      double pre_fs = 0.0;
-      if (t > 0) {
-        const double2* tg2 = reinterpret_cast<const double2*>(bf.tiles + (nb + t - 1) * D::TILE);
-#pragma unroll
-        for (int r = 0; r < S::PREF; ++r) { const int i = tid + r * NT; if (i < D::TILE / 2) pre[r] = tg2[i]; }
-        if (tid < NDX) pre_fs = bf.fs[(nb + t - 1) * NDX + tid];
-      }
-      // FxTV = Fx^T V ; FuTV = Fu^T V ; Qx += Fx^T Vx' ; Qu += Fu^T Vx'
-      cta_mm<NDX, NDX, NDX, 2, 3, true, false, false>(FxTV, NDX, Fx, NDX, V, NDX, tid, NT);
-      cta_mm<NU, NDX, NDX, 2, 3, true, false, false>(FuTV, NDX, Fu, NU, V, NDX, tid, NT);
-      for (int i = tid; i < NDX + NU; i += NT) {
-        double s = 0;
-        if (i < NDX) { for (int l = 0; l < NDX; ++l) s += Fx[l * NDX + i] * Vxp[l]; Qx[i] += s; }
-        else { const int ii = i - NDX; for (int l = 0; l < NDX; ++l) s += Fu[l * NU + ii] * Vxp[l]; Qu[ii] += s; }
-      }
-      __syncthreads();
-      // Warp 0: Qxu += FxTV Fu ; Quu += FuTV Fu (+ ureg) ; Cholesky ; gains.   Other warps: Qxx += FxTV Fu meanwhile
-      // (Qxx is not needed by the factorisation).
-      double* L = FuTV + NU * NDX - NU * NU - NU;  // tail of the FuTV area; FuTV itself is consumed before L is written
-      double* Linv = L + NU * NU;
-      if (warp != 0) {
-        cta_mm<NDX, NDX, NDX, 2, 3, false, true, false>(Qxx, NDX, FxTV, NDX, Fx, NDX, tid - 32, NT - 32);
-      } else {
-        cta_mm<NDX, NU, NDX, 2, 3, false, true, false>(Qxu, NU, FxTV, NDX, Fu, NU, lane, 32);
-        cta_mm<NU, NU, NDX, 2, 3, false, true, false>(Quu, NU, FuTV, NDX, Fu, NU, lane, 32);
-        __syncwarp();
-        for (int i = lane; i < NU; i += 32) Quu[i * NU + i] += xreg;
-        __syncwarp();
-        for (int i = lane; i < NU * NU; i += 32) L[i] = Quu[i];
-        __syncwarp();
-        int bad = 0;
-        // right-looking Cholesky; the subtraction order equals the scalar left-looking loop of the reference LLT
-#pragma unroll 1
-        for (int j = 0; j < NU; ++j) {
-          const double djj = L[j * NU + j];
-          if (!(djj > 0.0)) bad = 1;
-          const double d = sqrt(djj);
-          const double dinv = 1.0 / d;
-          __syncwarp();
-          if (lane == 0) { L[j * NU + j] = d; Linv[j] = dinv; }
-          for (int i = j + 1 + lane; i < NU; i += 32) L[i * NU + j] = L[i * NU + j] * dinv;
-          __syncwarp();
-          for (int idx = lane; idx < NU * NU; idx += 32) {
-            const int i = idx / NU, kk = idx - i * NU;
-            if (kk > j && kk <= i) L[idx] -= L[i * NU + j] * L[kk * NU + j];
-          }
-          __syncwarp();
-        }
-        if (bad) { if (lane == 0) s_flag = 1; }
-        else {
-          // K = Quu^-1 Qxu^T (one right-hand side per lane), k = Quu^-1 Qu
-          for (int c = lane; c < NDX + 1; c += 32) {
-            double rhs[NU];
-            if (c < NDX) {
-#pragma unroll
-              for (int i = 0; i < NU; ++i) rhs[i] = Qxu[c * NU + i];
-            } else {
-#pragma unroll
-              for (int i = 0; i < NU; ++i) rhs[i] = Qu[i];
-            }
-#pragma unroll
-            for (int i = 0; i < NU; ++i) {
-              double s = rhs[i];
-#pragma unroll
-              for (int kk = 0; kk < i; ++kk) s -= L[i * NU + kk] * rhs[kk];
-              rhs[i] = s * Linv[i];
-            }
-#pragma unroll
-            for (int i = NU - 1; i >= 0; --i) {
-              double s = rhs[i];
-#pragma unroll
-              for (int kk = i + 1; kk < NU; ++kk) s -= L[kk * NU + i] * rhs[kk];
-              rhs[i] = s * Linv[i];
-            }
-            if (c < NDX) {
-#pragma unroll
-              for (int i = 0; i < NU; ++i) Kt[i * NDX + c] = rhs[i];
-            } else {
-#pragma unroll
-              for (int i = 0; i < NU; ++i) kv[i] = rhs[i];
-            }
-          }
-          __syncwarp();
-          for (int i = lane; i < NU; i += 32) {  // Quuk = Quu k
-            double s = 0;
-            for (int j = 0; j < NU; ++j) s += Quu[i * NU + j] * kv[j];
-            Quuk[i] = s;
-          }
-        }
-      }
-      __syncthreads();
-      if (s_flag) { failed = 1; break; }
-      // Vx = Qx + K^T Quuk - 2 K^T Qu ; Vxx = Qxx - Qxu K
-      for (int i = tid; i < NDX; i += NT) {
-        double s1 = 0, s2 = 0;
-        for (int j = 0; j < NU; ++j) { s1 += Kt[j * NDX + i] * Quuk[j]; s2 += Kt[j * NDX + i] * Qu[j]; }
-        tmpv[i] = Qx[i] + s1 - 2 * s2;
-      }
-      cta_mm<NDX, NDX, NU, 2, 3, false, true, true>(Qxx, NDX, Qxu, NU, Kt, NDX, tid, NT);
-      __syncthreads();
-      // symmetrise + xreg -> V, NaN guard ("backward_error")
+      cp_async_wait<0>();
+      __syncwarp();
+      double pre[S::PREF], pre_fs = 0.0;
+      if (t > 0) load_L(t - 1, pre, pre_fs);
+      // ---- FxTV = Fx^T V ; FuTV = Fu^T V ----
       {
-        int bad = 0;
-        for (int idx = tid; idx < NDX * NDX; idx += NT) {
-          const int i = idx / NDX, j = idx - i * NDX;
-          const int lo = i < j ? i : j, hi = i < j ? j : i;
-          double a = 0.5 * (Qxx[lo * NDX + hi] + Qxx[hi * NDX + lo]);
-          if (i == j) a += xreg;
-          if (isnan(a)) bad = 1;
-          V[idx] = a;
-        }
-        if (bad) s_flag = 1;
+        double acc[S::NT][S::NT][2];
+        acc_zero(acc);
+        warp_mm<S::NT, S::NT, S::KN, true, false>(acc, sFx, LDB, sV, LDB, fr, fc);
+        acc_store(acc, sFxTV, LDA, LDA, fr, fc);
       }
-      __syncthreads();
-      for (int i = tid; i < NDX; i += NT) {
+      {
+        double acc[S::MT][S::NT][2];
+        acc_zero(acc);
+        warp_mm<S::MT, S::NT, S::KN, true, false>(acc, sFu, LDB, sV, LDB, fr, fc);
+        acc_store(acc, sFuTV, LDA, LDA, fr, fc);
+      }
+      // Qx += Fx^T Vx' ; Qu += Fu^T Vx'   (lane = output row, ascending l as in the reference)
+      if (lane < n) {
         double s = 0;
-        for (int j = 0; j < NDX; ++j) s += V[i * NDX + j] * fsv[j];
-        gv[i] = s;
-        const double vx = feasible ? tmpv[i] : (tmpv[i] + s);
-        if (isnan(vx)) s_flag = 1;
-        Vxp[i] = vx;
+#pragma unroll 6
+        for (int l = 0; l < n; ++l) s += sFx[l * LDB + lane] * Vxp[l];
+        Qx[lane] += s;
       }
-      __syncthreads();
-      if (s_flag) { failed = 1; break; }
+      for (int i = lane; i < m; i += 32) {
+        double s = 0;
+#pragma unroll 6
+        for (int l = 0; l < n; ++l) s += sFu[l * LDB + i] * Vxp[l];
+        Qu[i] += s;
+      }
+      __syncwarp();
+      // ---- Qxx += FxTV Fx ; Qxu += FxTV Fu ; Quu += FuTV Fu + ureg I ----
+      {
+        double acc[S::NT][S::NT][2];
+        acc_load(acc, sQxx, LDB, fr, fc);
+        warp_mm<S::NT, S::NT, S::KN, false, false>(acc, sFxTV, LDA, sFx, LDB, fr, fc);
+        acc_store(acc, sQxx, LDB, LDB, fr, fc);
+      }
+      {
+        double acc[S::NT][S::MT][2];
+        acc_load(acc, sQxu, LDQ, fr, fc);
+        warp_mm<S::NT, S::MT, S::KN, false, false>(acc, sFxTV, LDA, sFu, LDB, fr, fc);
+        acc_store(acc, sQxu, LDQ, LDQ, fr, fc);
+      }
+      {
+        double acc[S::MT][S::MT][2];
+        acc_load(acc, sQuu, LDQ, fr, fc);
+        warp_mm<S::MT, S::MT, S::KN, false, false>(acc, sFuTV, LDA, sFu, LDB, fr, fc);
+        acc_store(acc, sQuu, LDQ, LDQ, fr, fc);
+      }
+      __syncwarp();
+      // Fx, Fu of this node are dead: start fetching the next node's while Quu is factorised
+      if (t > 0) fetch_F(t - 1);
+      if (lane < m) sQuu[lane * LDQ + lane] += xreg;
+      __syncwarp();
+      // ---- Cholesky of Quu (lane = row, left-looking: the reference LLT's subtraction order) ----
+      int bad = 0;
+      {
+        const int i = lane < m ? lane : m - 1;
+        double row[m];
+#pragma unroll
+        for (int k = 0; k < m; ++k) row[k] = sQuu[i * LDQ + k];
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+          double d = sQuu[j * LDQ + j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) { const double ljk = sL[j * m + k]; d -= ljk * ljk; }
+          if (!(d > 0.0)) bad = 1;
+          const double dinv = rsqrt_nr(d);
+          double sij = row[j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) sij -= row[k] * sL[j * m + k];
+          sij = (i == j) ? d * dinv : sij * dinv;
+          row[j] = sij;
+          if (lane < m && i >= j) sL[i * m + j] = sij;
+          if (lane == j) sLinv[j] = dinv;
+          __syncwarp();
+        }
+      }
+      if (bad) { failed = 1; break; }  // uniform: every lane evaluates every pivot
+      // ---- gains: K = Quu^-1 Qxu^T (one right-hand side per lane), k = Quu^-1 Qu ----
+      for (int c = lane; c < n + 1; c += 32) {
+        double rhs[m];
+        if (c < n) {
+#pragma unroll
+          for (int i = 0; i < m; ++i) rhs[i] = sQxu[c * LDQ + i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < m; ++i) rhs[i] = Qu[i];
+        }
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+          double s = rhs[i];
+#pragma unroll
+          for (int kk = 0; kk < i; ++kk) s -= sL[i * m + kk] * rhs[kk];
+          rhs[i] = s * sLinv[i];
+        }
+#pragma unroll
+        for (int i = m - 1; i >= 0; --i) {
+          double s = rhs[i];
+#pragma unroll
+          for (int kk = i + 1; kk < m; ++kk) s -= sL[kk * m + i] * rhs[kk];
+          rhs[i] = s * sLinv[i];
+        }
+        if (c < n) {
+#pragma unroll
+          for (int i = 0; i < m; ++i) sK[i * LDB + c] = rhs[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < m; ++i) kv[i] = rhs[i];
+        }
+      }
+      __syncwarp();
+      if (lane < m) {  // Quuk = Quu k
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < m; ++j) s += sQuu[lane * LDQ + j] * kv[j];
+        Quuk[lane] = s;
+      }
+      __syncwarp();
+      // Vx = Qx + K^T Quuk - 2 K^T Qu
+      if (lane < n) {
+        double s1 = 0, s2 = 0;
+#pragma unroll
+        for (int j = 0; j < m; ++j) { const double kji = sK[j * LDB + lane]; s1 += kji * Quuk[j]; s2 += kji * Qu[j]; }
+        tmpv[lane] = Qx[lane] + s1 - 2 * s2;
+      }
+      // ---- Qxx - Qxu K ----
+      {
+        double acc[S::NT][S::NT][2];
+        acc_load(acc, sQxx, LDB, fr, fc);
+        warp_mm<S::NT, S::NT, S::KM, false, true>(acc, sQxu, LDQ, sK, LDB, fr, fc);
+        acc_store(acc, sQxx, LDB, LDB, fr, fc);
+      }
+      __syncwarp();
+      // symmetrise + xreg -> V, NaN guard ("backward_error")
+      for (int idx = lane; idx < n * n; idx += 32) {
+        const int i = idx / n, j = idx - i * n;
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        double a = 0.5 * (sQxx[lo * LDB + hi] + sQxx[hi * LDB + lo]);
+        if (i == j) a += xreg;
+        if (isnan(a)) bad = 1;
+        sV[i * LDB + j] = a;
+      }
+      __syncwarp();
+      if (lane < n) {
+        double s = 0;
+#pragma unroll 6
+        for (int j = 0; j < n; ++j) s += sV[j * LDB + lane] * fsv[j];  // = row `lane` of the symmetric V, conflict-free
+        gv[lane] = s;
+        const double vx = feasible ? tmpv[lane] : (tmpv[lane] + s);
+        if (isnan(vx)) bad = 1;
+        Vxp[lane] = vx;
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      if (bad) { failed = 1; break; }
+      __syncwarp();
       // outputs
       {
-        double* Kg = bf.K + ((size_t)b * T + t) * NU * NDX;
-        for (int i = tid; i < NU * NDX; i += NT) Kg[i] = Kt[i];
-        double* kg = bf.k + ((size_t)b * T + t) * NU;
-        for (int i = tid; i < NU; i += NT) kg[i] = kv[i];
-        for (int i = tid; i < NDX; i += NT) { bf.Vx[(nb + t) * NDX + i] = Vxp[i]; bf.g[(nb + t) * NDX + i] = gv[i]; }
-        if (tid == NT - 1) {
+        double* Kg = bf.K + ((size_t)b * T + t) * m * n;
+        for (int e = lane; e < m * n; e += 32) { const int i = e / n; Kg[e] = sK[i * LDB + (e - i * n)]; }
+        double* kg = bf.k + ((size_t)b * T + t) * m;
+        if (lane < m) kg[lane] = kv[lane];
+        if (lane < n) { bf.Vx[(nb + t) * n + lane] = Vxp[lane]; bf.g[(nb + t) * n + lane] = gv[lane]; }
+        if (lane == 31) {
           double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-          for (int i = 0; i < NU; ++i) { s0 += Qu[i] * kv[i]; s1 += kv[i] * Quuk[i]; }
-          for (int i = 0; i < NDX; ++i) { s2 += Vxp[i] * fsv[i]; s3 += fsv[i] * gv[i]; }
+          for (int i = 0; i < m; ++i) { s0 += Qu[i] * kv[i]; s1 += kv[i] * Quuk[i]; }
+          for (int i = 0; i < n; ++i) { s2 += Vxp[i] * fsv[i]; s3 += fsv[i] * gv[i]; }
           double* ns = bf.nodesc + (nb + t) * 4;
           ns[0] = s0; ns[1] = s1; ns[2] = s2; ns[3] = s3;
         }
       }
-      __syncthreads();
-      if (t > 0) {
-#pragma unroll
-        for (int r = 0; r < S::PREF; ++r) { const int i = tid + r * NT; if (i < D::TILE / 2) tile2[i] = pre[r]; }
-        if (tid < NDX) fsv[tid] = pre_fs;
-      }
-      __syncthreads();
+      __syncwarp();
+      if (t > 0) store_L(pre, pre_fs);
     }
+    cp_async_wait<0>();
+    __syncwarp();
     if (!failed || P.force) break;
     // computeDirection threw: recalcDiff = false; increaseRegularization(); give up at reg_max (src/sbfddp.cpp:245-253)
     st.xreg *= P.reg_factor;
     if (st.xreg > P.reg_max) st.xreg = P.reg_max;
     if (st.xreg == P.reg_max) break;
-    __syncthreads();
   }
   st.bw_fail = failed ? 1 : 0;
   // SolverFDDP::updateExpectedImprovement / expectedImprovementDDP: ordered sums over the nodes
   if (!failed) {
     double dg = 0, dq = 0, dg0 = 0, dq0 = 0;
-    __syncthreads();
-    if (!feasible && tid == 0) { dg -= bf.nodesc[(nb + T) * 4 + 2]; dq += bf.nodesc[(nb + T) * 4 + 3]; }
+    __syncwarp();
+    if (!feasible && lane == 0) { dg -= bf.nodesc[(nb + T) * 4 + 2]; dq += bf.nodesc[(nb + T) * 4 + 3]; }
     constexpr int CH = S::TOTAL / 4;
     for (int base = 0; base < T; base += CH) {
       const int cnt = min(CH, T - base);
-      for (int i = tid; i < cnt * 4; i += NT) sm[i] = bf.nodesc[(nb + base) * 4 + i];
-      __syncthreads();
-      if (tid == 0) {
+      for (int i = lane; i < cnt * 4; i += 32) sm[i] = bf.nodesc[(nb + base) * 4 + i];
+      __syncwarp();
+      if (lane == 0) {
         for (int t = 0; t < cnt; ++t) {
           dg += sm[t * 4 + 0]; dq -= sm[t * 4 + 1];
           dg0 += sm[t * 4 + 0]; dq0 -= sm[t * 4 + 1];
           if (!feasible) { dg -= sm[t * 4 + 2]; dq += sm[t * 4 + 3]; }
         }
       }
-      __syncthreads();
+      __syncwarp();
     }
-    if (tid == 0) { st.dg = dg; st.dq = dq; st.dg0 = dg0; st.dq0 = dq0; }
+    if (lane == 0) { st.dg = dg; st.dq = dq; st.dg0 = dg0; st.dq0 = dq0; }
   }
-  if (tid == 0) bf.st[b] = st;
+  if (lane == 0) bf.st[b] = st;
 }

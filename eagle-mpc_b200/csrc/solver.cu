@@ -377,7 +377,7 @@ static cudaError_t launch_backward(empc_solver* h, int force, const Buffers* gb 
     attr_set = true;
   }
   BwParams P{h->P.reg_max, h->P.reg_factor, h->P.th_gaptol, force};
-  backward_kernel<D><<<bf.nb, S::THREADS, smem, st>>>(bf, P);
+  backward_kernel<D><<<bf.nb, 32, smem, st>>>(bf, P);  // one warp per OCP
   h->launches++;
   return cudaGetLastError();
 }
