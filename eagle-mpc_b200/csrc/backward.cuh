@@ -41,18 +41,23 @@ struct BwCfg {
   static constexpr int oQuu = oQxu + NP * LDQ;                   // MP x LDQ       Luu -> Quu
   static constexpr int oFxTV = oQuu + MP * LDQ;                  // NP x LDA
   static constexpr int oFuTV = oFxTV + NP * LDA;                 // MP x LDA
-  static constexpr int oK = oFuTV + MP * LDA;                    // KMP x LDB      gains K (m x n)
+  // K and the Cholesky factor live in the FxTV area, which is dead once Qxx and Qxu are formed
+  static constexpr int oK = oFxTV;                               // KMP x LDB      gains K (m x n)
   static constexpr int oL = oK + KMP * LDB;                      // m x m Cholesky factor of Quu, then m reciprocal pivots
-  static constexpr int oVec = oL + m * m + m + ((m * m + m) & 1);
+  static_assert(KMP * LDB + m * m + m <= NP * LDA, "K and L do not fit the FxTV area");
+  static constexpr int oVec = oFuTV + MP * LDA;
   static constexpr int vQx = 0, vQu = vQx + NP, vVx = vQu + MP, vFs = vVx + NP, vG = vFs + NP, vKv = vG + NP,
                        vQuuk = vKv + MP, vTmp = vQuuk + MP, VEC = vTmp + NP;
   static constexpr int TOTAL0 = oVec + VEC;
   static constexpr int TOTAL = TOTAL0 + (TOTAL0 & 1);
-  // register prefetch of the cost blocks Lxx | Lxu | Luu | Lx | Lu (contiguous in the tile) + fs
-  static constexpr int LBLK = n * n + n * m + m * m + n + m;
+  // register prefetch of the cost blocks: Lxx (n^2), diag(Luu) (m), Lx | Lu (n + m, contiguous) + fs.  Lxu is
+  // identically zero and Luu diagonal for every cost the reference's factories build (state / control / frame
+  // residuals never couple x and u; control residuals are u - ref), so those entries are neither written by
+  // node_diff_kernel (the tile buffer is zero-initialised) nor read here.
+  static constexpr int LBLK = n * n + m + n + m;
   static constexpr int PREF = (LBLK + 31) / 32;
 #ifndef EMPC_BW_WARPS_PER_SM
-#define EMPC_BW_WARPS_PER_SM 6
+#define EMPC_BW_WARPS_PER_SM 7
 #endif
 };
 
@@ -165,27 +170,30 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
     for (int e = lane; e < n * m; e += 32) { const int i = e / m, j = e - i * m; cp_async8(sFu + i * LDB + j, tg + D::oFu + e); }
     cp_async_commit();
   };
-  // cost blocks of node t: HBM -> registers (issued early) -> shared memory (at the end of the previous node)
+  // cost blocks of node t: HBM -> registers (issued early) -> shared memory (at the end of the previous node).
+  // Source / destination offsets of this lane's elements are fixed: computed once, packed in 32-bit registers.
+  unsigned pre_off[S::PREF];  // (src offset in the tile, relative to oLxx) << 16 | (dst offset in sm)
+#pragma unroll
+  for (int q = 0; q < S::PREF; ++q) {
+    int e = lane + 32 * q, src = 0, dst = 0xffff;
+    if (e < n * n) { const int i = e / n; src = e; dst = S::oQxx + i * LDB + (e - i * n); }
+    else if (e < n * n + m) { const int i = e - n * n; src = (D::oLuu - D::oLxx) + i * (m + 1); dst = S::oQuu + i * LDQ + i; }
+    else if (e < n * n + m + n) { const int i = e - n * n - m; src = (D::oLx - D::oLxx) + i; dst = S::oVec + S::vQx + i; }
+    else if (e < S::LBLK) { const int i = e - n * n - m - n; src = (D::oLu - D::oLxx) + i; dst = S::oVec + S::vQu + i; }
+    pre_off[q] = ((unsigned)src << 16) | (unsigned)dst;
+  }
   auto load_L = [&](int t, double (&pre)[S::PREF], double& pre_fs) {
     const double* tg = bf.tiles + (nb + t) * D::TILE + D::oLxx;
 #pragma unroll
-    for (int q = 0; q < S::PREF; ++q) { const int e = lane + 32 * q; pre[q] = (e < S::LBLK) ? tg[e] : 0.0; }
+    for (int q = 0; q < S::PREF; ++q) pre[q] = tg[pre_off[q] >> 16];
     pre_fs = (lane < n) ? bf.fs[(nb + t) * n + lane] : 0.0;
   };
   auto store_L = [&](const double (&pre)[S::PREF], double pre_fs) {
+    // Quu's off-diagonal part restarts from zero (Luu is diagonal); Qxu is formed without an initial value
+    for (int e = lane; e < m * m; e += 32) { const int i = e / m; sQuu[i * LDQ + (e - i * m)] = 0.0; }
+    __syncwarp();
 #pragma unroll
-    for (int q = 0; q < S::PREF; ++q) {
-      int e = lane + 32 * q;
-      if (e < n * n) { const int i = e / n; sQxx[i * LDB + (e - i * n)] = pre[q]; continue; }
-      e -= n * n;
-      if (e < n * m) { const int i = e / m; sQxu[i * LDQ + (e - i * m)] = pre[q]; continue; }
-      e -= n * m;
-      if (e < m * m) { const int i = e / m; sQuu[i * LDQ + (e - i * m)] = pre[q]; continue; }
-      e -= m * m;
-      if (e < n) { Qx[e] = pre[q]; continue; }
-      e -= n;
-      if (e < m) Qu[e] = pre[q];
-    }
+    for (int q = 0; q < S::PREF; ++q) { const unsigned d = pre_off[q] & 0xffffu; if (d != 0xffffu) sm[d] = pre[q]; }
     if (lane < n) fsv[lane] = pre_fs;
   };
 
@@ -228,18 +236,28 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       __syncwarp();
       double pre[S::PREF], pre_fs = 0.0;
       if (t > 0) load_L(t - 1, pre, pre_fs);
-      // ---- FxTV = Fx^T V ; FuTV = Fu^T V ----
+      // ---- FxTV = Fx^T V ; FuTV = Fu^T V   (one k-loop: the V fragments are loaded once for both) ----
       {
-        double acc[S::NT][S::NT][2];
-        acc_zero(acc);
-        warp_mm<S::NT, S::NT, S::KN, true, false>(acc, sFx, LDB, sV, LDB, fr, fc);
-        acc_store(acc, sFxTV, LDA, LDA, fr, fc);
-      }
-      {
-        double acc[S::MT][S::NT][2];
-        acc_zero(acc);
-        warp_mm<S::MT, S::NT, S::KN, true, false>(acc, sFu, LDB, sV, LDB, fr, fc);
-        acc_store(acc, sFuTV, LDA, LDA, fr, fc);
+        double aX[S::NT][S::NT][2], aU[S::MT][S::NT][2];
+        acc_zero(aX); acc_zero(aU);
+#pragma unroll
+        for (int ks = 0; ks < S::KN; ++ks) {
+          double fx[S::NT], fu[S::MT], vv[S::NT];
+#pragma unroll
+          for (int i = 0; i < S::NT; ++i) { fx[i] = sFx[(4 * ks + fc) * LDB + 8 * i + fr]; vv[i] = sV[(4 * ks + fc) * LDB + 8 * i + fr]; }
+#pragma unroll
+          for (int i = 0; i < S::MT; ++i) fu[i] = sFu[(4 * ks + fc) * LDB + 8 * i + fr];
+#pragma unroll
+          for (int i = 0; i < S::NT; ++i)
+#pragma unroll
+            for (int j = 0; j < S::NT; ++j) dmma884(aX[i][j][0], aX[i][j][1], fx[i], vv[j]);
+#pragma unroll
+          for (int i = 0; i < S::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < S::NT; ++j) dmma884(aU[i][j][0], aU[i][j][1], fu[i], vv[j]);
+        }
+        acc_store(aX, sFxTV, LDA, LDA, fr, fc);
+        acc_store(aU, sFuTV, LDA, LDA, fr, fc);
       }
       // Qx += Fx^T Vx' ; Qu += Fu^T Vx'   (lane = output row, ascending l as in the reference)
       if (lane < n) {
@@ -255,24 +273,35 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         Qu[i] += s;
       }
       __syncwarp();
-      // ---- Qxx += FxTV Fx ; Qxu += FxTV Fu ; Quu += FuTV Fu + ureg I ----
+      // ---- Qxx = Lxx + FxTV Fx ; Qxu = FxTV Fu ; Quu = Luu + FuTV Fu   (one k-loop, every fragment loaded once).
+      // Qxx stays in registers until Qxu K has been subtracted from it. ----
+      double qxx[S::NT][S::NT][2];
       {
-        double acc[S::NT][S::NT][2];
-        acc_load(acc, sQxx, LDB, fr, fc);
-        warp_mm<S::NT, S::NT, S::KN, false, false>(acc, sFxTV, LDA, sFx, LDB, fr, fc);
-        acc_store(acc, sQxx, LDB, LDB, fr, fc);
-      }
-      {
-        double acc[S::NT][S::MT][2];
-        acc_load(acc, sQxu, LDQ, fr, fc);
-        warp_mm<S::NT, S::MT, S::KN, false, false>(acc, sFxTV, LDA, sFu, LDB, fr, fc);
-        acc_store(acc, sQxu, LDQ, LDQ, fr, fc);
-      }
-      {
-        double acc[S::MT][S::MT][2];
-        acc_load(acc, sQuu, LDQ, fr, fc);
-        warp_mm<S::MT, S::MT, S::KN, false, false>(acc, sFuTV, LDA, sFu, LDB, fr, fc);
-        acc_store(acc, sQuu, LDQ, LDQ, fr, fc);
+        double qxu[S::NT][S::MT][2], quu[S::MT][S::MT][2];
+        acc_load(qxx, sQxx, LDB, fr, fc);
+        acc_zero(qxu);  // Lxu == 0
+        acc_load(quu, sQuu, LDQ, fr, fc);
+#pragma unroll
+        for (int ks = 0; ks < S::KN; ++ks) {
+          double ax[S::NT], au[S::MT], bx[S::NT], bu[S::MT];
+#pragma unroll
+          for (int i = 0; i < S::NT; ++i) { ax[i] = sFxTV[(8 * i + fr) * LDA + 4 * ks + fc]; bx[i] = sFx[(4 * ks + fc) * LDB + 8 * i + fr]; }
+#pragma unroll
+          for (int i = 0; i < S::MT; ++i) { au[i] = sFuTV[(8 * i + fr) * LDA + 4 * ks + fc]; bu[i] = sFu[(4 * ks + fc) * LDB + 8 * i + fr]; }
+#pragma unroll
+          for (int i = 0; i < S::NT; ++i) {
+#pragma unroll
+            for (int j = 0; j < S::NT; ++j) dmma884(qxx[i][j][0], qxx[i][j][1], ax[i], bx[j]);
+#pragma unroll
+            for (int j = 0; j < S::MT; ++j) dmma884(qxu[i][j][0], qxu[i][j][1], ax[i], bu[j]);
+          }
+#pragma unroll
+          for (int i = 0; i < S::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < S::MT; ++j) dmma884(quu[i][j][0], quu[i][j][1], au[i], bu[j]);
+        }
+        acc_store(qxu, sQxu, LDQ, LDQ, fr, fc);
+        acc_store(quu, sQuu, LDQ, LDQ, fr, fc);
       }
       __syncwarp();
       // Fx, Fu of this node are dead: start fetching the next node's while Quu is factorised
@@ -304,6 +333,8 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         }
       }
       if (bad) { failed = 1; break; }  // uniform: every lane evaluates every pivot
+      // K shares its storage with FxTV: clear the part the solve below does not overwrite (rows m.., columns n..)
+      for (int e = lane; e < S::KMP * LDB; e += 32) { const int i = e / LDB, j = e - i * LDB; if (i >= m || j >= n) sK[e] = 0.0; }
       // ---- gains: K = Quu^-1 Qxu^T (one right-hand side per lane), k = Quu^-1 Qu ----
       for (int c = lane; c < n + 1; c += 32) {
         double rhs[m];
@@ -314,19 +345,19 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
 #pragma unroll
           for (int i = 0; i < m; ++i) rhs[i] = Qu[i];
         }
+        // column-oriented substitution: entry i receives its subtractions in the same order (k ascending / descending)
+        // as the row-oriented reference loops, but the dependent chain is one multiply + one FMA per column
 #pragma unroll
-        for (int i = 0; i < m; ++i) {
-          double s = rhs[i];
+        for (int kk = 0; kk < m; ++kk) {
+          rhs[kk] *= sLinv[kk];
 #pragma unroll
-          for (int kk = 0; kk < i; ++kk) s -= sL[i * m + kk] * rhs[kk];
-          rhs[i] = s * sLinv[i];
+          for (int i = kk + 1; i < m; ++i) rhs[i] -= sL[i * m + kk] * rhs[kk];
         }
 #pragma unroll
-        for (int i = m - 1; i >= 0; --i) {
-          double s = rhs[i];
+        for (int kk = m - 1; kk >= 0; --kk) {
+          rhs[kk] *= sLinv[kk];
 #pragma unroll
-          for (int kk = i + 1; kk < m; ++kk) s -= sL[kk * m + i] * rhs[kk];
-          rhs[i] = s * sLinv[i];
+          for (int i = kk - 1; i >= 0; --i) rhs[i] -= sL[kk * m + i] * rhs[kk];
         }
         if (c < n) {
 #pragma unroll
@@ -351,22 +382,29 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         for (int j = 0; j < m; ++j) { const double kji = sK[j * LDB + lane]; s1 += kji * Quuk[j]; s2 += kji * Qu[j]; }
         tmpv[lane] = Qx[lane] + s1 - 2 * s2;
       }
-      // ---- Qxx - Qxu K ----
+      // ---- Vxx = sym(Qxx - Qxu K) + xreg I, all in the accumulator registers ----
+      warp_mm<S::NT, S::NT, S::KM, false, true>(qxx, sQxu, LDQ, sK, LDB, fr, fc);
       {
-        double acc[S::NT][S::NT][2];
-        acc_load(acc, sQxx, LDB, fr, fc);
-        warp_mm<S::NT, S::NT, S::KM, false, true>(acc, sQxu, LDQ, sK, LDB, fr, fc);
-        acc_store(acc, sQxx, LDB, LDB, fr, fc);
-      }
-      __syncwarp();
-      // symmetrise + xreg -> V, NaN guard ("backward_error")
-      for (int idx = lane; idx < n * n; idx += 32) {
-        const int i = idx / n, j = idx - i * n;
-        const int lo = i < j ? i : j, hi = i < j ? j : i;
-        double a = 0.5 * (sQxx[lo * LDB + hi] + sQxx[hi * LDB + lo]);
-        if (i == j) a += xreg;
-        if (isnan(a)) bad = 1;
-        sV[i * LDB + j] = a;
+        // the mirror image of this lane's pair (row fr, columns 2 fc + h) of tile (i, j) is element (2 fc + h, fr) of
+        // tile (j, i): it sits in lane (2 fc + h) * 4 + (fr >> 1), slot fr & 1
+        double vsym[S::NT][S::NT][2];
+        const int src0 = (2 * fc) * 4 + (fr >> 1), src1 = (2 * fc + 1) * 4 + (fr >> 1);
+        const bool odd = fr & 1;
+#pragma unroll
+        for (int i = 0; i < S::NT; ++i)
+#pragma unroll
+          for (int j = 0; j < S::NT; ++j) {
+            const double a0 = __shfl_sync(0xffffffffu, qxx[j][i][0], src0), a1 = __shfl_sync(0xffffffffu, qxx[j][i][1], src0);
+            const double b0 = __shfl_sync(0xffffffffu, qxx[j][i][0], src1), b1 = __shfl_sync(0xffffffffu, qxx[j][i][1], src1);
+            double v0 = 0.5 * (qxx[i][j][0] + (odd ? a1 : a0));
+            double v1 = 0.5 * (qxx[i][j][1] + (odd ? b1 : b0));
+            const int row = 8 * i + fr, col = 8 * j + 2 * fc;
+            if (row == col && row < n) v0 += xreg;
+            if (row == col + 1 && row < n) v1 += xreg;
+            if (isnan(v0) || isnan(v1)) bad = 1;  // "backward_error"
+            vsym[i][j][0] = v0; vsym[i][j][1] = v1;
+          }
+        acc_store(vsym, sV, LDB, LDB, fr, fc);
       }
       __syncwarp();
       if (lane < n) {
@@ -384,16 +422,21 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       // outputs
       {
         double* Kg = bf.K + ((size_t)b * T + t) * m * n;
-        for (int e = lane; e < m * n; e += 32) { const int i = e / n; Kg[e] = sK[i * LDB + (e - i * n)]; }
+        for (int e2 = lane; e2 < m * n / 2; e2 += 32) {
+          const int e = 2 * e2, i = e / n, j = e - i * n;  // n even: a pair never straddles rows
+          reinterpret_cast<double2*>(Kg)[e2] = *reinterpret_cast<const double2*>(sK + i * LDB + j);
+        }
         double* kg = bf.k + ((size_t)b * T + t) * m;
         if (lane < m) kg[lane] = kv[lane];
         if (lane < n) { bf.Vx[(nb + t) * n + lane] = Vxp[lane]; bf.g[(nb + t) * n + lane] = gv[lane]; }
-        if (lane == 31) {
-          double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-          for (int i = 0; i < m; ++i) { s0 += Qu[i] * kv[i]; s1 += kv[i] * Quuk[i]; }
-          for (int i = 0; i < n; ++i) { s2 += Vxp[i] * fsv[i]; s3 += fsv[i] * gv[i]; }
-          double* ns = bf.nodesc + (nb + t) * 4;
-          ns[0] = s0; ns[1] = s1; ns[2] = s2; ns[3] = s3;
+        if (lane >= 28) {  // four ordered dot products, one per lane
+          const int w = lane - 28;
+          const double* pa = (w == 0) ? Qu : (w == 1) ? kv : (w == 2) ? Vxp : fsv;
+          const double* pb = (w == 0) ? kv : (w == 1) ? Quuk : (w == 2) ? fsv : gv;
+          const int cnt = (w < 2) ? m : n;
+          double sacc = 0;
+          for (int i = 0; i < cnt; ++i) sacc += pa[i] * pb[i];
+          bf.nodesc[(nb + t) * 4 + w] = sacc;
         }
       }
       __syncwarp();

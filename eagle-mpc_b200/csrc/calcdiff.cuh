@@ -625,12 +625,12 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
 
   // ---- B7: cost derivatives ----
   {
-    double* gLxx = tile + D::oLxx; double* gLxu = tile + D::oLxu; double* gLuu = tile + D::oLuu;
+    double* gLxx = tile + D::oLxx; double* gLuu = tile + D::oLuu;
     double* gLx = tile + D::oLx; double* gLu = tile + D::oLu;
     static_assert(D::oLxx % 2 == 0 && D::oLxu % 2 == 0 && NDX % 2 == 0, "double2 stores need even offsets");
-    // Lxu = 0, Luu diagonal, Lu: the same for every node
-    for (int e = l; e < NDX * NU / 2; e += W::LANES) reinterpret_cast<double2*>(gLxu)[e] = make_double2(0.0, 0.0);
-    for (int e = l; e < NU * NU; e += W::LANES) { const int i = e / NU, j = e - i * NU; gLuu[e] = (i == j) ? pk[P::oLUUD + i] * dt : 0.0; }
+    // Lxu == 0 and the off-diagonal part of Luu == 0 for every cost the factories build: those tile entries keep the
+    // zeros of the allocation (empc_create) and are never written, nor read by backward_kernel
+    for (int i = l; i < NU; i += W::LANES) gLuu[i * NU + i] = pk[P::oLUUD + i] * dt;
     for (int i = l; i < NU; i += W::LANES) gLu[i] = pk[P::oLU + i] * dt;
     if (D::TILE != D::TILE0 && l == 0) tile[D::TILE0] = 0.0;
     auto lxx_state = [&](int i, int j) -> double {  // state-cost part: 6x6 block + diagonal
