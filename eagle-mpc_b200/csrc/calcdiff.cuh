@@ -45,20 +45,37 @@ EMPC_DI size_t pk_index(size_t n, int f) { return (n / Pk<D>::GROUP) * (size_t)(
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Kernel A: serial part, one thread per node.
+#ifndef EMPC_NC_FULL
+#define EMPC_NC_FULL true
+#endif
+// The kernel is ~19 000 straight-line instructions (300 KB): far beyond the instruction caches.  All warps of an SM
+// therefore run as ONE block and re-converge at block barriers between the phases, so that they stream the same code
+// window together instead of each thrashing the instruction cache at its own program counter.  Barriers need every thread,
+// so threads without a node to process do not return: they shadow a valid node with their stores switched off.
+#ifndef EMPC_NC_THREADS
+#define EMPC_NC_THREADS 256
+#endif
+#ifndef EMPC_NC_BLOCKS
+#define EMPC_NC_BLOCKS 2
+#endif
+constexpr int NC_THREADS = EMPC_NC_THREADS;
+#define EMPC_NC_PHASE() __syncthreads()
 template <class D>
-__global__ void __launch_bounds__(128, 2) node_calc_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
+__global__ void __launch_bounds__(NC_THREADS, EMPC_NC_BLOCKS) node_calc_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
   constexpr int NJ = D::NJ, NV = D::NV, NDX = D::NDX, NU = D::NU, NX = D::NX, NR = D::NR;
   using P = Pk<D>;
-  const int nl = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nl0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int T1 = bf.T + 1;
-  if (nl >= bf.nb * T1) return;
-  const size_t n = (size_t)bf.b0 * T1 + nl;
+  const long long n_nodes = (long long)bf.nb * T1;
+  bool on = nl0 < n_nodes;
+  const size_t n = (size_t)bf.b0 * T1 + (on ? nl0 : n_nodes - 1);
   const int b = (int)(n / T1), t = (int)(n - (size_t)b * T1);
   const OcpState st = bf.st[b];
-  if (!force && (st.phase == PHASE_DONE || !st.recalc)) return;
+  if (!force && (st.phase == PHASE_DONE || !st.recalc)) on = false;
+  if (__syncthreads_or(on) == 0) return;  // nothing to do for the whole block
   const double smooth = force ? force_smooth : st.smooth;
   double* pk = bf.packets + pk_index<D>(n, 0);  // field f of this node: pk[f * GROUP]
-  auto put = [&](int f, double v) { pk[(size_t)f * P::GROUP] = v; };
+  auto put = [&](int f, double v) { if (on) pk[(size_t)f * P::GROUP] = v; };
 
   double x[NX], u[NU];
   const double* xg = bf.xs + n * NX;
@@ -99,7 +116,9 @@ __global__ void __launch_bounds__(128, 2) node_calc_kernel(Buffers bf, int force
 #pragma unroll
   for (int i = 0; i < D::NA; ++i) tau[6 + i] = nd.s[NR + i];
 
-  aba_kinematics<D, true>(M, x, nd);
+  EMPC_NC_PHASE();
+  aba_kinematics<D, EMPC_NC_FULL>(M, x, nd);
+  EMPC_NC_PHASE();
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
 #pragma unroll
@@ -169,10 +188,12 @@ __global__ void __launch_bounds__(128, 2) node_calc_kernel(Buffers bf, int force
     for (int i = 0; i < NU; ++i) { put(P::oLU + i, Lu[i]); put(P::oLUUD + i, Luud[i]); }
     put(P::oFLAG, flag);
   }
-  bf.node_cost[n] = M.dt * csum;
+  if (on) bf.node_cost[n] = M.dt * csum;
 
   // forward dynamics + semi-implicit Euler
-  aba_dynamics<D, true>(M, tau, nd);
+  EMPC_NC_PHASE();
+  aba_dynamics<D, EMPC_NC_FULL>(M, tau, nd);
+  EMPC_NC_PHASE();
   double xn[NX];
   {
     const double dt = M.dt, dt2 = dt * dt;
@@ -183,8 +204,11 @@ __global__ void __launch_bounds__(128, 2) node_calc_kernel(Buffers bf, int force
     }
     state_integrate<D>(x, nd.dx, xn);
     double* xng = bf.xnext + n * NX;
+    if (on) {
 #pragma unroll
-    for (int i = 0; i < NX; ++i) xng[i] = xn[i];
+      for (int i = 0; i < NX; ++i) xng[i] = xn[i];
+    }
+    EMPC_NC_PHASE();
     // Lie-group transport pieces of Fx / Fu
     double JeA[9], JeQ[9]; Jexp6_blocks(nd.dx, JeA, JeQ);
     SE3 E; exp6(nd.dx, E);
@@ -201,6 +225,7 @@ __global__ void __launch_bounds__(128, 2) node_calc_kernel(Buffers bf, int force
     for (int i = 0; i < 9; ++i) { cIo[i] = 0; cG[i] = 0; }
 #pragma unroll
     for (int k = NJ - 1; k >= 0; --k) {
+      EMPC_NC_PHASE();
       const SE3& oMk = nd.oM[k];
       double ov[6], oa[6];
       act_motion(oMk, nd.v[k], ov);
@@ -252,6 +277,8 @@ __global__ void __launch_bounds__(128, 2) node_calc_kernel(Buffers bf, int force
   }
 
   // gaps (SolverDDP::calcDiff): fs[0] = x0 (-) xs[0], fs[t+1] = xnext_t (-) xs[t+1]
+  EMPC_NC_PHASE();
+  if (!on) return;
   if (!st.is_feasible) {
     if (t < bf.T) {
       double x1[NX], f[NDX];

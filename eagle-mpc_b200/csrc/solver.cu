@@ -342,7 +342,7 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   if (!st) st = h->stream;
   const int T1 = h->T + 1;
   const long long n = (long long)bf.nb * T1;
-  node_calc_kernel<D><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bf, force, smooth, h->hmodel);
+  node_calc_kernel<D><<<(unsigned)((n + NC_THREADS - 1) / NC_THREADS), NC_THREADS, 0, st>>>(bf, force, smooth, h->hmodel);
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
