@@ -288,18 +288,40 @@ def main():
             "rollout": 8 * ((nx + nu + nu * ndx + nu + ndx) + (nx + nu + 1)),  # one trial (the sequential reference's usual case)
         }
         names = ["calc_diff", "backward", "rollout", "decide"]
+        kernels = {"calc_diff": "node_calc_kernel+node_diff_kernel", "backward": "backward_kernel",
+                   "rollout": "rollout_kernel", "decide": "decide_kernel"}
         dom = int(np.argmax(ms_k[:3]))
         n_launch = max(1, (launches_serial - 2) // 7)  # batch-iterations of the instrumented step (7 launches each)
         ach = bytes_node[names[dom]] * float(units_k[dom]) * T / (ms_k[dom] * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        roofline = {"bound": "hbm", "kernel": names[dom] + "_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_kind": peak_kind,
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r1_traffic.json:
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload), if there is one
+        traffic = None
+        try:
+            tr_json = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tr_json.get("workload") == args.workload and tr_json.get("batch") == B:
+                traffic = tr_json["kernels"].get(names[dom], {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+        # exact FLOP count of the Riccati sweep per node against the measured FP64 tensor rate
+        flops_bw = 2 * (2 * ndx**3 + 2 * ndx**2 * nu + ndx * nu**2 + ndx**2 * nu) + nu**3 / 3 + 2 * nu**2 * (ndx + 1) + 2 * ndx**2
+        fp64_peak = 37.05  # TFLOP/s, mma.sync m8n8k4.f64 measured on this pool (profiles/r1_baseline.md)
+        fp64_ach = flops_bw * float(units_k[1]) * T / (ms_k[1] * 1e-3) / 1e12
+        ceiling = peak * 1e9 / (T * sum(bytes_node.values()))  # HBM-bound OCP-iterations/s per GPU (1 rollout trial)
+        roofline = {"bound": "hbm", "kernel": kernels[names[dom]], "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": traffic, "peak_kind": peak_kind,
                     "algorithmic_bytes_per_node": bytes_node[names[dom]],
+                    "algorithmic_bytes_per_launch": bytes_node[names[dom]] * float(units_k[dom]) * T / n_launch,
                     "avg_launch_ms": float(ms_k[dom] / n_launch),
                     "share_of_step": {n: float(ms_k[i] / ms_k.sum()) for i, n in enumerate(names)},
                     "ms_by_kernel_per_step": {n: float(ms_k[i]) for i, n in enumerate(names)},
-                    "note": "per-kernel times from one instrumented step on the serial schedule; the timed steps overlap "
-                            "batch groups on separate streams"}
+                    "hbm_frac_by_kernel": {n: float(bytes_node[n] * float(units_k[i]) * T / (ms_k[i] * 1e-3) / 1e9 / peak)
+                                           for i, n in enumerate(names[:3])},
+                    "backward_fp64": {"achieved_tflops": fp64_ach, "peak_tflops": fp64_peak, "frac": fp64_ach / fp64_peak,
+                                      "flops_per_node": flops_bw, "peak_kind": "measured DMMA (scripts/microbench/fp64_peak.cu)"},
+                    "step_hbm_ceiling_ocp_iter_per_s": ceiling, "step_frac_of_hbm_ceiling": (iters_all / world) / wall / ceiling,
+                    "note": "per-kernel times: CUDA events on the solver's stream around every launch of one extra instrumented "
+                            "step (same schedule as the timed steps)"}
         out = {"metric": METRIC, "value": iters_all / wall, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
