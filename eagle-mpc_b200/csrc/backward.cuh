@@ -36,8 +36,9 @@ struct BwCfg {
   static constexpr int oFx = 0;                                  // KNP x LDB
   static constexpr int oFu = oFx + KNP * LDB;                    // KNP x LDB
   static constexpr int oV = oFu + KNP * LDB;                     // ROWS_K x LDB   Vxx' (symmetric)
-  static constexpr int oQxx = oV + ROWS_K * LDB;                 // NP x LDB       Lxx -> Qxx -> Qxx - Qxu K
-  static constexpr int oQxu = oQxx + NP * LDB;                   // NP x LDQ       Lxu -> Qxu
+  // (Qxx never touches shared memory: Lxx is loaded from HBM straight into the accumulator fragments and
+  //  Qxx - Qxu K is symmetrised in registers)
+  static constexpr int oQxu = oV + ROWS_K * LDB;                 // NP x LDQ       Qxu
   static constexpr int oQuu = oQxu + NP * LDQ;                   // MP x LDQ       Luu -> Quu
   static constexpr int oFxTV = oQuu + MP * LDQ;                  // NP x LDA
   static constexpr int oFuTV = oFxTV + NP * LDA;                 // MP x LDA
@@ -50,14 +51,14 @@ struct BwCfg {
                        vQuuk = vKv + MP, vTmp = vQuuk + MP, VEC = vTmp + NP;
   static constexpr int TOTAL0 = oVec + VEC;
   static constexpr int TOTAL = TOTAL0 + (TOTAL0 & 1);
-  // register prefetch of the cost blocks: Lxx (n^2), diag(Luu) (m), Lx | Lu (n + m, contiguous) + fs.  Lxu is
+  // register prefetch (one node ahead) of the small cost blocks: diag(Luu) (m), Lx | Lu (n + m, contiguous) + fs.  Lxu is
   // identically zero and Luu diagonal for every cost the reference's factories build (state / control / frame
   // residuals never couple x and u; control residuals are u - ref), so those entries are neither written by
   // node_diff_kernel (the tile buffer is zero-initialised) nor read here.
-  static constexpr int LBLK = n * n + m + n + m;
+  static constexpr int LBLK = m + n + m;
   static constexpr int PREF = (LBLK + 31) / 32;
 #ifndef EMPC_BW_WARPS_PER_SM
-#define EMPC_BW_WARPS_PER_SM 7
+#define EMPC_BW_WARPS_PER_SM 8
 #endif
 };
 
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
   }
   const int feasible = st.is_feasible;
 
-  double* sFx = sm + S::oFx; double* sFu = sm + S::oFu; double* sV = sm + S::oV; double* sQxx = sm + S::oQxx;
+  double* sFx = sm + S::oFx; double* sFu = sm + S::oFu; double* sV = sm + S::oV;
   double* sQxu = sm + S::oQxu; double* sQuu = sm + S::oQuu; double* sFxTV = sm + S::oFxTV; double* sFuTV = sm + S::oFuTV;
   double* sK = sm + S::oK; double* sL = sm + S::oL; double* sLinv = sL + m * m;
   double* vec = sm + S::oVec;
@@ -176,10 +177,9 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
 #pragma unroll
   for (int q = 0; q < S::PREF; ++q) {
     int e = lane + 32 * q, src = 0, dst = 0xffff;
-    if (e < n * n) { const int i = e / n; src = e; dst = S::oQxx + i * LDB + (e - i * n); }
-    else if (e < n * n + m) { const int i = e - n * n; src = (D::oLuu - D::oLxx) + i * (m + 1); dst = S::oQuu + i * LDQ + i; }
-    else if (e < n * n + m + n) { const int i = e - n * n - m; src = (D::oLx - D::oLxx) + i; dst = S::oVec + S::vQx + i; }
-    else if (e < S::LBLK) { const int i = e - n * n - m - n; src = (D::oLu - D::oLxx) + i; dst = S::oVec + S::vQu + i; }
+    if (e < m) { src = (D::oLuu - D::oLxx) + e * (m + 1); dst = S::oQuu + e * LDQ + e; }
+    else if (e < m + n) { const int i = e - m; src = (D::oLx - D::oLxx) + i; dst = S::oVec + S::vQx + i; }
+    else if (e < S::LBLK) { const int i = e - m - n; src = (D::oLu - D::oLxx) + i; dst = S::oVec + S::vQu + i; }
     pre_off[q] = ((unsigned)src << 16) | (unsigned)dst;
   }
   auto load_L = [&](int t, double (&pre)[S::PREF], double& pre_fs) {
@@ -236,6 +236,21 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       __syncwarp();
       double pre[S::PREF], pre_fs = 0.0;
       if (t > 0) load_L(t - 1, pre, pre_fs);
+      // Lxx of this node: HBM -> accumulator fragments (row 8 i + fr, columns 8 j + 2 fc, +1); in flight during the
+      // first two products
+      double qxx[S::NT][S::NT][2];
+      {
+        const double* lg = bf.tiles + (nb + t) * D::TILE + D::oLxx;
+#pragma unroll
+        for (int i = 0; i < S::NT; ++i)
+#pragma unroll
+          for (int j = 0; j < S::NT; ++j) {
+            const int row = 8 * i + fr, col = 8 * j + 2 * fc;
+            double2 v = make_double2(0.0, 0.0);
+            if (row < n && col < n) v = *reinterpret_cast<const double2*>(lg + row * n + col);
+            qxx[i][j][0] = v.x; qxx[i][j][1] = v.y;
+          }
+      }
       // ---- FxTV = Fx^T V ; FuTV = Fu^T V   (one k-loop: the V fragments are loaded once for both) ----
       {
         double aX[S::NT][S::NT][2], aU[S::MT][S::NT][2];
@@ -275,10 +290,8 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       __syncwarp();
       // ---- Qxx = Lxx + FxTV Fx ; Qxu = FxTV Fu ; Quu = Luu + FuTV Fu   (one k-loop, every fragment loaded once).
       // Qxx stays in registers until Qxu K has been subtracted from it. ----
-      double qxx[S::NT][S::NT][2];
       {
         double qxu[S::NT][S::MT][2], quu[S::MT][S::MT][2];
-        acc_load(qxx, sQxx, LDB, fr, fc);
         acc_zero(qxu);  // Lxu == 0
         acc_load(quu, sQuu, LDQ, fr, fc);
 #pragma unroll
