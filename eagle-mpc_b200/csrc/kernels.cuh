@@ -46,6 +46,7 @@ struct Buffers {
   double* K; double* k; double* Vx; double* g; double* nodesc;
   // trials
   double* xs_try; double* us_try; double* cost_try; double* dv; int* ok;
+  double* trial_node_cost;  // [alpha][OCP][T+1] node costs of the trial trajectories
   double* us_squash;
   int* n_active;
 };

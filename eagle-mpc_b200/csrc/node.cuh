@@ -496,6 +496,57 @@ EMPC_DI void node_calc(const DevModel& M, const CostTables& C, int costset, doub
   cost = dt * csum;
 }
 
+// Dynamics half of IntegratedActionModelEuler::calc (squash -> thrust map -> ABA -> semi-implicit Euler), without the
+// costs: the rollout's sequential chain (rollout.cuh) evaluates only this; the trial costs are computed in parallel over
+// all (trial, node) pairs afterwards (trial_cost_kernel).
+template <class D, bool FULL = false>
+EMPC_DI void node_dyn(const DevModel& M, double smooth, const double* x, const double* u, double* xnext) {
+  NodeData<D> nd;
+  squash<D>(M, smooth, u, nd.s);
+  double tau[D::NV];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double t = 0;
+#pragma unroll
+    for (int j = 0; j < D::NR; ++j) t += M.tau_f[i * D::NR + j] * nd.s[j];
+    tau[i] = t;
+  }
+#pragma unroll
+  for (int i = 0; i < D::NA; ++i) tau[6 + i] = nd.s[D::NR + i];
+  aba_kinematics<D, FULL>(M, x, nd);
+  aba_dynamics<D, FULL>(M, tau, nd);
+  const double dt = M.dt, dt2 = dt * dt;
+#pragma unroll
+  for (int i = 0; i < D::NV; ++i) {
+    nd.dx[i] = x[D::NQ + i] * dt + nd.a[i] * dt2;
+    nd.dx[D::NV + i] = nd.a[i] * dt;
+  }
+  state_integrate<D>(x, nd.dx, xnext);
+}
+
+// Cost half: dt * sum_c w_c a_c(r_c(x, u)) in the reference's cost order; needs the kinematics only when the cost set
+// holds frame costs.
+template <class D>
+EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x, const double* u) {
+  const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
+  bool need_kin = false;
+  for (int c = c0; c < c1; ++c) {
+    const int ty = C.costs[c].type;
+    if (C.costs[c].active && ty != EMPC_COST_STATE && ty != EMPC_COST_CONTROL && ty != EMPC_COST_SQUASH_BARRIER) need_kin = true;
+  }
+  NodeData<D> nd;
+  if (need_kin) aba_kinematics<D, false>(M, x, nd);
+  double csum = 0;
+  for (int c = c0; c < c1; ++c) {
+    const empc_cost_t cs = C.costs[c];
+    if (!cs.active) continue;
+    double r[D::NDX], Ar[D::NDX], Arr[D::NDX];
+    SE3 rMf;
+    csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
+  }
+  return M.dt * csum;
+}
+
 // world-frame RNEA-derivative recursion + Minv (DESIGN.md "ABA derivatives"); outputs a_q, a_v (NV x NV), Minv, Jc, ov.
 // Tip-to-base sweep with running composite quantities of the subtree: rigid-body inertia Ycrb (m, m c, I_o: 13
 // numbers), subtree force Fcrb, and the composite "B" operator, which reduces to a momentum vector hf and one 3x3

@@ -229,6 +229,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   CKH(dalloc(h, &bf.xs_try, (size_t)EMPC_N_ALPHAS * B * T1 * nx));
   CKH(dalloc(h, &bf.us_try, (size_t)EMPC_N_ALPHAS * B * T * nu));
   CKH(dalloc(h, &bf.cost_try, B * EMPC_N_ALPHAS));
+  CKH(dalloc(h, &bf.trial_node_cost, (size_t)EMPC_N_ALPHAS * B * T1));
   CKH(dalloc(h, &bf.dv, B * EMPC_N_ALPHAS));
   CKH(dalloc(h, &bf.ok, B * EMPC_N_ALPHAS));
   CKH(dalloc(h, &bf.us_squash, B * T * nu));
@@ -405,8 +406,17 @@ static cudaError_t launch_rollout(empc_solver* h, int stage, int force, int feas
   const Buffers& bf = gb ? *gb : h->bf;
   if (!st) st = h->stream;
   RoParams P{force, feasible, ddp, smooth, stage == 0 ? 0 : RO_WIDTH_A};
-  if (stage == 0) return launch_rollout_w<D, RO_WIDTH_A>(h, P, bf, st);
-  return launch_rollout_w<D, 8>(h, P, bf, st);
+  cudaError_t e = (stage == 0) ? launch_rollout_w<D, RO_WIDTH_A>(h, P, bf, st) : launch_rollout_w<D, 8>(h, P, bf, st);
+  if (e != cudaSuccess) return e;
+  // node costs of the trial trajectories (parallel over trials and nodes), then the ordered per-trial sums
+  const int width = (stage == 0) ? RO_WIDTH_A : EMPC_N_ALPHAS - RO_WIDTH_A;
+  const long long n_thr = (long long)bf.nb * width * (h->T + 1);
+  trial_cost_kernel<D><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
+  h->launches++;
+  const long long n_warps = (long long)bf.nb * width;
+  trial_sum_kernel<<<(unsigned)((n_warps + 3) / 4), 128, 0, st>>>(bf, P, width);
+  h->launches++;
+  return cudaGetLastError();
 }
 template <class D>
 static cudaError_t launch_decide(empc_solver* h, int stage, const Buffers* gb = nullptr, cudaStream_t st = nullptr) {
