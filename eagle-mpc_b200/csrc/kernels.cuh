@@ -99,61 +99,125 @@ __device__ __forceinline__ void end_inner_solve(OcpState& st, const empc_solver_
   st.iters_out = st.total_iters - 1;
 }
 
+// One block per OCP.  The step lengths of the stage are visited in the reference's order (src/sbfddp.cpp:260-290,
+// :348-368); for each one whose rollout succeeded the block evaluates the node costs of that trial trajectory in parallel
+// (thread per node), thread 0 adds them in node order (cost_try_) and applies the acceptance test — and the loop stops at
+// the first accepted step, so the costs of the later, speculative rollouts are never computed.
 template <class D>
-__global__ void __launch_bounds__(128) decide_kernel(Buffers bf, DecideParams dp) {
+__global__ void __launch_bounds__(128, 4) decide_kernel(Buffers bf, DecideParams dp, const __grid_constant__ DevModel M) {
   constexpr int NX = D::NX, NU = D::NU;
+  constexpr int CH = 512;  // nodes per chunk of the ordered cost sum
   const int b = bf.b0 + blockIdx.x;
-  __shared__ int s_acc, s_last;
+  __shared__ int s_acc, s_last, s_go, s_stop;
+  __shared__ double s_smooth;
+  __shared__ double s_cost[CH];
   const empc_solver_params_t& P = dp.P;
   const int T = bf.T, T1 = T + 1;
-  if (threadIdx.x == 0) {
-    OcpState st = bf.st[b];
-    int acc = -1, last = -1;
-    const int n_begin = dp.stage == 0 ? 0 : RO_WIDTH_A, n_end = dp.stage == 0 ? RO_WIDTH_A : EMPC_N_ALPHAS;
-    const bool mine = st.phase != PHASE_DONE && (dp.stage == 0 || st.pending);
+  const int tid = threadIdx.x;
+  const int n_begin = dp.stage == 0 ? 0 : RO_WIDTH_A, n_end = dp.stage == 0 ? RO_WIDTH_A : EMPC_N_ALPHAS;
+  OcpState st;  // live in thread 0 only
+  int acc = -1, last = -1;
+  bool mine = false;
+  if (tid == 0) {
+    st = bf.st[b];
+    mine = st.phase != PHASE_DONE && (dp.stage == 0 || st.pending);
+    int go = 0;
     if (mine) {
       if (dp.stage == 1) { st.pending = 0; atomicSub(bf.n_active, 1); }  // re-counted below if still active
       if (st.bw_fail) {
         st.bw_fail = 0;
         end_inner_solve(st, P);  // computeDirection gave up at reg_max: the inner solve returns false
       } else {
-        const int ddp = st.phase == PHASE_DDP;
-        for (int n = n_begin; n < n_end; ++n) {
-          st.steplength = 1.0 / (double)(1 << n);
-          last = n;
-          if (!bf.ok[b * EMPC_N_ALPHAS + n]) continue;  // "forward_error": try the next step length
-          const double cost_try = bf.cost_try[b * EMPC_N_ALPHAS + n];
-          const double dV = st.cost - cost_try;
-          double d0, d1;
-          if (ddp) { d0 = st.dg0; d1 = st.dq0; }
+        go = 1;
+      }
+    }
+    s_go = go; s_smooth = st.smooth; s_acc = -1; s_last = -1;
+  }
+  __syncthreads();
+  if (s_go) {
+    const double smooth = s_smooth;
+    const int* costsets = bf.node_costset + (size_t)bf.ocp_map[b] * T1;
+    for (int n = n_begin; n < n_end; ++n) {
+      const size_t tn = (size_t)b * EMPC_N_ALPHAS + n;
+      const int okn = bf.ok[tn];  // uniform over the block
+      double cost_try = 0.0;
+      if (okn) {
+        // node costs of trial n, chunk by chunk; thread 0 accumulates in node order
+        const size_t trial = (size_t)n * bf.B + b;
+        for (int base = 0; base < T1; base += CH) {
+          const int cnt = min(CH, T1 - base);
+          for (int tt = tid; tt < cnt; tt += blockDim.x) {
+            const int t = base + tt;
+            double x[NX], u[NU];
+            const double* xg = bf.xs_try + (trial * T1 + t) * NX;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) x[i] = xg[i];
+            if (t < T) {
+              const double* ug = bf.us_try + (trial * T + t) * NU;
+#pragma unroll
+              for (int i = 0; i < NU; ++i) u[i] = ug[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < NU; ++i) u[i] = 0.0;
+            }
+            s_cost[tt] = node_cost_value<D>(M, bf.ct, costsets[t], smooth, x, u);
+          }
+          __syncthreads();
+          if (tid == 0) for (int i = 0; i < cnt; ++i) cost_try += s_cost[i];
+          __syncthreads();
+        }
+      }
+      if (tid == 0) {
+        st.steplength = 1.0 / (double)(1 << n);
+        last = n;
+        int stop = 0;
+        if (okn) {
+          bf.cost_try[tn] = cost_try;
+          if (isnan(cost_try)) bf.ok[tn] = 0;  // raiseIfNaN(cost_try_): "forward_error", try the next step length
           else {
-            const double dv = st.is_feasible ? 0.0 : bf.dv[b * EMPC_N_ALPHAS + n];
-            d0 = st.dg + dv; d1 = st.dq - 2 * dv;
-          }
-          const double dVexp = st.steplength * (d0 + 0.5 * st.steplength * d1);
-          bool accept = false;
-          if (dVexp >= 0) {
-            if (ddp) accept = (d0 < P.th_grad || !st.is_feasible || dV > P.th_acceptstep * dVexp);
-            else accept = (d0 < P.th_grad || dV > P.th_acceptstep * dVexp);
-          } else if (!ddp) {
-            accept = dV > P.th_acceptnegstep * dVexp;
-          }
-          if (accept) {
-            st.was_feasible = st.is_feasible;
-            st.is_feasible = ddp ? 1 : ((st.was_feasible || n == 0) ? 1 : 0);
-            st.cost_prev = st.cost; st.cost = cost_try;
-            acc = n;
-            break;
+            const int ddp = st.phase == PHASE_DDP;
+            const double dV = st.cost - cost_try;
+            double d0, d1;
+            if (ddp) { d0 = st.dg0; d1 = st.dq0; }
+            else {
+              const double dv = st.is_feasible ? 0.0 : bf.dv[tn];
+              d0 = st.dg + dv; d1 = st.dq - 2 * dv;
+            }
+            const double dVexp = st.steplength * (d0 + 0.5 * st.steplength * d1);
+            bool accept = false;
+            if (dVexp >= 0) {
+              if (ddp) accept = (d0 < P.th_grad || !st.is_feasible || dV > P.th_acceptstep * dVexp);
+              else accept = (d0 < P.th_grad || dV > P.th_acceptstep * dVexp);
+            } else if (!ddp) {
+              accept = dV > P.th_acceptnegstep * dVexp;
+            }
+            if (accept) {
+              st.was_feasible = st.is_feasible;
+              st.is_feasible = ddp ? 1 : ((st.was_feasible || n == 0) ? 1 : 0);
+              st.cost_prev = st.cost; st.cost = cost_try;
+              acc = n;
+              stop = 1;
+            }
           }
         }
-        if (acc < 0 && n_end < EMPC_N_ALPHAS) {
-          // none of the stage-A step lengths passed: the smaller ones are evaluated by rollout stage B, then decide again
-          st.pending = 1;
-          atomicAdd(bf.n_active, 1);
-          bf.st[b] = st;
-          s_acc = -1; s_last = -1;
-          goto decided;
-        }
+        s_stop = stop;
+      }
+      __syncthreads();
+      if (s_stop) break;
+    }
+  }
+  if (tid == 0 && mine) {
+    bool finish = true;
+    if (s_go) {
+      const int ddp = st.phase == PHASE_DDP;
+      if (acc < 0 && n_end < EMPC_N_ALPHAS) {
+        // none of the stage-A step lengths passed: the smaller ones are evaluated by rollout stage B, then decide again
+        st.pending = 1;
+        atomicAdd(bf.n_active, 1);
+        bf.st[b] = st;
+        finish = false;
+        last = -1;
+      } else {
         st.recalc = acc >= 0 ? 1 : 0;
         st.accepted = acc;
         bool ended = false;
@@ -178,27 +242,28 @@ __global__ void __launch_bounds__(128) decide_kernel(Buffers bf, DecideParams dp
           }
         }
       }
+    }
+    if (finish) {
       if (st.phase != PHASE_DONE) { atomicAdd(bf.n_active, 1); if (st.recalc) atomicAdd(bf.n_active + 1, 1); }
       bf.st[b] = st;
     }
     s_acc = acc; s_last = last;
-  decided:;
   }
   __syncthreads();
-  const int acc = s_acc, last = s_last;
+  acc = s_acc; last = s_last;
   if (last >= 0) {
     // xs_try_[0] persists into the DDP phase from the last forwardPass executed (src/sbfddp.cpp:430)
     const size_t trial = (size_t)last * bf.B + b;
-    for (int i = threadIdx.x; i < NX; i += blockDim.x) bf.xs_try0[(size_t)b * NX + i] = bf.xs_try[trial * T1 * NX + i];
+    for (int i = tid; i < NX; i += blockDim.x) bf.xs_try0[(size_t)b * NX + i] = bf.xs_try[trial * T1 * NX + i];
   }
   if (acc >= 0) {
     const size_t trial = (size_t)acc * bf.B + b;
     const double* xsrc = bf.xs_try + trial * T1 * NX;
     double* xdst = bf.xs + (size_t)b * T1 * NX;
-    for (int i = threadIdx.x; i < T1 * NX; i += blockDim.x) xdst[i] = xsrc[i];
+    for (int i = tid; i < T1 * NX; i += blockDim.x) xdst[i] = xsrc[i];
     const double* usrc = bf.us_try + trial * T * NU;
     double* udst = bf.us + (size_t)b * T * NU;
-    for (int i = threadIdx.x; i < T * NU; i += blockDim.x) udst[i] = usrc[i];
+    for (int i = tid; i < T * NU; i += blockDim.x) udst[i] = usrc[i];
   }
 }
 

@@ -408,7 +408,9 @@ static cudaError_t launch_rollout(empc_solver* h, int stage, int force, int feas
   RoParams P{force, feasible, ddp, smooth, stage == 0 ? 0 : RO_WIDTH_A};
   cudaError_t e = (stage == 0) ? launch_rollout_w<D, RO_WIDTH_A>(h, P, bf, st) : launch_rollout_w<D, 8>(h, P, bf, st);
   if (e != cudaSuccess) return e;
-  // node costs of the trial trajectories (parallel over trials and nodes), then the ordered per-trial sums
+  // In a solve, decide_kernel evaluates the trial costs lazily in line-search order.  The tile-level parity hook wants
+  // cost_try of EVERY step length: node costs in parallel over trials and nodes, then the ordered per-trial sums.
+  if (!force) return cudaSuccess;
   const int width = (stage == 0) ? RO_WIDTH_A : EMPC_N_ALPHAS - RO_WIDTH_A;
   const long long n_thr = (long long)bf.nb * width * (h->T + 1);
   trial_cost_kernel<D><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
@@ -423,7 +425,7 @@ static cudaError_t launch_decide(empc_solver* h, int stage, const Buffers* gb = 
   const Buffers& bf = gb ? *gb : h->bf;
   if (!st) st = h->stream;
   DecideParams dp{h->P, stage};
-  decide_kernel<D><<<bf.nb, 128, 0, st>>>(bf, dp);
+  decide_kernel<D><<<bf.nb, 128, 0, st>>>(bf, dp, h->hmodel);
   h->launches++;
   return cudaGetLastError();
 }
