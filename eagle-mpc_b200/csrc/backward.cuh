@@ -42,11 +42,11 @@ struct BwCfg {
   static constexpr int oQuu = oQxu + NP * LDQ;                   // MP x LDQ       Luu -> Quu
   static constexpr int oFxTV = oQuu + MP * LDQ;                  // NP x LDA
   static constexpr int oFuTV = oFxTV + NP * LDA;                 // MP x LDA
-  // K and the Cholesky factor live in the FxTV area, which is dead once Qxx and Qxu are formed
-  static constexpr int oK = oFxTV;                               // KMP x LDB      gains K (m x n)
-  static constexpr int oL = oK + KMP * LDB;                      // m x m Cholesky factor of Quu, then m reciprocal pivots
-  static_assert(KMP * LDB + m * m + m <= NP * LDA, "K and L do not fit the FxTV area");
-  static constexpr int oVec = oFuTV + MP * LDA;
+  static constexpr int oK = oFuTV + MP * LDA;                    // KMP x LDB      gains K (m x n), zero padded
+  // the Cholesky factor lives in the FxTV area, which is dead once Qxx and Qxu are formed
+  static constexpr int oL = oFxTV;                               // m x m Cholesky factor of Quu, then m reciprocal pivots
+  static_assert(m * m + m <= NP * LDA, "L does not fit the FxTV area");
+  static constexpr int oVec = oK + KMP * LDB;
   static constexpr int vQx = 0, vQu = vQx + NP, vVx = vQu + MP, vFs = vVx + NP, vG = vFs + NP, vKv = vG + NP,
                        vQuuk = vKv + MP, vTmp = vQuuk + MP, VEC = vTmp + NP;
   static constexpr int TOTAL0 = oVec + VEC;
@@ -58,7 +58,7 @@ struct BwCfg {
   static constexpr int LBLK = m + n + m;
   static constexpr int PREF = (LBLK + 31) / 32;
 #ifndef EMPC_BW_WARPS_PER_SM
-#define EMPC_BW_WARPS_PER_SM 8
+#define EMPC_BW_WARPS_PER_SM 7
 #endif
 };
 
@@ -167,8 +167,26 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
   // asynchronous fetch of Fx (16-byte pieces, n even) and Fu (8-byte pieces) of node t into their padded layouts
   auto fetch_F = [&](int t) {
     const double* tg = bf.tiles + (nb + t) * D::TILE;
-    for (int e = lane; e < n * n / 2; e += 32) { const int i = e / (n / 2), cc = e - i * (n / 2); cp_async16(sFx + i * LDB + 2 * cc, tg + D::oFx + 2 * e); }
-    for (int e = lane; e < n * m; e += 32) { const int i = e / m, j = e - i * m; cp_async8(sFu + i * LDB + j, tg + D::oFu + e); }
+    {  // Fx: n rows of n/2 16-byte pieces; piece e = lane + 32 q sits in row e / (n/2); indices advance incrementally
+      constexpr int H = n / 2, DI = 32 / H, DC = 32 % H;
+      int i = lane / H, cc = lane - i * H;
+#pragma unroll
+      for (int q = 0; q < (n * H + 31) / 32; ++q) {
+        if (lane + 32 * q < n * H) cp_async16(sFx + i * LDB + 2 * cc, tg + D::oFx + 2 * (lane + 32 * q));
+        i += DI; cc += DC;
+        if (cc >= H) { cc -= H; i += 1; }
+      }
+    }
+    {  // Fu: n rows of m 8-byte pieces
+      constexpr int DI = 32 / m, DC = 32 % m;
+      int i = lane / m, j = lane - i * m;
+#pragma unroll
+      for (int q = 0; q < (n * m + 31) / 32; ++q) {
+        if (lane + 32 * q < n * m) cp_async8(sFu + i * LDB + j, tg + D::oFu + lane + 32 * q);
+        i += DI; j += DC;
+        if (j >= m) { j -= m; i += 1; }
+      }
+    }
     cp_async_commit();
   };
   // cost blocks of node t: HBM -> registers (issued early) -> shared memory (at the end of the previous node).
@@ -274,18 +292,29 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         acc_store(aX, sFxTV, LDA, LDA, fr, fc);
         acc_store(aU, sFuTV, LDA, LDA, fr, fc);
       }
-      // Qx += Fx^T Vx' ; Qu += Fu^T Vx'   (lane = output row, ascending l as in the reference)
-      if (lane < n) {
-        double s = 0;
-#pragma unroll 6
-        for (int l = 0; l < n; ++l) s += sFx[l * LDB + lane] * Vxp[l];
-        Qx[lane] += s;
+      // Qx += Fx^T Vx' ; Qu += Fu^T Vx'   (lane = output row; three interleaved partial sums cut the dependent chain)
+      {
+        const int i = lane < n ? lane : (lane - n < m ? lane - n : 0);
+        const double* Fm = lane < n ? sFx : sFu;
+        double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int l = 0; l + 2 < n; l += 3) {
+          s0 += Fm[l * LDB + i] * Vxp[l]; s1 += Fm[(l + 1) * LDB + i] * Vxp[l + 1]; s2 += Fm[(l + 2) * LDB + i] * Vxp[l + 2];
+        }
+#pragma unroll
+        for (int l = n - n % 3; l < n; ++l) s0 += Fm[l * LDB + i] * Vxp[l];
+        const double sacc = (s0 + s1) + s2;
+        if (lane < n) Qx[lane] += sacc;
+        else if (lane - n < m) Qu[lane - n] += sacc;
       }
-      for (int i = lane; i < m; i += 32) {
-        double s = 0;
+      if (n + m > 32) {  // rows of Qu that did not fit beside Qx in the warp
+        const int i = lane + 32 - n;
+        if (i < m) {
+          double sacc = 0;
 #pragma unroll 6
-        for (int l = 0; l < n; ++l) s += sFu[l * LDB + i] * Vxp[l];
-        Qu[i] += s;
+          for (int l = 0; l < n; ++l) sacc += sFu[l * LDB + i] * Vxp[l];
+          Qu[i] += sacc;
+        }
       }
       __syncwarp();
       // ---- Qxx = Lxx + FxTV Fx ; Qxu = FxTV Fu ; Quu = Luu + FuTV Fu   (one k-loop, every fragment loaded once).
@@ -346,8 +375,6 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         }
       }
       if (bad) { failed = 1; break; }  // uniform: every lane evaluates every pivot
-      // K shares its storage with FxTV: clear the part the solve below does not overwrite (rows m.., columns n..)
-      for (int e = lane; e < S::KMP * LDB; e += 32) { const int i = e / LDB, j = e - i * LDB; if (i >= m || j >= n) sK[e] = 0.0; }
       // ---- gains: K = Quu^-1 Qxu^T (one right-hand side per lane), k = Quu^-1 Qu ----
       for (int c = lane; c < n + 1; c += 32) {
         double rhs[m];
@@ -421,9 +448,14 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       }
       __syncwarp();
       if (lane < n) {
-        double s = 0;
-#pragma unroll 6
-        for (int j = 0; j < n; ++j) s += sV[j * LDB + lane] * fsv[j];  // = row `lane` of the symmetric V, conflict-free
+        double s0 = 0, s1 = 0, s2 = 0;  // row `lane` of the symmetric V read as a column: conflict-free
+#pragma unroll
+        for (int j = 0; j + 2 < n; j += 3) {
+          s0 += sV[j * LDB + lane] * fsv[j]; s1 += sV[(j + 1) * LDB + lane] * fsv[j + 1]; s2 += sV[(j + 2) * LDB + lane] * fsv[j + 2];
+        }
+#pragma unroll
+        for (int j = n - n % 3; j < n; ++j) s0 += sV[j * LDB + lane] * fsv[j];
+        const double s = (s0 + s1) + s2;
         gv[lane] = s;
         const double vx = feasible ? tmpv[lane] : (tmpv[lane] + s);
         if (isnan(vx)) bad = 1;
@@ -442,14 +474,15 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         double* kg = bf.k + ((size_t)b * T + t) * m;
         if (lane < m) kg[lane] = kv[lane];
         if (lane < n) { bf.Vx[(nb + t) * n + lane] = Vxp[lane]; bf.g[(nb + t) * n + lane] = gv[lane]; }
-        if (lane >= 28) {  // four ordered dot products, one per lane
-          const int w = lane - 28;
+        {  // four ordered dot products on lanes 28..31: same unrolled, predicated code for all of them (loads hoisted)
+          const int w = lane & 3;
           const double* pa = (w == 0) ? Qu : (w == 1) ? kv : (w == 2) ? Vxp : fsv;
           const double* pb = (w == 0) ? kv : (w == 1) ? Quuk : (w == 2) ? fsv : gv;
           const int cnt = (w < 2) ? m : n;
           double sacc = 0;
-          for (int i = 0; i < cnt; ++i) sacc += pa[i] * pb[i];
-          bf.nodesc[(nb + t) * 4 + w] = sacc;
+#pragma unroll
+          for (int i = 0; i < n; ++i) { const double av = (i < cnt) ? pa[i] : 0.0, bv = (i < cnt) ? pb[i] : 0.0; sacc += av * bv; }
+          if (lane >= 28) bf.nodesc[(nb + t) * 4 + w] = sacc;
         }
       }
       __syncwarp();
