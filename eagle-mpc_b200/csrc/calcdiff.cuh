@@ -552,7 +552,9 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
   }
   __syncwarp(hm);
 
-  // ---- B4: a_q = -M^-1 dtau/dq, a_v = -M^-1 dtau/dv, lane = column, in place ----
+  // ---- B4 + B5: a_q = -M^-1 dtau/dq, a_v = -M^-1 dtau/dv (lane = column j), and straight from those registers the two
+  // columns j and NV + j of Fx: rows 6.. are scaled copies, rows 0..5 go through the Lie-group transport ----
+  const double* JeA = pk + P::oJE; const double* JeQ = JeA + 9;
   if (l < NV) {
     double cq[NV], cv[NV], rq[NV], rv[NV];
 #pragma unroll
@@ -564,52 +566,46 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
       for (int k = 0; k < NV; ++k) { const double mi = wk[W::wMinv + i * NV + k]; sq += mi * cq[k]; sv += mi * cv[k]; }
       rq[i] = -sq; rv[i] = -sv;
     }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { wk[W::wDq + i * NV + l] = rq[i]; wk[W::wDv + i * NV + l] = rv[i]; }
-  }
-  __syncwarp(hm);
-  const double* aq = wk + W::wDq; const double* av = wk + W::wDv;
-
-  // ---- B5: Fx.  Rows 6.. are scaled copies; rows 0..5 go through the Lie-group transport ----
-  const double* JeA = pk + P::oJE; const double* JeQ = JeA + 9;
-  {
     double* Fx = tile + D::oFx;
-    for (int e = 6 * NDX + l; e < NDX * NDX; e += W::LANES) {
-      const int i = e / NDX, j = e - i * NDX;
-      double v;
-      if (i < NV) v = (j < NV) ? aq[i * NV + j] * dt2 + ((i == j) ? 1.0 : 0.0) : av[i * NV + (j - NV)] * dt2 + ((i == j - NV) ? dt : 0.0);
-      else { const int ii = i - NV; v = (j < NV) ? aq[ii * NV + j] * dt : av[ii * NV + (j - NV)] * dt + ((ii == j - NV) ? 1.0 : 0.0); }
-      Fx[e] = v;
+    // rows 6 .. NV-1 (arm joint positions) and NV .. 2 NV-1 (velocities)
+#pragma unroll
+    for (int i = 6; i < NV; ++i) {
+      Fx[i * NDX + l] = rq[i] * dt2 + ((i == l) ? 1.0 : 0.0);
+      Fx[i * NDX + NV + l] = rv[i] * dt2 + ((i == l) ? dt : 0.0);
     }
-    // Ad(E^-1) = (X*)^T of E = exp(dx): column c (< 6), row a:  Xs[6 c + a]
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      Fx[(NV + i) * NDX + l] = rq[i] * dt;
+      Fx[(NV + i) * NDX + NV + l] = rv[i] * dt + ((i == l) ? 1.0 : 0.0);
+    }
+    // rows 0..5: Je [dt^2 a_q | dt^2 a_v + dt I] + [Ad(E^-1) | 0];  Ad(E^-1) = (X*)^T of E = exp(dx), entry (a, c) = Xs[6 c + a]
     SE3 E;
 #pragma unroll
     for (int k = 0; k < 9; ++k) E.R[k] = pk[P::oJE + 18 + k];
 #pragma unroll
     for (int k = 0; k < 3; ++k) E.p[k] = pk[P::oJE + 27 + k];
     double Xs[36]; force_action_matrix(E, Xs);
-    for (int c = l; c < NDX; c += W::LANES) {
-      double top[6];
+    double tq[6], tv[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) top[k] = ((c < NV) ? aq[k * NV + c] : av[k * NV + (c - NV)]) * dt2 + ((c == NV + k) ? dt : 0.0);
+    for (int k = 0; k < 6; ++k) { tq[k] = rq[k] * dt2; tv[k] = rv[k] * dt2 + ((k == l) ? dt : 0.0); }
 #pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        double s = 0;
+    for (int a = 0; a < 6; ++a) {
+      double sq = 0, sv = 0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          double je;  // Je = [[A,Q],[0,A]]
-          if (a < 3) je = (k < 3) ? JeA[3 * a + k] : JeQ[3 * a + (k - 3)];
-          else je = (k < 3) ? 0.0 : JeA[3 * (a - 3) + (k - 3)];
-          s += je * top[k];
-        }
-        if (c < 6) {
-          double xs_ = 0.0;
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) xs_ = (cc == c) ? Xs[6 * cc + a] : xs_;
-          s += xs_;
-        }
-        Fx[a * NDX + c] = s;
+      for (int k = 0; k < 6; ++k) {
+        double je;  // Je = [[A,Q],[0,A]]
+        if (a < 3) je = (k < 3) ? JeA[3 * a + k] : JeQ[3 * a + (k - 3)];
+        else je = (k < 3) ? 0.0 : JeA[3 * (a - 3) + (k - 3)];
+        sq += je * tq[k]; sv += je * tv[k];
       }
+      if (l < 6) {
+        double xs_ = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) xs_ = (cc == l) ? Xs[6 * cc + a] : xs_;
+        sq += xs_;
+      }
+      Fx[a * NDX + l] = sq;
+      Fx[a * NDX + NV + l] = sv;
     }
   }
 
@@ -665,10 +661,20 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
       if (i == j) return pk[P::oLXXD + i - 6];
       return 0.0;
     };
+    // Without frame costs Lxx is a 6x6 block plus a diagonal.  Its zeros are already in the tile (zero-initialised by
+    // empc_create) unless an earlier pass wrote a dense Lxx for this node (frame costs come and go when an MPC
+    // controller retargets its cost sets): bf.node_dense remembers that, and only then the full block is rewritten.
+    const bool was_dense = bf.node_dense[n] != 0;
     if (pk[P::oFLAG] == 0.0) {
-      for (int e2 = l; e2 < NDX * NDX / 2; e2 += W::LANES) {
-        const int e = 2 * e2, i = e / NDX, j = e - i * NDX;
-        reinterpret_cast<double2*>(gLxx)[e2] = make_double2(lxx_state(i, j) * dt, lxx_state(i, j + 1) * dt);
+      if (was_dense) {
+        for (int e2 = l; e2 < NDX * NDX / 2; e2 += W::LANES) {
+          const int e = 2 * e2, i = e / NDX, j = e - i * NDX;
+          reinterpret_cast<double2*>(gLxx)[e2] = make_double2(lxx_state(i, j) * dt, lxx_state(i, j + 1) * dt);
+        }
+        if (l == 0) bf.node_dense[n] = 0;
+      } else {
+        for (int e = l; e < 36; e += W::LANES) { const int i = e / 6, j = e - 6 * i; gLxx[i * NDX + j] = pk[P::oLXXB + e] * dt; }
+        for (int i = 6 + l; i < NDX; i += W::LANES) gLxx[i * NDX + i] = pk[P::oLXXD + i - 6] * dt;
       }
       for (int i = l; i < NDX; i += W::LANES) gLx[i] = pk[P::oLX + i] * dt;
     } else {
@@ -785,6 +791,7 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
       for (int e2 = l; e2 < NDX * NDX / 2; e2 += W::LANES)
         reinterpret_cast<double2*>(gLxx)[e2] = make_double2(Lxx[2 * e2] * dt, Lxx[2 * e2 + 1] * dt);
       for (int i = l; i < NDX; i += W::LANES) gLx[i] = Lxv[i] * dt;
+      if (l == 0 && !was_dense) bf.node_dense[n] = 1;
     }
   }
 }

@@ -42,6 +42,7 @@ struct Buffers {
   double* xs_try0;
   // per node
   double* packets;  // calcdiff.cuh: per-node hand-over from node_calc_kernel to node_diff_kernel (AoSoA, groups of 8)
+  unsigned char* node_dense;  // per node: the tile currently holds a dense Lxx (frame costs), see node_diff_kernel
   double* tiles; double* xnext; double* node_cost; double* fs; double* gap_inf; double* gap_l1;
   double* K; double* k; double* Vx; double* g; double* nodesc;
   // trials

@@ -215,6 +215,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   CKH(dalloc(h, &bf.us, B * T * nu));
   CKH(dalloc(h, &bf.xs_try0, B * nx));
   CKH(dalloc(h, &bf.tiles, B * T1 * tile));
+  CKH(dalloc(h, &bf.node_dense, B * T1));
   CKH(dalloc(h, &bf.packets, (B * T1 + 7) / 8 * 8 * (size_t)packet_doubles(h->na, h->nr)));
   CKH(dalloc(h, &bf.xnext, B * T1 * nx));
   CKH(dalloc(h, &bf.node_cost, B * T1));
