@@ -151,8 +151,8 @@ def run_reference(args):
     tr, fp, wl, seed0, dt = load_problem(args.workload)
     ob = oracle_binding()
     cores = os.cpu_count() or 1
-    n = args.cpu_sample or max(cores, 8 * cores)
-    n = min(n, 512)
+    n = args.cpu_sample or 32 * cores   # ~5 s of CPU work per step on this workload (bounded sample of the 4096-OCP batch)
+    n = min(n, 1024)
     x0 = wl.noisy_x0(fp.x0, n, seed0)
     for _ in range(max(args.warmup, 0)):
         ob.solve_batch(fp, x0[:cores], cores)
@@ -336,7 +336,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             ob = oracle_binding()
             cores = os.cpu_count() or 1
-            n = args.cpu_sample or min(512, 12 * cores)
+            n = args.cpu_sample or min(1024, 64 * cores)  # 10-20 s of CPU work
             sec, it, _c = ob.solve_batch(fp, x0[:n], cores)
             out["cpu_baseline"] = {"value": float(it.sum() / sec), "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"first {n} OCPs of the same batch, {cores} host threads, {sec:.1f} s; CPU restatement (oracle/), not Crocoddyl itself"}

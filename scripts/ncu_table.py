@@ -1,0 +1,35 @@
+#!/usr/bin/env python3
+"""profiles/ table + traffic JSON from an `ncu --set full` report holding one launch of each kernel family.
+usage: ncu_table.py <report.ncu-rep> <out.md> <out.json> <workload> <batch> <T>"""
+import csv, io, json, subprocess, sys
+rep, out_md, out_json, workload, batch, T = sys.argv[1:7]
+batch, T = int(batch), int(T)
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw))); hdr, units = rows[0], rows[1]
+def col(r, k, scale=1.0):
+    try: return float(r[hdr.index(k)].replace(",", "")) * scale
+    except Exception: return float("nan")
+def unit(k): return units[hdr.index(k)]
+fam = {"node_calc_kernel": "calc_diff", "node_diff_kernel": "calc_diff", "backward_kernel": "backward", "rollout_kernel": "rollout", "decide_kernel": "decide"}
+seen = {}; lines = []; traffic = {}
+for r in rows[2:]:
+    name = r[hdr.index("Kernel Name")]
+    short = name.split("<")[0].replace("void ", "").replace("empc::", "")
+    if short == "rollout_kernel" and ", 8>" in name: continue
+    if short in seen or short not in fam: continue
+    seen[short] = 1
+    def gb(k):
+        v = col(r, k); u = unit(k)
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
+    dur = col(r, "gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(unit("gpu__time_duration.sum"), 1.0)
+    rd, wr = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
+    lines.append(f"| `{short}` | {dur:.2f} | {rd/1e9:.2f} | {wr/1e9:.2f} | {(rd+wr)/dur/1e6:.0f} | {int(col(r,'launch__registers_per_thread'))} | "
+                 f"{col(r,'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {col(r,'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                 f"{col(r,'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | {col(r,'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active'):.1f} | "
+                 f"{col(r,'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {col(r,'smsp__inst_executed.sum')/1e6:.0f} |")
+    t = traffic.setdefault(fam[short], {"dram_bytes_per_launch": 0.0, "kernels": {}})
+    t["dram_bytes_per_launch"] += rd + wr
+    t["kernels"][short] = {"ms": dur, "dram_read_bytes": rd, "dram_write_bytes": wr}
+open(out_md, "w").write("| kernel | ms | DRAM read GB | DRAM write GB | DRAM GB/s | regs | warps active % | issue active % | FP64 pipe % | DMMA pipe % | DRAM % of peak | M warp-instr |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n" + "\n".join(lines) + "\n")
+json.dump({"workload": workload, "batch": batch, "T": T, "source": rep.split("/")[-1], "kernels": traffic}, open(out_json, "w"), indent=1)
+print(open(out_md).read())
