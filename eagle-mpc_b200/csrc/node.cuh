@@ -1,4 +1,5 @@
-// node.cuh — per-node action model on the device (one thread evaluates one shooting node), FP64, sm_100a.
+// node.cuh — per-node action model on the device: the pieces one thread evaluates for one shooting node (squashing,
+// ABA, Euler step, residuals and activations), FP64, sm_100a.  The derivative side lives in calcdiff.cuh.
 //
 // Replaces, for the model chain eagle-mpc instantiates (src/factory/diff-action.cpp:31-35, src/factory/int-action.cpp:26,
 // src/trajectory.cpp:47-52), the per-node work crocoddyl does inside ShootingProblem::calc / calcDiff:
@@ -545,401 +546,6 @@ EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costs
     csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
   }
   return M.dt * csum;
-}
-
-// world-frame RNEA-derivative recursion + Minv (DESIGN.md "ABA derivatives"); outputs a_q, a_v (NV x NV), Minv, Jc, ov.
-// Tip-to-base sweep with running composite quantities of the subtree: rigid-body inertia Ycrb (m, m c, I_o: 13
-// numbers), subtree force Fcrb, and the composite "B" operator, which reduces to a momentum vector hf and one 3x3
-// block G because  B_i = crf(v_i) Y_i - Y_i crm(v_i) + Hx(h_i) = [[0, -2[hf_i]x],[0, G_i]].
-template <class D>
-EMPC_DI void aba_derivatives(const DevModel& M, const NodeData<D>& nd, double (*Jc)[6], double (*ov)[6], double* a_q,
-                             double* a_v, double* Minv) {
-  constexpr int NJ = D::NJ, NV = D::NV, NA = D::NA;
-  double oa[NJ][6];
-#pragma unroll 1
-  for (int i = 0; i < NJ; ++i) {
-    if (i == 0) {
-      // motion action matrix columns of oM0: X = [[R, px R],[0,R]]
-      double S[9], SR[9]; skew3(nd.oM[0].p, S); matmul3(S, nd.oM[0].R, SR);
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          Jc[b][a] = nd.oM[0].R[3 * a + b]; Jc[b][3 + a] = 0;
-          Jc[3 + b][a] = SR[3 * a + b]; Jc[3 + b][3 + a] = nd.oM[0].R[3 * a + b];
-        }
-      }
-    } else {
-      const double S[6] = {0, 0, 0, M.axis[i][0], M.axis[i][1], M.axis[i][2]};
-      act_motion(nd.oM[i], S, Jc[5 + i]);
-    }
-    act_motion(nd.oM[i], nd.v[i], ov[i]);
-    act_motion(nd.oM[i], nd.agf[i], oa[i]);
-  }
-  double cm = 0, cmc[3] = {0, 0, 0}, cIo[9], chf[3] = {0, 0, 0}, cG[9], cF[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-  for (int i = 0; i < 9; ++i) { cIo[i] = 0; cG[i] = 0; }
-  double YJa[NA > 0 ? NA : 1][6], BtJa[NA > 0 ? NA : 1][3];
-  double Mm[NV * NV];
-  double* dq = a_q; double* dv = a_v;
-  // Ycrb u  and  Bcrb u  with the running composites
-  auto Yc = [&](const double* u, double* o) {
-    double t1[3], t2[3], t3[3];
-    cross3(cmc, u + 3, t1); cross3(cmc, u, t2); matvec3(cIo, u + 3, t3);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { o[i] = cm * u[i] - t1[i]; o[3 + i] = t2[i] + t3[i]; }
-  };
-  auto Bc = [&](const double* u, double* o) {
-    double t1[3], t2[3];
-    cross3(chf, u + 3, t1); matvec3(cG, u + 3, t2);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { o[i] = -2.0 * t1[i]; o[3 + i] = t2[i]; }
-  };
-#pragma unroll 1
-  for (int k = NJ - 1; k >= 0; --k) {
-    {  // add body k to the composites
-      const SE3& oMk = nd.oM[k];
-      double cw[3]; matvec3(oMk.R, M.com[k], cw);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) cw[i] += oMk.p[i];
-      double RI[9], Iw[9];
-      matmul3(oMk.R, M.Ic[k], RI);
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Iw[3 * i + j] = RI[3 * i] * oMk.R[3 * j] + RI[3 * i + 1] * oMk.R[3 * j + 1] + RI[3 * i + 2] * oMk.R[3 * j + 2];
-      const double m = M.mass[k];
-      double h[6], Ya[6], vh[6];
-      inertia_apply(m, cw, Iw, ov[k], h); inertia_apply(m, cw, Iw, oa[k], Ya); cross_mf(ov[k], h, vh);
-      const double c2 = dot3(cw, cw);
-      double Io[9], mc[3] = {m * cw[0], m * cw[1], m * cw[2]};
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Io[3 * i + j] = Iw[3 * i + j] + m * (((i == j) ? c2 : 0.0) - cw[i] * cw[j]);
-      const double* vl = ov[k]; const double* w = ov[k] + 3;
-      double Sw[9], A1[9], Shn[9]; skew3(w, Sw); matmul3(Sw, Io, A1); skew3(h + 3, Shn);
-      const double vm = dot3(vl, mc);
-      cm += m;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { cmc[i] += mc[i]; chf[i] += h[i]; }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) cF[i] += Ya[i] + vh[i];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          cIo[3 * i + j] += Io[3 * i + j];
-          cG[3 * i + j] += A1[3 * i + j] + A1[3 * j + i] - (mc[i] * vl[j] + vl[i] * mc[j]) + ((i == j) ? 2.0 * vm : 0.0) - Shn[3 * i + j];
-        }
-    }
-    const int c_begin = (k == 0) ? 0 : 5 + k, c_end = (k == 0) ? 6 : 6 + k;
-#pragma unroll 1
-    for (int ck = c_begin; ck < c_end; ++ck) {
-      const double* s = Jc[ck];
-      double vp[6], ap[6];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) { vp[a] = (k > 0) ? ov[k > 0 ? k - 1 : 0][a] : 0.0; ap[a] = (k > 0) ? oa[k > 0 ? k - 1 : 0][a] : M.a0[a]; }
-      double dVdq[6], dAdq[6], dAdv[6], t6[6], vsum[6];
-      cross_mm(vp, s, dVdq);
-      cross_mm(ap, s, dAdq); cross_mm(vp, dVdq, t6);
-#pragma unroll
-      for (int a = 0; a < 6; ++a) { dAdq[a] += t6[a]; vsum[a] = vp[a] + ov[k][a]; }
-      cross_mm(vsum, s, dAdv);
-      double P[6], Fq[6], Fv[6], YJ[6], t1[6], t2[6];
-      Yc(dAdq, t1); Bc(dVdq, t2);
-#pragma unroll
-      for (int a = 0; a < 6; ++a) P[a] = t1[a] + t2[a];
-      cross_mf(s, cF, t1);
-#pragma unroll
-      for (int a = 0; a < 6; ++a) Fq[a] = P[a] + t1[a];
-      Yc(dAdv, t1); Bc(s, t2);
-#pragma unroll
-      for (int a = 0; a < 6; ++a) Fv[a] = t1[a] + t2[a];
-      Yc(s, YJ);
-      if (k > 0) {
-        double c1[3], c2v[3];
-        cross3(chf, s, c1);  // 2 hf x s_v + G^T s_w
-#pragma unroll
-        for (int i = 0; i < 3; ++i) c2v[i] = cG[i] * s[3] + cG[3 + i] * s[4] + cG[6 + i] * s[5];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) YJa[k - 1][i] = YJ[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) BtJa[k - 1][i] = 2.0 * c1[i] + c2v[i];
-      }
-#pragma unroll 1
-      for (int cj = 0; cj < NV; ++cj) {
-        double vq_, vv_;
-        if (cj < c_begin) { vq_ = dot6(Jc[cj], Fq); vv_ = dot6(Jc[cj], Fv); }
-        else if (cj < c_end) { vq_ = dot6(Jc[cj], P); vv_ = dot6(Jc[cj], Fv); }
-        else {
-          const double* yj = YJa[cj - 6]; const double* bj = BtJa[cj - 6];
-          vq_ = dot6(yj, dAdq) + (bj[0] * dVdq[3] + bj[1] * dVdq[4] + bj[2] * dVdq[5]);
-          vv_ = dot6(yj, dAdv) + (bj[0] * s[3] + bj[1] * s[4] + bj[2] * s[5]);
-        }
-        dq[cj * NV + ck] = vq_; dv[cj * NV + ck] = vv_;
-        if (cj <= ck) { const double mv = dot6(Jc[cj], YJ); Mm[cj * NV + ck] = mv; Mm[ck * NV + cj] = mv; }
-      }
-    }
-  }
-  double Minvd[NV];
-  llt_inplace_inv<NV>(Mm, Minvd);
-#pragma unroll 1
-  for (int i = 0; i < NV; ++i)
-#pragma unroll 1
-    for (int j = 0; j < NV; ++j) Minv[i * NV + j] = (i == j) ? 1.0 : 0.0;
-#pragma unroll 1
-  for (int c = 0; c < NV; ++c) llt_solve_vec_inv<NV>(Mm, Minvd, Minv + c, NV);
-  // a_q = -Minv dq, a_v = -Minv dv, column by column in place
-#pragma unroll 1
-  for (int j = 0; j < NV; ++j) {
-    double cq[NV], cv[NV];
-#pragma unroll 1
-    for (int i = 0; i < NV; ++i) {
-      double sq = 0, sv = 0;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) { sq += Minv[i * NV + k] * dq[k * NV + j]; sv += Minv[i * NV + k] * dv[k * NV + j]; }
-      cq[i] = -sq; cv[i] = -sv;
-    }
-#pragma unroll 1
-    for (int i = 0; i < NV; ++i) { a_q[i * NV + j] = cq[i]; a_v[i * NV + j] = cv[i]; }
-  }
-}
-
-// IntegratedActionModelEuler::calcDiff: writes the node tile Fx|Fu|Lxx|Lxu|Luu|Lx|Lu to `tile` (global memory).
-// Must follow node_calc on the same (x,u,nd).
-template <class D>
-EMPC_DI void node_calc_diff(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x,
-                            const double* u, const NodeData<D>& nd, double* __restrict__ tile) {
-  constexpr int NV = D::NV, NDX = D::NDX, NU = D::NU, NR = D::NR, NJ = D::NJ;
-  const double dt = M.dt, dt2 = dt * dt;
-  double ds[NU];
-#pragma unroll
-  for (int i = 0; i < NU; ++i) {
-    if (M.use_squash) {
-      const double lbv = M.u_lb[i], ubv = M.u_ub[i];
-      const double dd = (ubv - lbv) * smooth, a = dd * dd;
-      const double l = u[i] - lbv, h = u[i] - ubv;
-      ds[i] = 0.5 * (rsqrt_nr(a + l * l) * l - rsqrt_nr(a + h * h) * h);
-    } else {
-      ds[i] = 1.0;
-    }
-  }
-  double Jc[NV][6], ov[NJ][6];
-  double a_q[NV * NV], a_v[NV * NV], Minv[NV * NV];
-  aba_derivatives<D>(M, nd, Jc, ov, a_q, a_v, Minv);
-
-  double* Fx = tile + D::oFx; double* Fu = tile + D::oFu;
-  // Lie-group transport pieces
-  double JeA[9], JeQ[9]; Jexp6_blocks(nd.dx, JeA, JeQ);
-  SE3 E; exp6(nd.dx, E);
-  double Xs[36]; force_action_matrix(E, Xs);  // Ad(E^-1) = (X*)^T
-  // rows 0..5 of Fx/Fu need the transport; build them in registers
-  {
-    double top[6][NDX];
-#pragma unroll 1
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll 1
-      for (int j = 0; j < NV; ++j) { top[i][j] = a_q[i * NV + j] * dt2; top[i][NV + j] = a_v[i * NV + j] * dt2; }
-      top[i][NV + i] += dt;
-    }
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll 1
-      for (int c = 0; c < NDX; ++c) {
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          // Je = [[A,Q],[0,A]]
-          double je;
-          if (a < 3) je = (k < 3) ? JeA[3 * a + k] : JeQ[3 * a + (k - 3)];
-          else je = (k < 3) ? 0.0 : JeA[3 * (a - 3) + (k - 3)];
-          s += je * top[k][c];
-        }
-        if (c < 6) s += Xs[6 * c + a];
-        Fx[a * NDX + c] = s;
-      }
-  }
-#pragma unroll 1
-  for (int i = 6; i < NV; ++i) {
-#pragma unroll 1
-    for (int j = 0; j < NV; ++j) {
-      Fx[i * NDX + j] = a_q[i * NV + j] * dt2 + ((i == j) ? 1.0 : 0.0);
-      Fx[i * NDX + NV + j] = a_v[i * NV + j] * dt2 + ((i == j) ? dt : 0.0);
-    }
-  }
-#pragma unroll 1
-  for (int i = 0; i < NV; ++i) {
-#pragma unroll 1
-    for (int j = 0; j < NV; ++j) {
-      Fx[(NV + i) * NDX + j] = a_q[i * NV + j] * dt;
-      Fx[(NV + i) * NDX + NV + j] = a_v[i * NV + j] * dt + ((i == j) ? 1.0 : 0.0);
-    }
-  }
-  // Fu = [dt^2; dt] * Minv * A diag(ds), rows 0..5 transported
-  {
-    double top[6][NU];
-#pragma unroll 1
-    for (int i = 0; i < NV; ++i) {
-#pragma unroll 1
-      for (int j = 0; j < NU; ++j) {
-        double s;
-        if (j < NR) {
-          s = 0;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) s += Minv[i * NV + k] * (M.tau_f[k * NR + j] * ds[j]);
-        } else {
-          s = Minv[i * NV + 6 + (j - NR)] * ds[j];
-        }
-        if (i < 6) top[i][j] = dt2 * s; else Fu[i * NU + j] = dt2 * s;
-        Fu[(NV + i) * NU + j] = dt * s;
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll 1
-      for (int c = 0; c < NU; ++c) {
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          double je;
-          if (a < 3) je = (k < 3) ? JeA[3 * a + k] : JeQ[3 * a + (k - 3)];
-          else je = (k < 3) ? 0.0 : JeA[3 * (a - 3) + (k - 3)];
-          s += je * top[k][c];
-        }
-        Fu[a * NU + c] = s;
-      }
-  }
-  // ---- cost derivatives ----
-  double Lxx[NDX * NDX], Lx[NDX], Lu[NU], Luud[NU];
-#pragma unroll 1
-  for (int i = 0; i < NDX * NDX; ++i) Lxx[i] = 0;
-#pragma unroll
-  for (int i = 0; i < NDX; ++i) Lx[i] = 0;
-#pragma unroll
-  for (int i = 0; i < NU; ++i) { Lu[i] = 0; Luud[i] = 0; }
-  const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
-  for (int c = c0; c < c1; ++c) {
-    const empc_cost_t cs = C.costs[c];
-    if (!cs.active) continue;
-    double r[NDX], Ar[NDX], Arr[NDX];
-    SE3 rMf;
-    cost_eval<D>(M, C, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
-    const double wt = cs.weight;
-    if (cs.type == EMPC_COST_STATE) {
-      SE3 Mref, Mx, Dm;
-      double xr[7];
-#pragma unroll
-      for (int i = 0; i < 7; ++i) xr[i] = C.pool[cs.ref_off + i];
-      q_to_se3(xr, Mref); q_to_se3(x, Mx); se3_inv_mul(Mref, Mx, Dm);
-      double Jl[36]; Jlog6(Dm, Jl);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s += Jl[6 * k + i] * Ar[k];
-        Lx[i] += wt * s;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          double h = 0;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) h += Jl[6 * k + i] * (Arr[k] * Jl[6 * k + j]);
-          Lxx[i * NDX + j] += wt * h;
-        }
-      }
-#pragma unroll 1
-      for (int i = 6; i < NDX; ++i) { Lx[i] += wt * Ar[i]; Lxx[i * NDX + i] += wt * Arr[i]; }
-    } else if (cs.type == EMPC_COST_CONTROL || cs.type == EMPC_COST_SQUASH_BARRIER) {
-#pragma unroll
-      for (int i = 0; i < NU; ++i) { Lu[i] += wt * Ar[i]; Luud[i] += wt * Arr[i]; }
-    } else {
-      const int f = cs.frame, jf = M.frame_joint[f];
-      SE3 oMf; frame_placement<D>(M, nd, f, oMf);
-      double fJ[6][NV];
-#pragma unroll 1
-      for (int cc = 0; cc < NV; ++cc) {
-        const int jc = (cc < 6) ? 0 : cc - 5;
-        double o[6];
-        actinv_motion(oMf, Jc[cc], o);
-#pragma unroll
-        for (int a = 0; a < 6; ++a) fJ[a][cc] = (jc <= jf) ? o[a] : 0.0;
-      }
-      double Rx[6][NDX];
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll 1
-        for (int b = 0; b < NDX; ++b) Rx[a][b] = 0;
-      int n = 3;
-      bool full = false;
-      if (cs.type == EMPC_COST_FRAME_PLACEMENT) {
-        n = 6;
-        double Jl[36]; Jlog6(rMf, Jl);
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll 1
-          for (int b = 0; b < NV; ++b) {
-            double s = 0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) s += Jl[6 * a + k] * fJ[k][b];
-            Rx[a][b] = s;
-          }
-      } else if (cs.type == EMPC_COST_FRAME_ROTATION) {
-        double wv[3], th, Jl[9]; log3(rMf.R, wv, th); Jlog3(th, wv, Jl);
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll 1
-          for (int b = 0; b < NV; ++b) Rx[a][b] = Jl[3 * a] * fJ[3][b] + Jl[3 * a + 1] * fJ[4][b] + Jl[3 * a + 2] * fJ[5][b];
-      } else if (cs.type == EMPC_COST_FRAME_TRANSLATION) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll 1
-          for (int b = 0; b < NV; ++b)
-            Rx[a][b] = oMf.R[3 * a] * fJ[0][b] + oMf.R[3 * a + 1] * fJ[1][b] + oMf.R[3 * a + 2] * fJ[2][b];
-      } else {  // FRAME_VELOCITY
-        n = 6; full = true;
-#pragma unroll 1
-        for (int b = 6; b < NV; ++b) {  // base columns have no parent body: zero
-          const int k = b - 5;
-          if (k <= jf) {
-            double cr[6], o[6];
-            cross_mm(ov[k - 1], Jc[b], cr); actinv_motion(oMf, cr, o);
-#pragma unroll
-            for (int a = 0; a < 6; ++a) Rx[a][b] = o[a];
-          }
-        }
-#pragma unroll 1
-        for (int b = 0; b < NV; ++b)
-#pragma unroll
-          for (int a = 0; a < 6; ++a) Rx[a][NV + b] = fJ[a][b];
-      }
-      const int ncols = full ? NDX : NV;
-      for (int i = 0; i < ncols; ++i) {
-        double s = 0;
-        for (int k = 0; k < n; ++k) s += Rx[k][i] * Ar[k];
-        Lx[i] += wt * s;
-        for (int j = 0; j < ncols; ++j) {
-          double h = 0;
-          for (int k = 0; k < n; ++k) h += Rx[k][i] * (Arr[k] * Rx[k][j]);
-          Lxx[i * NDX + j] += wt * h;
-        }
-      }
-    }
-  }
-  double* gLxx = tile + D::oLxx; double* gLxu = tile + D::oLxu; double* gLuu = tile + D::oLuu;
-  double* gLx = tile + D::oLx; double* gLu = tile + D::oLu;
-#pragma unroll 1
-  for (int i = 0; i < NDX * NDX; ++i) gLxx[i] = Lxx[i] * dt;
-#pragma unroll 1
-  for (int i = 0; i < NDX * NU; ++i) gLxu[i] = 0.0;
-#pragma unroll 1
-  for (int i = 0; i < NU; ++i)
-#pragma unroll 1
-    for (int j = 0; j < NU; ++j) gLuu[i * NU + j] = (i == j) ? Luud[i] * dt : 0.0;
-#pragma unroll
-  for (int i = 0; i < NDX; ++i) gLx[i] = Lx[i] * dt;
-#pragma unroll
-  for (int i = 0; i < NU; ++i) gLu[i] = Lu[i] * dt;
-  if (D::TILE != D::TILE0) tile[D::TILE0] = 0.0;
 }
 
 }  // namespace empc
