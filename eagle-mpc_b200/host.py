@@ -22,6 +22,8 @@ def hlib():
         L.empc_host_trajectory_create.argtypes = [C.c_char_p]
         L.empc_host_trajectory_free.argtypes = [C.c_void_p]
         L.empc_host_trajectory_info.argtypes = [C.c_void_p, abi.c_int32_p]
+        L.empc_host_trajectory_stage_names.restype = C.c_void_p
+        L.empc_host_trajectory_stage_names.argtypes = [C.c_void_p]
         L.empc_host_trajectory_platform.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, abi.c_double_p]
         L.empc_host_flatten.restype = C.c_void_p
         L.empc_host_flatten.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
@@ -100,6 +102,10 @@ class Trajectory:
         self.tau_f = np.zeros((6, self.n_rotors)); self.u_lb = np.zeros(self.nu); self.u_ub = np.zeros(self.nu)
         hlib().empc_host_trajectory_platform(self._p, abi.as_double_p(self.tau_f), abi.as_double_p(self.u_lb),
                                              abi.as_double_p(self.u_ub))
+
+    def stage_names(self):
+        """current stages (WeightedMpc merges the transition stages of the trajectory it is given, in place)"""
+        return _take_str(hlib().empc_host_trajectory_stage_names(self._p)).split()
 
     def createProblem(self, dt, squash=True, integrator="IntegratedActionModelEuler", add_barrier=True):
         p = hlib().empc_host_flatten(self._p, int(dt), int(squash), integrator.encode(), int(add_barrier))

@@ -53,6 +53,14 @@ int empc_host_trajectory_info(void* t, int32_t* out /* nq nv nu n_stages duratio
   out[3] = (int)tr->get_stages().size(); out[4] = (int)tr->get_duration(); out[5] = (int)tr->get_platform_params()->n_rotors_;
   return 0;
 }
+// stage names, one per line, in trajectory order (caller frees with empc_host_free_str)
+char* empc_host_trajectory_stage_names(void* t) {
+  std::string out;
+  for (const auto& st : ((HostTrajectory*)t)->traj->get_stages()) out += st->get_name() + "\n";
+  char* c = new char[out.size() + 1];
+  std::copy(out.begin(), out.end(), c); c[out.size()] = 0;
+  return c;
+}
 int empc_host_trajectory_platform(void* t, double* tau_f /* 6*n_rotors */, double* u_lb, double* u_ub) {
   auto& pf = ((HostTrajectory*)t)->traj->get_platform_params();
   std::copy(pf->tau_f_.begin(), pf->tau_f_.end(), tau_f);
@@ -122,18 +130,42 @@ int empc_host_solver_result(void* s, double* xs, double* us, double* us_squash, 
   return 0;
 }
 
-// ---- CarrotMpc (src/mpc-controllers/carrot-mpc.cpp) ----
-struct HostCarrot { std::shared_ptr<Trajectory> traj; std::unique_ptr<CarrotMpc> mpc; };
+// ---- MPC controllers (src/mpc-controllers/{carrot,rail,weighted}-mpc.cpp).  The entry points after the three
+// constructors work on any controller; they keep their historical "carrot" names. ----
+struct HostCarrot { std::shared_ptr<Trajectory> traj; std::unique_ptr<MpcAbstract> mpc; };
+
+static std::vector<VectorXd> unpack_states(const double* state_ref, int32_t n_ref, std::size_t nx) {
+  std::vector<VectorXd> ref((std::size_t)n_ref);
+  for (int i = 0; i < n_ref; ++i) ref[(std::size_t)i].assign(state_ref + (std::size_t)i * nx, state_ref + (std::size_t)(i + 1) * nx);
+  return ref;
+}
+
+// RailMpc(state_ref, dt_ref, yaml_path): no trajectory object; nx is the row length of state_ref
+void* empc_host_rail_create(const double* state_ref, int32_t n_ref, int32_t nx, int32_t dt_ref, const char* yaml_path, int32_t create_solver) {
+  GUARD_BEGIN
+  auto* hc = new HostCarrot();
+  hc->mpc.reset(new RailMpc(unpack_states(state_ref, n_ref, (std::size_t)nx), (std::size_t)dt_ref, getYamlPath(yaml_path), create_solver != 0));
+  return hc;
+  GUARD_END(nullptr)
+}
+// WeightedMpc(trajectory, dt_ref, yaml_path): merges the transition stages of `trajectory` in place, like the reference
+void* empc_host_weighted_create(void* t, int32_t dt_ref, const char* yaml_path, int32_t create_solver) {
+  GUARD_BEGIN
+  auto& tr = ((HostTrajectory*)t)->traj;
+  auto* hc = new HostCarrot();
+  hc->traj = tr;
+  hc->mpc.reset(new WeightedMpc(tr, (std::size_t)dt_ref, getYamlPath(yaml_path), create_solver != 0));
+  return hc;
+  GUARD_END(nullptr)
+}
 
 void* empc_host_carrot_create(void* t, const double* state_ref, int32_t n_ref, int32_t dt_ref, const char* yaml_path, int32_t create_solver) {
   GUARD_BEGIN
   auto& tr = ((HostTrajectory*)t)->traj;
   const std::size_t nx = (std::size_t)tr->get_robot_state()->get_nx();
-  std::vector<VectorXd> ref((std::size_t)n_ref);
-  for (int i = 0; i < n_ref; ++i) ref[(std::size_t)i].assign(state_ref + (std::size_t)i * nx, state_ref + (std::size_t)(i + 1) * nx);
   auto* hc = new HostCarrot();
   hc->traj = tr;
-  hc->mpc.reset(new CarrotMpc(tr, ref, (std::size_t)dt_ref, getYamlPath(yaml_path), create_solver != 0));
+  hc->mpc.reset(new CarrotMpc(tr, unpack_states(state_ref, n_ref, nx), (std::size_t)dt_ref, getYamlPath(yaml_path), create_solver != 0));
   return hc;
   GUARD_END(nullptr)
 }
@@ -164,7 +196,7 @@ int empc_host_carrot_solve(void* m, const double* x0, const double* xs, const do
   GUARD_BEGIN
   auto& c = ((HostCarrot*)m)->mpc;
   auto& sv = c->get_solver();
-  if (!sv) throw std::runtime_error("CarrotMpc was created without a solver");
+  if (!sv) throw std::runtime_error("the MPC controller was created without a solver");
   const std::size_t nx = (std::size_t)c->get_robot_state()->get_nx(), T = c->get_problem()->get_T(), nu = c->get_squash()->get_ns();
   c->get_problem()->set_x0(VectorXd(x0, x0 + nx));
   sv->set_convergence_init(convergence_init);

@@ -1,7 +1,9 @@
-// mpc.cpp — MpcAbstract + CarrotMpc (src/mpc-base.cpp, src/mpc-controllers/carrot-mpc.cpp), bug-compatible where the
-// reference's behaviour is observable: integer-division interpolation (piecewise-constant
-// reference), t_stages clamped to >= dt, carrot_tail never deactivated, dimension checks that never throw.
+// mpc.cpp — MpcAbstract + CarrotMpc / RailMpc / WeightedMpc (src/mpc-base.cpp, src/mpc-controllers/*.cpp),
+// bug-compatible where the reference's behaviour is observable: integer-division interpolation
+// (piecewise-constant reference), t_stages clamped to >= dt, carrot_tail never deactivated, dimension checks that
+// never throw, prefix matching of stage names, the hover quaternion of RailMpc that keeps the x / y components.
 #include <algorithm>
+#include <cmath>
 
 #include "mpc.hpp"
 
@@ -42,6 +44,55 @@ void MpcAbstract::loadParams() {
   else throw std::out_of_range("map::at");
   try { params_.callback = params_server_->getParam<bool>(p + "callback"); }
   catch (const std::exception&) { params_.callback = false; }
+}
+
+void MpcAbstract::checkHotPathSupport() const {
+  if (params_.solver_type != SolverTypes::SolverSbFDDP)
+    throw std::runtime_error("only SolverSbFDDP is part of the B200 hot path (SolverBoxFDDP/BoxDDP: SURVEY.md §8f rank 4)");
+  if (params_.integrator_type != "IntegratedActionModelEuler")
+    throw std::runtime_error("IntegratedActionModelRK4 is not part of the B200 hot path yet");
+}
+
+std::shared_ptr<ActionModel> MpcAbstract::makeKnotModel(const std::shared_ptr<CostModelSum>& costs) const {
+  auto iam = std::make_shared<ActionModel>();
+  iam->costs = costs;
+  iam->dt = double(params_.dt) / 1000.;
+  iam->squash = true;
+  iam->u_lb = platform_params_->u_lb; iam->u_ub = platform_params_->u_ub;
+  return iam;
+}
+
+void MpcAbstract::finishProblem() {
+  problem_ = std::make_shared<ShootingProblem>();
+  problem_->x0 = robot_state_->zero();
+  problem_->runningModels.assign(int_models_.begin(), int_models_.end() - 1);
+  problem_->terminalModel = int_models_.back();
+  problem_->state = robot_state_;
+  problem_->platform = platform_params_;
+  if (!defer_solver_) attachSolver();
+  else {
+    sbfddp_barrier_init(*problem_, squash_->get_ns(), 1e-3);
+    flatten_problem(*problem_, flat_local_);
+  }
+}
+
+void MpcAbstract::attachSolver() {
+  if (!solver_) solver_ = std::make_shared<SolverSbFDDP>(problem_, squash_, 1, 0);
+}
+
+FlatProblem& MpcAbstract::flat() { return solver_ ? solver_->flat() : flat_local_; }
+
+// copy one cost item of knot `knot` into the flat tables and remember the dirty range
+void MpcAbstract::syncCost(std::size_t knot, const std::string& name) {
+  FlatProblem& fl = flat();
+  const int set = fl.node_costset[knot];
+  const FlatProblem::Slot& sl = fl.slots[set].at(name);
+  fill_cost_record(*int_models_[knot]->costs->get_costs().at(name), fl.costs[sl.cost_index], fl.pool.data());
+  dirty_lo_ = std::min(dirty_lo_, sl.cost_index); dirty_hi_ = std::max(dirty_hi_, sl.cost_index);
+}
+
+void MpcAbstract::endUpdate() {
+  if (solver_ && dirty_hi_ >= dirty_lo_) solver_->pushCosts(dirty_lo_, dirty_hi_ - dirty_lo_ + 1);
 }
 
 // ---- CarrotMpc --------------------------------------------------------------------------------------------------------
@@ -124,36 +175,10 @@ std::shared_ptr<CostModelSum> CarrotMpc::createCosts() const {
 
 void CarrotMpc::createProblem() {
   if (trajectory_->get_has_contact()) throw std::runtime_error("Carrot with contact has not been implemented");
-  if (params_.solver_type != SolverTypes::SolverSbFDDP)
-    throw std::runtime_error("only SolverSbFDDP is part of the B200 hot path (SolverBoxFDDP/BoxDDP: SURVEY.md §8f rank 4)");
-  if (params_.integrator_type != "IntegratedActionModelEuler")
-    throw std::runtime_error("IntegratedActionModelRK4 is not part of the B200 hot path yet");
-  for (std::size_t i = 0; i < params_.knots; ++i) {
-    auto iam = std::make_shared<ActionModel>();
-    iam->costs = createCosts();  // one model per knot (:195-225)
-    iam->dt = double(params_.dt) / 1000.;
-    iam->squash = true;
-    iam->u_lb = platform_params_->u_lb; iam->u_ub = platform_params_->u_ub;
-    int_models_.push_back(iam);
-  }
-  problem_ = std::make_shared<ShootingProblem>();
-  problem_->x0 = robot_state_->zero();
-  problem_->runningModels.assign(int_models_.begin(), int_models_.end() - 1);
-  problem_->terminalModel = int_models_.back();
-  problem_->state = robot_state_;
-  problem_->platform = platform_params_;
-  if (!defer_solver_) attachSolver();
-  else {
-    sbfddp_barrier_init(*problem_, squash_->get_ns(), 1e-3);
-    flatten_problem(*problem_, flat_local_);
-  }
+  checkHotPathSupport();
+  for (std::size_t i = 0; i < params_.knots; ++i) int_models_.push_back(makeKnotModel(createCosts()));  // one model per knot (:195-225)
+  finishProblem();
 }
-
-void CarrotMpc::attachSolver() {
-  if (!solver_) solver_ = std::make_shared<SolverSbFDDP>(problem_, squash_, 1, 0);
-}
-
-FlatProblem& CarrotMpc::flat() { return solver_ ? solver_->flat() : flat_local_; }
 
 void CarrotMpc::computeActiveStage(std::size_t t) {
   update_vars_.idx_stage = std::size_t(std::upper_bound(t_stages_.begin(), t_stages_.end(), t) - t_stages_.begin()) - 1;
@@ -169,15 +194,6 @@ void CarrotMpc::computeStateReference(std::size_t time) {
     // alpha = (time - t_ref[i-1]) / (t_ref[i] - t_ref[i-1]) in integer arithmetic == 0  (:391-392): piecewise constant
     update_vars_.state_ref = state_ref_[update_vars_.idx_state - 1];
   }
-}
-
-// copy one cost item of knot `knot` into the flat tables and remember the dirty range
-void CarrotMpc::syncCost(std::size_t knot, const std::string& name) {
-  FlatProblem& fl = flat();
-  const int set = fl.node_costset[knot];
-  const FlatProblem::Slot& sl = fl.slots[set].at(name);
-  fill_cost_record(*int_models_[knot]->costs->get_costs().at(name), fl.costs[sl.cost_index], fl.pool.data());
-  dirty_lo_ = std::min(dirty_lo_, sl.cost_index); dirty_hi_ = std::max(dirty_hi_, sl.cost_index);
 }
 
 void CarrotMpc::updateFreeCosts(std::size_t idx) {
@@ -205,14 +221,198 @@ void CarrotMpc::updateFreeCosts(std::size_t idx) {
 void CarrotMpc::updateProblem(const std::size_t& current_time) {
   computeActiveStage(current_time);
   update_vars_.idx_last_stage = update_vars_.idx_stage;
-  dirty_lo_ = 1 << 30; dirty_hi_ = -1;
+  beginUpdate();
   for (std::size_t i = 0; i < int_models_.size(); ++i) {
     update_vars_.node_time = current_time + i * params_.dt;
     computeActiveStage(update_vars_.node_time);
     updateFreeCosts(i);
     update_vars_.idx_last_stage = update_vars_.idx_stage;
   }
-  if (solver_ && dirty_hi_ >= dirty_lo_) solver_->pushCosts(dirty_lo_, dirty_hi_ - dirty_lo_ + 1);
+  endUpdate();
+}
+
+// ---- RailMpc (src/mpc-controllers/rail-mpc.cpp) -------------------------------------------------------------------------
+RailMpc::RailMpc(const std::vector<VectorXd>& state_ref, std::size_t dt_ref, const std::string& yaml_path, bool create_solver)
+    : MpcAbstract(yaml_path) {
+  defer_solver_ = !create_solver;
+  state_ref_ = state_ref;
+  for (std::size_t i = 0; i < state_ref_.size(); ++i) t_ref_.push_back(dt_ref * i);
+  const std::size_t ndx = (std::size_t)robot_state_->get_ndx();
+  try { state_weight_ = params_server_->getParam<double>("mpc_controller/rail_weight"); }
+  catch (const std::exception&) { state_weight_ = 10; }
+  try { state_activation_weights_ = converter<VectorXd>::convert(params_server_->getParam<std::string>("mpc_controller/rail_activation_weights")); }
+  catch (const std::exception&) { state_activation_weights_ = VectorXd(ndx, 1.0); }
+  // (:41-45 constructs a std::runtime_error without throwing it; a wrong size would be read out of bounds there)
+  if (state_activation_weights_.size() != ndx)
+    throw std::runtime_error("RailMPC: the dimension for the state activation weights vector is " +
+                             std::to_string(state_activation_weights_.size()) + ", should be " + std::to_string(ndx));
+  try { control_weight_ = params_server_->getParam<double>("mpc_controller/rail_control_weight"); }
+  catch (const std::exception&) { control_weight_ = 1e-1; }
+  createProblem();
+  update_vars_.state_ref = robot_state_->zero();
+}
+
+std::shared_ptr<CostModelSum> RailMpc::createCosts() const {
+  auto costs = std::make_shared<CostModelSum>();
+  auto rail = std::make_shared<CostModelResidual>();
+  rail->type = CostModelTypes::CostModelState;
+  rail->activation.type = ActivationModelTypes::ActivationModelWeightedQuad;
+  rail->activation.nr = (std::size_t)robot_state_->get_ndx();
+  rail->activation.weights = state_activation_weights_;
+  rail->reference = robot_state_->zero();
+  costs->addCost("rail_state", rail, state_weight_, true);
+  auto control = std::make_shared<CostModelResidual>();  // CostModelResidual(state, ResidualModelControl): ActivationModelQuad
+  control->type = CostModelTypes::CostModelControl;
+  control->activation.type = ActivationModelTypes::ActivationModelQuad; control->activation.nr = nu_;
+  control->reference.assign(nu_, 0.0);
+  costs->addCost("control", control, control_weight_, true);
+  return costs;
+}
+
+void RailMpc::createProblem() {
+  checkHotPathSupport();
+  for (std::size_t i = 0; i < params_.knots; ++i) int_models_.push_back(makeKnotModel(createCosts()));
+  finishProblem();
+}
+
+void RailMpc::computeStateReference(std::size_t time) {
+  update_vars_.idx_state = std::size_t(std::upper_bound(t_ref_.begin(), t_ref_.end(), time) - t_ref_.begin());
+  const std::size_t nq = (std::size_t)robot_state_->get_nq();
+  if (update_vars_.idx_state >= state_ref_.size()) {
+    // hover at the last configuration with a yaw-only attitude (:180-186); the quaternion is rebuilt from (w, z) only,
+    // but the x / y components copied with head(nq) stay in the reference
+    const VectorXd& last = state_ref_.back();
+    update_vars_.state_ref = robot_state_->zero();
+    std::copy(last.begin(), last.begin() + (long)nq, update_vars_.state_ref.begin());
+    const double w = last[6], z = last[5];
+    const double norm = std::sqrt(w * w + z * z);  // Eigen::Quaterniond::normalize(): coefficient-wise division by the norm
+    update_vars_.state_ref[5] = z / norm;
+    update_vars_.state_ref[6] = w / norm;
+  } else {
+    // alpha = (time - t_ref[i-1]) / (t_ref[i] - t_ref[i-1]) is evaluated in std::size_t arithmetic => 0 (:188-189):
+    // pinocchio::interpolate(q0, q1, 0) = q0 and v0 + 0 (v1 - v0) = v0, i.e. a piecewise-constant reference
+    update_vars_.state_ref = state_ref_[update_vars_.idx_state - 1];
+  }
+}
+
+void RailMpc::updateFreeCosts(std::size_t idx) {
+  computeStateReference(update_vars_.node_time);
+  int_models_[idx]->costs->get_costs().at("rail_state")->cost->reference = update_vars_.state_ref;
+  syncCost(idx, "rail_state");
+}
+
+void RailMpc::updateProblem(const std::size_t& current_time) {
+  beginUpdate();
+  for (std::size_t i = 0; i < int_models_.size(); ++i) {
+    update_vars_.node_time = current_time + i * params_.dt;
+    updateFreeCosts(i);
+  }
+  endUpdate();
+}
+
+// ---- WeightedMpc (src/mpc-controllers/weighted-mpc.cpp) -----------------------------------------------------------------
+WeightedMpc::WeightedMpc(const std::shared_ptr<Trajectory>& trajectory, std::size_t /*dt_ref*/, const std::string& yaml_path,
+                         bool create_solver)
+    : MpcAbstract(yaml_path), trajectory_(trajectory), cost_factory_(std::make_shared<CostModelFactory>()) {
+  defer_solver_ = !create_solver;
+  auto dbl = [&](const char* key, double def) {
+    try { return params_server_->getParam<double>(std::string("mpc_controller/") + key); }
+    catch (const std::exception&) { return def; }
+  };
+  alpha_ = dbl("weighted_alpha", 20.0);
+  beta_ = dbl("weighted_beta", 1.0);
+  state_reg_ = dbl("weighted_state_reg", 1e-1);
+  control_reg_ = dbl("weighted_control_reg", 1e-1);
+  // transition stages are merged into the stage that follows them (:63-75): the trajectory object is modified in place
+  for (std::size_t i = 0; i < trajectory_->get_stages().size();) {
+    const auto& stages = trajectory_->get_stages();
+    if (stages[i]->get_is_transition()) {
+      if (i + 1 >= stages.size()) throw std::runtime_error("WeightedMpc: the last stage of the trajectory is a transition stage");
+      stages[i + 1]->set_duration(stages[i]->get_duration() + stages[i + 1]->get_duration());
+      stages[i + 1]->set_t_ini(stages[i]->get_t_ini());
+      trajectory_->removeStage(i);
+      t_stages_.push_back(trajectory_->get_stages()[i]->get_t_ini());
+      ++i;
+    } else {
+      t_stages_.push_back(stages[i]->get_t_ini());
+      ++i;
+    }
+  }
+  createProblem();
+}
+
+std::shared_ptr<CostModelSum> WeightedMpc::createCosts() const {
+  auto costs = std::make_shared<CostModelSum>();
+  for (const auto& stage : trajectory_->get_stages()) {
+    if (stage->get_is_transition()) continue;
+    const std::string path_to_stage = "stages/" + stage->get_name();
+    for (const auto& ctype : stage->get_cost_types()) {
+      CostModelTypes cost_type = ctype.second;
+      auto cost = cost_factory_->create(path_to_stage + "/costs/" + ctype.first + "/", trajectory_->get_params_server(), robot_state_,
+                                        nu_, cost_type);
+      costs->addCost(stage->get_name() + "/" + ctype.first, cost, stage->get_costs()->get_costs().at(ctype.first)->weight, false);
+    }
+  }
+  return costs;
+}
+
+void WeightedMpc::createProblem() {
+  if (trajectory_->get_has_contact()) throw std::runtime_error("Weighted with contact has not been implemented");
+  checkHotPathSupport();
+  for (std::size_t i = 0; i < params_.knots; ++i) int_models_.push_back(makeKnotModel(createCosts()));
+  finishProblem();
+}
+
+void WeightedMpc::computeActiveStage(std::size_t current_time) {
+  update_vars_.idx_stage = std::size_t(std::upper_bound(t_stages_.begin(), t_stages_.end(), current_time) - t_stages_.begin()) - 1;
+}
+
+void WeightedMpc::computeActiveStage(std::size_t current_time, std::size_t last_stage) {
+  computeActiveStage(current_time);
+  if (update_vars_.idx_stage == last_stage + 2) update_vars_.idx_stage -= 1;
+}
+
+void WeightedMpc::computeWeight(std::size_t time) {
+  // saturate the weight once the nodes are beyond the end of the trajectory (:229-241)
+  if (time > trajectory_->get_duration()) update_vars_.weight_time = 0.0;
+  else {
+    const auto& st = trajectory_->get_stages()[update_vars_.idx_stage];
+    update_vars_.weight_time = ((int)time - ((int)st->get_t_ini() + (int)st->get_duration())) / 1000.0;
+  }
+  update_vars_.weight = std::exp(alpha_ * update_vars_.weight_time);
+}
+
+void WeightedMpc::updateFreeCosts(std::size_t idx) {
+  auto& costs = int_models_[idx]->costs->get_costs();
+  const std::string& ns = update_vars_.name_stage;
+  for (auto& kv : costs) {
+    const std::string& name = kv.first;
+    if (name.compare(0, ns.size(), ns) == 0) {  // prefix match, like the reference (:205)
+      kv.second->active = true;
+      if (name.compare(ns.size(), 4, "/reg") != 0 && name.compare(ns.size(), 7, "/limits") != 0) {
+        computeWeight(update_vars_.node_time);
+        kv.second->weight = trajectory_->get_stages()[update_vars_.idx_stage]->get_costs()->get_costs().at(name.substr(ns.size() + 1))->weight *
+                            update_vars_.weight * beta_;
+      }
+    } else if (name != "barrier") {
+      kv.second->active = false;
+    }
+    if (name != "barrier") syncCost(idx, name);
+  }
+}
+
+void WeightedMpc::updateProblem(const std::size_t& current_time) {
+  computeActiveStage(current_time);
+  update_vars_.idx_last_stage = update_vars_.idx_stage;
+  beginUpdate();
+  for (std::size_t i = 0; i < int_models_.size(); ++i) {
+    update_vars_.node_time = current_time + i * params_.dt;
+    computeActiveStage(update_vars_.node_time, update_vars_.idx_last_stage);
+    update_vars_.name_stage = trajectory_->get_stages()[update_vars_.idx_stage]->get_name();
+    updateFreeCosts(i);
+    update_vars_.idx_last_stage = update_vars_.idx_stage;
+  }
+  endUpdate();
 }
 
 }  // namespace eagle_mpc

@@ -1,7 +1,8 @@
-"""Closed-loop MPC driver over the host-side CarrotMpc mirror (examples/python/mpc.py of the reference).
+"""Closed-loop MPC driver over the host-side controller mirrors (examples/python/mpc.py of the reference).
 
-`CarrotMpc` wraps the C++ controller (host/mpc.cpp): updateProblem(t) retargets the per-knot costs, solve() runs the
-B200 SbFDDP path for the single MPC instance, and the RK4 plant runs as a CUDA kernel behind `empc_plant_step`.
+`CarrotMpc` / `RailMpc` / `WeightedMpc` wrap the C++ controllers (host/mpc.cpp): updateProblem(t) retargets the per-knot
+costs, solve() runs the B200 SbFDDP path for the single MPC instance, and the RK4 plant runs as a CUDA kernel behind
+`empc_plant_step`.
 """
 import ctypes as C
 import time
@@ -18,6 +19,10 @@ def _mlib():
     if not getattr(L, "_mpc_ready", False):
         L.empc_host_carrot_create.restype = C.c_void_p
         L.empc_host_carrot_create.argtypes = [C.c_void_p, abi.c_double_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+        L.empc_host_rail_create.restype = C.c_void_p
+        L.empc_host_rail_create.argtypes = [abi.c_double_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+        L.empc_host_weighted_create.restype = C.c_void_p
+        L.empc_host_weighted_create.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32]
         L.empc_host_carrot_free.argtypes = [C.c_void_p]
         L.empc_host_carrot_info.argtypes = [C.c_void_p, abi.c_int32_p]
         L.empc_host_carrot_desc.restype = C.POINTER(abi.ProblemDesc)
@@ -33,15 +38,11 @@ def _mlib():
     return L
 
 
-class CarrotMpc(abi.DescView):
-    """eagle_mpc.CarrotMpc(trajectory, state_ref, dt_ref, yaml_path)"""
+class _MpcBase(abi.DescView):
+    """Shared surface of the controllers: updateProblem / solve / result / plant_step over an opaque C++ object."""
 
-    def __init__(self, trajectory, state_ref, dt_ref, yaml_path, create_solver=True):
+    def _adopt(self, p, create_solver):
         L = _mlib()
-        self._traj = trajectory
-        ref = np.ascontiguousarray(state_ref, dtype=np.float64)
-        p = L.empc_host_carrot_create(trajectory._p, abi.as_double_p(ref), ref.shape[0], int(dt_ref), yaml_path.encode(),
-                                      int(create_solver))
         if not p:
             raise EmpcError(_err())
         self._p = C.c_void_p(p)
@@ -50,6 +51,11 @@ class CarrotMpc(abi.DescView):
         self.knots, self.dt, self.iters, self.n_costs, self.n_pool = (int(v) for v in info)
         self.desc = L.empc_host_carrot_desc(self._p).contents
         self.handle = C.c_void_p(L.empc_host_carrot_handle(self._p)) if create_solver else None
+
+    def refresh_sizes(self):
+        info = np.zeros(5, dtype=np.int32)
+        _mlib().empc_host_carrot_info(self._p, abi.as_int32_p(info))
+        self.n_costs, self.n_pool = int(info[3]), int(info[4])
 
     def updateProblem(self, t_ms):
         if _mlib().empc_host_carrot_update(self._p, int(t_ms)):
@@ -90,6 +96,34 @@ class CarrotMpc(abi.DescView):
         if getattr(self, "_p", None) and self._p.value:
             _mlib().empc_host_carrot_free(self._p)
             self._p = C.c_void_p()
+
+
+class CarrotMpc(_MpcBase):
+    """eagle_mpc.CarrotMpc(trajectory, state_ref, dt_ref, yaml_path)"""
+
+    def __init__(self, trajectory, state_ref, dt_ref, yaml_path, create_solver=True):
+        self._traj = trajectory
+        ref = np.ascontiguousarray(state_ref, dtype=np.float64)
+        self._adopt(_mlib().empc_host_carrot_create(trajectory._p, abi.as_double_p(ref), ref.shape[0], int(dt_ref),
+                                                    yaml_path.encode(), int(create_solver)), create_solver)
+
+
+class RailMpc(_MpcBase):
+    """eagle_mpc.RailMpc(state_ref, dt_ref, yaml_path)"""
+
+    def __init__(self, state_ref, dt_ref, yaml_path, create_solver=True):
+        ref = np.ascontiguousarray(state_ref, dtype=np.float64)
+        self._adopt(_mlib().empc_host_rail_create(abi.as_double_p(ref), ref.shape[0], ref.shape[1], int(dt_ref),
+                                                  yaml_path.encode(), int(create_solver)), create_solver)
+
+
+class WeightedMpc(_MpcBase):
+    """eagle_mpc.WeightedMpc(trajectory, dt_ref, yaml_path) — merges the trajectory's transition stages in place"""
+
+    def __init__(self, trajectory, dt_ref, yaml_path, create_solver=True):
+        self._traj = trajectory
+        self._adopt(_mlib().empc_host_weighted_create(trajectory._p, int(dt_ref), yaml_path.encode(), int(create_solver)),
+                    create_solver)
 
 
 def closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, record=False):

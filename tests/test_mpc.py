@@ -67,3 +67,104 @@ def test_carrot_closed_loop_gpu_vs_oracle():
     assert np.abs(u_g - u_o).max() <= 1e-7 * max(1.0, np.abs(u_o).max())
     assert np.abs(st_g - st_o).max() <= 1e-8 * max(1.0, np.abs(st_o).max())
     print("p50 latency gpu %.3f ms, oracle %.3f ms" % (1e3 * np.median(lat_g), 1e3 * np.median(lat_o)))
+
+
+# ---- RailMpc / WeightedMpc (BASELINE.json config 5: iris_px4) ---------------------------------------------------------
+IRIS_TRAJ = "iris_px4/trajectories/displacement.yaml"
+IRIS_MPC = "iris_px4/mpc/mpc.yaml"
+
+
+def _iris_solution():
+    tr = host.Trajectory(IRIS_TRAJ)
+    fp = tr.createProblem(20)
+    p = ob.default_params(); p.maxiter = 400
+    o = ob.Oracle(fp); o.set_params(p); o.set_x0(fp.x0); o.solve()
+    return tr, fp, o.get("xs"), o.get("us")
+
+
+def _cost_records(mpc, knot):
+    costs, pool = mpc.cost_tables()
+    begin = np.ctypeslib.as_array(mpc.desc.costset_begin, shape=(mpc.knots + 1,))
+    return [costs[i] for i in range(begin[knot], begin[knot + 1])], pool
+
+
+def test_rail_retargeting_matches_reference_rules():
+    tr, fp, xs, us = _iris_solution()
+    mpc = mpcmod.RailMpc(xs, 20, IRIS_MPC, create_solver=False)
+    assert (mpc.knots, mpc.dt, mpc.iters) == (40, 20, 2) and mpc.T == 39
+    # per knot: [barrier,] control (Quad, weight rail_control_weight), rail_state (WeightedQuad, weight rail_weight)
+    recs, pool = _cost_records(mpc, 0)
+    assert [r.type for r in recs] == [abi.COST_SQUASH_BARRIER, abi.COST_CONTROL, abi.COST_STATE]
+    assert recs[1].weight == 1e-1 and recs[2].weight == 1000 and recs[2].activation == abi.ACT_WEIGHTED_QUAD
+    assert [r.type for r in _cost_records(mpc, 39)[0]] == [abi.COST_CONTROL, abi.COST_STATE]   # terminal knot: no barrier
+    # knot i at time t + i dt tracks state_ref[upper_bound(t_ref, time) - 1] (integer-division interpolation, rail-mpc.cpp:188)
+    mpc.updateProblem(130)
+    for k in (0, 7, 39):
+        recs, pool = _cost_records(mpc, k)
+        ref = pool[recs[-1].ref_off:recs[-1].ref_off + mpc.nx]
+        assert np.array_equal(ref, xs[(130 + 20 * k) // 20])
+    # beyond the end: hover at the last configuration, yaw-only quaternion from (w, z), zero velocity (:180-186)
+    t_end = 20 * (len(xs) - 1)
+    mpc.updateProblem(t_end + 500)
+    recs, pool = _cost_records(mpc, 5)
+    ref = pool[recs[-1].ref_off:recs[-1].ref_off + mpc.nx]
+    last = xs[-1]
+    n = np.hypot(last[6], last[5])
+    assert np.array_equal(ref[:5], last[:5]) and ref[5] == last[5] / n and ref[6] == last[6] / n
+    assert np.all(ref[7:] == 0)
+
+
+def test_weighted_retargeting_matches_reference_rules():
+    tr = host.Trajectory(IRIS_TRAJ)
+    n_before = len(tr.stage_names())
+    mpc = mpcmod.WeightedMpc(tr, 20, IRIS_MPC, create_solver=False)
+    # the transition stages were merged into their successors, in place (weighted-mpc.cpp:63-75)
+    names = tr.stage_names()
+    assert len(names) < n_before and not any(n.startswith("nav_") for n in names)
+    assert mpc.knots == 40
+    recs0, _ = _cost_records(mpc, 0)
+    n_stage_costs = len(recs0) - 1                      # minus the solver's barrier
+    assert n_stage_costs >= 4 * 3                       # every stage's costs live in every knot
+    # t = 0: all 40 knots (0 .. 780 ms) fall into the first merged stage (wp_1, 0 .. 2000 ms)
+    mpc.updateProblem(0)
+    for k in (0, 20, 39):
+        recs, _ = _cost_records(mpc, k)
+        act = [r for r in recs if r.active and r.type != abi.COST_SQUASH_BARRIER]
+        assert len(act) == 4                            # wp_1/{motion,placement}_base_link, wp_1/reg_{control,state}
+        w = sorted(r.weight for r in act if r.type in (abi.COST_FRAME_PLACEMENT, abi.COST_FRAME_VELOCITY))
+        # task costs: stage weight * exp(alpha (t - t_end_of_stage)) * beta with alpha = 20, beta = 1 (defaults)
+        expw = np.exp(20.0 * ((20 * k) - 2000) / 1000.0)
+        assert len(w) == 2 and w[0] > 0 and abs(w[0] / expw - round(w[0] / expw)) < 1e-9
+    # regularisation costs keep their stage weight
+    recs, _ = _cost_records(mpc, 3)
+    regs = [r for r in recs if r.active and r.type in (abi.COST_STATE, abi.COST_CONTROL)]
+    assert len(regs) == 2
+    # later: knots straddle the switch from the first to the second merged stage
+    mpc.updateProblem(1700)
+    first = [sum(1 for r in _cost_records(mpc, k)[0] if r.active and r.type == abi.COST_FRAME_PLACEMENT) for k in range(40)]
+    assert all(v == 1 for v in first)                   # exactly one stage active per knot
+
+
+def _closed_loop_pair(make, xs, us, n_steps):
+    mpc_g = make(True)
+    lat_g, st_g, u_g, it_g = mpcmod.closed_loop(mpc_g, xs, us, xs[0], n_steps, record=True)
+    mpc_o = make(False)
+    lat_o, st_o, u_o, it_o = ob.oracle_closed_loop(mpc_o, xs, us, xs[0], n_steps, record=True)
+    assert it_g == it_o
+    assert np.abs(u_g - u_o).max() <= 1e-7 * max(1.0, np.abs(u_o).max())
+    assert np.abs(st_g - st_o).max() <= 1e-8 * max(1.0, np.abs(st_o).max())
+    return 1e3 * np.median(lat_g), 1e3 * np.median(lat_o)
+
+
+@pytest.mark.gpu
+def test_rail_closed_loop_gpu_vs_oracle():
+    tr, fp, xs, us = _iris_solution()
+    g, o = _closed_loop_pair(lambda s: mpcmod.RailMpc(xs, 20, IRIS_MPC, create_solver=s), xs, us, 30)
+    print("rail p50 latency gpu %.3f ms, oracle %.3f ms" % (g, o))
+
+
+@pytest.mark.gpu
+def test_weighted_closed_loop_gpu_vs_oracle():
+    _tr, fp, xs, us = _iris_solution()
+    g, o = _closed_loop_pair(lambda s: mpcmod.WeightedMpc(host.Trajectory(IRIS_TRAJ), 20, IRIS_MPC, create_solver=s), xs, us, 30)
+    print("weighted p50 latency gpu %.3f ms, oracle %.3f ms" % (g, o))
