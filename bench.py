@@ -291,7 +291,7 @@ def main():
         kernels = {"calc_diff": "node_calc_kernel+node_diff_kernel", "backward": "backward_kernel",
                    "rollout": "rollout_kernel", "decide": "decide_kernel"}
         dom = int(np.argmax(ms_k[:3]))
-        n_launch = max(1, (launches_serial - 2) // 7)  # batch-iterations of the instrumented step (7 launches each)
+        n_launch = max(1, (launches_serial - 2) // 8)  # batch-iterations of the instrumented step (8 launches each)
         ach = bytes_node[names[dom]] * float(units_k[dom]) * T / (ms_k[dom] * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r1_traffic.json:

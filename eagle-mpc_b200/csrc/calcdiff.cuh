@@ -10,9 +10,10 @@
 // d tau/dq, d tau/dv, M^-1, the NDX x NDX / NDX x NU Jacobian and Hessian blocks).  A thread-per-node kernel needs the
 // whole ~9 KB matrix working set per thread (local memory, thrashing L1/L2: profiles/r1_baseline.md); a
 // lanes-per-node kernel would repeat the serial part on every lane.  So:
-//   node_calc_kernel  thread per node   serial part; writes xnext, cost, gaps and a 344-double "packet" per node
-//                                        (world placements / velocities / accelerations, composite-rigid-body sweep,
-//                                        squashing slopes, Lie transport blocks, state/control cost summaries)
+//   node_calc_kernel  thread per node   serial dynamics part; writes xnext, gaps and most of a 344-double "packet" per
+//                                        node (world placements / velocities / accelerations, composite-rigid-body
+//                                        sweep, squashing slopes, Lie transport blocks)
+//   node_cost_kernel  thread per node   cost value + state/control cost derivative summaries (rest of the packet)
 //   node_diff_kernel  16 lanes per node  column-parallel part out of shared memory; writes the node tile
 //                                        Fx|Fu|Lxx|Lxu|Luu|Lx|Lu with contiguous half-warp stores.
 // The packet is stored AoSoA in groups of 8 nodes ([group][field][8]): the producer's warp (32 consecutive nodes) writes
@@ -126,69 +127,6 @@ __global__ void __launch_bounds__(NC_THREADS, EMPC_NC_BLOCKS) node_calc_kernel(B
 #pragma unroll
     for (int k = 0; k < 3; ++k) put(P::oOM + 12 * i + 9 + k, nd.oM[i].p[k]);
   }
-
-  // costs: value, and the derivative summaries of the state / control type costs (frame costs are left to kernel B)
-  double csum = 0;
-  {
-    double Lx[NDX], LxxB[36], LxxD[NDX - 6], Lu[NU], Luud[NU];
-#pragma unroll
-    for (int i = 0; i < NDX; ++i) Lx[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 36; ++i) LxxB[i] = 0;
-#pragma unroll
-    for (int i = 0; i < NDX - 6; ++i) LxxD[i] = 0;
-#pragma unroll
-    for (int i = 0; i < NU; ++i) { Lu[i] = 0; Luud[i] = 0; }
-    double flag = 0.0;
-    const int c0 = bf.ct.costset_begin[costset], c1 = bf.ct.costset_begin[costset + 1];
-    for (int c = c0; c < c1; ++c) {
-      const empc_cost_t cs = bf.ct.costs[c];
-      if (!cs.active) continue;
-      double r[NDX], Ar[NDX], Arr[NDX];
-      SE3 rMf;
-      const double wt = cs.weight;
-      csum += wt * cost_eval<D>(M, bf.ct, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
-      if (cs.type == EMPC_COST_STATE) {
-        SE3 Mref, Mx, Dm;
-        double xr[7];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) xr[i] = bf.ct.pool[cs.ref_off + i];
-        q_to_se3(xr, Mref); q_to_se3(x, Mx); se3_inv_mul(Mref, Mx, Dm);
-        double Jl[36]; Jlog6(Dm, Jl);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          double s = 0;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) s += Jl[6 * k + i] * Ar[k];
-          Lx[i] += wt * s;
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            double h = 0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) h += Jl[6 * k + i] * (Arr[k] * Jl[6 * k + j]);
-            LxxB[6 * i + j] += wt * h;
-          }
-        }
-#pragma unroll
-        for (int i = 6; i < NDX; ++i) { Lx[i] += wt * Ar[i]; LxxD[i - 6] += wt * Arr[i]; }
-      } else if (cs.type == EMPC_COST_CONTROL || cs.type == EMPC_COST_SQUASH_BARRIER) {
-#pragma unroll
-        for (int i = 0; i < NU; ++i) { Lu[i] += wt * Ar[i]; Luud[i] += wt * Arr[i]; }
-      } else {
-        flag = 1.0;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NDX; ++i) put(P::oLX + i, Lx[i]);
-#pragma unroll
-    for (int i = 0; i < 36; ++i) put(P::oLXXB + i, LxxB[i]);
-#pragma unroll
-    for (int i = 0; i < NDX - 6; ++i) put(P::oLXXD + i, LxxD[i]);
-#pragma unroll
-    for (int i = 0; i < NU; ++i) { put(P::oLU + i, Lu[i]); put(P::oLUUD + i, Luud[i]); }
-    put(P::oFLAG, flag);
-  }
-  if (on) bf.node_cost[n] = M.dt * csum;
 
   // forward dynamics + semi-implicit Euler
   EMPC_NC_PHASE();
@@ -312,6 +250,106 @@ __global__ void __launch_bounds__(NC_THREADS, EMPC_NC_BLOCKS) node_calc_kernel(B
       bf.gap_inf[n] = 0; bf.gap_l1[n] = 0;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel A2: the cost half of calc / calcDiff, one thread per node: cost value (node_cost) and the derivative summaries of
+// the state / control type costs (packet fields oLX .. oFLAG).  Split from node_calc_kernel so that neither kernel has to
+// keep the other's working set live (the dynamics + composite sweep spill less, and this one needs no dynamics at all);
+// the kinematics are recomputed only for nodes whose cost set holds frame costs.
+template <class D>
+__global__ void __launch_bounds__(128, 4) node_cost_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
+  constexpr int NDX = D::NDX, NU = D::NU, NX = D::NX;
+  using P = Pk<D>;
+  const long long nl0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int T1 = bf.T + 1;
+  if (nl0 >= (long long)bf.nb * T1) return;
+  const size_t n = (size_t)bf.b0 * T1 + nl0;
+  const int b = (int)(n / T1), t = (int)(n - (size_t)b * T1);
+  const OcpState st = bf.st[b];
+  if (!force && (st.phase == PHASE_DONE || !st.recalc)) return;
+  const double smooth = force ? force_smooth : st.smooth;
+  const bool on = true;
+  double* pk = bf.packets + pk_index<D>(n, 0);
+  auto put = [&](int f, double v) { pk[(size_t)f * P::GROUP] = v; };
+  double x[NX], u[NU];
+  const double* xg = bf.xs + n * NX;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = xg[i];
+  if (t < bf.T) {
+    const double* ug = bf.us + ((size_t)b * bf.T + t) * NU;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = ug[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = 0.0;  // calc(data,x) == calc(data,x,0), SURVEY B.7
+  }
+  const int costset = bf.node_costset[bf.ocp_map[b] * T1 + t];
+  double csum = 0;
+  {
+    double Lx[NDX], LxxB[36], LxxD[NDX - 6], Lu[NU], Luud[NU];
+#pragma unroll
+    for (int i = 0; i < NDX; ++i) Lx[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) LxxB[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NDX - 6; ++i) LxxD[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) { Lu[i] = 0; Luud[i] = 0; }
+    double flag = 0.0;
+    const int c0 = bf.ct.costset_begin[costset], c1 = bf.ct.costset_begin[costset + 1];
+    for (int c = c0; c < c1; ++c) {
+      const empc_cost_t cs = bf.ct.costs[c];
+      if (!cs.active) continue;
+      const double wt = cs.weight;
+      if (is_frame_cost(cs.type)) {  // value here, derivatives in node_diff_kernel
+        csum += wt * frame_cost_value<D>(M, bf.ct, cs, smooth, x);
+        flag = 1.0;
+        continue;
+      }
+      double r[NDX], Ar[NDX], Arr[NDX];
+      SE3 rMf;
+      NodeData<D>* no_kinematics = nullptr;  // state / control residuals never touch the kinematics
+      csum += wt * cost_eval<D>(M, bf.ct, cs, smooth, x, u, *no_kinematics, r, Ar, Arr, rMf);
+      if (cs.type == EMPC_COST_STATE) {
+        SE3 Mref, Mx, Dm;
+        double xr[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) xr[i] = bf.ct.pool[cs.ref_off + i];
+        q_to_se3(xr, Mref); q_to_se3(x, Mx); se3_inv_mul(Mref, Mx, Dm);
+        double Jl[36]; Jlog6(Dm, Jl);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          double s = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += Jl[6 * k + i] * Ar[k];
+          Lx[i] += wt * s;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            double h = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) h += Jl[6 * k + i] * (Arr[k] * Jl[6 * k + j]);
+            LxxB[6 * i + j] += wt * h;
+          }
+        }
+#pragma unroll
+        for (int i = 6; i < NDX; ++i) { Lx[i] += wt * Ar[i]; LxxD[i - 6] += wt * Arr[i]; }
+      } else {  // EMPC_COST_CONTROL, EMPC_COST_SQUASH_BARRIER
+#pragma unroll
+        for (int i = 0; i < NU; ++i) { Lu[i] += wt * Ar[i]; Luud[i] += wt * Arr[i]; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NDX; ++i) put(P::oLX + i, Lx[i]);
+#pragma unroll
+    for (int i = 0; i < 36; ++i) put(P::oLXXB + i, LxxB[i]);
+#pragma unroll
+    for (int i = 0; i < NDX - 6; ++i) put(P::oLXXD + i, LxxD[i]);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) { put(P::oLU + i, Lu[i]); put(P::oLUUD + i, Luud[i]); }
+    put(P::oFLAG, flag);
+  }
+  bf.node_cost[n] = M.dt * csum;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -525,25 +525,32 @@ EMPC_DI void node_dyn(const DevModel& M, double smooth, const double* x, const d
   state_integrate<D>(x, nd.dx, xnext);
 }
 
+// Value of one FRAME cost at state x (kinematics recomputed inside).  Deliberately not inlined: the world placements and
+// joint velocities (NodeData, ~1.3 KB) then live in this function's frame only, and only on the rare nodes with frame costs.
+template <class D>
+__device__ __noinline__ double frame_cost_value(const DevModel& M, const CostTables& C, const empc_cost_t& cs, double smooth, const double* x) {
+  NodeData<D> nd;
+  aba_kinematics<D, false>(M, x, nd);
+  double r[D::NDX], Ar[D::NDX], Arr[D::NDX];
+  SE3 rMf;
+  return cost_eval<D>(M, C, cs, smooth, x, nullptr, nd, r, Ar, Arr, rMf);
+}
+EMPC_DI bool is_frame_cost(int type) { return type != EMPC_COST_STATE && type != EMPC_COST_CONTROL && type != EMPC_COST_SQUASH_BARRIER; }
+
 // Cost half: dt * sum_c w_c a_c(r_c(x, u)) in the reference's cost order; needs the kinematics only when the cost set
 // holds frame costs.
 template <class D>
 EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x, const double* u) {
   const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
-  bool need_kin = false;
-  for (int c = c0; c < c1; ++c) {
-    const int ty = C.costs[c].type;
-    if (C.costs[c].active && ty != EMPC_COST_STATE && ty != EMPC_COST_CONTROL && ty != EMPC_COST_SQUASH_BARRIER) need_kin = true;
-  }
-  NodeData<D> nd;
-  if (need_kin) aba_kinematics<D, false>(M, x, nd);
   double csum = 0;
   for (int c = c0; c < c1; ++c) {
     const empc_cost_t cs = C.costs[c];
     if (!cs.active) continue;
+    if (is_frame_cost(cs.type)) { csum += cs.weight * frame_cost_value<D>(M, C, cs, smooth, x); continue; }
     double r[D::NDX], Ar[D::NDX], Arr[D::NDX];
     SE3 rMf;
-    csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
+    NodeData<D>* no_kinematics = nullptr;  // state / control residuals never touch the kinematics
+    csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, *no_kinematics, r, Ar, Arr, rMf);
   }
   return M.dt * csum;
 }

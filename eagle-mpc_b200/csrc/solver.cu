@@ -346,6 +346,8 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   const long long n = (long long)bf.nb * T1;
   node_calc_kernel<D><<<(unsigned)((n + NC_THREADS - 1) / NC_THREADS), NC_THREADS, 0, st>>>(bf, force, smooth, h->hmodel);
   h->launches++;
+  node_cost_kernel<D><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bf, force, smooth, h->hmodel);
+  h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   using W = DiffCfg<D>;
