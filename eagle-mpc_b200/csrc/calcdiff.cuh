@@ -269,7 +269,6 @@ __global__ void __launch_bounds__(128, 4) node_cost_kernel(Buffers bf, int force
   const OcpState st = bf.st[b];
   if (!force && (st.phase == PHASE_DONE || !st.recalc)) return;
   const double smooth = force ? force_smooth : st.smooth;
-  const bool on = true;
   double* pk = bf.packets + pk_index<D>(n, 0);
   auto put = [&](int f, double v) { pk[(size_t)f * P::GROUP] = v; };
   double x[NX], u[NU];
@@ -287,16 +286,37 @@ __global__ void __launch_bounds__(128, 4) node_cost_kernel(Buffers bf, int force
   const int costset = bf.node_costset[bf.ocp_map[b] * T1 + t];
   double csum = 0;
   {
-    double Lx[NDX], LxxB[36], LxxD[NDX - 6], Lu[NU], Luud[NU];
+    // State costs that share a reference (typically a regularisation and a limits barrier around the same state) share
+    // the residual r = x (-) ref and its Jacobian [[A, B], [0, A]] = Jlog6(ref^-1 x): they are grouped, their activation
+    // derivatives are summed first (a6 = sum w Ar[0:6], d6 = sum w Arr[0:6]) and Jl^T a6, Jl^T diag(d6) Jl are formed
+    // once per group, straight into the packet — no 36-entry Hessian accumulator has to stay live across the cost loop.
+    double LxT[NDX - 6], LxxD[NDX - 6], Lu[NU], Luud[NU];
 #pragma unroll
-    for (int i = 0; i < NDX; ++i) Lx[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 36; ++i) LxxB[i] = 0;
-#pragma unroll
-    for (int i = 0; i < NDX - 6; ++i) LxxD[i] = 0;
+    for (int i = 0; i < NDX - 6; ++i) { LxT[i] = 0; LxxD[i] = 0; }
 #pragma unroll
     for (int i = 0; i < NU; ++i) { Lu[i] = 0; Luud[i] = 0; }
     double flag = 0.0;
+    double gref[NX], gr[NDX], gA[9], gB[9], a6[6], d6[6];
+    bool g_open = false, g_first = true;
+    auto flush_group = [&]() {
+      // J = [[A, B], [0, A]]:  J(k, i) for k, i in 0..5
+      auto J = [&](int k, int i) -> double { return (k < 3) ? ((i < 3) ? gA[3 * k + i] : gB[3 * k + i - 3]) : ((i < 3) ? 0.0 : gA[3 * (k - 3) + i - 3]); };
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double sacc = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sacc += J(k, i) * a6[k];
+        if (g_first) put(P::oLX + i, sacc); else pk[(size_t)(P::oLX + i) * P::GROUP] += sacc;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          double h = 0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) h += J(k, i) * (d6[k] * J(k, j));
+          if (g_first) put(P::oLXXB + 6 * i + j, h); else pk[(size_t)(P::oLXXB + 6 * i + j) * P::GROUP] += h;
+        }
+      }
+      g_first = false; g_open = false;
+    };
     const int c0 = bf.ct.costset_begin[costset], c1 = bf.ct.costset_begin[costset + 1];
     for (int c = c0; c < c1; ++c) {
       const empc_cost_t cs = bf.ct.costs[c];
@@ -307,44 +327,49 @@ __global__ void __launch_bounds__(128, 4) node_cost_kernel(Buffers bf, int force
         flag = 1.0;
         continue;
       }
-      double r[NDX], Ar[NDX], Arr[NDX];
-      SE3 rMf;
-      NodeData<D>* no_kinematics = nullptr;  // state / control residuals never touch the kinematics
-      csum += wt * cost_eval<D>(M, bf.ct, cs, smooth, x, u, *no_kinematics, r, Ar, Arr, rMf);
+      double Ar[NDX], Arr[NDX];
       if (cs.type == EMPC_COST_STATE) {
-        SE3 Mref, Mx, Dm;
-        double xr[7];
+        const double* ref = bf.ct.pool + cs.ref_off;
+        bool same = g_open;
+        if (same) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) xr[i] = bf.ct.pool[cs.ref_off + i];
-        q_to_se3(xr, Mref); q_to_se3(x, Mx); se3_inv_mul(Mref, Mx, Dm);
-        double Jl[36]; Jlog6(Dm, Jl);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          double s = 0;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) s += Jl[6 * k + i] * Ar[k];
-          Lx[i] += wt * s;
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            double h = 0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) h += Jl[6 * k + i] * (Arr[k] * Jl[6 * k + j]);
-            LxxB[6 * i + j] += wt * h;
-          }
+          for (int i = 0; i < NX; ++i) same &= (ref[i] == gref[i]);
         }
+        if (!same) {
+          if (g_open) flush_group();
 #pragma unroll
-        for (int i = 6; i < NDX; ++i) { Lx[i] += wt * Ar[i]; LxxD[i - 6] += wt * Arr[i]; }
+          for (int i = 0; i < NX; ++i) gref[i] = ref[i];
+          state_diff<D>(gref, x, gr);
+          SE3 Mref, Mx, Dm;
+          q_to_se3(gref, Mref); q_to_se3(x, Mx); se3_inv_mul(Mref, Mx, Dm);
+          Jlog6_blocks(Dm, gA, gB);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { a6[i] = 0; d6[i] = 0; }
+          g_open = true;
+        }
+        csum += wt * activation<NDX>(cs.activation, gr, bf.ct.pool + cs.w_off, bf.ct.pool + cs.lb_off, bf.ct.pool + cs.ub_off, Ar, Arr);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { a6[i] += wt * Ar[i]; d6[i] += wt * Arr[i]; }
+#pragma unroll
+        for (int i = 6; i < NDX; ++i) { LxT[i - 6] += wt * Ar[i]; LxxD[i - 6] += wt * Arr[i]; }
       } else {  // EMPC_COST_CONTROL, EMPC_COST_SQUASH_BARRIER
+        double r[NDX];
+        SE3 rMf;
+        NodeData<D>* no_kinematics = nullptr;  // control residuals never touch the kinematics
+        csum += wt * cost_eval<D>(M, bf.ct, cs, smooth, x, u, *no_kinematics, r, Ar, Arr, rMf);
 #pragma unroll
         for (int i = 0; i < NU; ++i) { Lu[i] += wt * Ar[i]; Luud[i] += wt * Arr[i]; }
       }
     }
+    if (g_open) flush_group();
+    if (g_first) {  // no state cost at all
 #pragma unroll
-    for (int i = 0; i < NDX; ++i) put(P::oLX + i, Lx[i]);
+      for (int i = 0; i < 6; ++i) put(P::oLX + i, 0.0);
 #pragma unroll
-    for (int i = 0; i < 36; ++i) put(P::oLXXB + i, LxxB[i]);
+      for (int i = 0; i < 36; ++i) put(P::oLXXB + i, 0.0);
+    }
 #pragma unroll
-    for (int i = 0; i < NDX - 6; ++i) put(P::oLXXD + i, LxxD[i]);
+    for (int i = 6; i < NDX; ++i) { put(P::oLX + i, LxT[i - 6]); put(P::oLXXD + i - 6, LxxD[i - 6]); }
 #pragma unroll
     for (int i = 0; i < NU; ++i) { put(P::oLU + i, Lu[i]); put(P::oLUUD + i, Luud[i]); }
     put(P::oFLAG, flag);

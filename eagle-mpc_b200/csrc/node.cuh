@@ -543,14 +543,33 @@ template <class D>
 EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x, const double* u) {
   const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
   double csum = 0;
+  double gref[D::NX], gr[D::NDX];  // state costs that share a reference share the residual x (-) ref
+  bool g_open = false;
   for (int c = c0; c < c1; ++c) {
     const empc_cost_t cs = C.costs[c];
     if (!cs.active) continue;
     if (is_frame_cost(cs.type)) { csum += cs.weight * frame_cost_value<D>(M, C, cs, smooth, x); continue; }
-    double r[D::NDX], Ar[D::NDX], Arr[D::NDX];
-    SE3 rMf;
-    NodeData<D>* no_kinematics = nullptr;  // state / control residuals never touch the kinematics
-    csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, *no_kinematics, r, Ar, Arr, rMf);
+    double Ar[D::NDX], Arr[D::NDX];
+    if (cs.type == EMPC_COST_STATE) {
+      const double* ref = C.pool + cs.ref_off;
+      bool same = g_open;
+      if (same) {
+#pragma unroll
+        for (int i = 0; i < D::NX; ++i) same &= (ref[i] == gref[i]);
+      }
+      if (!same) {
+#pragma unroll
+        for (int i = 0; i < D::NX; ++i) gref[i] = ref[i];
+        state_diff<D>(gref, x, gr);
+        g_open = true;
+      }
+      csum += cs.weight * activation<D::NDX>(cs.activation, gr, C.pool + cs.w_off, C.pool + cs.lb_off, C.pool + cs.ub_off, Ar, Arr);
+    } else {
+      double r[D::NDX];
+      SE3 rMf;
+      NodeData<D>* no_kinematics = nullptr;  // control residuals never touch the kinematics
+      csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, *no_kinematics, r, Ar, Arr, rMf);
+    }
   }
   return M.dt * csum;
 }
