@@ -259,12 +259,17 @@ __global__ void __launch_bounds__(128, 4) decide_kernel(Buffers bf, DecideParams
   }
   if (acc >= 0) {
     const size_t trial = (size_t)acc * bf.B + b;
-    const double* xsrc = bf.xs_try + trial * T1 * NX;
-    double* xdst = bf.xs + (size_t)b * T1 * NX;
-    for (int i = tid; i < T1 * NX; i += blockDim.x) xdst[i] = xsrc[i];
-    const double* usrc = bf.us_try + trial * T * NU;
-    double* udst = bf.us + (size_t)b * T * NU;
-    for (int i = tid; i < T * NU; i += blockDim.x) udst[i] = usrc[i];
+    // candidate copy (setCandidate): 4 independent loads in flight per thread
+    auto copy4 = [&](double* __restrict__ dst, const double* __restrict__ src, int cnt) {
+      int i = tid;
+      for (; i + 3 * (int)blockDim.x < cnt; i += 4 * blockDim.x) {
+        const double a = src[i], b2 = src[i + blockDim.x], c = src[i + 2 * blockDim.x], d = src[i + 3 * blockDim.x];
+        dst[i] = a; dst[i + blockDim.x] = b2; dst[i + 2 * blockDim.x] = c; dst[i + 3 * blockDim.x] = d;
+      }
+      for (; i < cnt; i += blockDim.x) dst[i] = src[i];
+    };
+    copy4(bf.xs + (size_t)b * T1 * NX, bf.xs_try + trial * T1 * NX, T1 * NX);
+    copy4(bf.us + (size_t)b * T * NU, bf.us_try + trial * T * NU, T * NU);
   }
 }
 
