@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
 #pragma unroll
           for (int i = 0; i < S::NT; ++i) {
 #pragma unroll
-            for (int j = 0; j < S::NT; ++j) dmma884(qxx[i][j][0], qxx[i][j][1], ax[i], bx[j]);
+            for (int j = i; j < S::NT; ++j) dmma884(qxx[i][j][0], qxx[i][j][1], ax[i], bx[j]);  // upper tiles: Qxx is symmetric
 #pragma unroll
             for (int j = 0; j < S::MT; ++j) dmma884(qxu[i][j][0], qxu[i][j][1], ax[i], bu[j]);
           }
@@ -422,8 +422,19 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         for (int j = 0; j < m; ++j) { const double kji = sK[j * LDB + lane]; s1 += kji * Quuk[j]; s2 += kji * Qu[j]; }
         tmpv[lane] = Qx[lane] + s1 - 2 * s2;
       }
-      // ---- Vxx = sym(Qxx - Qxu K) + xreg I, all in the accumulator registers ----
-      warp_mm<S::NT, S::NT, S::KM, false, true>(qxx, sQxu, LDQ, sK, LDB, fr, fc);
+      // ---- Vxx = sym(Qxx - Qxu K) + xreg I, all in the accumulator registers.  Qxx and Qxu K are symmetric up to
+      // rounding, so only the upper tiles (j >= i) are computed: diagonal tiles are averaged with their own transpose
+      // (the reference's 0.5 (Vxx + Vxx^T)), the lower tiles are the mirror images of the upper ones. ----
+#pragma unroll
+      for (int ks = 0; ks < S::KM; ++ks) {
+        double a[S::NT], bq[S::NT];
+#pragma unroll
+        for (int i = 0; i < S::NT; ++i) { a[i] = -sQxu[(8 * i + fr) * LDQ + 4 * ks + fc]; bq[i] = sK[(4 * ks + fc) * LDB + 8 * i + fr]; }
+#pragma unroll
+        for (int i = 0; i < S::NT; ++i)
+#pragma unroll
+          for (int j = i; j < S::NT; ++j) dmma884(qxx[i][j][0], qxx[i][j][1], a[i], bq[j]);
+      }
       {
         // the mirror image of this lane's pair (row fr, columns 2 fc + h) of tile (i, j) is element (2 fc + h, fr) of
         // tile (j, i): it sits in lane (2 fc + h) * 4 + (fr >> 1), slot fr & 1
@@ -433,16 +444,23 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
 #pragma unroll
         for (int i = 0; i < S::NT; ++i)
 #pragma unroll
-          for (int j = 0; j < S::NT; ++j) {
-            const double a0 = __shfl_sync(0xffffffffu, qxx[j][i][0], src0), a1 = __shfl_sync(0xffffffffu, qxx[j][i][1], src0);
-            const double b0 = __shfl_sync(0xffffffffu, qxx[j][i][0], src1), b1 = __shfl_sync(0xffffffffu, qxx[j][i][1], src1);
-            double v0 = 0.5 * (qxx[i][j][0] + (odd ? a1 : a0));
-            double v1 = 0.5 * (qxx[i][j][1] + (odd ? b1 : b0));
-            const int row = 8 * i + fr, col = 8 * j + 2 * fc;
-            if (row == col && row < n) v0 += xreg;
-            if (row == col + 1 && row < n) v1 += xreg;
-            if (isnan(v0) || isnan(v1)) bad = 1;  // "backward_error"
-            vsym[i][j][0] = v0; vsym[i][j][1] = v1;
+          for (int j = i; j < S::NT; ++j) {
+            // transposed element of the upper tile (i, j), as seen from this lane
+            const double a0 = __shfl_sync(0xffffffffu, qxx[i][j][0], src0), a1 = __shfl_sync(0xffffffffu, qxx[i][j][1], src0);
+            const double b0 = __shfl_sync(0xffffffffu, qxx[i][j][0], src1), b1 = __shfl_sync(0xffffffffu, qxx[i][j][1], src1);
+            const double t0 = odd ? a1 : a0, t1 = odd ? b1 : b0;
+            if (i == j) {
+              double v0 = 0.5 * (qxx[i][i][0] + t0), v1 = 0.5 * (qxx[i][i][1] + t1);
+              const int row = 8 * i + fr, col = 8 * i + 2 * fc;
+              if (row == col && row < n) v0 += xreg;
+              if (row == col + 1 && row < n) v1 += xreg;
+              if (isnan(v0) || isnan(v1)) bad = 1;  // "backward_error"
+              vsym[i][i][0] = v0; vsym[i][i][1] = v1;
+            } else {
+              if (isnan(qxx[i][j][0]) || isnan(qxx[i][j][1])) bad = 1;
+              vsym[i][j][0] = qxx[i][j][0]; vsym[i][j][1] = qxx[i][j][1];
+              vsym[j][i][0] = t0; vsym[j][i][1] = t1;
+            }
           }
         acc_store(vsym, sV, LDB, LDB, fr, fc);
       }
