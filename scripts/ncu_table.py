@@ -10,7 +10,7 @@ def col(r, k, scale=1.0):
     try: return float(r[hdr.index(k)].replace(",", "")) * scale
     except Exception: return float("nan")
 def unit(k): return units[hdr.index(k)]
-fam = {"node_calc_kernel": "calc_diff", "node_diff_kernel": "calc_diff", "backward_kernel": "backward", "rollout_kernel": "rollout", "decide_kernel": "decide"}
+fam = {"node_calc_kernel": "calc_diff", "node_cost_kernel": "calc_diff", "node_diff_kernel": "calc_diff", "backward_kernel": "backward", "rollout_kernel": "rollout", "decide_kernel": "decide"}
 seen = {}; lines = []; traffic = {}
 for r in rows[2:]:
     name = r[hdr.index("Kernel Name")]
