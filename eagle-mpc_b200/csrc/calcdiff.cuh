@@ -54,10 +54,10 @@ EMPC_DI size_t pk_index(size_t n, int f) { return (n / Pk<D>::GROUP) * (size_t)(
 // window together instead of each thrashing the instruction cache at its own program counter.  Barriers need every thread,
 // so threads without a node to process do not return: they shadow a valid node with their stores switched off.
 #ifndef EMPC_NC_THREADS
-#define EMPC_NC_THREADS 256
+#define EMPC_NC_THREADS 128
 #endif
 #ifndef EMPC_NC_BLOCKS
-#define EMPC_NC_BLOCKS 2
+#define EMPC_NC_BLOCKS 3
 #endif
 constexpr int NC_THREADS = EMPC_NC_THREADS;
 #define EMPC_NC_PHASE() __syncthreads()
