@@ -436,6 +436,16 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
       for (int e = tid; e < P::SIZE * P::GROUP; e += W::THREADS) cp_async8(dst + e / P::GROUP, src + e);
     }
     cp_async_commit();
+    // Blocks are dispatched in index order, 4 per SM: the block that will run on this SM slot after this one is about
+    // PF_AHEAD groups further on.  Pull its packet from HBM into L2 now, so that its own load above hits L2.
+    {
+      constexpr int PF_AHEAD = 148 * 4;
+      constexpr int LINES = (P::SIZE * P::GROUP * 8 + 127) / 128;
+      if (blockIdx.x + PF_AHEAD < gridDim.x) {
+        const char* nxt = reinterpret_cast<const char*>(src + (size_t)PF_AHEAD * (P::SIZE * P::GROUP));
+        for (int ln = tid; ln < LINES; ln += W::THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)ln * 128));
+      }
+    }
     cp_async_wait<0>();
   }
   __syncthreads();
