@@ -687,19 +687,28 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
     double* Fu = tile + D::oFu;
     const double* Minv = wk + W::wMinv;
     __syncwarp(hm);
-    for (int j = l; j < NU; j += W::LANES) {
+    static_assert(NU <= W::LANES, "one lane per control");
+    if (l < NU) {
+      const int j = l;
       const double dsj = pk[P::oDS + j];
+      // column j of d tau / d u = (thrust map | identity) diag(ds): the same NV-term product for every lane, no
+      // divergence between rotor and arm columns (the zero terms add exactly)
+      double acol[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acol[k] = 0.0;
+      if (j < NR) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acol[k] = M.tau_f[k * NR + j] * dsj;
+      } else {
+#pragma unroll
+        for (int k = 6; k < NV; ++k) acol[k] = (k == 6 + (j - NR)) ? dsj : 0.0;
+      }
       double top[6];
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        double s;
-        if (j < NR) {
-          s = 0;
+        double s = 0;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) s += Minv[i * NV + k] * (M.tau_f[k * NR + j] * dsj);
-        } else {
-          s = Minv[i * NV + 6 + (j - NR)] * dsj;
-        }
+        for (int k = 0; k < NV; ++k) s += Minv[i * NV + k] * acol[k];
         if (i < 6) top[i] = dt2 * s; else Fu[i * NU + j] = dt2 * s;
         Fu[(NV + i) * NU + j] = dt * s;
       }
