@@ -1,0 +1,80 @@
+#!/usr/bin/env python3
+"""BASELINE.json config 5: iris_px4 Rail / Weighted MPC, horizon sweep, B batched warm-started instances.
+
+For every controller and every `knots` value: one MPC problem (cost tables retargeted by the host-side controller at time
+t0), B instances that differ in their initial state (trajectory state at t0 + the benchmark's noise recipe, seeds 9000+b),
+warm-started from the trajectory slice, `iters` SbFDDP iterations each (mpc.yaml: 2).  Prints one JSON line per case.
+Not a bench.py line (bench.py measures config 2); evidence for profiles/.
+"""
+import argparse, importlib, json, os, sys, tempfile, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+host = importlib.import_module("eagle-mpc_b200.host")
+capi = importlib.import_module("eagle-mpc_b200.capi")
+mpcmod = importlib.import_module("eagle-mpc_b200.mpc")
+wl = importlib.import_module("eagle-mpc_b200.workloads")
+
+TRAJ = "iris_px4/trajectories/displacement.yaml"
+MPC_YAML = os.path.join(ROOT, "yaml", "iris_px4", "mpc", "mpc.yaml")
+
+
+def yaml_with_knots(knots, tmpdir):
+    txt = open(MPC_YAML).read().replace("knots: 40", f"knots: {knots}")
+    p = os.path.join(tmpdir, f"mpc_{knots}.yaml")
+    open(p, "w").write(txt)
+    return p
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--knots", type=int, nargs="+", default=[50, 100, 200, 400])
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--t0", type=int, default=1000, help="controller time (ms) at which the instances are solved")
+    args = ap.parse_args()
+    # reference trajectory: iris_px4 displacement solved by the B200 path itself (B = 1, maxiter 400)
+    tr = host.Trajectory(TRAJ)
+    fp = tr.createProblem(20)
+    s1 = capi.BatchSolver(fp, 1)
+    p = capi.default_params(); p.maxiter = 400
+    s1.set_params(p); s1.set_x0(fp.x0); s1.set_candidate(None, None, False); s1.solve()
+    xs, us = s1.xs()[0], s1.us()[0]
+    s1.close()
+    tmpdir = tempfile.mkdtemp()
+    B = args.batch
+    for kind in ("rail", "weighted"):
+        for knots in args.knots:
+            y = yaml_with_knots(knots, tmpdir)
+            mpc = (mpcmod.RailMpc(xs, 20, y, create_solver=False) if kind == "rail"
+                   else mpcmod.WeightedMpc(host.Trajectory(TRAJ), 20, y, create_solver=False))
+            mpc.updateProblem(args.t0)
+            T = mpc.knots - 1
+            i0 = args.t0 // 20
+            idx = np.minimum(i0 + np.arange(T + 1), len(xs) - 1)
+            xs_w = xs[idx]
+            us_w = us[np.minimum(idx[:-1], len(us) - 1)]
+            x0 = wl.noisy_x0(xs[i0], B, 9000)
+            g = capi.BatchSolver(mpc, B)
+            costs, pool = mpc.cost_tables()
+            g.update_costs(0, costs, 0, pool)
+            pr = capi.default_params(); pr.maxiter = mpc.iters; pr.convergence_init = 1e-3
+            g.set_params(pr)
+            xs_b = np.broadcast_to(xs_w, (B,) + xs_w.shape).copy()
+            xs_b[:, 0] = x0
+            us_b = np.broadcast_to(us_w, (B,) + us_w.shape).copy()
+            g.set_x0(x0); g.set_candidate(xs_b, us_b, False)
+            g.solve()  # warm-up
+            t_tot, it_tot = 0.0, 0
+            for _ in range(args.steps):
+                g.reset()
+                t1 = time.perf_counter(); g.solve(); t_tot += time.perf_counter() - t1
+                it_tot += g.total_iterations()
+            print(json.dumps({"controller": kind, "knots": knots, "T": T, "batch": B, "iters_per_instance": it_tot / args.steps / B,
+                              "ms_per_batched_mpc_step": 1e3 * t_tot / args.steps, "ocp_iterations_per_s": it_tot / t_tot,
+                              "us_per_instance_step": 1e6 * t_tot / args.steps / B}))
+            g.close()
+
+
+if __name__ == "__main__":
+    main()

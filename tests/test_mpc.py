@@ -1,4 +1,5 @@
 """CarrotMpc: host-side retargeting (CPU) and closed-loop parity GPU vs oracle (GPU)."""
+import ctypes as C
 import importlib
 
 import numpy as np
@@ -168,3 +169,36 @@ def test_weighted_closed_loop_gpu_vs_oracle():
     _tr, fp, xs, us = _iris_solution()
     g, o = _closed_loop_pair(lambda s: mpcmod.WeightedMpc(host.Trajectory(IRIS_TRAJ), 20, IRIS_MPC, create_solver=s), xs, us, 30)
     print("weighted p50 latency gpu %.3f ms, oracle %.3f ms" % (g, o))
+
+
+@pytest.mark.gpu
+def test_batched_rail_instances_match_oracle():
+    """Config 5 shape: one retargeted RailMpc problem, several warm-started instances with different initial states."""
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    wl = importlib.import_module("eagle-mpc_b200.workloads")
+    _tr, fp, xs, us = _iris_solution()
+    mpc = mpcmod.RailMpc(xs, 20, IRIS_MPC, create_solver=False)
+    t0 = 1000
+    mpc.updateProblem(t0)
+    T, i0, B = mpc.knots - 1, t0 // 20, 5
+    x0 = wl.noisy_x0(xs[i0], B, 9000)
+    xs_w, us_w = xs[i0:i0 + T + 1], us[i0:i0 + T]
+    g = capi.BatchSolver(mpc, B)
+    costs, pool = mpc.cost_tables()
+    g.update_costs(0, costs, 0, pool)
+    pg = capi.default_params(); pg.maxiter = mpc.iters; pg.convergence_init = 1e-3
+    g.set_params(pg)
+    xs_b = np.broadcast_to(xs_w, (B,) + xs_w.shape).copy(); xs_b[:, 0] = x0
+    us_b = np.broadcast_to(us_w, (B,) + us_w.shape).copy()
+    g.set_x0(x0); g.set_candidate(xs_b, us_b, False); g.solve()
+    gx, gu, gc, gi = g.xs(), g.us(), g.cost(), g.iters()
+    po = ob.default_params(); po.maxiter = mpc.iters; po.convergence_init = 1e-3
+    for b in range(B):
+        o = ob.Oracle(mpc); o.set_params(po)
+        ob.lib.orc_update_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Cost), C.c_int, C.c_int, abi.c_double_p]
+        ob.lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), ob.dp(pool))
+        o.set_x0(x0[b]); o.solve(xs_b[b], us_b[b])
+        assert int(o.get("iter")) == gi[b]
+        assert abs(gc[b] - o.get("cost")) <= 1e-9 * max(1.0, abs(o.get("cost")))
+        assert np.abs(gx[b] - o.get("xs")).max() <= 1e-9 * max(1.0, np.abs(o.get("xs")).max())
+        assert np.abs(gu[b] - o.get("us")).max() <= 1e-9 * max(1.0, np.abs(o.get("us")).max())
