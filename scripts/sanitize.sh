@@ -1,0 +1,25 @@
+#!/bin/bash
+# compute-sanitizer passes over a small solve of every robot family (memcheck, racecheck, synccheck)
+mkdir -p gpurun_out
+cat > /tmp/san_case.py <<'PY'
+import importlib, sys, numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import synth
+capi = importlib.import_module("eagle-mpc_b200.capi")
+for na, nr in ((3, 6), (0, 4), (5, 6)):
+    h = synth.make_problem(seed=20 + na, na=na, n_rotors=nr, T=12, all_costs=True)
+    B = 5
+    rng = np.random.default_rng(5)
+    x0 = np.zeros((B, h.nx)); x0[:, 6] = 1
+    x0[:, :3] = rng.uniform(-0.3, 0.3, size=(B, 3))
+    g = capi.BatchSolver(h, B)
+    p = capi.default_params(); p.maxiter = 4
+    g.set_params(p); g.set_x0(x0); g.set_candidate(None, None, False); g.solve()
+    g.phase_calc_diff(0.1); g.phase_backward(1e-6, False); g.phase_rollout(0.1, False, False)
+    print("ok", na, nr, g.iters().tolist())
+    g.close()
+PY
+for tool in memcheck racecheck synccheck; do
+  echo "== $tool"
+  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san_case.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^ok|Error|error|hazard" | head -12
+done
