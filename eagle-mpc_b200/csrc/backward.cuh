@@ -14,8 +14,11 @@
 // warp-instructions and needs two 8-byte fragment loads instead of ~7 (measured: the FP64 tensor rate equals the vector
 // rate on B200, so the gain is issue slots and shared-memory bandwidth, not FLOPs; profiles/r1_baseline.md).
 // Leading dimensions are chosen per operand role so that every fragment load is bank-conflict free:
-//   LDB = 24  (= 8 mod 16)  operands read as B (k x n, row k) or as transposed A:   Fx, Fu, V', K
-//   LDA = 20  (= 4 mod 16)  operands read as row-major A (row i, 4 consecutive k):   FxTV, FuTV, Qxu
+//   LDB = 24 / LDF = 40  (= 8 mod 16)  operands read as B (row k) or as transposed A:   [Fx | Fu] (packed), V', K
+//   LDA = 20  (= 4 mod 16)  operands read as row-major A (row i, 4 consecutive k):   F^T V, Qxu
+// Fx and Fu are packed side by side, so that F^T V = [FxTV ; FuTV] and the symmetric [[Qxx, Qxu], [Qux, Quu]] =
+// (F^T V) F each take one k-loop and only the upper tiles of the latter are computed: 128 DMMAs per node instead of
+// 197 for the six separate padded products.
 // Everything else (Cholesky of Quu, triangular solves, vector updates, ordered reductions) is warp-cooperative out of
 // shared memory with __syncwarp only: no block-level barrier anywhere on the sweep.  The next node's Fx / Fu arrive by
 // cp.async while the current node is being factorised; its cost blocks are prefetched into registers.
@@ -28,27 +31,30 @@ struct BwCfg {
   static constexpr int KN = (n + 3) / 4, KM = (m + 3) / 4;      // 4-deep k-steps over n, m
   static constexpr int NP = 8 * NT, MP = 8 * MT, KNP = 4 * KN, KMP = 4 * KM;
   static constexpr int LDB = 24;
+  // packed operand F = [Fx | Fu] (n x (n + m)): one product F^T V gives FxTV and FuTV, one product (F^T V) F gives the
+  // whole symmetric matrix [[Qxx, Qxu], [Qux, Quu]], of which only the upper tiles are computed
+  static constexpr int PW = n + m, PT = (PW + 7) / 8, PP = 8 * PT;
+  static constexpr int LDF = (PP <= 24) ? 24 : 40;               // = 8 mod 16, >= PP
+  static_assert(PP <= LDF, "packed operand wider than its leading dimension");
   static constexpr int lda_for(int k) { return k <= 20 ? 20 : 36; }
-  static constexpr int LDA = lda_for(KNP);                       // FxTV, FuTV
+  static constexpr int LDA = lda_for(KNP);                       // F^T V (row-major A operand)
   static constexpr int LDQ = 20;                                 // Qxu (k extent KMP <= 16)
   static_assert(NP <= LDB && MP <= LDB && KMP <= LDQ, "operand wider than its leading dimension");
   static constexpr int ROWS_K = (KNP > NP ? KNP : NP);
-  static constexpr int oFx = 0;                                  // KNP x LDB
-  static constexpr int oFu = oFx + KNP * LDB;                    // KNP x LDB
-  static constexpr int oV = oFu + KNP * LDB;                     // ROWS_K x LDB   Vxx' (symmetric)
+  static constexpr int oF = 0;                                   // KNP x LDF      [Fx | Fu]
+  static constexpr int oV = oF + KNP * LDF;                      // ROWS_K x LDB   Vxx' (symmetric)
   // (Qxx never touches shared memory: Lxx is loaded from HBM straight into the accumulator fragments and
   //  Qxx - Qxu K is symmetrised in registers)
   static constexpr int oQxu = oV + ROWS_K * LDB;                 // NP x LDQ       Qxu
-  static constexpr int oQuu = oQxu + NP * LDQ;                   // MP x LDQ       Luu -> Quu
-  static constexpr int oFxTV = oQuu + MP * LDQ;                  // NP x LDA
-  static constexpr int oFuTV = oFxTV + NP * LDA;                 // MP x LDA
-  static constexpr int oK = oFuTV + MP * LDA;                    // KMP x LDB      gains K (m x n), zero padded
-  // the Cholesky factor lives in the FxTV area, which is dead once Qxx and Qxu are formed
-  static constexpr int oL = oFxTV;                               // m x m Cholesky factor of Quu, then m reciprocal pivots
-  static_assert(m * m + m <= NP * LDA, "L does not fit the FxTV area");
+  static constexpr int oQuu = oQxu + NP * LDQ;                   // MP x LDQ       Quu
+  static constexpr int oFTV = oQuu + MP * LDQ;                   // PP x LDA       F^T V = [FxTV ; FuTV]
+  static constexpr int oK = oFTV + PP * LDA;                     // KMP x LDB      gains K (m x n), zero padded
+  // the Cholesky factor lives in the F^T V area, which is dead once the Q blocks are formed
+  static constexpr int oL = oFTV;                                // m x m Cholesky factor of Quu, then m reciprocal pivots
+  static_assert(m * m + m <= PP * LDA, "L does not fit the F^T V area");
   static constexpr int oVec = oK + KMP * LDB;
   static constexpr int vQx = 0, vQu = vQx + NP, vVx = vQu + MP, vFs = vVx + NP, vG = vFs + NP, vKv = vG + NP,
-                       vQuuk = vKv + MP, vTmp = vQuuk + MP, VEC = vTmp + NP;
+                       vQuuk = vKv + MP, vTmp = vQuuk + MP, vLuu = vTmp + NP, VEC = vLuu + MP;
   static constexpr int TOTAL0 = oVec + VEC;
   static constexpr int TOTAL = TOTAL0 + (TOTAL0 & 1);
   // register prefetch (one node ahead) of the small cost blocks: diag(Luu) (m), Lx | Lu (n + m, contiguous) + fs.  Lxu is
@@ -58,7 +64,7 @@ struct BwCfg {
   static constexpr int LBLK = m + n + m;
   static constexpr int PREF = (LBLK + 31) / 32;
 #ifndef EMPC_BW_WARPS_PER_SM
-#define EMPC_BW_WARPS_PER_SM 7
+#define EMPC_BW_WARPS_PER_SM 8
 #endif
 };
 
@@ -157,12 +163,14 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
   }
   const int feasible = st.is_feasible;
 
-  double* sFx = sm + S::oFx; double* sFu = sm + S::oFu; double* sV = sm + S::oV;
-  double* sQxu = sm + S::oQxu; double* sQuu = sm + S::oQuu; double* sFxTV = sm + S::oFxTV; double* sFuTV = sm + S::oFuTV;
+  constexpr int LDF = S::LDF, PW = S::PW;
+  double* sF = sm + S::oF; double* sV = sm + S::oV;
+  double* sQxu = sm + S::oQxu; double* sQuu = sm + S::oQuu; double* sFTV = sm + S::oFTV;
   double* sK = sm + S::oK; double* sL = sm + S::oL; double* sLinv = sL + m * m;
   double* vec = sm + S::oVec;
   double* Qx = vec + S::vQx; double* Qu = vec + S::vQu; double* Vxp = vec + S::vVx; double* fsv = vec + S::vFs;
   double* gv = vec + S::vG; double* kv = vec + S::vKv; double* Quuk = vec + S::vQuuk; double* tmpv = vec + S::vTmp;
+  double* Luud = vec + S::vLuu;
 
   // asynchronous fetch of Fx (16-byte pieces, n even) and Fu (8-byte pieces) of node t into their padded layouts
   auto fetch_F = [&](int t) {
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       int i = lane / H, cc = lane - i * H;
 #pragma unroll
       for (int q = 0; q < (n * H + 31) / 32; ++q) {
-        if (lane + 32 * q < n * H) cp_async16(sFx + i * LDB + 2 * cc, tg + D::oFx + 2 * (lane + 32 * q));
+        if (lane + 32 * q < n * H) cp_async16(sF + i * LDF + 2 * cc, tg + D::oFx + 2 * (lane + 32 * q));
         i += DI; cc += DC;
         if (cc >= H) { cc -= H; i += 1; }
       }
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       int i = lane / m, j = lane - i * m;
 #pragma unroll
       for (int q = 0; q < (n * m + 31) / 32; ++q) {
-        if (lane + 32 * q < n * m) cp_async8(sFu + i * LDB + j, tg + D::oFu + lane + 32 * q);
+        if (lane + 32 * q < n * m) cp_async8(sF + i * LDF + n + j, tg + D::oFu + lane + 32 * q);
         i += DI; j += DC;
         if (j >= m) { j -= m; i += 1; }
       }
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
 #pragma unroll
   for (int q = 0; q < S::PREF; ++q) {
     int e = lane + 32 * q, src = 0, dst = 0xffff;
-    if (e < m) { src = (D::oLuu - D::oLxx) + e * (m + 1); dst = S::oQuu + e * LDQ + e; }
+    if (e < m) { src = (D::oLuu - D::oLxx) + e * (m + 1); dst = S::oVec + S::vLuu + e; }
     else if (e < m + n) { const int i = e - m; src = (D::oLx - D::oLxx) + i; dst = S::oVec + S::vQx + i; }
     else if (e < S::LBLK) { const int i = e - m - n; src = (D::oLu - D::oLxx) + i; dst = S::oVec + S::vQu + i; }
     pre_off[q] = ((unsigned)src << 16) | (unsigned)dst;
@@ -207,9 +215,6 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
     pre_fs = (lane < n) ? bf.fs[(nb + t) * n + lane] : 0.0;
   };
   auto store_L = [&](const double (&pre)[S::PREF], double pre_fs) {
-    // Quu's off-diagonal part restarts from zero (Luu is diagonal); Qxu is formed without an initial value
-    for (int e = lane; e < m * m; e += 32) { const int i = e / m; sQuu[i * LDQ + (e - i * m)] = 0.0; }
-    __syncwarp();
 #pragma unroll
     for (int q = 0; q < S::PREF; ++q) { const unsigned d = pre_off[q] & 0xffffu; if (d != 0xffffu) sm[d] = pre[q]; }
     if (lane < n) fsv[lane] = pre_fs;
@@ -256,100 +261,97 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       if (t > 0) load_L(t - 1, pre, pre_fs);
       // Lxx of this node: HBM -> accumulator fragments (row 8 i + fr, columns 8 j + 2 fc, +1); in flight during the
       // first two products
-      double qxx[S::NT][S::NT][2];
+      // (they are the top-left tiles of the packed accumulator q of [[Qxx, Qxu], [Qux, Quu]]; upper tiles only)
+      double q[S::PT][S::PT][2];
       {
         const double* lg = bf.tiles + (nb + t) * D::TILE + D::oLxx;
 #pragma unroll
-        for (int i = 0; i < S::NT; ++i)
+        for (int i = 0; i < S::PT; ++i)
 #pragma unroll
-          for (int j = 0; j < S::NT; ++j) {
+          for (int j = i; j < S::PT; ++j) {
             const int row = 8 * i + fr, col = 8 * j + 2 * fc;
             double2 v = make_double2(0.0, 0.0);
             if (row < n && col < n) v = *reinterpret_cast<const double2*>(lg + row * n + col);
-            qxx[i][j][0] = v.x; qxx[i][j][1] = v.y;
+            q[i][j][0] = v.x; q[i][j][1] = v.y;
           }
       }
-      // ---- FxTV = Fx^T V ; FuTV = Fu^T V   (one k-loop: the V fragments are loaded once for both) ----
+      // ---- F^T V = [FxTV ; FuTV]  (one k-loop over the packed operand) ----
       {
-        double aX[S::NT][S::NT][2], aU[S::MT][S::NT][2];
-        acc_zero(aX); acc_zero(aU);
+        double ftv[S::PT][S::NT][2];
+        acc_zero(ftv);
 #pragma unroll
         for (int ks = 0; ks < S::KN; ++ks) {
-          double fx[S::NT], fu[S::MT], vv[S::NT];
+          double fa[S::PT], vv[S::NT];
 #pragma unroll
-          for (int i = 0; i < S::NT; ++i) { fx[i] = sFx[(4 * ks + fc) * LDB + 8 * i + fr]; vv[i] = sV[(4 * ks + fc) * LDB + 8 * i + fr]; }
+          for (int i = 0; i < S::PT; ++i) fa[i] = sF[(4 * ks + fc) * LDF + 8 * i + fr];
 #pragma unroll
-          for (int i = 0; i < S::MT; ++i) fu[i] = sFu[(4 * ks + fc) * LDB + 8 * i + fr];
+          for (int i = 0; i < S::NT; ++i) vv[i] = sV[(4 * ks + fc) * LDB + 8 * i + fr];
 #pragma unroll
-          for (int i = 0; i < S::NT; ++i)
+          for (int i = 0; i < S::PT; ++i)
 #pragma unroll
-            for (int j = 0; j < S::NT; ++j) dmma884(aX[i][j][0], aX[i][j][1], fx[i], vv[j]);
-#pragma unroll
-          for (int i = 0; i < S::MT; ++i)
-#pragma unroll
-            for (int j = 0; j < S::NT; ++j) dmma884(aU[i][j][0], aU[i][j][1], fu[i], vv[j]);
+            for (int j = 0; j < S::NT; ++j) dmma884(ftv[i][j][0], ftv[i][j][1], fa[i], vv[j]);
         }
-        acc_store(aX, sFxTV, LDA, LDA, fr, fc);
-        acc_store(aU, sFuTV, LDA, LDA, fr, fc);
+        acc_store(ftv, sFTV, LDA, LDA, fr, fc);
       }
-      // Qx += Fx^T Vx' ; Qu += Fu^T Vx'   (lane = output row; three interleaved partial sums cut the dependent chain)
-      {
-        const int i = lane < n ? lane : (lane - n < m ? lane - n : 0);
-        const double* Fm = lane < n ? sFx : sFu;
+      // Qx += Fx^T Vx' ; Qu += Fu^T Vx'   (lane = column of the packed operand; three interleaved partial sums)
+#pragma unroll
+      for (int c0 = 0; c0 < PW; c0 += 32) {
+        const int c = c0 + lane;
+        const int cc = c < PW ? c : 0;
         double s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
         for (int l = 0; l + 2 < n; l += 3) {
-          s0 += Fm[l * LDB + i] * Vxp[l]; s1 += Fm[(l + 1) * LDB + i] * Vxp[l + 1]; s2 += Fm[(l + 2) * LDB + i] * Vxp[l + 2];
+          s0 += sF[l * LDF + cc] * Vxp[l]; s1 += sF[(l + 1) * LDF + cc] * Vxp[l + 1]; s2 += sF[(l + 2) * LDF + cc] * Vxp[l + 2];
         }
 #pragma unroll
-        for (int l = n - n % 3; l < n; ++l) s0 += Fm[l * LDB + i] * Vxp[l];
+        for (int l = n - n % 3; l < n; ++l) s0 += sF[l * LDF + cc] * Vxp[l];
         const double sacc = (s0 + s1) + s2;
-        if (lane < n) Qx[lane] += sacc;
-        else if (lane - n < m) Qu[lane - n] += sacc;
-      }
-      if (n + m > 32) {  // rows of Qu that did not fit beside Qx in the warp
-        const int i = lane + 32 - n;
-        if (i < m) {
-          double sacc = 0;
-#pragma unroll 6
-          for (int l = 0; l < n; ++l) sacc += sFu[l * LDB + i] * Vxp[l];
-          Qu[i] += sacc;
-        }
+        if (c < n) Qx[c] += sacc;
+        else if (c < PW) Qu[c - n] += sacc;
       }
       __syncwarp();
-      // ---- Qxx = Lxx + FxTV Fx ; Qxu = FxTV Fu ; Quu = Luu + FuTV Fu   (one k-loop, every fragment loaded once).
-      // Qxx stays in registers until Qxu K has been subtracted from it. ----
+      // ---- [[Qxx, Qxu], [., Quu]] = [[Lxx, 0], [0, Luu + ureg I]] + (F^T V) F, upper tiles of the packed symmetric matrix.
+      // Qxx (the top-left tiles) stays in registers until Qxu K has been subtracted from it; Qxu and Quu go to shared memory. ----
       {
-        double qxu[S::NT][S::MT][2], quu[S::MT][S::MT][2];
-        acc_zero(qxu);  // Lxu == 0
-        acc_load(quu, sQuu, LDQ, fr, fc);
+#pragma unroll
+        for (int i = 0; i < S::PT; ++i)
+#pragma unroll
+          for (int j = i; j < S::PT; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int row = 8 * i + fr, col = 8 * j + 2 * fc + h;
+              if (row == col && row >= n && row < PW) q[i][j][h] = Luud[row - n] + xreg;
+            }
 #pragma unroll
         for (int ks = 0; ks < S::KN; ++ks) {
-          double ax[S::NT], au[S::MT], bx[S::NT], bu[S::MT];
+          double fa[S::PT], fb[S::PT];
 #pragma unroll
-          for (int i = 0; i < S::NT; ++i) { ax[i] = sFxTV[(8 * i + fr) * LDA + 4 * ks + fc]; bx[i] = sFx[(4 * ks + fc) * LDB + 8 * i + fr]; }
+          for (int i = 0; i < S::PT; ++i) { fa[i] = sFTV[(8 * i + fr) * LDA + 4 * ks + fc]; fb[i] = sF[(4 * ks + fc) * LDF + 8 * i + fr]; }
 #pragma unroll
-          for (int i = 0; i < S::MT; ++i) { au[i] = sFuTV[(8 * i + fr) * LDA + 4 * ks + fc]; bu[i] = sFu[(4 * ks + fc) * LDB + 8 * i + fr]; }
+          for (int i = 0; i < S::PT; ++i)
 #pragma unroll
-          for (int i = 0; i < S::NT; ++i) {
-#pragma unroll
-            for (int j = i; j < S::NT; ++j) dmma884(qxx[i][j][0], qxx[i][j][1], ax[i], bx[j]);  // upper tiles: Qxx is symmetric
-#pragma unroll
-            for (int j = 0; j < S::MT; ++j) dmma884(qxu[i][j][0], qxu[i][j][1], ax[i], bu[j]);
-          }
-#pragma unroll
-          for (int i = 0; i < S::MT; ++i)
-#pragma unroll
-            for (int j = 0; j < S::MT; ++j) dmma884(quu[i][j][0], quu[i][j][1], au[i], bu[j]);
+            for (int j = i; j < S::PT; ++j) dmma884(q[i][j][0], q[i][j][1], fa[i], fb[j]);
         }
-        acc_store(qxu, sQxu, LDQ, LDQ, fr, fc);
-        acc_store(quu, sQuu, LDQ, LDQ, fr, fc);
+        __syncwarp();  // every lane is done reading F^T V before the Quu factor (same storage) is written further down
+#pragma unroll
+        for (int i = 0; i < S::PT; ++i)
+#pragma unroll
+          for (int j = i; j < S::PT; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int row = 8 * i + fr, col = 8 * j + 2 * fc + h;
+              if (col >= n && col < PW) {
+                if (row < n) sQxu[row * LDQ + (col - n)] = q[i][j][h];
+                else if (row < PW) {
+                  sQuu[(row - n) * LDQ + (col - n)] = q[i][j][h];
+                  if (i != j) sQuu[(col - n) * LDQ + (row - n)] = q[i][j][h];  // the lower tiles are not computed: mirror
+                }
+              }
+            }
       }
       __syncwarp();
       // Fx, Fu of this node are dead: start fetching the next node's while Quu is factorised
       if (t > 0) fetch_F(t - 1);
-      if (lane < m) sQuu[lane * LDQ + lane] += xreg;
-      __syncwarp();
       // ---- Cholesky of Quu (lane = row, left-looking: the reference LLT's subtraction order) ----
       int bad = 0;
       {
@@ -424,7 +426,8 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       }
       // ---- Vxx = sym(Qxx - Qxu K) + xreg I, all in the accumulator registers.  Qxx and Qxu K are symmetric up to
       // rounding, so only the upper tiles (j >= i) are computed: diagonal tiles are averaged with their own transpose
-      // (the reference's 0.5 (Vxx + Vxx^T)), the lower tiles are the mirror images of the upper ones. ----
+      // (the reference's 0.5 (Vxx + Vxx^T)), the lower tiles are the mirror images of the upper ones.  Entries of the
+      // top-left tiles beyond row / column n belong to Qxu / Quu and are masked: V's padding has to stay zero. ----
 #pragma unroll
       for (int ks = 0; ks < S::KM; ++ks) {
         double a[S::NT], bq[S::NT];
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
 #pragma unroll
         for (int i = 0; i < S::NT; ++i)
 #pragma unroll
-          for (int j = i; j < S::NT; ++j) dmma884(qxx[i][j][0], qxx[i][j][1], a[i], bq[j]);
+          for (int j = i; j < S::NT; ++j) dmma884(q[i][j][0], q[i][j][1], a[i], bq[j]);
       }
       {
         // the mirror image of this lane's pair (row fr, columns 2 fc + h) of tile (i, j) is element (2 fc + h, fr) of
@@ -446,20 +449,25 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
 #pragma unroll
           for (int j = i; j < S::NT; ++j) {
             // transposed element of the upper tile (i, j), as seen from this lane
-            const double a0 = __shfl_sync(0xffffffffu, qxx[i][j][0], src0), a1 = __shfl_sync(0xffffffffu, qxx[i][j][1], src0);
-            const double b0 = __shfl_sync(0xffffffffu, qxx[i][j][0], src1), b1 = __shfl_sync(0xffffffffu, qxx[i][j][1], src1);
+            const double a0 = __shfl_sync(0xffffffffu, q[i][j][0], src0), a1 = __shfl_sync(0xffffffffu, q[i][j][1], src0);
+            const double b0 = __shfl_sync(0xffffffffu, q[i][j][0], src1), b1 = __shfl_sync(0xffffffffu, q[i][j][1], src1);
             const double t0 = odd ? a1 : a0, t1 = odd ? b1 : b0;
+            const int row = 8 * i + fr, col = 8 * j + 2 * fc;   // this lane's entries of tile (i, j): (row, col), (row, col + 1)
+            const int rowT = 8 * j + fr, colT = 8 * i + 2 * fc;  // ... and of the mirrored tile (j, i)
             if (i == j) {
-              double v0 = 0.5 * (qxx[i][i][0] + t0), v1 = 0.5 * (qxx[i][i][1] + t1);
-              const int row = 8 * i + fr, col = 8 * i + 2 * fc;
-              if (row == col && row < n) v0 += xreg;
-              if (row == col + 1 && row < n) v1 += xreg;
+              double v0 = 0.5 * (q[i][i][0] + t0), v1 = 0.5 * (q[i][i][1] + t1);
+              if (row == col) v0 += xreg;
+              if (row == col + 1) v1 += xreg;
+              if (row >= n || col >= n) v0 = 0.0;
+              if (row >= n || col + 1 >= n) v1 = 0.0;
               if (isnan(v0) || isnan(v1)) bad = 1;  // "backward_error"
               vsym[i][i][0] = v0; vsym[i][i][1] = v1;
             } else {
-              if (isnan(qxx[i][j][0]) || isnan(qxx[i][j][1])) bad = 1;
-              vsym[i][j][0] = qxx[i][j][0]; vsym[i][j][1] = qxx[i][j][1];
-              vsym[j][i][0] = t0; vsym[j][i][1] = t1;
+              const double u0 = (row < n && col < n) ? q[i][j][0] : 0.0, u1 = (row < n && col + 1 < n) ? q[i][j][1] : 0.0;
+              if (isnan(u0) || isnan(u1)) bad = 1;
+              vsym[i][j][0] = u0; vsym[i][j][1] = u1;
+              vsym[j][i][0] = (rowT < n && colT < n) ? t0 : 0.0;
+              vsym[j][i][1] = (rowT < n && colT + 1 < n) ? t1 : 0.0;
             }
           }
         acc_store(vsym, sV, LDB, LDB, fr, fc);
