@@ -11,7 +11,7 @@ for l in open(src):
     m = re.match(r'\s*\.text\.(\S+):', l)
     if m: cur = m.group(1); bufs[cur] = []; continue
     if cur and re.match(r'\s+/\*[0-9a-f]{4,}\*/', l): bufs[cur].append(l.rstrip())
-want = {"node_calc_kernel": "node_calc", "node_diff_kernel": "node_diff", "backward_kernel": "backward",
+want = {"node_calc_kernel": "node_calc", "node_cost_kernel": "node_cost", "node_diff_kernel": "node_diff", "backward_kernel": "backward",
         "rollout_kernelINS_3DimILi3ELi6EEELi4": "rollout_w4", "decide_kernel": "decide"}
 summary = []
 for name, lines in bufs.items():
