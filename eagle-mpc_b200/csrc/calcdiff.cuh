@@ -378,11 +378,20 @@ __global__ void __launch_bounds__(128, 4) node_cost_kernel(Buffers bf, int force
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Kernel B: column-parallel part, 16 lanes per node, 8 nodes per block.
+// Kernel B: column-parallel part, DiffCfg::LANES lanes per node, 8 nodes per block.
 template <class D>
 struct DiffCfg {
   static constexpr int NJ = D::NJ, NV = D::NV, NDX = D::NDX, NU = D::NU, NA = D::NA;
-  static constexpr int NODES = Pk<D>::GROUP, LANES = 16, THREADS = NODES * LANES;
+  // LANES lanes work on one node (one lane per column of the NV x NV matrices); a node never straddles a warp, so the
+  // hand-overs between the phases are __syncwarp's over the node's lanes.  10 lanes/node puts 3 nodes of the nv=9
+  // flying arm into a warp instead of 2.
+#ifdef EMPC_ND_LANES
+  static constexpr int LANES = EMPC_ND_LANES;
+#else
+  static constexpr int LANES = (NV <= 8 && NU <= 8) ? 8 : (NV <= 10 && NU <= 10) ? 10 : 16;
+#endif
+  static_assert(NV <= LANES && NU <= LANES, "one lane per column");
+  static constexpr int NODES = Pk<D>::GROUP, NPW = 32 / LANES, WARPS = (NODES + NPW - 1) / NPW, THREADS = 32 * WARPS;
   // per-node work area (doubles)
   static constexpr int wJc = 0;                          // NV x 6   world motion axes
   static constexpr int wYJa = wJc + 6 * NV;              // NA x 6   Ycrb_j J_j of the arm joints
@@ -450,8 +459,10 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
   }
   __syncthreads();
 
-  const int node = tid / W::LANES, l = tid % W::LANES;
-  const unsigned hm = 0xFFFFu << (16 * ((tid & 31) >> 4));  // the half-warp working on this node
+  const int slot = (tid & 31) / W::LANES, l = (tid & 31) - slot * W::LANES;
+  const int node = (tid >> 5) * W::NPW + slot;
+  if (slot >= W::NPW || node >= W::NODES) return;
+  const unsigned hm = (0xFFFFFFFFu >> (32 - W::LANES)) << (W::LANES * slot);  // the lanes working on this node
   const size_t n = nbase + node;
   if (n < n_first || n >= n_end) return;
   const int b = (int)(n / T1), t = (int)(n - (size_t)b * T1);
