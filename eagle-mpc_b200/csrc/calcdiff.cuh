@@ -14,8 +14,8 @@
 //                                        node (world placements / velocities / accelerations, composite-rigid-body
 //                                        sweep, squashing slopes, Lie transport blocks)
 //   node_cost_kernel  thread per node   cost value + state/control cost derivative summaries (rest of the packet)
-//   node_diff_kernel  16 lanes per node  column-parallel part out of shared memory; writes the node tile
-//                                        Fx|Fu|Lxx|Lxu|Luu|Lx|Lu with contiguous half-warp stores.
+//   node_diff_kernel  8/10/16 lanes per node  column-parallel part out of shared memory; writes the node tile
+//                                        Fx|Fu|Lxx|Lxu|Luu|Lx|Lu.
 // The packet is stored AoSoA in groups of 8 nodes ([group][field][8]): the producer's warp (32 consecutive nodes) writes
 // full 64-byte runs per field, and the consumer's block (8 nodes) reads one contiguous chunk.
 #pragma once
@@ -399,22 +399,25 @@ struct DiffCfg {
   static constexpr int wDq = wBtJa + 3 * (NA > 0 ? NA : 1);   // NV x NV  d tau/dq  -> a_q
   static constexpr int wDv = wDq + NV * NV;              // NV x NV  d tau/dv  -> a_v
   static constexpr int wMm = wDv + NV * NV;              // NV x NV  joint-space inertia -> its Cholesky factor
-  static constexpr int wMinv = wMm + NV * NV;            // NV x NV
-  static constexpr int wLxx = wDq;                       // NDX x NDX cost Hessian accumulator (frame costs only), aliases Dq|Dv|Mm|Minv
-  static constexpr int wLinv = wMinv + NV * NV;          // NV       reciprocal Cholesky pivots
-  static constexpr int wFJ = wLinv + NV;                 // 6 x NV   LOCAL frame Jacobian of one frame cost
-  static constexpr int wVec = wFJ + 6 * NV;              // Lx accumulator (NDX)
-  static constexpr int WORK0 = wVec + NDX;
-  static constexpr int WORK = WORK0 | 1;
-  // the residual Jacobian of a frame cost (6 x NDX) reuses the packet's composite area, dead after phase B2
+  static constexpr int wLinv = wMm + NV * NV;            // NV       reciprocal Cholesky pivots
+  // M^-1 (NV x NV) and, later, the residual Jacobian of a frame cost (6 x NDX) live in the packet's composite area,
+  // which is dead after phase B2; short arms whose composite area is too small get them in the work area instead
+  static constexpr int MINV_IN_PACKET = (NV * NV <= Pk<D>::COMP * NJ) ? 1 : 0;
   static constexpr int RX_IN_PACKET = (6 * NDX <= Pk<D>::COMP * NJ) ? 1 : 0;
-  static constexpr int wRx = WORK;                       // used when the composite area is too small (short arms)
-  static constexpr int WORK_TOTAL = WORK + (RX_IN_PACKET ? 0 : 6 * NDX + 1);
+  static constexpr int wMinv = wLinv + NV;
+  static constexpr int wRx = wMinv + (MINV_IN_PACKET ? 0 : NV * NV);
+  static constexpr int WORK0 = wRx + (RX_IN_PACKET ? 0 : 6 * NDX);
+  static constexpr int WORK_TOTAL = WORK0 | 1;
+  // frame costs only (phase B7, when a_q and a_v are dead): LOCAL frame Jacobian 6 x NV and the Lx accumulator (NDX)
+  static constexpr int wFJ = wDq, wVec = wDv;
+  static_assert(6 * NV <= NV * NV && NDX <= NV * NV, "frame-cost scratch fits the a_q / a_v areas");
+  // resident blocks per SM the kernel is built for (shared memory: 5 x 43.4 KB for the 3-joint flying arm)
+  static constexpr int MINB = THREADS <= 96 ? 5 : 4;
   static constexpr int SMEM_DOUBLES = NODES * (Pk<D>::STRIDE + WORK_TOTAL);
 };
 
 template <class D>
-__global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
+__global__ void __launch_bounds__(DiffCfg<D>::THREADS, DiffCfg<D>::MINB) node_diff_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
   constexpr int NJ = D::NJ, NV = D::NV, NDX = D::NDX, NU = D::NU, NR = D::NR;
   using P = Pk<D>;
   using W = DiffCfg<D>;
@@ -445,10 +448,10 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
       for (int e = tid; e < P::SIZE * P::GROUP; e += W::THREADS) cp_async8(dst + e / P::GROUP, src + e);
     }
     cp_async_commit();
-    // Blocks are dispatched in index order, 4 per SM: the block that will run on this SM slot after this one is about
-    // PF_AHEAD groups further on.  Pull its packet from HBM into L2 now, so that its own load above hits L2.
+    // Blocks are dispatched in index order, MINB per SM: the block that will run on this SM slot after this one is
+    // about PF_AHEAD groups further on.  Pull its packet from HBM into L2 now, so that its own load above hits L2.
     {
-      constexpr int PF_AHEAD = 148 * 4;
+      constexpr int PF_AHEAD = 148 * W::MINB;
       constexpr int LINES = (P::SIZE * P::GROUP * 8 + 127) / 128;
       if (blockIdx.x + PF_AHEAD < gridDim.x) {
         const char* nxt = reinterpret_cast<const char*>(src + (size_t)PF_AHEAD * (P::SIZE * P::GROUP));
@@ -587,6 +590,7 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
   }
   __syncwarp(hm);
 
+  double* Minv = W::MINV_IN_PACKET ? const_cast<double*>(pk) + P::oCOMP : wk + W::wMinv;
   // ---- B3: Cholesky of the joint-space inertia in shared memory (lane = row, left-looking, same subtraction order as
   // llt_inplace_inv) and one column of M^-1 per lane ----
   {
@@ -631,7 +635,7 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
     }
     if (l < NV) {
 #pragma unroll
-      for (int r = 0; r < NV; ++r) wk[W::wMinv + r * NV + l] = e[r];
+      for (int r = 0; r < NV; ++r) Minv[r * NV + l] = e[r];
     }
   }
   __syncwarp(hm);
@@ -647,7 +651,7 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
     for (int i = 0; i < NV; ++i) {
       double sq = 0, sv = 0;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) { const double mi = wk[W::wMinv + i * NV + k]; sq += mi * cq[k]; sv += mi * cv[k]; }
+      for (int k = 0; k < NV; ++k) { const double mi = Minv[i * NV + k]; sq += mi * cq[k]; sv += mi * cv[k]; }
       rq[i] = -sq; rv[i] = -sv;
     }
     double* Fx = tile + D::oFx;
@@ -696,7 +700,6 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
   // ---- B6: Fu = [dt^2; dt] M^-1 A diag(ds), rows 0..5 transported; lane = column ----
   {
     double* Fu = tile + D::oFu;
-    const double* Minv = wk + W::wMinv;
     __syncwarp(hm);
     static_assert(NU <= W::LANES, "one lane per control");
     if (l < NU) {
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
       }
     }
   }
-  __syncwarp(hm);  // Minv, a_q, a_v are dead from here on: their area becomes the Lxx accumulator
+  __syncwarp(hm);  // Minv, a_q, a_v are dead from here on: their areas become the frame-cost scratch
 
   // ---- B7: cost derivatives ----
   {
@@ -771,9 +774,12 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
       }
       for (int i = l; i < NDX; i += W::LANES) gLx[i] = pk[P::oLX + i] * dt;
     } else {
-      double* Lxx = wk + W::wLxx;
+      // The dense Lxx of a node with frame costs is accumulated in place in the tile: lane l owns the columns l,
+      // l + LANES, ... from the state-cost initial value to the final scaling, so no hand-over is involved.
+      double* Lxx = gLxx;
       double* Lxv = wk + W::wVec;
-      for (int e = l; e < NDX * NDX; e += W::LANES) { const int i = e / NDX; Lxx[e] = lxx_state(i, e - i * NDX); }
+      for (int j = l; j < NDX; j += W::LANES)
+        for (int i = 0; i < NDX; ++i) Lxx[i * NDX + j] = lxx_state(i, j);
       for (int i = l; i < NDX; i += W::LANES) Lxv[i] = pk[P::oLX + i];
       __syncwarp(hm);
       // frame costs: residual / activation on every lane (serial), Jacobian columns and Hessian entries across lanes
@@ -881,8 +887,8 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, 4) node_diff_kernel(Buffe
         }
         __syncwarp(hm);
       }
-      for (int e2 = l; e2 < NDX * NDX / 2; e2 += W::LANES)
-        reinterpret_cast<double2*>(gLxx)[e2] = make_double2(Lxx[2 * e2] * dt, Lxx[2 * e2 + 1] * dt);
+      for (int j = l; j < NDX; j += W::LANES)
+        for (int i = 0; i < NDX; ++i) Lxx[i * NDX + j] *= dt;
       for (int i = l; i < NDX; i += W::LANES) gLx[i] = Lxv[i] * dt;
       if (l == 0 && !was_dense) bf.node_dense[n] = 1;
     }

@@ -1,7 +1,7 @@
 // kernels.cuh — the four kernel families of the batched SbFDDP iteration (FP64, sm_100a).
 //
 //   node_calc_kernel  thread per (OCP, node): calc + gaps + serial half of calcDiff  (src/sbfddp.cpp:244,332 -> SolverDDP::calcDiff)
-//   node_diff_kernel  16 lanes per (OCP, node): column-parallel half of calcDiff, writes the node tiles
+//   node_diff_kernel  8/10/16 lanes per (OCP, node): column-parallel half of calcDiff, writes the node tiles
 //   backward_kernel   warp per OCP: Riccati sweep, Quu LLT, gains, expected-improvement sums, regularisation retry
 //                                                                              (SolverDDP::backwardPass/computeGains, :245-253)
 //   rollout_kernel    thread per (OCP, step length): all 10 alphas concurrently (SolverFDDP::forwardPass, :416-460)
