@@ -41,6 +41,9 @@ def lib():
             getattr(L, "empc_get_" + name).argtypes = [C.c_void_p, abi.c_double_p]
         for name in ("iters", "feasible"):
             getattr(L, "empc_get_" + name).argtypes = [C.c_void_p, abi.c_int32_p]
+        L.empc_replicate_instances.argtypes = [C.c_void_p, C.c_int32]
+        L.empc_set_reference_trajectory.argtypes = [C.c_void_p, abi.c_double_p, C.c_int32, C.c_int32]
+        L.empc_rail_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
         L.empc_get_total_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.empc_get_launch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), abi.c_double_p]
         L.empc_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
@@ -115,6 +118,22 @@ class BatchSolver:
     def update_node_costsets(self, nc):
         nc = np.ascontiguousarray(nc, dtype=np.int32)
         _ck(lib().empc_update_node_costsets(self.h, abi.as_int32_p(nc)))
+
+    # ---- batched MPC instances (device-side retargeting) ----
+    def replicate_instances(self, n):
+        """private cost tables for n controller instances; OCP b then belongs to instance b % n"""
+        _ck(lib().empc_replicate_instances(self.h, int(n)))
+        self.n_instances = int(n)
+
+    def set_reference_trajectory(self, state_ref, dt_ref_ms):
+        ref = np.ascontiguousarray(state_ref, dtype=np.float64).reshape(-1, self.nx)
+        _ck(lib().empc_set_reference_trajectory(self.h, abi.as_double_p(ref), ref.shape[0], int(dt_ref_ms)))
+
+    def rail_retarget(self, times_ms, dt_node_ms):
+        """RailMpc.updateProblem(times_ms[m]) for every instance m, on the device"""
+        t = np.ascontiguousarray(times_ms, dtype=np.int64)
+        assert t.size == getattr(self, "n_instances", 1)
+        _ck(lib().empc_rail_retarget(self.h, t.ctypes.data_as(C.POINTER(C.c_int64)), int(dt_node_ms)))
 
     # ---- hot path ----
     def solve(self):

@@ -1,0 +1,56 @@
+// retarget.cuh — batched MPC instances: one private copy of the cost tables per instance and device-side retargeting of
+// the rail reference.  The reference retargets one problem on the host before every solve
+// (src/mpc-controllers/rail-mpc.cpp:154-200: a loop over the knots with string-keyed map lookups); with thousands of
+// instances at different controller times that loop becomes the bottleneck, so here a kernel writes the per-node state
+// references of all instances at once.
+#pragma once
+#include "kernels.cuh"
+
+namespace empc {
+
+// n private copies of the (single node map) cost tables: cost records with their pool offsets shifted, the pool, the
+// cost-set boundaries and the node -> cost set map.
+__global__ void replicate_tables_kernel(const empc_cost_t* costs, int n_costs, const double* pool, int n_pool, const int* begin,
+                                        int n_sets, const int* node_set, int T1, int n, empc_cost_t* o_costs, double* o_pool,
+                                        int* o_begin, int* o_node_set) {
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = gridDim.x * (size_t)blockDim.x;
+  for (size_t e = tid; e < (size_t)n * n_costs; e += nth) {
+    const int m = (int)(e / n_costs);
+    empc_cost_t cs = costs[e - (size_t)m * n_costs];
+    const int sh = m * n_pool;
+    if (cs.ref_off >= 0) cs.ref_off += sh;
+    if (cs.w_off >= 0) cs.w_off += sh;
+    if (cs.lb_off >= 0) cs.lb_off += sh;
+    if (cs.ub_off >= 0) cs.ub_off += sh;
+    o_costs[e] = cs;
+  }
+  for (size_t e = tid; e < (size_t)n * n_pool; e += nth) o_pool[e] = pool[e % n_pool];
+  for (size_t e = tid; e < (size_t)n * n_sets; e += nth) { const int m = (int)(e / n_sets); o_begin[e] = begin[e - (size_t)m * n_sets] + m * n_costs; }
+  if (tid == 0) o_begin[(size_t)n * n_sets] = n * n_costs;
+  for (size_t e = tid; e < (size_t)n * T1; e += nth) { const int m = (int)(e / T1); o_node_set[e] = node_set[e - (size_t)m * T1] + m * n_sets; }
+}
+
+// RailMpc::updateProblem for every instance (rail-mpc.cpp:154-200), thread per (instance, knot): node_time = time_m +
+// i dt; idx_state = upper_bound(t_ref, node_time) with t_ref[j] = j dt_ref, i.e. node_time / dt_ref + 1; past the end of
+// the reference the knot tracks the hover state (row n_ref of the table, built by empc_set_reference_trajectory),
+// otherwise state_ref[idx_state - 1] (the interpolation factor is evaluated in integer arithmetic and is always 0,
+// :188-189).  The reference of the knot's state cost ("rail_state", the only CostModelState of a rail knot) is rewritten.
+__global__ void rail_retarget_kernel(const empc_cost_t* costs, double* pool, const int* begin, const int* node_set, int T1,
+                                     int n_maps, const long long* times, int dt_node_ms, const double* ref_table, int n_ref,
+                                     int dt_ref_ms, int nx) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_maps * T1) return;
+  const int m = idx / T1, i = idx - m * T1;
+  const long long node_time = times[m] + (long long)i * dt_node_ms;
+  const long long q = node_time / dt_ref_ms;
+  const int row = (q + 1 >= n_ref) ? n_ref : (int)q;
+  const int set = node_set[idx];
+  for (int c = begin[set]; c < begin[set + 1]; ++c) {
+    const empc_cost_t cs = costs[c];
+    if (cs.type != EMPC_COST_STATE || cs.ref_off < 0) continue;
+    for (int k = 0; k < nx; ++k) pool[cs.ref_off + k] = ref_table[(size_t)row * nx + k];
+    break;
+  }
+}
+
+}  // namespace empc

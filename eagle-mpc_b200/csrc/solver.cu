@@ -4,6 +4,8 @@
 // carries its own state machine on the device (kernels.cuh: OcpState), the host only loops
 //   calc_diff -> backward -> rollout -> decide
 // until no OCP is active.  No CPU fallback: every entry point fails with EMPC_ERR_CUDA if the device is unusable.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -11,6 +13,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "retarget.cuh"
 
 using namespace empc;
 
@@ -26,7 +29,7 @@ static int fail(int code, const std::string& msg) { g_last_error = msg; return c
 struct empc_solver {
   int device = 0, B = 0, T = 0;
   int na = 0, nr = 0, nq = 0, nv = 0, nx = 0, ndx = 0, nu = 0, tile = 0;
-  int n_costs = 0, n_pool = 0, n_node_maps = 0;
+  int n_costs = 0, n_pool = 0, n_node_maps = 0, n_costsets = 0;
   empc_solver_params_t P;
   DevModel hmodel;
   Buffers bf;
@@ -40,6 +43,10 @@ struct empc_solver {
   int* d_ocp_map = nullptr;
   double* d_x0 = nullptr;
   double *d_xs_init = nullptr, *d_us_init = nullptr;
+  // batched MPC instances (retarget.cuh)
+  double* d_ref_table = nullptr;  // (n_ref + 1) x nx: reference trajectory + hover row
+  int n_ref = 0, dt_ref_ms = 0;
+  long long* d_times = nullptr;   // n_node_maps controller times
   int init_feasible = 0;
   cudaStream_t stream = nullptr;
   int* h_active = nullptr;  // pinned: [group][slot][2]
@@ -151,7 +158,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   h->na = r.n_joints - 1; h->nr = d->n_rotors;
   h->nq = 7 + h->na; h->nv = 6 + h->na; h->nx = h->nq + h->nv; h->ndx = 2 * h->nv; h->nu = h->nr + h->na;
   empc_default_params(&h->P);
-  h->n_costs = d->n_costs; h->n_pool = d->n_pool; h->n_node_maps = d->n_node_maps;
+  h->n_costs = d->n_costs; h->n_pool = d->n_pool; h->n_node_maps = d->n_node_maps; h->n_costsets = d->n_costsets;
 
   DevModel& M = h->hmodel;
   std::memset(&M, 0, sizeof(M));
@@ -332,6 +339,73 @@ int empc_update_node_costsets(empc_solver_t* h, const int32_t* nc) {
   if (!h || !nc) return fail(EMPC_ERR_INVALID, "null");
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpy(h->d_node_costset, nc, sizeof(int) * h->n_node_maps * (h->T + 1), cudaMemcpyHostToDevice));
+  return EMPC_OK;
+}
+
+// ---- batched MPC instances: private cost tables per instance, device-side rail retargeting (retarget.cuh) ----
+int empc_replicate_instances(empc_solver_t* h, int32_t n) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  if (n < 1) return fail(EMPC_ERR_INVALID, "n_instances < 1");
+  if (h->n_node_maps != 1) return fail(EMPC_ERR_INVALID, "instances are replicated from a problem with a single node map");
+  if ((long long)n * std::max(h->n_pool, h->n_costs) > 0x7fffffffLL / 2) return fail(EMPC_ERR_INVALID, "replicated tables exceed the 32-bit offsets");
+  CK(cudaSetDevice(h->device));
+  const int T1 = h->T + 1;
+  empc_cost_t* costs = nullptr; double* pool = nullptr; int *begin = nullptr, *node_set = nullptr;
+  CK(dalloc(h, &costs, (size_t)std::max(1, n * h->n_costs)));
+  CK(dalloc(h, &pool, (size_t)std::max(1, n * h->n_pool)));
+  CK(dalloc(h, &begin, (size_t)n * h->n_costsets + 1));
+  CK(dalloc(h, &node_set, (size_t)n * T1));
+  CK(dalloc(h, &h->d_times, (size_t)n));
+  replicate_tables_kernel<<<296, 256, 0, h->stream>>>(h->d_costs, h->n_costs, h->d_pool, h->n_pool, h->d_costset_begin, h->n_costsets,
+                                                       h->d_node_costset, T1, n, costs, pool, begin, node_set);
+  CK(cudaGetLastError());
+  std::vector<int> map((size_t)h->B);
+  for (int b = 0; b < h->B; ++b) map[(size_t)b] = b % n;
+  CK(cudaMemcpyAsync(h->d_ocp_map, map.data(), sizeof(int) * h->B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  // the single-map tables stay allocated until empc_destroy (they are small); the handle now points at the copies
+  h->d_costs = costs; h->d_pool = pool; h->d_costset_begin = begin; h->d_node_costset = node_set;
+  h->bf.ct.costs = costs; h->bf.ct.pool = pool; h->bf.ct.costset_begin = begin; h->bf.node_costset = node_set;
+  h->n_costs *= n; h->n_pool *= n; h->n_costsets *= n; h->n_node_maps = n;
+  return EMPC_OK;
+}
+
+int empc_set_reference_trajectory(empc_solver_t* h, const double* state_ref, int32_t n_ref, int32_t dt_ref_ms) {
+  if (!h || !state_ref) return fail(EMPC_ERR_INVALID, "null");
+  if (n_ref < 1 || dt_ref_ms < 1) return fail(EMPC_ERR_INVALID, "empty reference trajectory / dt_ref < 1 ms");
+  CK(cudaSetDevice(h->device));
+  const int nx = h->nx, nq = h->nq;
+  std::vector<double> tab((size_t)(n_ref + 1) * nx, 0.0);
+  std::copy(state_ref, state_ref + (size_t)n_ref * nx, tab.begin());
+  // hover row (rail-mpc.cpp:180-186): last configuration, zero velocity, quaternion rebuilt from its (z, w) pair only
+  // -- the x / y components copied along with the configuration stay
+  const double* last = state_ref + (size_t)(n_ref - 1) * nx;
+  double* hov = tab.data() + (size_t)n_ref * nx;
+  std::copy(last, last + nq, hov);
+  const double w = last[6], z = last[5], norm = std::sqrt(w * w + z * z);
+  hov[5] = z / norm; hov[6] = w / norm;
+  CK(dalloc(h, &h->d_ref_table, tab.size()));
+  CK(cudaMemcpyAsync(h->d_ref_table, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_ref = n_ref; h->dt_ref_ms = dt_ref_ms;
+  return EMPC_OK;
+}
+
+int empc_rail_retarget(empc_solver_t* h, const int64_t* times_ms, int32_t dt_node_ms) {
+  if (!h || !times_ms) return fail(EMPC_ERR_INVALID, "null");
+  if (!h->d_ref_table) return fail(EMPC_ERR_INVALID, "empc_set_reference_trajectory has not been called");
+  if (dt_node_ms < 1) return fail(EMPC_ERR_INVALID, "dt_node < 1 ms");
+  for (int m = 0; m < h->n_node_maps; ++m) if (times_ms[m] < 0) return fail(EMPC_ERR_INVALID, "negative controller time");
+  CK(cudaSetDevice(h->device));
+  if (!h->d_times) CK(dalloc(h, &h->d_times, (size_t)h->n_node_maps));
+  static_assert(sizeof(long long) == sizeof(int64_t), "controller times are 64-bit");
+  CK(cudaMemcpyAsync(h->d_times, times_ms, sizeof(int64_t) * h->n_node_maps, cudaMemcpyHostToDevice, h->stream));
+  const int T1 = h->T + 1, total = h->n_node_maps * T1;
+  rail_retarget_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d_costs, h->d_pool, h->d_costset_begin, h->d_node_costset, T1,
+                                                                   h->n_node_maps, h->d_times, dt_node_ms, h->d_ref_table, h->n_ref,
+                                                                   h->dt_ref_ms, h->nx);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
   return EMPC_OK;
 }
 

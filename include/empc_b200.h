@@ -172,6 +172,19 @@ int empc_update_costs(empc_solver_t* h, int32_t first_cost, int32_t n, const emp
                       int32_t pool_off, int32_t n_pool, const double* pool);
 int empc_update_node_costsets(empc_solver_t* h, const int32_t* node_costset /* n_node_maps*(T+1) */);
 
+/* ---- batched MPC instances: one handle, `n_instances` controllers at different times ----
+ * empc_replicate_instances gives every instance a private copy of the cost tables of a single-node-map problem (one
+ * model per knot, src/mpc-controllers/rail-mpc.cpp:66-79): afterwards n_node_maps = n_instances, OCP b uses instance
+ * b % n_instances (change with empc_set_node_maps), and the cost / pool indices of empc_update_costs address instance m
+ * at m*n_costs + c and m*n_pool + i.
+ * empc_set_reference_trajectory uploads the state reference of a rail controller (n_ref states of nx doubles, dt_ref_ms
+ * apart: RailMpc(state_ref, dt_ref, yaml), rail-mpc.cpp:26-35).
+ * empc_rail_retarget is RailMpc::updateProblem(current_time) (rail-mpc.cpp:154-200) for all instances at once, on the
+ * device: times_ms[m] is the controller time of instance m, dt_node_ms the knot spacing (mpc_controller/dt). */
+int empc_replicate_instances(empc_solver_t* h, int32_t n_instances);
+int empc_set_reference_trajectory(empc_solver_t* h, const double* state_ref, int32_t n_ref, int32_t dt_ref_ms);
+int empc_rail_retarget(empc_solver_t* h, const int64_t* times_ms /* n_node_maps */, int32_t dt_node_ms);
+
 /* ---- the hot path ---- */
 /* Full SbFDDP solve of the whole batch (squash-smoothing schedule, FDDP passes, DDP clean-up). */
 int empc_solve(empc_solver_t* h);

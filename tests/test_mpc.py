@@ -202,3 +202,58 @@ def test_batched_rail_instances_match_oracle():
         assert abs(gc[b] - o.get("cost")) <= 1e-9 * max(1.0, abs(o.get("cost")))
         assert np.abs(gx[b] - o.get("xs")).max() <= 1e-9 * max(1.0, np.abs(o.get("xs")).max())
         assert np.abs(gu[b] - o.get("us")).max() <= 1e-9 * max(1.0, np.abs(o.get("us")).max())
+
+
+@pytest.mark.gpu
+def test_device_rail_retarget_instances_at_different_times():
+    """several rail controllers at different times in one handle, retargeted by one kernel
+    (empc_rail_retarget).  Every instance must equal the oracle solving the problem that the host mirror of
+    RailMpc::updateProblem retargets at that instance's time, including the hover tail past the end of the reference."""
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    wl = importlib.import_module("eagle-mpc_b200.workloads")
+    _tr, fp, xs, us = _iris_solution()
+    mpc = mpcmod.RailMpc(xs, 20, IRIS_MPC, create_solver=False)
+    t_end = 20 * (len(xs) - 1)
+    times = [0, 210, 1000, 3999, t_end - 300, t_end + 5000]   # not all multiples of the reference spacing; tail cases
+    B, T = len(times), mpc.knots - 1
+    x0 = np.zeros((B, mpc.nx)); xs_b = np.zeros((B, T + 1, mpc.nx)); us_b = np.zeros((B, T, mpc.nu))
+    for b, t0 in enumerate(times):
+        idx = np.minimum(t0 // 20 + np.arange(T + 1), len(xs) - 1)
+        x0[b] = wl.noisy_x0(xs[idx[0]], 1, 9000 + b)[0]
+        xs_b[b] = xs[idx]; xs_b[b, 0] = x0[b]
+        us_b[b] = us[np.minimum(idx[:-1], len(us) - 1)]
+    mpc.updateProblem(123456)   # the tables the handle starts from: every knot on the hover state
+    g = capi.BatchSolver(mpc, B)
+    costs, pool = mpc.cost_tables()
+    g.update_costs(0, costs, 0, pool)
+    g.replicate_instances(B)
+    g.set_reference_trajectory(xs, 20)
+    g.rail_retarget(times, mpc.dt)
+    pg = capi.default_params(); pg.maxiter = mpc.iters; pg.convergence_init = 1e-3
+    g.set_params(pg)
+    g.set_x0(x0); g.set_candidate(xs_b, us_b, False); g.solve()
+    gx, gu, gc, gi = g.xs(), g.us(), g.cost(), g.iters()
+    po = ob.default_params(); po.maxiter = mpc.iters; po.convergence_init = 1e-3
+    ob.lib.orc_update_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Cost), C.c_int, C.c_int, abi.c_double_p]
+    costs_seen = []
+    for b, t0 in enumerate(times):
+        mpc.updateProblem(t0)
+        costs, pool = mpc.cost_tables()
+        o = ob.Oracle(mpc); o.set_params(po)
+        ob.lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), ob.dp(pool))
+        o.set_x0(x0[b]); o.solve(xs_b[b], us_b[b])
+        assert int(o.get("iter")) == gi[b], (b, t0)
+        assert abs(gc[b] - o.get("cost")) <= 1e-9 * max(1.0, abs(o.get("cost"))), (b, t0)
+        assert np.abs(gx[b] - o.get("xs")).max() <= 1e-9 * max(1.0, np.abs(o.get("xs")).max()), (b, t0)
+        assert np.abs(gu[b] - o.get("us")).max() <= 1e-9 * max(1.0, np.abs(o.get("us")).max()), (b, t0)
+        costs_seen.append(float(o.get("cost")))
+    assert len({round(c, 6) for c in costs_seen}) > 3   # the instances really solve different problems
+    # a second retarget of the same handle (all instances moved on by one controller period) is picked up
+    g.rail_retarget([t + 20 for t in times], mpc.dt)
+    g.set_x0(x0); g.set_candidate(xs_b, us_b, False); g.solve()
+    mpc.updateProblem(times[2] + 20)
+    costs, pool = mpc.cost_tables()
+    o = ob.Oracle(mpc); o.set_params(po)
+    ob.lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), ob.dp(pool))
+    o.set_x0(x0[2]); o.solve(xs_b[2], us_b[2])
+    assert abs(g.cost()[2] - o.get("cost")) <= 1e-9 * max(1.0, abs(o.get("cost")))
