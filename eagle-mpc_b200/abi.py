@@ -38,6 +38,18 @@ class Robot(C.Structure):
     ]
 
 
+class WeightedSchedule(C.Structure):
+    """empc_weighted_schedule_t"""
+    _fields_ = [
+        ("n_stages", C.c_int32), ("n_slots", C.c_int32),
+        ("t_ini", C.POINTER(C.c_int64)), ("t_end", C.POINTER(C.c_int64)),
+        ("duration", C.c_int64),
+        ("alpha", C.c_double), ("beta", C.c_double),
+        ("match", C.POINTER(C.c_uint8)), ("task", C.POINTER(C.c_uint8)),
+        ("base", C.POINTER(C.c_double)),
+    ]
+
+
 class Cost(C.Structure):
     _fields_ = [
         ("type", C.c_int32),

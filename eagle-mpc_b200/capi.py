@@ -44,6 +44,8 @@ def lib():
         L.empc_replicate_instances.argtypes = [C.c_void_p, C.c_int32]
         L.empc_set_reference_trajectory.argtypes = [C.c_void_p, abi.c_double_p, C.c_int32, C.c_int32]
         L.empc_rail_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
+        L.empc_set_weighted_schedule.argtypes = [C.c_void_p, C.POINTER(abi.WeightedSchedule)]
+        L.empc_weighted_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
         L.empc_get_total_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.empc_get_launch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), abi.c_double_p]
         L.empc_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
@@ -134,6 +136,23 @@ class BatchSolver:
         t = np.ascontiguousarray(times_ms, dtype=np.int64)
         assert t.size == getattr(self, "n_instances", 1)
         _ck(lib().empc_rail_retarget(self.h, t.ctypes.data_as(C.POINTER(C.c_int64)), int(dt_node_ms)))
+
+    def set_weighted_schedule(self, sch):
+        """sch: WeightedMpc.schedule()"""
+        t_ini = np.ascontiguousarray(sch["t_ini"], dtype=np.int64); t_end = np.ascontiguousarray(sch["t_end"], dtype=np.int64)
+        match = np.ascontiguousarray(sch["match"], dtype=np.uint8); task = np.ascontiguousarray(sch["task"], dtype=np.uint8)
+        base = np.ascontiguousarray(sch["base"], dtype=np.float64)
+        s = abi.WeightedSchedule(match.shape[0], match.shape[1], t_ini.ctypes.data_as(C.POINTER(C.c_int64)),
+                                 t_end.ctypes.data_as(C.POINTER(C.c_int64)), int(sch["duration"]), float(sch["alpha"]),
+                                 float(sch["beta"]), match.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                 task.ctypes.data_as(C.POINTER(C.c_uint8)), abi.as_double_p(base))
+        _ck(lib().empc_set_weighted_schedule(self.h, C.byref(s)))
+
+    def weighted_retarget(self, times_ms, dt_node_ms):
+        """WeightedMpc.updateProblem(times_ms[m]) for every instance m, on the device"""
+        t = np.ascontiguousarray(times_ms, dtype=np.int64)
+        assert t.size == getattr(self, "n_instances", 1)
+        _ck(lib().empc_weighted_retarget(self.h, t.ctypes.data_as(C.POINTER(C.c_int64)), int(dt_node_ms)))
 
     # ---- hot path ----
     def solve(self):

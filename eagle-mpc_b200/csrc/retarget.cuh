@@ -53,4 +53,60 @@ __global__ void rail_retarget_kernel(const empc_cost_t* costs, double* pool, con
   }
 }
 
+// WeightedMpc::updateProblem for every instance (weighted-mpc.cpp:173-245), block per instance.  The active stage of a
+// knot depends on the one of the knot before it (a stage of zero duration is not skipped, :186-192): thread 0 walks that
+// chain into shared memory (stage = upper_bound(t_ini, node_time) - 1, pulled back by one when it jumped two stages), then
+// the knots are rewritten in parallel: costs of the knot's stage on, its task costs re-weighted, all other costs off; the
+// barrier is left alone.
+struct WeightedScheduleDev {
+  int n_stages, n_slots;
+  const long long* t_ini; const long long* t_end;
+  long long duration;
+  double alpha, beta;
+  const unsigned char* match; const unsigned char* task;
+  const double* base;
+};
+
+__device__ inline int weighted_stage_of(const WeightedScheduleDev& s, long long t) {
+  int ub = 0;  // first stage with t_ini > t
+  while (ub < s.n_stages && s.t_ini[ub] <= t) ++ub;
+  return ub - 1;
+}
+
+__global__ void weighted_retarget_kernel(empc_cost_t* costs, const int* begin, const int* node_set, int T1, int n_maps,
+                                         const long long* times, int dt_node_ms, WeightedScheduleDev s) {
+  extern __shared__ int wr_stage[];  // T1 entries
+  const int m = blockIdx.x;
+  const long long t0 = times[m];
+  if (threadIdx.x == 0) {
+    int last = weighted_stage_of(s, t0);
+    for (int i = 0; i < T1; ++i) {
+      int st = weighted_stage_of(s, t0 + (long long)i * dt_node_ms);
+      if (st == last + 2) st -= 1;
+      wr_stage[i] = st;
+      last = st;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T1; i += blockDim.x) {
+    const long long node_time = t0 + (long long)i * dt_node_ms;
+    const int st = wr_stage[i];
+    const double wt = (node_time > s.duration) ? 0.0 : (double)((int)node_time - (int)s.t_end[st]) / 1000.0;
+    const double w = exp(s.alpha * wt);
+    const int set = node_set[m * T1 + i];
+    int slot = 0;
+    for (int c = begin[set]; c < begin[set + 1]; ++c) {
+      if (costs[c].type == EMPC_COST_SQUASH_BARRIER) continue;
+      const int e = st * s.n_slots + slot;
+      if (s.match[e]) {
+        costs[c].active = 1;
+        if (s.task[e]) costs[c].weight = s.base[e] * w * s.beta;
+      } else {
+        costs[c].active = 0;
+      }
+      ++slot;
+    }
+  }
+}
+
 }  // namespace empc

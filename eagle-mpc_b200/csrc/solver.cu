@@ -47,6 +47,7 @@ struct empc_solver {
   double* d_ref_table = nullptr;  // (n_ref + 1) x nx: reference trajectory + hover row
   int n_ref = 0, dt_ref_ms = 0;
   long long* d_times = nullptr;   // n_node_maps controller times
+  WeightedScheduleDev wsched = {0, 0, nullptr, nullptr, 0, 0.0, 0.0, nullptr, nullptr, nullptr};
   int init_feasible = 0;
   cudaStream_t stream = nullptr;
   int* h_active = nullptr;  // pinned: [group][slot][2]
@@ -404,6 +405,40 @@ int empc_rail_retarget(empc_solver_t* h, const int64_t* times_ms, int32_t dt_nod
   rail_retarget_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d_costs, h->d_pool, h->d_costset_begin, h->d_node_costset, T1,
                                                                    h->n_node_maps, h->d_times, dt_node_ms, h->d_ref_table, h->n_ref,
                                                                    h->dt_ref_ms, h->nx);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
+
+int empc_set_weighted_schedule(empc_solver_t* h, const empc_weighted_schedule_t* s) {
+  if (!h || !s) return fail(EMPC_ERR_INVALID, "null");
+  if (s->n_stages < 1 || s->n_slots < 1 || !s->t_ini || !s->t_end || !s->match || !s->task || !s->base)
+    return fail(EMPC_ERR_INVALID, "incomplete weighted schedule");
+  CK(cudaSetDevice(h->device));
+  const size_t ns = (size_t)s->n_stages, ne = ns * (size_t)s->n_slots;
+  long long *t_ini = nullptr, *t_end = nullptr; unsigned char *match = nullptr, *task = nullptr; double* base = nullptr;
+  CK(dalloc(h, &t_ini, ns)); CK(dalloc(h, &t_end, ns)); CK(dalloc(h, &match, ne)); CK(dalloc(h, &task, ne)); CK(dalloc(h, &base, ne));
+  CK(cudaMemcpyAsync(t_ini, s->t_ini, sizeof(int64_t) * ns, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(t_end, s->t_end, sizeof(int64_t) * ns, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(match, s->match, ne, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(task, s->task, ne, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(base, s->base, sizeof(double) * ne, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->wsched = WeightedScheduleDev{s->n_stages, s->n_slots, t_ini, t_end, (long long)s->duration, s->alpha, s->beta, match, task, base};
+  return EMPC_OK;
+}
+
+int empc_weighted_retarget(empc_solver_t* h, const int64_t* times_ms, int32_t dt_node_ms) {
+  if (!h || !times_ms) return fail(EMPC_ERR_INVALID, "null");
+  if (!h->wsched.base) return fail(EMPC_ERR_INVALID, "empc_set_weighted_schedule has not been called");
+  if (dt_node_ms < 1) return fail(EMPC_ERR_INVALID, "dt_node < 1 ms");
+  for (int m = 0; m < h->n_node_maps; ++m) if (times_ms[m] < 0) return fail(EMPC_ERR_INVALID, "negative controller time");
+  CK(cudaSetDevice(h->device));
+  if (!h->d_times) CK(dalloc(h, &h->d_times, (size_t)h->n_node_maps));
+  CK(cudaMemcpyAsync(h->d_times, times_ms, sizeof(int64_t) * h->n_node_maps, cudaMemcpyHostToDevice, h->stream));
+  weighted_retarget_kernel<<<h->n_node_maps, 128, sizeof(int) * (h->T + 1), h->stream>>>(h->d_costs, h->d_costset_begin, h->d_node_costset,
+                                                                                        h->T + 1, h->n_node_maps, h->d_times, dt_node_ms,
+                                                                                        h->wsched);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return EMPC_OK;

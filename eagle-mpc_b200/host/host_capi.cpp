@@ -1,4 +1,6 @@
 // host_capi.cpp — plain-C access to the host-side mirror (for the Python front-end / tests; no compute here).
+#include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <string>
 
@@ -168,6 +170,23 @@ void* empc_host_carrot_create(void* t, const double* state_ref, int32_t n_ref, i
   hc->mpc.reset(new CarrotMpc(tr, unpack_states(state_ref, n_ref, nx), (std::size_t)dt_ref, getYamlPath(yaml_path), create_solver != 0));
   return hc;
   GUARD_END(nullptr)
+}
+// WeightedMpc::schedule() in flat arrays; call once with null arrays for dims = {n_stages, n_slots}
+int empc_host_weighted_schedule(void* m, int32_t* dims, int64_t* t_ini, int64_t* t_end, int64_t* duration, double* alpha_beta,
+                                uint8_t* match, uint8_t* task, double* base) {
+  GUARD_BEGIN
+    auto* w = dynamic_cast<WeightedMpc*>(((HostCarrot*)m)->mpc.get());
+    if (!w) throw std::runtime_error("not a WeightedMpc");
+    const WeightedSchedule s = w->schedule();
+    dims[0] = (int32_t)s.t_ini.size(); dims[1] = (int32_t)s.n_slots;
+    if (t_ini) {
+      std::copy(s.t_ini.begin(), s.t_ini.end(), t_ini); std::copy(s.t_end.begin(), s.t_end.end(), t_end);
+      *duration = s.duration; alpha_beta[0] = s.alpha; alpha_beta[1] = s.beta;
+      std::copy(s.match.begin(), s.match.end(), match); std::copy(s.task.begin(), s.task.end(), task);
+      std::copy(s.base.begin(), s.base.end(), base);
+    }
+    return 0;
+  GUARD_END(1)
 }
 void empc_host_carrot_free(void* m) { delete (HostCarrot*)m; }
 int empc_host_carrot_info(void* m, int32_t* out /* knots dt iters n_costs n_pool */) {

@@ -401,6 +401,36 @@ void WeightedMpc::updateFreeCosts(std::size_t idx) {
   }
 }
 
+WeightedSchedule WeightedMpc::schedule() const {
+  WeightedSchedule s;
+  const auto& stages = trajectory_->get_stages();
+  s.duration = (std::int64_t)trajectory_->get_duration();
+  s.alpha = alpha_; s.beta = beta_;
+  std::vector<std::string> names;  // the cost names of a knot in map order, barrier excluded
+  for (const auto& kv : int_models_.front()->costs->get_costs())
+    if (kv.first != "barrier") names.push_back(kv.first);
+  s.n_slots = names.size();
+  if (t_stages_.size() != stages.size()) throw std::runtime_error("WeightedMpc: stage table out of sync");
+  for (std::size_t si = 0; si < stages.size(); ++si) {
+    const auto& st = stages[si];
+    s.t_ini.push_back((std::int64_t)t_stages_[si]);  // what computeActiveStage searches
+    s.t_end.push_back((std::int64_t)st->get_t_ini() + (std::int64_t)st->get_duration());
+    const std::string& ns = st->get_name();
+    for (const auto& name : names) {
+      const bool m = name.compare(0, ns.size(), ns) == 0;
+      const bool task = m && name.compare(ns.size(), 4, "/reg") != 0 && name.compare(ns.size(), 7, "/limits") != 0;
+      double base = 0.0;
+      if (task) {
+        // updateFreeCosts looks the cost up in the stage by the rest of the name; with stage names that are prefixes of
+        // one another that lookup throws in the reference, and so does the schedule
+        base = st->get_costs()->get_costs().at(name.substr(ns.size() + 1))->weight;
+      }
+      s.match.push_back(m); s.task.push_back(task); s.base.push_back(base);
+    }
+  }
+  return s;
+}
+
 void WeightedMpc::updateProblem(const std::size_t& current_time) {
   computeActiveStage(current_time);
   update_vars_.idx_last_stage = update_vars_.idx_stage;

@@ -3,6 +3,8 @@
 // exactly like the reference (src/mpc-controllers/carrot-mpc.cpp:298-401, rail-mpc.cpp:154-200,
 // weighted-mpc.cpp:173-245) and pushes only the changed records to the device through empc_update_costs.
 #pragma once
+#include <cstdint>
+
 #include "eagle_mpc.hpp"
 
 namespace eagle_mpc {
@@ -114,6 +116,17 @@ class RailMpc : public MpcAbstract {
 // WeightedMpc (include/eagle_mpc/mpc-controllers/weighted-mpc.hpp:27-71): every knot carries the costs of every
 // (non-transition) stage of the trajectory; the ones of the stage active at the knot's time are switched on, the task
 // costs with the weight exp(alpha (t - t_end_of_stage)) * beta.
+// The weight schedule of a WeightedMpc in flat form, for the device-side retargeting (empc_weighted_retarget): per
+// (stage, cost slot of a knot) what updateFreeCosts would do.  Slots are the costs of a knot in name order, barrier excluded.
+struct WeightedSchedule {
+  std::vector<std::int64_t> t_ini, t_end;  // per (merged, non-transition) stage, ms
+  std::int64_t duration = 0;               // trajectory duration, ms
+  double alpha = 0, beta = 0;
+  std::size_t n_slots = 0;
+  std::vector<std::uint8_t> match, task;   // n_stages x n_slots: prefix match / weight follows the schedule
+  std::vector<double> base;                // n_stages x n_slots: the stage's own weight of that cost
+};
+
 class WeightedMpc : public MpcAbstract {
  public:
   WeightedMpc(const std::shared_ptr<Trajectory>& trajectory, std::size_t dt_ref, const std::string& yaml_path, bool create_solver = true);
@@ -121,6 +134,7 @@ class WeightedMpc : public MpcAbstract {
   void updateProblem(const std::size_t& current_time) override;
   const std::shared_ptr<Trajectory>& get_trajectory() const { return trajectory_; }
   const std::vector<std::size_t>& get_t_stages() const { return t_stages_; }
+  WeightedSchedule schedule() const;
 
  private:
   std::shared_ptr<CostModelSum> createCosts() const;

@@ -23,6 +23,9 @@ def _mlib():
         L.empc_host_rail_create.argtypes = [abi.c_double_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
         L.empc_host_weighted_create.restype = C.c_void_p
         L.empc_host_weighted_create.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32]
+        L.empc_host_weighted_schedule.argtypes = [C.c_void_p, abi.c_int32_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                                  C.POINTER(C.c_int64), abi.c_double_p, C.POINTER(C.c_uint8),
+                                                  C.POINTER(C.c_uint8), abi.c_double_p]
         L.empc_host_carrot_free.argtypes = [C.c_void_p]
         L.empc_host_carrot_info.argtypes = [C.c_void_p, abi.c_int32_p]
         L.empc_host_carrot_desc.restype = C.POINTER(abi.ProblemDesc)
@@ -124,6 +127,25 @@ class WeightedMpc(_MpcBase):
         self._traj = trajectory
         self._adopt(_mlib().empc_host_weighted_create(trajectory._p, int(dt_ref), yaml_path.encode(), int(create_solver)),
                     create_solver)
+
+    def schedule(self):
+        """The weight schedule in flat arrays (for BatchSolver.set_weighted_schedule): dict with t_ini, t_end (ms per
+        stage), duration, alpha, beta and the n_stages x n_slots tables match / task / base."""
+        L = _mlib()
+        dims = np.zeros(2, dtype=np.int32)
+        if L.empc_host_weighted_schedule(self._p, abi.as_int32_p(dims), None, None, None, None, None, None, None):
+            raise EmpcError(_err())
+        ns, nc = int(dims[0]), int(dims[1])
+        t_ini = np.zeros(ns, dtype=np.int64); t_end = np.zeros(ns, dtype=np.int64); dur = C.c_int64()
+        ab = np.zeros(2); match = np.zeros((ns, nc), dtype=np.uint8); task = np.zeros((ns, nc), dtype=np.uint8)
+        base = np.zeros((ns, nc))
+        i64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        u8 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint8))
+        if L.empc_host_weighted_schedule(self._p, abi.as_int32_p(dims), i64(t_ini), i64(t_end), C.byref(dur), abi.as_double_p(ab),
+                                         u8(match), u8(task), abi.as_double_p(base)):
+            raise EmpcError(_err())
+        return {"t_ini": t_ini, "t_end": t_end, "duration": int(dur.value), "alpha": float(ab[0]), "beta": float(ab[1]),
+                "match": match, "task": task, "base": base}
 
 
 def closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, record=False):

@@ -185,6 +185,25 @@ int empc_replicate_instances(empc_solver_t* h, int32_t n_instances);
 int empc_set_reference_trajectory(empc_solver_t* h, const double* state_ref, int32_t n_ref, int32_t dt_ref_ms);
 int empc_rail_retarget(empc_solver_t* h, const int64_t* times_ms /* n_node_maps */, int32_t dt_node_ms);
 
+/* The weight schedule of a WeightedMpc (src/mpc-controllers/weighted-mpc.cpp:173-245) in flat form.  A "slot" is a cost of
+ * a knot in the order of its cost set, the squashing barrier excluded; every knot carries the same slots.  For stage s and
+ * slot c: match = the cost's name starts with the stage's name (:205) => active, otherwise inactive; task = its weight
+ * follows the schedule base * exp(alpha * (node_time - t_end[s]) / 1000) * beta (:207-214; exponent 0 once node_time is
+ * past `duration`, :229-241); "/reg" and "/limits" costs keep their weight. */
+typedef struct empc_weighted_schedule {
+  int32_t n_stages, n_slots;
+  const int64_t* t_ini;   /* n_stages: start of each (merged) stage, ms */
+  const int64_t* t_end;   /* n_stages: t_ini + duration of the stage */
+  int64_t duration;       /* trajectory duration, ms */
+  double alpha, beta;
+  const uint8_t* match;   /* n_stages * n_slots */
+  const uint8_t* task;    /* n_stages * n_slots */
+  const double* base;     /* n_stages * n_slots */
+} empc_weighted_schedule_t;
+int empc_set_weighted_schedule(empc_solver_t* h, const empc_weighted_schedule_t* s);
+/* WeightedMpc::updateProblem(current_time) for all instances at once, on the device. */
+int empc_weighted_retarget(empc_solver_t* h, const int64_t* times_ms /* n_node_maps */, int32_t dt_node_ms);
+
 /* ---- the hot path ---- */
 /* Full SbFDDP solve of the whole batch (squash-smoothing schedule, FDDP passes, DDP clean-up). */
 int empc_solve(empc_solver_t* h);

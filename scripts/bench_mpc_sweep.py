@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--t0", type=int, default=1000, help="controller time (ms) at which the instances are solved")
     ap.add_argument("--spread", action="store_true",
-                    help="rail only: every instance at its own controller time, retargeted on the device (empc_rail_retarget)")
+                    help="every instance at its own controller time, retargeted on the device (empc_rail_retarget / empc_weighted_retarget)")
     args = ap.parse_args()
     # reference trajectory: iris_px4 displacement solved by the B200 path itself (B = 1, maxiter 400)
     tr = host.Trajectory(TRAJ)
@@ -81,13 +81,15 @@ def main():
 
 
 def spread(args, xs, us, tmpdir):
-    """B rail controllers at different times (7 ms apart, wrapping over the trajectory): device-side retargeting of all
-    instances by one kernel vs the host-side RailMpc::updateProblem loop run once per instance."""
+    """B controllers at different times (7 ms apart, wrapping over the trajectory): device-side retargeting of all
+    instances by one kernel vs the host-side updateProblem loop run once per instance."""
     B = args.batch
     t_end = 20 * (len(xs) - 1)
     times = (7 * np.arange(B)) % t_end
-    for knots in args.knots:
-        mpc = mpcmod.RailMpc(xs, 20, yaml_with_knots(knots, tmpdir), create_solver=False)
+    for kind, knots in [(k, n) for k in ("rail", "weighted") for n in args.knots]:
+        rail = kind == "rail"
+        mpc = (mpcmod.RailMpc(xs, 20, yaml_with_knots(knots, tmpdir), create_solver=False) if rail
+               else mpcmod.WeightedMpc(host.Trajectory(TRAJ), 20, yaml_with_knots(knots, tmpdir), create_solver=False))
         T = mpc.knots - 1
         idx = np.minimum((times // 20)[:, None] + np.arange(T + 1)[None, :], len(xs) - 1)
         xs_b = xs[idx]
@@ -99,17 +101,22 @@ def spread(args, xs, us, tmpdir):
         costs, pool = mpc.cost_tables()
         g.update_costs(0, costs, 0, pool)
         g.replicate_instances(B)
-        g.set_reference_trajectory(xs, 20)
+        if rail:
+            g.set_reference_trajectory(xs, 20)
+            retarget = g.rail_retarget
+        else:
+            g.set_weighted_schedule(mpc.schedule())
+            retarget = g.weighted_retarget
         pr = capi.default_params(); pr.maxiter = mpc.iters; pr.convergence_init = 1e-3
         g.set_params(pr)
-        g.rail_retarget(times, mpc.dt)
+        retarget(times, mpc.dt)
         g.set_x0(x0); g.set_candidate(xs_b, us_b, False)
         g.solve()  # warm-up
         t_ret = t_sol = 0.0
         it_tot = 0
         for s in range(args.steps):
             g.reset()
-            t1 = time.perf_counter(); g.rail_retarget(times + 20 * (s + 1), mpc.dt); t2 = time.perf_counter()
+            t1 = time.perf_counter(); retarget(times + 20 * (s + 1), mpc.dt); t2 = time.perf_counter()
             g.solve(); t3 = time.perf_counter()
             t_ret += t2 - t1; t_sol += t3 - t2
             it_tot += g.total_iterations()
@@ -118,7 +125,7 @@ def spread(args, xs, us, tmpdir):
         for b in range(n_host):
             mpc.updateProblem(int(times[b]))
         t_host = (time.perf_counter() - t1) / n_host
-        print(json.dumps({"controller": "rail", "mode": "instances at different times, device retarget", "knots": knots, "T": T,
+        print(json.dumps({"controller": kind, "mode": "instances at different times, device retarget", "knots": knots, "T": T,
                           "batch": B, "iters_per_instance": it_tot / args.steps / B,
                           "ms_retarget_all_instances": 1e3 * t_ret / args.steps,
                           "ms_host_updateProblem_all_instances": 1e3 * t_host * B,

@@ -11,7 +11,7 @@ def col(r, k, scale=1.0):
     except Exception: return float("nan")
 def unit(k): return units[hdr.index(k)]
 fam = {"node_calc_kernel": "calc_diff", "node_cost_kernel": "calc_diff", "node_diff_kernel": "calc_diff", "backward_kernel": "backward", "rollout_kernel": "rollout", "decide_kernel": "decide"}
-seen = {}; lines = []; traffic = {}
+seen = {}; lines = []; traffic = {}; flines = []
 for r in rows[2:]:
     name = r[hdr.index("Kernel Name")]
     short = name.split("<")[0].replace("void ", "").replace("empc::", "")
@@ -27,9 +27,20 @@ for r in rows[2:]:
                  f"{col(r,'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {col(r,'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
                  f"{col(r,'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | {col(r,'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active'):.1f} | "
                  f"{col(r,'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {col(r,'smsp__inst_executed.sum')/1e6:.0f} |")
+    # FP64 work of the launch: thread-level DADD/DMUL/DFMA counts (rate per elapsed SMSP cycle x elapsed cycles) and the
+    # tensor-path FLOPs of the DMMAs; algorithmic in the sense of "what this formulation executes", counted by the hardware
+    cyc = col(r, "smsp__cycles_elapsed.sum") / max(col(r, "smsp__cycles_elapsed.sum") / col(r, "smsp__cycles_elapsed.avg"), 1.0) if "smsp__cycles_elapsed.avg" in hdr else col(r, "sm__cycles_elapsed.max")
+    ops = {k: col(r, f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum.per_cycle_elapsed") * cyc for k in ("dadd", "dmul", "dfma")}
+    tens = col(r, "sm__ops_path_tensor_src_fp64.sum")
+    flops = ops["dadd"] + ops["dmul"] + 2 * ops["dfma"] + (tens if tens == tens else 0.0)
+    nodes = batch * (T + 1)
+    flines.append(f"| `{short}` | {ops['dadd']/1e9:.2f} | {ops['dmul']/1e9:.2f} | {ops['dfma']/1e9:.2f} | {tens/1e9:.1f} | {flops/1e9:.1f} | {flops/nodes/1e3:.1f} | {flops/dur/1e9:.2f} |")
     t = traffic.setdefault(fam[short], {"dram_bytes_per_launch": 0.0, "kernels": {}})
     t["dram_bytes_per_launch"] += rd + wr
     t["kernels"][short] = {"ms": dur, "dram_read_bytes": rd, "dram_write_bytes": wr}
 open(out_md, "w").write("| kernel | ms | DRAM read GB | DRAM write GB | DRAM GB/s | regs | warps active % | issue active % | FP64 pipe % | DMMA pipe % | DRAM % of peak | M warp-instr |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n" + "\n".join(lines) + "\n")
+open(out_md, "a").write("\nFP64 work per launch (hardware counters; DADD/DMUL/DFMA are thread-level instruction counts, DMMA column in FLOPs; "
+                       "FLOPs = DADD + DMUL + 2 DFMA + DMMA FLOPs; per node = / (batch x (T+1)); rollout and decide touch each node once per trial):\n\n"
+                       "| kernel | G DADD | G DMUL | G DFMA | G DMMA FLOP | GFLOP per launch | kFLOP per node | TFLOP/s |\n|---|---|---|---|---|---|---|---|\n" + "\n".join(flines) + "\n")
 json.dump({"workload": workload, "batch": batch, "T": T, "source": rep.split("/")[-1], "kernels": traffic}, open(out_json, "w"), indent=1)
 print(open(out_md).read())

@@ -257,3 +257,84 @@ def test_device_rail_retarget_instances_at_different_times():
     ob.lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), ob.dp(pool))
     o.set_x0(x0[2]); o.solve(xs_b[2], us_b[2])
     assert abs(g.cost()[2] - o.get("cost")) <= 1e-9 * max(1.0, abs(o.get("cost")))
+
+
+@pytest.mark.gpu
+def test_device_weighted_retarget_instances_at_different_times():
+    """Same for WeightedMpc: empc_weighted_retarget walks the knots of every instance on the device (active stage with the
+    zero-duration rule, exp(alpha dt) weights, saturation past the end); per instance the solve equals the oracle on the
+    problem the host mirror retargets at that time."""
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    wl = importlib.import_module("eagle-mpc_b200.workloads")
+    _tr, fp, xs, us = _iris_solution()
+    mpc = mpcmod.WeightedMpc(host.Trajectory(IRIS_TRAJ), 20, IRIS_MPC, create_solver=False)
+    times = [0, 510, 1990, 3999, 7500, 9000]   # stage changes inside the horizon, the end of the trajectory, beyond it
+    B, T = len(times), mpc.knots - 1
+    x0 = np.zeros((B, mpc.nx)); xs_b = np.zeros((B, T + 1, mpc.nx)); us_b = np.zeros((B, T, mpc.nu))
+    for b, t0 in enumerate(times):
+        idx = np.minimum(t0 // 20 + np.arange(T + 1), len(xs) - 1)
+        x0[b] = wl.noisy_x0(xs[idx[0]], 1, 9000 + b)[0]
+        xs_b[b] = xs[idx]; xs_b[b, 0] = x0[b]
+        us_b[b] = us[np.minimum(idx[:-1], len(us) - 1)]
+    mpc.updateProblem(2500)
+    g = capi.BatchSolver(mpc, B)
+    costs, pool = mpc.cost_tables()
+    g.update_costs(0, costs, 0, pool)
+    g.replicate_instances(B)
+    g.set_weighted_schedule(mpc.schedule())
+    g.weighted_retarget(times, mpc.dt)
+    pg = capi.default_params(); pg.maxiter = mpc.iters; pg.convergence_init = 1e-3
+    g.set_params(pg)
+    g.set_x0(x0); g.set_candidate(xs_b, us_b, False); g.solve()
+    gx, gu, gc, gi = g.xs(), g.us(), g.cost(), g.iters()
+    po = ob.default_params(); po.maxiter = mpc.iters; po.convergence_init = 1e-3
+    ob.lib.orc_update_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Cost), C.c_int, C.c_int, abi.c_double_p]
+    costs_seen = []
+    for b, t0 in enumerate(times):
+        mpc.updateProblem(t0)
+        costs, pool = mpc.cost_tables()
+        o = ob.Oracle(mpc); o.set_params(po)
+        ob.lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), ob.dp(pool))
+        o.set_x0(x0[b]); o.solve(xs_b[b], us_b[b])
+        assert int(o.get("iter")) == gi[b], (b, t0)
+        assert abs(gc[b] - o.get("cost")) <= 1e-9 * max(1.0, abs(o.get("cost"))), (b, t0)
+        assert np.abs(gx[b] - o.get("xs")).max() <= 1e-9 * max(1.0, np.abs(o.get("xs")).max()), (b, t0)
+        assert np.abs(gu[b] - o.get("us")).max() <= 1e-9 * max(1.0, np.abs(o.get("us")).max()), (b, t0)
+        costs_seen.append(float(o.get("cost")))
+    assert len({round(c, 6) for c in costs_seen}) > 3
+
+
+def test_weighted_schedule_reproduces_updateProblem():
+    """WeightedMpc.schedule() (what empc_weighted_retarget consumes) replayed in Python gives the cost tables that the
+    host mirror of WeightedMpc::updateProblem writes, at times inside, across and beyond the stages."""
+    import math
+    mpc = mpcmod.WeightedMpc(host.Trajectory(IRIS_TRAJ), 20, IRIS_MPC, create_solver=False)
+    sch = mpc.schedule()
+    begin = np.ctypeslib.as_array(mpc.desc.costset_begin, shape=(mpc.knots + 1,))
+    assert sch["match"].shape == sch["task"].shape == sch["base"].shape == (4, 16)
+    assert (sch["match"].sum(axis=0) == 1).all()        # iris displacement: no stage name is a prefix of another
+
+    def stage_of(t):
+        return int(np.searchsorted(sch["t_ini"], t, side="right")) - 1
+
+    for t0 in (0, 510, 1990, 3999, 7500, 9000):
+        mpc.updateProblem(t0)
+        costs, _pool = mpc.cost_tables()
+        last = stage_of(t0)
+        for i in range(mpc.knots):
+            nt = t0 + i * mpc.dt
+            st = stage_of(nt)
+            if st == last + 2:
+                st -= 1
+            wt = 0.0 if nt > sch["duration"] else (nt - int(sch["t_end"][st])) / 1000.0
+            w = math.exp(sch["alpha"] * wt)
+            slot = 0
+            for c in range(begin[i], begin[i + 1]):
+                if costs[c].type == abi.COST_SQUASH_BARRIER:
+                    continue
+                assert costs[c].active == int(sch["match"][st, slot]), (t0, i, slot)
+                if sch["task"][st, slot]:
+                    assert costs[c].weight == sch["base"][st, slot] * w * sch["beta"], (t0, i, slot)
+                slot += 1
+            assert slot == 16
+            last = st
