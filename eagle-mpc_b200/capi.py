@@ -44,6 +44,8 @@ def lib():
         L.empc_replicate_instances.argtypes = [C.c_void_p, C.c_int32]
         L.empc_set_reference_trajectory.argtypes = [C.c_void_p, abi.c_double_p, C.c_int32, C.c_int32]
         L.empc_rail_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
+        L.empc_set_carrot_schedule.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]
+        L.empc_carrot_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
         L.empc_set_weighted_schedule.argtypes = [C.c_void_p, C.POINTER(abi.WeightedSchedule)]
         L.empc_weighted_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
         L.empc_get_total_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -136,6 +138,19 @@ class BatchSolver:
         t = np.ascontiguousarray(times_ms, dtype=np.int64)
         assert t.size == getattr(self, "n_instances", 1)
         _ck(lib().empc_rail_retarget(self.h, t.ctypes.data_as(C.POINTER(C.c_int64)), int(dt_node_ms)))
+
+    def set_carrot_schedule(self, sch):
+        """sch: CarrotMpc.schedule() = (t_stages [n_stages + 1], is_transition [n_stages])"""
+        t = np.ascontiguousarray(sch[0], dtype=np.int64); tr = np.ascontiguousarray(sch[1], dtype=np.uint8)
+        assert t.size == tr.size + 1
+        _ck(lib().empc_set_carrot_schedule(self.h, tr.size, t.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           tr.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def carrot_retarget(self, times_ms, dt_node_ms):
+        """CarrotMpc.updateProblem(times_ms[m]) for every instance m, on the device"""
+        t = np.ascontiguousarray(times_ms, dtype=np.int64)
+        assert t.size == getattr(self, "n_instances", 1)
+        _ck(lib().empc_carrot_retarget(self.h, t.ctypes.data_as(C.POINTER(C.c_int64)), int(dt_node_ms)))
 
     def set_weighted_schedule(self, sch):
         """sch: WeightedMpc.schedule()"""

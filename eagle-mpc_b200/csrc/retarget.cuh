@@ -53,6 +53,45 @@ __global__ void rail_retarget_kernel(const empc_cost_t* costs, double* pool, con
   }
 }
 
+// CarrotMpc::updateProblem for every instance (carrot-mpc.cpp:298-401), thread per (instance, knot).  The knot's cost set
+// in name order is [barrier,] carrot_state, carrot_tail, control_reg, state_limits, state_reg: the first two
+// CostModelState records are the carrot and its tail.  Row n_ref + 1 of the reference table is the tail state (last
+// configuration, zero velocity, :376-388).
+__global__ void carrot_retarget_kernel(empc_cost_t* costs, double* pool, const int* begin, const int* node_set, int T1, int n_maps,
+                                       const long long* times, int dt_node_ms, const double* ref_table, int n_ref, int dt_ref_ms,
+                                       int nx, int n_stages, const long long* t_stages, const unsigned char* is_transition) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_maps * T1) return;
+  const int m = idx / T1, i = idx - m * T1;
+  const long long node_time = times[m] + (long long)i * dt_node_ms;
+  int ub = 0;  // first entry of t_stages (n_stages + 1 entries) beyond node_time
+  while (ub <= n_stages && t_stages[ub] <= node_time) ++ub;
+  const int st = ub - 1;
+  const long long q = node_time / dt_ref_ms;
+  const double* ref = ref_table + (size_t)((q + 1 >= n_ref) ? n_ref + 1 : (int)q) * nx;
+  const int set = node_set[idx];
+  int c_state = -1, c_tail = -1;
+  for (int c = begin[set]; c < begin[set + 1]; ++c) {
+    if (costs[c].type != EMPC_COST_STATE) continue;
+    if (c_state < 0) c_state = c; else { c_tail = c; break; }
+  }
+  if (c_state < 0 || c_tail < 0) return;
+  if (st < n_stages) {
+    if (!is_transition[st] || i == T1 - 1) {
+      costs[c_state].active = 1;
+      const int off = costs[c_state].ref_off;
+      for (int k = 0; k < nx; ++k) pool[off + k] = ref[k];
+    } else {
+      costs[c_state].active = 0;
+    }
+  } else {
+    costs[c_state].active = 0;
+    costs[c_tail].active = 1;
+    const int off = costs[c_tail].ref_off;
+    for (int k = 0; k < nx; ++k) pool[off + k] = ref[k];
+  }
+}
+
 // WeightedMpc::updateProblem for every instance (weighted-mpc.cpp:173-245), block per instance.  The active stage of a
 // knot depends on the one of the knot before it (a stage of zero duration is not skipped, :186-192): thread 0 walks that
 // chain into shared memory (stage = upper_bound(t_ini, node_time) - 1, pulled back by one when it jumped two stages), then

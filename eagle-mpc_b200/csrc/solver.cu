@@ -44,7 +44,8 @@ struct empc_solver {
   double* d_x0 = nullptr;
   double *d_xs_init = nullptr, *d_us_init = nullptr;
   // batched MPC instances (retarget.cuh)
-  double* d_ref_table = nullptr;  // (n_ref + 1) x nx: reference trajectory + hover row
+  double* d_ref_table = nullptr;  // (n_ref + 2) x nx: reference trajectory + rail hover row + carrot tail row
+  long long* d_t_stages = nullptr; unsigned char* d_is_transition = nullptr; int n_stages = 0;  // carrot schedule
   int n_ref = 0, dt_ref_ms = 0;
   long long* d_times = nullptr;   // n_node_maps controller times
   WeightedScheduleDev wsched = {0, 0, nullptr, nullptr, 0, 0.0, 0.0, nullptr, nullptr, nullptr};
@@ -376,7 +377,7 @@ int empc_set_reference_trajectory(empc_solver_t* h, const double* state_ref, int
   if (n_ref < 1 || dt_ref_ms < 1) return fail(EMPC_ERR_INVALID, "empty reference trajectory / dt_ref < 1 ms");
   CK(cudaSetDevice(h->device));
   const int nx = h->nx, nq = h->nq;
-  std::vector<double> tab((size_t)(n_ref + 1) * nx, 0.0);
+  std::vector<double> tab((size_t)(n_ref + 2) * nx, 0.0);
   std::copy(state_ref, state_ref + (size_t)n_ref * nx, tab.begin());
   // hover row (rail-mpc.cpp:180-186): last configuration, zero velocity, quaternion rebuilt from its (z, w) pair only
   // -- the x / y components copied along with the configuration stay
@@ -385,6 +386,8 @@ int empc_set_reference_trajectory(empc_solver_t* h, const double* state_ref, int
   std::copy(last, last + nq, hov);
   const double w = last[6], z = last[5], norm = std::sqrt(w * w + z * z);
   hov[5] = z / norm; hov[6] = w / norm;
+  // carrot tail row (carrot-mpc.cpp:376-388): last configuration as it is, zero velocity
+  std::copy(last, last + nq, hov + nx);
   CK(dalloc(h, &h->d_ref_table, tab.size()));
   CK(cudaMemcpyAsync(h->d_ref_table, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -405,6 +408,37 @@ int empc_rail_retarget(empc_solver_t* h, const int64_t* times_ms, int32_t dt_nod
   rail_retarget_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d_costs, h->d_pool, h->d_costset_begin, h->d_node_costset, T1,
                                                                    h->n_node_maps, h->d_times, dt_node_ms, h->d_ref_table, h->n_ref,
                                                                    h->dt_ref_ms, h->nx);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
+
+int empc_set_carrot_schedule(empc_solver_t* h, int32_t n_stages, const int64_t* t_stages, const uint8_t* is_transition) {
+  if (!h || !t_stages || !is_transition) return fail(EMPC_ERR_INVALID, "null");
+  if (n_stages < 1) return fail(EMPC_ERR_INVALID, "n_stages < 1");
+  CK(cudaSetDevice(h->device));
+  CK(dalloc(h, &h->d_t_stages, (size_t)n_stages + 1));
+  CK(dalloc(h, &h->d_is_transition, (size_t)n_stages));
+  CK(cudaMemcpyAsync(h->d_t_stages, t_stages, sizeof(int64_t) * ((size_t)n_stages + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_is_transition, is_transition, (size_t)n_stages, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_stages = n_stages;
+  return EMPC_OK;
+}
+
+int empc_carrot_retarget(empc_solver_t* h, const int64_t* times_ms, int32_t dt_node_ms) {
+  if (!h || !times_ms) return fail(EMPC_ERR_INVALID, "null");
+  if (!h->d_ref_table) return fail(EMPC_ERR_INVALID, "empc_set_reference_trajectory has not been called");
+  if (!h->d_t_stages) return fail(EMPC_ERR_INVALID, "empc_set_carrot_schedule has not been called");
+  if (dt_node_ms < 1) return fail(EMPC_ERR_INVALID, "dt_node < 1 ms");
+  for (int m = 0; m < h->n_node_maps; ++m) if (times_ms[m] < 0) return fail(EMPC_ERR_INVALID, "negative controller time");
+  CK(cudaSetDevice(h->device));
+  if (!h->d_times) CK(dalloc(h, &h->d_times, (size_t)h->n_node_maps));
+  CK(cudaMemcpyAsync(h->d_times, times_ms, sizeof(int64_t) * h->n_node_maps, cudaMemcpyHostToDevice, h->stream));
+  const int T1 = h->T + 1, total = h->n_node_maps * T1;
+  carrot_retarget_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d_costs, h->d_pool, h->d_costset_begin, h->d_node_costset, T1,
+                                                                     h->n_node_maps, h->d_times, dt_node_ms, h->d_ref_table, h->n_ref,
+                                                                     h->dt_ref_ms, h->nx, h->n_stages, h->d_t_stages, h->d_is_transition);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return EMPC_OK;

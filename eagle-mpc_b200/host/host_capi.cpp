@@ -171,6 +171,20 @@ void* empc_host_carrot_create(void* t, const double* state_ref, int32_t n_ref, i
   return hc;
   GUARD_END(nullptr)
 }
+// CarrotMpc stage table (t_stages: n_stages + 1 entries) and transition flags; null arrays => only *n_stages
+int empc_host_carrot_schedule(void* m, int32_t* n_stages, int64_t* t_stages, uint8_t* is_transition) {
+  GUARD_BEGIN
+    auto* c = dynamic_cast<CarrotMpc*>(((HostCarrot*)m)->mpc.get());
+    if (!c) throw std::runtime_error("not a CarrotMpc");
+    const auto& stages = c->get_trajectory()->get_stages();
+    *n_stages = (int32_t)stages.size();
+    if (t_stages) {
+      for (std::size_t i = 0; i < c->get_t_stages().size(); ++i) t_stages[i] = (int64_t)c->get_t_stages()[i];
+      for (std::size_t i = 0; i < stages.size(); ++i) is_transition[i] = stages[i]->get_is_transition() ? 1 : 0;
+    }
+    return 0;
+  GUARD_END(1)
+}
 // WeightedMpc::schedule() in flat arrays; call once with null arrays for dims = {n_stages, n_slots}
 int empc_host_weighted_schedule(void* m, int32_t* dims, int64_t* t_ini, int64_t* t_end, int64_t* duration, double* alpha_beta,
                                 uint8_t* match, uint8_t* task, double* base) {

@@ -23,6 +23,7 @@ def _mlib():
         L.empc_host_rail_create.argtypes = [abi.c_double_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
         L.empc_host_weighted_create.restype = C.c_void_p
         L.empc_host_weighted_create.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32]
+        L.empc_host_carrot_schedule.argtypes = [C.c_void_p, abi.c_int32_p, C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]
         L.empc_host_weighted_schedule.argtypes = [C.c_void_p, abi.c_int32_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                                   C.POINTER(C.c_int64), abi.c_double_p, C.POINTER(C.c_uint8),
                                                   C.POINTER(C.c_uint8), abi.c_double_p]
@@ -109,6 +110,18 @@ class CarrotMpc(_MpcBase):
         ref = np.ascontiguousarray(state_ref, dtype=np.float64)
         self._adopt(_mlib().empc_host_carrot_create(trajectory._p, abi.as_double_p(ref), ref.shape[0], int(dt_ref),
                                                     yaml_path.encode(), int(create_solver)), create_solver)
+
+    def schedule(self):
+        """(t_stages [n_stages + 1] in ms, is_transition [n_stages]) for BatchSolver.set_carrot_schedule"""
+        L = _mlib()
+        n = np.zeros(1, dtype=np.int32)
+        if L.empc_host_carrot_schedule(self._p, abi.as_int32_p(n), None, None):
+            raise EmpcError(_err())
+        t = np.zeros(int(n[0]) + 1, dtype=np.int64); tr = np.zeros(int(n[0]), dtype=np.uint8)
+        if L.empc_host_carrot_schedule(self._p, abi.as_int32_p(n), t.ctypes.data_as(C.POINTER(C.c_int64)),
+                                       tr.ctypes.data_as(C.POINTER(C.c_uint8))):
+            raise EmpcError(_err())
+        return t, tr
 
 
 class RailMpc(_MpcBase):

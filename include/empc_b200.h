@@ -185,6 +185,15 @@ int empc_replicate_instances(empc_solver_t* h, int32_t n_instances);
 int empc_set_reference_trajectory(empc_solver_t* h, const double* state_ref, int32_t n_ref, int32_t dt_ref_ms);
 int empc_rail_retarget(empc_solver_t* h, const int64_t* times_ms /* n_node_maps */, int32_t dt_node_ms);
 
+/* CarrotMpc::updateProblem(current_time) (src/mpc-controllers/carrot-mpc.cpp:298-401) for all instances at once, on the
+ * device.  t_stages (n_stages + 1 entries, ms) is the controller's stage table (:60-75: durations clamped to at least one
+ * knot spacing), is_transition[s] the stage's flag.  Per knot: stage = upper_bound(t_stages, node_time) - 1; inside the
+ * trajectory "carrot_state" is on (with the piecewise-constant state reference of empc_set_reference_trajectory) unless
+ * the stage is a transition stage and the knot is not the last one; past the last stage "carrot_state" is off and
+ * "carrot_tail" on, tracking the last configuration at rest (:376-388).  "carrot_tail" is never switched off (:349-357). */
+int empc_set_carrot_schedule(empc_solver_t* h, int32_t n_stages, const int64_t* t_stages, const uint8_t* is_transition);
+int empc_carrot_retarget(empc_solver_t* h, const int64_t* times_ms /* n_node_maps */, int32_t dt_node_ms);
+
 /* The weight schedule of a WeightedMpc (src/mpc-controllers/weighted-mpc.cpp:173-245) in flat form.  A "slot" is a cost of
  * a knot in the order of its cost set, the squashing barrier excluded; every knot carries the same slots.  For stage s and
  * slot c: match = the cost's name starts with the stage's name (:205) => active, otherwise inactive; task = its weight

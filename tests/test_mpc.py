@@ -338,3 +338,50 @@ def test_weighted_schedule_reproduces_updateProblem():
                 slot += 1
             assert slot == 16
             last = st
+
+
+@pytest.mark.gpu
+def test_device_carrot_retarget_instances_at_different_times():
+    """Same for CarrotMpc (flying arm, config 3's controller): empc_carrot_retarget switches the carrot on the knots that
+    fall into non-transition stages (and on the last knot), moves its reference, and hands over to the tail past the end."""
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    wl = importlib.import_module("eagle-mpc_b200.workloads")
+    tr, fp, xs, us = _trajectory_solution()
+    mpc = mpcmod.CarrotMpc(tr, xs, 20, MPC, create_solver=False)
+    t_st, is_tr = mpc.schedule()
+    assert len(t_st) == len(is_tr) + 1 and t_st[0] == 0 and is_tr[0] == 1 and is_tr[1] == 0
+    times = [0, 1500, 1985, 5200, 7900, 9000]   # before / across the zero-duration way-point stages, the end, the tail
+    B, T = len(times), mpc.knots - 1
+    x0 = np.zeros((B, mpc.nx)); xs_b = np.zeros((B, T + 1, mpc.nx)); us_b = np.zeros((B, T, mpc.nu))
+    for b, t0 in enumerate(times):
+        idx = np.minimum((t0 + mpc.dt * np.arange(T + 1)) // 20, len(xs) - 1)
+        x0[b] = wl.noisy_x0(xs[idx[0]], 1, 2024 + b)[0]
+        xs_b[b] = xs[idx]; xs_b[b, 0] = x0[b]
+        us_b[b] = us[np.minimum(idx[:-1], len(us) - 1)]
+    g = capi.BatchSolver(mpc, B)   # tables as created: carrot and tail off everywhere
+    g.replicate_instances(B)
+    g.set_reference_trajectory(xs, 20)
+    g.set_carrot_schedule((t_st, is_tr))
+    g.carrot_retarget(times, mpc.dt)
+    pg = capi.default_params(); pg.maxiter = mpc.iters; pg.convergence_init = 1e-3
+    g.set_params(pg)
+    g.set_x0(x0); g.set_candidate(xs_b, us_b, False); g.solve()
+    gx, gu, gc, gi = g.xs(), g.us(), g.cost(), g.iters()
+    po = ob.default_params(); po.maxiter = mpc.iters; po.convergence_init = 1e-3
+    ob.lib.orc_update_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Cost), C.c_int, C.c_int, abi.c_double_p]
+    costs_seen = []
+    for b, t0 in enumerate(times):
+        # a fresh controller per instance: "carrot_tail" is never switched off again (carrot-mpc.cpp:349-357), so the
+        # tables depend on the controller's history; the device instances start from the tables as created
+        mpc_b = mpcmod.CarrotMpc(tr, xs, 20, MPC, create_solver=False)
+        mpc_b.updateProblem(t0)
+        costs, pool = mpc_b.cost_tables()
+        o = ob.Oracle(mpc_b); o.set_params(po)
+        ob.lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), ob.dp(pool))
+        o.set_x0(x0[b]); o.solve(xs_b[b], us_b[b])
+        assert int(o.get("iter")) == gi[b], (b, t0)
+        assert abs(gc[b] - o.get("cost")) <= 1e-9 * max(1.0, abs(o.get("cost"))), (b, t0)
+        assert np.abs(gx[b] - o.get("xs")).max() <= 1e-9 * max(1.0, np.abs(o.get("xs")).max()), (b, t0)
+        assert np.abs(gu[b] - o.get("us")).max() <= 1e-9 * max(1.0, np.abs(o.get("us")).max()), (b, t0)
+        costs_seen.append(float(o.get("cost")))
+    assert len({round(c, 6) for c in costs_seen}) > 3
