@@ -44,6 +44,7 @@ def lib():
         L.empc_replicate_instances.argtypes = [C.c_void_p, C.c_int32]
         L.empc_set_reference_trajectory.argtypes = [C.c_void_p, abi.c_double_p, C.c_int32, C.c_int32]
         L.empc_rail_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
+        L.empc_plant_advance.argtypes = [C.c_void_p, C.c_double, abi.c_double_p, abi.c_double_p]
         L.empc_set_carrot_schedule.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]
         L.empc_carrot_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
         L.empc_set_weighted_schedule.argtypes = [C.c_void_p, C.POINTER(abi.WeightedSchedule)]
@@ -168,6 +169,15 @@ class BatchSolver:
         t = np.ascontiguousarray(times_ms, dtype=np.int64)
         assert t.size == getattr(self, "n_instances", 1)
         _ck(lib().empc_weighted_retarget(self.h, t.ctypes.data_as(C.POINTER(C.c_int64)), int(dt_node_ms)))
+
+    def plant_advance(self, dt_s, fetch=True):
+        """x0[b] <- RK4 plant(x0[b], us_squash[b][0], dt) on the device; returns (x_plant, u_applied) if fetch"""
+        if not fetch:
+            _ck(lib().empc_plant_advance(self.h, float(dt_s), None, None))
+            return None
+        x = np.zeros((self.B, self.nx)); u = np.zeros((self.B, self.nu))
+        _ck(lib().empc_plant_advance(self.h, float(dt_s), abi.as_double_p(x), abi.as_double_p(u)))
+        return x, u
 
     # ---- hot path ----
     def solve(self):

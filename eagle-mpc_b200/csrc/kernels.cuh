@@ -310,8 +310,8 @@ __global__ void squash_out_kernel(Buffers bf) {
 // RK4 plant of the closed-loop drivers (bindings/python/eagle_mpc/utils/simulator.py:7-29: IntegratedActionModelRK4 over
 // DifferentialActionModelFreeFwdDynamics with the plain multicopter actuation, no costs).  One thread per instance.
 template <class D>
-__global__ void plant_rk4_kernel(const DevModel* Mp, const double* __restrict__ xin, const double* __restrict__ uin, double dt,
-                                 double* __restrict__ xout, int n) {
+__global__ void plant_rk4_kernel(const DevModel* Mp, const double* xin, const double* __restrict__ uin, double dt, double* xout, int n,
+                                 size_t u_stride) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   const DevModel& M = *Mp;
@@ -319,7 +319,7 @@ __global__ void plant_rk4_kernel(const DevModel* Mp, const double* __restrict__ 
 #pragma unroll
   for (int i = 0; i < D::NX; ++i) x[i] = xin[(size_t)b * D::NX + i];
 #pragma unroll
-  for (int i = 0; i < D::NU; ++i) u[i] = uin[(size_t)b * D::NU + i];
+  for (int i = 0; i < D::NU; ++i) u[i] = uin[(size_t)b * u_stride + i];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     double t = 0;

@@ -803,14 +803,33 @@ static int plant_impl(empc_solver* h, const double* x, const double* u, double d
   CK(cudaMalloc(&dx_, sizeof(double) * n * h->nx)); CK(cudaMalloc(&du_, sizeof(double) * n * h->nu)); CK(cudaMalloc(&dxn_, sizeof(double) * n * h->nx));
   CK(cudaMemcpyAsync(dx_, x, sizeof(double) * n * h->nx, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(du_, u, sizeof(double) * n * h->nu, cudaMemcpyHostToDevice, h->stream));
-  plant_rk4_kernel<D><<<(n + 63) / 64, 64, 0, h->stream>>>(h->d_model, dx_, du_, dt, dxn_, n);
+  plant_rk4_kernel<D><<<(n + 63) / 64, 64, 0, h->stream>>>(h->d_model, dx_, du_, dt, dxn_, n, (size_t)h->nu);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(xnext, dxn_, sizeof(double) * n * h->nx, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(dx_); cudaFree(du_); cudaFree(dxn_);
   return EMPC_OK;
 }
+// device-resident closed loop: x0[b] <- RK4(x0[b], us_squash[b][0], dt)
+template <class D>
+static int plant_advance_impl(empc_solver* h, double dt, double* x_plant, double* u_applied) {
+  plant_rk4_kernel<D><<<(h->B + 63) / 64, 64, 0, h->stream>>>(h->d_model, h->d_x0, h->bf.us_squash, dt, h->d_x0, h->B, (size_t)h->T * h->nu);
+  CK(cudaGetLastError());
+  if (x_plant) CK(cudaMemcpyAsync(x_plant, h->d_x0, sizeof(double) * h->B * h->nx, cudaMemcpyDeviceToHost, h->stream));
+  if (u_applied)
+    CK(cudaMemcpy2DAsync(u_applied, sizeof(double) * h->nu, h->bf.us_squash, sizeof(double) * h->T * h->nu, sizeof(double) * h->nu, (size_t)h->B,
+                         cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMPC_OK;
+}
 extern "C" {
+int empc_plant_advance(empc_solver_t* h, double dt, double* x_plant, double* u_applied) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  if (!(dt > 0)) return fail(EMPC_ERR_INVALID, "dt <= 0");
+  CK(cudaSetDevice(h->device));
+  EMPC_DISPATCH(h, return plant_advance_impl<D>(h, dt, x_plant, u_applied));
+  return EMPC_OK;
+}
 int empc_plant_step(empc_solver_t* h, const double* x, const double* u, double dt, double* xnext, int32_t n) {
   if (!h || !x || !u || !xnext || n <= 0) return fail(EMPC_ERR_INVALID, "null / bad count");
   CK(cudaSetDevice(h->device));

@@ -224,6 +224,14 @@ int empc_reset(empc_solver_t* h);
  * instances, x (n*nx), u (n*nu, thrusts and joint torques actually applied), dt in seconds; host pointers. */
 int empc_plant_step(empc_solver_t* h, const double* x, const double* u, double dt, double* xnext, int32_t n);
 
+/* Device-resident closed loop for a batch of controller instances (examples/python/mpc.py:49-61, all instances at once):
+ * every OCP's plant state (its x0) is advanced by one RK4 step of dt seconds under the first squashed control of its
+ * current solution, x0[b] <- plant(x0[b], us_squash[b][0], dt), and becomes the initial state of the next empc_solve,
+ * which warm-starts from the solution left on the device (solver.solve(solver.xs, solver.us, iters)).  A closed-loop
+ * step is: empc_*_retarget(times) -> empc_solve -> empc_plant_advance.  x_plant (batch*nx) and u_applied (batch*nu) are
+ * optional host outputs (NULL to skip the copies). */
+int empc_plant_advance(empc_solver_t* h, double dt, double* x_plant, double* u_applied);
+
 /* ---- outputs (host pointers) ---- */
 int empc_get_xs(const empc_solver_t* h, double* xs /* batch*(T+1)*nx */);
 int empc_get_us(const empc_solver_t* h, double* us /* batch*T*nu */);

@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--t0", type=int, default=1000, help="controller time (ms) at which the instances are solved")
     ap.add_argument("--spread", action="store_true",
                     help="every instance at its own controller time, retargeted on the device (empc_rail_retarget / empc_weighted_retarget)")
+    ap.add_argument("--closed-loop", action="store_true",
+                    help="device-resident closed loop of B controllers at different times: retarget -> warm solve -> RK4 plant")
     args = ap.parse_args()
     # reference trajectory: iris_px4 displacement solved by the B200 path itself (B = 1, maxiter 400)
     tr = host.Trajectory(TRAJ)
@@ -47,6 +49,8 @@ def main():
     B = args.batch
     if args.spread:
         return spread(args, xs, us, tmpdir)
+    if args.closed_loop:
+        return closed_loop(args, xs, us)
     for kind in ("rail", "weighted"):
         for knots in args.knots:
             y = yaml_with_knots(knots, tmpdir)
@@ -78,6 +82,62 @@ def main():
                               "ms_per_batched_mpc_step": 1e3 * t_tot / args.steps, "ocp_iterations_per_s": it_tot / t_tot,
                               "us_per_instance_step": 1e6 * t_tot / args.steps / B}))
             g.close()
+
+
+def closed_loop(args, xs_iris, us_iris):
+    """examples/python/mpc.py:49-61 for B controllers at once, everything device-resident between steps: per step one
+    retarget kernel, one warm-started batched solve (mpc.yaml iters), one RK4 plant kernel (2 ms); only the B controller
+    times go to the device and the applied controls / plant states come back."""
+    B, dt_sim = args.batch, 2
+    cases = [("rail", "iris_px4", TRAJ, MPC_YAML, xs_iris, us_iris)]
+    arm_traj = "hexacopter370_flying_arm_3/trajectories/displacement.yaml"
+    tr = host.Trajectory(arm_traj); fp = tr.createProblem(20)
+    s1 = capi.BatchSolver(fp, 1); p = capi.default_params(); p.maxiter = 400
+    s1.set_params(p); s1.set_x0(fp.x0); s1.set_candidate(None, None, False); s1.solve()
+    xa, ua = s1.xs()[0], s1.us()[0]; s1.close()
+    cases.append(("carrot", "hexacopter370_flying_arm_3", arm_traj, "hexacopter370_flying_arm_3/mpc/mpc.yaml", xa, ua))
+    cases.append(("weighted", "iris_px4", TRAJ, MPC_YAML, xs_iris, us_iris))
+    for kind, robot, traj, yaml, xs, us in cases:
+        if kind == "rail":
+            mpc = mpcmod.RailMpc(xs, 20, yaml, create_solver=False)
+        elif kind == "carrot":
+            mpc = mpcmod.CarrotMpc(host.Trajectory(traj), xs, 20, yaml, create_solver=False)
+        else:
+            mpc = mpcmod.WeightedMpc(host.Trajectory(traj), 20, yaml, create_solver=False)
+        T = mpc.knots - 1
+        t_end = 20 * (len(xs) - 1)
+        times = ((7 * np.arange(B)) % t_end).astype(np.int64)
+        idx = np.minimum((times[:, None] + mpc.dt * np.arange(T + 1)[None, :]) // 20, len(xs) - 1)
+        xs_b = xs[idx]; us_b = us[np.minimum(idx[:, :-1], len(us) - 1)]
+        x0 = xs_b[:, 0].copy()
+        g = capi.BatchSolver(mpc, B)
+        g.replicate_instances(B)
+        if kind == "rail":
+            g.set_reference_trajectory(xs, 20); retarget = g.rail_retarget
+        elif kind == "carrot":
+            g.set_reference_trajectory(xs, 20); g.set_carrot_schedule(mpc.schedule()); retarget = g.carrot_retarget
+        else:
+            g.set_weighted_schedule(mpc.schedule()); retarget = g.weighted_retarget
+        retarget(times, mpc.dt)
+        pr = capi.default_params(); pr.maxiter = 100; pr.convergence_init = 1e-2
+        g.set_params(pr); g.set_x0(x0); g.set_candidate(xs_b, us_b, False); g.solve()
+        pr.maxiter = mpc.iters; pr.convergence_init = 1e-3
+        g.set_params(pr)
+        lat, its = [], 0
+        n_steps = 10 * args.steps
+        for step in range(n_steps + 5):
+            t1 = time.perf_counter()
+            retarget(times, mpc.dt); g.solve(); g.plant_advance(dt_sim / 1000.0)
+            t2 = time.perf_counter()
+            if step >= 5:
+                lat.append(t2 - t1); its += g.total_iterations()
+            times += dt_sim
+        lat = np.array(lat)
+        print(json.dumps({"controller": kind, "robot": robot, "mode": "device-resident closed loop", "knots": mpc.knots, "batch": B,
+                          "steps": n_steps, "iters_per_instance_step": its / n_steps / B,
+                          "ms_per_batched_step_p50": 1e3 * float(np.median(lat)), "ms_per_batched_step_p95": 1e3 * float(np.percentile(lat, 95)),
+                          "instance_steps_per_s": B / float(np.median(lat)), "us_per_instance_step": 1e6 * float(np.median(lat)) / B}))
+        g.close()
 
 
 def spread(args, xs, us, tmpdir):

@@ -195,7 +195,7 @@ def R_to_quat(R):
     R = np.ascontiguousarray(R, dtype=np.float64); q = np.zeros(4); lib.orc_R_to_quat(dp(R), dp(q)); return q
 
 
-def oracle_closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, record=False):
+def oracle_closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, record=False, t_start=0, xs_warm=None, us_warm=None):
     """CPU twin of eagle-mpc_b200.mpc.closed_loop: same host-side CarrotMpc retargeting (created without a solver),
     oracle solves and oracle RK4 plant."""
     import time
@@ -209,14 +209,15 @@ def oracle_closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, rec
         lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), dp(pool))
 
     p = default_params()
-    mpc.updateProblem(0); push()
+    mpc.updateProblem(int(t_start)); push()
     p.maxiter = 100; p.convergence_init = 1e-2
-    o.set_params(p); o.set_x0(x_start); o.solve(xs_traj[:T + 1], us_traj[:T])
+    o.set_params(p); o.set_x0(x_start)
+    o.solve(xs_traj[:T + 1] if xs_warm is None else xs_warm, us_traj[:T] if us_warm is None else us_warm)
     p.maxiter = mpc.iters; p.convergence_init = 1e-3
     o.set_params(p)
     x = np.array(x_start, dtype=np.float64)
     lat, states, controls, iters = [], [x.copy()], [], []
-    t = 0
+    t = int(t_start)
     for _ in range(n_steps):
         t0 = time.perf_counter()
         mpc.updateProblem(int(t)); push()

@@ -385,3 +385,45 @@ def test_device_carrot_retarget_instances_at_different_times():
         assert np.abs(gu[b] - o.get("us")).max() <= 1e-9 * max(1.0, np.abs(o.get("us")).max()), (b, t0)
         costs_seen.append(float(o.get("cost")))
     assert len({round(c, 6) for c in costs_seen}) > 3
+
+
+@pytest.mark.gpu
+def test_batched_device_closed_loop_rail():
+    """Device-resident closed loop of several rail controllers that are at different points of the trajectory
+    (retarget -> warm solve -> RK4 plant advance, no host round trip of states or warm starts) against the oracle twin
+    of examples/python/mpc.py run once per instance."""
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    _tr, fp, xs, us = _iris_solution()
+    mpc = mpcmod.RailMpc(xs, 20, IRIS_MPC, create_solver=False)
+    starts = [0, 1000, 3010, 7000]
+    n_steps, dt_sim = 12, 2
+    B, T = len(starts), mpc.knots - 1
+    x0 = np.zeros((B, mpc.nx)); xs_b = np.zeros((B, T + 1, mpc.nx)); us_b = np.zeros((B, T, mpc.nu))
+    for b, t0 in enumerate(starts):
+        idx = np.minimum(t0 // 20 + np.arange(T + 1), len(xs) - 1)
+        x0[b] = xs[idx[0]]; xs_b[b] = xs[idx]; us_b[b] = us[np.minimum(idx[:-1], len(us) - 1)]
+    g = capi.BatchSolver(mpc, B)
+    g.replicate_instances(B)
+    g.set_reference_trajectory(xs, 20)
+    times = np.array(starts, dtype=np.int64)
+    g.rail_retarget(times, mpc.dt)
+    pg = capi.default_params(); pg.maxiter = 100; pg.convergence_init = 1e-2
+    g.set_params(pg); g.set_x0(x0); g.set_candidate(xs_b, us_b, False); g.solve()
+    pg.maxiter = mpc.iters; pg.convergence_init = 1e-3
+    g.set_params(pg)
+    st_g, u_g, it_g = [x0.copy()], [], []
+    for _ in range(n_steps):
+        g.rail_retarget(times, mpc.dt)
+        g.solve()
+        it_g.append(g.iters().copy())
+        x, u = g.plant_advance(dt_sim / 1000.0)
+        st_g.append(x); u_g.append(u)
+        times += dt_sim
+    st_g, u_g, it_g = np.array(st_g), np.array(u_g), np.array(it_g)
+    for b, t0 in enumerate(starts):
+        mpc_o = mpcmod.RailMpc(xs, 20, IRIS_MPC, create_solver=False)
+        _lat, st_o, u_o, it_o = ob.oracle_closed_loop(mpc_o, xs, us, x0[b], n_steps, dt_sim_ms=dt_sim, record=True, t_start=t0,
+                                                       xs_warm=xs_b[b], us_warm=us_b[b])
+        assert list(it_g[:, b]) == it_o, (b, t0)
+        assert np.abs(u_g[:, b] - u_o).max() <= 1e-7 * max(1.0, np.abs(u_o).max()), (b, t0)
+        assert np.abs(st_g[:, b] - st_o).max() <= 1e-8 * max(1.0, np.abs(st_o).max()), (b, t0)
