@@ -18,7 +18,7 @@ $(PKG)/host/%.o: $(PKG)/host/%.cpp $(PKG)/host/eagle_mpc.hpp $(PKG)/host/mpc.hpp
 
 $(LIB): $(CU_OBJ) $(HOST_OBJ)
 	mkdir -p $(PKG)/lib
-	$(NVCC) -shared -o $@ $(CU_OBJ) $(HOST_OBJ) -ldl
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(CU_OBJ) $(HOST_OBJ) -ldl
 
 oracle:
 	$(MAKE) -C oracle
