@@ -340,6 +340,11 @@ def main():
             sec, it, _c = ob.solve_batch(fp, x0[:n], cores)
             out["cpu_baseline"] = {"value": float(it.sum() / sec), "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"first {n} OCPs of the same batch, {cores} host threads, {sec:.1f} s; CPU restatement (oracle/), not Crocoddyl itself"}
+            # also the way the reference itself runs -- one OCP at a time on one thread
+            n1 = max(8, min(48, n))
+            sec1, it1, _c1 = ob.solve_batch(fp, x0[:n1], 1)
+            out["cpu_baseline"]["single_thread"] = {"value": float(it1.sum() / sec1), "unit": UNIT, "cores": 1,
+                                                    "sample": f"first {n1} OCPs, one at a time on one thread, {sec1:.1f} s"}
         if world == 1 and not args.no_mpc:
             solver.close()
             out["mpc_step_latency"] = mpc_latency(args.mpc_steps, not args.no_cpu_baseline)
