@@ -105,7 +105,7 @@ __device__ __forceinline__ void end_inner_solve(OcpState& st, const empc_solver_
 // (thread per node), thread 0 adds them in node order (cost_try_) and applies the acceptance test — and the loop stops at
 // the first accepted step, so the costs of the later, speculative rollouts are never computed.
 template <class D>
-__global__ void __launch_bounds__(128, 4) decide_kernel(Buffers bf, DecideParams dp, const __grid_constant__ DevModel M) {
+__global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams dp, const __grid_constant__ DevModel M) {
   constexpr int NX = D::NX, NU = D::NU;
   constexpr int CH = 512;  // nodes per chunk of the ordered cost sum
   const int b = bf.b0 + blockIdx.x;

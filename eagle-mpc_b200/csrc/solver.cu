@@ -571,7 +571,16 @@ static cudaError_t launch_decide(empc_solver* h, int stage, const Buffers* gb = 
   const Buffers& bf = gb ? *gb : h->bf;
   if (!st) st = h->stream;
   DecideParams dp{h->P, stage};
-  decide_kernel<D><<<bf.nb, 128, 0, st>>>(bf, dp, h->hmodel);
+  // one block per OCP, one node per thread and round: the block size (a multiple of 32, at most 256) that wastes the fewest
+  // thread slots over the ceil((T+1)/threads) rounds of the trial-cost evaluation; ties go to the larger block
+  const int T1 = h->T + 1;
+  int threads = 128; double best = 0.0;
+  for (int n = 32; n <= 256; n += 32) {
+    const int rounds = (T1 + n - 1) / n;
+    const double eff = (double)T1 / ((double)rounds * n);
+    if (eff >= best - 1e-12) { best = eff; threads = n; }
+  }
+  decide_kernel<D><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
   h->launches++;
   return cudaGetLastError();
 }
