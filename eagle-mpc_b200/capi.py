@@ -49,6 +49,8 @@ def lib():
         L.empc_carrot_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
         L.empc_set_weighted_schedule.argtypes = [C.c_void_p, C.POINTER(abi.WeightedSchedule)]
         L.empc_weighted_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
+        L.empc_get_solution.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p,
+                                        abi.c_double_p, abi.c_int32_p, abi.c_int32_p]
         L.empc_get_total_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.empc_get_launch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), abi.c_double_p]
         L.empc_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
@@ -213,6 +215,15 @@ class BatchSolver:
     def Vx(self): return self._get("Vx", (self.B, self.T + 1, self.ndx))
     def Vxx_fs(self): return self._get("Vxx_fs", (self.B, self.T + 1, self.ndx))
     def dgdq(self): return self._get("dgdq", (self.B, 2))
+
+    def solution(self):
+        """(xs, us, us_squash, cost, stop, iters, feasible) in one call (one packed copy for small batches)"""
+        xs = np.zeros((self.B, self.T + 1, self.nx)); us = np.zeros((self.B, self.T, self.nu)); uss = np.zeros_like(us)
+        cost = np.zeros(self.B); stop = np.zeros(self.B)
+        it = np.zeros(self.B, dtype=np.int32); fe = np.zeros(self.B, dtype=np.int32)
+        _ck(lib().empc_get_solution(self.h, abi.as_double_p(xs), abi.as_double_p(us), abi.as_double_p(uss), abi.as_double_p(cost),
+                                    abi.as_double_p(stop), abi.as_int32_p(it), abi.as_int32_p(fe)))
+        return xs, us, uss, cost, stop, it, fe
 
     def total_iterations(self):
         v = C.c_int64()

@@ -359,6 +359,19 @@ __global__ void plant_rk4_kernel(const DevModel* Mp, const double* xin, const do
   for (int i = 0; i < D::NX; ++i) xout[(size_t)b * D::NX + i] = xn[i];
 }
 
+// empc_get_solution for small batches: xs | us | us_squash | per-OCP (cost, stop, iter, is_feasible) packed into one
+// buffer, so that an MPC step reads its result with a single device-to-host copy
+__global__ void pack_solution_kernel(Buffers bf, double* __restrict__ out, size_t nxs, size_t nus) {
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = gridDim.x * (size_t)blockDim.x;
+  for (size_t i = tid; i < nxs; i += nth) out[i] = bf.xs[i];
+  for (size_t i = tid; i < nus; i += nth) { out[nxs + i] = bf.us[i]; out[nxs + nus + i] = bf.us_squash[i]; }
+  double* sc = out + nxs + 2 * nus;
+  for (size_t b = tid; b < (size_t)bf.B; b += nth) {
+    const OcpState& s = bf.st[b];
+    sc[4 * b] = s.cost; sc[4 * b + 1] = s.stop; sc[4 * b + 2] = (double)s.iters_out; sc[4 * b + 3] = (double)s.is_feasible;
+  }
+}
+
 // SolverAbstract::setCandidate with empty warm starts: xs[t] = state.zero(), us[t] = 0
 __global__ void zero_candidate_kernel(double* xs, size_t n_states, int nx) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

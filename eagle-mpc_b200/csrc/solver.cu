@@ -48,6 +48,7 @@ struct empc_solver {
   long long* d_t_stages = nullptr; unsigned char* d_is_transition = nullptr; int n_stages = 0;  // carrot schedule
   int n_ref = 0, dt_ref_ms = 0;
   long long* d_times = nullptr;   // n_node_maps controller times
+  double *d_pack = nullptr, *h_pack = nullptr;  // empc_get_solution staging (small batches)
   WeightedScheduleDev wsched = {0, 0, nullptr, nullptr, 0, 0.0, 0.0, nullptr, nullptr, nullptr};
   int init_feasible = 0;
   cudaStream_t stream = nullptr;
@@ -128,6 +129,7 @@ int empc_destroy(empc_solver_t* h) {
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_active) cudaFreeHost(h->h_active);
+  if (h->h_pack) cudaFreeHost(h->h_pack);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_solve) if (e) cudaEventDestroy(e);
   for (int g = 0; g < empc_solver::MAXG; ++g) {
@@ -310,9 +312,11 @@ int empc_set_params(empc_solver_t* h, const empc_solver_params_t* p) {
   if (!h || !p) return fail(EMPC_ERR_INVALID, "null");
   if (p->maxiter < 1) return fail(EMPC_ERR_INVALID, "maxiter < 1");
   h->P = *p;
-  h->hmodel.barrier_weight = p->barrier_weight;
-  CK(cudaSetDevice(h->device));
-  CK(cudaMemcpy(h->d_model, &h->hmodel, sizeof(DevModel), cudaMemcpyHostToDevice));
+  if (h->hmodel.barrier_weight != p->barrier_weight) {  // the device copy of the model only changes with this field
+    h->hmodel.barrier_weight = p->barrier_weight;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(h->d_model, &h->hmodel, sizeof(DevModel), cudaMemcpyHostToDevice));
+  }
   return EMPC_OK;
 }
 
@@ -768,6 +772,48 @@ int empc_get_stop(const empc_solver_t* h, double* o) {
 int empc_get_feasible(const empc_solver_t* h, int32_t* o) {
   std::vector<OcpState> st; int rc = get_states(h, st); if (rc) return rc;
   for (int b = 0; b < h->B; ++b) o[b] = st[b].is_feasible;
+  return EMPC_OK;
+}
+int empc_get_solution(empc_solver_t* h, double* xs, double* us, double* us_squash, double* cost, double* stop, int32_t* iters,
+                      int32_t* feasible) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  const size_t nxs = (size_t)h->B * (h->T + 1) * h->nx, nus = (size_t)h->B * h->T * h->nu, total = nxs + 2 * nus + 4 * (size_t)h->B;
+  if (total * sizeof(double) > (8u << 20)) {  // large batches: plain copies straight into the caller's buffers
+    int rc = 0;
+    if (xs && (rc = empc_get_xs(h, xs))) return rc;
+    if (us && (rc = empc_get_us(h, us))) return rc;
+    if (us_squash && (rc = empc_get_us_squash(h, us_squash))) return rc;
+    if (cost || stop || iters || feasible) {
+      std::vector<OcpState> st; rc = get_states(h, st); if (rc) return rc;
+      for (int b = 0; b < h->B; ++b) {
+        if (cost) cost[b] = st[b].cost;
+        if (stop) stop[b] = st[b].stop;
+        if (iters) iters[b] = st[b].iters_out;
+        if (feasible) feasible[b] = st[b].is_feasible;
+      }
+    }
+    return EMPC_OK;
+  }
+  CK(cudaSetDevice(h->device));
+  if (!h->d_pack) {
+    CK(dalloc(h, &h->d_pack, total));
+    CK(cudaMallocHost((void**)&h->h_pack, total * sizeof(double)));
+  }
+  pack_solution_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 592), 256, 0, h->stream>>>(h->bf, h->d_pack, nxs, nus);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_pack, h->d_pack, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const double* p = h->h_pack;
+  if (xs) std::memcpy(xs, p, nxs * sizeof(double));
+  if (us) std::memcpy(us, p + nxs, nus * sizeof(double));
+  if (us_squash) std::memcpy(us_squash, p + nxs + nus, nus * sizeof(double));
+  const double* sc = p + nxs + 2 * nus;
+  for (int b = 0; b < h->B; ++b) {
+    if (cost) cost[b] = sc[4 * b];
+    if (stop) stop[b] = sc[4 * b + 1];
+    if (iters) iters[b] = (int32_t)sc[4 * b + 2];
+    if (feasible) feasible[b] = (int32_t)sc[4 * b + 3];
+  }
   return EMPC_OK;
 }
 int empc_get_reg(const empc_solver_t* h, double* o) {

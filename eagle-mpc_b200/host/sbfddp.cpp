@@ -78,14 +78,13 @@ void SolverSbFDDP::setCandidate(const std::vector<VectorXd>& xs_warm, const std:
 void SolverSbFDDP::fetch(bool with_gains) {
   const std::size_t T = problem_->get_T(), nx = (std::size_t)problem_->state->get_nx(), nu = squashing_model_->get_ns(),
                     ndx = (std::size_t)problem_->state->get_ndx(), B = (std::size_t)batch_;
-  std::vector<double> buf(B * (T + 1) * nx);
-  ck(empc_get_xs(handle_, buf.data()), "empc_get_xs");
+  std::vector<double> buf(B * (T + 1) * nx), ub(B * T * nu), sb(B * T * nu), c(B), s(B);
+  std::vector<int32_t> it(B), fe(B);
+  ck(empc_get_solution(handle_, buf.data(), ub.data(), sb.data(), c.data(), s.data(), it.data(), fe.data()), "empc_get_solution");
   for (std::size_t t = 0; t <= T; ++t) xs_[t].assign(buf.begin() + t * nx, buf.begin() + (t + 1) * nx);
+  for (std::size_t t = 0; t < T; ++t) us_[t].assign(ub.begin() + t * nu, ub.begin() + (t + 1) * nu);
+  for (std::size_t t = 0; t < T; ++t) us_squash_[t].assign(sb.begin() + t * nu, sb.begin() + (t + 1) * nu);
   buf.resize(B * T * nu);
-  ck(empc_get_us(handle_, buf.data()), "empc_get_us");
-  for (std::size_t t = 0; t < T; ++t) us_[t].assign(buf.begin() + t * nu, buf.begin() + (t + 1) * nu);
-  ck(empc_get_us_squash(handle_, buf.data()), "empc_get_us_squash");
-  for (std::size_t t = 0; t < T; ++t) us_squash_[t].assign(buf.begin() + t * nu, buf.begin() + (t + 1) * nu);
   if (with_gains) {
     ck(empc_get_k(handle_, buf.data()), "empc_get_k");
     for (std::size_t t = 0; t < T; ++t) k_[t].assign(buf.begin() + t * nu, buf.begin() + (t + 1) * nu);
@@ -93,12 +92,6 @@ void SolverSbFDDP::fetch(bool with_gains) {
     ck(empc_get_K(handle_, buf.data()), "empc_get_K");
     for (std::size_t t = 0; t < T; ++t) K_[t].assign(buf.begin() + t * nu * ndx, buf.begin() + (t + 1) * nu * ndx);
   }
-  std::vector<double> c(B), s(B);
-  std::vector<int32_t> it(B), fe(B);
-  ck(empc_get_cost(handle_, c.data()), "empc_get_cost");
-  ck(empc_get_stop(handle_, s.data()), "empc_get_stop");
-  ck(empc_get_iters(handle_, it.data()), "empc_get_iters");
-  ck(empc_get_feasible(handle_, fe.data()), "empc_get_feasible");
   cost_ = c[0]; stop_ = s[0]; iter_ = (std::size_t)it[0]; is_feasible_ = fe[0] != 0;
 }
 

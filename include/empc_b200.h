@@ -243,6 +243,10 @@ int empc_get_iters(const empc_solver_t* h, int32_t* iters /* batch: iter_ as lef
 int empc_get_stop(const empc_solver_t* h, double* stop /* batch */);
 int empc_get_feasible(const empc_solver_t* h, int32_t* feasible /* batch */);
 int empc_get_reg(const empc_solver_t* h, double* xreg /* batch */);
+/* Everything SolverSbFDDP::solve leaves behind for the MPC loop (get_xs, get_us, getSquashControls, get_cost, get_stop,
+ * get_iter, is_feasible) in one call; any pointer may be NULL.  Small batches travel as one packed device-to-host copy. */
+int empc_get_solution(empc_solver_t* h, double* xs, double* us, double* us_squash, double* cost, double* stop, int32_t* iters,
+                      int32_t* feasible);
 /* total inner iterations executed by the last solve, summed over the batch (the benchmark's work unit) */
 int empc_get_total_iterations(const empc_solver_t* h, int64_t* total);
 /* number of kernel launches issued by the last solve and device time (ms) spent per kernel family:

@@ -41,6 +41,8 @@ def test_full_batch_properties_and_sampled_parity(name, B, T, dims):
     g.solve()
     xs, us, uss, cost, iters, feas = g.xs(), g.us(), g.us_squash(), g.cost(), g.iters(), g.feasible()
     assert np.isfinite(cost).all() and np.isfinite(xs).all() and np.isfinite(us).all()
+    for a, b_ in zip(g.solution(), (xs, us, uss, cost, g.stop(), iters, feas)):   # large-batch path of empc_get_solution
+        assert np.array_equal(a, b_)
     assert (feas == 1).all()
     assert (iters >= 1).all() and (iters < 100).all()           # nobody ran into maxiter
     assert g.total_iterations() == int((iters + 1).sum())       # iter_ = total_iters_ - 1 (src/sbfddp.cpp:222)

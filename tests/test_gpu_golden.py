@@ -30,6 +30,9 @@ def test_gpu_matches_golden(name):
     assert (g.T, g.nx, g.nu) == (gold["T"], gold["nx"], gold["nu"])
     g.set_x0(x0); g.set_candidate(None, None, False); g.solve()
     xs, us, K, cost, iters, feas = g.xs(), g.us(), g.K(), g.cost(), g.iters(), g.feasible()
+    # the packed one-call getter returns the same bits as the individual ones
+    for a, b_ in zip(g.solution(), (xs, us, g.us_squash(), cost, g.stop(), iters, feas)):
+        assert np.array_equal(a, b_)
     for b, r in enumerate(recs):
         if name == "hexacopter370_hover" and b > 0:
             # perturbed hover starts crawl for 30+ iterations: iteration count pinned, values to 1e-8
