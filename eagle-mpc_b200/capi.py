@@ -49,6 +49,7 @@ def lib():
         L.empc_carrot_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
         L.empc_set_weighted_schedule.argtypes = [C.c_void_p, C.POINTER(abi.WeightedSchedule)]
         L.empc_weighted_retarget.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
+        L.empc_get_cost_tables.argtypes = [C.c_void_p, C.POINTER(abi.Cost), abi.c_double_p]
         L.empc_get_solution.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p,
                                         abi.c_double_p, abi.c_int32_p, abi.c_int32_p]
         L.empc_get_total_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -215,6 +216,12 @@ class BatchSolver:
     def Vx(self): return self._get("Vx", (self.B, self.T + 1, self.ndx))
     def Vxx_fs(self): return self._get("Vxx_fs", (self.B, self.T + 1, self.ndx))
     def dgdq(self): return self._get("dgdq", (self.B, 2))
+
+    def cost_tables(self, n_costs, n_pool):
+        """the device's cost records and pool (sizes: those of the problem times the number of instances)"""
+        costs = (abi.Cost * n_costs)(); pool = np.zeros(n_pool)
+        _ck(lib().empc_get_cost_tables(self.h, costs, abi.as_double_p(pool)))
+        return costs, pool
 
     def solution(self):
         """(xs, us, us_squash, cost, stop, iters, feasible) in one call (one packed copy for small batches)"""

@@ -774,6 +774,13 @@ int empc_get_feasible(const empc_solver_t* h, int32_t* o) {
   for (int b = 0; b < h->B; ++b) o[b] = st[b].is_feasible;
   return EMPC_OK;
 }
+int empc_get_cost_tables(const empc_solver_t* h, empc_cost_t* costs, double* pool) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  int rc = 0;
+  if (costs && h->n_costs && (rc = d2h(h, costs, h->d_costs, sizeof(empc_cost_t) * h->n_costs))) return rc;
+  if (pool && h->n_pool && (rc = d2h(h, pool, h->d_pool, sizeof(double) * h->n_pool))) return rc;
+  return EMPC_OK;
+}
 int empc_get_solution(empc_solver_t* h, double* xs, double* us, double* us_squash, double* cost, double* stop, int32_t* iters,
                       int32_t* feasible) {
   if (!h) return fail(EMPC_ERR_INVALID, "null");

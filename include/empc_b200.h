@@ -243,6 +243,9 @@ int empc_get_iters(const empc_solver_t* h, int32_t* iters /* batch: iter_ as lef
 int empc_get_stop(const empc_solver_t* h, double* stop /* batch */);
 int empc_get_feasible(const empc_solver_t* h, int32_t* feasible /* batch */);
 int empc_get_reg(const empc_solver_t* h, double* xreg /* batch */);
+/* The cost tables as they currently are on the device (after empc_update_costs / empc_replicate_instances / the retarget
+ * kernels): n_costs records and n_pool doubles, both as passed to empc_create times the number of instances.  For tests. */
+int empc_get_cost_tables(const empc_solver_t* h, empc_cost_t* costs, double* pool);
 /* Everything SolverSbFDDP::solve leaves behind for the MPC loop (get_xs, get_us, getSquashControls, get_cost, get_stop,
  * get_iter, is_feasible) in one call; any pointer may be NULL.  Small batches travel as one packed device-to-host copy. */
 int empc_get_solution(empc_solver_t* h, double* xs, double* us, double* us_squash, double* cost, double* stop, int32_t* iters,

@@ -427,3 +427,64 @@ def test_batched_device_closed_loop_rail():
         assert list(it_g[:, b]) == it_o, (b, t0)
         assert np.abs(u_g[:, b] - u_o).max() <= 1e-7 * max(1.0, np.abs(u_o).max()), (b, t0)
         assert np.abs(st_g[:, b] - st_o).max() <= 1e-8 * max(1.0, np.abs(st_o).max()), (b, t0)
+
+
+# ---- golden cost tables (tests/golden/mpc_cost_tables.json, written by tests/golden/make_golden_mpc.py) --------------------
+GOLD_CASES = {"carrot": (TRAJ, MPC), "rail": (IRIS_TRAJ, IRIS_MPC), "weighted": (IRIS_TRAJ, IRIS_MPC)}
+
+
+def _gold_controller(kind, tr, xs):
+    traj_yaml, mpc_yaml = GOLD_CASES[kind]
+    if kind == "carrot":
+        return mpcmod.CarrotMpc(tr, xs, 20, mpc_yaml, create_solver=False)
+    if kind == "rail":
+        return mpcmod.RailMpc(xs, 20, mpc_yaml, create_solver=False)
+    return mpcmod.WeightedMpc(host.Trajectory(traj_yaml), 20, mpc_yaml, create_solver=False)
+
+
+def _check_table(costs, pool, nx, gold, tag):
+    """active flags always; weights and reference checksums of the active records (inactive ones keep stale values)"""
+    assert len(costs) == len(gold), tag
+    for i, (c, g) in enumerate(zip(costs, gold)):
+        assert (c.type, c.active) == (g[0], g[1]), (tag, i)
+        if c.active:
+            assert abs(c.weight - g[2]) <= 4e-16 * abs(g[2]), (tag, i, c.weight, g[2])   # device exp(): last-bit differences
+            if c.type == abi.COST_STATE and c.ref_off >= 0:
+                ref = pool[c.ref_off:c.ref_off + nx]
+                assert float(np.dot(ref, np.arange(1, nx + 1))) == g[3], (tag, i)
+
+
+@pytest.mark.parametrize("kind", ["carrot", "rail", "weighted"])
+def test_host_retargeting_matches_golden_tables(kind):
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpc_cost_tables.json")))[kind]
+    tr, _fp, xs, _us = _trajectory_solution() if kind == "carrot" else _iris_solution()
+    for t, g in gold.items():
+        mpc = _gold_controller(kind, tr, xs)
+        mpc.updateProblem(int(t))
+        costs, pool = mpc.cost_tables()
+        _check_table(costs, pool, mpc.nx, g, (kind, t))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["carrot", "rail", "weighted"])
+def test_device_retargeting_matches_golden_tables(kind):
+    """The tables the retarget kernels leave on the device, read back and compared with the committed golden tables
+    (no oracle, no host retargeting at run time)."""
+    import json, os
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpc_cost_tables.json")))[kind]
+    tr, _fp, xs, _us = _trajectory_solution() if kind == "carrot" else _iris_solution()
+    mpc = _gold_controller(kind, tr, xs)
+    times = [int(t) for t in gold]
+    g = capi.BatchSolver(mpc, len(times))
+    g.replicate_instances(len(times))
+    if kind == "rail":
+        g.set_reference_trajectory(xs, 20); g.rail_retarget(times, mpc.dt)
+    elif kind == "carrot":
+        g.set_reference_trajectory(xs, 20); g.set_carrot_schedule(mpc.schedule()); g.carrot_retarget(times, mpc.dt)
+    else:
+        g.set_weighted_schedule(mpc.schedule()); g.weighted_retarget(times, mpc.dt)
+    costs, pool = g.cost_tables(mpc.n_costs * len(times), mpc.n_pool * len(times))
+    for m, t in enumerate(times):
+        _check_table(costs[m * mpc.n_costs:(m + 1) * mpc.n_costs], pool, mpc.nx, gold[str(t)], (kind, t))
