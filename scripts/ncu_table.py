@@ -11,7 +11,8 @@ def col(r, k, scale=1.0):
     except Exception: return float("nan")
 def unit(k): return units[hdr.index(k)]
 fam = {"node_calc_kernel": "calc_diff", "node_cost_kernel": "calc_diff", "node_diff_kernel": "calc_diff", "backward_kernel": "backward", "rollout_kernel": "rollout", "decide_kernel": "decide"}
-seen = {}; lines = []; traffic = {}; flines = []
+seen = {}; lines = []; traffic = {}; flines = []; slines = []
+stall_keys = [k for k in hdr if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")]
 for r in rows[2:]:
     name = r[hdr.index("Kernel Name")]
     short = name.split("<")[0].replace("void ", "").replace("empc::", "")
@@ -35,6 +36,9 @@ for r in rows[2:]:
     flops = ops["dadd"] + ops["dmul"] + 2 * ops["dfma"] + (tens if tens == tens else 0.0)
     nodes = batch * (T + 1)
     flines.append(f"| `{short}` | {ops['dadd']/1e9:.2f} | {ops['dmul']/1e9:.2f} | {ops['dfma']/1e9:.2f} | {tens/1e9:.1f} | {flops/1e9:.1f} | {flops/nodes/1e3:.1f} | {flops/dur/1e9:.2f} |")
+    st = sorted(((col(r, k), k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for k in stall_keys), reverse=True)
+    st = [(v, n) for v, n in st if v == v and n != "selected"][:5]
+    slines.append(f"| `{short}` | {sum(v for v, _ in st) + 1.0:.1f} | " + ", ".join(f"{n} {v:.2f}" for v, n in st) + " |")
     t = traffic.setdefault(fam[short], {"dram_bytes_per_launch": 0.0, "kernels": {}})
     t["dram_bytes_per_launch"] += rd + wr
     t["kernels"][short] = {"ms": dur, "dram_read_bytes": rd, "dram_write_bytes": wr}
@@ -42,5 +46,7 @@ open(out_md, "w").write("| kernel | ms | DRAM read GB | DRAM write GB | DRAM GB/
 open(out_md, "a").write("\nFP64 work per launch (hardware counters; DADD/DMUL/DFMA are thread-level instruction counts, DMMA column in FLOPs; "
                        "FLOPs = DADD + DMUL + 2 DFMA + DMMA FLOPs; per node = / (batch x (T+1)); rollout and decide touch each node once per trial):\n\n"
                        "| kernel | G DADD | G DMUL | G DFMA | G DMMA FLOP | GFLOP per launch | kFLOP per node | TFLOP/s |\n|---|---|---|---|---|---|---|---|\n" + "\n".join(flines) + "\n")
+open(out_md, "a").write("\nWarp stall reasons (cycles a resident warp waits per instruction it issues, ncu `smsp__average_warps_issue_stalled_*_per_issue_active`; "
+                       "top five besides the issue cycle itself):\n\n| kernel | ≈ cycles per issued instruction (top five + 1) | stalls |\n|---|---|---|\n" + "\n".join(slines) + "\n")
 json.dump({"workload": workload, "batch": batch, "T": T, "source": rep.split("/")[-1], "kernels": traffic}, open(out_json, "w"), indent=1)
 print(open(out_md).read())
