@@ -63,7 +63,8 @@ struct Buffers {
 // ---------------------------------------------------------------------------------------------------------------------
 struct DecideParams {
   empc_solver_params_t P;
-  int stage;  // 0: after rollout stage A (step lengths [0, RO_WIDTH_A)); 1: after stage B, pending OCPs only
+  int stage;    // 0: after rollout stage A (step lengths [0, width_a)); 1: after stage B, pending OCPs only
+  int width_a;  // step lengths rolled out by stage A: 4 for large batches, 8 when the GPU has idle sub-partitions anyway
 };
 
 __device__ __forceinline__ void increase_reg(OcpState& st, const empc_solver_params_t& P) {
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams
   const empc_solver_params_t& P = dp.P;
   const int T = bf.T, T1 = T + 1;
   const int tid = threadIdx.x;
-  const int n_begin = dp.stage == 0 ? 0 : RO_WIDTH_A, n_end = dp.stage == 0 ? RO_WIDTH_A : EMPC_N_ALPHAS;
+  const int n_begin = dp.stage == 0 ? 0 : dp.width_a, n_end = dp.stage == 0 ? dp.width_a : EMPC_N_ALPHAS;
   OcpState st;  // live in thread 0 only
   int acc = -1, last = -1;
   bool mine = false;

@@ -27,10 +27,13 @@
 struct RoParams {
   int force, force_feasible, force_ddp;
   double force_smooth;
-  int a_begin;  // first step-length index of this launch (0: stage A, RO_WIDTH_A: stage B)
+  int a_begin;  // first step-length index of this launch (0: stage A, the width of stage A: stage B)
 };
 
-constexpr int RO_WIDTH_A = 4;  // step lengths tried by stage A (alpha index 0..3); stage B covers the rest
+// Step lengths tried by stage A; stage B covers the rest.  4 when the batch fills the GPU (one warp per sub-partition
+// already at 4096 OCPs x 4 trials); 8 for smaller batches, where the extra trials run on sub-partitions that would idle
+// and stage B (alpha <= 1/256) is practically never needed.
+constexpr int RO_WIDTH_A = 4, RO_WIDTH_A_SMALL = 8;
 
 template <class D, int W>
 struct RoCfg {

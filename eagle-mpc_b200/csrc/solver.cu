@@ -48,6 +48,7 @@ struct empc_solver {
   long long* d_t_stages = nullptr; unsigned char* d_is_transition = nullptr; int n_stages = 0;  // carrot schedule
   int n_ref = 0, dt_ref_ms = 0;
   long long* d_times = nullptr;   // n_node_maps controller times
+  int width_a = RO_WIDTH_A;  // stage-A width of the line search (rollout.cuh)
   double *d_pack = nullptr, *h_pack = nullptr;  // empc_get_solution staging (small batches)
   WeightedScheduleDev wsched = {0, 0, nullptr, nullptr, 0, 0.0, 0.0, nullptr, nullptr, nullptr};
   int init_feasible = 0;
@@ -162,6 +163,9 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   h->na = r.n_joints - 1; h->nr = d->n_rotors;
   h->nq = 7 + h->na; h->nv = 6 + h->na; h->nx = h->nq + h->nv; h->ndx = 2 * h->nv; h->nu = h->nr + h->na;
   empc_default_params(&h->P);
+  // 8 trials per OCP in stage A while that still leaves at most one rollout warp per SM sub-partition
+  h->width_a = ((long long)batch * RO_WIDTH_A_SMALL <= 32LL * 148 * 4) ? RO_WIDTH_A_SMALL : RO_WIDTH_A;
+  if (const char* e = std::getenv("EMPC_RO_WIDTH_A")) { const int w = std::atoi(e); if (w == RO_WIDTH_A || w == RO_WIDTH_A_SMALL) h->width_a = w; }
   h->n_costs = d->n_costs; h->n_pool = d->n_pool; h->n_node_maps = d->n_node_maps; h->n_costsets = d->n_costsets;
 
   DevModel& M = h->hmodel;
@@ -549,19 +553,19 @@ static cudaError_t launch_rollout_w(empc_solver* h, const RoParams& P, const Buf
   h->launches++;
   return cudaGetLastError();
 }
-// stage 0: step lengths [0, RO_WIDTH_A) of every active OCP; stage 1: the remaining ones, pending OCPs only
+// stage 0: step lengths [0, width_a) of every active OCP; stage 1: the remaining ones, pending OCPs only
 template <class D>
 static cudaError_t launch_rollout(empc_solver* h, int stage, int force, int feasible, int ddp, double smooth, const Buffers* gb = nullptr,
                                   cudaStream_t st = nullptr) {
   const Buffers& bf = gb ? *gb : h->bf;
   if (!st) st = h->stream;
-  RoParams P{force, feasible, ddp, smooth, stage == 0 ? 0 : RO_WIDTH_A};
-  cudaError_t e = (stage == 0) ? launch_rollout_w<D, RO_WIDTH_A>(h, P, bf, st) : launch_rollout_w<D, 8>(h, P, bf, st);
+  RoParams P{force, feasible, ddp, smooth, stage == 0 ? 0 : h->width_a};
+  cudaError_t e = (stage == 0 && h->width_a == RO_WIDTH_A) ? launch_rollout_w<D, RO_WIDTH_A>(h, P, bf, st) : launch_rollout_w<D, 8>(h, P, bf, st);
   if (e != cudaSuccess) return e;
   // In a solve, decide_kernel evaluates the trial costs lazily in line-search order.  The tile-level parity hook wants
   // cost_try of EVERY step length: node costs in parallel over trials and nodes, then the ordered per-trial sums.
   if (!force) return cudaSuccess;
-  const int width = (stage == 0) ? RO_WIDTH_A : EMPC_N_ALPHAS - RO_WIDTH_A;
+  const int width = (stage == 0) ? h->width_a : EMPC_N_ALPHAS - h->width_a;
   const long long n_thr = (long long)bf.nb * width * (h->T + 1);
   trial_cost_kernel<D><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
   h->launches++;
@@ -574,7 +578,7 @@ template <class D>
 static cudaError_t launch_decide(empc_solver* h, int stage, const Buffers* gb = nullptr, cudaStream_t st = nullptr) {
   const Buffers& bf = gb ? *gb : h->bf;
   if (!st) st = h->stream;
-  DecideParams dp{h->P, stage};
+  DecideParams dp{h->P, stage, h->width_a};
   // one block per OCP, one node per thread and round: the block size (a multiple of 32, at most 256) that wastes the fewest
   // thread slots over the ceil((T+1)/threads) rounds of the trial-cost evaluation; ties go to the larger block
   const int T1 = h->T + 1;

@@ -19,8 +19,11 @@ def rel(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
 
+@pytest.mark.parametrize("width_a", [4, 8])
 @pytest.mark.parametrize("na,nr,T,th", [(3, 6, 20, 0.999), (0, 4, 25, 0.9999), (2, 6, 15, 0.99999)])
-def test_small_steps_take_stage_b(na, nr, T, th):
+def test_small_steps_take_stage_b(na, nr, T, th, width_a, monkeypatch):
+    # stage A rolls out 4 step lengths for batches that fill the GPU and 8 for smaller ones; both splits are exercised here
+    monkeypatch.setenv("EMPC_RO_WIDTH_A", str(width_a))
     B = 6
     h = synth.make_problem(seed=40 + na, na=na, n_rotors=nr, T=T, all_costs=False)
     rng = np.random.default_rng(9)
