@@ -49,6 +49,9 @@ struct empc_solver {
   int n_ref = 0, dt_ref_ms = 0;
   long long* d_times = nullptr;   // n_node_maps controller times
   int width_a = RO_WIDTH_A;  // stage-A width of the line search (rollout.cuh)
+  // small batches (one wave of node_calc_kernel or less): node_cost_kernel runs beside node_calc_kernel on a second stream
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double *d_pack = nullptr, *h_pack = nullptr;  // empc_get_solution staging (small batches)
   WeightedScheduleDev wsched = {0, 0, nullptr, nullptr, 0, 0.0, 0.0, nullptr, nullptr, nullptr};
   int init_feasible = 0;
@@ -140,6 +143,9 @@ int empc_destroy(empc_solver_t* h) {
     if (h->ev_gdone[g]) cudaEventDestroy(h->ev_gdone[g]);
   }
   if (h->ev_init) cudaEventDestroy(h->ev_init);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return EMPC_OK;
@@ -196,6 +202,9 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   M.barrier_weight = h->P.barrier_weight;
 
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete h; return fail(EMPC_ERR_CUDA, cudaGetErrorString(e)); }
 #define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); empc_destroy(h); return fail(EMPC_ERR_CUDA, m_); } } while (0)
   const size_t B = batch, T = d->T, T1 = T + 1, nx = h->nx, tile = h->tile;
@@ -495,12 +504,23 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   if (!st) st = h->stream;
   const int T1 = h->T + 1;
   const long long n = (long long)bf.nb * T1;
+  // the two thread-per-node halves are independent (different packet fields); when they do not fill the GPU they overlap
+  const bool fork = h->side_stream && !gb && st == h->stream && n <= 148LL * NC_THREADS * EMPC_NC_BLOCKS;
+  cudaError_t e;
+  if (fork) {
+    if ((e = cudaEventRecord(h->ev_fork, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0)) != cudaSuccess) return e;
+  }
   node_calc_kernel<D><<<(unsigned)((n + NC_THREADS - 1) / NC_THREADS), NC_THREADS, 0, st>>>(bf, force, smooth, h->hmodel);
   h->launches++;
-  node_cost_kernel<D><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bf, force, smooth, h->hmodel);
+  node_cost_kernel<D><<<(unsigned)((n + 127) / 128), 128, 0, fork ? h->side_stream : st>>>(bf, force, smooth, h->hmodel);
   h->launches++;
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (fork) {
+    if ((e = cudaEventRecord(h->ev_join, h->side_stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(st, h->ev_join, 0)) != cudaSuccess) return e;
+  }
   using W = DiffCfg<D>;
   const size_t smem = sizeof(double) * W::SMEM_DOUBLES;
   static bool attr_set = false;
