@@ -2,28 +2,35 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 PKG := eagle-mpc_b200
 LIB := $(PKG)/lib/libempc_b200.so
+# host-side mirror of the reference's C++ surfaces (YAML / URDF / Trajectory / MPC controllers): no CUDA code, binds the
+# C ABI of $(LIB) at run time (host/cuda_abi.cpp), so problem construction never loads the CUDA library
+HOSTLIB := $(PKG)/lib/libempc_host.so
 CUFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
-HOST_SRC := $(PKG)/host/params.cpp $(PKG)/host/urdf.cpp $(PKG)/host/trajectory.cpp $(PKG)/host/sbfddp.cpp $(PKG)/host/mpc.cpp $(PKG)/host/host_capi.cpp
+HOST_SRC := $(PKG)/host/params.cpp $(PKG)/host/urdf.cpp $(PKG)/host/trajectory.cpp $(PKG)/host/sbfddp.cpp $(PKG)/host/mpc.cpp $(PKG)/host/host_capi.cpp $(PKG)/host/cuda_abi.cpp
 HOST_OBJ := $(HOST_SRC:.cpp=.o)
 CU_OBJ := $(PKG)/csrc/solver.o
 
-all: $(LIB) oracle
+all: $(LIB) $(HOSTLIB) oracle
 
 $(PKG)/csrc/solver.o: $(PKG)/csrc/solver.cu $(wildcard $(PKG)/csrc/*.cuh) include/empc_b200.h
 	$(NVCC) $(CUFLAGS) -c -o $@ $<
 
-$(PKG)/host/%.o: $(PKG)/host/%.cpp $(PKG)/host/eagle_mpc.hpp $(PKG)/host/mpc.hpp include/empc_b200.h
+$(PKG)/host/%.o: $(PKG)/host/%.cpp $(PKG)/host/eagle_mpc.hpp $(PKG)/host/mpc.hpp $(PKG)/host/cuda_abi.hpp include/empc_b200.h
 	g++ $(CXXFLAGS) -c -o $@ $<
 
-$(LIB): $(CU_OBJ) $(HOST_OBJ)
+$(LIB): $(CU_OBJ)
 	mkdir -p $(PKG)/lib
-	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(CU_OBJ) $(HOST_OBJ) -ldl
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(CU_OBJ)
+
+$(HOSTLIB): $(HOST_OBJ)
+	mkdir -p $(PKG)/lib
+	g++ -shared -o $@ $(HOST_OBJ) -ldl
 
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(PKG)/csrc/*.o $(PKG)/host/*.o $(LIB)
+	rm -f $(PKG)/csrc/*.o $(PKG)/host/*.o $(LIB) $(HOSTLIB)
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean

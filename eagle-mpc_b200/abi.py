@@ -90,6 +90,8 @@ class SolverParams(C.Structure):
         ("maxiter", C.c_int32),
         ("stop_gap_norm", C.c_int32),
         ("squash_quirk", C.c_int32),
+        ("stop_criteria", C.c_int32),
+        ("stop_test", C.c_int32),
         ("reserved", C.c_int32),
         ("convergence_init", C.c_double),
         ("convergence_stop", C.c_double),
@@ -109,6 +111,18 @@ class SolverParams(C.Structure):
         ("th_stepinc", C.c_double),
         ("th_stop_gaps", C.c_double),
     ]
+
+
+STOP_CRITERIA_COST_REDUCTION, STOP_CRITERIA_QU_NORM = 0, 1
+STOP_TEST_GAPS, STOP_TEST_FEASIBLE = 0, 1
+
+
+class IterRecord(C.Structure):
+    """empc_iter_record_t"""
+    _fields_ = [("iter", C.c_int32), ("total_iter", C.c_int32), ("phase", C.c_int32), ("accepted", C.c_int32),
+                ("is_feasible", C.c_int32), ("reserved", C.c_int32), ("cost", C.c_double), ("stop", C.c_double),
+                ("steplength", C.c_double), ("xreg", C.c_double), ("d0", C.c_double), ("d1", C.c_double),
+                ("smooth", C.c_double)]
 
 
 class Dims(C.Structure):

@@ -59,6 +59,8 @@ def lib():
         L.empc_phase_calc_diff.argtypes = [C.c_void_p, C.c_double]
         L.empc_phase_backward.argtypes = [C.c_void_p, C.c_double, C.c_int32, abi.c_int32_p]
         L.empc_phase_rollout.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32]
+        L.empc_enable_iteration_log.argtypes = [C.c_void_p, C.c_int32]
+        L.empc_get_iteration_log.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.IterRecord), C.c_int32, abi.c_int32_p]
         L.empc_get_trial.argtypes = [C.c_void_p, C.c_int32, abi.c_double_p, abi.c_double_p, abi.c_double_p,
                                      abi.c_double_p, abi.c_int32_p]
         _lib = L
@@ -231,6 +233,19 @@ class BatchSolver:
         _ck(lib().empc_get_solution(self.h, abi.as_double_p(xs), abi.as_double_p(us), abi.as_double_p(uss), abi.as_double_p(cost),
                                     abi.as_double_p(stop), abi.as_int32_p(it), abi.as_int32_p(fe)))
         return xs, us, uss, cost, stop, it, fe
+
+    def enable_iteration_log(self, capacity):
+        """keep the last `capacity` iteration records per OCP (the stand-in for setCallbacks); 0 switches it off"""
+        _ck(lib().empc_enable_iteration_log(self.h, int(capacity)))
+        self._log_cap = int(capacity)
+
+    def iteration_log(self, ocp):
+        """records of OCP `ocp` from the last solve, oldest first (list of abi.IterRecord)"""
+        cap = max(getattr(self, "_log_cap", 0), 1)
+        rec = (abi.IterRecord * cap)()
+        n = np.zeros(1, dtype=np.int32)
+        _ck(lib().empc_get_iteration_log(self.h, int(ocp), rec, cap, abi.as_int32_p(n)))
+        return [rec[i] for i in range(int(n[0]))]
 
     def total_iterations(self):
         v = C.c_int64()

@@ -71,6 +71,7 @@ struct BwCfg {
 struct BwParams {
   double reg_max, reg_factor, th_gaptol;
   int force;  // phase hook: single attempt, xreg / is_feasible taken from the state as they are, no prologue
+  int stop_qu_norm;  // EMPC_STOP_CRITERIA_QU_NORM: also leave sum_t ||Qu_t||^2 in the OCP state
 };
 
 EMPC_DI void dmma884(double& c0, double& c1, double a, double b) {
@@ -460,11 +461,11 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
               if (row == col + 1) v1 += xreg;
               if (row >= n || col >= n) v0 = 0.0;
               if (row >= n || col + 1 >= n) v1 = 0.0;
-              if (isnan(v0) || isnan(v1)) bad = 1;  // "backward_error"
+              if (raise_if_nan_abs(v0) || raise_if_nan_abs(v1)) bad = 1;  // "backward_error": raiseIfNaN(Vxx.lpNorm<Infinity>())
               vsym[i][i][0] = v0; vsym[i][i][1] = v1;
             } else {
               const double u0 = (row < n && col < n) ? q[i][j][0] : 0.0, u1 = (row < n && col + 1 < n) ? q[i][j][1] : 0.0;
-              if (isnan(u0) || isnan(u1)) bad = 1;
+              if (raise_if_nan_abs(u0) || raise_if_nan_abs(u1)) bad = 1;
               vsym[i][j][0] = u0; vsym[i][j][1] = u1;
               vsym[j][i][0] = (rowT < n && colT < n) ? t0 : 0.0;
               vsym[j][i][1] = (rowT < n && colT + 1 < n) ? t1 : 0.0;
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         const double s = (s0 + s1) + s2;
         gv[lane] = s;
         const double vx = feasible ? tmpv[lane] : (tmpv[lane] + s);
-        if (isnan(vx)) bad = 1;
+        if (raise_if_nan_abs(vx)) bad = 1;  // raiseIfNaN(Vx.lpNorm<Infinity>())
         Vxp[lane] = vx;
       }
       bad = __any_sync(0xffffffffu, bad);
@@ -500,15 +501,16 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         double* kg = bf.k + ((size_t)b * T + t) * m;
         if (lane < m) kg[lane] = kv[lane];
         if (lane < n) { bf.Vx[(nb + t) * n + lane] = Vxp[lane]; bf.g[(nb + t) * n + lane] = gv[lane]; }
-        {  // four ordered dot products on lanes 28..31: same unrolled, predicated code for all of them (loads hoisted)
-          const int w = lane & 3;
-          const double* pa = (w == 0) ? Qu : (w == 1) ? kv : (w == 2) ? Vxp : fsv;
-          const double* pb = (w == 0) ? kv : (w == 1) ? Quuk : (w == 2) ? fsv : gv;
-          const int cnt = (w < 2) ? m : n;
+        {  // five ordered dot products on lanes 24..28: same unrolled, predicated code for all of them (loads hoisted)
+          const int w = lane & 7;
+          const double* pa = (w == 0) ? Qu : (w == 1) ? kv : (w == 2) ? Vxp : (w == 3) ? fsv : Qu;
+          const double* pb = (w == 0) ? kv : (w == 1) ? Quuk : (w == 2) ? fsv : (w == 3) ? gv : Qu;
+          const int cnt = (w == 2 || w == 3) ? n : m;
           double sacc = 0;
 #pragma unroll
           for (int i = 0; i < n; ++i) { const double av = (i < cnt) ? pa[i] : 0.0, bv = (i < cnt) ? pb[i] : 0.0; sacc += av * bv; }
-          if (lane >= 28) bf.nodesc[(nb + t) * 4 + w] = sacc;
+          if (lane >= 24 && w < 4) bf.nodesc[(nb + t) * 4 + w] = sacc;
+          if (lane == 28) bf.qu2[nb + t] = sacc;  // ||Qu_t||^2 (upstream stoppingCriteria)
         }
       }
       __syncwarp();
@@ -541,6 +543,17 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         }
       }
       __syncwarp();
+    }
+    if (P.stop_qu_norm) {  // SolverDDP::stoppingCriteria of upstream: sum over the running nodes, node order
+      double s = 0;
+      for (int base = 0; base < T; base += S::TOTAL) {
+        const int cnt = min(S::TOTAL, T - base);
+        for (int i = lane; i < cnt; i += 32) sm[i] = bf.qu2[nb + base + i];
+        __syncwarp();
+        if (lane == 0) for (int t = 0; t < cnt; ++t) s += sm[t];
+        __syncwarp();
+      }
+      if (lane == 0) st.qu2 = s;
     }
     if (lane == 0) { st.dg = dg; st.dq = dq; st.dg0 = dg0; st.dq0 = dq0; }
   }

@@ -25,6 +25,10 @@ struct OcpState {
   int phase, iter, total_iters, is_feasible, was_feasible, recalc, bw_fail, iters_out;
   int accepted;
   int pending;  // every stage-A step length was rejected: stage B of the line search has to run (rollout.cuh)
+  double qu2;   // sum_t ||Qu_t||^2 of the last backward pass (upstream's stoppingCriteria, EMPC_STOP_CRITERIA_QU_NORM)
+  double d0_last, d1_last;  // expected-improvement pair of the last trial the line search evaluated (iteration log)
+  int log_count;            // iteration records written by this solve (iteration log ring)
+  int pad_;
 };
 
 struct Buffers {
@@ -49,7 +53,10 @@ struct Buffers {
   double* xs_try; double* us_try; double* cost_try; double* dv; int* ok;
   double* trial_node_cost;  // [alpha][OCP][T+1] node costs of the trial trajectories
   double* us_squash;
+  double* qu2;  // per node ||Qu_t||^2
   int* n_active;
+  empc_iter_record_t* iter_log;  // [OCP][log_cap] ring, or nullptr
+  int log_cap;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams
         int stop = 0;
         if (okn) {
           bf.cost_try[tn] = cost_try;
-          if (isnan(cost_try)) bf.ok[tn] = 0;  // raiseIfNaN(cost_try_): "forward_error", try the next step length
+          if (raise_if_nan(cost_try)) bf.ok[tn] = 0;  // raiseIfNaN(cost_try_): "forward_error", try the next step length
           else {
             const int ddp = st.phase == PHASE_DDP;
             const double dV = st.cost - cost_try;
@@ -185,6 +192,7 @@ __global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams
               const double dv = st.is_feasible ? 0.0 : bf.dv[tn];
               d0 = st.dg + dv; d1 = st.dq - 2 * dv;
             }
+            st.d0_last = d0; st.d1_last = d1;
             const double dVexp = st.steplength * (d0 + 0.5 * st.steplength * d1);
             bool accept = false;
             if (dVexp >= 0) {
@@ -229,10 +237,22 @@ __global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams
           if (st.xreg == P.reg_max) { end_inner_solve(st, P); ended = true; }
         }
         if (!ended) {
-          // fork stop rules, inferred: StopCriteriaCostReduction / StopTestGaps
-          st.stop = fabs(st.cost_prev - st.cost);
+          // stoppingCriteria(): the fork's StopCriteriaCostReduction (inferred) or upstream's sum ||Qu||^2
+          st.stop = (P.stop_criteria == EMPC_STOP_CRITERIA_QU_NORM) ? st.qu2 : fabs(st.cost_prev - st.cost);
+          // callbacks run here in the reference (src/sbfddp.cpp:303-307, :381-385): one record per iteration
+          if (bf.iter_log && bf.log_cap > 0) {
+            empc_iter_record_t r;
+            r.iter = st.iter; r.total_iter = st.total_iters + st.iter; r.phase = st.phase; r.accepted = acc;
+            r.is_feasible = st.is_feasible; r.reserved = 0;
+            r.cost = st.cost; r.stop = st.stop; r.steplength = st.steplength; r.xreg = st.xreg;
+            r.d0 = st.d0_last; r.d1 = st.d1_last; r.smooth = st.smooth;
+            bf.iter_log[(size_t)b * bf.log_cap + (st.log_count % bf.log_cap)] = r;
+            st.log_count += 1;
+          }
+          // stoppingTest() of the FDDP passes: the fork's StopTestGaps (inferred) or upstream's feasibility rule;
+          // stoppingTestFeasible() of the DDP clean-up (src/sbfddp.cpp:387)
           bool stop_now;
-          if (ddp) stop_now = st.was_feasible && st.stop < st.th_stop;
+          if (ddp || P.stop_test == EMPC_STOP_TEST_FEASIBLE) stop_now = st.was_feasible && st.stop < st.th_stop;
           else {
             const double gn = st.is_feasible ? 0.0 : (P.stop_gap_norm == 0 ? st.gap_inf : st.gap_l1);
             stop_now = st.stop < st.th_stop && gn < P.th_stop_gaps;
@@ -285,6 +305,7 @@ __global__ void init_state_kernel(Buffers bf, empc_solver_params_t P, int is_fea
   st.dg = st.dq = st.dg0 = st.dq0 = 0; st.gap_inf = 0; st.gap_l1 = 0;
   st.iter = 0; st.total_iters = 0; st.is_feasible = 0; st.was_feasible = 0; st.recalc = 1; st.bw_fail = 0;
   st.iters_out = 0; st.accepted = -1; st.pending = 0;
+  st.qu2 = 0; st.d0_last = 0; st.d1_last = 0; st.log_count = 0; st.pad_ = 0;
   (void)is_feasible_arg;  // solveFDDP(maxiter, false, ...) overrides the caller's flag (src/sbfddp.cpp:210,230)
   if (P.convergence_init >= P.convergence_stop) st.phase = PHASE_FDDP;
   else { st.phase = is_feasible_arg ? PHASE_DONE : PHASE_DDP; st.is_feasible = is_feasible_arg; }

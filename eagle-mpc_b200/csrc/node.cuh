@@ -59,6 +59,11 @@ struct NodeData {
   double s[D::NU];
 };
 
+// crocoddyl::raiseIfNaN(value): NaN, +-inf or value >= 1e30 ("forward_error" / "backward_error" of the solvers)
+EMPC_DI bool raise_if_nan(double v) { return !(v < 1e30) || isinf(v); }
+// ... applied to an infinity norm: max_i |v_i| trips it as soon as one entry does
+EMPC_DI bool raise_if_nan_abs(double v) { return !(fabs(v) < 1e30); }
+
 // ---- StateMultibody ------------------------------------------------------------------------------------------------
 EMPC_DI void q_to_se3(const double* q, SE3& M) {
   quat_to_R(q + 3, M.R);

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
         node_dyn<D, true>(M, smooth, xt, u, xn);
         bool bad = false;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) bad |= isnan(xn[i]);
+        for (int i = 0; i < NX; ++i) bad |= raise_if_nan_abs(xn[i]);  // raiseIfNaN(xnext.lpNorm<Infinity>())
         if (bad) { ok = 0; active = false; }  // "forward_error": this step length is skipped by decide_kernel
       }
     }
@@ -250,6 +250,6 @@ __global__ void __launch_bounds__(128) trial_sum_kernel(Buffers bf, RoParams P, 
   }
   if (lane == 0) {
     bf.cost_try[n] = s;
-    if (isnan(s)) bf.ok[n] = 0;  // raiseIfNaN(cost_try_)
+    if (raise_if_nan(s)) bf.ok[n] = 0;  // raiseIfNaN(cost_try_)
   }
 }

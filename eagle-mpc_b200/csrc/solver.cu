@@ -45,7 +45,14 @@ struct empc_solver {
   double *d_xs_init = nullptr, *d_us_init = nullptr;
   // batched MPC instances (retarget.cuh)
   double* d_ref_table = nullptr;  // (n_ref + 2) x nx: reference trajectory + rail hover row + carrot tail row
+  size_t cap_ref_table = 0;
   long long* d_t_stages = nullptr; unsigned char* d_is_transition = nullptr; int n_stages = 0;  // carrot schedule
+  size_t cap_t_stages = 0, cap_is_transition = 0;
+  // weighted schedule storage (the const views the kernels see are in wsched)
+  long long *d_ws_t_ini = nullptr, *d_ws_t_end = nullptr; unsigned char *d_ws_match = nullptr, *d_ws_task = nullptr; double* d_ws_base = nullptr;
+  size_t cap_ws_stage = 0, cap_ws_entry = 0;
+  // empc_plant_step staging (host-pointer plant), grown on demand
+  double *d_plant_x = nullptr, *d_plant_u = nullptr, *d_plant_xn = nullptr; size_t cap_plant = 0;
   int n_ref = 0, dt_ref_ms = 0;
   long long* d_times = nullptr;   // n_node_maps controller times
   int width_a = RO_WIDTH_A;  // stage-A width of the line search (rollout.cuh)
@@ -55,6 +62,7 @@ struct empc_solver {
   double *d_pack = nullptr, *h_pack = nullptr;  // empc_get_solution staging (small batches)
   WeightedScheduleDev wsched = {0, 0, nullptr, nullptr, 0, 0.0, 0.0, nullptr, nullptr, nullptr};
   int init_feasible = 0;
+  size_t cap_iter_log = 0;  // records allocated for bf.iter_log (batch x bf.log_cap used)
   cudaStream_t stream = nullptr;
   int* h_active = nullptr;  // pinned: [group][slot][2]
   static constexpr int MAXG = 4;
@@ -78,6 +86,20 @@ static cudaError_t dalloc(empc_solver* h, Tp** p, size_t n) {
   return e;
 }
 
+// (re)allocation of a buffer whose size may change between calls: reuse when it fits, otherwise free the old one
+template <class Tp>
+static cudaError_t dreuse(empc_solver* h, Tp** p, size_t* cap, size_t n) {
+  if (*p && *cap >= n) return cudaSuccess;
+  if (*p) {
+    cudaFree(*p);  // synchronises with work that may still read it
+    h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), (void*)*p), h->allocs.end());
+    *p = nullptr; *cap = 0;
+  }
+  cudaError_t e = dalloc(h, p, n);
+  if (e == cudaSuccess) *cap = n;
+  return e;
+}
+
 // ---- (NA, NR) dispatch: one instantiation per eagle-mpc platform family ---------------------------------------------
 #define EMPC_DISPATCH(h, CALL)                                               \
   do {                                                                       \
@@ -98,6 +120,23 @@ static int packet_doubles(int na, int nr) {
 }
 static bool supported(int na, int nr) {
   return (na == 0 && nr == 4) || (na == 0 && nr == 6) || (na == 2 && nr == 6) || (na == 3 && nr == 6) || (na == 5 && nr == 6);
+}
+
+// Dynamic shared memory opt-in of the kernels that need more than 48 KB.  The attribute belongs to the (function, device)
+// pair, so it is set for the handle's device every time a handle is created (one process may hold handles on several GPUs).
+template <class K>
+static cudaError_t opt_in_smem(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+template <class D>
+static cudaError_t set_kernel_attributes() {
+  cudaError_t e;
+  if ((e = opt_in_smem(node_diff_kernel<D>, sizeof(double) * DiffCfg<D>::SMEM_DOUBLES)) != cudaSuccess) return e;
+  if ((e = opt_in_smem(backward_kernel<D>, sizeof(double) * BwCfg<D>::TOTAL)) != cudaSuccess) return e;
+  if ((e = opt_in_smem(rollout_kernel<D, RO_WIDTH_A>, sizeof(double) * RoCfg<D, RO_WIDTH_A>::SMEM_DOUBLES)) != cudaSuccess) return e;
+  return opt_in_smem(rollout_kernel<D, 8>, sizeof(double) * RoCfg<D, 8>::SMEM_DOUBLES);
 }
 
 static void inertia_matrix(double m, const double* c, const double* Ic, double* Y) {
@@ -205,7 +244,12 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-  if (e != cudaSuccess) { delete h; return fail(EMPC_ERR_CUDA, cudaGetErrorString(e)); }
+  if (e == cudaSuccess) {
+#define EMPC_ATTR(NA_, NR_) if (h->na == NA_ && h->nr == NR_) e = set_kernel_attributes<Dim<NA_, NR_>>();
+    EMPC_ATTR(0, 4) EMPC_ATTR(0, 6) EMPC_ATTR(2, 6) EMPC_ATTR(3, 6) EMPC_ATTR(5, 6)
+#undef EMPC_ATTR
+  }
+  if (e != cudaSuccess) { std::string m_ = cudaGetErrorString(e); empc_destroy(h); return fail(EMPC_ERR_CUDA, m_); }
 #define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); empc_destroy(h); return fail(EMPC_ERR_CUDA, m_); } } while (0)
   const size_t B = batch, T = d->T, T1 = T + 1, nx = h->nx, tile = h->tile;
   CKH(cudaMallocHost((void**)&h->h_active, empc_solver::MAXG * 2 * 2 * sizeof(int)));
@@ -258,6 +302,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   CKH(dalloc(h, &bf.dv, B * EMPC_N_ALPHAS));
   CKH(dalloc(h, &bf.ok, B * EMPC_N_ALPHAS));
   CKH(dalloc(h, &bf.us_squash, B * T * nu));
+  CKH(dalloc(h, &bf.qu2, B * T1));
   CKH(dalloc(h, &bf.n_active, 2 * empc_solver::MAXG));
   bf.model = h->d_model; bf.ct.costs = h->d_costs; bf.ct.pool = h->d_pool; bf.ct.costset_begin = h->d_costset_begin;
   bf.node_costset = h->d_node_costset; bf.ocp_map = h->d_ocp_map; bf.x0 = h->d_x0;
@@ -405,7 +450,7 @@ int empc_set_reference_trajectory(empc_solver_t* h, const double* state_ref, int
   hov[5] = z / norm; hov[6] = w / norm;
   // carrot tail row (carrot-mpc.cpp:376-388): last configuration as it is, zero velocity
   std::copy(last, last + nq, hov + nx);
-  CK(dalloc(h, &h->d_ref_table, tab.size()));
+  CK(dreuse(h, &h->d_ref_table, &h->cap_ref_table, tab.size()));
   CK(cudaMemcpyAsync(h->d_ref_table, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->n_ref = n_ref; h->dt_ref_ms = dt_ref_ms;
@@ -434,8 +479,8 @@ int empc_set_carrot_schedule(empc_solver_t* h, int32_t n_stages, const int64_t* 
   if (!h || !t_stages || !is_transition) return fail(EMPC_ERR_INVALID, "null");
   if (n_stages < 1) return fail(EMPC_ERR_INVALID, "n_stages < 1");
   CK(cudaSetDevice(h->device));
-  CK(dalloc(h, &h->d_t_stages, (size_t)n_stages + 1));
-  CK(dalloc(h, &h->d_is_transition, (size_t)n_stages));
+  CK(dreuse(h, &h->d_t_stages, &h->cap_t_stages, (size_t)n_stages + 1));
+  CK(dreuse(h, &h->d_is_transition, &h->cap_is_transition, (size_t)n_stages));
   CK(cudaMemcpyAsync(h->d_t_stages, t_stages, sizeof(int64_t) * ((size_t)n_stages + 1), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_is_transition, is_transition, (size_t)n_stages, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -467,8 +512,13 @@ int empc_set_weighted_schedule(empc_solver_t* h, const empc_weighted_schedule_t*
     return fail(EMPC_ERR_INVALID, "incomplete weighted schedule");
   CK(cudaSetDevice(h->device));
   const size_t ns = (size_t)s->n_stages, ne = ns * (size_t)s->n_slots;
-  long long *t_ini = nullptr, *t_end = nullptr; unsigned char *match = nullptr, *task = nullptr; double* base = nullptr;
-  CK(dalloc(h, &t_ini, ns)); CK(dalloc(h, &t_end, ns)); CK(dalloc(h, &match, ne)); CK(dalloc(h, &task, ne)); CK(dalloc(h, &base, ne));
+  {
+    size_t c1 = h->cap_ws_stage, c2 = h->cap_ws_stage, c3 = h->cap_ws_entry, c4 = h->cap_ws_entry, c5 = h->cap_ws_entry;
+    CK(dreuse(h, &h->d_ws_t_ini, &c1, ns)); CK(dreuse(h, &h->d_ws_t_end, &c2, ns));
+    CK(dreuse(h, &h->d_ws_match, &c3, ne)); CK(dreuse(h, &h->d_ws_task, &c4, ne)); CK(dreuse(h, &h->d_ws_base, &c5, ne));
+    h->cap_ws_stage = std::min(c1, c2); h->cap_ws_entry = std::min(c3, std::min(c4, c5));
+  }
+  long long *t_ini = h->d_ws_t_ini, *t_end = h->d_ws_t_end; unsigned char *match = h->d_ws_match, *task = h->d_ws_task; double* base = h->d_ws_base;
   CK(cudaMemcpyAsync(t_ini, s->t_ini, sizeof(int64_t) * ns, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(t_end, s->t_end, sizeof(int64_t) * ns, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(match, s->match, ne, cudaMemcpyHostToDevice, h->stream));
@@ -523,14 +573,6 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   }
   using W = DiffCfg<D>;
   const size_t smem = sizeof(double) * W::SMEM_DOUBLES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(node_diff_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(node_diff_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   const long long n_first = (long long)bf.b0 * T1, n_last = n_first + n - 1;
   const long long groups = n_last / Pk<D>::GROUP - n_first / Pk<D>::GROUP + 1;
   node_diff_kernel<D><<<(unsigned)groups, W::THREADS, smem, st>>>(bf, force, smooth, h->hmodel);
@@ -543,15 +585,7 @@ static cudaError_t launch_backward(empc_solver* h, int force, const Buffers* gb 
   if (!st) st = h->stream;
   using S = BwCfg<D>;
   const size_t smem = sizeof(double) * S::TOTAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(backward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(backward_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  BwParams P{h->P.reg_max, h->P.reg_factor, h->P.th_gaptol, force};
+  BwParams P{h->P.reg_max, h->P.reg_factor, h->P.th_gaptol, force, h->P.stop_criteria == EMPC_STOP_CRITERIA_QU_NORM};
   backward_kernel<D><<<bf.nb, 32, smem, st>>>(bf, P);  // one warp per OCP
   h->launches++;
   return cudaGetLastError();
@@ -560,14 +594,6 @@ template <class D, int W>
 static cudaError_t launch_rollout_w(empc_solver* h, const RoParams& P, const Buffers& bf, cudaStream_t st) {
   using S = RoCfg<D, W>;
   const size_t smem = sizeof(double) * S::SMEM_DOUBLES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rollout_kernel<D, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rollout_kernel<D, W>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   // one warp per block = 32/W OCPs x W step lengths
   rollout_kernel<D, W><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
   h->launches++;
@@ -634,7 +660,9 @@ static int solve_impl(empc_solver* h) {
   // upper bound on batch iterations: every pass of every phase can use maxiter iterations
   int passes = 1;
   for (double c = h->P.convergence_init; c >= h->P.convergence_stop && passes < 64; c *= h->P.convergence_mult) passes++;
-  const long long max_loops = (long long)passes * h->P.maxiter + 8;
+  // every pass runs at most maxiter iterations plus one loop that only ends it (computeDirection giving up at reg_max)
+  const long long max_loops = (long long)passes * ((long long)h->P.maxiter + 1) + 2;
+  bool finished = false;
   const bool trace = std::getenv("EMPC_TRACE_OCP") != nullptr;
   if (h->timing || trace || h->n_groups == 1) {
     // serial schedule with per-kernel CUDA-event timing (used for the roofline numbers and for tracing)
@@ -668,7 +696,7 @@ static int solve_impl(empc_solver* h) {
                       s.phase, it, s.iter, s.cost, s.cost_prev, s.steplength, s.xreg, s.is_feasible, s.was_feasible, s.stop, s.gap_inf, s.accepted, s.dg, s.dq, s.smooth, s.total_iters);
         }
       }
-      if (*h->h_active == 0) break;
+      if (*h->h_active == 0) { finished = true; break; }
     }
   } else {
     // pipelined schedule: G batch groups on their own streams, started one backward pass apart
@@ -705,7 +733,7 @@ static int solve_impl(empc_solver* h) {
         CK(cudaMemcpyAsync(h->h_active + (g * 2 + slot) * 2, gb[g].n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(h->ev_it[g][slot], st));
       }
-      if (!any) break;
+      if (!any) { finished = true; break; }
       if (it >= 1) {  // lagged termination check: look at the counters of the previous batch-iteration
         const int ps = (int)((it - 1) & 1);
         for (int g = 0; g < G; ++g) {
@@ -733,6 +761,8 @@ static int solve_impl(empc_solver* h) {
   for (const OcpState& s : st) tot += s.total_iters;
   h->total_iterations = tot;
   { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev_solve[0], h->ev_solve[1])); h->solve_ms = ms; }
+  if (!finished)  // cannot happen with a terminating schedule (convergence_mult < 1); never report a truncated solve as done
+    return fail(EMPC_ERR_INVALID, "solve stopped after " + std::to_string(max_loops) + " batch iterations with OCPs still active (check convergence_mult / maxiter)");
   return EMPC_OK;
 }
 
@@ -857,6 +887,34 @@ int empc_get_dgdq(const empc_solver_t* h, double* o) {
   for (int b = 0; b < h->B; ++b) { o[2 * b] = st[b].dg; o[2 * b + 1] = st[b].dq; }
   return EMPC_OK;
 }
+int empc_enable_iteration_log(empc_solver_t* h, int32_t capacity) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  if (capacity < 0) return fail(EMPC_ERR_INVALID, "negative log capacity");
+  CK(cudaSetDevice(h->device));
+  if (capacity == 0) { h->bf.log_cap = 0; return EMPC_OK; }  // the buffer (if any) is kept for the next enable
+  CK(dreuse(h, &h->bf.iter_log, &h->cap_iter_log, (size_t)h->B * (size_t)capacity));
+  h->bf.log_cap = capacity;
+  return EMPC_OK;
+}
+int empc_get_iteration_log(const empc_solver_t* h, int32_t ocp, empc_iter_record_t* out, int32_t max_records, int32_t* n_records) {
+  if (!h || !n_records || (!out && max_records > 0)) return fail(EMPC_ERR_INVALID, "null");
+  if (ocp < 0 || ocp >= h->B) return fail(EMPC_ERR_INVALID, "OCP index out of range");
+  *n_records = 0;
+  if (!h->bf.iter_log || h->bf.log_cap <= 0) return EMPC_OK;
+  CK(cudaSetDevice(h->device));
+  OcpState st;
+  CK(cudaMemcpyAsync(&st, h->bf.st + ocp, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int cap = h->bf.log_cap, have = std::min(st.log_count, cap), n = std::min(have, (int)max_records);
+  if (n <= 0) return EMPC_OK;
+  std::vector<empc_iter_record_t> ring((size_t)cap);
+  CK(cudaMemcpyAsync(ring.data(), h->bf.iter_log + (size_t)ocp * cap, sizeof(empc_iter_record_t) * cap, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int first = st.log_count - have;  // oldest record still in the ring
+  for (int i = 0; i < n; ++i) out[i] = ring[(size_t)((first + i) % cap)];
+  *n_records = n;
+  return EMPC_OK;
+}
 int empc_get_total_iterations(const empc_solver_t* h, int64_t* total) {
   if (!h || !total) return fail(EMPC_ERR_INVALID, "null");
   *total = h->total_iterations;
@@ -885,15 +943,19 @@ int empc_enable_kernel_timing(empc_solver_t* h, int32_t on) {
 // ---- plant (closed-loop drivers) ----
 template <class D>
 static int plant_impl(empc_solver* h, const double* x, const double* u, double dt, double* xnext, int n) {
-  double *dx_ = nullptr, *du_ = nullptr, *dxn_ = nullptr;
-  CK(cudaMalloc(&dx_, sizeof(double) * n * h->nx)); CK(cudaMalloc(&du_, sizeof(double) * n * h->nu)); CK(cudaMalloc(&dxn_, sizeof(double) * n * h->nx));
+  if (!h->d_plant_x || h->cap_plant < (size_t)n) {  // persistent staging, grown on demand
+    size_t c1 = h->cap_plant, c2 = h->cap_plant, c3 = h->cap_plant;
+    CK(dreuse(h, &h->d_plant_x, &c1, (size_t)n * h->nx)); CK(dreuse(h, &h->d_plant_u, &c2, (size_t)n * h->nu));
+    CK(dreuse(h, &h->d_plant_xn, &c3, (size_t)n * h->nx));
+    h->cap_plant = (size_t)n;
+  }
+  double *dx_ = h->d_plant_x, *du_ = h->d_plant_u, *dxn_ = h->d_plant_xn;
   CK(cudaMemcpyAsync(dx_, x, sizeof(double) * n * h->nx, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(du_, u, sizeof(double) * n * h->nu, cudaMemcpyHostToDevice, h->stream));
   plant_rk4_kernel<D><<<(n + 63) / 64, 64, 0, h->stream>>>(h->d_model, dx_, du_, dt, dxn_, n, (size_t)h->nu);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(xnext, dxn_, sizeof(double) * n * h->nx, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(dx_); cudaFree(du_); cudaFree(dxn_);
   return EMPC_OK;
 }
 // device-resident closed loop: x0[b] <- RK4(x0[b], us_squash[b][0], dt)

@@ -4,7 +4,11 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .capi import LIB_PATH, EmpcError, lib as _cuda_lib
+import os
+
+from .capi import EmpcError
+
+HOST_LIB_PATH = os.environ.get("EMPC_HOST_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libempc_host.so"))
 
 _h = None
 
@@ -12,7 +16,11 @@ _h = None
 def hlib():
     global _h
     if _h is None:
-        L = _cuda_lib()  # same shared object
+        # the host-side mirror is its own shared object: no CUDA code, so YAML / problem construction (and the CPU arm of
+        # bench.py) never loads the CUDA library; SolverSbFDDP binds libempc_b200.so at run time (host/cuda_abi.cpp)
+        if not os.path.exists(HOST_LIB_PATH):
+            raise EmpcError(f"{HOST_LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(HOST_LIB_PATH)
         L.empc_host_last_error.restype = C.c_char_p
         L.empc_host_parse_yaml.restype = C.c_void_p
         L.empc_host_parse_yaml.argtypes = [C.c_char_p]

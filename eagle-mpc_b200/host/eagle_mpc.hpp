@@ -285,6 +285,18 @@ void sbfddp_barrier_init(ShootingProblem& problem, std::size_t ns, double barrie
 
 // SolverSbFDDP : the hot path.  `batch` independent copies of the problem (different x0 / warm starts) are solved at
 // once on `device`; batch = 1 reproduces the reference's single-OCP interface.
+// crocoddyl::CallbackAbstract / CallbackVerbose as eagle-mpc uses them (setCallbacks, src/mpc-controllers/carrot-mpc.cpp:244-247,
+// bindings/python/eagle_mpc/sbfddp.hpp:63).  A callback receives the record of one iteration (empc_iter_record_t).
+class CallbackAbstract {
+ public:
+  virtual ~CallbackAbstract() = default;
+  virtual void operator()(const empc_iter_record_t& record) = 0;
+};
+class CallbackVerbose : public CallbackAbstract {
+ public:
+  void operator()(const empc_iter_record_t& record) override;
+};
+
 class SolverSbFDDP {
  public:
   SolverSbFDDP(const std::shared_ptr<ShootingProblem>& problem, const std::shared_ptr<SquashingModelSmoothSat>& squashing_model,
@@ -297,6 +309,9 @@ class SolverSbFDDP {
   // batched variants: flat arrays batch*(T+1)*nx / batch*T*nu (nullptr => zero guess)
   bool solveBatch(const double* x0, const double* xs, const double* us, std::size_t maxiter = 100, bool is_feasible = false);
   bool solveWarm(std::size_t maxiter);  // re-solve from the candidate left on the device (MPC warm start)
+
+  void setCallbacks(const std::vector<std::shared_ptr<CallbackAbstract>>& callbacks);
+  const std::vector<std::shared_ptr<CallbackAbstract>>& getCallbacks() const { return callbacks_; }
 
   const std::vector<VectorXd>& get_xs() const { return xs_; }
   const std::vector<VectorXd>& get_us() const { return us_; }
@@ -321,6 +336,8 @@ class SolverSbFDDP {
 
  private:
   void barrierInit();
+  void replayCallbacks();
+  std::vector<std::shared_ptr<CallbackAbstract>> callbacks_;
   std::shared_ptr<ShootingProblem> problem_;
   std::shared_ptr<SquashingModelSmoothSat> squashing_model_;
   FlatProblem flat_;

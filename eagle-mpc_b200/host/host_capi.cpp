@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "eagle_mpc.hpp"
@@ -75,11 +76,11 @@ int empc_host_trajectory_platform(void* t, double* tau_f /* 6*n_rotors */, doubl
 void* empc_host_flatten(void* t, int32_t dt_ms, int32_t squash, const char* integrator, int32_t add_barrier) {
   GUARD({
     auto& tr = ((HostTrajectory*)t)->traj;
-    auto* hf = new HostFlat();
+    std::unique_ptr<HostFlat> hf(new HostFlat());  // released only once nothing can throw any more
     hf->problem = tr->createProblem((std::size_t)dt_ms, squash != 0, integrator);
     if (add_barrier) sbfddp_barrier_init(*hf->problem, tr->get_squash()->get_ns(), 1e-3);
     flatten_problem(*hf->problem, hf->flat);
-    return hf;
+    return hf.release();
   }, nullptr)
 }
 void empc_host_flat_free(void* f) { delete (HostFlat*)f; }
@@ -106,11 +107,11 @@ char* empc_host_flat_cost_names(void* f, int32_t s) {
 void* empc_host_solver_create(void* t, int32_t dt_ms, int32_t squash, const char* integrator, int32_t batch, int32_t device) {
   GUARD({
     auto& tr = ((HostTrajectory*)t)->traj;
-    auto* hs = new HostSolver();
+    std::unique_ptr<HostSolver> hs(new HostSolver());
     hs->traj = tr;
     hs->problem = tr->createProblem((std::size_t)dt_ms, squash != 0, integrator);
     hs->solver.reset(new SolverSbFDDP(hs->problem, tr->get_squash(), batch, device));
-    return hs;
+    return hs.release();
   }, nullptr)
 }
 void empc_host_solver_free(void* s) { delete (HostSolver*)s; }
@@ -145,19 +146,19 @@ static std::vector<VectorXd> unpack_states(const double* state_ref, int32_t n_re
 // RailMpc(state_ref, dt_ref, yaml_path): no trajectory object; nx is the row length of state_ref
 void* empc_host_rail_create(const double* state_ref, int32_t n_ref, int32_t nx, int32_t dt_ref, const char* yaml_path, int32_t create_solver) {
   GUARD_BEGIN
-  auto* hc = new HostCarrot();
+  std::unique_ptr<HostCarrot> hc(new HostCarrot());
   hc->mpc.reset(new RailMpc(unpack_states(state_ref, n_ref, (std::size_t)nx), (std::size_t)dt_ref, getYamlPath(yaml_path), create_solver != 0));
-  return hc;
+  return hc.release();
   GUARD_END(nullptr)
 }
 // WeightedMpc(trajectory, dt_ref, yaml_path): merges the transition stages of `trajectory` in place, like the reference
 void* empc_host_weighted_create(void* t, int32_t dt_ref, const char* yaml_path, int32_t create_solver) {
   GUARD_BEGIN
   auto& tr = ((HostTrajectory*)t)->traj;
-  auto* hc = new HostCarrot();
+  std::unique_ptr<HostCarrot> hc(new HostCarrot());
   hc->traj = tr;
   hc->mpc.reset(new WeightedMpc(tr, (std::size_t)dt_ref, getYamlPath(yaml_path), create_solver != 0));
-  return hc;
+  return hc.release();
   GUARD_END(nullptr)
 }
 
@@ -165,10 +166,10 @@ void* empc_host_carrot_create(void* t, const double* state_ref, int32_t n_ref, i
   GUARD_BEGIN
   auto& tr = ((HostTrajectory*)t)->traj;
   const std::size_t nx = (std::size_t)tr->get_robot_state()->get_nx();
-  auto* hc = new HostCarrot();
+  std::unique_ptr<HostCarrot> hc(new HostCarrot());
   hc->traj = tr;
   hc->mpc.reset(new CarrotMpc(tr, unpack_states(state_ref, n_ref, nx), (std::size_t)dt_ref, getYamlPath(yaml_path), create_solver != 0));
-  return hc;
+  return hc.release();
   GUARD_END(nullptr)
 }
 // CarrotMpc stage table (t_stages: n_stages + 1 entries) and transition flags; null arrays => only *n_stages

@@ -345,13 +345,19 @@ ParserYaml::ParserYaml(const std::string& file, const std::string& path_root, bo
     if (!nm || !du || !costs || costs->type != Node::Sequence)
       throw std::runtime_error("Error parsing stages @" + path + ". Make sure every stage has a name, duration and, at least, one cost.");
     const std::string transition = st.get("transition") ? "true" : "false";  // presence, not value (:274-278)
+    // every cost / contact entry needs a name: the reference's try/catch turns the yaml-cpp exception into this message
+    auto name_of = [&](const Node& entry) -> const std::string& {
+      const Node* n = entry.get("name");
+      if (!n) throw std::runtime_error("Error parsing stages @" + path + ". Make sure every stage has a name, duration and, at least, one cost.");
+      return n->scalar;
+    };
     std::string clist = "[";
-    for (size_t i = 0; i < costs->seq.size(); ++i) clist += (i ? "," : "") + costs->seq[i].get("name")->scalar;
+    for (size_t i = 0; i < costs->seq.size(); ++i) clist += (i ? "," : "") + name_of(costs->seq[i]);
     clist += "]";
     std::string entry = "{name:" + nm->scalar + ",duration:" + du->scalar + ",transition:" + transition + ",costs:" + clist;
     if (const Node* contacts = st.get("contacts")) {
       std::string l = "[";
-      for (size_t i = 0; i < contacts->seq.size(); ++i) l += (i ? "," : "") + contacts->seq[i].get("name")->scalar;
+      for (size_t i = 0; i < contacts->seq.size(); ++i) l += (i ? "," : "") + name_of(contacts->seq[i]);
       entry += ",contacts:" + l + "]";
     }
     entry += "}";

@@ -2,21 +2,24 @@
 // (include/eagle_mpc/sbfddp.hpp:39-52, src/sbfddp.cpp), with the whole iteration running in CUDA behind the C ABI.
 #include <cstring>
 
+#include <cstdio>
+
+#include "cuda_abi.hpp"
 #include "eagle_mpc.hpp"
 
 namespace eagle_mpc {
 
 static void ck(int rc, const char* what) {
-  if (rc != EMPC_OK) throw std::runtime_error(std::string(what) + ": " + empc_last_error());
+  if (rc != EMPC_OK) throw std::runtime_error(std::string(what) + ": " + cuda_abi().last_error());
 }
 
 SolverSbFDDP::SolverSbFDDP(const std::shared_ptr<ShootingProblem>& problem,
                            const std::shared_ptr<SquashingModelSmoothSat>& squashing_model, int batch, int device)
     : problem_(problem), squashing_model_(squashing_model), batch_(batch), device_(device) {
-  empc_default_params(&params_);
+  cuda_abi().default_params(&params_);
   barrierInit();
   flatten_problem(*problem_, flat_);
-  ck(empc_create(&flat_.desc, batch_, device_, &handle_), "empc_create");
+  ck(cuda_abi().create(&flat_.desc, batch_, device_, &handle_), "empc_create");
   const std::size_t T = problem_->get_T();
   const std::size_t nx = (std::size_t)problem_->state->get_nx(), nu = squashing_model_->get_ns(), ndx = (std::size_t)problem_->state->get_ndx();
   xs_.assign(T + 1, problem_->state->zero());
@@ -27,7 +30,7 @@ SolverSbFDDP::SolverSbFDDP(const std::shared_ptr<ShootingProblem>& problem,
   syncX0();
 }
 
-SolverSbFDDP::~SolverSbFDDP() { if (handle_) empc_destroy(handle_); }
+SolverSbFDDP::~SolverSbFDDP() { if (handle_) cuda_abi().destroy(handle_); }
 
 // src/sbfddp.cpp:169-190: add the "barrier" cost (weight 1e-3) to every running model that does not have it yet.
 // One shared cost object; its activation weights follow the smoothing schedule on the device.
@@ -47,11 +50,11 @@ void SolverSbFDDP::syncX0() {
   const std::size_t nx = problem_->x0.size();
   std::vector<double> x0((std::size_t)batch_ * nx);
   for (int b = 0; b < batch_; ++b) std::copy(problem_->x0.begin(), problem_->x0.end(), x0.begin() + (std::size_t)b * nx);
-  ck(empc_set_x0(handle_, x0.data()), "empc_set_x0");
+  ck(cuda_abi().set_x0(handle_, x0.data()), "empc_set_x0");
 }
 
 void SolverSbFDDP::pushCosts(int first, int n) {
-  ck(empc_update_costs(handle_, first, n, flat_.costs.data() + first, 0, (int)flat_.pool.size(), flat_.pool.data()), "empc_update_costs");
+  ck(cuda_abi().update_costs(handle_, first, n, flat_.costs.data() + first, 0, (int)flat_.pool.size(), flat_.pool.data()), "empc_update_costs");
 }
 void SolverSbFDDP::pushAllCosts() { pushCosts(0, (int)flat_.costs.size()); }
 
@@ -72,7 +75,7 @@ void SolverSbFDDP::setCandidate(const std::vector<VectorXd>& xs_warm, const std:
     for (int b = 0; b < batch_; ++b)
       for (std::size_t t = 0; t < T; ++t) std::copy(us_warm[t].begin(), us_warm[t].end(), us.begin() + ((std::size_t)b * T + t) * nu);
   }
-  ck(empc_set_candidate(handle_, xs.empty() ? nullptr : xs.data(), us.empty() ? nullptr : us.data(), is_feasible ? 1 : 0), "empc_set_candidate");
+  ck(cuda_abi().set_candidate(handle_, xs.empty() ? nullptr : xs.data(), us.empty() ? nullptr : us.data(), is_feasible ? 1 : 0), "empc_set_candidate");
 }
 
 void SolverSbFDDP::fetch(bool with_gains) {
@@ -80,19 +83,43 @@ void SolverSbFDDP::fetch(bool with_gains) {
                     ndx = (std::size_t)problem_->state->get_ndx(), B = (std::size_t)batch_;
   std::vector<double> buf(B * (T + 1) * nx), ub(B * T * nu), sb(B * T * nu), c(B), s(B);
   std::vector<int32_t> it(B), fe(B);
-  ck(empc_get_solution(handle_, buf.data(), ub.data(), sb.data(), c.data(), s.data(), it.data(), fe.data()), "empc_get_solution");
+  ck(cuda_abi().get_solution(handle_, buf.data(), ub.data(), sb.data(), c.data(), s.data(), it.data(), fe.data()), "empc_get_solution");
   for (std::size_t t = 0; t <= T; ++t) xs_[t].assign(buf.begin() + t * nx, buf.begin() + (t + 1) * nx);
   for (std::size_t t = 0; t < T; ++t) us_[t].assign(ub.begin() + t * nu, ub.begin() + (t + 1) * nu);
   for (std::size_t t = 0; t < T; ++t) us_squash_[t].assign(sb.begin() + t * nu, sb.begin() + (t + 1) * nu);
   buf.resize(B * T * nu);
   if (with_gains) {
-    ck(empc_get_k(handle_, buf.data()), "empc_get_k");
+    ck(cuda_abi().get_k(handle_, buf.data()), "empc_get_k");
     for (std::size_t t = 0; t < T; ++t) k_[t].assign(buf.begin() + t * nu, buf.begin() + (t + 1) * nu);
     buf.resize(B * T * nu * ndx);
-    ck(empc_get_K(handle_, buf.data()), "empc_get_K");
+    ck(cuda_abi().get_K(handle_, buf.data()), "empc_get_K");
     for (std::size_t t = 0; t < T; ++t) K_[t].assign(buf.begin() + t * nu * ndx, buf.begin() + (t + 1) * nu * ndx);
   }
   cost_ = c[0]; stop_ = s[0]; iter_ = (std::size_t)it[0]; is_feasible_ = fe[0] != 0;
+}
+
+// crocoddyl::CallbackVerbose, fed from the device-side iteration log
+void CallbackVerbose::operator()(const empc_iter_record_t& r) {
+  if (r.total_iter % 10 == 0) std::printf("iter \t cost \t      stop \t    grad \t  xreg \t      ureg \t step \t feas\n");
+  std::printf("%4d  %.5e  %.5e  %.5e  %.5e  %.5e   %.4f     %d\n", r.total_iter, r.cost, r.stop, -r.d1, r.xreg, r.xreg, r.steplength,
+              r.is_feasible);
+}
+
+void SolverSbFDDP::setCallbacks(const std::vector<std::shared_ptr<CallbackAbstract>>& callbacks) {
+  callbacks_ = callbacks;
+  const int passes = 8;  // FDDP passes + DDP clean-up of one solve() (2 + 1 with the default convergence schedule)
+  ck(cuda_abi().enable_iteration_log(handle_, callbacks_.empty() ? 0 : passes * (params_.maxiter + 1)), "empc_enable_iteration_log");
+}
+
+// The reference runs its callbacks inside the iteration loop (src/sbfddp.cpp:303-307); here the loop runs on the device and
+// leaves one record per iteration, which are replayed through the callbacks in order once the solve has returned.
+void SolverSbFDDP::replayCallbacks() {
+  if (callbacks_.empty()) return;
+  std::vector<empc_iter_record_t> rec((std::size_t)8 * (std::size_t)(params_.maxiter + 1));
+  int32_t n = 0;
+  ck(cuda_abi().get_iteration_log(handle_, 0, rec.data(), (int32_t)rec.size(), &n), "empc_get_iteration_log");
+  for (int32_t i = 0; i < n; ++i)
+    for (auto& cb : callbacks_) (*cb)(rec[(std::size_t)i]);
 }
 
 bool SolverSbFDDP::solve(const std::vector<VectorXd>& init_xs, const std::vector<VectorXd>& init_us, std::size_t maxiter,
@@ -100,28 +127,31 @@ bool SolverSbFDDP::solve(const std::vector<VectorXd>& init_xs, const std::vector
   syncX0();
   setCandidate(init_xs, init_us, is_feasible);
   params_.maxiter = (int)maxiter;
-  ck(empc_set_params(handle_, &params_), "empc_set_params");
-  ck(empc_solve(handle_), "empc_solve");
+  ck(cuda_abi().set_params(handle_, &params_), "empc_set_params");
+  ck(cuda_abi().solve(handle_), "empc_solve");
   fetch(true);
+  replayCallbacks();
   return true;  // the reference always returns true (src/sbfddp.cpp:225)
 }
 
 bool SolverSbFDDP::solveWarm(std::size_t maxiter) {
   syncX0();
   params_.maxiter = (int)maxiter;
-  ck(empc_set_params(handle_, &params_), "empc_set_params");
-  ck(empc_solve(handle_), "empc_solve");
+  ck(cuda_abi().set_params(handle_, &params_), "empc_set_params");
+  ck(cuda_abi().solve(handle_), "empc_solve");
   fetch(false);
+  replayCallbacks();
   return true;
 }
 
 bool SolverSbFDDP::solveBatch(const double* x0, const double* xs, const double* us, std::size_t maxiter, bool is_feasible) {
-  if (x0) ck(empc_set_x0(handle_, x0), "empc_set_x0");
-  ck(empc_set_candidate(handle_, xs, us, is_feasible ? 1 : 0), "empc_set_candidate");
+  if (x0) ck(cuda_abi().set_x0(handle_, x0), "empc_set_x0");
+  ck(cuda_abi().set_candidate(handle_, xs, us, is_feasible ? 1 : 0), "empc_set_candidate");
   params_.maxiter = (int)maxiter;
-  ck(empc_set_params(handle_, &params_), "empc_set_params");
-  ck(empc_solve(handle_), "empc_solve");
+  ck(cuda_abi().set_params(handle_, &params_), "empc_set_params");
+  ck(cuda_abi().solve(handle_), "empc_solve");
   fetch(false);
+  replayCallbacks();
   return true;
 }
 

@@ -37,7 +37,6 @@ def _mlib():
         L.empc_host_carrot_costs.argtypes = [C.c_void_p, C.POINTER(abi.Cost), abi.c_double_p]
         L.empc_host_carrot_solve.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, abi.c_double_p, C.c_int32, C.c_double]
         L.empc_host_carrot_result.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_int32_p]
-        L.empc_plant_step.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, C.c_double, abi.c_double_p, C.c_int32]
         L._mpc_ready = True
     return L
 
@@ -91,7 +90,8 @@ class _MpcBase(abi.DescView):
     def plant_step(self, x, u, dt_s):
         x = np.ascontiguousarray(x, dtype=np.float64); u = np.ascontiguousarray(u, dtype=np.float64)
         out = np.zeros_like(x)
-        rc = _mlib().empc_plant_step(self.handle, abi.as_double_p(x), abi.as_double_p(u), float(dt_s), abi.as_double_p(out), 1)
+        _lib().empc_plant_step.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, C.c_double, abi.c_double_p, C.c_int32]
+        rc = _lib().empc_plant_step(self.handle, abi.as_double_p(x), abi.as_double_p(u), float(dt_s), abi.as_double_p(out), 1)
         if rc:
             raise EmpcError(_lib().empc_last_error().decode())
         return out

@@ -118,11 +118,24 @@ typedef struct empc_problem_desc {
   const int32_t* node_costset;              /* n_node_maps*(T+1) */
 } empc_problem_desc_t;
 
+/* Stop rules.  The PepMS Crocoddyl fork defines stoppingCriteria()/stoppingTest() behind two enums that eagle-mpc sets to
+ * StopCriteriaCostReduction / StopTestGaps (src/sbfddp.cpp:28-29); the fork is not in the reference tree, so their
+ * meaning is inferred and upstream Crocoddyl's rule is selectable beside it:
+ *   COST_REDUCTION  stop_ = |cost_prev_ - cost_|                       (fork, inferred; default)
+ *   QU_NORM         stop_ = sum_t ||Qu_t||^2                           (upstream SolverDDP::stoppingCriteria)
+ *   GAPS            converged when stop_ < th_stop_ && gap norm < th_stop_gaps_   (fork, inferred; default)
+ *   FEASIBLE        converged when was_feasible_ && stop_ < th_stop_   (upstream SolverFDDP::solve) */
+enum { EMPC_STOP_CRITERIA_COST_REDUCTION = 0, EMPC_STOP_CRITERIA_QU_NORM = 1 };
+enum { EMPC_STOP_TEST_GAPS = 0, EMPC_STOP_TEST_FEASIBLE = 1 };
+
 /* Solver constants: eagle-mpc's (src/sbfddp.cpp:5-29) and crocoddyl SolverDDP/FDDP defaults. */
 typedef struct empc_solver_params {
   int32_t maxiter;          /* solve(maxiter), default 100 */
   int32_t stop_gap_norm;    /* fork policy knob: 0 = max_t ||fs_t||_inf, 1 = sum_t ||fs_t||_1 */
   int32_t squash_quirk;     /* oracle only: emulate us_squash = "last calc on the data"  */
+  int32_t stop_criteria;    /* set_stoppingCriteria (src/sbfddp.cpp:28): EMPC_STOP_CRITERIA_* */
+  int32_t stop_test;        /* set_stoppingTest (src/sbfddp.cpp:29): EMPC_STOP_TEST_* (FDDP passes; the DDP clean-up always
+                               uses stoppingTestFeasible, src/sbfddp.cpp:387) */
   int32_t reserved;
   double convergence_init;  /* 1e-2 */
   double convergence_stop;  /* 1e-3 */
@@ -250,6 +263,28 @@ int empc_get_cost_tables(const empc_solver_t* h, empc_cost_t* costs, double* poo
  * get_iter, is_feasible) in one call; any pointer may be NULL.  Small batches travel as one packed device-to-host copy. */
 int empc_get_solution(empc_solver_t* h, double* xs, double* us, double* us_squash, double* cost, double* stop, int32_t* iters,
                       int32_t* feasible);
+/* ---- iteration log: the device-side stand-in for setCallbacks({CallbackVerbose}) (src/sbfddp.cpp:303-307,
+ * src/mpc-controllers/carrot-mpc.cpp:244-247, bindings/python/eagle_mpc/sbfddp.hpp:63).  The whole iteration loop runs on
+ * the device, so instead of calling back into the host every iteration each OCP appends one record per inner iteration
+ * (at the point where the reference runs its callbacks: after the line search, the regularisation update and
+ * stoppingCriteria) to a ring of `capacity` records; the host reads it after empc_solve. ---- */
+typedef struct empc_iter_record {
+  int32_t iter;         /* iter_ of the inner solve (SolverAbstract::get_iter inside the callback) */
+  int32_t total_iter;   /* iterations executed by this solve() before this one, all passes */
+  int32_t phase;        /* 0: FDDP pass, 1: DDP clean-up */
+  int32_t accepted;     /* index of the accepted step length (steplength = 2^-accepted), -1: none accepted */
+  int32_t is_feasible;
+  int32_t reserved;
+  double cost, stop, steplength, xreg; /* ureg_ = xreg_ */
+  double d0, d1;        /* expected improvement of the last trial: CallbackVerbose prints grad = -d1 */
+  double smooth;        /* squashing smoothing of the pass */
+} empc_iter_record_t;
+/* capacity = records kept per OCP (the most recent ones); 0 switches the log off (default). */
+int empc_enable_iteration_log(empc_solver_t* h, int32_t capacity);
+/* records of OCP `ocp` from the last solve, oldest first; *n_records = number written (<= max_records). */
+int empc_get_iteration_log(const empc_solver_t* h, int32_t ocp, empc_iter_record_t* out, int32_t max_records,
+                           int32_t* n_records);
+
 /* total inner iterations executed by the last solve, summed over the batch (the benchmark's work unit) */
 int empc_get_total_iterations(const empc_solver_t* h, int64_t* total);
 /* number of kernel launches issued by the last solve and device time (ms) spent per kernel family:

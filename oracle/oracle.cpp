@@ -19,6 +19,7 @@
 //   fillSquashedOutputs            src/sbfddp.cpp:479-486
 // Upstream (restated): SolverAbstract::setCandidate, SolverDDP::{calcDiff,backwardPass,computeGains,
 //   increase/decreaseRegularization}, SolverFDDP::{forwardPass,updateExpectedImprovement,expectedImprovement}.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -232,8 +233,8 @@ struct Solver {
         }
         for (int i = 0; i < ndx; ++i) Vx_t[i] += Qx[i];
       }
-      for (int i = 0; i < ndx; ++i) if (std::isnan(Vx_t[i])) return false;  // raiseIfNaN(lpNorm<inf>)
-      for (int i = 0; i < ndx * ndx; ++i) if (std::isnan(Vxx_t[i])) return false;
+      for (int i = 0; i < ndx; ++i) if (!(std::fabs(Vx_t[i]) < 1e30)) return false;  // raiseIfNaN(lpNorm<inf>)
+      for (int i = 0; i < ndx * ndx; ++i) if (!(std::fabs(Vxx_t[i]) < 1e30)) return false;
     }
     return true;
   }
@@ -303,7 +304,9 @@ struct Solver {
       d0 += a; d1 -= b;
     }
   }
-  static bool has_nan(const double* v, int n) { for (int i = 0; i < n; ++i) if (std::isnan(v[i])) return true; return false; }
+  // crocoddyl::raiseIfNaN(value): isnan || isinf || value >= 1e30; has_bad is that test on the infinity norm of v
+  static bool raise_if_nan(double v) { return std::isnan(v) || std::isinf(v) || v >= 1e30; }
+  static bool has_bad(const double* v, int n) { for (int i = 0; i < n; ++i) if (!(std::fabs(v[i]) < 1e30)) return true; return false; }
 
   // one node of a rollout: us_try = us - alpha k - K dx ; calc ; returns false on NaN ("forward_error")
   bool rollout_node(int t, double alpha, double* xnext) {
@@ -318,8 +321,8 @@ struct Solver {
     node_calc(m, ctx(), costset_of(t), &xs_try[(size_t)t * nx], &us_try[(size_t)t * nu], work[t], &evals[t]);
     std::memcpy(xnext, work[t].xnext, sizeof(double) * nx);
     cost_try += work[t].cost;
-    if (std::isnan(cost_try)) return false;
-    if (has_nan(xnext, nx)) return false;
+    if (raise_if_nan(cost_try)) return false;
+    if (has_bad(xnext, nx)) return false;
     return true;
   }
   // SolverFDDP::forwardPass
@@ -343,7 +346,7 @@ struct Solver {
     }
     node_calc(m, ctx(), costset_of(T), &xs_try[(size_t)T * nx], nullptr, work[T], &evals[T]);
     cost_try += work[T].cost;
-    return !std::isnan(cost_try);
+    return !raise_if_nan(cost_try);
   }
   // SolverSbFDDP::forwardPassDDP (src/sbfddp.cpp:416-460): classical rollout from xs_try[0] as left by earlier calls
   bool forward_pass_ddp(double alpha) {
@@ -356,7 +359,7 @@ struct Solver {
     }
     node_calc(m, ctx(), costset_of(T), &xs_try[(size_t)T * nx], nullptr, work[T], &evals[T]);
     cost_try += work[T].cost;
-    return !std::isnan(cost_try);
+    return !raise_if_nan(cost_try);
   }
   void accept_candidate(bool feasible) {
     xs = xs_try; us = us_try; is_feasible = feasible;
@@ -372,10 +375,34 @@ struct Solver {
     }
     return n;
   }
-  void stopping_criteria() { stop = std::fabs(cost_prev - cost); }                       // StopCriteriaCostReduction
-  bool stopping_test() const { return stop < th_stop && gap_norm() < P.th_stop_gaps; }   // StopTestGaps
+  void stopping_criteria() {
+    if (P.stop_criteria == EMPC_STOP_CRITERIA_QU_NORM) {  // upstream SolverDDP::stoppingCriteria: sum_t ||Qu_t||^2
+      stop = 0;
+      for (int t = 0; t < T; ++t) {
+        double s = 0;
+        for (int i = 0; i < m.nu; ++i) s += Qu[(size_t)t * m.nu + i] * Qu[(size_t)t * m.nu + i];
+        stop += s;
+      }
+    } else {
+      stop = std::fabs(cost_prev - cost);  // StopCriteriaCostReduction (fork, inferred)
+    }
+  }
   bool stopping_test_feasible() const { return was_feasible && stop < th_stop; }
+  bool stopping_test() const {
+    if (P.stop_test == EMPC_STOP_TEST_FEASIBLE) return stopping_test_feasible();  // upstream SolverFDDP::solve
+    return stop < th_stop && gap_norm() < P.th_stop_gaps;                         // StopTestGaps (fork, inferred)
+  }
 
+  // the point where the reference runs its callbacks (src/sbfddp.cpp:303-307, :381-385): one record per iteration
+  std::vector<empc_iter_record_t> log;
+  int accepted_index = -1;
+  void record(int phase) {
+    empc_iter_record_t r;
+    r.iter = iter; r.total_iter = (int)total_iters + iter; r.phase = phase; r.accepted = accepted_index;
+    r.is_feasible = is_feasible ? 1 : 0; r.reserved = 0;
+    r.cost = cost; r.stop = stop; r.steplength = steplength; r.xreg = xreg; r.d0 = d0; r.d1 = d1; r.smooth = smooth_model;
+    log.push_back(r);
+  }
   void trace(const char* ph) const {
     static const char* on = std::getenv("ORC_TRACE");
     if (!on) return;
@@ -400,6 +427,7 @@ struct Solver {
       }
       update_expected_improvement();
       recalc = false;
+      accepted_index = -1;
       for (int n = 0; n < EMPC_N_ALPHAS; ++n) {
         steplength = alphas[n];
         if (!forward_pass(steplength)) continue;
@@ -410,14 +438,14 @@ struct Solver {
           if (d0 < P.th_grad || dV > P.th_acceptstep * dVexp) {
             was_feasible = is_feasible;
             accept_candidate(was_feasible || steplength == 1);
-            cost_prev = cost; cost = cost_try; recalc = true;
+            cost_prev = cost; cost = cost_try; recalc = true; accepted_index = n;
             break;
           }
         } else {
           if (dV > P.th_acceptnegstep * dVexp) {
             was_feasible = is_feasible;
             accept_candidate(was_feasible || steplength == 1);
-            cost_prev = cost; cost = cost_try; recalc = true;
+            cost_prev = cost; cost = cost_try; recalc = true; accepted_index = n;
             break;
           }
         }
@@ -428,6 +456,7 @@ struct Solver {
         if (xreg == P.reg_max) return false;
       }
       stopping_criteria();
+      record(0);
       trace("fddp");
       if (stopping_test()) return true;
     }
@@ -451,6 +480,7 @@ struct Solver {
       }
       expected_improvement_ddp();
       recalc = false;
+      accepted_index = -1;
       for (int n = 0; n < EMPC_N_ALPHAS; ++n) {
         steplength = alphas[n];
         if (!forward_pass_ddp(steplength)) continue;
@@ -460,7 +490,7 @@ struct Solver {
           if (d0 < P.th_grad || !is_feasible || dV > P.th_acceptstep * dVexp) {
             was_feasible = is_feasible;
             accept_candidate(true);
-            cost_prev = cost; cost = cost_try; recalc = true;
+            cost_prev = cost; cost = cost_try; recalc = true; accepted_index = n;
             break;
           }
         }
@@ -471,6 +501,7 @@ struct Solver {
         if (xreg == P.reg_max) return false;
       }
       stopping_criteria();
+      record(1);
       trace("ddp");
       if (stopping_test_feasible()) return true;
     }
@@ -484,6 +515,7 @@ struct Solver {
     smooth = P.smooth_init;
     convergence = P.convergence_init;
     total_iters = 0;
+    log.clear();
     while (convergence >= P.convergence_stop) {
       smooth_model = smooth;  // squashingUpdate() + barrierUpdate() (src/sbfddp.cpp:206-207,462-477)
       th_stop = convergence;
@@ -581,6 +613,14 @@ int orc_phase_rollout(void* h, double smooth, int feasible, int ddp, int alpha_i
   return ok ? 1 : 0;
 }
 void orc_set_xs_try0(void* h, const double* x) { Solver* s = (Solver*)h; std::memcpy(&s->xs_try[0], x, sizeof(double) * s->m.nx); }
+
+// iteration records of the last solve (what a CallbackVerbose would have seen), oldest first
+int orc_get_iteration_log(void* h, empc_iter_record_t* out, int max_records) {
+  Solver* s = (Solver*)h;
+  const int n = std::min((int)s->log.size(), max_records);
+  for (int i = 0; i < n; ++i) out[i] = s->log[i];
+  return (int)s->log.size();
+}
 
 static void copy_out(const std::vector<double>& v, double* out) { std::memcpy(out, v.data(), sizeof(double) * v.size()); }
 int orc_get(void* h, const char* name, double* out) {

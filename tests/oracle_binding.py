@@ -28,6 +28,7 @@ def _load(name="liboracle.so"):
     lib.orc_solve_batch.restype = C.c_double
     lib.orc_solve_batch.argtypes = [C.POINTER(abi.ProblemDesc), C.POINTER(abi.SolverParams), abi.c_double_p, C.c_int, C.c_int,
                                     abi.c_int32_p, abi.c_double_p]
+    lib.orc_get_iteration_log.argtypes = [C.c_void_p, C.POINTER(abi.IterRecord), C.c_int]
     return lib
 
 
@@ -102,6 +103,13 @@ class Oracle:
         rc = self.lib.orc_get(self.p, name.encode(), dp(out))
         assert rc == 0, name
         return out if out.size > 1 else out.reshape(-1)[0]
+
+    def iteration_log(self):
+        """one record per iteration of the last solve (what CallbackVerbose would have seen)"""
+        n = self.lib.orc_get_iteration_log(self.p, None, 0)
+        rec = (abi.IterRecord * max(n, 1))()
+        self.lib.orc_get_iteration_log(self.p, rec, n)
+        return [rec[i] for i in range(n)]
 
     def phase_calc_diff(self, smooth):
         self.lib.orc_phase_calc_diff(self.p, smooth)

@@ -8,7 +8,8 @@ the batch size, and a sample of its OCPs against the oracle:
   * the work counter (sum of inner iterations) equals the per-OCP iteration counts;
   * batch independence: OCPs taken out of the big batch and solved in a batch of their own give bit-identical results
     (an OCP's arithmetic does not depend on its neighbours or its position);
-  * the sampled OCPs match the oracle: identical iteration count, cost / xs / us within 1e-9.
+  * the sampled OCPs match the oracle: identical iteration count, cost / xs / us / K / k / us_squash within the bar of
+    tests/parity.py (1e-9, scaled only by the oracle's own measured rounding sensitivity).
 """
 import importlib
 
@@ -16,6 +17,7 @@ import numpy as np
 import pytest
 
 import oracle_binding as ob
+import parity
 
 pytestmark = pytest.mark.gpu
 host = importlib.import_module("eagle-mpc_b200.host")
@@ -61,10 +63,9 @@ def test_full_batch_properties_and_sampled_parity(name, B, T, dims):
     assert np.array_equal(s.iters(), iters[sample])
     assert np.array_equal(s.cost(), cost[sample])
     assert np.array_equal(s.xs(), xs[sample]) and np.array_equal(s.us(), us[sample])
+    K, k, su = s.K(), s.k(), s.us_squash()
     for j, b in enumerate(sample):
-        o = ob.Oracle(fp); o.set_x0(x0[b]); o.solve()
-        assert int(o.get("iter")) == iters[b], (b, o.get("iter"), iters[b])
-        assert rel(cost[b], o.get("cost")) <= 1e-9
-        assert rel(xs[b], o.get("xs")) <= 1e-9 and rel(us[b], o.get("us")) <= 1e-9
+        got = {"cost": cost[b], "xs": xs[b], "us": us[b], "K": K[j], "k": k[j], "us_squash": su[j]}
+        parity.check_ocp((name, int(b)), fp, x0[b], got, iters[b], feas[b])
     print(name, "full batch: iterations min/median/max", iters.min(), int(np.median(iters)), iters.max(),
           "total", int((iters + 1).sum()))

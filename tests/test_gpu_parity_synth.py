@@ -111,21 +111,11 @@ def test_full_solve(na, nr, T):
     g.solve()
     xs, us, K, k, cost, iters, feas, stop, uss = g.xs(), g.us(), g.K(), g.k(), g.cost(), g.iters(), g.feasible(), g.stop(), g.us_squash()
     assert g.total_iterations() == int((iters + 1).sum())
+    # random synthetic problems converge slowly and stop far from a stationary point, so rounding-level differences are
+    # amplified along the iterations: the yardstick of tests/parity.py (the oracle's own FMA / no-FMA sensitivity on the
+    # same OCP) bounds every key; no OCP is skipped.
+    import parity
+    got = {"xs": xs, "us": us, "K": K, "k": k, "cost": cost, "us_squash": uss, "stop": stop}
     for b in range(B):
-        o = ob.Oracle(h)
-        o.set_x0(x0[b])
-        o.solve()
-        if iters[b] > 60 or o.get("iter") > 60:
-            continue  # long, poorly conditioned runs on random problems: rounding-level differences get amplified
-        assert int(o.get("iter")) == iters[b], (b, o.get("iter"), iters[b])
-        assert int(o.get("feasible")) == feas[b]
-        assert rel(cost[b], o.get("cost")) < 1e-9
-        assert rel(stop[b], o.get("stop")) < 1e-6
-        # these random synthetic problems converge slowly and stop far from a stationary point, so rounding-level
-        # differences are amplified along the iterations; the 1e-9 bar is asserted on the named YAML problems
-        # (test_gpu_parity_yaml.py) and on every phase above.
-        assert rel(xs[b], o.get("xs")) < 1e-6
-        assert rel(us[b], o.get("us")) < 1e-6
-        assert rel(K[b], o.get("K")) < 1e-5
-        assert rel(k[b], o.get("k")) < 1e-5
-        assert rel(uss[b], o.get("us_squash")) < 1e-6
+        parity.check_ocp(("synth", na, b), h, x0[b], {k_: v[b] for k_, v in got.items()}, iters[b], feas[b],
+                         keys=parity.KEYS + ("stop",))

@@ -33,7 +33,7 @@ def test_abi_exports_every_declared_symbol():
     assert not missing, missing
     p = capi.default_params()
     assert p.maxiter == 100 and p.convergence_init == 1e-2 and p.th_acceptnegstep == 2 and p.th_stop_gaps == 1.0
-    assert C.sizeof(abi.Cost) == 40 and C.sizeof(abi.SolverParams) == 16 + 17 * 8
+    assert C.sizeof(abi.Cost) == 40 and C.sizeof(abi.SolverParams) == 24 + 17 * 8
 
 
 def test_no_gpu_means_loud_failure():
