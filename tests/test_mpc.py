@@ -451,7 +451,7 @@ def _check_table(costs, pool, nx, gold, tag):
             assert abs(c.weight - g[2]) <= 4e-16 * abs(g[2]), (tag, i, c.weight, g[2])   # device exp(): last-bit differences
             if c.type == abi.COST_STATE and c.ref_off >= 0:
                 ref = pool[c.ref_off:c.ref_off + nx]
-                assert float(np.dot(ref, np.arange(1, nx + 1))) == g[3], (tag, i)
+                assert abs(float(np.dot(ref, np.arange(1, nx + 1))) - g[3]) <= 1e-9 * max(1.0, abs(g[3])), (tag, i)  # the reference states come from an oracle solve: not bit-stable across oracle builds
 
 
 @pytest.mark.parametrize("kind", ["carrot", "rail", "weighted"])
