@@ -39,6 +39,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mpc", action="store_true", help="skip the single-instance MPC-step latency leg")
     ap.add_argument("--mpc-steps", type=int, default=300)
+    ap.add_argument("--no-config4", action="store_true", help="skip the strong-scaling leg (16384 hextilt_flying_arm_5 OCPs over all ranks)")
+    ap.add_argument("--config4-batch", type=int, default=16384, help="OCPs of the strong-scaling leg, TOTAL over all ranks")
+    ap.add_argument("--no-config5", action="store_true", help="skip the iris_px4 rail / weighted MPC horizon sweep (N = 1 only)")
     return ap.parse_args()
 
 
@@ -141,6 +144,165 @@ def mpc_latency(n_steps, with_cpu):
         out["cpu_p50_ms"] = float(1e3 * np.median(lat_o)); out["cpu_p95_ms"] = float(1e3 * np.percentile(lat_o, 95))
         out["cpu_kind"] = "port (oracle/), 1 thread"
     return out
+
+
+def source_hash():
+    """sha256 over the CUDA sources of the library: stamps ncu-derived numbers so that they cannot go stale silently"""
+    import hashlib
+    hsh = hashlib.sha256()
+    d = os.path.join(ROOT, "eagle-mpc_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            hsh.update(open(os.path.join(d, f), "rb").read())
+    return hsh.hexdigest()[:16]
+
+
+def config4_leg(args, torch, dist, world, rank, local_rank, barrier):
+    """BASELINE.json config 4: hextilt_flying_arm_5 push_slide (T = 100), 16384 OCPs in TOTAL, contiguous index ranges per
+    rank (strong scaling).  No collective on the solver path.  The e2e leg is the data plane of SURVEY 8(e): rank 0 owns the
+    host buffers; every step it uploads all initial states, scatters them over NCCL, every rank solves its shard, and the
+    solutions (xs, us, cost, iterations) are gathered over NCCL to rank 0 and copied to its pinned host memory."""
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    sharding = importlib.import_module("eagle-mpc_b200.sharding")
+    name = "hextilt_flying_arm_5_push_slide"
+    tr, fp, wl, seed0, dt = load_problem(name)
+    total = args.config4_batch
+    b0, b1 = sharding.shard_range(total, rank, world)
+    nb = b1 - b0
+    nx, nu, T = fp.nx, fp.nu, fp.T
+    dev = torch.device("cuda", local_rank)
+    x0_mine = wl.noisy_x0(fp.x0, nb, seed0, first=b0)
+    solver = capi.BatchSolver(fp, nb, device=local_rank)
+    solver.set_x0(x0_mine); solver.set_candidate(None, None, False)
+    solver.enable_kernel_timing(False)
+
+    def resident():
+        solver.reset(); solver.solve()
+        return solver.total_iterations(), solver.solve_stats()[0]
+
+    for _ in range(args.warmup):
+        resident()
+    barrier()
+    t0 = time.perf_counter()
+    it_res, dev_ms = 0, 0.0
+    for _ in range(args.steps):
+        i, ms = resident(); it_res += i; dev_ms += ms
+    barrier()
+    wall = time.perf_counter() - t0
+    # ---- e2e with the NCCL data plane ----
+    x0_pin = torch.from_numpy(wl.noisy_x0(fp.x0, total, seed0)).pin_memory() if rank == 0 else None
+    if rank == 0:
+        xs_pin = torch.empty((total, T + 1, nx), dtype=torch.float64).pin_memory()
+        us_pin = torch.empty((total, T, nu), dtype=torch.float64).pin_memory()
+        cost_pin = torch.empty((total,), dtype=torch.float64).pin_memory()
+        it_pin = torch.empty((total,), dtype=torch.int32).pin_memory()
+    xs_d = torch.empty((nb, T + 1, nx), dtype=torch.float64, device=dev)
+    us_d = torch.empty((nb, T, nu), dtype=torch.float64, device=dev)
+    nccl_bytes = [0]
+
+    def e2e():
+        x0_all = x0_pin.to(dev, non_blocking=True) if rank == 0 else None
+        x0_d = sharding.scatter_rows(x0_all, total, (nx,), dist, device=dev, world=world, rank=rank)
+        torch.cuda.current_stream().synchronize()
+        solver.set_x0_ptr(x0_d.data_ptr())            # device pointer: the C ABI copies with cudaMemcpyDefault
+        solver.set_candidate(None, None, False)
+        solver.solve()
+        solver.get_into("xs", xs_d.data_ptr()); solver.get_into("us", us_d.data_ptr())
+        cost_d = torch.from_numpy(solver.cost()).to(dev); it_d = torch.from_numpy(solver.iters()).to(dev)
+        outs = [sharding.gather_rows(t_, total, dist, world=world, rank=rank) for t_ in (xs_d, us_d, cost_d, it_d)]
+        if rank == 0:
+            for dst, src in zip((xs_pin, us_pin, cost_pin, it_pin), outs):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        if world > 1:
+            mine = nb * (nx + (T + 1) * nx + T * nu + 1) * 8 + nb * 4
+            nccl_bytes[0] += 0 if rank == 0 else mine
+        return solver.total_iterations()
+
+    e2e()
+    barrier()
+    t1 = time.perf_counter()
+    it_e2e = 0
+    for _ in range(args.steps):
+        it_e2e += e2e()
+    barrier()
+    wall_e2e = time.perf_counter() - t1
+    if rank == 0:  # the gathered batch is the batch: initial states in place, finite costs
+        assert torch.equal(xs_pin[:, 0], x0_pin) and bool(torch.isfinite(cost_pin).all()) and int(it_pin.min()) >= 1
+    stats = torch.tensor([wall, wall_e2e, dev_ms], dtype=torch.float64, device=dev)
+    work = torch.tensor([it_res, it_e2e, nccl_bytes[0]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    wall, wall_e2e, dev_ms = stats.tolist()
+    it_res, it_e2e, nccl_b = work.tolist()
+    solver.close()
+    if rank != 0:
+        return None
+    ndx = fp.ndx
+    D = 2 * ndx * ndx + 2 * ndx * nu + nu * nu + ndx + nu
+    peaks, _k = measured_peaks()
+    ceiling = float(peaks.get("hbm_gbs", 6650.0)) * 1e9 / (T * wl.algorithmic_bytes_per_node(nx, ndx, nu))
+    return {"workload": name, "T": T, "dt_ms": dt, "batch_total": total, "batch_per_gpu": nb, "scaling": "strong",
+            "value": it_res / wall, "unit": UNIT, "ms_per_step": 1e3 * wall / args.steps, "device_ms_per_step": dev_ms / args.steps,
+            "iterations_per_step": it_res / args.steps,
+            "frac_of_hbm_ceiling": it_res / wall / world / ceiling,
+            "e2e": {"value": it_e2e / wall_e2e, "unit": UNIT, "ms_per_step": 1e3 * wall_e2e / args.steps,
+                    "h2d_bytes_per_step": total * nx * 8, "d2h_bytes_per_step": total * ((T + 1) * nx + T * nu + 1) * 8 + total * 4,
+                    "nccl_bytes_per_step": nccl_b / args.steps,
+                    "data_plane": "rank 0 pinned host -> H2D -> NCCL scatter of x0 -> solve -> NCCL gather of xs/us/cost/iters -> D2H on rank 0",
+                    "outputs": "xs, us, cost, iters"}}
+
+
+def config5_leg(args):
+    """BASELINE.json config 5: iris_px4 Rail and Weighted MPC, `knots` in {50, 100, 200, 400}, B = 1024 instances of one MPC
+    problem warm-started from the trajectory slice (x0 = trajectory state + the benchmark's noise, seeds 9000+b), mpc.yaml
+    iters (2) SbFDDP iterations each; reference trajectory = iris_px4 displacement solved by the B200 path (maxiter 400)."""
+    import tempfile
+    host = importlib.import_module("eagle-mpc_b200.host")
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    mpcmod = importlib.import_module("eagle-mpc_b200.mpc")
+    wl = importlib.import_module("eagle-mpc_b200.workloads")
+    traj = "iris_px4/trajectories/displacement.yaml"
+    tr = host.Trajectory(traj); fp = tr.createProblem(20)
+    s1 = capi.BatchSolver(fp, 1)
+    p = capi.default_params(); p.maxiter = 400
+    s1.set_params(p); s1.set_x0(fp.x0); s1.set_candidate(None, None, False); s1.solve()
+    xs, us = s1.xs()[0], s1.us()[0]
+    s1.close()
+    tmpdir = tempfile.mkdtemp()
+    B, t0_ms, rows = 1024, 1000, []
+    for kind in ("rail", "weighted"):
+        for knots in (50, 100, 200, 400):
+            y = os.path.join(tmpdir, f"mpc_{knots}.yaml")
+            open(y, "w").write(open(os.path.join(ROOT, "yaml", "iris_px4", "mpc", "mpc.yaml")).read().replace("knots: 40", f"knots: {knots}"))
+            mpc = (mpcmod.RailMpc(xs, 20, y, create_solver=False) if kind == "rail"
+                   else mpcmod.WeightedMpc(host.Trajectory(traj), 20, y, create_solver=False))
+            mpc.updateProblem(t0_ms)
+            T = mpc.knots - 1
+            i0 = t0_ms // 20
+            idx = np.minimum(i0 + np.arange(T + 1), len(xs) - 1)
+            x0 = wl.noisy_x0(xs[i0], B, 9000)
+            g = capi.BatchSolver(mpc, B)
+            costs, pool = mpc.cost_tables()
+            g.update_costs(0, costs, 0, pool)
+            pr = capi.default_params(); pr.maxiter = mpc.iters; pr.convergence_init = 1e-3
+            g.set_params(pr)
+            xs_b = np.broadcast_to(xs[idx], (B, T + 1, xs.shape[1])).copy(); xs_b[:, 0] = x0
+            us_b = np.broadcast_to(us[np.minimum(idx[:-1], len(us) - 1)], (B, T, us.shape[1])).copy()
+            g.set_x0(x0); g.set_candidate(xs_b, us_b, False)
+            for _ in range(3):
+                g.reset(); g.solve()
+            ms, its = 0.0, 0
+            for _ in range(5):
+                g.reset(); g.solve()
+                ms += g.solve_stats()[0]; its += g.total_iterations()
+            rows.append({"controller": kind, "knots": knots, "T": T, "iters_per_instance": its / 5 / B,
+                         "device_ms_per_batched_mpc_step": ms / 5, "ocp_iterations_per_s": its / (ms * 1e-3),
+                         "us_per_instance_step": 1e3 * ms / 5 / B})
+            g.close()
+    return {"workload": "iris_px4 rail / weighted MPC horizon sweep (yaml/iris_px4/mpc/mpc.yaml, knots overridden), B = 1024 warm-started instances",
+            "batch": B, "unit": UNIT, "timing": "CUDA events around each batched solve, 3 warm-ups, mean of 5", "cases": rows}
 
 
 def run_reference(args):
@@ -294,22 +456,26 @@ def main():
         n_launch = max(1, (launches_serial - 2) // 8)  # batch-iterations of the instrumented step (8 launches each)
         ach = bytes_node[names[dom]] * float(units_k[dom]) * T / (ms_k[dom] * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r1_traffic.json:
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload), if there is one
-        traffic = None
+        # DRAM traffic of the dominant kernel: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch at this
+        # workload (ncu cannot run inside a timed bench).  The capture is stamped with the hash of the CUDA sources it
+        # was taken from; a capture of other sources is refused (null) rather than reported stale.
+        traffic, traffic_note = None, "no ncu capture of the current kernels (profiles/r2_traffic.json)"
         try:
-            tr_json = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if tr_json.get("workload") == args.workload and tr_json.get("batch") == B:
+            tr_json = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if tr_json.get("source_hash") != source_hash():
+                traffic_note = "profiles/r2_traffic.json was captured from other kernel sources (%s): refused" % tr_json.get("source_hash")
+            elif tr_json.get("workload") == args.workload and tr_json.get("batch") == B:
                 traffic = tr_json["kernels"].get(names[dom], {}).get("dram_bytes_per_launch")
+                traffic_note = "ncu --set full capture of these sources (profiles/r2_traffic.json)"
         except Exception:
-            traffic = None
+            pass
         # exact FLOP count of the Riccati sweep per node against the measured FP64 tensor rate
         flops_bw = 2 * (2 * ndx**3 + 2 * ndx**2 * nu + ndx * nu**2 + ndx**2 * nu) + nu**3 / 3 + 2 * nu**2 * (ndx + 1) + 2 * ndx**2
         fp64_peak = 37.05  # TFLOP/s, mma.sync m8n8k4.f64 measured on this pool (profiles/r1_baseline.md)
         fp64_ach = flops_bw * float(units_k[1]) * T / (ms_k[1] * 1e-3) / 1e12
         ceiling = peak * 1e9 / (T * sum(bytes_node.values()))  # HBM-bound OCP-iterations/s per GPU (1 rollout trial)
         roofline = {"bound": "hbm", "kernel": kernels[names[dom]], "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic, "peak_kind": peak_kind,
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_kind": peak_kind,
                     "algorithmic_bytes_per_node": bytes_node[names[dom]],
                     "algorithmic_bytes_per_launch": bytes_node[names[dom]] * float(units_k[dom]) * T / n_launch,
                     "avg_launch_ms": float(ms_k[dom] / n_launch),
@@ -331,7 +497,8 @@ def main():
                           "iterations_per_step": iters_all / args.steps, "device_ms_per_step": dev_ms / args.steps},
                "clocks": clocks,
                "e2e": {"value": iters_e2e_all / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": 1e3 * wall_e2e / args.steps},
+                       "ms_per_step": 1e3 * wall_e2e / args.steps,
+                       "outputs": "xs, us, cost, iters (K and k stay on the device: empc_get_K / empc_get_k on request)"},
                "gpu_launches": int(launches_all), "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             ob = oracle_binding()
@@ -348,6 +515,15 @@ def main():
         if world == 1 and not args.no_mpc:
             solver.close()
             out["mpc_step_latency"] = mpc_latency(args.mpc_steps, not args.no_cpu_baseline)
+        if world == 1 and not args.no_config5:
+            solver.close()
+            out["config5"] = config5_leg(args)
+    solver.close()
+    if not args.no_config4:
+        c4 = config4_leg(args, torch, dist, world, rank, local_rank, barrier)
+        if rank == 0:
+            out["config4"] = c4
+    if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

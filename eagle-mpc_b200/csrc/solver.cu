@@ -333,7 +333,7 @@ int empc_get_dims(const empc_solver_t* h, empc_dims_t* o) {
 int empc_set_x0(empc_solver_t* h, const double* x0) {
   if (!h || !x0) return fail(EMPC_ERR_INVALID, "null");
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(h->d_x0, x0, sizeof(double) * h->B * h->nx, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_x0, x0, sizeof(double) * h->B * h->nx, cudaMemcpyDefault, h->stream));  // x0: host or device memory
   CK(cudaStreamSynchronize(h->stream));
   return EMPC_OK;
 }
@@ -349,12 +349,12 @@ int empc_set_candidate(empc_solver_t* h, const double* xs, const double* us, int
   if (!h) return fail(EMPC_ERR_INVALID, "null");
   CK(cudaSetDevice(h->device));
   const size_t nxs = (size_t)h->B * (h->T + 1) * h->nx, nus = (size_t)h->B * h->T * h->nu;
-  if (xs) CK(cudaMemcpyAsync(h->d_xs_init, xs, sizeof(double) * nxs, cudaMemcpyHostToDevice, h->stream));
+  if (xs) CK(cudaMemcpyAsync(h->d_xs_init, xs, sizeof(double) * nxs, cudaMemcpyDefault, h->stream));
   else {
     zero_candidate_kernel<<<(unsigned)((nxs + 255) / 256), 256, 0, h->stream>>>(h->d_xs_init, nxs / h->nx, h->nx);
     CK(cudaGetLastError());
   }
-  if (us) CK(cudaMemcpyAsync(h->d_us_init, us, sizeof(double) * nus, cudaMemcpyHostToDevice, h->stream));
+  if (us) CK(cudaMemcpyAsync(h->d_us_init, us, sizeof(double) * nus, cudaMemcpyDefault, h->stream));
   else CK(cudaMemsetAsync(h->d_us_init, 0, sizeof(double) * nus, h->stream));
   h->init_feasible = is_feasible ? 1 : 0;
   int rc = load_candidate(h);
@@ -788,7 +788,7 @@ int empc_reset(empc_solver_t* h) {
 static int d2h(const empc_solver* h, void* dst, const void* src, size_t bytes) {
   if (!h || !dst) return fail(EMPC_ERR_INVALID, "null");
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream));  // dst: host or device memory (unified addressing)
   CK(cudaStreamSynchronize(h->stream));
   return EMPC_OK;
 }

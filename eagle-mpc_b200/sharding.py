@@ -14,15 +14,27 @@ def shard_range(total, rank, world):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def scatter_rows(array_on_rank0, total, row_shape, dist, device="cpu", dtype=None):
-    """Rank 0 holds `array_on_rank0` (total x row_shape); every rank receives its shard_range rows."""
+def _who(dist, world, rank):
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    return rank, world
+
+
+def scatter_rows(array_on_rank0, total, row_shape, dist, device="cpu", dtype=None, world=None, rank=None):
+    """Rank 0 holds `array_on_rank0` (total x row_shape; a numpy array or a tensor already on `device`); every rank
+    receives its shard_range rows.  Point-to-point sends from rank 0 (NCCL on GPUs): no collective, nothing on the
+    solver path.  A single process (no process group) gets the whole array."""
     import torch
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _who(dist, world, rank)
     dtype = dtype or torch.float64
     b, e = shard_range(total, rank, world)
     out = torch.empty((e - b,) + tuple(row_shape), dtype=dtype, device=device)
     if rank == 0:
-        src = torch.as_tensor(np.ascontiguousarray(array_on_rank0), dtype=dtype, device=device)
+        if torch.is_tensor(array_on_rank0):
+            src = array_on_rank0.to(device=device, dtype=dtype)
+        else:
+            src = torch.as_tensor(np.ascontiguousarray(array_on_rank0), dtype=dtype, device=device)
         reqs = []
         for r in range(1, world):
             rb, re = shard_range(total, r, world)
@@ -36,10 +48,10 @@ def scatter_rows(array_on_rank0, total, row_shape, dist, device="cpu", dtype=Non
     return out
 
 
-def gather_rows(local, total, dist):
+def gather_rows(local, total, dist, world=None, rank=None):
     """Inverse of scatter_rows: rank 0 returns the (total x row_shape) tensor, other ranks None."""
     import torch
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _who(dist, world, rank)
     if rank == 0:
         out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         b, e = shard_range(total, 0, world)
