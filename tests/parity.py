@@ -5,9 +5,16 @@ Where a problem is ill-conditioned the bar is scaled by the oracle's own sensiti
 compiled with and without FMA contraction (liboracle.so / liboracle_nofma.so) gives the yardstick d_self = |o - o_nofma|,
 and the GPU must stay within max(1e-9, 4 d_self) of the oracle (16 d_self where d_self > 1e-6: there a single sample of
 the sensitivity is only an order of magnitude).  The tolerance is therefore always bounded by a measured quantity: there
-is no path on which a key goes unchecked.  If the two oracle builds do not even agree on the iteration count (a stop
-test decided by the last bits), the GPU must reproduce the iteration count and feasibility of ONE of them and is compared
-against that build, the distance between the two builds being the yardstick.
+is no unbounded tolerance.
+
+Iteration path (`log` = the device iteration log, the stand-in for setCallbacks): every iteration's decisions (accepted step
+length, feasibility, regularisation, phase) must be identical and its cost within max(1e-9, 4 x the running maximum of the
+two oracle builds' own per-iteration cost difference), up to the REPRODUCIBILITY HORIZON of the reference itself: the
+first iteration at which the two oracle builds differ from each other by more than 1e-6 or take different decisions.
+Long crawling solves of random synthetic problems are chaotic (the two builds of the same source drift apart to 1e-4
+after ~130 iterations, scripts/diag/iteration_path.py); past that horizon the reference does not reproduce itself and
+neither an iteration count nor a solution can be compared, so the final keys are checked only when the horizon is the end
+of the solve.  Every OCP is checked strictly over all the iterations before its horizon; none is skipped.
 """
 import numpy as np
 
@@ -34,20 +41,48 @@ def oracle_pair(fp, x0, params=None, xs=None, us=None):
     return out
 
 
-def check_ocp(tag, fp, x0, got, iters, feas, params=None, keys=KEYS, xs=None, us=None):
-    """got: dict key -> this OCP's array from the GPU.  Returns [(key, d_gpu, d_self)]."""
+def _decisions(r):
+    return (r.iter, r.total_iter, r.phase, r.accepted, r.is_feasible, r.steplength, r.xreg, r.smooth)
+
+
+def horizon_of(lo, lo2):
+    """(first iteration at which the two oracle builds stop reproducing each other, running max of their cost distance)"""
+    run, dmax = [], 0.0
+    for i in range(min(len(lo), len(lo2))):
+        if _decisions(lo[i]) != _decisions(lo2[i]):
+            return i, run
+        dmax = max(dmax, abs(lo[i].cost - lo2[i].cost) / max(1.0, abs(lo[i].cost)))
+        if dmax > 1e-6:
+            return i, run
+        run.append(dmax)
+    return (len(lo) if len(lo) == len(lo2) else min(len(lo), len(lo2))), run
+
+
+def check_ocp(tag, fp, x0, got, iters, feas, params=None, keys=KEYS, xs=None, us=None, log=None):
+    """got: dict key -> this OCP's array from the GPU; log: its device iteration log (or None).
+    Returns [(key, d_gpu, d_self)]."""
     o, o2 = oracle_pair(fp, x0, params, xs, us)
     it = (int(o.get("iter")), int(o2.get("iter")))
-    ref = o
-    if it[0] != it[1]:
-        assert int(iters) in it, (tag, "iterations", int(iters), it)
-        ref = o if int(iters) == it[0] else o2
-    assert int(ref.get("iter")) == int(iters), (tag, "iterations", int(iters), it)
-    assert int(ref.get("feasible")) == int(feas), (tag, "feasible")
+    lo, lo2 = o.iteration_log(), o2.iteration_log()
+    H, run = horizon_of(lo, lo2)
+    reproducible = it[0] == it[1] and H == len(lo)
+    if log is not None:
+        assert len(log) >= min(H, len(lo)), (tag, "log shorter than the horizon", len(log), H)
+        for i in range(H):
+            assert _decisions(log[i]) == _decisions(lo[i]), (tag, "decisions at iteration", i, _decisions(log[i]), _decisions(lo[i]))
+            d = abs(log[i].cost - lo[i].cost) / max(1.0, abs(lo[i].cost))
+            assert d <= max(TOL, 4 * run[i]), (tag, "cost at iteration", i, d, run[i])
+    else:
+        assert reproducible, (tag, "the oracle does not reproduce itself on this OCP: pass the iteration log", it, H)
+    if not reproducible:
+        assert H >= 1, (tag, "no reproducible iteration at all")
+        return [("horizon", float(H), float(len(lo)))]
+    assert it[0] == int(iters), (tag, "iterations", int(iters), it)
+    assert int(o.get("feasible")) == int(feas), (tag, "feasible")
     report = []
     for key in keys:
         d_self = rel(o2.get(key), o.get(key))
-        d_gpu = rel(got[key], ref.get(key))
+        d_gpu = rel(got[key], o.get(key))
         factor = 16 if d_self > 1e-6 else 4
         assert d_gpu <= max(TOL, factor * d_self), (tag, key, d_gpu, d_self)
         report.append((key, d_gpu, d_self))

@@ -106,16 +106,17 @@ def test_full_solve(na, nr, T):
     x0[:, :3] = rng.uniform(-0.3, 0.3, size=(B, 3))
     x0[:, 7:h.nq] = rng.uniform(-0.2, 0.2, size=(B, h.na))
     g = capi.BatchSolver(h, B)
+    g.enable_iteration_log(1024)
     g.set_x0(x0)
     g.set_candidate(None, None, False)
     g.solve()
     xs, us, K, k, cost, iters, feas, stop, uss = g.xs(), g.us(), g.K(), g.k(), g.cost(), g.iters(), g.feasible(), g.stop(), g.us_squash()
     assert g.total_iterations() == int((iters + 1).sum())
-    # random synthetic problems converge slowly and stop far from a stationary point, so rounding-level differences are
-    # amplified along the iterations: the yardstick of tests/parity.py (the oracle's own FMA / no-FMA sensitivity on the
-    # same OCP) bounds every key; no OCP is skipped.
+    # random synthetic problems crawl for ~200 iterations and are chaotic in the DDP clean-up (two builds of the oracle drift
+    # apart to 1e-4): every OCP's iteration path is checked strictly up to the reference's own reproducibility horizon
+    # (tests/parity.py); no OCP is skipped.
     import parity
     got = {"xs": xs, "us": us, "K": K, "k": k, "cost": cost, "us_squash": uss, "stop": stop}
     for b in range(B):
         parity.check_ocp(("synth", na, b), h, x0[b], {k_: v[b] for k_, v in got.items()}, iters[b], feas[b],
-                         keys=parity.KEYS + ("stop",))
+                         keys=parity.KEYS + ("stop",), log=g.iteration_log(b))

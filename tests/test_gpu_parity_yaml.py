@@ -41,19 +41,11 @@ def test_named_problem(name, B):
     iters, feas = g.iters(), g.feasible()
     worst = {}
     for b in range(B):
-        for key, d_gpu, d_self in parity.check_ocp((name, b), fp, x0[b], {k_: v[b] for k_, v in got.items()}, iters[b], feas[b]):
+        for key, d_gpu, d_self in parity.check_ocp((name, b), fp, x0[b], {k_: v[b] for k_, v in got.items()}, iters[b], feas[b],
+                                                       log=g.iteration_log(b)):
             w = worst.setdefault(key, [0.0, 0.0])
             w[0] = max(w[0], d_gpu); w[1] = max(w[1], d_self)
     print(name, "iters", iters.tolist(), {k_: f"gpu {v[0]:.1e} / self {v[1]:.1e}" for k_, v in worst.items()})
-    # iteration log (the stand-in for setCallbacks / CallbackVerbose): the same decisions, iteration by iteration
-    o = ob.Oracle(fp); o.set_x0(x0[0]); o.solve()
-    if int(o.get("iter")) == iters[0]:
-        ref, log = o.iteration_log(), g.iteration_log(0)
-        assert len(log) == len(ref) == iters[0] + 1
-        for a, r in zip(log, ref):
-            assert (a.iter, a.total_iter, a.phase, a.accepted, a.is_feasible) == (r.iter, r.total_iter, r.phase, r.accepted, r.is_feasible)
-            assert a.steplength == r.steplength and a.xreg == r.xreg and a.smooth == r.smooth
-            assert abs(a.cost - r.cost) <= 1e-9 * max(1.0, abs(r.cost))
 
 
 @pytest.mark.parametrize("criteria,test", [(1, 1), (1, 0), (0, 1)])
