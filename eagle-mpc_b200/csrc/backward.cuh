@@ -9,52 +9,60 @@
 // Quu = Luu + FuTV Fu + ureg I, Qx = Lx + Fx^T Vx', Qu = Lu + Fu^T Vx', LLT(Quu), K = Quu^-1 Qxu^T, k = Quu^-1 Qu,
 // Vx = Qx + K^T Quu k - 2 K^T Qu (+ Vxx fs), Vxx = sym(Qxx - Qxu K) + xreg I.
 //
-// The six dense products are the only GEMM-shaped work on the SbFDDP path (18x18x18 for flying_arm_3).  They run as
-// mma.sync.m8n8k4.f64 (SASS DMMA) on 8x8 tiles with zero-padded operands in shared memory: one DMMA replaces 8 DFMA
-// warp-instructions and needs two 8-byte fragment loads instead of ~7 (measured: the FP64 tensor rate equals the vector
-// rate on B200, so the gain is issue slots and shared-memory bandwidth, not FLOPs; profiles/r1_baseline.md).
-// Leading dimensions are chosen per operand role so that every fragment load is bank-conflict free:
-//   LDB = 24 / LDF = 40  (= 8 mod 16)  operands read as B (row k) or as transposed A:   [Fx | Fu] (packed), V', K
-//   LDA = 20  (= 4 mod 16)  operands read as row-major A (row i, 4 consecutive k):   F^T V, Qxu
-// Fx and Fu are packed side by side, so that F^T V = [FxTV ; FuTV] and the symmetric [[Qxx, Qxu], [Qux, Quu]] =
-// (F^T V) F each take one k-loop and only the upper tiles of the latter are computed: 128 DMMAs per node instead of
-// 197 for the six separate padded products.
-// Everything else (Cholesky of Quu, triangular solves, vector updates, ordered reductions) is warp-cooperative out of
-// shared memory with __syncwarp only: no block-level barrier anywhere on the sweep.  The next node's Fx / Fu arrive by
-// cp.async while the current node is being factorised; its cost blocks are prefetched into registers.
+// The dense products are the only GEMM-shaped work on the SbFDDP path (18x18x18 for flying_arm_3).  They run as
+// mma.sync.m8n8k4.f64 (SASS DMMA) on 8x8 tiles with zero-padded operands: one DMMA replaces 8 DFMA warp-instructions and
+// needs two 8-byte fragment elements per lane instead of ~7 (the FP64 tensor rate equals the vector rate on B200, so the
+// gain is issue slots and shared-memory traffic, not FLOPs).  Fx and Fu are treated as one packed operand F = [Fx | Fu]
+// (n x (n + m)), so that F^T V = [FxTV ; FuTV] and the symmetric [[Qxx, Qxu], [Qux, Quu]] = (F^T V) F each take one k-loop
+// and only the upper tiles of the latter are computed: 128 DMMAs per node instead of 197 for six separate padded products.
+//
+// What bounds the kernel (ncu, round 2: profiles/r2_backward.md): the LSU data pipe — shared-memory wavefronts, 26 % of
+// them bank-conflict replays in the round-1 layout — not occupancy (14 resident warps per SM were SLOWER than 8) and not
+// HBM or the FP64 pipes.  The kernel is therefore organised around shared-memory wavefronts per node:
+//   * F never touches shared memory.  In both products it is read with the same fragment pattern (element
+//     (4 ks + c, 8 i + r)), so each lane loads its KN x PT fragment elements of [Fx | Fu] straight from HBM into
+//     registers — issued as soon as the previous node's F is dead, in flight during the factorisation — and the same
+//     registers feed F^T V (as the transposed A operand) and (F^T V) F (as the B operand).
+//   * Vx' rides along as column n of the V' operand: F^T [V' | Vx'] gives F^T V and the Qx / Qu updates in the same
+//     DMMAs (the tile holding column n is computed anyway).
+//   * every matrix in shared memory has leading dimension 24 with an XOR swizzle of the column index by row bit 1
+//     (element (r, c) at r * 24 + (c ^ ((r & 2) << 1))): conflict-free for the C-layout 16-byte stores, for the B /
+//     transposed-A fragment loads (4 rows x 8 columns) AND for the row-major A fragment loads (8 rows x 4 columns); the
+//     plain leading dimensions of round 1 (24 / 20) made half of those two-way conflicts.
+//   * Qxu is kept transposed (Qux, m x n): the gain solves read their right-hand sides and the product Qxu K its A
+//     operand without conflicts from the same array.
+//   * the Cholesky factor is read row-wise only (row-oriented substitutions), as 16-byte broadcasts.
+//   * Qxx lives in accumulator registers from Lxx (HBM -> fragments) to the symmetrised Vxx.
+// Everything is warp-cooperative with __syncwarp only: no block-level barrier anywhere on the sweep.
 #pragma once
 
 template <class D>
 struct BwCfg {
   static constexpr int n = D::NDX, m = D::NU;
   static constexpr int NT = (n + 7) / 8, MT = (m + 7) / 8;      // 8-wide tiles over n, m
+  static constexpr int NTV = (n + 8) / 8;                        // ... over the n + 1 columns of [V' | Vx']
   static constexpr int KN = (n + 3) / 4, KM = (m + 3) / 4;      // 4-deep k-steps over n, m
   static constexpr int NP = 8 * NT, MP = 8 * MT, KNP = 4 * KN, KMP = 4 * KM;
-  static constexpr int LDB = 24;
-  // packed operand F = [Fx | Fu] (n x (n + m)): one product F^T V gives FxTV and FuTV, one product (F^T V) F gives the
-  // whole symmetric matrix [[Qxx, Qxu], [Qux, Quu]], of which only the upper tiles are computed
+  static constexpr int LD = 24;                                  // leading dimension of every swizzled matrix
+  static_assert(8 * NTV <= LD && KNP <= LD && NP <= LD, "operand wider than the leading dimension");
+  // packed operand F = [Fx | Fu] (n x (n + m))
   static constexpr int PW = n + m, PT = (PW + 7) / 8, PP = 8 * PT;
-  static constexpr int LDF = (PP <= 24) ? 24 : 40;               // = 8 mod 16, >= PP
-  static_assert(PP <= LDF, "packed operand wider than its leading dimension");
-  static constexpr int lda_for(int k) { return k <= 20 ? 20 : 36; }
-  static constexpr int LDA = lda_for(KNP);                       // F^T V (row-major A operand)
-  static constexpr int LDQ = 20;                                 // Qxu (k extent KMP <= 16)
-  static_assert(NP <= LDB && MP <= LDB && KMP <= LDQ, "operand wider than its leading dimension");
-  static constexpr int ROWS_K = (KNP > NP ? KNP : NP);
-  static constexpr int oF = 0;                                   // KNP x LDF      [Fx | Fu]
-  static constexpr int oV = oF + KNP * LDF;                      // ROWS_K x LDB   Vxx' (symmetric)
+  static constexpr int ROWS_V = (KNP > NP ? KNP : NP);
+  static constexpr int oV = 0;                                   // ROWS_V x LD    [Vxx' | Vx'] (Vxx' symmetric)
   // (Qxx never touches shared memory: Lxx is loaded from HBM straight into the accumulator fragments and
   //  Qxx - Qxu K is symmetrised in registers)
-  static constexpr int oQxu = oV + ROWS_K * LDB;                 // NP x LDQ       Qxu
-  static constexpr int oQuu = oQxu + NP * LDQ;                   // MP x LDQ       Quu
-  static constexpr int oFTV = oQuu + MP * LDQ;                   // PP x LDA       F^T V = [FxTV ; FuTV]
-  static constexpr int oK = oFTV + PP * LDA;                     // KMP x LDB      gains K (m x n), zero padded
-  // the Cholesky factor lives in the F^T V area, which is dead once the Q blocks are formed
-  static constexpr int oL = oFTV;                                // m x m Cholesky factor of Quu, then m reciprocal pivots
-  static_assert(m * m + m <= PP * LDA, "L does not fit the F^T V area");
-  static constexpr int oVec = oK + KMP * LDB;
-  static constexpr int vQx = 0, vQu = vQx + NP, vVx = vQu + MP, vFs = vVx + NP, vG = vFs + NP, vKv = vG + NP,
-                       vQuuk = vKv + MP, vTmp = vQuuk + MP, vLuu = vTmp + NP, VEC = vLuu + MP;
+  static constexpr int oFTV = oV + ROWS_V * LD;                  // PP x LD        F^T V = [FxTV ; FuTV]
+  static constexpr int oQux = oFTV + PP * LD;                    // KMP x LD       Qux = Qxu^T, zero padded
+  static constexpr int oK = oQux + KMP * LD;                     // KMP x LD       gains K (m x n), zero padded
+  static constexpr int LM = m + (m & 1);                         // row stride of Quu and of its Cholesky factor (even)
+  static constexpr int oQuu = oK + KMP * LD;                     // m x LM         Quu
+  static constexpr int oL = oQuu + m * LM;                       // m x LM         Cholesky factor L (rows), L^T (rows), LM reciprocal pivots
+  static constexpr int oVec = oL + 2 * m * LM + LM;
+  // vectors: slots of NP + 2 doubles (zero beyond the vector's length: they are DMMA operands of the dot products at the
+  // end of a node), skewed so that the same index of different vectors falls into different banks
+  static constexpr int SLOT = NP + 2;
+  static constexpr int vQx = 0, vQu = SLOT, vVx = 2 * SLOT, vFs = 3 * SLOT, vG = 4 * SLOT, vKv = 5 * SLOT,
+                       vQuuk = 6 * SLOT, vTmp = 7 * SLOT, vLuu = 8 * SLOT, VEC = 9 * SLOT;
   static constexpr int TOTAL0 = oVec + VEC;
   static constexpr int TOTAL = TOTAL0 + (TOTAL0 & 1);
   // register prefetch (one node ahead) of the small cost blocks: diag(Luu) (m), Lx | Lu (n + m, contiguous) + fs.  Lxu is
@@ -63,9 +71,18 @@ struct BwCfg {
   // node_diff_kernel (the tile buffer is zero-initialised) nor read here.
   static constexpr int LBLK = m + n + m;
   static constexpr int PREF = (LBLK + 31) / 32;
-#ifndef EMPC_BW_WARPS_PER_SM
-#define EMPC_BW_WARPS_PER_SM 8
+  // resident warps (= OCPs) per SM; the register budget follows from it (65536 / (32 WARPS))
+#ifndef EMPC_BW_WARPS
+#define EMPC_BW_WARPS 8
 #endif
+  static constexpr int WARPS = EMPC_BW_WARPS;
+  // (registers are allocated per warp in units that round the per-thread count up to a multiple of 32 — measured:
+  //  144 registers gave 12 resident warps, 200 gave 9 — so the budget is the multiple of 32 below 65536 / (32 WARPS))
+  static constexpr int MAXREG = (65536 / (32 * WARPS)) / 32 * 32 > 255 ? 255 : (65536 / (32 * WARPS)) / 32 * 32;
+  // tile rows of F^T V per pass: all at once when the registers allow it, otherwise in halves
+  static constexpr int IH = (PT <= 3 || (MAXREG >= 200 && KN * PT <= 20)) ? PT : (PT + 1) / 2;
+  static constexpr int HALVES = (PT + IH - 1) / IH;
+  static_assert((TOTAL * 8 + 1024) * WARPS <= 228 * 1024, "shared memory of the resident warps exceeds the SM");
 };
 
 struct BwParams {
@@ -74,31 +91,19 @@ struct BwParams {
   int stop_qu_norm;  // EMPC_STOP_CRITERIA_QU_NORM: also leave sum_t ||Qu_t||^2 in the OCP state
 };
 
+// optional phase timing (-DEMPC_BW_PROFILE): lane 0 of block 0 accumulates clock64() differences between the marks of a
+// node into bf.nodesc of the last OCP... (diagnostic builds only; scripts/diag/backward_phases.py)
+#ifdef EMPC_BW_PROFILE
+__device__ unsigned long long g_bw_prof[16];
+#define EMPC_BW_MARK(k) do { if (lane == 0 && blockIdx.x == 0) { const long long c_ = clock64(); if ((k) > 0) atomicAdd(&g_bw_prof[(k)], (unsigned long long)(c_ - prof_t)); else if (t < T - 1) atomicAdd(&g_bw_prof[8], (unsigned long long)(c_ - prof_t)); prof_t = c_; } } while (0)
+#else
+#define EMPC_BW_MARK(k) do { } while (0)
+#endif
+
 EMPC_DI void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// acc[i][j] (+)= op(A) B over KS k-steps.  Fragment coordinates: r = lane >> 2, c = lane & 3.
-//   AT  : A is stored k-major (A(i,k) = Ab[k * lda + i]), else row-major (A(i,k) = Ab[i * lda + k])
-//   NEG : accumulate -A B
-template <int MT_, int NT_, int KS_, bool AT, bool NEG>
-EMPC_DI void warp_mm(double (&acc)[MT_][NT_][2], const double* __restrict__ Ab, int lda, const double* __restrict__ Bb, int ldb, int r, int c) {
-#pragma unroll
-  for (int ks = 0; ks < KS_; ++ks) {
-    double a[MT_], b[NT_];
-#pragma unroll
-    for (int i = 0; i < MT_; ++i) {
-      const double v = AT ? Ab[(4 * ks + c) * lda + 8 * i + r] : Ab[(8 * i + r) * lda + 4 * ks + c];
-      a[i] = NEG ? -v : v;
-    }
-#pragma unroll
-    for (int j = 0; j < NT_; ++j) b[j] = Bb[(4 * ks + c) * ldb + 8 * j + r];
-#pragma unroll
-    for (int i = 0; i < MT_; ++i)
-#pragma unroll
-      for (int j = 0; j < NT_; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-  }
-}
 template <int MT_, int NT_>
 EMPC_DI void acc_zero(double (&acc)[MT_][NT_][2]) {
 #pragma unroll
@@ -106,34 +111,20 @@ EMPC_DI void acc_zero(double (&acc)[MT_][NT_][2]) {
 #pragma unroll
     for (int j = 0; j < NT_; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 }
-// C tile (i, j): lane holds C[8 i + r][8 j + 2 c], C[8 i + r][8 j + 2 c + 1]
-template <int MT_, int NT_>
-EMPC_DI void acc_load(double (&acc)[MT_][NT_][2], const double* Cb, int ldc, int r, int c) {
-#pragma unroll
-  for (int i = 0; i < MT_; ++i)
-#pragma unroll
-    for (int j = 0; j < NT_; ++j) {
-      const double2 v = *reinterpret_cast<const double2*>(Cb + (8 * i + r) * ldc + 8 * j + 2 * c);
-      acc[i][j][0] = v.x; acc[i][j][1] = v.y;
-    }
-}
-// columns >= ncols are not stored (the padded tail of a narrow leading dimension)
-template <int MT_, int NT_>
-EMPC_DI void acc_store(const double (&acc)[MT_][NT_][2], double* Cb, int ldc, int ncols, int r, int c) {
-#pragma unroll
-  for (int i = 0; i < MT_; ++i)
-#pragma unroll
-    for (int j = 0; j < NT_; ++j)
-      if (8 * j + 2 * c < ncols) *reinterpret_cast<double2*>(Cb + (8 * i + r) * ldc + 8 * j + 2 * c) = make_double2(acc[i][j][0], acc[i][j][1]);
-}
+
+// column swizzle of the LD = 24 matrices: element (r, c) lives at r * 24 + (c ^ bw_swz(r))
+EMPC_DI constexpr int bw_swz(int r) { return (r & 2) << 1; }
 
 template <class D>
-__global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buffers bf, BwParams P) {
+__global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_kernel(Buffers bf, BwParams P) {
   using S = BwCfg<D>;
-  constexpr int n = S::n, m = S::m, LDB = S::LDB, LDA = S::LDA, LDQ = S::LDQ;
+  constexpr int n = S::n, m = S::m, LD = S::LD, LM = S::LM, PW = S::PW;
   extern __shared__ __align__(16) double bw_sm[];
   double* sm = bw_sm;
   const int lane = threadIdx.x, fr = lane >> 2, fc = lane & 3;
+  // fragment coordinates under the swizzle.  B / transposed-A fragments: element (4 ks + fc, 8 j + fr) -> column 8 j + frs;
+  // C fragments and row-major A fragments: row 8 i + fr -> column offset XOR swr
+  const int swr = bw_swz(fr), frs = fr ^ bw_swz(fc), c2s = (2 * fc) ^ swr;
   const int b = bf.b0 + blockIdx.x;
   OcpState st = bf.st[b];
   if (!P.force && st.phase == PHASE_DONE) return;
@@ -164,39 +155,33 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
   }
   const int feasible = st.is_feasible;
 
-  constexpr int LDF = S::LDF, PW = S::PW;
-  double* sF = sm + S::oF; double* sV = sm + S::oV;
-  double* sQxu = sm + S::oQxu; double* sQuu = sm + S::oQuu; double* sFTV = sm + S::oFTV;
-  double* sK = sm + S::oK; double* sL = sm + S::oL; double* sLinv = sL + m * m;
+  double* sV = sm + S::oV; double* sFTV = sm + S::oFTV; double* sQux = sm + S::oQux; double* sK = sm + S::oK;
+  double* sQuu = sm + S::oQuu; double* sL = sm + S::oL; double* sLT = sL + m * LM; double* sLinv = sLT + m * LM;
   double* vec = sm + S::oVec;
   double* Qx = vec + S::vQx; double* Qu = vec + S::vQu; double* Vxp = vec + S::vVx; double* fsv = vec + S::vFs;
   double* gv = vec + S::vG; double* kv = vec + S::vKv; double* Quuk = vec + S::vQuuk; double* tmpv = vec + S::vTmp;
   double* Luud = vec + S::vLuu;
 
-  // asynchronous fetch of Fx (16-byte pieces, n even) and Fu (8-byte pieces) of node t into their padded layouts
-  auto fetch_F = [&](int t) {
+  // F = [Fx | Fu] of a node as DMMA fragments, HBM -> registers: f[ks][i] = F(4 ks + fc, 8 i + fr), zero beyond (n, PW).
+  // The same element is this lane's share of the transposed-A fragment of F^T V and of the B fragment of (F^T V) F.
+  int f_off[S::PT], f_str[S::PT];  // per tile column: offset of (row fc, this lane's column) in the node tile, row stride
+#pragma unroll
+  for (int i = 0; i < S::PT; ++i) {
+    const int col = 8 * i + fr;
+    f_str[i] = col < n ? n : m;
+    f_off[i] = (col < n ? D::oFx + col : D::oFu + (col - n)) + fc * f_str[i];
+    if (col >= PW) { f_off[i] = 0; f_str[i] = 0; }
+  }
+  double f[S::KN][S::PT];
+  auto load_F = [&](int t) {
     const double* tg = bf.tiles + (nb + t) * D::TILE;
-    {  // Fx: n rows of n/2 16-byte pieces; piece e = lane + 32 q sits in row e / (n/2); indices advance incrementally
-      constexpr int H = n / 2, DI = 32 / H, DC = 32 % H;
-      int i = lane / H, cc = lane - i * H;
 #pragma unroll
-      for (int q = 0; q < (n * H + 31) / 32; ++q) {
-        if (lane + 32 * q < n * H) cp_async16(sF + i * LDF + 2 * cc, tg + D::oFx + 2 * (lane + 32 * q));
-        i += DI; cc += DC;
-        if (cc >= H) { cc -= H; i += 1; }
-      }
-    }
-    {  // Fu: n rows of m 8-byte pieces
-      constexpr int DI = 32 / m, DC = 32 % m;
-      int i = lane / m, j = lane - i * m;
+    for (int ks = 0; ks < S::KN; ++ks)
 #pragma unroll
-      for (int q = 0; q < (n * m + 31) / 32; ++q) {
-        if (lane + 32 * q < n * m) cp_async8(sF + i * LDF + n + j, tg + D::oFu + lane + 32 * q);
-        i += DI; j += DC;
-        if (j >= m) { j -= m; i += 1; }
+      for (int i = 0; i < S::PT; ++i) {
+        const bool on = (4 * ks + fc < n) && (8 * i + fr < PW);
+        f[ks][i] = on ? __ldg(tg + f_off[i] + 4 * ks * f_str[i]) : 0.0;
       }
-    }
-    cp_async_commit();
   };
   // cost blocks of node t: HBM -> registers (issued early) -> shared memory (at the end of the previous node).
   // Source / destination offsets of this lane's elements are fixed: computed once, packed in 32-bit registers.
@@ -220,7 +205,34 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
     for (int q = 0; q < S::PREF; ++q) { const unsigned d = pre_off[q] & 0xffffu; if (d != 0xffffu) sm[d] = pre[q]; }
     if (lane < n) fsv[lane] = pre_fs;
   };
+  // Lxx of a node as accumulator fragments (row 8 i + fr, columns 8 j + 2 fc, +1; upper tiles), HBM -> registers one node
+  // ahead, issued together with F: a load issued at the start of a node would stall its first DMMA for the whole HBM
+  // latency (ncu round 2: 10 % of the kernel's time sat on that one instruction)
+  double qn[S::NT][S::NT][2];
+  auto load_Lxx = [&](int t) {
+    const double* lg = bf.tiles + (nb + t) * D::TILE + D::oLxx;
+#pragma unroll
+    for (int i = 0; i < S::NT; ++i)
+#pragma unroll
+      for (int j = i; j < S::NT; ++j) {
+        const int row = 8 * i + fr, col = 8 * j + 2 * fc;
+        double2 v = make_double2(0.0, 0.0);
+        if (row < n && col < n) v = __ldg(reinterpret_cast<const double2*>(lg + row * n + col));
+        qn[i][j][0] = v.x; qn[i][j][1] = v.y;
+      }
+  };
+  // operands of the dot-product DMMA at the end of a node (see there): this lane's row of A / column of B
+  const double* dot_a = vec + ((fr == 0) ? S::vQu : (fr == 1) ? S::vKv : (fr == 2) ? S::vVx : (fr == 3) ? S::vFs : S::vQu);
+  const double* dot_b = vec + ((fr == 0) ? S::vKv : (fr == 1) ? S::vQuuk : (fr == 2) ? S::vFs : (fr == 3) ? S::vG : S::vQu);
+  // column n of the V operand carries Vx': tile JV, fragment column FCV (n is even: slot 0 of the pair)
+  constexpr int JV = n / 8, FCV = (n % 8) / 2;
+  // this lane as a column index under the swizzle of rows with bit 1 set: (row j, column `lane`)
+  const int lane_sw = lane ^ 4;
 
+#ifdef EMPC_BW_PROFILE
+  long long prof_t = clock64();
+#endif
+  double pre[S::PREF], pre_fs = 0.0;
   int failed;
   while (true) {
     failed = 0;
@@ -231,13 +243,14 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
     // ---- terminal node: Vxx = Lxx + xreg I ; Vx = Lx (+ Vxx fs) ----
     {
       const double* tg = bf.tiles + (nb + T) * D::TILE;
-      for (int e = lane; e < n * n; e += 32) { const int i = e / n, j = e - i * n; sV[i * LDB + j] = tg[D::oLxx + e] + ((i == j) ? xreg : 0.0); }
+      for (int e = lane; e < n * n; e += 32) { const int i = e / n, j = e - i * n; sV[i * LD + (j ^ bw_swz(i))] = tg[D::oLxx + e] + ((i == j) ? xreg : 0.0); }
       if (lane < n) { Vxp[lane] = tg[D::oLx + lane]; fsv[lane] = bf.fs[(nb + T) * n + lane]; }
       __syncwarp();
       if (lane < n) {
         double s = 0;
+        const int sw = bw_swz(lane);
 #pragma unroll 6
-        for (int j = 0; j < n; ++j) s += sV[lane * LDB + j] * fsv[j];
+        for (int j = 0; j < n; ++j) s += sV[lane * LD + (j ^ sw)] * fsv[j];
         gv[lane] = s;
         if (!feasible) Vxp[lane] += s;
       }
@@ -248,71 +261,61 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         double* ns = bf.nodesc + (nb + T) * 4;
         ns[0] = 0; ns[1] = 0; ns[2] = s0; ns[3] = s1;
       }
-      if (lane < n) { bf.Vx[(nb + T) * n + lane] = Vxp[lane]; bf.g[(nb + T) * n + lane] = gv[lane]; }
-      fetch_F(T - 1);
-      double pre[S::PREF], pre_fs;
+      if (lane < n) { bf.Vx[(nb + T) * n + lane] = Vxp[lane]; bf.g[(nb + T) * n + lane] = gv[lane]; sV[lane * LD + (n ^ bw_swz(lane))] = Vxp[lane]; }
+      load_F(T - 1);
+      load_Lxx(T - 1);
       load_L(T - 1, pre, pre_fs);
       __syncwarp();
       store_L(pre, pre_fs);
     }
     for (int t = T - 1; t >= 0; --t) {
-      cp_async_wait<0>();
       __syncwarp();
-      double pre[S::PREF], pre_fs = 0.0;
-      if (t > 0) load_L(t - 1, pre, pre_fs);
-      // Lxx of this node: HBM -> accumulator fragments (row 8 i + fr, columns 8 j + 2 fc, +1); in flight during the
-      // first two products
-      // (they are the top-left tiles of the packed accumulator q of [[Qxx, Qxu], [Qux, Quu]]; upper tiles only)
+      EMPC_BW_MARK(0);
+      // packed accumulator q of [[Qxx, Qxu], [Qux, Quu]] (upper tiles only): its top-left tiles start from Lxx
       double q[S::PT][S::PT][2];
-      {
-        const double* lg = bf.tiles + (nb + t) * D::TILE + D::oLxx;
 #pragma unroll
-        for (int i = 0; i < S::PT; ++i)
+      for (int i = 0; i < S::PT; ++i)
 #pragma unroll
-          for (int j = i; j < S::PT; ++j) {
-            const int row = 8 * i + fr, col = 8 * j + 2 * fc;
-            double2 v = make_double2(0.0, 0.0);
-            if (row < n && col < n) v = *reinterpret_cast<const double2*>(lg + row * n + col);
-            q[i][j][0] = v.x; q[i][j][1] = v.y;
-          }
-      }
-      // ---- F^T V = [FxTV ; FuTV]  (one k-loop over the packed operand) ----
-      {
-        double ftv[S::PT][S::NT][2];
+        for (int j = i; j < S::PT; ++j) {
+          if (j < S::NT) { q[i][j][0] = qn[i][j][0]; q[i][j][1] = qn[i][j][1]; }
+          else { q[i][j][0] = 0.0; q[i][j][1] = 0.0; }
+        }
+      // ---- F^T [V | Vx'] = [FxTV ; FuTV | Fx^T Vx' ; Fu^T Vx'].  Column n of the product is the Qx / Qu update (each
+      // entry owned by one lane); it is not part of F^T V and is stored as zero. ----
+#pragma unroll
+      for (int hf = 0; hf < S::HALVES; ++hf) {
+        double ftv[S::IH][S::NTV][2];
         acc_zero(ftv);
 #pragma unroll
         for (int ks = 0; ks < S::KN; ++ks) {
-          double fa[S::PT], vv[S::NT];
+          double vv[S::NTV];
 #pragma unroll
-          for (int i = 0; i < S::PT; ++i) fa[i] = sF[(4 * ks + fc) * LDF + 8 * i + fr];
+          for (int j = 0; j < S::NTV; ++j) vv[j] = sV[(4 * ks + fc) * LD + 8 * j + frs];
 #pragma unroll
-          for (int i = 0; i < S::NT; ++i) vv[i] = sV[(4 * ks + fc) * LDB + 8 * i + fr];
+          for (int ii = 0; ii < S::IH; ++ii)
+            if (hf * S::IH + ii < S::PT) {
 #pragma unroll
-          for (int i = 0; i < S::PT; ++i)
-#pragma unroll
-            for (int j = 0; j < S::NT; ++j) dmma884(ftv[i][j][0], ftv[i][j][1], fa[i], vv[j]);
-        }
-        acc_store(ftv, sFTV, LDA, LDA, fr, fc);
-      }
-      // Qx += Fx^T Vx' ; Qu += Fu^T Vx'   (lane = column of the packed operand; three interleaved partial sums)
-#pragma unroll
-      for (int c0 = 0; c0 < PW; c0 += 32) {
-        const int c = c0 + lane;
-        const int cc = c < PW ? c : 0;
-        double s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-        for (int l = 0; l + 2 < n; l += 3) {
-          s0 += sF[l * LDF + cc] * Vxp[l]; s1 += sF[(l + 1) * LDF + cc] * Vxp[l + 1]; s2 += sF[(l + 2) * LDF + cc] * Vxp[l + 2];
+              for (int j = 0; j < S::NTV; ++j) dmma884(ftv[ii][j][0], ftv[ii][j][1], f[ks][hf * S::IH + ii], vv[j]);
+            }
         }
 #pragma unroll
-        for (int l = n - n % 3; l < n; ++l) s0 += sF[l * LDF + cc] * Vxp[l];
-        const double sacc = (s0 + s1) + s2;
-        if (c < n) Qx[c] += sacc;
-        else if (c < PW) Qu[c - n] += sacc;
+        for (int ii = 0; ii < S::IH; ++ii)
+          if (hf * S::IH + ii < S::PT) {
+            const int row = 8 * (hf * S::IH + ii) + fr;
+            if (fc == FCV) {
+              const double v = ftv[ii][JV][0];
+              if (row < n) Qx[row] += v;
+              else if (row < PW) Qu[row - n] += v;
+              ftv[ii][JV][0] = 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < S::NT; ++j) *reinterpret_cast<double2*>(sFTV + row * LD + 8 * j + c2s) = make_double2(ftv[ii][j][0], ftv[ii][j][1]);
+          }
       }
       __syncwarp();
+      EMPC_BW_MARK(1);
       // ---- [[Qxx, Qxu], [., Quu]] = [[Lxx, 0], [0, Luu + ureg I]] + (F^T V) F, upper tiles of the packed symmetric matrix.
-      // Qxx (the top-left tiles) stays in registers until Qxu K has been subtracted from it; Qxu and Quu go to shared memory. ----
+      // Qxx (the top-left tiles) stays in registers until Qxu K has been subtracted from it; Qux and Quu go to shared memory. ----
       {
 #pragma unroll
         for (int i = 0; i < S::PT; ++i)
@@ -325,15 +328,14 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
             }
 #pragma unroll
         for (int ks = 0; ks < S::KN; ++ks) {
-          double fa[S::PT], fb[S::PT];
+          double fa[S::PT];
 #pragma unroll
-          for (int i = 0; i < S::PT; ++i) { fa[i] = sFTV[(8 * i + fr) * LDA + 4 * ks + fc]; fb[i] = sF[(4 * ks + fc) * LDF + 8 * i + fr]; }
+          for (int i = 0; i < S::PT; ++i) fa[i] = sFTV[(8 * i + fr) * LD + ((4 * ks + fc) ^ swr)];
 #pragma unroll
           for (int i = 0; i < S::PT; ++i)
 #pragma unroll
-            for (int j = i; j < S::PT; ++j) dmma884(q[i][j][0], q[i][j][1], fa[i], fb[j]);
+            for (int j = i; j < S::PT; ++j) dmma884(q[i][j][0], q[i][j][1], fa[i], f[ks][j]);
         }
-        __syncwarp();  // every lane is done reading F^T V before the Quu factor (same storage) is written further down
 #pragma unroll
         for (int i = 0; i < S::PT; ++i)
 #pragma unroll
@@ -342,40 +344,47 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
             for (int h = 0; h < 2; ++h) {
               const int row = 8 * i + fr, col = 8 * j + 2 * fc + h;
               if (col >= n && col < PW) {
-                if (row < n) sQxu[row * LDQ + (col - n)] = q[i][j][h];
+                const int cu = col - n;
+                if (row < n) sQux[cu * LD + (row ^ bw_swz(cu))] = q[i][j][h];
                 else if (row < PW) {
-                  sQuu[(row - n) * LDQ + (col - n)] = q[i][j][h];
-                  if (i != j) sQuu[(col - n) * LDQ + (row - n)] = q[i][j][h];  // the lower tiles are not computed: mirror
+                  sQuu[(row - n) * LM + cu] = q[i][j][h];
+                  if (i != j) sQuu[cu * LM + (row - n)] = q[i][j][h];  // the lower tiles are not computed: mirror
                 }
               }
             }
       }
       __syncwarp();
-      // Fx, Fu of this node are dead: start fetching the next node's while Quu is factorised
-      if (t > 0) fetch_F(t - 1);
-      // ---- Cholesky of Quu (lane = row, left-looking: the reference LLT's subtraction order) ----
+      EMPC_BW_MARK(2);
+      // Fx, Fu of this node are dead: the next node's fragments travel HBM -> registers while Quu is factorised
+      if (t > 0) { load_F(t - 1); load_Lxx(t - 1); load_L(t - 1, pre, pre_fs); }
+      // ---- Cholesky of Quu, right-looking in registers: lane i holds row i; per pivot the diagonal entry and the scaled
+      // column travel by shuffles, so the dependent chain of a pivot is shuffle -> rsqrt -> multiply -> shuffle -> FMA (an
+      // FP64 operation has ~20 cycles of latency on B200: the left-looking form with its dot-product chains through shared
+      // memory cost ~50 % more per pivot).  L goes to shared memory row-wise and column-wise for the substitutions. ----
       int bad = 0;
       {
         const int i = lane < m ? lane : m - 1;
-        double row[m];
+        double a[LM];
 #pragma unroll
-        for (int k = 0; k < m; ++k) row[k] = sQuu[i * LDQ + k];
+        for (int k = 0; k < LM; k += 2) { const double2 v = *reinterpret_cast<const double2*>(sQuu + i * LM + k); a[k] = v.x; a[k + 1] = v.y; }
 #pragma unroll
         for (int j = 0; j < m; ++j) {
-          double d = sQuu[j * LDQ + j];
-#pragma unroll
-          for (int k = 0; k < j; ++k) { const double ljk = sL[j * m + k]; d -= ljk * ljk; }
+          const double d = __shfl_sync(0xffffffffu, a[j], j);
           if (!(d > 0.0)) bad = 1;
-          const double dinv = rsqrt_nr(d);
-          double sij = row[j];
+          const double dinv = rsqrt_h(d);
+          const double lij = (i == j) ? d * dinv : a[j] * dinv;
+          a[j] = lij;
 #pragma unroll
-          for (int k = 0; k < j; ++k) sij -= row[k] * sL[j * m + k];
-          sij = (i == j) ? d * dinv : sij * dinv;
-          row[j] = sij;
-          if (lane < m && i >= j) sL[i * m + j] = sij;
+          for (int c = j + 1; c < m; ++c) { const double lcj = __shfl_sync(0xffffffffu, lij, c); a[c] = fma(-lij, lcj, a[c]); }
+          if (lane < m) sLT[j * LM + i] = lij;  // column j of L = row j of L^T (entries i < j are never read)
           if (lane == j) sLinv[j] = dinv;
-          __syncwarp();
         }
+        if (lane < m) {
+#pragma unroll
+          for (int k = 0; k < LM; k += 2) *reinterpret_cast<double2*>(sL + i * LM + k) = make_double2(a[k], a[k + 1]);  // (entries k > i are never read)
+        }
+        __syncwarp();
+      EMPC_BW_MARK(3);
       }
       if (bad) { failed = 1; break; }  // uniform: every lane evaluates every pivot
       // ---- gains: K = Quu^-1 Qxu^T (one right-hand side per lane), k = Quu^-1 Qu ----
@@ -383,47 +392,63 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
         double rhs[m];
         if (c < n) {
 #pragma unroll
-          for (int i = 0; i < m; ++i) rhs[i] = sQxu[c * LDQ + i];
+          for (int i = 0; i < m; ++i) rhs[i] = sQux[i * LD + (c ^ bw_swz(i))];
         } else {
 #pragma unroll
           for (int i = 0; i < m; ++i) rhs[i] = Qu[i];
         }
-        // column-oriented substitution: entry i receives its subtractions in the same order (k ascending / descending)
-        // as the row-oriented reference loops, but the dependent chain is one multiply + one FMA per column
+        double linv[LM];
+#pragma unroll
+        for (int k = 0; k < LM; k += 2) { const double2 v = *reinterpret_cast<const double2*>(sLinv + k); linv[k] = v.x; linv[k + 1] = v.y; }
+        // column-oriented substitutions: as soon as an entry is final it is subtracted from all the others, so the
+        // dependent chain is one multiply + one FMA per column; column kk of L is row kk of L^T (16-byte broadcasts)
 #pragma unroll
         for (int kk = 0; kk < m; ++kk) {
-          rhs[kk] *= sLinv[kk];
+          rhs[kk] *= linv[kk];
 #pragma unroll
-          for (int i = kk + 1; i < m; ++i) rhs[i] -= sL[i * m + kk] * rhs[kk];
+          for (int i = (kk + 1) & ~1; i < m; i += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(sLT + kk * LM + i);
+            if (i > kk) rhs[i] -= v.x * rhs[kk];
+            if (i + 1 < m) rhs[i + 1] -= v.y * rhs[kk];
+          }
         }
 #pragma unroll
         for (int kk = m - 1; kk >= 0; --kk) {
-          rhs[kk] *= sLinv[kk];
+          rhs[kk] *= linv[kk];
 #pragma unroll
-          for (int i = kk - 1; i >= 0; --i) rhs[i] -= sL[kk * m + i] * rhs[kk];
+          for (int i = 0; i < kk; i += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(sL + kk * LM + i);
+            rhs[i] -= v.x * rhs[kk];
+            if (i + 1 < kk) rhs[i + 1] -= v.y * rhs[kk];
+          }
         }
         if (c < n) {
 #pragma unroll
-          for (int i = 0; i < m; ++i) sK[i * LDB + c] = rhs[i];
+          for (int i = 0; i < m; ++i) sK[i * LD + (c ^ bw_swz(i))] = rhs[i];
         } else {
 #pragma unroll
           for (int i = 0; i < m; ++i) kv[i] = rhs[i];
         }
       }
       __syncwarp();
+      EMPC_BW_MARK(4);
       if (lane < m) {  // Quuk = Quu k
-        double s = 0;
+        double s[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int j = 0; j < m; ++j) s += sQuu[lane * LDQ + j] * kv[j];
-        Quuk[lane] = s;
+        for (int j = 0; j < m; ++j) s[j % 3] = fma(sQuu[lane * LM + j], kv[j], s[j % 3]);
+        const double quuk = (s[0] + s[1]) + s[2];
+        Quuk[lane] = quuk;
+        tmpv[lane] = quuk - 2.0 * Qu[lane];  // w = Quu k - 2 Qu
       }
       __syncwarp();
-      // Vx = Qx + K^T Quuk - 2 K^T Qu
+      // Vx = Qx + K^T Quuk - 2 K^T Qu = Qx + K^T (Quuk - 2 Qu)
+      double vx_q = 0.0;
+      const double* wv = tmpv;
       if (lane < n) {
-        double s1 = 0, s2 = 0;
+        double s1[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int j = 0; j < m; ++j) { const double kji = sK[j * LDB + lane]; s1 += kji * Quuk[j]; s2 += kji * Qu[j]; }
-        tmpv[lane] = Qx[lane] + s1 - 2 * s2;
+        for (int j = 0; j < m; ++j) s1[j % 3] = fma(sK[j * LD + ((j & 2) ? lane_sw : lane)], wv[j], s1[j % 3]);
+        vx_q = Qx[lane] + ((s1[0] + s1[1]) + s1[2]);
       }
       // ---- Vxx = sym(Qxx - Qxu K) + xreg I, all in the accumulator registers.  Qxx and Qxu K are symmetric up to
       // rounding, so only the upper tiles (j >= i) are computed: diagonal tiles are averaged with their own transpose
@@ -433,7 +458,7 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
       for (int ks = 0; ks < S::KM; ++ks) {
         double a[S::NT], bq[S::NT];
 #pragma unroll
-        for (int i = 0; i < S::NT; ++i) { a[i] = -sQxu[(8 * i + fr) * LDQ + 4 * ks + fc]; bq[i] = sK[(4 * ks + fc) * LDB + 8 * i + fr]; }
+        for (int i = 0; i < S::NT; ++i) { a[i] = -sQux[(4 * ks + fc) * LD + 8 * i + frs]; bq[i] = sK[(4 * ks + fc) * LD + 8 * i + frs]; }
 #pragma unroll
         for (int i = 0; i < S::NT; ++i)
 #pragma unroll
@@ -471,52 +496,66 @@ __global__ void __launch_bounds__(32, EMPC_BW_WARPS_PER_SM) backward_kernel(Buff
               vsym[j][i][1] = (rowT < n && colT + 1 < n) ? t1 : 0.0;
             }
           }
-        acc_store(vsym, sV, LDB, LDB, fr, fc);
+#pragma unroll
+        for (int i = 0; i < S::NT; ++i)
+#pragma unroll
+          for (int j = 0; j < S::NT; ++j) *reinterpret_cast<double2*>(sV + (8 * i + fr) * LD + 8 * j + c2s) = make_double2(vsym[i][j][0], vsym[i][j][1]);
       }
       __syncwarp();
+      EMPC_BW_MARK(5);
       if (lane < n) {
         double s0 = 0, s1 = 0, s2 = 0;  // row `lane` of the symmetric V read as a column: conflict-free
 #pragma unroll
         for (int j = 0; j + 2 < n; j += 3) {
-          s0 += sV[j * LDB + lane] * fsv[j]; s1 += sV[(j + 1) * LDB + lane] * fsv[j + 1]; s2 += sV[(j + 2) * LDB + lane] * fsv[j + 2];
+          s0 += sV[j * LD + ((j & 2) ? lane_sw : lane)] * fsv[j];
+          s1 += sV[(j + 1) * LD + (((j + 1) & 2) ? lane_sw : lane)] * fsv[j + 1];
+          s2 += sV[(j + 2) * LD + (((j + 2) & 2) ? lane_sw : lane)] * fsv[j + 2];
         }
 #pragma unroll
-        for (int j = n - n % 3; j < n; ++j) s0 += sV[j * LDB + lane] * fsv[j];
+        for (int j = n - n % 3; j < n; ++j) s0 += sV[j * LD + ((j & 2) ? lane_sw : lane)] * fsv[j];
         const double s = (s0 + s1) + s2;
         gv[lane] = s;
-        const double vx = feasible ? tmpv[lane] : (tmpv[lane] + s);
+        const double vx = feasible ? vx_q : (vx_q + s);
         if (raise_if_nan_abs(vx)) bad = 1;  // raiseIfNaN(Vx.lpNorm<Infinity>())
         Vxp[lane] = vx;
+        sV[lane * LD + (n ^ bw_swz(lane))] = vx;  // column n of the V operand of the next node (the V store above left zero there)
       }
       bad = __any_sync(0xffffffffu, bad);
       if (bad) { failed = 1; break; }
       __syncwarp();
+      EMPC_BW_MARK(6);
       // outputs
       {
         double* Kg = bf.K + ((size_t)b * T + t) * m * n;
         for (int e2 = lane; e2 < m * n / 2; e2 += 32) {
           const int e = 2 * e2, i = e / n, j = e - i * n;  // n even: a pair never straddles rows
-          reinterpret_cast<double2*>(Kg)[e2] = *reinterpret_cast<const double2*>(sK + i * LDB + j);
+          reinterpret_cast<double2*>(Kg)[e2] = *reinterpret_cast<const double2*>(sK + i * LD + (j ^ bw_swz(i)));
         }
         double* kg = bf.k + ((size_t)b * T + t) * m;
         if (lane < m) kg[lane] = kv[lane];
         if (lane < n) { bf.Vx[(nb + t) * n + lane] = Vxp[lane]; bf.g[(nb + t) * n + lane] = gv[lane]; }
-        {  // five ordered dot products on lanes 24..28: same unrolled, predicated code for all of them (loads hoisted)
-          const int w = lane & 7;
-          const double* pa = (w == 0) ? Qu : (w == 1) ? kv : (w == 2) ? Vxp : (w == 3) ? fsv : Qu;
-          const double* pb = (w == 0) ? kv : (w == 1) ? Quuk : (w == 2) ? fsv : (w == 3) ? gv : Qu;
-          const int cnt = (w == 2 || w == 3) ? n : m;
-          double sacc = 0;
+        {
+          // five dot products as ONE 8x8 tensor-core product: row w of A and column w of B are the two vectors of
+          // product w (Qu.k, k.Quuk, Vx.fs, fs.(Vxx fs), Qu.Qu), KN k-steps over the zero-padded vector slots; the
+          // result is the diagonal: entry (w, w) sits in lane 4 w + (w >> 1), slot w & 1.  All lanes take part, nothing
+          // diverges, and the dependent chain is KN DMMAs instead of n FMAs on five lanes.
+          double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-          for (int i = 0; i < n; ++i) { const double av = (i < cnt) ? pa[i] : 0.0, bv = (i < cnt) ? pb[i] : 0.0; sacc += av * bv; }
-          if (lane >= 24 && w < 4) bf.nodesc[(nb + t) * 4 + w] = sacc;
-          if (lane == 28) bf.qu2[nb + t] = sacc;  // ||Qu_t||^2 (upstream stoppingCriteria)
+          for (int ks = 0; ks < S::KN; ++ks) {
+            const double av = (fr < 5) ? dot_a[4 * ks + fc] : 0.0, bv = (fr < 5) ? dot_b[4 * ks + fc] : 0.0;
+            dmma884(c0, c1, av, bv);
+          }
+          if (fr < 5 && fc == (fr >> 1)) {
+            const double v = (fr & 1) ? c1 : c0;
+            if (fr < 4) bf.nodesc[(nb + t) * 4 + fr] = v;
+            else bf.qu2[nb + t] = v;  // ||Qu_t||^2 (upstream stoppingCriteria)
+          }
         }
       }
       __syncwarp();
+      EMPC_BW_MARK(7);
       if (t > 0) store_L(pre, pre_fs);
     }
-    cp_async_wait<0>();
     __syncwarp();
     if (!failed || P.force) break;
     // computeDirection threw: recalcDiff = false; increaseRegularization(); give up at reg_max (src/sbfddp.cpp:245-253)

@@ -1006,6 +1006,14 @@ int empc_phase_backward(empc_solver_t* h, double xreg, int32_t is_feasible, int3
   }
   return EMPC_OK;
 }
+#ifdef EMPC_BW_PROFILE
+// diagnostic builds only (scripts/diag/backward_phases.py): clock64() cycles per phase of backward_kernel, block 0
+int empc_debug_backward_profile(unsigned long long* out16, int reset) {
+  if (out16) CK(cudaMemcpyFromSymbol(out16, g_bw_prof, sizeof(unsigned long long) * 16));
+  if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_bw_prof, z, sizeof(z))); }
+  return EMPC_OK;
+}
+#endif
 int empc_phase_rollout(empc_solver_t* h, double smooth, int32_t is_feasible, int32_t ddp) {
   if (!h) return fail(EMPC_ERR_INVALID, "null");
   CK(cudaSetDevice(h->device));

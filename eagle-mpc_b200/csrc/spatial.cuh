@@ -45,6 +45,15 @@ EMPC_DI double rsqrt_nr(double x) {
   r = r * fma(-h * r, r, 1.5);
   return r;
 }
+// ... with one third-order (Halley) step instead of two Newton steps: r (1 + e/2 + 3 e^2 / 8), e = 1 - x r^2.  The seed's
+// 2^-22 gives e^3 ~ 2^-64; four dependent FP64 operations instead of six (the Cholesky pivots of the Riccati sweep sit on
+// the critical path of every node, and an FP64 operation has ~20 cycles of latency on B200).
+EMPC_DI double rsqrt_h(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-(x * r), r, 1.0);
+  return fma(r * e, fma(e, 0.375, 0.5), r);
+}
 // sqrt(x) for x >= 0 (0 -> 0, negative -> NaN like sqrt)
 EMPC_DI double sqrt_nr(double x) {
   const double r = rsqrt_nr(x);
