@@ -47,12 +47,14 @@ struct BwCfg {
   static_assert(8 * NTV <= LD && KNP <= LD && NP <= LD, "operand wider than the leading dimension");
   // packed operand F = [Fx | Fu] (n x (n + m))
   static constexpr int PW = n + m, PT = (PW + 7) / 8, PP = 8 * PT;
-  static constexpr int ROWS_V = (KNP > NP ? KNP : NP);
+  static constexpr int ROWS_V = KNP;                             // rows of V read as B fragments (stores beyond are masked)
   static constexpr int oV = 0;                                   // ROWS_V x LD    [Vxx' | Vx'] (Vxx' symmetric)
   // (Qxx never touches shared memory: Lxx is loaded from HBM straight into the accumulator fragments and
   //  Qxx - Qxu K is symmetrised in registers)
   static constexpr int oFTV = oV + ROWS_V * LD;                  // PP x LD        F^T V = [FxTV ; FuTV]
-  static constexpr int oQux = oFTV + PP * LD;                    // KMP x LD       Qux = Qxu^T, zero padded
+  // (F^T V keeps its PW live rows: the A fragments of the last tile row read up to 4 rows into the next array — finite
+  //  values that only reach accumulator rows that are never used)
+  static constexpr int oQux = oFTV + PW * LD;                    // KMP x LD       Qux = Qxu^T, zero padded
   static constexpr int oK = oQux + KMP * LD;                     // KMP x LD       gains K (m x n), zero padded
   static constexpr int LM = m + (m & 1);                         // row stride of Quu and of its Cholesky factor (even)
   static constexpr int oQuu = oK + KMP * LD;                     // m x LM         Quu
@@ -60,7 +62,8 @@ struct BwCfg {
   static constexpr int oVec = oL + 2 * m * LM + LM;
   // vectors: slots of NP + 2 doubles (zero beyond the vector's length: they are DMMA operands of the dot products at the
   // end of a node), skewed so that the same index of different vectors falls into different banks
-  static constexpr int SLOT = NP + 2;
+  static constexpr int SLOT = (KNP > n ? KNP : n) + 2;
+  static_assert(PP - PW <= KMP, "the over-read of F^T V must stay inside Qux");
   static constexpr int vQx = 0, vQu = SLOT, vVx = 2 * SLOT, vFs = 3 * SLOT, vG = 4 * SLOT, vKv = 5 * SLOT,
                        vQuuk = 6 * SLOT, vTmp = 7 * SLOT, vLuu = 8 * SLOT, VEC = 9 * SLOT;
   static constexpr int TOTAL0 = oVec + VEC;
@@ -73,12 +76,14 @@ struct BwCfg {
   static constexpr int PREF = (LBLK + 31) / 32;
   // resident warps (= OCPs) per SM; the register budget follows from it (65536 / (32 WARPS))
 #ifndef EMPC_BW_WARPS
-#define EMPC_BW_WARPS 8
+#define EMPC_BW_WARPS 12
 #endif
-  static constexpr int WARPS = EMPC_BW_WARPS;
-  // (registers are allocated per warp in units that round the per-thread count up to a multiple of 32 — measured:
-  //  144 registers gave 12 resident warps, 200 gave 9 — so the budget is the multiple of 32 below 65536 / (32 WARPS))
-  static constexpr int MAXREG = (65536 / (32 * WARPS)) / 32 * 32 > 255 ? 255 : (65536 / (32 * WARPS)) / 32 * 32;
+  static constexpr int WARPS = ((TOTAL * 8 + 1024) * EMPC_BW_WARPS <= 227 * 1024 && KN * PT <= 20) ? EMPC_BW_WARPS : 8;  // the wide platforms keep 8
+  // (a warp lives on one of the four sub-partitions and takes its registers from that sub-partition's 16384: WARPS / 4
+  //  warps per sub-partition leave 16384 / (WARPS / 4) / 32 registers per thread — 255 for 8 warps per SM, 168 for 12,
+  //  128 for 16; other values of WARPS only round down to one of these)
+  static constexpr int WPS = (WARPS + 3) / 4;
+  static constexpr int MAXREG = (16384 / WPS / 32) / 8 * 8 > 255 ? 255 : (16384 / WPS / 32) / 8 * 8;
   // tile rows of F^T V per pass: all at once when the registers allow it, otherwise in halves
   static constexpr int IH = (PT <= 3 || (MAXREG >= 200 && KN * PT <= 20)) ? PT : (PT + 1) / 2;
   static constexpr int HALVES = (PT + IH - 1) / IH;
@@ -309,7 +314,8 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
               ftv[ii][JV][0] = 0.0;
             }
 #pragma unroll
-            for (int j = 0; j < S::NT; ++j) *reinterpret_cast<double2*>(sFTV + row * LD + 8 * j + c2s) = make_double2(ftv[ii][j][0], ftv[ii][j][1]);
+            for (int j = 0; j < S::NT; ++j)
+              if (row < PW) *reinterpret_cast<double2*>(sFTV + row * LD + 8 * j + c2s) = make_double2(ftv[ii][j][0], ftv[ii][j][1]);
           }
       }
       __syncwarp();
@@ -499,7 +505,8 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
 #pragma unroll
         for (int i = 0; i < S::NT; ++i)
 #pragma unroll
-          for (int j = 0; j < S::NT; ++j) *reinterpret_cast<double2*>(sV + (8 * i + fr) * LD + 8 * j + c2s) = make_double2(vsym[i][j][0], vsym[i][j][1]);
+          for (int j = 0; j < S::NT; ++j)
+            if (8 * i + fr < S::ROWS_V) *reinterpret_cast<double2*>(sV + (8 * i + fr) * LD + 8 * j + c2s) = make_double2(vsym[i][j][0], vsym[i][j][1]);
       }
       __syncwarp();
       EMPC_BW_MARK(5);
