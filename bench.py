@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--no-config4", action="store_true", help="skip the strong-scaling leg (16384 hextilt_flying_arm_5 OCPs over all ranks)")
     ap.add_argument("--config4-batch", type=int, default=16384, help="OCPs of the strong-scaling leg, TOTAL over all ranks")
     ap.add_argument("--no-config5", action="store_true", help="skip the iris_px4 rail / weighted MPC horizon sweep (N = 1 only)")
+    ap.add_argument("--no-divergent", action="store_true", help="skip the divergent-batch leg (hexacopter370 hover, N = 1 only)")
     return ap.parse_args()
 
 
@@ -305,6 +306,38 @@ def config5_leg(args):
             "batch": B, "unit": UNIT, "timing": "CUDA events around each batched solve, 3 warm-ups, mean of 5", "cases": rows}
 
 
+def divergent_leg(args):
+    """A batch whose OCPs need very different numbers of iterations (hexacopter370 hover from noisy initial states: a few
+    iterations for some OCPs, 100+ crawling ones for others).  Every kernel masks finished OCPs, but the batch runs until its
+    slowest OCP is done, and the sequential kernels (Riccati sweep, rollouts) cost their per-OCP latency however few OCPs
+    are left: the leg reports the throughput, the straggler factor (batch-iterations x batch / OCP-iterations executed) and
+    how the batch-iterations split by the share of OCPs still active."""
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    tr, fp, wl, seed0, dt = load_problem("hexacopter370_hover")
+    B = 4096
+    x0 = wl.noisy_x0(fp.x0, B, seed0)
+    g = capi.BatchSolver(fp, B)
+    g.set_x0(x0); g.set_candidate(None, None, False)
+    g.enable_kernel_timing(False)
+    for _ in range(2):
+        g.reset(); g.solve()
+    ms, its, launches = 0.0, 0, 0
+    for _ in range(3):
+        g.reset(); g.solve()
+        ms += g.solve_stats()[0]; its += g.total_iterations(); launches += g.launch_stats()[0]
+    it = g.iters() + 1
+    batch_iters = (launches / 3 - 2) / 8
+    g.close()
+    alive = [(it > k).mean() for k in range(int(it.max()))]   # share of OCPs still iterating at batch-iteration k
+    return {"workload": "hexacopter370_hover, B = 4096, x0 = YAML state + 0.05*U(-1,1), seeds 1000+b", "T": fp.T, "batch": B,
+            "value": its / (ms * 1e-3), "unit": UNIT, "device_ms_per_solve": ms / 3,
+            "iterations_per_ocp": {"min": int(it.min()), "median": float(np.median(it)), "mean": float(it.mean()), "p95": float(np.percentile(it, 95)), "max": int(it.max())},
+            "batch_iterations": batch_iters, "straggler_factor": batch_iters * B / (its / 3),
+            "batch_iterations_by_active_share": {">50%": int(sum(a > 0.5 for a in alive)), "5-50%": int(sum(0.05 < a <= 0.5 for a in alive)),
+                                                 "<5%": int(sum(a <= 0.05 for a in alive))},
+            "ms_per_batch_iteration": ms / 3 / batch_iters}
+
+
 def run_reference(args):
     """CPU arm: the in-repo restatement (oracle/) on all host threads; each step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
@@ -518,6 +551,9 @@ def main():
         if world == 1 and not args.no_config5:
             solver.close()
             out["config5"] = config5_leg(args)
+        if world == 1 and not args.no_divergent:
+            solver.close()
+            out["divergent_batch"] = divergent_leg(args)
     solver.close()
     if not args.no_config4:
         c4 = config4_leg(args, torch, dist, world, rank, local_rank, barrier)

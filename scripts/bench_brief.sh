@@ -1,6 +1,6 @@
 #!/bin/bash
 # prints value, ms/step and the per-kernel split of one bench run
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-mpc --no-config4 --no-config5 "$@" 2>&1 | tail -1 | python -c "
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-mpc --no-config4 --no-config5 --no-divergent "$@" 2>&1 | tail -1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
