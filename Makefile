@@ -11,7 +11,10 @@ HOST_SRC := $(PKG)/host/params.cpp $(PKG)/host/urdf.cpp $(PKG)/host/trajectory.c
 HOST_OBJ := $(HOST_SRC:.cpp=.o)
 CU_OBJ := $(PKG)/csrc/solver.o
 
-all: $(LIB) $(HOSTLIB) oracle
+PYEXT := $(PKG)/python/eagle_mpc/_eagle_mpc$(shell python3 -c "import sysconfig; print(sysconfig.get_config_var('EXT_SUFFIX'))")
+PYINC := $(shell python3 -c "import pybind11, sysconfig; print('-I' + pybind11.get_include() + ' -I' + sysconfig.get_paths()['include'])")
+
+all: $(LIB) $(HOSTLIB) $(PYEXT) oracle
 
 $(PKG)/csrc/solver.o: $(PKG)/csrc/solver.cu $(wildcard $(PKG)/csrc/*.cuh) include/empc_b200.h
 	$(NVCC) $(CUFLAGS) -c -o $@ $<
@@ -27,10 +30,14 @@ $(HOSTLIB): $(HOST_OBJ)
 	mkdir -p $(PKG)/lib
 	g++ -shared -o $@ $(HOST_OBJ) -ldl
 
+# Python front-end with the reference's names (pybind11 over the host mirror; binds the CUDA library at run time)
+$(PYEXT): $(PKG)/host/pybind.cpp $(HOST_OBJ)
+	g++ $(CXXFLAGS) -shared -fvisibility=hidden $(PYINC) -o $@ $(PKG)/host/pybind.cpp $(filter-out $(PKG)/host/host_capi.o,$(HOST_OBJ)) -ldl
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(PKG)/csrc/*.o $(PKG)/host/*.o $(LIB) $(HOSTLIB)
+	rm -f $(PKG)/csrc/*.o $(PKG)/host/*.o $(LIB) $(HOSTLIB) $(PYEXT)
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean
