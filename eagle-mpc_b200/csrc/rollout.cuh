@@ -171,10 +171,10 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
           us_try[(size_t)t * NU + i] = u[i];
         }
         node_dyn<D, true>(M, smooth, xt, u, xn);
-        bool bad = false;
+        int worst = -1;  // raiseIfNaN(xnext.lpNorm<Infinity>()): integer test on the high words (node.cuh: raise_bits)
 #pragma unroll
-        for (int i = 0; i < NX; ++i) bad |= raise_if_nan_abs(xn[i]);  // raiseIfNaN(xnext.lpNorm<Infinity>())
-        if (bad) { ok = 0; active = false; }  // "forward_error": this step length is skipped by decide_kernel
+        for (int i = 0; i < NX; ++i) worst = max(worst, raise_bits(xn[i]));
+        if (worst >= 0) { ok = 0; active = false; }  // "forward_error": this step length is skipped by decide_kernel
       }
     }
     if (__ballot_sync(0xffffffffu, active) == 0) break;  // every trial of this warp hit a forward error

@@ -69,6 +69,19 @@ EMPC_DI double rcp_nr(double x) {
   return r;
 }
 
+// inverse of a symmetric positive definite 3x3 matrix by cofactors (row-major 9, only the upper entries of A are read;
+// the result is written symmetric).  Five dependent FP64 operations plus one reciprocal instead of a three-pivot
+// factorisation: used for the free-flyer's 6x6 articulated inertia, split in 3x3 blocks (node.cuh: aba_dynamics).
+EMPC_DI void inv3_sym(const double* A, double* Ai) {
+  const double a00 = A[0], a01 = A[1], a02 = A[2], a11 = A[4], a12 = A[5], a22 = A[8];
+  const double c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+  const double c11 = a00 * a22 - a02 * a02, c12 = a01 * a02 - a00 * a12, c22 = a00 * a11 - a01 * a01;
+  const double r = rcp_nr(a00 * c00 + a01 * c01 + a02 * c02);
+  Ai[0] = c00 * r; Ai[1] = c01 * r; Ai[2] = c02 * r;
+  Ai[3] = Ai[1];   Ai[4] = c11 * r; Ai[5] = c12 * r;
+  Ai[6] = Ai[2];   Ai[7] = Ai[5];   Ai[8] = c22 * r;
+}
+
 EMPC_DI void cross3(const double* a, const double* b, double* o) {
   const double x = a[1] * b[2] - a[2] * b[1];
   const double y = a[2] * b[0] - a[0] * b[2];
