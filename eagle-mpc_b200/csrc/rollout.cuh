@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
         double u[NU];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
+          // (one accumulator per row: splitting the row products into partial sums shortens the dependent chain but costs
+          //  registers this kernel does not have — measured slower, B = 1: 0.48 vs 0.42 ms per two rollouts)
           double kd = 0;
 #pragma unroll
           for (int jj = 0; jj < NDX; ++jj) kd += in[S::oK + i * NDX + jj] * dx[jj];

@@ -55,8 +55,11 @@ EMPC_DI double rsqrt_h(double x) {
   return fma(r * e, fma(e, 0.375, 0.5), r);
 }
 // sqrt(x) for x >= 0 (0 -> 0, negative -> NaN like sqrt)
+#ifndef EMPC_SQRT_HALLEY
+#define EMPC_SQRT_HALLEY 1
+#endif
 EMPC_DI double sqrt_nr(double x) {
-  const double r = rsqrt_nr(x);
+  const double r = EMPC_SQRT_HALLEY ? rsqrt_h(x) : rsqrt_nr(x);
   double s = x * r;
   s = fma(fma(-s, s, x), 0.5 * r, s);
   return x == 0.0 ? 0.0 : s;

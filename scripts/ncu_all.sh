@@ -4,7 +4,7 @@
 tag=${1:-all}
 mkdir -p gpurun_out
 ARGS="--steps 1 --warmup 0 --no-cpu-baseline --no-mpc --no-config4 --no-config5 --no-divergent"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'node_calc|node_cost|node_diff|backward|rollout_kernel|decide' -s 12 -c 6 -f -o gpurun_out/prof_$tag \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'node_calc|node_cost|node_diff|backward|rollout_kernel|decide' -s 16 -c 8 -f -o gpurun_out/prof_$tag \
   python bench.py $ARGS > gpurun_out/ncu_$tag.log 2>&1
 echo "ncu full rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
