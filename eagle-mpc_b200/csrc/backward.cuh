@@ -52,8 +52,7 @@ struct BwCfg {
   // (Qxx never touches shared memory: Lxx is loaded from HBM straight into the accumulator fragments and
   //  Qxx - Qxu K is symmetrised in registers)
   static constexpr int oFTV = oV + ROWS_V * LD;                  // PP x LD        F^T V = [FxTV ; FuTV]
-  // (F^T V keeps its PW live rows: the A fragments of the last tile row read up to 4 rows into the next array — finite
-  //  values that only reach accumulator rows that are never used)
+  // (F^T V keeps its PW live rows; the A-fragment loads of the last tile row clamp their row index)
   static constexpr int oQux = oFTV + PW * LD;                    // KMP x LD       Qux = Qxu^T, zero padded
   static constexpr int oK = oQux + KMP * LD;                     // KMP x LD       gains K (m x n), zero padded
   static constexpr int LM = m + (m & 1);                         // row stride of Quu and of its Cholesky factor (even)
@@ -63,7 +62,6 @@ struct BwCfg {
   // vectors: slots of NP + 2 doubles (zero beyond the vector's length: they are DMMA operands of the dot products at the
   // end of a node), skewed so that the same index of different vectors falls into different banks
   static constexpr int SLOT = (KNP > n ? KNP : n) + 2;
-  static_assert(PP - PW <= KMP, "the over-read of F^T V must stay inside Qux");
   static constexpr int vQx = 0, vQu = SLOT, vVx = 2 * SLOT, vFs = 3 * SLOT, vG = 4 * SLOT, vKv = 5 * SLOT,
                        vQuuk = 6 * SLOT, vTmp = 7 * SLOT, vLuu = 8 * SLOT, VEC = 9 * SLOT;
   static constexpr int TOTAL0 = oVec + VEC;
@@ -336,7 +334,12 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
         for (int ks = 0; ks < S::KN; ++ks) {
           double fa[S::PT];
 #pragma unroll
-          for (int i = 0; i < S::PT; ++i) fa[i] = sFTV[(8 * i + fr) * LD + ((4 * ks + fc) ^ swr)];
+          for (int i = 0; i < S::PT; ++i) {
+            // F^T V keeps only its PW live rows: the lanes of the last tile row that fall beyond read row PW - 1 again
+            // (finite values that only reach accumulator rows nobody uses)
+            const int row = (8 * i + 7 < PW) ? 8 * i + fr : min(8 * i + fr, PW - 1);
+            fa[i] = sFTV[row * LD + ((4 * ks + fc) ^ bw_swz(row))];
+          }
 #pragma unroll
           for (int i = 0; i < S::PT; ++i)
 #pragma unroll

@@ -13,8 +13,10 @@ for na, nr in ((3, 6), (0, 4), (2, 6), (5, 6)):
     x0 = np.zeros((B, h.nx)); x0[:, 6] = 1
     x0[:, :3] = rng.uniform(-0.3, 0.3, size=(B, 3))
     g = capi.BatchSolver(h, B)
-    p = capi.default_params(); p.maxiter = 4
+    p = capi.default_params(); p.maxiter = 4; p.stop_criteria = 1
+    g.enable_iteration_log(16)
     g.set_params(p); g.set_x0(x0); g.set_candidate(None, None, False); g.solve()
+    assert len(g.iteration_log(0)) > 0
     g.phase_calc_diff(0.1); g.phase_backward(1e-6, False); g.phase_rollout(0.1, False, False)
     print("ok", na, nr, g.iters().tolist())
     # batched-MPC entry points (memory safety only: made-up schedules on the synthetic problem)

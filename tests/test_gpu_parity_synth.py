@@ -120,3 +120,63 @@ def test_full_solve(na, nr, T):
     for b in range(B):
         parity.check_ocp(("synth", na, b), h, x0[b], {k_: v[b] for k_, v in got.items()}, iters[b], feas[b],
                          keys=parity.KEYS + ("stop",), log=g.iteration_log(b))
+
+
+def test_diverging_rollout_is_a_forward_error():
+    """crocoddyl::raiseIfNaN trips on NaN, +-inf AND any value >= 1e30: a rollout whose states leave that range without ever
+    producing a NaN must be skipped like the reference's forward_error (src/sbfddp.cpp:265-267), and a finite but huge cost_try
+    likewise.  x0 carries a finite base velocity of 2e30: every step length fails at the first node, on both sides."""
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    h = synth.make_problem(seed=31, na=3, n_rotors=6, T=8, all_costs=False)
+    B = 3
+    x0 = np.zeros((B, h.nx)); x0[:, 6] = 1
+    x0[1, h.nq] = 2e30          # OCP 1: finite, but beyond the raiseIfNaN range
+    x0[2, h.nq + 1] = -3e30     # OCP 2: the same with a negative entry (the test is on the infinity norm)
+    xs = np.repeat(x0[:, None, :], h.T + 1, axis=1)
+    us = np.zeros((B, h.T, h.nu))
+    g = capi.BatchSolver(h, B)
+    g.set_x0(x0); g.set_candidate(xs, us, False)
+    g.phase_calc_diff(0.1)
+    g.phase_rollout(0.1, True, False)
+    for ai in (0, 3, 9):
+        _xt, _ut, _c, _dv, ok = g.trial(ai)
+        assert ok.tolist() == [1, 0, 0], (ai, ok)
+    for b in range(B):
+        o = ob.Oracle(h); o.set_x0(x0[b]); o.set_candidate(xs[b], us[b], False)
+        o.phase_calc_diff(0.1)
+        assert bool(o.phase_rollout(0.1, True, False, 0)) == (b == 0)
+
+
+def test_device_pointers_at_the_c_abi():
+    """empc_set_x0 / empc_set_candidate / empc_get_* take host or device memory (the NCCL data plane hands device buffers
+    straight to the handle): identical results either way."""
+    torch = pytest.importorskip("torch")
+    capi = importlib.import_module("eagle-mpc_b200.capi")
+    abi = importlib.import_module("eagle-mpc_b200.abi")
+    import ctypes as C
+    h = synth.make_problem(seed=23, na=3, n_rotors=6, T=20, all_costs=False)
+    B = 4
+    rng = np.random.default_rng(9)
+    x0 = np.zeros((B, h.nx)); x0[:, 6] = 1; x0[:, :3] = rng.uniform(-0.2, 0.2, size=(B, 3))
+    p = capi.default_params(); p.maxiter = 6
+    g = capi.BatchSolver(h, B); g.set_params(p)
+    g.set_x0(x0); g.set_candidate(None, None, False); g.solve()
+    xs_host, us_host = g.xs(), g.us()
+    g2 = capi.BatchSolver(h, B); g2.set_params(p)
+    x0_d = torch.from_numpy(x0).cuda()
+    g2.set_x0_ptr(x0_d.data_ptr())
+    g2.set_candidate(None, None, False)
+    g2.solve()
+    xs_d = torch.empty((B, h.T + 1, h.nx), dtype=torch.float64, device="cuda")
+    us_d = torch.empty((B, h.T, h.nu), dtype=torch.float64, device="cuda")
+    g2.get_into("xs", xs_d.data_ptr()); g2.get_into("us", us_d.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(xs_d.cpu().numpy(), xs_host) and np.array_equal(us_d.cpu().numpy(), us_host)
+    # a device-resident candidate
+    lib = capi.lib()
+    xs_c, us_c = torch.from_numpy(xs_host).cuda(), torch.from_numpy(us_host).cuda()
+    rc = lib.empc_set_candidate(g2.h, C.cast(xs_c.data_ptr(), abi.c_double_p), C.cast(us_c.data_ptr(), abi.c_double_p), 0)
+    assert rc == 0
+    g.set_candidate(xs_host, us_host, False)
+    g.solve(); g2.solve()
+    assert np.array_equal(g.xs(), g2.xs()) and np.array_equal(g.iters(), g2.iters())
