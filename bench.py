@@ -327,6 +327,19 @@ def divergent_leg(args):
         ms += g.solve_stats()[0]; its += g.total_iterations(); launches += g.launch_stats()[0]
     it = g.iters() + 1
     batch_iters = (launches / 3 - 2) / 8
+    # the same workload through empc_solve_stream: 4 x B jobs through the B slots, refilled on the device as OCPs finish
+    jobs = 4 * B
+    x0_jobs = wl.noisy_x0(fp.x0, jobs, seed0)
+    g.solve_stream(x0_jobs[:2 * B], want_trajectories=False)   # warm-up
+    out = g.solve_stream(x0_jobs, want_trajectories=True)
+    ms_stream = g.solve_stats()[0]; its_stream = g.total_iterations()
+    assert int((out["iters"][:B] + 1).sum()) == int(it.sum())   # the first B jobs are the plain batch's OCPs: same iteration counts
+    # ... and the uniform yardstick: every OCP cut at the same small maxiter, so that (nearly) all of them are active in every batch-iteration
+    pu = capi.default_params(); pu.maxiter = 6
+    g.set_params(pu); g.set_x0(x0); g.set_candidate(None, None, False)
+    g.reset(); g.solve()
+    g.reset(); g.solve()
+    ms_uni = g.solve_stats()[0]; its_uni = g.total_iterations()
     g.close()
     alive = [(it > k).mean() for k in range(int(it.max()))]   # share of OCPs still iterating at batch-iteration k
     return {"workload": "hexacopter370_hover, B = 4096, x0 = YAML state + 0.05*U(-1,1), seeds 1000+b", "T": fp.T, "batch": B,
@@ -335,7 +348,13 @@ def divergent_leg(args):
             "batch_iterations": batch_iters, "straggler_factor": batch_iters * B / (its / 3),
             "batch_iterations_by_active_share": {">50%": int(sum(a > 0.5 for a in alive)), "5-50%": int(sum(0.05 < a <= 0.5 for a in alive)),
                                                  "<5%": int(sum(a <= 0.05 for a in alive))},
-            "ms_per_batch_iteration": ms / 3 / batch_iters}
+            "ms_per_batch_iteration": ms / 3 / batch_iters,
+            "stream": {"what": "empc_solve_stream: %d jobs through the %d slots, refilled on the device as OCPs finish" % (jobs, B),
+                       "value": its_stream / (ms_stream * 1e-3), "unit": UNIT, "device_ms": ms_stream, "ocp_iterations": its_stream,
+                       "speedup_over_plain_batch": (its_stream / ms_stream) / (its / ms)},
+            "uniform_yardstick": {"what": "the same batch with every OCP cut at maxiter 6 per pass (all OCPs active in nearly every batch-iteration)",
+                                  "value": its_uni / (ms_uni * 1e-3), "unit": UNIT},
+            "per_iteration_cost_vs_uniform": {"plain_batch": (its_uni / ms_uni) / (its / ms), "stream": (its_uni / ms_uni) / (its_stream / ms_stream)}}
 
 
 def run_reference(args):

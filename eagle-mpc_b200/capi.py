@@ -59,6 +59,8 @@ def lib():
         L.empc_phase_calc_diff.argtypes = [C.c_void_p, C.c_double]
         L.empc_phase_backward.argtypes = [C.c_void_p, C.c_double, C.c_int32, abi.c_int32_p]
         L.empc_phase_rollout.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32]
+        L.empc_solve_stream.argtypes = [C.c_void_p, C.c_int32, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p,
+                                        abi.c_double_p, abi.c_double_p, abi.c_int32_p, abi.c_int32_p]
         L.empc_enable_iteration_log.argtypes = [C.c_void_p, C.c_int32]
         L.empc_get_iteration_log.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.IterRecord), C.c_int32, abi.c_int32_p]
         L.empc_get_trial.argtypes = [C.c_void_p, C.c_int32, abi.c_double_p, abi.c_double_p, abi.c_double_p,
@@ -187,6 +189,18 @@ class BatchSolver:
     # ---- hot path ----
     def solve(self):
         _ck(lib().empc_solve(self.h))
+
+    def solve_stream(self, x0_jobs, want_trajectories=True):
+        """solve len(x0_jobs) independent OCPs through this handle's slots (refilled as OCPs finish); results per job"""
+        x0 = np.ascontiguousarray(x0_jobs, dtype=np.float64).reshape(-1, self.nx)
+        J = x0.shape[0]
+        out = {"cost": np.zeros(J), "stop": np.zeros(J), "iters": np.zeros(J, dtype=np.int32), "feasible": np.zeros(J, dtype=np.int32)}
+        if want_trajectories:
+            out["xs"] = np.zeros((J, self.T + 1, self.nx)); out["us"] = np.zeros((J, self.T, self.nu)); out["us_squash"] = np.zeros((J, self.T, self.nu))
+        p = lambda k: abi.as_double_p(out[k]) if k in out else None  # noqa: E731
+        _ck(lib().empc_solve_stream(self.h, J, abi.as_double_p(x0), p("xs"), p("us"), p("us_squash"), p("cost"), p("stop"),
+                                    abi.as_int32_p(out["iters"]), abi.as_int32_p(out["feasible"])))
+        return out
 
     def reset(self):
         _ck(lib().empc_reset(self.h))

@@ -294,24 +294,101 @@ __global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams
   }
 }
 
-// state initialisation at the start of solve() (src/sbfddp.cpp:198-210)
-__global__ void init_state_kernel(Buffers bf, empc_solver_params_t P, int is_feasible_arg, int nx) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= bf.B) return;
-  OcpState st;
+// state of an OCP at the start of solve() (src/sbfddp.cpp:198-210)
+__device__ __forceinline__ void init_ocp_state(OcpState& st, const empc_solver_params_t& P, int is_feasible_arg, double cost_prev) {
   st.smooth = P.smooth_init; st.smooth_next = P.smooth_init;
   st.convergence = P.convergence_init; st.th_stop = P.convergence_init;
-  st.xreg = P.reg_init; st.cost = 0; st.cost_prev = bf.st[b].cost_prev; st.stop = 0; st.steplength = 1;
+  st.xreg = P.reg_init; st.cost = 0; st.cost_prev = cost_prev; st.stop = 0; st.steplength = 1;
   st.dg = st.dq = st.dg0 = st.dq0 = 0; st.gap_inf = 0; st.gap_l1 = 0;
   st.iter = 0; st.total_iters = 0; st.is_feasible = 0; st.was_feasible = 0; st.recalc = 1; st.bw_fail = 0;
   st.iters_out = 0; st.accepted = -1; st.pending = 0;
   st.qu2 = 0; st.d0_last = 0; st.d1_last = 0; st.log_count = 0; st.pad_ = 0;
-  (void)is_feasible_arg;  // solveFDDP(maxiter, false, ...) overrides the caller's flag (src/sbfddp.cpp:210,230)
+  // solveFDDP(maxiter, false, ...) overrides the caller's flag (src/sbfddp.cpp:210,230)
   if (P.convergence_init >= P.convergence_stop) st.phase = PHASE_FDDP;
   else { st.phase = is_feasible_arg ? PHASE_DONE : PHASE_DDP; st.is_feasible = is_feasible_arg; }
   if (st.phase == PHASE_DONE) st.iters_out = -1;
+}
+__global__ void init_state_kernel(Buffers bf, empc_solver_params_t P, int is_feasible_arg, int nx) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bf.B) return;
+  OcpState st;
+  init_ocp_state(st, P, is_feasible_arg, bf.st[b].cost_prev);
   bf.st[b] = st;
   for (int i = 0; i < nx; ++i) bf.xs_try0[(size_t)b * nx + i] = bf.x0[(size_t)b * nx + i];  // xs_try_[0] = x0 (:198)
+}
+
+// ---- streaming solve (empc_solve_stream): the handle's OCP slots are refilled from a queue of jobs between
+// batch-iterations, so a batch with very different iteration counts per OCP does not run at the pace of its slowest member.
+struct StreamBuffers {
+  int n_jobs;
+  const double* job_x0;   // n_jobs x nx
+  double* out_xs;         // n_jobs x (T+1) x nx, or nullptr
+  double* out_us;         // n_jobs x T x nu, or nullptr
+  double* out_us_squash;  // n_jobs x T x nu, or nullptr
+  double* out_cost; double* out_stop; int* out_iters; int* out_feasible;  // n_jobs
+  int* slot_job;          // per slot: job being solved, -1: none
+  int* queue_next;        // next job to hand out
+};
+// One block per slot.  start = 1: hand job b to slot b (the first `batch` jobs).  Otherwise: a slot whose OCP has finished
+// writes its result to the job's rows and takes the next job from the queue (x0 -> slot, zero candidate, fresh state:
+// exactly solve([], [], maxiter) of a new solver, src/sbfddp.cpp:192-210).
+template <class D>
+__global__ void __launch_bounds__(128) stream_refill_kernel(Buffers bf, StreamBuffers sb, empc_solver_params_t P, int start) {
+  constexpr int NX = D::NX, NU = D::NU;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int T = bf.T, T1 = T + 1;
+  __shared__ int s_job;
+  __shared__ double s_smooth;
+  int job = -1;
+  if (start) {
+    job = b < sb.n_jobs ? b : -1;
+  } else {
+    const int cur = sb.slot_job[b];
+    if (cur < 0) return;
+    if (tid == 0) { const OcpState st = bf.st[b]; s_job = (st.phase == PHASE_DONE) ? 1 : 0; s_smooth = st.smooth; }
+    __syncthreads();
+    if (!s_job) return;  // still solving
+    // ---- harvest ----
+    if (sb.out_xs) for (int i = tid; i < T1 * NX; i += blockDim.x) sb.out_xs[(size_t)cur * T1 * NX + i] = bf.xs[(size_t)b * T1 * NX + i];
+    if (sb.out_us) for (int i = tid; i < T * NU; i += blockDim.x) sb.out_us[(size_t)cur * T * NU + i] = bf.us[(size_t)b * T * NU + i];
+    if (sb.out_us_squash) {
+      const DevModel& M = *bf.model;
+      for (int t = tid; t < T; t += blockDim.x) {
+        double u[NU], s[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = bf.us[((size_t)b * T + t) * NU + i];
+        squash<D>(M, s_smooth, u, s);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) sb.out_us_squash[((size_t)cur * T + t) * NU + i] = s[i];
+      }
+    }
+    if (tid == 0) {
+      const OcpState st = bf.st[b];
+      sb.out_cost[cur] = st.cost; sb.out_stop[cur] = st.stop; sb.out_iters[cur] = st.iters_out; sb.out_feasible[cur] = st.is_feasible;
+      const int nxt = atomicAdd(sb.queue_next, 1);
+      s_job = nxt < sb.n_jobs ? nxt : -1;
+    }
+    __syncthreads();   // (also: every thread is done reading xs / us of the finished OCP)
+    job = s_job;
+  }
+  if (tid == 0) sb.slot_job[b] = job;
+  if (job < 0) {
+    if (start && tid == 0) { OcpState st; init_ocp_state(st, P, 0, 0.0); st.phase = PHASE_DONE; st.recalc = 0; bf.st[b] = st; }
+    return;
+  }
+  // ---- load the job: x0, xs[t] = state.zero(), us[t] = 0, fresh solver state ----
+  for (int i = tid; i < NX; i += blockDim.x) {
+    const double v = sb.job_x0[(size_t)job * NX + i];
+    const_cast<double*>(bf.x0)[(size_t)b * NX + i] = v; bf.xs_try0[(size_t)b * NX + i] = v;  // (x0 is read-only for every other kernel)
+  }
+  for (int i = tid; i < T1 * NX; i += blockDim.x) bf.xs[(size_t)b * T1 * NX + i] = ((i % NX) == 6) ? 1.0 : 0.0;
+  for (int i = tid; i < T * NU; i += blockDim.x) bf.us[(size_t)b * T * NU + i] = 0.0;
+  if (tid == 0) {
+    OcpState st;
+    init_ocp_state(st, P, 0, 0.0);
+    bf.st[b] = st;
+    if (!start && st.phase != PHASE_DONE) { atomicAdd(bf.n_active, 1); atomicAdd(bf.n_active + 1, 1); }
+  }
 }
 
 // fillSquashedOutputs (src/sbfddp.cpp:479-486): us_squash[t] = s(us[t]) with the smoothing of the last pass

@@ -63,6 +63,9 @@ struct empc_solver {
   WeightedScheduleDev wsched = {0, 0, nullptr, nullptr, 0, 0.0, 0.0, nullptr, nullptr, nullptr};
   int init_feasible = 0;
   size_t cap_iter_log = 0;  // records allocated for bf.iter_log (batch x bf.log_cap used)
+  // empc_solve_stream staging: job table and per-job results on the device
+  double *d_st_x0 = nullptr, *d_st_xs = nullptr, *d_st_us = nullptr, *d_st_uss = nullptr, *d_st_sc = nullptr; int* d_st_int = nullptr;
+  size_t cap_st_x0 = 0, cap_st_xs = 0, cap_st_us = 0, cap_st_uss = 0, cap_st_sc = 0, cap_st_int = 0;
   cudaStream_t stream = nullptr;
   int* h_active = nullptr;  // pinned: [group][slot][2]
   static constexpr int MAXG = 4;
@@ -766,7 +769,93 @@ static int solve_impl(empc_solver* h) {
   return EMPC_OK;
 }
 
+// empc_solve_stream: the batch-iteration loop of solve_impl (serial schedule) with a refill step after the line search
+template <class D>
+static int stream_impl(empc_solver* h, int n_jobs, const double* x0, double* xs, double* us, double* us_squash, double* cost,
+                       double* stop, int32_t* iters, int32_t* feasible) {
+  if (D::TILE != h->tile) return fail(EMPC_ERR_INVALID, "tile size mismatch");
+  h->launches = 0; h->total_iterations = 0;
+  for (double& m : h->ms_by_kernel) m = 0;
+  for (long long& u : h->units_by_kernel) u = 0;
+  const size_t J = (size_t)n_jobs, T = h->T, T1 = T + 1, nx = h->nx, nu = h->nu;
+  // device staging of the job table and of the per-job results (kept in the handle, grown on demand)
+  StreamBuffers sb;
+  sb.n_jobs = n_jobs;
+  CK(dreuse(h, &h->d_st_x0, &h->cap_st_x0, std::max<size_t>(1, J * nx)));
+  CK(dreuse(h, &h->d_st_sc, &h->cap_st_sc, std::max<size_t>(1, 2 * J)));
+  CK(dreuse(h, &h->d_st_int, &h->cap_st_int, std::max<size_t>(1, 2 * J) + (size_t)h->B + 1));
+  if (xs) CK(dreuse(h, &h->d_st_xs, &h->cap_st_xs, std::max<size_t>(1, J * T1 * nx)));
+  if (us) CK(dreuse(h, &h->d_st_us, &h->cap_st_us, std::max<size_t>(1, J * T * nu)));
+  if (us_squash) CK(dreuse(h, &h->d_st_uss, &h->cap_st_uss, std::max<size_t>(1, J * T * nu)));
+  sb.job_x0 = h->d_st_x0; sb.out_xs = xs ? h->d_st_xs : nullptr; sb.out_us = us ? h->d_st_us : nullptr;
+  sb.out_us_squash = us_squash ? h->d_st_uss : nullptr;
+  sb.out_cost = h->d_st_sc; sb.out_stop = h->d_st_sc + J;
+  sb.out_iters = h->d_st_int; sb.out_feasible = h->d_st_int + J; sb.slot_job = h->d_st_int + 2 * J; sb.queue_next = sb.slot_job + h->B;
+  if (J) CK(cudaMemcpyAsync(h->d_st_x0, x0, sizeof(double) * J * nx, cudaMemcpyDefault, h->stream));
+  const int first = std::min(n_jobs, h->B);
+  CK(cudaMemcpyAsync(sb.queue_next, &first, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->ev_solve[0], h->stream));
+  stream_refill_kernel<D><<<h->B, 128, 0, h->stream>>>(h->bf, sb, h->P, 1);
+  h->launches++;
+  CK(cudaGetLastError());
+  // every job runs at most passes x (maxiter + 1) batch-iterations, and a slot serves ceil(n_jobs / B) jobs at worst... the
+  // queue hands jobs out dynamically, so the bound is on the total work of the busiest slot: all jobs
+  int passes = 1;
+  for (double c = h->P.convergence_init; c >= h->P.convergence_stop && passes < 64; c *= h->P.convergence_mult) passes++;
+  const long long per_job = (long long)passes * ((long long)h->P.maxiter + 1) + 2;
+  const long long max_loops = per_job * ((long long)(n_jobs + h->B - 1) / std::max(1, h->B) + 1) + 2;
+  long long n_act = first, n_recalc = first;
+  bool finished = first == 0;
+  for (long long it = 0; it < max_loops && !finished; ++it) {
+    CK(launch_calc_diff<D>(h, 0, 0.0));
+    CK(launch_backward<D>(h, 0));
+    CK(launch_rollout<D>(h, 0, 0, 0, 0, 0.0));
+    CK(cudaMemsetAsync(h->bf.n_active, 0, 2 * sizeof(int), h->stream));
+    CK(launch_decide<D>(h, 0));
+    CK(launch_rollout<D>(h, 1, 0, 0, 0, 0.0));
+    CK(launch_decide<D>(h, 1));
+    stream_refill_kernel<D><<<h->B, 128, 0, h->stream>>>(h->bf, sb, h->P, 0);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_active, h->bf.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->units_by_kernel[0] += n_recalc; h->units_by_kernel[1] += n_act; h->units_by_kernel[2] += n_act; h->units_by_kernel[3] += n_act;
+    n_act = h->h_active[0]; n_recalc = h->h_active[1];
+    if (n_act == 0) finished = true;
+  }
+  CK(cudaEventRecord(h->ev_solve[1], h->stream));
+  if (!finished) return fail(EMPC_ERR_INVALID, "streaming solve stopped with OCPs still active (check convergence_mult / maxiter)");
+  // results -> caller (host or device memory)
+  std::vector<int32_t> it_host(J);
+  if (J) {
+    if (xs) CK(cudaMemcpyAsync(xs, h->d_st_xs, sizeof(double) * J * T1 * nx, cudaMemcpyDefault, h->stream));
+    if (us) CK(cudaMemcpyAsync(us, h->d_st_us, sizeof(double) * J * T * nu, cudaMemcpyDefault, h->stream));
+    if (us_squash) CK(cudaMemcpyAsync(us_squash, h->d_st_uss, sizeof(double) * J * T * nu, cudaMemcpyDefault, h->stream));
+    if (cost) CK(cudaMemcpyAsync(cost, sb.out_cost, sizeof(double) * J, cudaMemcpyDefault, h->stream));
+    if (stop) CK(cudaMemcpyAsync(stop, sb.out_stop, sizeof(double) * J, cudaMemcpyDefault, h->stream));
+    if (iters) CK(cudaMemcpyAsync(iters, sb.out_iters, sizeof(int32_t) * J, cudaMemcpyDefault, h->stream));
+    if (feasible) CK(cudaMemcpyAsync(feasible, sb.out_feasible, sizeof(int32_t) * J, cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(it_host.data(), sb.out_iters, sizeof(int32_t) * J, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  long long tot = 0;
+  for (int32_t v : it_host) tot += (long long)v + 1;  // iter_ = total_iters_ - 1 (src/sbfddp.cpp:222)
+  h->total_iterations = tot;
+  { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev_solve[0], h->ev_solve[1])); h->solve_ms = ms; }
+  return EMPC_OK;
+}
+
 extern "C" {
+
+int empc_solve_stream(empc_solver_t* h, int32_t n_jobs, const double* x0, double* xs, double* us, double* us_squash, double* cost,
+                      double* stop, int32_t* iters, int32_t* feasible) {
+  if (!h) return fail(EMPC_ERR_INVALID, "null");
+  if (n_jobs < 0 || (n_jobs > 0 && !x0)) return fail(EMPC_ERR_INVALID, "n_jobs < 0 or no initial states");
+  if (h->n_node_maps != 1) return fail(EMPC_ERR_INVALID, "streaming solves share one problem: not for replicated MPC instances");
+  CK(cudaSetDevice(h->device));
+  EMPC_DISPATCH(h, return stream_impl<D>(h, n_jobs, x0, xs, us, us_squash, cost, stop, iters, feasible));
+  return EMPC_OK;
+}
 
 int empc_solve(empc_solver_t* h) {
   if (!h) return fail(EMPC_ERR_INVALID, "null");

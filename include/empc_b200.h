@@ -10,6 +10,7 @@
  *   empc_create            SolverSbFDDP::SolverSbFDDP(problem, squashing)        src/sbfddp.cpp:5-38 (+ barrierInit :169-190)
  *   empc_set_x0            crocoddyl::ShootingProblem::set_x0                     examples/python/mpc.py:50
  *   empc_set_candidate     crocoddyl::SolverAbstract::setCandidate                src/sbfddp.cpp:199
+ *   empc_solve_stream      a queue of independent SolverSbFDDP::solve calls       src/sbfddp.cpp:192-226
  *   empc_set_params        set_convergence_init / solve(maxiter)                  include/eagle_mpc/sbfddp.hpp:43-52
  *   empc_update_costs      {Carrot,Rail,Weighted}Mpc::updateProblem               src/mpc-controllers/carrot-mpc.cpp:298-401
  *   empc_solve             SolverSbFDDP::solve                                    src/sbfddp.cpp:192-226
@@ -284,6 +285,16 @@ int empc_enable_iteration_log(empc_solver_t* h, int32_t capacity);
 /* records of OCP `ocp` from the last solve, oldest first; *n_records = number written (<= max_records). */
 int empc_get_iteration_log(const empc_solver_t* h, int32_t ocp, empc_iter_record_t* out, int32_t max_records,
                            int32_t* n_records);
+
+/* ---- streaming solve: more OCPs than slots.  The handle's `batch` OCP slots are refilled from a queue of `n_jobs`
+ * initial states as soon as an OCP finishes (on the device, between batch-iterations), so a workload whose OCPs need very
+ * different numbers of iterations does not run at the pace of its slowest member (every job of the reference is an
+ * independent SolverSbFDDP::solve, src/sbfddp.cpp:192-226; nothing couples them).  Each job is solve([], [], maxiter) of the
+ * handle's problem from its own x0 with a fresh solver state; results are per job, in job order, bit-identical to solving
+ * the job in a plain batch.  x0: n_jobs*nx.  xs (n_jobs*(T+1)*nx), us, us_squash (n_jobs*T*nu), cost, stop, iters,
+ * feasible (n_jobs) may each be NULL.  Pointers: host or device memory.  K / k are not kept per job. ---- */
+int empc_solve_stream(empc_solver_t* h, int32_t n_jobs, const double* x0, double* xs, double* us, double* us_squash,
+                      double* cost, double* stop, int32_t* iters, int32_t* feasible);
 
 /* total inner iterations executed by the last solve, summed over the batch (the benchmark's work unit) */
 int empc_get_total_iterations(const empc_solver_t* h, int64_t* total);

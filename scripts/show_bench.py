@@ -10,5 +10,5 @@ if "cpu_baseline" in d: print("cpu", round(d["cpu_baseline"]["value"]), d["cpu_b
 if "mpc_step_latency" in d: print("mpc", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in d["mpc_step_latency"].items() if k != "config"})
 if "config4" in d: c = d["config4"]; print("config4", round(c["value"]), "e2e", round(c["e2e"]["value"]), "ms", round(c["ms_per_step"], 1), "nccl MB/step", round(c["e2e"]["nccl_bytes_per_step"] / 1e6, 1))
 if "config5" in d: print("config5", [(c["controller"], c["knots"], round(c["ocp_iterations_per_s"])) for c in d["config5"]["cases"]])
-if "divergent_batch" in d: v = d["divergent_batch"]; print("divergent", round(v["value"]), v["iterations_per_ocp"], "batch its", v["batch_iterations"], "straggler", round(v["straggler_factor"], 2), v["batch_iterations_by_active_share"], "ms/batch-it", round(v["ms_per_batch_iteration"], 2))
+if "divergent_batch" in d: v = d["divergent_batch"]; print("divergent", round(v["value"]), v["iterations_per_ocp"], "batch its", v["batch_iterations"], "straggler", round(v["straggler_factor"], 2), v["batch_iterations_by_active_share"], "ms/batch-it", round(v["ms_per_batch_iteration"], 2)); print("   stream", round(v["stream"]["value"]), "uniform", round(v["uniform_yardstick"]["value"]), v["per_iteration_cost_vs_uniform"])
 print("clocks", d.get("clocks"))
