@@ -28,7 +28,7 @@ def test_stream_equals_plain_batch(name, slots, jobs):
     if len(set(out["iters"].tolist())) > 1:
         print(name, "iterations per job", sorted(set(out["iters"].tolist()))[:6], "...")
     # the handle is reusable: a plain solve afterwards, and a second stream without trajectories
-    g.set_x0(x0[:slots] if jobs >= slots else np.vstack([x0, x0])[:slots]); g.set_candidate(None, None, False); g.solve()
+    g.set_x0(np.resize(x0, (slots, fp.nx))); g.set_candidate(None, None, False); g.solve()   # (np.resize repeats the rows)
     n = min(slots, jobs)
     assert np.array_equal(g.iters()[:n], ref.iters()[:n]) and np.array_equal(g.xs()[:n], ref.xs()[:n])
     out2 = g.solve_stream(x0, want_trajectories=False)
