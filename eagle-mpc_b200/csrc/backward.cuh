@@ -539,11 +539,11 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
         double* Kg = bf.K + ((size_t)b * T + t) * m * n;
         for (int e2 = lane; e2 < m * n / 2; e2 += 32) {
           const int e = 2 * e2, i = e / n, j = e - i * n;  // n even: a pair never straddles rows
-          reinterpret_cast<double2*>(Kg)[e2] = *reinterpret_cast<const double2*>(sK + i * LD + (j ^ bw_swz(i)));
+          __stcs(reinterpret_cast<double2*>(Kg) + e2, *reinterpret_cast<const double2*>(sK + i * LD + (j ^ bw_swz(i))));  // written once, read by the rollout much later: streaming
         }
         double* kg = bf.k + ((size_t)b * T + t) * m;
-        if (lane < m) kg[lane] = kv[lane];
-        if (lane < n) { bf.Vx[(nb + t) * n + lane] = Vxp[lane]; bf.g[(nb + t) * n + lane] = gv[lane]; }
+        if (lane < m) __stcs(kg + lane, kv[lane]);
+        if (lane < n) { __stcs(bf.Vx + (nb + t) * n + lane, Vxp[lane]); __stcs(bf.g + (nb + t) * n + lane, gv[lane]); }
         {
           // five dot products as ONE 8x8 tensor-core product: row w of A and column w of B are the two vectors of
           // product w (Qu.k, k.Quuk, Vx.fs, fs.(Vxx fs), Qu.Qu), KN k-steps over the zero-padded vector slots; the

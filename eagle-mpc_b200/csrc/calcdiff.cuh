@@ -20,6 +20,15 @@
 // full 64-byte runs per field, and the consumer's block (8 nodes) reads one contiguous chunk.
 #pragma once
 
+#ifndef EMPC_STREAM_STORES
+#define EMPC_STREAM_STORES 1
+#endif
+#if EMPC_STREAM_STORES
+#define EMPC_ST_STREAM(ptr, v) __stcs((ptr), (v))
+#else
+#define EMPC_ST_STREAM(ptr, v) (*(ptr) = (v))
+#endif
+
 template <class D>
 struct Pk {
   static constexpr int NJ = D::NJ, NV = D::NV, NDX = D::NDX, NU = D::NU;
@@ -76,7 +85,9 @@ __global__ void __launch_bounds__(NC_THREADS, EMPC_NC_BLOCKS) node_calc_kernel(B
   if (__syncthreads_or(on) == 0) return;  // nothing to do for the whole block
   const double smooth = force ? force_smooth : st.smooth;
   double* pk = bf.packets + pk_index<D>(n, 0);  // field f of this node: pk[f * GROUP]
-  auto put = [&](int f, double v) { if (on) pk[(size_t)f * P::GROUP] = v; };
+  // packet fields are written once and read once by a later kernel, far beyond the reach of L2: streaming stores
+  // (evict-first) keep them from displacing the local-memory lines of the resident threads
+  auto put = [&](int f, double v) { if (on) EMPC_ST_STREAM(pk + (size_t)f * P::GROUP, v); };
 
   double x[NX], u[NU];
   const double* xg = bf.xs + n * NX;
@@ -144,7 +155,7 @@ __global__ void __launch_bounds__(NC_THREADS, EMPC_NC_BLOCKS) node_calc_kernel(B
     double* xng = bf.xnext + n * NX;
     if (on) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) xng[i] = xn[i];
+      for (int i = 0; i < NX; ++i) EMPC_ST_STREAM(xng + i, xn[i]);
     }
     EMPC_NC_PHASE();
     // Lie-group transport pieces of Fx / Fu
@@ -257,8 +268,11 @@ __global__ void __launch_bounds__(NC_THREADS, EMPC_NC_BLOCKS) node_calc_kernel(B
 // the state / control type costs (packet fields oLX .. oFLAG).  Split from node_calc_kernel so that neither kernel has to
 // keep the other's working set live (the dynamics + composite sweep spill less, and this one needs no dynamics at all);
 // the kinematics are recomputed only for nodes whose cost set holds frame costs.
+#ifndef EMPC_NCOST_BLOCKS
+#define EMPC_NCOST_BLOCKS 4
+#endif
 template <class D>
-__global__ void __launch_bounds__(128, 4) node_cost_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
+__global__ void __launch_bounds__(128, EMPC_NCOST_BLOCKS) node_cost_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
   constexpr int NDX = D::NDX, NU = D::NU, NX = D::NX;
   using P = Pk<D>;
   const long long nl0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(128, 4) node_cost_kernel(Buffers bf, int force
   if (!force && (st.phase == PHASE_DONE || !st.recalc)) return;
   const double smooth = force ? force_smooth : st.smooth;
   double* pk = bf.packets + pk_index<D>(n, 0);
-  auto put = [&](int f, double v) { pk[(size_t)f * P::GROUP] = v; };
+  auto put = [&](int f, double v) { EMPC_ST_STREAM(pk + (size_t)f * P::GROUP, v); };
   double x[NX], u[NU];
   const double* xg = bf.xs + n * NX;
 #pragma unroll
@@ -658,13 +672,13 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, DiffCfg<D>::MINB) node_di
     // rows 6 .. NV-1 (arm joint positions) and NV .. 2 NV-1 (velocities)
 #pragma unroll
     for (int i = 6; i < NV; ++i) {
-      Fx[i * NDX + l] = rq[i] * dt2 + ((i == l) ? 1.0 : 0.0);
-      Fx[i * NDX + NV + l] = rv[i] * dt2 + ((i == l) ? dt : 0.0);
+      EMPC_ST_STREAM(Fx + i * NDX + l, rq[i] * dt2 + ((i == l) ? 1.0 : 0.0));
+      EMPC_ST_STREAM(Fx + i * NDX + NV + l, rv[i] * dt2 + ((i == l) ? dt : 0.0));
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      Fx[(NV + i) * NDX + l] = rq[i] * dt;
-      Fx[(NV + i) * NDX + NV + l] = rv[i] * dt + ((i == l) ? 1.0 : 0.0);
+      EMPC_ST_STREAM(Fx + (NV + i) * NDX + l, rq[i] * dt);
+      EMPC_ST_STREAM(Fx + (NV + i) * NDX + NV + l, rv[i] * dt + ((i == l) ? 1.0 : 0.0));
     }
     // rows 0..5: Je [dt^2 a_q | dt^2 a_v + dt I] + [Ad(E^-1) | 0];  Ad(E^-1) = (X*)^T of E = exp(dx), entry (a, c) = Xs[6 c + a]
     SE3 E;
@@ -692,8 +706,8 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, DiffCfg<D>::MINB) node_di
         for (int cc = 0; cc < 6; ++cc) xs_ = (cc == l) ? Xs[6 * cc + a] : xs_;
         sq += xs_;
       }
-      Fx[a * NDX + l] = sq;
-      Fx[a * NDX + NV + l] = sv;
+      EMPC_ST_STREAM(Fx + a * NDX + l, sq);
+      EMPC_ST_STREAM(Fx + a * NDX + NV + l, sv);
     }
   }
 
@@ -723,8 +737,8 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, DiffCfg<D>::MINB) node_di
         double s = 0;
 #pragma unroll
         for (int k = 0; k < NV; ++k) s += Minv[i * NV + k] * acol[k];
-        if (i < 6) top[i] = dt2 * s; else Fu[i * NU + j] = dt2 * s;
-        Fu[(NV + i) * NU + j] = dt * s;
+        if (i < 6) top[i] = dt2 * s; else EMPC_ST_STREAM(Fu + i * NU + j, dt2 * s);
+        EMPC_ST_STREAM(Fu + (NV + i) * NU + j, dt * s);
       }
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
@@ -736,7 +750,7 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, DiffCfg<D>::MINB) node_di
           else je = (k < 3) ? 0.0 : JeA[3 * (a - 3) + (k - 3)];
           s += je * top[k];
         }
-        Fu[a * NU + j] = s;
+        EMPC_ST_STREAM(Fu + a * NU + j, s);
       }
     }
   }
@@ -749,8 +763,8 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, DiffCfg<D>::MINB) node_di
     static_assert(D::oLxx % 2 == 0 && D::oLxu % 2 == 0 && NDX % 2 == 0, "double2 stores need even offsets");
     // Lxu == 0 and the off-diagonal part of Luu == 0 for every cost the factories build: those tile entries keep the
     // zeros of the allocation (empc_create) and are never written, nor read by backward_kernel
-    for (int i = l; i < NU; i += W::LANES) gLuu[i * NU + i] = pk[P::oLUUD + i] * dt;
-    for (int i = l; i < NU; i += W::LANES) gLu[i] = pk[P::oLU + i] * dt;
+    for (int i = l; i < NU; i += W::LANES) EMPC_ST_STREAM(gLuu + i * NU + i, pk[P::oLUUD + i] * dt);
+    for (int i = l; i < NU; i += W::LANES) EMPC_ST_STREAM(gLu + i, pk[P::oLU + i] * dt);
     if (D::TILE != D::TILE0 && l == 0) tile[D::TILE0] = 0.0;
     auto lxx_state = [&](int i, int j) -> double {  // state-cost part: 6x6 block + diagonal
       if (i < 6 && j < 6) return pk[P::oLXXB + 6 * i + j];
@@ -769,10 +783,10 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, DiffCfg<D>::MINB) node_di
         }
         if (l == 0) bf.node_dense[n] = 0;
       } else {
-        for (int e = l; e < 36; e += W::LANES) { const int i = e / 6, j = e - 6 * i; gLxx[i * NDX + j] = pk[P::oLXXB + e] * dt; }
-        for (int i = 6 + l; i < NDX; i += W::LANES) gLxx[i * NDX + i] = pk[P::oLXXD + i - 6] * dt;
+        for (int e = l; e < 36; e += W::LANES) { const int i = e / 6, j = e - 6 * i; EMPC_ST_STREAM(gLxx + i * NDX + j, pk[P::oLXXB + e] * dt); }
+        for (int i = 6 + l; i < NDX; i += W::LANES) EMPC_ST_STREAM(gLxx + i * NDX + i, pk[P::oLXXD + i - 6] * dt);
       }
-      for (int i = l; i < NDX; i += W::LANES) gLx[i] = pk[P::oLX + i] * dt;
+      for (int i = l; i < NDX; i += W::LANES) EMPC_ST_STREAM(gLx + i, pk[P::oLX + i] * dt);
     } else {
       // The dense Lxx of a node with frame costs is accumulated in place in the tile: lane l owns the columns l,
       // l + LANES, ... from the state-cost initial value to the final scaling, so no hand-over is involved.

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
         state_integrate<D>(xn, gap, xt);
       }
 #pragma unroll
-      for (int i = 0; i < NX; ++i) xs_try[(size_t)t * NX + i] = xt[i];
+      for (int i = 0; i < NX; ++i) __stcs(xs_try + (size_t)t * NX + i, xt[i]);  // trial rows: read once by decide_kernel, streaming
       double dx[NDX];
       {
         double x0t[NX];
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
 #pragma unroll
           for (int jj = 0; jj < NDX; ++jj) kd += in[S::oK + i * NDX + jj] * dx[jj];
           u[i] = in[S::oUs + i] - in[S::oKk + i] * alpha - kd;
-          us_try[(size_t)t * NU + i] = u[i];
+          __stcs(us_try + (size_t)t * NU + i, u[i]);
         }
         node_dyn<D, true>(M, smooth, xt, u, xn);
         int worst = -1;  // raiseIfNaN(xnext.lpNorm<Infinity>()): integer test on the high words (node.cuh: raise_bits)
