@@ -13,7 +13,8 @@ MAX_NU = 16
 N_ALPHAS = 10
 
 COST_STATE, COST_CONTROL, COST_FRAME_PLACEMENT, COST_FRAME_ROTATION, COST_FRAME_VELOCITY, \
-    COST_FRAME_TRANSLATION, COST_SQUASH_BARRIER = range(7)
+    COST_FRAME_TRANSLATION, COST_SQUASH_BARRIER, COST_CONTACT_FRICTION_CONE = range(8)
+CONTACT_3D, CONTACT_6D = 1, 2
 ACT_QUAD, ACT_WEIGHTED_QUAD, ACT_QUAD_BARRIER, ACT_WEIGHTED_QUAD_BARRIER = range(4)
 
 c_double_p = C.POINTER(C.c_double)
@@ -64,6 +65,16 @@ class Cost(C.Structure):
     ]
 
 
+class Contact(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("frame", C.c_int32),
+        ("gains", C.c_double * 2),
+        ("ref_p", C.c_double * 3),
+        ("ref_R", C.c_double * 9),
+    ]
+
+
 class ProblemDesc(C.Structure):
     _fields_ = [
         ("robot", Robot),
@@ -82,6 +93,10 @@ class ProblemDesc(C.Structure):
         ("costs", C.POINTER(Cost)),
         ("pool", c_double_p),
         ("node_costset", c_int32_p),
+        ("n_contacts", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("contacts", C.POINTER(Contact)),
+        ("costset_contact", c_int32_p),
     ]
 
 

@@ -65,8 +65,10 @@ EMPC_DI size_t pk_index(size_t n, int f) { return (n / Pk<D>::GROUP) * (size_t)(
 #ifndef EMPC_NC_THREADS
 #define EMPC_NC_THREADS 128
 #endif
+// 2 blocks of 128 threads per SM (255 registers): with the packet written by streaming stores the smaller spill frame of
+// the 255-register build beats the third resident block (calc_diff 86.5 -> 80.8 ms per step, gpurun_out/variants_b.txt)
 #ifndef EMPC_NC_BLOCKS
-#define EMPC_NC_BLOCKS 3
+#define EMPC_NC_BLOCKS 2
 #endif
 constexpr int NC_THREADS = EMPC_NC_THREADS;
 #define EMPC_NC_PHASE() __syncthreads()

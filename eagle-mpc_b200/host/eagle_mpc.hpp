@@ -163,6 +163,29 @@ class CostModelSum {  // crocoddyl::CostModelSum: std::map => iteration in name 
   std::map<std::string, std::shared_ptr<CostItem>> costs_;
 };
 
+// crocoddyl::ContactModel3D / ContactModel6D as src/factory/contacts.cpp:32-81 builds them, and ContactModelMultiple
+enum class ContactModelTypes { ContactModel3D, ContactModel6D };
+struct ContactModel {
+  ContactModelTypes type = ContactModelTypes::ContactModel3D;
+  std::size_t frame_id = 0;         // index into RobotModel::frames
+  double gains[2] = {0, 0};         // Baumgarte gains
+  double position[3] = {0, 0, 0};   // reference position
+  double rotation[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // reference orientation (6D)
+};
+class ContactModelMultiple {
+ public:
+  void addContact(const std::string& name, const std::shared_ptr<ContactModel>& contact) { contacts_[name] = contact; }
+  const std::map<std::string, std::shared_ptr<ContactModel>>& get_contacts() const { return contacts_; }
+
+ private:
+  std::map<std::string, std::shared_ptr<ContactModel>> contacts_;
+};
+class ContactModelFactory {
+ public:
+  std::shared_ptr<ContactModel> create(const std::string& path_to_contact, const std::shared_ptr<ParamsServer>& server,
+                                       const std::shared_ptr<StateMultibody>& state, ContactModelTypes& contact_type) const;
+};
+
 class ActivationModelFactory {
  public:
   std::shared_ptr<ActivationModel> create(const std::string& path_to_cost, const std::shared_ptr<ParamsServer>& server,
@@ -178,6 +201,9 @@ class CostModelFactory {
 // IntegratedActionModelEuler( DifferentialActionModelFreeFwdDynamics(state, actuation, costs), dt )
 struct ActionModel {
   std::shared_ptr<CostModelSum> costs;
+  // DifferentialActionModelContactFwdDynamics(state, actuation, contacts, costs, 0, true) when the trajectory has a
+  // contact stage (src/factory/diff-action.cpp:30-32), DifferentialActionModelFreeFwdDynamics otherwise (contacts null)
+  std::shared_ptr<ContactModelMultiple> contacts;
   double dt = 0;     // seconds
   bool squash = true;
   VectorXd u_lb, u_ub;
@@ -203,22 +229,26 @@ class Stage : public std::enable_shared_from_this<Stage> {
   void set_duration(std::size_t d) { duration_ = d; }
   const std::shared_ptr<Trajectory>& get_trajectory() const { return trajectory_; }
   const std::shared_ptr<CostModelSum>& get_costs() const { return costs_; }
+  const std::shared_ptr<ContactModelMultiple>& get_contacts() const { return contacts_; }
+  const std::map<std::string, ContactModelTypes>& get_contact_types() const { return contact_types_; }
   const std::map<std::string, CostModelTypes>& get_cost_types() const { return cost_types_; }
   std::size_t get_duration() const { return duration_; }
   std::size_t get_t_ini() const { return t_ini_; }
   const std::string& get_name() const { return name_; }
   bool get_is_terminal() const { return is_terminal_; }
   bool get_is_transition() const { return is_transition_; }
-  bool has_contacts() const { return has_contacts_; }
+  bool has_contacts() const { return !contacts_->get_contacts().empty(); }
 
  private:
   explicit Stage(const std::shared_ptr<Trajectory>& trajectory);
   std::shared_ptr<Trajectory> trajectory_;
   std::shared_ptr<CostModelSum> costs_;
+  std::shared_ptr<ContactModelMultiple> contacts_;
   std::map<std::string, CostModelTypes> cost_types_;
+  std::map<std::string, ContactModelTypes> contact_types_;
   std::string name_;
   std::size_t duration_ = 0, t_ini_ = 0;
-  bool is_terminal_ = false, is_transition_ = false, has_contacts_ = false;
+  bool is_terminal_ = false, is_transition_ = false;
 };
 
 struct ProblemParams {
@@ -269,8 +299,9 @@ class Trajectory : public std::enable_shared_from_this<Trajectory> {
 // Flattened problem (what goes over the C ABI).  Owns the arrays the desc points to.
 struct FlatProblem {
   empc_problem_desc_t desc;
-  std::vector<int32_t> costset_begin, node_costset;
+  std::vector<int32_t> costset_begin, node_costset, costset_contact;
   std::vector<empc_cost_t> costs;
+  std::vector<empc_contact_t> contacts;
   std::vector<double> pool;
   // where each (model, cost name) landed, for MPC retargeting
   struct Slot { int cost_index; int ref_off, w_off, lb_off, ub_off; };

@@ -218,14 +218,95 @@ std::shared_ptr<CostModelResidual> CostModelFactory::create(const std::string& p
       cost->reference = vec("position");
       cost->frame_id = frame_of();
     } break;
+    case CostModelTypes::CostModelContactFrictionCone: {
+      // crocoddyl::FrictionCone(n_surf, mu, 4, false) + ActivationModelQuadraticBarrier(bounds(cone.lb, cone.ub)) +
+      // ResidualModelContactFrictionCone (src/factory/cost.cpp:149-167).  reference = A, 5 x 3 row-major:
+      // rows (-mu z +- t_i)^T c_R_o for the nf/2 = 2 tangents t_i = (cos, sin, 0)(2 pi i / nf), then n_surf^T;
+      // bounds (-max, 0] for the cone facets, [0, max) for the normal force (min_nforce = 0, max_nforce = max)
+      VectorXd n = vec("n_surf");
+      const double mu = server->getParam<double>(path + "mu");
+      if (n.size() != 3) throw std::runtime_error("n_surf @" + path + "n_surf must have 3 entries");
+      const double nn = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      for (int i = 0; i < 3; ++i) n[i] /= nn;
+      // c_R_o = Quaternion::FromTwoVectors(n_surf, UnitZ): rotation about n x z by the angle between them
+      double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      {
+        const double ax[3] = {n[1], -n[0], 0.0};  // n x z
+        const double sn = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1]), cs = n[2];
+        if (sn > 1e-12) {
+          const double k[3] = {ax[0] / sn, ax[1] / sn, 0.0};
+          const double K[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+              double kk = 0;
+              for (int l = 0; l < 3; ++l) kk += K[3 * i + l] * K[3 * l + j];
+              R[3 * i + j] = (i == j ? 1.0 : 0.0) + sn * K[3 * i + j] + (1.0 - cs) * kk;
+            }
+        } else if (cs < 0) {  // n = -z: half turn about x
+          R[4] = -1; R[8] = -1;
+        }
+      }
+      cost->reference.assign(15, 0.0);
+      const double z[3] = {0, 0, 1};
+      for (int i = 0; i < 2; ++i) {
+        const double th = 2.0 * M_PI * double(i) / 4.0;
+        const double ts[3] = {std::cos(th), std::sin(th), 0.0};
+        for (int c = 0; c < 3; ++c) {
+          double p = 0, q = 0;
+          for (int l = 0; l < 3; ++l) { p += (-mu * z[l] + ts[l]) * R[3 * l + c]; q += (-mu * z[l] - ts[l]) * R[3 * l + c]; }
+          cost->reference[3 * (2 * i) + c] = p;
+          cost->reference[3 * (2 * i + 1) + c] = q;
+        }
+      }
+      for (int c = 0; c < 3; ++c) cost->reference[12 + c] = n[c];
+      cost->frame_id = frame_of();
+      cost->activation.type = ActivationModelTypes::ActivationModelQuadraticBarrier;
+      cost->activation.nr = 5;
+      const double big = std::numeric_limits<double>::max();
+      cost->activation.lb = {-big, -big, -big, -big, 0.0};
+      cost->activation.ub = {0.0, 0.0, 0.0, 0.0, big};
+      activation_bounds(cost->activation.lb, cost->activation.ub);
+    } break;
     default:
-      throw std::runtime_error("CostModelContactFrictionCone needs the contact dynamics path, which the B200 hot path does not cover (SURVEY.md §8f)");
+      throw std::runtime_error("cost type not supported");
   }
   return cost;
 }
 
+// src/factory/contacts.cpp:17-81
+std::shared_ptr<ContactModel> ContactModelFactory::create(const std::string& path, const std::shared_ptr<ParamsServer>& server,
+                                                          const std::shared_ptr<StateMultibody>& state,
+                                                          ContactModelTypes& contact_type) const {
+  static const std::map<std::string, ContactModelTypes> ContactModelTypes_map = {
+      {"ContactModel3D", ContactModelTypes::ContactModel3D}, {"ContactModel6D", ContactModelTypes::ContactModel6D}};
+  try {
+    contact_type = ContactModelTypes_map.at(server->getParam<std::string>(path + "type"));
+  } catch (const std::exception&) {
+    throw std::runtime_error("Contact " + server->getParam<std::string>(path + "type") + "not found. Please make sure the specified contact exists.");
+  }
+  auto contact = std::make_shared<ContactModel>();
+  contact->type = contact_type;
+  VectorXd position = converter<VectorXd>::convert(server->getParam<std::string>(path + "position"));
+  for (int i = 0; i < 3; ++i) contact->position[i] = position[i];
+  if (contact_type == ContactModelTypes::ContactModel6D) {
+    VectorXd orientation = converter<VectorXd>::convert(server->getParam<std::string>(path + "orientation"));
+    quat_to_R(orientation.data(), contact->rotation);  // Eigen::Quaterniond(orientation).normalize().toRotationMatrix()
+  }
+  const std::string link_name = server->getParam<std::string>(path + "link_name");
+  contact->frame_id = state->pinocchio->getFrameId(link_name);
+  if (contact->frame_id == state->pinocchio->frames.size()) throw std::runtime_error("Link " + link_name + "does no exists");
+  try {
+    VectorXd gains = converter<VectorXd>::convert(server->getParam<std::string>(path + "gains"));
+    contact->gains[0] = gains[0]; contact->gains[1] = gains[1];
+  } catch (const std::exception&) {
+    contact->gains[0] = contact->gains[1] = 0;  // "Set to the zero gains vector"
+  }
+  return contact;
+}
+
 // ---- Stage ------------------------------------------------------------------------------------------------------------
-Stage::Stage(const std::shared_ptr<Trajectory>& trajectory) : trajectory_(trajectory), costs_(std::make_shared<CostModelSum>()) {}
+Stage::Stage(const std::shared_ptr<Trajectory>& trajectory)
+    : trajectory_(trajectory), costs_(std::make_shared<CostModelSum>()), contacts_(std::make_shared<ContactModelMultiple>()) {}
 std::shared_ptr<Stage> Stage::create(const std::shared_ptr<Trajectory>& trajectory) { return std::shared_ptr<Stage>(new Stage(trajectory)); }
 
 void Stage::autoSetup(const std::string& path_to_stages, const std::map<std::string, std::string>& stage,
@@ -235,9 +316,14 @@ void Stage::autoSetup(const std::string& path_to_stages, const std::map<std::str
   duration_ = std::size_t(converter<int>::convert(stage.at("duration")));
   t_ini_ = t_ini;
   is_transition_ = converter<bool>::convert(stage.at("transition"));
-  if (stage.count("contacts")) {
-    auto names = converter<std::vector<std::string>>::convert(stage.at("contacts"));
-    has_contacts_ = !names.empty();
+  if (stage.count("contacts")) {  // src/stage.cpp:38-47
+    ContactModelFactory ctf;
+    for (const std::string& contact_name : converter<std::vector<std::string>>::convert(stage.at("contacts"))) {
+      ContactModelTypes contact_type;
+      auto contact = ctf.create(path_to_stage + "contacts/" + contact_name + "/", server, trajectory_->get_robot_state(), contact_type);
+      contacts_->addContact(contact_name, contact);
+      contact_types_.insert({contact_name, contact_type});
+    }
   }
   CostModelFactory cf;
   for (const std::string& cost_name : converter<std::vector<std::string>>::convert(stage.at("costs"))) {
@@ -305,8 +391,6 @@ std::shared_ptr<ShootingProblem> Trajectory::createProblem() const {
 }
 
 std::shared_ptr<ShootingProblem> Trajectory::createProblem(std::size_t dt, bool squash, const std::string& integration_method) const {
-  if (has_contact_)
-    throw std::runtime_error("Contact trajectories need DifferentialActionModelContactFwdDynamics, outside the B200 hot path (SURVEY.md §8f)");
   if (integration_method == "IntegratedActionModelRK4")
     throw std::runtime_error("IntegratedActionModelRK4 is not part of the B200 hot path yet; use IntegratedActionModelEuler");
   if (integration_method != "IntegratedActionModelEuler") throw std::out_of_range("map::at");
@@ -315,6 +399,7 @@ std::shared_ptr<ShootingProblem> Trajectory::createProblem(std::size_t dt, bool 
   for (auto stage = stages_.begin(); stage != stages_.end(); ++stage) {
     auto iam = std::make_shared<ActionModel>();
     iam->costs = (*stage)->get_costs();
+    if (has_contact_) iam->contacts = (*stage)->get_contacts();  // dam_factory_->create(has_contact_, squash, *stage), :115-116
     iam->dt = double(dt) / 1000.;
     iam->squash = squash;
     std::size_t n_knots;
@@ -347,6 +432,7 @@ static int cost_type_code(CostModelTypes t) {
     case CostModelTypes::CostModelFrameVelocity: return EMPC_COST_FRAME_VELOCITY;
     case CostModelTypes::CostModelFrameTranslation: return EMPC_COST_FRAME_TRANSLATION;
     case CostModelTypes::CostModelSquashBarrier: return EMPC_COST_SQUASH_BARRIER;
+    case CostModelTypes::CostModelContactFrictionCone: return EMPC_COST_CONTACT_FRICTION_CONE;
     default: throw std::runtime_error("cost type not supported by the B200 hot path");
   }
 }
@@ -368,6 +454,9 @@ void FlatProblem::finalize() {
   desc.costs = costs.data();
   desc.pool = pool.data();
   desc.node_costset = node_costset.data();
+  desc.n_contacts = (int)contacts.size();
+  desc.contacts = contacts.empty() ? nullptr : contacts.data();
+  desc.costset_contact = contacts.empty() ? nullptr : costset_contact.data();
 }
 
 void fill_cost_record(const CostItem& item, empc_cost_t& rec, double* pool) {
@@ -422,6 +511,7 @@ void flatten_problem(const ShootingProblem& problem, FlatProblem& out) {
   out.desc.n_node_maps = 1;
   out.costset_begin.assign(1, 0);
   out.costs.clear(); out.pool.clear(); out.node_costset.assign(T + 1, 0); out.slots.clear(); out.set_models.clear();
+  out.contacts.clear(); out.costset_contact.clear();
   std::map<const ActionModel*, int> set_of;
   auto add_model = [&](const ActionModel* m) {
     auto it = set_of.find(m);
@@ -431,13 +521,34 @@ void flatten_problem(const ShootingProblem& problem, FlatProblem& out) {
     out.set_models.push_back(m);
     out.slots.emplace_back();
     if (m->dt != out.desc.dt) throw std::runtime_error("all action models must share the same time step");
+    // the model's ContactModelMultiple: one contact per model is what the corpus uses and what the kernels cover
+    int contact_index = -1;
+    if (m->contacts && !m->contacts->get_contacts().empty()) {
+      if (m->contacts->get_contacts().size() > 1) throw std::runtime_error("more than one contact per stage is not supported by the B200 hot path");
+      const ContactModel& c = *m->contacts->get_contacts().begin()->second;
+      if (c.gains[0] != 0.0 || c.gains[1] != 0.0) throw std::runtime_error("non-zero contact gains are not supported by the B200 hot path");
+      empc_contact_t rec;
+      std::memset(&rec, 0, sizeof(rec));
+      rec.type = c.type == ContactModelTypes::ContactModel6D ? EMPC_CONTACT_6D : EMPC_CONTACT_3D;
+      rec.frame = slot_of(c.frame_id);
+      rec.gains[0] = c.gains[0]; rec.gains[1] = c.gains[1];
+      std::copy(c.position, c.position + 3, rec.ref_p);
+      std::copy(c.rotation, c.rotation + 9, rec.ref_R);
+      contact_index = (int)out.contacts.size();
+      out.contacts.push_back(rec);
+    }
+    out.costset_contact.push_back(contact_index);
     for (const auto& kv : m->costs->get_costs()) {  // std::map => sorted by name, crocoddyl's iteration order
       const CostItem& item = *kv.second;
       const CostModelResidual& c = *item.cost;
       empc_cost_t rec;
       rec.type = cost_type_code(c.type);
       rec.activation = act_code(c.activation.type);
-      const bool is_frame = rec.type >= EMPC_COST_FRAME_PLACEMENT && rec.type <= EMPC_COST_FRAME_TRANSLATION;
+      const bool is_frame = (rec.type >= EMPC_COST_FRAME_PLACEMENT && rec.type <= EMPC_COST_FRAME_TRANSLATION) ||
+                            rec.type == EMPC_COST_CONTACT_FRICTION_CONE;
+      if (rec.type == EMPC_COST_CONTACT_FRICTION_CONE &&
+          (contact_index < 0 || out.contacts[contact_index].frame != slot_of(c.frame_id)))
+        throw std::runtime_error("CostModelContactFrictionCone '" + kv.first + "' needs a contact on the same link in its stage");
       rec.frame = is_frame ? slot_of(c.frame_id) : 0;
       auto reserve = [&](std::size_t n) { if (!n) return -1; const int off = (int)out.pool.size(); out.pool.resize(out.pool.size() + n, 0.0); return off; };
       rec.ref_off = reserve(c.reference.size());

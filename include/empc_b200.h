@@ -53,8 +53,19 @@ enum {
   EMPC_COST_FRAME_ROTATION = 3,
   EMPC_COST_FRAME_VELOCITY = 4,
   EMPC_COST_FRAME_TRANSLATION = 5,
-  EMPC_COST_SQUASH_BARRIER = 6 /* the "barrier" cost SolverSbFDDP adds, src/sbfddp.cpp:169-190 */
+  EMPC_COST_SQUASH_BARRIER = 6, /* the "barrier" cost SolverSbFDDP adds, src/sbfddp.cpp:169-190 */
+  EMPC_COST_CONTACT_FRICTION_CONE = 7 /* src/factory/cost.cpp:149-167: r = A f on the force of the stage's contact */
 };
+
+/* contact models — src/factory/contacts.cpp:32-81 (DifferentialActionModelContactFwdDynamics, src/factory/diff-action.cpp:30-32) */
+enum { EMPC_CONTACT_3D = 1, EMPC_CONTACT_6D = 2 };
+typedef struct empc_contact {
+  int32_t type;       /* EMPC_CONTACT_3D: the frame origin is held (3 constraint rows); _6D: the whole frame (6 rows) */
+  int32_t frame;      /* index into empc_robot_t::frame_* */
+  double gains[2];    /* Baumgarte gains; the corpus uses (0, 0) and the kernels require it */
+  double ref_p[3];    /* reference position (used by the gains only) */
+  double ref_R[9];    /* reference orientation, 6D (used by the gains only) */
+} empc_contact_t;
 
 /* activation types — src/factory/activation.cpp:34-101 */
 enum {
@@ -83,7 +94,8 @@ typedef struct empc_robot {
 
 /* One cost term of a CostModelSum.  Offsets index `pool` (doubles); -1 = absent.
  * Reference layouts: STATE nx | CONTROL nu | FRAME_PLACEMENT R(9)+p(3) | FRAME_ROTATION R(9) |
- * FRAME_VELOCITY lin(3)+ang(3) | FRAME_TRANSLATION p(3) | SQUASH_BARRIER none.
+ * FRAME_VELOCITY lin(3)+ang(3) | FRAME_TRANSLATION p(3) | SQUASH_BARRIER none |
+ * CONTACT_FRICTION_CONE A (5 x 3 row-major: crocoddyl::FrictionCone(n_surf, mu, 4, false)), lb / ub 5 each.
  * Activation vectors (weights / lower / upper bound) have the residual's dimension. */
 typedef struct empc_cost {
   int32_t type;
@@ -117,6 +129,13 @@ typedef struct empc_problem_desc {
   const empc_cost_t* costs;                 /* n_costs */
   const double* pool;                       /* n_pool */
   const int32_t* node_costset;              /* n_node_maps*(T+1) */
+  /* Contact dynamics.  n_contacts = 0: DifferentialActionModelFreeFwdDynamics everywhere.  Otherwise
+   * costset_contact[c] is the contact of the model that owns cost set c (one ContactModel per stage, as in the
+   * corpus), or -1: that model has an empty ContactModelMultiple and behaves like the free dynamics. */
+  int32_t n_contacts;
+  int32_t reserved_;
+  const empc_contact_t* contacts;           /* n_contacts */
+  const int32_t* costset_contact;           /* n_costsets, or NULL when n_contacts = 0 */
 } empc_problem_desc_t;
 
 /* Stop rules.  The PepMS Crocoddyl fork defines stoppingCriteria()/stoppingTest() behind two enums that eagle-mpc sets to

@@ -37,8 +37,9 @@ namespace orc {
 struct Solver {
   // deep copy of the problem
   empc_problem_desc_t desc;
-  std::vector<int32_t> costset_begin, node_costset;
+  std::vector<int32_t> costset_begin, node_costset, costset_contact;
   std::vector<empc_cost_t> costs;
+  std::vector<empc_contact_t> contacts;
   std::vector<double> pool;
   Model m;
   empc_solver_params_t P;
@@ -64,6 +65,13 @@ struct Solver {
     node_costset.assign(d->node_costset, d->node_costset + (size_t)d->n_node_maps * (d->T + 1));
     desc.costset_begin = costset_begin.data(); desc.costs = costs.data();
     desc.pool = pool.data(); desc.node_costset = node_costset.data();
+    if (d->n_contacts > 0 && d->contacts && d->costset_contact) {
+      contacts.assign(d->contacts, d->contacts + d->n_contacts);
+      costset_contact.assign(d->costset_contact, d->costset_contact + d->n_costsets);
+      desc.contacts = contacts.data(); desc.costset_contact = costset_contact.data();
+    } else {
+      desc.n_contacts = 0; desc.contacts = nullptr; desc.costset_contact = nullptr;
+    }
     m.init(&desc);
     T = d->T;
     const int nx = m.nx, ndx = m.ndx, nu = m.nu;

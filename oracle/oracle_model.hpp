@@ -4,6 +4,9 @@
 // reference instantiates (src/factory/diff-action.cpp:31-35, src/factory/int-action.cpp:26, src/trajectory.cpp:47-52):
 //   IntegratedActionModelEuler            crocoddyl/core/integrator/euler.hxx           (calc / calcDiff)
 //   DifferentialActionModelFreeFwdDynamics crocoddyl/multibody/actions/free-fwddyn.hxx
+//   DifferentialActionModelContactFwdDynamics crocoddyl/multibody/actions/contact-fwddyn.hxx, ContactModel3D / 6D,
+//     pinocchio::forwardDynamics / getKKTContactDynamicMatrixInverse, ResidualModelContactFrictionCone
+//     (src/factory/diff-action.cpp:30-32, src/factory/contacts.cpp:32-81, src/factory/cost.cpp:149-167)
 //   ActuationSquashingModel + SquashingModelSmoothSat + ActuationModelMultiCopterBase
 //   CostModelSum / CostModelResidual / Activation* / Residual{State,Control,Frame*}
 //   StateMultibody (integrate / diff / Jdiff / Jintegrate / JintegrateTransport)
@@ -122,6 +125,14 @@ struct Work {
   double J[6][MAXV];
   double ov[MAXJ][6], oa[MAXJ][6];
   double Minv[MAXV * MAXV];
+  // contact dynamics (nc = 0: free dynamics)
+  int nc = 0, cframe = -1;
+  SE3 oMf;                    // world placement of the contact frame
+  double fJ[6][MAXV];         // its LOCAL Jacobian; the constraint rows Jc are rows 0 .. nc-1
+  double vf[6];               // its LOCAL velocity
+  double lam[6];              // contact force, contact-frame coordinates (pinocchio lambda_c)
+  double Bc[MAXV][6];         // Minv Jc^T
+  double Ginv[36];            // (Jc Minv Jc^T)^-1, nc x nc
 };
 
 struct SolverCtx {  // the pieces of solver state the node model depends on
@@ -297,6 +308,7 @@ inline int residual_dim(const Model& m, int type) {
     case EMPC_COST_SQUASH_BARRIER: return m.nu;
     case EMPC_COST_FRAME_PLACEMENT: return 6;
     case EMPC_COST_FRAME_VELOCITY: return 6;
+    case EMPC_COST_CONTACT_FRICTION_CONE: return 5;
     default: return 3;
   }
 }
@@ -347,9 +359,14 @@ inline double cost_calc(const Model& m, const SolverCtx& ctx, const empc_cost_t&
       double vf[6]; actinv_motion(m.fplace[c.frame], w.v[m.d->robot.frame_joint[c.frame]], vf);
       for (int i = 0; i < 6; ++i) e.r[i] = vf[i] - ref[i];
     } break;
+    case EMPC_COST_CONTACT_FRICTION_CONE:  // ResidualModelContactFrictionCone: r = A f, f in the contact frame
+      for (int i = 0; i < 5; ++i) e.r[i] = (w.nc > 0) ? ref[3 * i] * w.lam[0] + ref[3 * i + 1] * w.lam[1] + ref[3 * i + 2] * w.lam[2] : 0.0;
+      break;
   }
   return activation(c.activation, n, e.r, aw, lb, ub, e.Ar, e.Arr);
 }
+
+inline void contact_calc(const Model& m, const empc_contact_t& ct, const double* vq, Work& w);
 
 // IntegratedActionModelEuler::calc — fills w (xnext, cost, and everything calcDiff reuses)
 inline void node_calc(const Model& m, const SolverCtx& ctx, int costset, const double* x, const double* u, Work& w,
@@ -375,6 +392,11 @@ inline void node_calc(const Model& m, const SolverCtx& ctx, int costset, const d
   }
   for (int i = 0; i < m.na; ++i) w.tau[6 + i] = w.s[m.nr + i];
   aba(m, x, x + m.nq, w.tau, w);
+  // a model with a contact: DifferentialActionModelContactFwdDynamics (src/factory/diff-action.cpp:30-32); a model of a
+  // contact trajectory whose ContactModelMultiple is empty reduces to the free dynamics
+  w.nc = 0;
+  if (d.n_contacts > 0 && d.costset_contact && d.costset_contact[costset] >= 0)
+    contact_calc(m, d.contacts[d.costset_contact[costset]], x + m.nq, w);
   // semi-implicit Euler (euler.hxx calc)
   const double dt = m.dt, dt2 = dt * dt;
   for (int i = 0; i < m.nv; ++i) {
@@ -395,13 +417,10 @@ inline void node_calc(const Model& m, const SolverCtx& ctx, int costset, const d
   w.cost = dt * cost;
 }
 
-// world Jacobian columns, velocities/accelerations, M^-1, d(ddq)/d(q,v,tau).  aq (nv x nv), av, Minv in w.Minv.
-inline void aba_derivatives(const Model& m, Work& w, double* a_q, double* a_v) {
+// world Jacobian columns (motion axes of the velocity columns) and world body velocities
+inline void world_kinematics(const Model& m, Work& w) {
   const empc_robot_t& r = m.d->robot;
-  const int nv = m.nv;
-  double oY[MAXJ][36], Bm[MAXJ][36], F[MAXJ][6];
   for (int i = 0; i < m.nj; ++i) {
-    // world Jacobian columns
     if (i == 0) {
       double X[36]; motion_action_matrix(w.oMi[0], X);
       for (int a = 0; a < 6; ++a)
@@ -412,12 +431,46 @@ inline void aba_derivatives(const Model& m, Work& w, double* a_q, double* a_v) {
       for (int a = 0; a < 6; ++a) w.J[a][m.col0[i]] = Jc[a];
     }
     act_motion(w.oMi[i], w.v[i], w.ov[i]);
-    act_motion(w.oMi[i], w.agf[i], w.oa[i]);
+  }
+}
+
+// world spatial accelerations of the bodies for joint velocities vq and accelerations aq, on top of the base acceleration
+// a_base (m.a0 = the gravity field of RNEA, or zero for the kinematic acceleration): A_i = A_p + S_i aq_i + V_p x S_i vq_i
+inline void world_accelerations(const Model& m, const Work& w, const double* vq, const double* aq, const double* a_base,
+                                double oa[][6]) {
+  const empc_robot_t& r = m.d->robot;
+  for (int i = 0; i < m.nj; ++i) {
+    if (i == 0) {
+      for (int k = 0; k < 6; ++k) {
+        double s = a_base[k];
+        for (int c = 0; c < 6; ++c) s += w.J[k][c] * aq[c];
+        oa[0][k] = s;  // V_0 x (S vq) = V_0 x V_0 = 0
+      }
+    } else {
+      const int c = m.col0[i], p = r.parent[i];
+      double col[6], cr[6];
+      for (int k = 0; k < 6; ++k) col[k] = w.J[k][c];
+      cross_mm(w.ov[p], col, cr);
+      for (int k = 0; k < 6; ++k) oa[i][k] = oa[p][k] + col[k] * aq[c] + cr[k] * vq[c];
+    }
+  }
+}
+
+// RNEA partial derivatives d tau/dq, d tau/dv (nv x nv) and the joint-space inertia M at the accelerations w.oa (world,
+// gravity field included), with an optional external force Fext_w (world spatial force, constant in the local frame of
+// joint jext, acting ON the robot: tau = RNEA - J^T F): pinocchio::computeRNEADerivatives(q, v, a, fext).
+// w.J, w.ov, w.oa must be set.
+inline void rnea_partials(const Model& m, Work& w, const double* Fext_w, int jext, double* M, double* dq, double* dv) {
+  const empc_robot_t& r = m.d->robot;
+  const int nv = m.nv;
+  double oY[MAXJ][36], Bm[MAXJ][36], F[MAXJ][6];
+  for (int i = 0; i < m.nj; ++i) {
     double X[36]; force_action_matrix(w.oMi[i], X);
     congruence6(X, m.Y[i], oY[i]);
     double h[6], Ya[6], vh[6];
     mat6_vec(oY[i], w.ov[i], h); mat6_vec(oY[i], w.oa[i], Ya); cross_mf(w.ov[i], h, vh);
     for (int k = 0; k < 6; ++k) F[i][k] = Ya[k] + vh[k];
+    if (Fext_w && i == jext) for (int k = 0; k < 6; ++k) F[i][k] -= Fext_w[k];
     // B_i = crf(v) Y - Y crm(v) + Hx(h)   (DESIGN.md "RNEA derivatives")
     double Sv[9], Sw[9]; skew3(w.ov[i], Sv); skew3(w.ov[i] + 3, Sw);
     double crf[36], crm[36];
@@ -457,7 +510,6 @@ inline void aba_derivatives(const Model& m, Work& w, double* a_q, double* a_v) {
     mat6T_vec(Bm[j], Jc[c], BtJ[c]);
   }
   // joint-space inertia
-  double M[MAXV * MAXV];
   for (int cj = 0; cj < nv; ++cj)
     for (int ck = 0; ck < nv; ++ck) {
       const int j = m.joint_of_col[cj], k = m.joint_of_col[ck];
@@ -467,7 +519,6 @@ inline void aba_derivatives(const Model& m, Work& w, double* a_q, double* a_v) {
       M[cj * nv + ck] = val;
     }
   // RNEA partial derivatives
-  double dq[MAXV * MAXV], dv[MAXV * MAXV];
   const double zero6[6] = {0, 0, 0, 0, 0, 0};
   for (int ck = 0; ck < nv; ++ck) {
     const int k = m.joint_of_col[ck], pk = r.parent[k];
@@ -498,13 +549,26 @@ inline void aba_derivatives(const Model& m, Work& w, double* a_q, double* a_v) {
       dq[cj * nv + ck] = vq_; dv[cj * nv + ck] = vv_;
     }
   }
-  // Minv by Cholesky; ddq_dq = -Minv dtau_dq etc. (computeABADerivatives)
+}
+
+inline void invert_spd(const double* M, int n, double* Minv) {
   double L[MAXV * MAXV];
-  std::memcpy(L, M, sizeof(double) * nv * nv);
-  llt_inplace(L, nv);
-  for (int i = 0; i < nv; ++i)
-    for (int j = 0; j < nv; ++j) w.Minv[i * nv + j] = (i == j) ? 1.0 : 0.0;
-  llt_solve(L, nv, w.Minv, nv);
+  std::memcpy(L, M, sizeof(double) * n * n);
+  llt_inplace(L, n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) Minv[i * n + j] = (i == j) ? 1.0 : 0.0;
+  llt_solve(L, n, Minv, n);
+}
+
+// world Jacobian columns, velocities/accelerations, M^-1, d(ddq)/d(q,v,tau).  aq (nv x nv), av, Minv in w.Minv.
+inline void aba_derivatives(const Model& m, Work& w, double* a_q, double* a_v) {
+  const int nv = m.nv;
+  world_kinematics(m, w);
+  for (int i = 0; i < m.nj; ++i) act_motion(w.oMi[i], w.agf[i], w.oa[i]);
+  double M[MAXV * MAXV], dq[MAXV * MAXV], dv[MAXV * MAXV];
+  rnea_partials(m, w, nullptr, -1, M, dq, dv);
+  // Minv by Cholesky; ddq_dq = -Minv dtau_dq etc. (computeABADerivatives)
+  invert_spd(M, nv, w.Minv);
   for (int i = 0; i < nv; ++i)
     for (int j = 0; j < nv; ++j) {
       double sq = 0, sv = 0;
@@ -527,6 +591,140 @@ inline void frame_jacobian(const Model& m, const Work& w, int f, const SE3& oMf,
   }
 }
 
+// ---- DifferentialActionModelContactFwdDynamics (one ContactModel3D / 6D, zero Baumgarte gains) ------------------------
+// calc: pinocchio::forwardDynamics(q, v, tau, Jc, a0, 0):  [M Jc^T; Jc 0] [a; -lambda] = [tau - h; -a0], with
+// Jc = the constrained rows of the LOCAL frame Jacobian and a0 = the constrained frame acceleration at zero joint
+// acceleration (3D: classical acceleration a.linear + w x v of the frame origin; 6D: the spatial acceleration).
+// Follows aba() on the same state: w.a holds the free acceleration on entry, the constrained one on exit.
+inline void contact_calc(const Model& m, const empc_contact_t& ct, const double* vq, Work& w) {
+  const int nv = m.nv, nc = (ct.type == EMPC_CONTACT_6D) ? 6 : 3;
+  const int jf = m.d->robot.frame_joint[ct.frame];
+  w.nc = nc; w.cframe = ct.frame;
+  world_kinematics(m, w);
+  // joint-space inertia and its inverse (world-frame composite rigid bodies)
+  {
+    double zero[MAXV] = {0};
+    world_accelerations(m, w, vq, zero, m.a0, w.oa);
+    double M[MAXV * MAXV], dq[MAXV * MAXV], dv[MAXV * MAXV];
+    rnea_partials(m, w, nullptr, -1, M, dq, dv);
+    invert_spd(M, nv, w.Minv);
+  }
+  frame_placement(m, w, ct.frame, w.oMf);
+  frame_jacobian(m, w, ct.frame, w.oMf, w.fJ);
+  // drift a0
+  double a0[6];
+  {
+    double zero[MAXV] = {0}, z6[6] = {0, 0, 0, 0, 0, 0}, oa[MAXJ][6], af[6];
+    world_accelerations(m, w, vq, zero, z6, oa);
+    actinv_motion(w.oMf, w.ov[jf], w.vf);
+    actinv_motion(w.oMf, oa[jf], af);
+    for (int k = 0; k < 6; ++k) a0[k] = af[k];
+    if (nc == 3) { double cr[3]; cross3(w.vf + 3, w.vf, cr); for (int k = 0; k < 3; ++k) a0[k] += cr[k]; }
+  }
+  // B = Minv Jc^T, G = Jc B
+  double G[36];
+  for (int i = 0; i < nv; ++i)
+    for (int r = 0; r < nc; ++r) {
+      double s = 0;
+      for (int k = 0; k < nv; ++k) s += w.Minv[i * nv + k] * w.fJ[r][k];
+      w.Bc[i][r] = s;
+    }
+  for (int r = 0; r < nc; ++r)
+    for (int c = 0; c < nc; ++c) {
+      double s = 0;
+      for (int i = 0; i < nv; ++i) s += w.fJ[r][i] * w.Bc[i][c];
+      G[r * nc + c] = s;
+    }
+  invert_spd(G, nc, w.Ginv);
+  // lambda = -G^-1 (Jc a_free + a0),  a = a_free + B lambda
+  double rhs[6];
+  for (int r = 0; r < nc; ++r) {
+    double s = a0[r];
+    for (int i = 0; i < nv; ++i) s += w.fJ[r][i] * w.a[i];
+    rhs[r] = s;
+  }
+  for (int r = 0; r < 6; ++r) w.lam[r] = 0;
+  for (int r = 0; r < nc; ++r) {
+    double s = 0;
+    for (int c = 0; c < nc; ++c) s += w.Ginv[r * nc + c] * rhs[c];
+    w.lam[r] = -s;
+  }
+  for (int i = 0; i < nv; ++i) {
+    double s = 0;
+    for (int r = 0; r < nc; ++r) s += w.Bc[i][r] * w.lam[r];
+    w.a[i] += s;
+  }
+}
+
+// calcDiff: implicit differentiation of the KKT system,
+//   [da; -dlambda] = -Kinv [d tau_rnea/dz (a and the local contact force held fixed); d alpha/dz (a held fixed)],
+//   Kinv = [[P, B Ginv], [Ginv B^T, -Ginv]],  P = Minv - B Ginv B^T  (getKKTContactDynamicMatrixInverse),
+// alpha = the constrained frame acceleration (ContactModel3D/6D::calcDiff: getJointAccelerationDerivatives, LOCAL).
+// Outputs a_q, a_v (nv x nv), P (nv x nv), lam_q, lam_v (nc x nv), GiBt = Ginv B^T (nc x nv).
+inline void contact_derivatives(const Model& m, Work& w, const double* vq, double* a_q, double* a_v, double* P,
+                                double* lam_q, double* lam_v, double* GiBt) {
+  const empc_robot_t& r = m.d->robot;
+  const int nv = m.nv, nc = w.nc, jf = r.frame_joint[w.cframe];
+  world_accelerations(m, w, vq, w.a, m.a0, w.oa);
+  double fl[6] = {w.lam[0], w.lam[1], w.lam[2], nc == 6 ? w.lam[3] : 0.0, nc == 6 ? w.lam[4] : 0.0, nc == 6 ? w.lam[5] : 0.0};
+  double Fw[6]; act_force(w.oMf, fl, Fw);
+  double M[MAXV * MAXV], dq[MAXV * MAXV], dv[MAXV * MAXV];
+  rnea_partials(m, w, Fw, jf, M, dq, dv);
+  // d alpha / dq, d alpha / dv
+  double dal_q[6][MAXV], dal_v[6][MAXV];
+  const double zero6[6] = {0, 0, 0, 0, 0, 0};
+  for (int c = 0; c < nv; ++c) {
+    const int i = m.joint_of_col[c], pi = r.parent[i];
+    if (!m.anc[i][jf]) { for (int k = 0; k < 6; ++k) { dal_q[k][c] = 0; dal_v[k][c] = 0; } continue; }
+    double s[6], Ap[6];
+    for (int k = 0; k < 6; ++k) { s[k] = w.J[k][c]; Ap[k] = pi >= 0 ? w.oa[pi][k] - m.a0[k] : 0.0; }
+    const double* Vp = pi >= 0 ? w.ov[pi] : zero6;
+    const double* Vd = w.ov[jf];
+    double dV[6], t1[6], t2[6], t3[6], aqw[6], vs[6], avw[6];
+    cross_mm(Vp, s, dV);
+    cross_mm(Ap, s, t1); cross_mm(Vp, dV, t2); cross_mm(dV, Vd, t3);
+    for (int k = 0; k < 6; ++k) { aqw[k] = t1[k] + t2[k] + t3[k]; vs[k] = w.ov[i][k] + Vp[k] - Vd[k]; }
+    cross_mm(vs, s, avw);
+    double vql[6], aql[6], avl[6], fJc[6];
+    actinv_motion(w.oMf, dV, vql); actinv_motion(w.oMf, aqw, aql); actinv_motion(w.oMf, avw, avl);
+    for (int k = 0; k < 6; ++k) fJc[k] = w.fJ[k][c];
+    if (nc == 3) {
+      double c1[3], c2[3], c3[3], c4[3];
+      cross3(vql + 3, w.vf, c1); cross3(w.vf + 3, vql, c2);
+      cross3(fJc + 3, w.vf, c3); cross3(w.vf + 3, fJc, c4);
+      for (int k = 0; k < 3; ++k) { dal_q[k][c] = aql[k] + c1[k] + c2[k]; dal_v[k][c] = avl[k] + c3[k] + c4[k]; }
+    } else {
+      for (int k = 0; k < 6; ++k) { dal_q[k][c] = aql[k]; dal_v[k][c] = avl[k]; }
+    }
+  }
+  for (int rr = 0; rr < nc; ++rr)
+    for (int i = 0; i < nv; ++i) {
+      double sacc = 0;
+      for (int c = 0; c < nc; ++c) sacc += w.Ginv[rr * nc + c] * w.Bc[i][c];
+      GiBt[rr * nv + i] = sacc;
+    }
+  for (int i = 0; i < nv; ++i)
+    for (int j = 0; j < nv; ++j) {
+      double sacc = w.Minv[i * nv + j];
+      for (int rr = 0; rr < nc; ++rr) sacc -= w.Bc[i][rr] * GiBt[rr * nv + j];
+      P[i * nv + j] = sacc;
+    }
+  for (int i = 0; i < nv; ++i)
+    for (int j = 0; j < nv; ++j) {
+      double sq = 0, sv = 0;
+      for (int k = 0; k < nv; ++k) { sq += P[i * nv + k] * dq[k * nv + j]; sv += P[i * nv + k] * dv[k * nv + j]; }
+      for (int rr = 0; rr < nc; ++rr) { sq += GiBt[rr * nv + i] * dal_q[rr][j]; sv += GiBt[rr * nv + i] * dal_v[rr][j]; }
+      a_q[i * nv + j] = -sq; a_v[i * nv + j] = -sv;
+    }
+  for (int rr = 0; rr < nc; ++rr)
+    for (int j = 0; j < nv; ++j) {
+      double sq = 0, sv = 0;
+      for (int k = 0; k < nv; ++k) { sq += GiBt[rr * nv + k] * dq[k * nv + j]; sv += GiBt[rr * nv + k] * dv[k * nv + j]; }
+      for (int c = 0; c < nc; ++c) { sq -= w.Ginv[rr * nc + c] * dal_q[c][j]; sv -= w.Ginv[rr * nc + c] * dal_v[c][j]; }
+      lam_q[rr * nv + j] = sq; lam_v[rr * nv + j] = sv;
+    }
+}
+
 // IntegratedActionModelEuler::calcDiff.  `tile` receives Fx|Fu|Lxx|Lxu|Luu|Lx|Lu (Model::o* offsets).
 // Must follow node_calc on the same (x,u) — crocoddyl's convention.
 inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Work& w, std::vector<CostEval>& evals,
@@ -535,7 +733,7 @@ inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Wo
   const int nv = m.nv, ndx = m.ndx, nu = m.nu, nr = m.nr;
   const double dt = m.dt, dt2 = dt * dt;
   for (int i = 0; i < m.tile; ++i) tile[i] = 0;
-  double* Fx = tile + m.oFx; double* Fu = tile + m.oFu; double* Lxx = tile + m.oLxx;
+  double* Fx = tile + m.oFx; double* Fu = tile + m.oFu; double* Lxx = tile + m.oLxx; double* Lxu = tile + m.oLxu;
   double* Luu = tile + m.oLuu; double* Lx = tile + m.oLx; double* Lu = tile + m.oLu;
   // squashing derivative
   for (int i = 0; i < nu; ++i) {
@@ -548,14 +746,32 @@ inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Wo
     }
   }
   double a_q[MAXV * MAXV], a_v[MAXV * MAXV], a_u[MAXV * MAXU];
-  aba_derivatives(m, w, a_q, a_v);
-  // Fu_cont = Minv * (A diag(ds)),  A = [tau_f 0; 0 I]
+  double lam_x[6 * MAXDX], lam_u[6 * MAXU];  // d lambda / d(q, v) (nc x ndx) and d lambda / du (nc x nu)
+  const double* Pm = w.Minv;                 // d a / d tau
+  double Pc[MAXV * MAXV], GiBt[6 * MAXV];
+  if (w.nc > 0) {
+    double lam_q[6 * MAXV], lam_v[6 * MAXV];
+    contact_derivatives(m, w, w.x + m.nq, a_q, a_v, Pc, lam_q, lam_v, GiBt);
+    Pm = Pc;
+    for (int r = 0; r < w.nc; ++r)
+      for (int j = 0; j < nv; ++j) { lam_x[r * ndx + j] = lam_q[r * nv + j]; lam_x[r * ndx + nv + j] = lam_v[r * nv + j]; }
+  } else {
+    aba_derivatives(m, w, a_q, a_v);
+  }
+  // Fu_cont = (d a / d tau) * (A diag(ds)),  A = [tau_f 0; 0 I];  d lambda / du = -Ginv B^T A diag(ds)
   for (int i = 0; i < nv; ++i)
     for (int j = 0; j < nu; ++j) {
       double s = 0;
-      if (j < nr) { for (int k = 0; k < 6; ++k) s += w.Minv[i * nv + k] * (d.tau_f[k * nr + j] * w.ds[j]); }
-      else s = w.Minv[i * nv + 6 + (j - nr)] * w.ds[j];
+      if (j < nr) { for (int k = 0; k < 6; ++k) s += Pm[i * nv + k] * (d.tau_f[k * nr + j] * w.ds[j]); }
+      else s = Pm[i * nv + 6 + (j - nr)] * w.ds[j];
       a_u[i * nu + j] = s;
+    }
+  for (int r = 0; r < w.nc; ++r)
+    for (int j = 0; j < nu; ++j) {
+      double s = 0;
+      if (j < nr) { for (int k = 0; k < 6; ++k) s += GiBt[r * nv + k] * (d.tau_f[k * nr + j] * w.ds[j]); }
+      else s = GiBt[r * nv + 6 + (j - nr)] * w.ds[j];
+      lam_u[r * nu + j] = -s;
     }
   // Euler: discrete Jacobians before the Lie-group transport
   for (int i = 0; i < nv; ++i) {
@@ -622,6 +838,41 @@ inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Wo
       case EMPC_COST_SQUASH_BARRIER:
         for (int i = 0; i < nu; ++i) { Lu[i] += wt * e.Ar[i]; Luu[i * nu + i] += wt * e.Arr[i]; }
         break;
+      case EMPC_COST_CONTACT_FRICTION_CONE: {
+        // Rx = A df/dx, Ru = A df/du (ResidualModelContactFrictionCone::calcDiff); the only cost that couples x and u
+        if (w.nc == 0) break;
+        const double* A = d.pool + cs.ref_off;
+        double Rx[5][MAXDX], Ru[5][MAXU];
+        for (int a = 0; a < 5; ++a) {
+          for (int b = 0; b < ndx; ++b) Rx[a][b] = A[3 * a] * lam_x[b] + A[3 * a + 1] * lam_x[ndx + b] + A[3 * a + 2] * lam_x[2 * ndx + b];
+          for (int b = 0; b < nu; ++b) Ru[a][b] = A[3 * a] * lam_u[b] + A[3 * a + 1] * lam_u[nu + b] + A[3 * a + 2] * lam_u[2 * nu + b];
+        }
+        for (int i = 0; i < ndx; ++i) {
+          double s = 0;
+          for (int k = 0; k < 5; ++k) s += Rx[k][i] * e.Ar[k];
+          Lx[i] += wt * s;
+          for (int j = 0; j < ndx; ++j) {
+            double h = 0;
+            for (int k = 0; k < 5; ++k) h += Rx[k][i] * (e.Arr[k] * Rx[k][j]);
+            Lxx[i * ndx + j] += wt * h;
+          }
+          for (int j = 0; j < nu; ++j) {
+            double h = 0;
+            for (int k = 0; k < 5; ++k) h += Rx[k][i] * (e.Arr[k] * Ru[k][j]);
+            Lxu[i * nu + j] += wt * h;
+          }
+        }
+        for (int i = 0; i < nu; ++i) {
+          double s = 0;
+          for (int k = 0; k < 5; ++k) s += Ru[k][i] * e.Ar[k];
+          Lu[i] += wt * s;
+          for (int j = 0; j < nu; ++j) {
+            double h = 0;
+            for (int k = 0; k < 5; ++k) h += Ru[k][i] * (e.Arr[k] * Ru[k][j]);
+            Luu[i * nu + j] += wt * h;
+          }
+        }
+      } break;
       default: {
         // frame costs: Rx = [Rq (nr x nv), Rv (nr x nv)]
         const int f = cs.frame, n = residual_dim(m, cs.type);
@@ -672,8 +923,9 @@ inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Wo
       } break;
     }
   }
-  // Euler scales the cost derivatives by dt (Lxu stays zero: no cost couples x and u)
+  // Euler scales the cost derivatives by dt (Lxu is zero unless the node has a contact-force cost)
   for (int i = 0; i < ndx * ndx; ++i) Lxx[i] *= dt;
+  for (int i = 0; i < ndx * nu; ++i) Lxu[i] *= dt;
   for (int i = 0; i < nu * nu; ++i) Luu[i] *= dt;
   for (int i = 0; i < ndx; ++i) Lx[i] *= dt;
   for (int i = 0; i < nu; ++i) Lu[i] *= dt;

@@ -254,14 +254,62 @@ class Robot:
                 frc[par] = frc[par] + np.concatenate([f, n + np.cross(p, f)])
         return tau, vel
 
-    def forward_dynamics(self, q, v, tau):
+    def mass_and_bias(self, q, v):
         z = np.zeros(self.nv)
         h, vel = self.rnea(q, v, z)
         M = np.zeros((self.nv, self.nv), dtype=np.result_type(q, float))
         for k in range(self.nv):
             e = np.zeros(self.nv); e[k] = 1.0
             M[:, k] = self.rnea(q, z, e, gravity=False)[0]
+        return M, h, vel
+
+    def forward_dynamics(self, q, v, tau):
+        M, h, vel = self.mass_and_bias(q, v)
         return np.linalg.solve(M, tau - h), vel
+
+    def frame_motion(self, frame, q, v, a):
+        """LOCAL spatial velocity and (gravity-free) spatial acceleration of an operational frame, [lin; ang], for joint
+        velocities v and accelerations a: the kinematic half of the body-coordinate recursion, then jMf.actInv"""
+        T = self.joint_transforms(q)
+        ct = np.result_type(q, v, a, float)
+        vel, acc = [None] * self.nj, [None] * self.nj
+        for i in range(self.nj):
+            R, p = T[i]
+            if i == 0:
+                vel[0] = v[0:6].astype(ct); acc[0] = a[0:6].astype(ct)   # v x v = 0
+                continue
+            vp, ap = vel[self.parent[i]], acc[self.parent[i]]
+            S = np.concatenate([np.zeros(3), self.axis[i]])
+            vi = np.concatenate([R.T @ (vp[:3] - np.cross(p, vp[3:])), R.T @ vp[3:]])
+            ai = np.concatenate([R.T @ (ap[:3] - np.cross(p, ap[3:])), R.T @ ap[3:]])
+            vel[i] = vi + S * v[5 + i]
+            vx, sq = vel[i], S * v[5 + i]
+            acc[i] = ai + S * a[5 + i] + np.concatenate([np.cross(vx[3:], sq[:3]) + np.cross(vx[:3], sq[3:]), np.cross(vx[3:], sq[3:])])
+        j, Rf, pf = self.frames[frame]
+        to_f = lambda m: np.concatenate([Rf.T @ (m[:3] - np.cross(pf, m[3:])), Rf.T @ m[3:]])
+        return to_f(vel[j]), to_f(acc[j])
+
+    def contact_acceleration(self, contact, q, v, a):
+        """what the contact constrains to zero (crocoddyl ContactModel3D / 6D, zero gains): the classical linear
+        acceleration of the frame origin in LOCAL coordinates (3D), the LOCAL spatial acceleration (6D)"""
+        vf, af = self.frame_motion(contact["frame"], q, v, a)
+        if contact["type"] == "ContactModel3D":
+            return af[:3] + np.cross(vf[3:], vf[:3])
+        return af
+
+    def contact_dynamics(self, contact, q, v, tau):
+        """pinocchio::forwardDynamics(q, v, tau, Jc, a0, 0): [M Jc^T; Jc 0] [a; -lambda] = [tau - h; -a0]"""
+        M, h, vel = self.mass_and_bias(q, v)
+        z = np.zeros(self.nv)
+        a0 = self.contact_acceleration(contact, q, v, z)
+        nc = a0.size
+        Jc = np.zeros((nc, self.nv), dtype=M.dtype)
+        for k in range(self.nv):   # the constrained acceleration is affine in a
+            e = np.zeros(self.nv); e[k] = 1.0
+            Jc[:, k] = self.contact_acceleration(contact, q, v, e) - a0
+        K = np.block([[M, Jc.T], [Jc, np.zeros((nc, nc))]])
+        sol = np.linalg.solve(K, np.concatenate([tau - h, -a0]))
+        return sol[:self.nv], -sol[self.nv:], vel
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -289,7 +337,8 @@ def diff(rob, x0, x1):
 # Problem front-end: YAML -> platform, stages, cost tables, knot layout
 
 COST_DIM = {"CostModelState": None, "CostModelControl": None, "CostModelFramePlacement": 6, "CostModelFrameRotation": 3,
-            "CostModelFrameVelocity": 6, "CostModelFrameTranslation": 3}
+            "CostModelFrameVelocity": 6, "CostModelFrameTranslation": 3, "CostModelContactFrictionCone": 5}
+BIG = np.finfo(float).max   # crocoddyl::FrictionCone's "infinite" bound
 
 
 def _vec(v):
@@ -329,6 +378,15 @@ class Problem:
             costs = {}
             for c in st["costs"]:
                 costs[c["name"]] = self._cost(c)
+            # src/stage.cpp:38-47, src/factory/contacts.cpp:32-81 (one contact per stage in the corpus)
+            contacts = st.get("contacts") or []
+            assert len(contacts) <= 1, "the twin handles one contact per stage"
+            contact = None
+            for c in contacts:
+                assert c["link_name"] in self.rob.frames, "Link " + c["link_name"] + " does not exist"
+                gains = _vec(c["gains"]) if "gains" in c else np.zeros(2)
+                assert not gains.any(), "Baumgarte gains: not restated in the twin"
+                contact = {"type": c["type"], "frame": c["link_name"]}
             # knot rule, src/trajectory.cpp:117-127 (integer division)
             dur = int(st["duration"])
             if dur // dt_ms == 0 and si + 1 < len(doc["stages"]):
@@ -341,7 +399,7 @@ class Problem:
             # stage, src/trajectory.cpp:134: a last stage without running knots is the terminal model only and has none)
             if n_knots > 0:
                 costs["barrier"] = {"type": "Barrier", "weight": barrier_weight, "active": True}
-            self.stages.append({"name": st["name"], "duration": dur, "costs": dict(sorted(costs.items()))})
+            self.stages.append({"name": st["name"], "duration": dur, "costs": dict(sorted(costs.items())), "contact": contact})
         self.T = len(node_stage)
         self.node_stage = node_stage + [len(self.stages) - 1]   # terminal model = the last stage's model (:135)
 
@@ -355,6 +413,28 @@ class Problem:
         elif t == "CostModelControl":
             nr = self.nu
             out["ref"] = _vec(c["reference"]) if "reference" in c else np.zeros(self.nu)
+        elif t == "CostModelContactFrictionCone":
+            # crocoddyl::FrictionCone(n_surf, mu, nf = 4, inner_appr = false) (src/factory/cost.cpp:149-167): rows
+            # (-mu z +- t_i)^T c_R_o for the nf/2 tangents t_i, then n_surf^T; bounds (-inf, 0] and [0, +inf)
+            nr = 5
+            n = _vec(c["n_surf"]); n = n / np.linalg.norm(n)
+            mu = float(c["mu"])
+            z = np.array([0.0, 0.0, 1.0])
+            ax = np.cross(n, z)   # rotation taking n_surf onto z (Quaternion::FromTwoVectors)
+            sn, cs = np.linalg.norm(ax), n @ z
+            cRo = np.eye(3) if sn < 1e-12 else exp3(ax / sn * np.arctan2(sn, cs))
+            A = np.zeros((5, 3))
+            for i in range(2):
+                th = 2 * np.pi * i / 4
+                ts = np.array([np.cos(th), np.sin(th), 0.0])
+                A[2 * i] = (-mu * z + ts) @ cRo
+                A[2 * i + 1] = (-mu * z - ts) @ cRo
+            A[4] = n
+            out["A"] = A
+            out["frame"] = c["link_name"]
+            out["act"] = "ActivationModelQuadraticBarrier"
+            out["lb"] = np.array([-BIG] * 4 + [0.0]); out["ub"] = np.array([0.0] * 4 + [BIG])
+            return out
         else:
             nr = COST_DIM[t]
             out["frame"] = c["link_name"]
@@ -381,12 +461,26 @@ class Problem:
         a = (smooth * (self.u_ub - self.u_lb)) ** 2
         return 0.5 * (np.sqrt((u - self.u_lb) ** 2 + a) - np.sqrt((u - self.u_ub) ** 2 + a) + self.u_lb + self.u_ub)
 
+    def dynamics(self, stage, x, u, smooth):
+        """(joint accelerations, contact force or None): DifferentialActionModelFreeFwdDynamics, or
+        DifferentialActionModelContactFwdDynamics for a stage with a contact (src/factory/diff-action.cpp:30-35)"""
+        rob = self.rob
+        q, v = x[:rob.nq], x[rob.nq:]
+        s = self.squash(u, smooth)
+        tau = np.concatenate([self.tau_f @ s[:self.nr], s[self.nr:]])
+        contact = self.stages[stage]["contact"]
+        if contact is None:
+            return rob.forward_dynamics(q, v, tau)[0], None
+        a, lam, _ = rob.contact_dynamics(contact, q, v, tau)
+        return a, lam
+
     def residuals(self, stage, x, u, smooth):
         """[(name, weight, r, activation dict)] of the active costs of the stage, in the reference's iteration order"""
         rob = self.rob
         q, v = x[:rob.nq], x[rob.nq:]
         oM = None
         out = []
+        lam = None
         for name, c in self.stages[stage]["costs"].items():
             if not c["active"]:
                 continue
@@ -400,6 +494,11 @@ class Problem:
                 r = diff(rob, c["ref"].astype(x.dtype), x)
             elif t == "CostModelControl":
                 r = u - c["ref"]
+            elif t == "CostModelContactFrictionCone":   # r = A f, f the contact force in the contact frame
+                if lam is None:
+                    lam = self.dynamics(stage, x, u, smooth)[1]
+                assert lam is not None and self.stages[stage]["contact"]["frame"] == c["frame"]
+                r = c["A"] @ lam[:3]
             else:
                 if oM is None:
                     oM = rob.world_placements(q)
@@ -440,10 +539,8 @@ class Problem:
         rob = self.rob
         if terminal:
             u = np.zeros(self.nu, dtype=x.dtype)
-        q, v = x[:rob.nq], x[rob.nq:]
-        s = self.squash(u, smooth)
-        tau = np.concatenate([self.tau_f @ s[:self.nr], s[self.nr:]])
-        a, _ = rob.forward_dynamics(q, v, tau)
+        v = x[rob.nq:]
+        a, _lam = self.dynamics(stage, x, u, smooth)
         dx = np.concatenate([v * self.dt + a * self.dt ** 2, a * self.dt])
         cost = 0
         for _name, w, r, c in self.residuals(stage, x, u, smooth):

