@@ -118,7 +118,9 @@ EMPC_DI void acc_zero(double (&acc)[MT_][NT_][2]) {
 // column swizzle of the LD = 24 matrices: element (r, c) lives at r * 24 + (c ^ bw_swz(r))
 EMPC_DI constexpr int bw_swz(int r) { return (r & 2) << 1; }
 
-template <class D>
+// COUPLED: some cost set holds a contact-force cost, the only kind that couples x and u (contact.cuh): its nodes add the
+// Lxu block and the off-diagonal part of Luu that every other node leaves at zero
+template <class D, bool COUPLED = false>
 __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_kernel(Buffers bf, BwParams P) {
   using S = BwCfg<D>;
   constexpr int n = S::n, m = S::m, LD = S::LD, LM = S::LM, PW = S::PW;
@@ -363,6 +365,14 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
             }
       }
       __syncwarp();
+      if (COUPLED) {
+        if (bf.ct.costset_coupled[bf.node_costset[(size_t)bf.ocp_map[b] * T1 + t]]) {  // warp-uniform
+          const double* tg = bf.tiles + (nb + t) * D::TILE;
+          for (int e = lane; e < n * m; e += 32) { const int i = e / m, cu = e - i * m; sQux[cu * LD + (i ^ bw_swz(cu))] += tg[D::oLxu + e]; }
+          for (int e = lane; e < m * m; e += 32) { const int r = e / m, c = e - r * m; if (r != c) sQuu[r * LM + c] += tg[D::oLuu + e]; }
+          __syncwarp();
+        }
+      }
       EMPC_BW_MARK(2);
       // Fx, Fu of this node are dead: the next node's fragments travel HBM -> registers while Quu is factorised
       if (t > 0) { load_F(t - 1); load_Lxx(t - 1); load_L(t - 1, pre, pre_fs); }

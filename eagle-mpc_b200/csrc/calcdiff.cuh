@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(128, EMPC_NCOST_BLOCKS) node_cost_kernel(Buffe
     const int c0 = bf.ct.costset_begin[costset], c1 = bf.ct.costset_begin[costset + 1];
     for (int c = c0; c < c1; ++c) {
       const empc_cost_t cs = bf.ct.costs[c];
-      if (!cs.active) continue;
+      if (!cs.active || cs.type == EMPC_COST_CONTACT_FRICTION_CONE) continue;  // (contact nodes: contact_node_kernel)
       const double wt = cs.weight;
       if (is_frame_cost(cs.type)) {  // value here, derivatives in node_diff_kernel
         csum += wt * frame_cost_value<D>(M, bf.ct, cs, smooth, x);
@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(DiffCfg<D>::THREADS, DiffCfg<D>::MINB) node_di
       for (int c = c0; c < c1; ++c) {
         const empc_cost_t cs = bf.ct.costs[c];
         if (!cs.active) continue;
-        if (cs.type == EMPC_COST_STATE || cs.type == EMPC_COST_CONTROL || cs.type == EMPC_COST_SQUASH_BARRIER) continue;
+        if (!is_frame_cost(cs.type)) continue;
         double r[NDX], Ar[NDX], Arr[NDX];
         SE3 rMf;
         cost_eval<D>(M, bf.ct, cs, smooth, nullptr, nullptr, nd, r, Ar, Arr, rMf);

@@ -62,6 +62,8 @@ struct Buffers {
 // ---------------------------------------------------------------------------------------------------------------------
 #include "calcdiff.cuh"
 
+#include "contact.cuh"
+
 #include "backward.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -112,7 +114,7 @@ __device__ __forceinline__ void end_inner_solve(OcpState& st, const empc_solver_
 // :348-368); for each one whose rollout succeeded the block evaluates the node costs of that trial trajectory in parallel
 // (thread per node), thread 0 adds them in node order (cost_try_) and applies the acceptance test — and the loop stops at
 // the first accepted step, so the costs of the later, speculative rollouts are never computed.
-template <class D>
+template <class D, bool CONTACT = false>
 __global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams dp, const __grid_constant__ DevModel M) {
   constexpr int NX = D::NX, NU = D::NU;
   constexpr int CH = 512;  // nodes per chunk of the ordered cost sum
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams
 #pragma unroll
               for (int i = 0; i < NU; ++i) u[i] = 0.0;
             }
-            s_cost[tt] = node_cost_value<D>(M, bf.ct, costsets[t], smooth, x, u);
+            s_cost[tt] = node_cost_value<D, CONTACT>(M, bf.ct, costsets[t], smooth, x, u);
           }
           __syncthreads();
           if (tid == 0) for (int i = 0; i < cnt; ++i) cost_try += s_cost[i];

@@ -36,6 +36,10 @@ struct CostTables {
   const empc_cost_t* costs;
   const double* pool;
   const int* costset_begin;
+  // contact dynamics (contact.cuh); all null for a problem without contacts
+  const empc_contact_t* contacts;
+  const int* costset_contact;             // per cost set: contact of the model that owns it, -1 = free dynamics
+  const unsigned char* costset_coupled;   // per cost set: holds a contact-force cost (Lxu and a full Luu exist)
 };
 
 template <int NA_, int NR_>
@@ -509,7 +513,7 @@ EMPC_DI void node_calc(const DevModel& M, const CostTables& C, int costset, doub
   const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
   for (int c = c0; c < c1; ++c) {
     const empc_cost_t cs = C.costs[c];
-    if (!cs.active) continue;
+    if (!cs.active || cs.type == EMPC_COST_CONTACT_FRICTION_CONE) continue;
     double r[D::NDX], Ar[D::NDX], Arr[D::NDX];
     SE3 rMf;
     csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
@@ -563,11 +567,26 @@ __device__ __noinline__ double frame_cost_value(const DevModel& M, const CostTab
   SE3 rMf;
   return cost_eval<D>(M, C, cs, smooth, x, nullptr, nd, r, Ar, Arr, rMf);
 }
-EMPC_DI bool is_frame_cost(int type) { return type != EMPC_COST_STATE && type != EMPC_COST_CONTROL && type != EMPC_COST_SQUASH_BARRIER; }
+EMPC_DI bool is_frame_cost(int type) { return type >= EMPC_COST_FRAME_PLACEMENT && type <= EMPC_COST_FRAME_TRANSLATION; }
+
+// contact.cuh: contact force at (x, u) of a node under contact dynamics
+template <class D>
+__device__ __noinline__ void contact_force(const DevModel& M, const empc_contact_t* ctp, double smooth, const double* x, const double* u,
+                                           double* lam);
+// value (and activation derivatives) of the friction-cone cost: activation(A f) with the quadratic barrier the factory
+// attaches (src/factory/cost.cpp:149-167); f = contact force in contact-frame coordinates
+EMPC_DI double friction_cone_eval(const CostTables& C, const empc_cost_t& cs, const double* lam, double* r, double* Ar, double* Arr) {
+  const double* A = C.pool + cs.ref_off;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) r[i] = A[3 * i] * lam[0] + A[3 * i + 1] * lam[1] + A[3 * i + 2] * lam[2];
+  return activation<5>(cs.activation, r, C.pool + cs.w_off, C.pool + cs.lb_off, C.pool + cs.ub_off, Ar, Arr);
+}
 
 // Cost half: dt * sum_c w_c a_c(r_c(x, u)) in the reference's cost order; needs the kinematics only when the cost set
 // holds frame costs.
-template <class D>
+// CONTACT: the problem has contact stages, so a cost set may hold a friction-cone cost (its residual needs the contact
+// solve at (x, u): a call the other instantiation does not carry)
+template <class D, bool CONTACT = false>
 EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x, const double* u) {
   const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
   double csum = 0;
@@ -578,6 +597,16 @@ EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costs
     if (!cs.active) continue;
     if (is_frame_cost(cs.type)) { csum += cs.weight * frame_cost_value<D>(M, C, cs, smooth, x); continue; }
     double Ar[D::NDX], Arr[D::NDX];
+    if (!CONTACT && cs.type == EMPC_COST_CONTACT_FRICTION_CONE) continue;  // (empc_create refuses it without a contact)
+    if (CONTACT && cs.type == EMPC_COST_CONTACT_FRICTION_CONE) {  // needs the contact force: the contact solve at (x, u)
+      const int ci = C.costset_contact ? C.costset_contact[costset] : -1;
+      if (ci >= 0) {
+        double lam[6], r5[5];
+        contact_force<D>(M, C.contacts + ci, smooth, x, u, lam);
+        csum += cs.weight * friction_cone_eval(C, cs, lam, r5, Ar, Arr);
+      }
+      continue;
+    }
     if (cs.type == EMPC_COST_STATE) {
       const double* ref = C.pool + cs.ref_off;
       bool same = g_open;

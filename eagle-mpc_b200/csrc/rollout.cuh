@@ -45,7 +45,8 @@ struct RoCfg {
   static constexpr int SMEM_DOUBLES = 2 * OCPS * STAGE;
 };
 
-template <class D, int W>
+// CONTACT: the problem has contact stages; the nodes of those stages integrate the contact dynamics (contact.cuh)
+template <class D, int W, bool CONTACT = false>
 __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, const __grid_constant__ DevModel M) {
   constexpr int NX = D::NX, NDX = D::NDX, NU = D::NU;
   using S = RoCfg<D, W>;
@@ -172,7 +173,13 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
           u[i] = in[S::oUs + i] - in[S::oKk + i] * alpha - kd;
           __stcs(us_try + (size_t)t * NU + i, u[i]);
         }
-        node_dyn<D, true>(M, smooth, xt, u, xn);
+        if (CONTACT) {
+          const int ci = bf.ct.costset_contact[bf.node_costset[(size_t)bf.ocp_map[b] * T1 + t]];
+          if (ci >= 0) node_dyn_contact<D>(M, bf.ct.contacts + ci, smooth, xt, u, xn);
+          else node_dyn<D, true>(M, smooth, xt, u, xn);
+        } else {
+          node_dyn<D, true>(M, smooth, xt, u, xn);
+        }
         int worst = -1;  // raiseIfNaN(xnext.lpNorm<Infinity>()): integer test on the high words (node.cuh: raise_bits)
 #pragma unroll
         for (int i = 0; i < NX; ++i) worst = max(worst, raise_bits(xn[i]));
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Node costs of the trial trajectories: one thread per (OCP, step length of this stage, node).
-template <class D>
+template <class D, bool CONTACT = false>
 __global__ void __launch_bounds__(128, 4) trial_cost_kernel(Buffers bf, RoParams P, int width, const __grid_constant__ DevModel M) {
   constexpr int NX = D::NX, NU = D::NU;
   const int T = bf.T, T1 = T + 1;
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(128, 4) trial_cost_kernel(Buffers bf, RoParams
     for (int i = 0; i < NU; ++i) u[i] = 0.0;
   }
   const int costset = bf.node_costset[(size_t)bf.ocp_map[b] * T1 + t];
-  bf.trial_node_cost[trial * T1 + t] = node_cost_value<D>(M, bf.ct, costset, smooth, x, u);
+  bf.trial_node_cost[trial * T1 + t] = node_cost_value<D, CONTACT>(M, bf.ct, costset, smooth, x, u);
 }
 
 // cost_try = sum of the node costs in node order (one warp per trial: coalesced loads, lane 0 adds in order)

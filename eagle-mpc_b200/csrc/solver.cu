@@ -55,6 +55,9 @@ struct empc_solver {
   double *d_plant_x = nullptr, *d_plant_u = nullptr, *d_plant_xn = nullptr; size_t cap_plant = 0;
   int n_ref = 0, dt_ref_ms = 0;
   long long* d_times = nullptr;   // n_node_maps controller times
+  // contact dynamics (contact.cuh): has_contact = some cost set's model carries a contact; has_coupled = some cost set
+  // holds a contact-force cost (backward_kernel<D, true>)
+  bool has_contact = false, has_coupled = false;
   int width_a = RO_WIDTH_A;  // stage-A width of the line search (rollout.cuh)
   // small batches (one wave of node_calc_kernel or less): node_cost_kernel runs beside node_calc_kernel on a second stream
   cudaStream_t side_stream = nullptr;
@@ -104,6 +107,13 @@ static cudaError_t dreuse(empc_solver* h, Tp** p, size_t* cap, size_t n) {
 }
 
 // ---- (NA, NR) dispatch: one instantiation per eagle-mpc platform family ---------------------------------------------
+#ifdef EMPC_DEBUG_ONLY_ARM3  /* development builds: one platform family, a quarter of the compile time */
+#define EMPC_DISPATCH(h, CALL)                                               \
+  do {                                                                       \
+    if ((h)->na == 3 && (h)->nr == 6) { using D = Dim<3, 6>; CALL; }         \
+    else return fail(EMPC_ERR_UNSUPPORTED, "debug build: flying_arm_3 only");                              \
+  } while (0)
+#else
 #define EMPC_DISPATCH(h, CALL)                                               \
   do {                                                                       \
     if ((h)->na == 0 && (h)->nr == 4) { using D = Dim<0, 4>; CALL; }         \
@@ -113,6 +123,7 @@ static cudaError_t dreuse(empc_solver* h, Tp** p, size_t* cap, size_t n) {
     else if ((h)->na == 5 && (h)->nr == 6) { using D = Dim<5, 6>; CALL; }    \
     else return fail(EMPC_ERR_UNSUPPORTED, "unsupported (arm joints, rotors) combination");                \
   } while (0)
+#endif
 
 static int packet_doubles(int na, int nr) {
   int out = 0;
@@ -137,9 +148,12 @@ template <class D>
 static cudaError_t set_kernel_attributes() {
   cudaError_t e;
   if ((e = opt_in_smem(node_diff_kernel<D>, sizeof(double) * DiffCfg<D>::SMEM_DOUBLES)) != cudaSuccess) return e;
-  if ((e = opt_in_smem(backward_kernel<D>, sizeof(double) * BwCfg<D>::TOTAL)) != cudaSuccess) return e;
-  if ((e = opt_in_smem(rollout_kernel<D, RO_WIDTH_A>, sizeof(double) * RoCfg<D, RO_WIDTH_A>::SMEM_DOUBLES)) != cudaSuccess) return e;
-  return opt_in_smem(rollout_kernel<D, 8>, sizeof(double) * RoCfg<D, 8>::SMEM_DOUBLES);
+  if ((e = opt_in_smem(backward_kernel<D, false>, sizeof(double) * BwCfg<D>::TOTAL)) != cudaSuccess) return e;
+  if ((e = opt_in_smem(backward_kernel<D, true>, sizeof(double) * BwCfg<D>::TOTAL)) != cudaSuccess) return e;
+  if ((e = opt_in_smem(rollout_kernel<D, RO_WIDTH_A, false>, sizeof(double) * RoCfg<D, RO_WIDTH_A>::SMEM_DOUBLES)) != cudaSuccess) return e;
+  if ((e = opt_in_smem(rollout_kernel<D, RO_WIDTH_A, true>, sizeof(double) * RoCfg<D, RO_WIDTH_A>::SMEM_DOUBLES)) != cudaSuccess) return e;
+  if ((e = opt_in_smem(rollout_kernel<D, 8, true>, sizeof(double) * RoCfg<D, 8>::SMEM_DOUBLES)) != cudaSuccess) return e;
+  return opt_in_smem(rollout_kernel<D, 8, false>, sizeof(double) * RoCfg<D, 8>::SMEM_DOUBLES);
 }
 
 static void inertia_matrix(double m, const double* c, const double* Ic, double* Y) {
@@ -201,6 +215,31 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
     if (r.parent[i] != i - 1) return fail(EMPC_ERR_UNSUPPORTED, "device path supports serial-chain arms only");
   if (!supported(r.n_joints - 1, d->n_rotors)) return fail(EMPC_ERR_UNSUPPORTED, "unsupported (arm joints, rotors) combination");
   if (d->T < 1 || d->n_node_maps < 1) return fail(EMPC_ERR_INVALID, "bad horizon / node maps");
+  // contact dynamics: one ContactModel3D / 6D per cost set, zero Baumgarte gains; a friction-cone cost needs the contact
+  // of its own cost set, on the same frame
+  std::vector<unsigned char> coupled((size_t)std::max(1, d->n_costsets), 0);
+  bool any_contact = false, any_coupled = false;
+  if (d->n_contacts > 0) {
+    if (!d->contacts || !d->costset_contact) return fail(EMPC_ERR_INVALID, "n_contacts > 0 without contact tables");
+    for (int c = 0; c < d->n_contacts; ++c) {
+      const empc_contact_t& ct = d->contacts[c];
+      if (ct.type != EMPC_CONTACT_3D && ct.type != EMPC_CONTACT_6D) return fail(EMPC_ERR_INVALID, "bad contact type");
+      if (ct.frame < 0 || ct.frame >= r.n_frames) return fail(EMPC_ERR_INVALID, "contact frame out of range");
+      if (ct.gains[0] != 0.0 || ct.gains[1] != 0.0) return fail(EMPC_ERR_UNSUPPORTED, "non-zero contact gains are not supported");
+    }
+    for (int cs = 0; cs < d->n_costsets; ++cs) {
+      if (d->costset_contact[cs] >= d->n_contacts) return fail(EMPC_ERR_INVALID, "costset_contact out of range");
+      if (d->costset_contact[cs] >= 0) any_contact = true;
+    }
+  }
+  for (int cs = 0; cs < d->n_costsets; ++cs)
+    for (int c = d->costset_begin[cs]; c < d->costset_begin[cs + 1]; ++c)
+      if (d->costs[c].type == EMPC_COST_CONTACT_FRICTION_CONE) {
+        const int ci = (d->n_contacts > 0) ? d->costset_contact[cs] : -1;
+        if (ci < 0 || d->contacts[ci].frame != d->costs[c].frame)
+          return fail(EMPC_ERR_INVALID, "a friction-cone cost needs a contact on the same frame in its cost set");
+        coupled[(size_t)cs] = 1; any_coupled = true;
+      }
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(EMPC_ERR_CUDA, "no such CUDA device");
@@ -215,6 +254,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   h->width_a = ((long long)batch * RO_WIDTH_A_SMALL <= 32LL * 148 * 4) ? RO_WIDTH_A_SMALL : RO_WIDTH_A;
   if (const char* e = std::getenv("EMPC_RO_WIDTH_A")) { const int w = std::atoi(e); if (w == RO_WIDTH_A || w == RO_WIDTH_A_SMALL) h->width_a = w; }
   h->n_costs = d->n_costs; h->n_pool = d->n_pool; h->n_node_maps = d->n_node_maps; h->n_costsets = d->n_costsets;
+  h->has_contact = any_contact; h->has_coupled = any_coupled;
 
   DevModel& M = h->hmodel;
   std::memset(&M, 0, sizeof(M));
@@ -249,7 +289,11 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) {
 #define EMPC_ATTR(NA_, NR_) if (h->na == NA_ && h->nr == NR_) e = set_kernel_attributes<Dim<NA_, NR_>>();
+#ifdef EMPC_DEBUG_ONLY_ARM3
+    EMPC_ATTR(3, 6)
+#else
     EMPC_ATTR(0, 4) EMPC_ATTR(0, 6) EMPC_ATTR(2, 6) EMPC_ATTR(3, 6) EMPC_ATTR(5, 6)
+#endif
 #undef EMPC_ATTR
   }
   if (e != cudaSuccess) { std::string m_ = cudaGetErrorString(e); empc_destroy(h); return fail(EMPC_ERR_CUDA, m_); }
@@ -314,6 +358,16 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   if (d->n_pool) CKH(cudaMemcpyAsync(h->d_pool, d->pool, sizeof(double) * d->n_pool, cudaMemcpyHostToDevice, h->stream));
   CKH(cudaMemcpyAsync(h->d_costset_begin, d->costset_begin, sizeof(int) * (d->n_costsets + 1), cudaMemcpyHostToDevice, h->stream));
   CKH(cudaMemcpyAsync(h->d_node_costset, d->node_costset, sizeof(int) * d->n_node_maps * T1, cudaMemcpyHostToDevice, h->stream));
+  if (any_contact) {
+    empc_contact_t* d_contacts = nullptr; int* d_cc = nullptr; unsigned char* d_cpl = nullptr;
+    CKH(dalloc(h, &d_contacts, (size_t)d->n_contacts));
+    CKH(dalloc(h, &d_cc, (size_t)d->n_costsets));
+    CKH(dalloc(h, &d_cpl, (size_t)d->n_costsets));
+    CKH(cudaMemcpyAsync(d_contacts, d->contacts, sizeof(empc_contact_t) * d->n_contacts, cudaMemcpyHostToDevice, h->stream));
+    CKH(cudaMemcpyAsync(d_cc, d->costset_contact, sizeof(int) * d->n_costsets, cudaMemcpyHostToDevice, h->stream));
+    CKH(cudaMemcpyAsync(d_cpl, coupled.data(), (size_t)d->n_costsets, cudaMemcpyHostToDevice, h->stream));
+    bf.ct.contacts = d_contacts; bf.ct.costset_contact = d_cc; bf.ct.costset_coupled = d_cpl;
+  }
   CKH(cudaStreamSynchronize(h->stream));
   // default x0 / candidate: state.zero()
   {
@@ -414,6 +468,7 @@ int empc_replicate_instances(empc_solver_t* h, int32_t n) {
   if (!h) return fail(EMPC_ERR_INVALID, "null");
   if (n < 1) return fail(EMPC_ERR_INVALID, "n_instances < 1");
   if (h->n_node_maps != 1) return fail(EMPC_ERR_INVALID, "instances are replicated from a problem with a single node map");
+  if (h->has_contact) return fail(EMPC_ERR_UNSUPPORTED, "MPC instances with contact stages are not supported (the reference's controllers refuse them, src/mpc-controllers/carrot-mpc.cpp:204-206)");
   if ((long long)n * std::max(h->n_pool, h->n_costs) > 0x7fffffffLL / 2) return fail(EMPC_ERR_INVALID, "replicated tables exceed the 32-bit offsets");
   CK(cudaSetDevice(h->device));
   const int T1 = h->T + 1;
@@ -580,6 +635,10 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   const long long groups = n_last / Pk<D>::GROUP - n_first / Pk<D>::GROUP + 1;
   node_diff_kernel<D><<<(unsigned)groups, W::THREADS, smem, st>>>(bf, force, smooth, h->hmodel);
   h->launches++;
+  if (h->has_contact) {  // the nodes of contact stages: calc + calcDiff again under the contact dynamics (contact.cuh)
+    contact_node_kernel<D><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(bf, force, smooth, h->hmodel);
+    h->launches++;
+  }
   return cudaGetLastError();
 }
 template <class D>
@@ -589,7 +648,8 @@ static cudaError_t launch_backward(empc_solver* h, int force, const Buffers* gb 
   using S = BwCfg<D>;
   const size_t smem = sizeof(double) * S::TOTAL;
   BwParams P{h->P.reg_max, h->P.reg_factor, h->P.th_gaptol, force, h->P.stop_criteria == EMPC_STOP_CRITERIA_QU_NORM};
-  backward_kernel<D><<<bf.nb, 32, smem, st>>>(bf, P);  // one warp per OCP
+  if (h->has_coupled) backward_kernel<D, true><<<bf.nb, 32, smem, st>>>(bf, P);
+  else backward_kernel<D, false><<<bf.nb, 32, smem, st>>>(bf, P);  // one warp per OCP
   h->launches++;
   return cudaGetLastError();
 }
@@ -598,7 +658,8 @@ static cudaError_t launch_rollout_w(empc_solver* h, const RoParams& P, const Buf
   using S = RoCfg<D, W>;
   const size_t smem = sizeof(double) * S::SMEM_DOUBLES;
   // one warp per block = 32/W OCPs x W step lengths
-  rollout_kernel<D, W><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
+  if (h->has_contact) rollout_kernel<D, W, true><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
+  else rollout_kernel<D, W, false><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
   h->launches++;
   return cudaGetLastError();
 }
@@ -616,7 +677,8 @@ static cudaError_t launch_rollout(empc_solver* h, int stage, int force, int feas
   if (!force) return cudaSuccess;
   const int width = (stage == 0) ? h->width_a : EMPC_N_ALPHAS - h->width_a;
   const long long n_thr = (long long)bf.nb * width * (h->T + 1);
-  trial_cost_kernel<D><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
+  if (h->has_contact) trial_cost_kernel<D, true><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
+  else trial_cost_kernel<D, false><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
   h->launches++;
   const long long n_warps = (long long)bf.nb * width;
   trial_sum_kernel<<<(unsigned)((n_warps + 3) / 4), 128, 0, st>>>(bf, P, width);
@@ -637,7 +699,8 @@ static cudaError_t launch_decide(empc_solver* h, int stage, const Buffers* gb = 
     const double eff = (double)T1 / ((double)rounds * n);
     if (eff >= best - 1e-12) { best = eff; threads = n; }
   }
-  decide_kernel<D><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
+  if (h->has_contact) decide_kernel<D, true><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
+  else decide_kernel<D, false><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
   h->launches++;
   return cudaGetLastError();
 }
