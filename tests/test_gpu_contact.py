@@ -7,11 +7,11 @@ rollout trials of several step lengths.  Solver level: same iteration count, cos
 """
 import importlib
 import os
-import shutil
 
 import numpy as np
 import pytest
 
+import contact_variants
 import oracle_binding as ob
 import parity
 
@@ -32,18 +32,11 @@ def rel(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
 
-def six_d_variant(tmp_path, monkeypatch):
-    root = tmp_path / "yaml"
-    shutil.copytree(os.path.join(YAML_ROOT, "hexacopter370_flying_arm_3"), root / "hexacopter370_flying_arm_3")
-    src = (root / "hexacopter370_flying_arm_3" / "trajectories" / "monkey_bar.yaml").read_text()
-    src = src.replace('type: "ContactModel3D"', 'type: "ContactModel6D"\n          orientation: [0, 0, 0, 1]')
-    (root / "hexacopter370_flying_arm_3" / "trajectories" / "monkey_bar_6d.yaml").write_text(src)
-    monkeypatch.setenv("EAGLE_MPC_YAML_DIR", str(root))
-    return "hexacopter370_flying_arm_3/trajectories/monkey_bar_6d.yaml"
-
-
 def problem(case, tmp_path, monkeypatch):
-    rel_path = six_d_variant(tmp_path, monkeypatch) if case == "6d" else case
+    rel_path = case
+    if case in ("6d", "hextilt"):
+        root, rel_path = contact_variants.six_d(tmp_path) if case == "6d" else contact_variants.hextilt_push(tmp_path)
+        monkeypatch.setenv("EAGLE_MPC_YAML_DIR", root)
     return host.Trajectory(rel_path).createProblem(20)
 
 
@@ -64,7 +57,7 @@ def random_candidate(fp, B, seed):
     return x0, xs, us
 
 
-@pytest.mark.parametrize("case", [CATCH, MONKEY, "6d"])
+@pytest.mark.parametrize("case", [CATCH, MONKEY, "6d", "hextilt"])
 def test_contact_phases(case, tmp_path, monkeypatch):
     fp = problem(case, tmp_path, monkeypatch)
     assert fp.desc.n_contacts == 1
@@ -98,7 +91,7 @@ def test_contact_phases(case, tmp_path, monkeypatch):
     print(case, {k: f"{v:.1e}" for k, v in worst.items()}, "max |Lxu|", lxu_seen)
     for k, v in worst.items():
         assert v < 1e-9, (k, v)
-    if case == CATCH:
+    if case in (CATCH, "hextilt"):
         assert lxu_seen > 0, "the random candidate should activate a facet of the friction cone"
     # backward pass with and without the gap terms
     for feasible in (False, True):

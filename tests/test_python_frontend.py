@@ -68,3 +68,20 @@ def test_reference_scripts_run():
         out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script)] + args, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
         assert "final position" in out.stdout
+
+
+@pytest.mark.gpu
+def test_contact_trajectory_through_the_front_end():
+    """examples/python/trajectory.py on eagle_catch.yaml: a contact trajectory (DifferentialActionModelContactFwdDynamics
+    for every stage, src/trajectory.cpp:115-116) built and solved through the reference's Python names"""
+    rel = "hexacopter370_flying_arm_3/trajectories/eagle_catch.yaml"
+    tr = _trajectory(rel)
+    problem = tr.createProblem(20, True, "IntegratedActionModelEuler")
+    solver = eagle_mpc.SolverSbFDDP(problem, tr.squash)
+    assert solver.solve([], [], maxiter=100)
+    fp = host.Trajectory(rel).createProblem(20)
+    assert fp.desc.n_contacts == 1
+    g = capi.BatchSolver(fp, 1)
+    g.set_x0(fp.x0); g.set_candidate(None, None, False); g.solve()
+    assert solver.iter == g.iters()[0]
+    assert np.array_equal(solver.xs, g.xs()[0]) and np.array_equal(solver.us, g.us()[0])

@@ -176,27 +176,18 @@ def test_oracle_blocks_equal_complex_step(rel):
 CONTACT_YAMLS = ["hexacopter370_flying_arm_3/trajectories/eagle_catch.yaml", "hexacopter370_flying_arm_3/trajectories/monkey_bar.yaml"]
 
 
-def _six_d_variant(tmp_path):
-    """monkey_bar.yaml with its ContactModel3D turned into a ContactModel6D, in a private YAML tree"""
-    import shutil
-    root = tmp_path / "yaml"
-    shutil.copytree(os.path.join(YAML_ROOT, "hexacopter370_flying_arm_3"), root / "hexacopter370_flying_arm_3")
-    src = (root / "hexacopter370_flying_arm_3" / "trajectories" / "monkey_bar.yaml").read_text()
-    assert 'type: "ContactModel3D"' in src
-    src = src.replace('type: "ContactModel3D"', 'type: "ContactModel6D"\n          orientation: [0, 0, 0, 1]')
-    (root / "hexacopter370_flying_arm_3" / "trajectories" / "monkey_bar_6d.yaml").write_text(src)
-    return str(root), "hexacopter370_flying_arm_3/trajectories/monkey_bar_6d.yaml"
+import contact_variants  # noqa: E402
 
 
-@pytest.mark.parametrize("case", CONTACT_YAMLS + ["6d"])
+@pytest.mark.parametrize("case", CONTACT_YAMLS + ["6d", "hextilt"])
 def test_oracle_contact_blocks_equal_complex_step(case, tmp_path, monkeypatch):
     """DifferentialActionModelContactFwdDynamics (ContactModel3D of the corpus, a ContactModel6D variant) and the
     friction-cone cost: the oracle's KKT dynamics and its implicit-function derivatives (Fx, Fu, and the force Jacobians
     inside Lx, Lu, Lxx, Lxu, Luu) against the twin's complex step through its own dense KKT solve.  The bar is 1e-10: the
     contact solve divides by Jc M^-1 Jc^T, and the two restatements factorise differently."""
     yaml_root, rel = YAML_ROOT, case
-    if case == "6d":
-        yaml_root, rel = _six_d_variant(tmp_path)
+    if case in ("6d", "hextilt"):
+        yaml_root, rel = contact_variants.six_d(tmp_path) if case == "6d" else contact_variants.hextilt_push(tmp_path)
         monkeypatch.setenv("EAGLE_MPC_YAML_DIR", yaml_root)
     fp = host.Trajectory(rel).createProblem(20)
     tw = twin.Problem(rel, yaml_root, URDF_ROOT, 20)
