@@ -15,6 +15,7 @@ N_ALPHAS = 10
 COST_STATE, COST_CONTROL, COST_FRAME_PLACEMENT, COST_FRAME_ROTATION, COST_FRAME_VELOCITY, \
     COST_FRAME_TRANSLATION, COST_SQUASH_BARRIER, COST_CONTACT_FRICTION_CONE = range(8)
 CONTACT_3D, CONTACT_6D = 1, 2
+INTEGRATOR_EULER, INTEGRATOR_RK4 = 0, 1
 ACT_QUAD, ACT_WEIGHTED_QUAD, ACT_QUAD_BARRIER, ACT_WEIGHTED_QUAD_BARRIER = range(4)
 
 c_double_p = C.POINTER(C.c_double)
@@ -94,7 +95,7 @@ class ProblemDesc(C.Structure):
         ("pool", c_double_p),
         ("node_costset", c_int32_p),
         ("n_contacts", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("integrator", C.c_int32),
         ("contacts", C.POINTER(Contact)),
         ("costset_contact", c_int32_p),
     ]

@@ -204,6 +204,7 @@ struct ActionModel {
   // DifferentialActionModelContactFwdDynamics(state, actuation, contacts, costs, 0, true) when the trajectory has a
   // contact stage (src/factory/diff-action.cpp:30-32), DifferentialActionModelFreeFwdDynamics otherwise (contacts null)
   std::shared_ptr<ContactModelMultiple> contacts;
+  bool rk4 = false;  // IntegratedActionModelRK4 instead of IntegratedActionModelEuler (src/factory/int-action.cpp:24-35)
   double dt = 0;     // seconds
   bool squash = true;
   VectorXd u_lb, u_ub;

@@ -49,14 +49,13 @@ void MpcAbstract::loadParams() {
 void MpcAbstract::checkHotPathSupport() const {
   if (params_.solver_type != SolverTypes::SolverSbFDDP)
     throw std::runtime_error("only SolverSbFDDP is part of the B200 hot path (SolverBoxFDDP/BoxDDP: SURVEY.md §8f rank 4)");
-  if (params_.integrator_type != "IntegratedActionModelEuler")
-    throw std::runtime_error("IntegratedActionModelRK4 is not part of the B200 hot path yet");
 }
 
 std::shared_ptr<ActionModel> MpcAbstract::makeKnotModel(const std::shared_ptr<CostModelSum>& costs) const {
   auto iam = std::make_shared<ActionModel>();
   iam->costs = costs;
   iam->dt = double(params_.dt) / 1000.;
+  iam->rk4 = params_.integrator_type == "IntegratedActionModelRK4";  // src/mpc-controllers/carrot-mpc.cpp:211-222
   iam->squash = true;
   iam->u_lb = platform_params_->u_lb; iam->u_ub = platform_params_->u_ub;
   return iam;

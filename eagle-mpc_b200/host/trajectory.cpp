@@ -391,9 +391,10 @@ std::shared_ptr<ShootingProblem> Trajectory::createProblem() const {
 }
 
 std::shared_ptr<ShootingProblem> Trajectory::createProblem(std::size_t dt, bool squash, const std::string& integration_method) const {
-  if (integration_method == "IntegratedActionModelRK4")
-    throw std::runtime_error("IntegratedActionModelRK4 is not part of the B200 hot path yet; use IntegratedActionModelEuler");
-  if (integration_method != "IntegratedActionModelEuler") throw std::out_of_range("map::at");
+  const bool rk4 = integration_method == "IntegratedActionModelRK4";
+  if (!rk4 && integration_method != "IntegratedActionModelEuler") throw std::out_of_range("map::at");  // IntegratedActionModelTypes_map.at()
+  if (rk4 && has_contact_)
+    throw std::runtime_error("IntegratedActionModelRK4 over contact dynamics is not supported by the B200 hot path");
   auto problem = std::make_shared<ShootingProblem>();
   bool last_duration0 = false;
   for (auto stage = stages_.begin(); stage != stages_.end(); ++stage) {
@@ -401,6 +402,7 @@ std::shared_ptr<ShootingProblem> Trajectory::createProblem(std::size_t dt, bool 
     iam->costs = (*stage)->get_costs();
     if (has_contact_) iam->contacts = (*stage)->get_contacts();  // dam_factory_->create(has_contact_, squash, *stage), :115-116
     iam->dt = double(dt) / 1000.;
+    iam->rk4 = rk4;
     iam->squash = squash;
     std::size_t n_knots;
     if ((*stage)->get_duration() / dt == 0 && std::next(stage) != stages_.end()) { n_knots = 1; last_duration0 = true; }
@@ -508,6 +510,7 @@ void flatten_problem(const ShootingProblem& problem, FlatProblem& out) {
   out.desc.T = (int)T;
   out.desc.dt = problem.terminalModel->dt;
   out.desc.use_squash = problem.terminalModel->squash ? 1 : 0;
+  out.desc.integrator = problem.terminalModel->rk4 ? EMPC_INTEGRATOR_RK4 : EMPC_INTEGRATOR_EULER;
   out.desc.n_node_maps = 1;
   out.costset_begin.assign(1, 0);
   out.costs.clear(); out.pool.clear(); out.node_costset.assign(T + 1, 0); out.slots.clear(); out.set_models.clear();
@@ -521,6 +524,7 @@ void flatten_problem(const ShootingProblem& problem, FlatProblem& out) {
     out.set_models.push_back(m);
     out.slots.emplace_back();
     if (m->dt != out.desc.dt) throw std::runtime_error("all action models must share the same time step");
+    if (m->rk4 != problem.terminalModel->rk4) throw std::runtime_error("all action models must share the same integrator");
     // the model's ContactModelMultiple: one contact per model is what the corpus uses and what the kernels cover
     int contact_index = -1;
     if (m->contacts && !m->contacts->get_contacts().empty()) {

@@ -57,6 +57,10 @@ enum {
   EMPC_COST_CONTACT_FRICTION_CONE = 7 /* src/factory/cost.cpp:149-167: r = A f on the force of the stage's contact */
 };
 
+/* integrators — src/factory/int-action.cpp:24-35, selected by createProblem(dt, squash, integration_method)
+ * (src/trajectory.cpp:102-104) or by mpc_controller/integration_method (src/mpc-base.cpp:42-43) */
+enum { EMPC_INTEGRATOR_EULER = 0, EMPC_INTEGRATOR_RK4 = 1 };
+
 /* contact models — src/factory/contacts.cpp:32-81 (DifferentialActionModelContactFwdDynamics, src/factory/diff-action.cpp:30-32) */
 enum { EMPC_CONTACT_3D = 1, EMPC_CONTACT_6D = 2 };
 typedef struct empc_contact {
@@ -133,7 +137,7 @@ typedef struct empc_problem_desc {
    * costset_contact[c] is the contact of the model that owns cost set c (one ContactModel per stage, as in the
    * corpus), or -1: that model has an empty ContactModelMultiple and behaves like the free dynamics. */
   int32_t n_contacts;
-  int32_t reserved_;
+  int32_t integrator;                       /* EMPC_INTEGRATOR_*: IntegratedActionModelEuler / RK4 (src/factory/int-action.cpp:24-35) */
   const empc_contact_t* contacts;           /* n_contacts */
   const int32_t* costset_contact;           /* n_costsets, or NULL when n_contacts = 0 */
 } empc_problem_desc_t;

@@ -368,9 +368,11 @@ inline double cost_calc(const Model& m, const SolverCtx& ctx, const empc_cost_t&
 
 inline void contact_calc(const Model& m, const empc_contact_t& ct, const double* vq, Work& w);
 
-// IntegratedActionModelEuler::calc — fills w (xnext, cost, and everything calcDiff reuses)
-inline void node_calc(const Model& m, const SolverCtx& ctx, int costset, const double* x, const double* u, Work& w,
-                      std::vector<CostEval>* evals = nullptr) {
+// Differential action model at (x, u) — DifferentialActionModelFreeFwdDynamics / ContactFwdDynamics::calc: squashing,
+// thrust map, forward dynamics, CostModelSum.  Fills w (kinematics, accelerations w.a) and returns the cost (not yet
+// weighted by the integrator).
+inline double diff_calc(const Model& m, const SolverCtx& ctx, int costset, const double* x, const double* u, Work& w,
+                        std::vector<CostEval>* evals = nullptr) {
   const empc_problem_desc_t& d = *m.d;
   std::memcpy(w.x, x, sizeof(double) * m.nx);
   for (int i = 0; i < m.nu; ++i) w.u[i] = u ? u[i] : 0.0;  // calc(data,x) == calc(data,x,unone_=0), SURVEY B.7
@@ -397,13 +399,6 @@ inline void node_calc(const Model& m, const SolverCtx& ctx, int costset, const d
   w.nc = 0;
   if (d.n_contacts > 0 && d.costset_contact && d.costset_contact[costset] >= 0)
     contact_calc(m, d.contacts[d.costset_contact[costset]], x + m.nq, w);
-  // semi-implicit Euler (euler.hxx calc)
-  const double dt = m.dt, dt2 = dt * dt;
-  for (int i = 0; i < m.nv; ++i) {
-    w.dx[i] = x[m.nq + i] * dt + w.a[i] * dt2;
-    w.dx[m.nv + i] = w.a[i] * dt;
-  }
-  state_integrate(m, x, w.dx, w.xnext);
   // CostModelSum::calc, costs in name order
   double cost = 0;
   const int c0 = d.costset_begin[costset], c1 = d.costset_begin[costset + 1];
@@ -414,7 +409,45 @@ inline void node_calc(const Model& m, const SolverCtx& ctx, int costset, const d
     CostEval& e = evals ? (*evals)[c - c0] : tmp;
     cost += d.costs[c].weight * cost_calc(m, ctx, d.costs[c], w, e);
   }
-  w.cost = dt * cost;
+  return cost;
+}
+
+// IntegratedActionModelRK4 (crocoddyl/core/integrator/rk4.hxx): stage coefficients and weights
+static const double kRk4C[4] = {0.0, 0.5, 0.5, 1.0}, kRk4W[4] = {1.0, 2.0, 2.0, 1.0};
+
+// IntegratedActionModelEuler::calc / IntegratedActionModelRK4::calc — fills w (xnext, cost, and for Euler everything
+// calcDiff reuses; w keeps the first stage's data, which is where the solver reads the squashed control, src/sbfddp.cpp:145)
+inline void node_calc(const Model& m, const SolverCtx& ctx, int costset, const double* x, const double* u, Work& w,
+                      std::vector<CostEval>* evals = nullptr) {
+  const double dt = m.dt, dt2 = dt * dt;
+  const double cost0 = diff_calc(m, ctx, costset, x, u, w, evals);
+  if (m.d->integrator != EMPC_INTEGRATOR_RK4) {
+    // semi-implicit Euler (euler.hxx calc)
+    for (int i = 0; i < m.nv; ++i) {
+      w.dx[i] = x[m.nq + i] * dt + w.a[i] * dt2;
+      w.dx[m.nv + i] = w.a[i] * dt;
+    }
+    state_integrate(m, x, w.dx, w.xnext);
+    w.cost = dt * cost0;
+    return;
+  }
+  // y_i = x (+) c_i dt k_{i-1}, k_i = [v(y_i); a(y_i, u)]; dx = dt/6 sum w_i k_i; cost = dt/6 sum w_i l(y_i, u)
+  double k[MAXDX], ksum[MAXDX], y[MAXX], dxi[MAXDX];
+  for (int i = 0; i < m.nv; ++i) { k[i] = x[m.nq + i]; k[m.nv + i] = w.a[i]; }
+  for (int i = 0; i < m.ndx; ++i) ksum[i] = k[i];
+  double csum = cost0;
+  static thread_local Work ws;  // (a stage's data is not kept: calcDiff re-evaluates the stages)
+  for (int st = 1; st < 4; ++st) {
+    for (int i = 0; i < m.ndx; ++i) dxi[i] = kRk4C[st] * dt * k[i];
+    state_integrate(m, x, dxi, y);
+    const double c = diff_calc(m, ctx, costset, y, u, ws, nullptr);
+    for (int i = 0; i < m.nv; ++i) { k[i] = y[m.nq + i]; k[m.nv + i] = ws.a[i]; }
+    for (int i = 0; i < m.ndx; ++i) ksum[i] += kRk4W[st] * k[i];
+    csum += kRk4W[st] * c;
+  }
+  for (int i = 0; i < m.ndx; ++i) w.dx[i] = ksum[i] * (dt / 6.0);
+  state_integrate(m, x, w.dx, w.xnext);
+  w.cost = csum * (dt / 6.0);
 }
 
 // world Jacobian columns (motion axes of the velocity columns) and world body velocities
@@ -726,9 +759,12 @@ inline void contact_derivatives(const Model& m, Work& w, const double* vq, doubl
 }
 
 // IntegratedActionModelEuler::calcDiff.  `tile` receives Fx|Fu|Lxx|Lxu|Luu|Lx|Lu (Model::o* offsets).
-// Must follow node_calc on the same (x,u) — crocoddyl's convention.
-inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Work& w, std::vector<CostEval>& evals,
-                           double* tile) {
+// Must follow diff_calc on the same (x,u) — crocoddyl's convention.
+// Differential mode (out_aq != nullptr): the derivatives of the DIFFERENTIAL model only — a_q, a_v (nv x nv), a_u (nv x nu)
+// go to out_*, the tile's L blocks receive the cost derivatives unscaled and its F blocks stay zero (what an integrator
+// other than Euler builds on).
+inline void node_calc_diff_impl(const Model& m, const SolverCtx& ctx, int costset, Work& w, std::vector<CostEval>& evals,
+                                double* tile, double* out_aq = nullptr, double* out_av = nullptr, double* out_au = nullptr) {
   const empc_problem_desc_t& d = *m.d;
   const int nv = m.nv, ndx = m.ndx, nu = m.nu, nr = m.nr;
   const double dt = m.dt, dt2 = dt * dt;
@@ -773,8 +809,14 @@ inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Wo
       else s = GiBt[r * nv + 6 + (j - nr)] * w.ds[j];
       lam_u[r * nu + j] = -s;
     }
+  const bool differential_only = out_aq != nullptr;
+  if (differential_only) {
+    std::memcpy(out_aq, a_q, sizeof(double) * nv * nv);
+    std::memcpy(out_av, a_v, sizeof(double) * nv * nv);
+    std::memcpy(out_au, a_u, sizeof(double) * nv * nu);
+  }
   // Euler: discrete Jacobians before the Lie-group transport
-  for (int i = 0; i < nv; ++i) {
+  for (int i = 0; i < nv && !differential_only; ++i) {
     for (int j = 0; j < nv; ++j) {
       Fx[i * ndx + j] = a_q[i * nv + j] * dt2;
       Fx[i * ndx + nv + j] = a_v[i * nv + j] * dt2;
@@ -786,7 +828,7 @@ inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Wo
   }
   // JintegrateTransport(x,dx,.,second): rows 0..5 <- Jexp6(dx[0:6]) * rows 0..5
   double Je[36]; Jexp6(w.dx, Je);
-  {
+  if (!differential_only) {
     double tmp[6][MAXDX];
     for (int a = 0; a < 6; ++a)
       for (int c = 0; c < ndx; ++c) {
@@ -804,7 +846,7 @@ inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Wo
     for (int a = 0; a < 6; ++a) for (int c = 0; c < nu; ++c) Fu[a * nu + c] = tmp[a][c];
   }
   // Jintegrate(x,dx,first,addto): += blockdiag(Ad(exp6(dx)^-1), I)
-  {
+  if (!differential_only) {
     SE3 E; exp6(w.dx, E);
     double Xs[36]; force_action_matrix(E, Xs);  // Ad(E^-1) = (X*)^T
     for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) Fx[a * ndx + b] += Xs[6 * b + a];
@@ -923,12 +965,118 @@ inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Wo
       } break;
     }
   }
+  if (differential_only) return;
   // Euler scales the cost derivatives by dt (Lxu is zero unless the node has a contact-force cost)
   for (int i = 0; i < ndx * ndx; ++i) Lxx[i] *= dt;
   for (int i = 0; i < ndx * nu; ++i) Lxu[i] *= dt;
   for (int i = 0; i < nu * nu; ++i) Luu[i] *= dt;
   for (int i = 0; i < ndx; ++i) Lx[i] *= dt;
   for (int i = 0; i < nu; ++i) Lu[i] *= dt;
+}
+
+
+// J <- d integrate(x, dx)/d(dx) * J  (+ d integrate/dx when add_first): JintegrateTransport(second) then Jintegrate(first,
+// addto) of StateMultibody, for an ndx x ncols row-major matrix J
+inline void jintegrate_apply(const Model& m, const double* dx, double* J, int ncols, bool add_first) {
+  double Je[36]; Jexp6(dx, Je);
+  double tmp[6];
+  for (int c = 0; c < ncols; ++c) {
+    for (int a = 0; a < 6; ++a) {
+      double s = 0;
+      for (int k = 0; k < 6; ++k) s += Je[6 * a + k] * J[k * ncols + c];
+      tmp[a] = s;
+    }
+    for (int a = 0; a < 6; ++a) J[a * ncols + c] = tmp[a];
+  }
+  if (add_first) {
+    SE3 E; exp6(dx, E);
+    double Xs[36]; force_action_matrix(E, Xs);  // Ad(E^-1) = (X*)^T
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) J[a * ncols + b] += Xs[6 * b + a];
+    for (int i = 6; i < m.ndx; ++i) J[i * ncols + i] += 1.0;
+  }
+}
+
+// IntegratedActionModelRK4::calcDiff (crocoddyl/core/integrator/rk4.hxx): chain rule through the four stages,
+//   dki_dx = dki_dy dyi_dx,  dki_du = dki_dy dyi_du + [0; a_u],  dki_dy = [[0, I], [a_q, a_v]],
+//   dyi_dx = Jint_2(x, c_i dt k_{i-1}) c_i dt dk(i-1)_dx + Jint_1,  dyi_du = Jint_2 c_i dt dk(i-1)_du,
+//   Fx = Jint_2(x, dx) dt/6 sum w_i dki_dx + Jint_1,  Fu = Jint_2 dt/6 sum w_i dki_du,
+// and the stage costs pulled back through (dyi_dx, dyi_du) with the Gauss-Newton products of rk4.hxx.
+inline void node_calc_diff_rk4(const Model& m, const SolverCtx& ctx, int costset, Work& w, double* tile) {
+  const int nv = m.nv, ndx = m.ndx, nu = m.nu;
+  const double dt = m.dt;
+  for (int i = 0; i < m.tile; ++i) tile[i] = 0;
+  double* Fx = tile + m.oFx; double* Fu = tile + m.oFu; double* Lxx = tile + m.oLxx; double* Lxu = tile + m.oLxu;
+  double* Luu = tile + m.oLuu; double* Lx = tile + m.oLx; double* Lu = tile + m.oLu;
+  std::vector<double> st_tile(m.tile);
+  std::vector<CostEval> ev;
+  static thread_local Work ws;
+  double x[MAXX], u[MAXU];
+  std::memcpy(x, w.x, sizeof(double) * m.nx); std::memcpy(u, w.u, sizeof(double) * nu);
+  std::vector<double> dyx(ndx * ndx, 0.0), dyu(ndx * nu, 0.0), dkx(ndx * ndx), dku(ndx * nu), tA(ndx * ndx), tB(ndx * nu);
+  for (int i = 0; i < ndx; ++i) dyx[i * ndx + i] = 1.0;  // stage 0: y_0 = x
+  double k[MAXDX], y[MAXX], dxi[MAXDX], a_q[MAXV * MAXV], a_v[MAXV * MAXV], a_u[MAXV * MAXU];
+  std::memcpy(y, x, sizeof(double) * m.nx);
+  for (int st = 0; st < 4; ++st) {
+    if (st > 0) {
+      // y_st and its Jacobians from the previous stage's k
+      for (int i = 0; i < ndx; ++i) dxi[i] = kRk4C[st] * dt * k[i];
+      state_integrate(m, x, dxi, y);
+      for (int i = 0; i < ndx * ndx; ++i) dyx[i] = kRk4C[st] * dt * dkx[i];
+      for (int i = 0; i < ndx * nu; ++i) dyu[i] = kRk4C[st] * dt * dku[i];
+      jintegrate_apply(m, dxi, dyx.data(), ndx, true);
+      jintegrate_apply(m, dxi, dyu.data(), nu, false);
+    }
+    diff_calc(m, ctx, costset, y, u, ws, &ev);
+    node_calc_diff_impl(m, ctx, costset, ws, ev, st_tile.data(), a_q, a_v, a_u);
+    for (int i = 0; i < nv; ++i) { k[i] = y[m.nq + i]; k[nv + i] = ws.a[i]; }
+    // dki_dx = dki_dy dyi_dx ; dki_du = dki_dy dyi_du + [0; a_u]
+    for (int i = 0; i < nv; ++i) {
+      for (int c = 0; c < ndx; ++c) {
+        dkx[i * ndx + c] = dyx[(nv + i) * ndx + c];
+        double s = 0;
+        for (int j = 0; j < nv; ++j) s += a_q[i * nv + j] * dyx[j * ndx + c] + a_v[i * nv + j] * dyx[(nv + j) * ndx + c];
+        dkx[(nv + i) * ndx + c] = s;
+      }
+      for (int c = 0; c < nu; ++c) {
+        dku[i * nu + c] = dyu[(nv + i) * nu + c];
+        double s = a_u[i * nu + c];
+        for (int j = 0; j < nv; ++j) s += a_q[i * nv + j] * dyu[j * nu + c] + a_v[i * nv + j] * dyu[(nv + j) * nu + c];
+        dku[(nv + i) * nu + c] = s;
+      }
+    }
+    const double wg = kRk4W[st] * dt / 6.0;
+    for (int i = 0; i < ndx * ndx; ++i) Fx[i] += wg * dkx[i];
+    for (int i = 0; i < ndx * nu; ++i) Fu[i] += wg * dku[i];
+    // stage cost derivatives (unscaled) pulled back through dyi_dx, dyi_du
+    const double* sLxx = st_tile.data() + m.oLxx; const double* sLxu = st_tile.data() + m.oLxu; const double* sLuu = st_tile.data() + m.oLuu;
+    const double* sLx = st_tile.data() + m.oLx; const double* sLu = st_tile.data() + m.oLu;
+    for (int c = 0; c < ndx; ++c) { double s = 0; for (int i = 0; i < ndx; ++i) s += sLx[i] * dyx[i * ndx + c]; Lx[c] += wg * s; }
+    for (int c = 0; c < nu; ++c) { double s = sLu[c]; for (int i = 0; i < ndx; ++i) s += sLx[i] * dyu[i * nu + c]; Lu[c] += wg * s; }
+    // tA = Lxx_i dyi_dx (ndx x ndx), tB = Lxx_i dyi_du + Lxu_i (ndx x nu)
+    for (int i = 0; i < ndx; ++i) {
+      for (int c = 0; c < ndx; ++c) { double s = 0; for (int j = 0; j < ndx; ++j) s += sLxx[i * ndx + j] * dyx[j * ndx + c]; tA[i * ndx + c] = s; }
+      for (int c = 0; c < nu; ++c) { double s = sLxu[i * nu + c]; for (int j = 0; j < ndx; ++j) s += sLxx[i * ndx + j] * dyu[j * nu + c]; tB[i * nu + c] = s; }
+    }
+    for (int r = 0; r < ndx; ++r) {
+      for (int c = 0; c < ndx; ++c) { double s = 0; for (int i = 0; i < ndx; ++i) s += dyx[i * ndx + r] * tA[i * ndx + c]; Lxx[r * ndx + c] += wg * s; }
+      for (int c = 0; c < nu; ++c) { double s = 0; for (int i = 0; i < ndx; ++i) s += dyx[i * ndx + r] * tB[i * nu + c]; Lxu[r * nu + c] += wg * s; }
+    }
+    // Luu_i + Lxu_i^T dyi_du + (Lxu_i^T dyi_du)^T + dyi_du^T Lxx_i dyi_du  =  Luu_i + dyi_du^T tB + (Lxu_i^T dyi_du)^T
+    for (int r = 0; r < nu; ++r)
+      for (int c = 0; c < nu; ++c) {
+        double s = sLuu[r * nu + c];
+        for (int i = 0; i < ndx; ++i) s += dyu[i * nu + r] * tB[i * nu + c] + sLxu[i * nu + c] * dyu[i * nu + r];
+        Luu[r * nu + c] += wg * s;
+      }
+  }
+  jintegrate_apply(m, w.dx, Fx, ndx, true);
+  jintegrate_apply(m, w.dx, Fu, nu, false);
+}
+
+inline void node_calc_diff(const Model& m, const SolverCtx& ctx, int costset, Work& w, std::vector<CostEval>& evals,
+                           double* tile) {
+  if (m.d->integrator == EMPC_INTEGRATOR_RK4) node_calc_diff_rk4(m, ctx, costset, w, tile);
+  else node_calc_diff_impl(m, ctx, costset, w, evals, tile);
 }
 
 }  // namespace orc

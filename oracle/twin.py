@@ -348,7 +348,9 @@ def _vec(v):
 class Problem:
     """trajectory YAML -> what SolverSbFDDP sees (robot, actuation, one cost dict per stage, node -> stage map)"""
 
-    def __init__(self, yaml_path, yaml_root, urdf_root, dt_ms, barrier_weight=1e-3):
+    def __init__(self, yaml_path, yaml_root, urdf_root, dt_ms, barrier_weight=1e-3, integrator="IntegratedActionModelEuler"):
+        assert integrator in ("IntegratedActionModelEuler", "IntegratedActionModelRK4")   # src/factory/int-action.cpp:24-35
+        self.rk4 = integrator == "IntegratedActionModelRK4"
         doc = pyyaml.safe_load(open(os.path.join(yaml_root, yaml_path)))["trajectory"]
         self.rob = Robot(os.path.join(urdf_root, doc["robot"]["urdf"]))
         plat = pyyaml.safe_load(open(os.path.join(yaml_root, doc["robot"]["follow"])))["platform"]
@@ -534,37 +536,57 @@ class Problem:
         w = c["w"]   # upstream: value and gradient carry w^2, the Gauss-Newton weight is w
         return 0.5 * ((w * rl) @ (w * rl)) + 0.5 * ((w * ru) @ (w * ru)), on * w
 
-    def calc(self, stage, x, u, smooth, terminal=False):
-        """(xnext, cost) of IntegratedActionModelEuler::calc; the terminal node evaluates with u = 0 (1.x convention)"""
+    def node_terms(self, stage, x, u, smooth):
+        """(xnext, [(total weight, residual, activation dict)]) of one node.  IntegratedActionModelEuler: semi-implicit
+        Euler, costs at (x, u) weighted by dt.  IntegratedActionModelRK4 (crocoddyl/core/integrator/rk4.hxx): stage states
+        y_i = x (+) c_i dt k_{i-1}, k_i = [v(y_i); a(y_i, u)], c = (0, 1/2, 1/2, 1), dx = dt/6 (k_0 + 2 k_1 + 2 k_2 + k_3), and
+        the costs of the four stages weighted by dt/6 (1, 2, 2, 1)."""
         rob = self.rob
+        if not self.rk4:
+            a, _lam = self.dynamics(stage, x, u, smooth)
+            dx = np.concatenate([x[rob.nq:] * self.dt + a * self.dt ** 2, a * self.dt])
+            return integrate(rob, x, dx), [(self.dt * w, r, c) for _n, w, r, c in self.residuals(stage, x, u, smooth)]
+        terms, ks = [], []
+        y = x
+        for i, (ci, wi) in enumerate(((0.0, 1.0), (0.5, 2.0), (0.5, 2.0), (1.0, 1.0))):
+            if i:
+                y = integrate(rob, x, ci * self.dt * ks[-1])
+            a, _lam = self.dynamics(stage, y, u, smooth)
+            ks.append(np.concatenate([y[rob.nq:], a]))
+            terms += [(self.dt / 6.0 * wi * w, r, c) for _n, w, r, c in self.residuals(stage, y, u, smooth)]
+        dx = self.dt / 6.0 * (ks[0] + 2 * ks[1] + 2 * ks[2] + ks[3])
+        return integrate(rob, x, dx), terms
+
+    def calc(self, stage, x, u, smooth, terminal=False):
+        """(xnext, cost) of the integrated action model's calc; the terminal node evaluates with u = 0 (1.x convention)"""
         if terminal:
             u = np.zeros(self.nu, dtype=x.dtype)
-        v = x[rob.nq:]
-        a, _lam = self.dynamics(stage, x, u, smooth)
-        dx = np.concatenate([v * self.dt + a * self.dt ** 2, a * self.dt])
+        xnext, terms = self.node_terms(stage, x, u, smooth)
         cost = 0
-        for _name, w, r, c in self.residuals(stage, x, u, smooth):
-            cost = cost + w * self.activation(c, r)[0]
-        return integrate(rob, x, dx), self.dt * cost
+        for wt, r, c in terms:
+            cost = cost + wt * self.activation(c, r)[0]
+        return xnext, cost
 
     def calc_diff(self, stage, x, u, smooth, terminal=False):
-        """dict of the node's blocks by the complex step: Fx, Fu, Lx, Lu, Lxx, Luu (Gauss-Newton), plus xnext, cost"""
+        """dict of the node's blocks by the complex step: Fx, Fu, Lx, Lu and the Gauss-Newton Lxx, Luu, Lxu (sum over the
+        node's residual terms of w R^T Arr R with the TOTAL residual Jacobians: for RK4 that is exactly rk4.hxx's
+        dyi_dx^T Lxx_i dyi_dx / ... assembly), plus xnext, cost"""
         rob = self.rob
         ndx, nu = rob.ndx, self.nu
         x = x.astype(complex); u = (np.zeros(nu) if terminal else u).astype(complex)
         xn0, c0 = self.calc(stage, x, u, smooth, terminal)
-        res0 = self.residuals(stage, x, u, smooth)
+        res0 = self.node_terms(stage, x, u, smooth)[1]
         Fx, Fu = np.zeros((ndx, ndx)), np.zeros((ndx, nu))
         Lx, Lu = np.zeros(ndx), np.zeros(nu)
-        Rx = [np.zeros((r.size, ndx)) for _n, _w, r, _c in res0]
-        Ru = [np.zeros((r.size, nu)) for _n, _w, r, _c in res0]
+        Rx = [np.zeros((r.size, ndx)) for _w, r, _c in res0]
+        Ru = [np.zeros((r.size, nu)) for _w, r, _c in res0]
         for k in range(ndx):
             e = np.zeros(ndx, dtype=complex); e[k] = 1j * H
             xk = integrate(rob, x, e)
             xn, c = self.calc(stage, xk, u, smooth, terminal)
             Fx[:, k] = diff(rob, xn0.real.astype(complex), xn).imag / H
             Lx[k] = c.imag / H
-            for i, (_n, _w, r, _c) in enumerate(self.residuals(stage, xk, u, smooth)):
+            for i, (_w, r, _c) in enumerate(self.node_terms(stage, xk, u, smooth)[1]):
                 Rx[i][:, k] = r.imag / H
         if not terminal:
             for k in range(nu):
@@ -572,14 +594,14 @@ class Problem:
                 xn, c = self.calc(stage, x, uk, smooth)
                 Fu[:, k] = diff(rob, xn0.real.astype(complex), xn).imag / H
                 Lu[k] = c.imag / H
-                for i, (_n, _w, r, _c) in enumerate(self.residuals(stage, x, uk, smooth)):
+                for i, (_w, r, _c) in enumerate(self.node_terms(stage, x, uk, smooth)[1]):
                     Ru[i][:, k] = r.imag / H
         Lxx, Luu, Lxu = np.zeros((ndx, ndx)), np.zeros((nu, nu)), np.zeros((ndx, nu))
-        for i, (_n, w, r, c) in enumerate(res0):
+        for i, (wt, r, c) in enumerate(res0):
             arr = self.activation(c, r)[1]
-            Lxx += self.dt * w * Rx[i].T @ (arr[:, None] * Rx[i])
-            Luu += self.dt * w * Ru[i].T @ (arr[:, None] * Ru[i])
-            Lxu += self.dt * w * Rx[i].T @ (arr[:, None] * Ru[i])
+            Lxx += wt * Rx[i].T @ (arr[:, None] * Rx[i])
+            Luu += wt * Ru[i].T @ (arr[:, None] * Ru[i])
+            Lxu += wt * Rx[i].T @ (arr[:, None] * Ru[i])
         return {"xnext": xn0.real, "cost": c0.real, "Fx": Fx, "Fu": Fu, "Lx": Lx, "Lu": Lu, "Lxx": Lxx, "Luu": Luu, "Lxu": Lxu}
 
 

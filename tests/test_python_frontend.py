@@ -33,8 +33,9 @@ def test_reference_surface_without_a_gpu():
     x = problem.x0; x[0] = 0.5
     problem.x0 = x
     assert problem.x0[0] == 0.5
-    with pytest.raises(RuntimeError):   # errors of the factories surface as exceptions, like the reference's
-        tr.createProblem(20, True, "IntegratedActionModelRK4")
+    assert tr.createProblem(20, True, "IntegratedActionModelRK4").T == 400   # both integrators of src/factory/int-action.cpp
+    with pytest.raises((RuntimeError, IndexError)):   # errors of the factories surface as exceptions, like the reference's
+        tr.createProblem(20, True, "IntegratedActionModelMidpoint")
     try:
         import torch
         gpu = torch.cuda.is_available()

@@ -221,6 +221,35 @@ def test_oracle_contact_blocks_equal_complex_step(case, tmp_path, monkeypatch):
     print(rel, {k: f"{v:.1e}" for k, v in worst.items()})
 
 
+@pytest.mark.parametrize("rel", ["hexacopter370_flying_arm_3/trajectories/displacement.yaml", "hexacopter370/trajectories/passthrough.yaml",
+                                 "hextilt_flying_arm_5/trajectories/push_slide.yaml"])
+def test_oracle_rk4_blocks_equal_complex_step(rel):
+    """IntegratedActionModelRK4 (src/factory/int-action.cpp:29-31): the oracle's chain rule through the four stages
+    (rk4.hxx: dyi_dx, dki_dx, the Gauss-Newton pull-back of the stage costs, Lxu and a dense Luu included) against the
+    twin's complex step of its own four-stage calc"""
+    rk4 = "IntegratedActionModelRK4"
+    fp = host.Trajectory(rel).createProblem(20, True, rk4)
+    assert fp.desc.integrator == abi.INTEGRATOR_RK4
+    tw = twin.Problem(rel, YAML_ROOT, URDF_ROOT, 20, integrator=rk4)
+    o = ob.Oracle(fp)
+    rng = np.random.default_rng(5)
+    worst = {}
+    stages = sorted(set(range(len(tw.stages))), key=lambda s: -len(tw.stages[s]["costs"]))[:2]
+    for cs in stages:
+        for smooth, terminal in ((0.1, False), (0.05, True)):
+            x = random_state(tw, rng)
+            u = rng.uniform(tw.u_lb - 0.3 * (tw.u_ub - tw.u_lb), tw.u_ub + 0.3 * (tw.u_ub - tw.u_lb))
+            ref = tw.calc_diff(cs, x, u, smooth, terminal)
+            xnext, cost, _s, tile = o.node_eval(cs, smooth, x, None if terminal else u)
+            got = tile_blocks(tile, fp.ndx, fp.nu)
+            got["xnext"], got["cost"] = xnext, cost
+            for key in (("cost", "Lx", "Lxx") if terminal else ("xnext", "cost", "Fx", "Fu", "Lx", "Lu", "Lxx", "Luu", "Lxu")):
+                e = rel_err(got[key], ref[key])
+                worst[key] = max(worst.get(key, 0.0), e)
+                assert e <= 1e-12, (rel, cs, smooth, terminal, key, e)
+    print(rel, {k: f"{v:.1e}" for k, v in worst.items()})
+
+
 def test_riccati_sweep_and_rollout_equal_dense_numpy():
     rel, dt = "hexacopter370/trajectories/hover.yaml", 20
     fp = host.Trajectory(rel).createProblem(dt)
