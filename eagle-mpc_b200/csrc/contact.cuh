@@ -388,6 +388,151 @@ __device__ __noinline__ void contact_force(const DevModel& M, const empc_contact
   EMPC_ROLLED for (int k = 0; k < 6; ++k) lam[k] = cw.lam[k];
 }
 
+// J <- d integrate(x, dx)/d(dx) J (+ d integrate(x, dx)/dx when add_first) for a row-major NDX x ncols matrix J:
+// StateMultibody::JintegrateTransport(second), then Jintegrate(first, addto) — rows 0..5 <- Jexp6(dx[0:6]) rows 0..5,
+// += blockdiag(Ad(exp6(dx)^-1), I)
+template <class D>
+__device__ __noinline__ void jintegrate_apply_dev(const double* dx, double* J, int ncols, bool add_first) {
+  double JeA[9], JeQ[9];
+  Jexp6_blocks(dx, JeA, JeQ);
+  auto Je = [&](int a, int k) -> double { return (a < 3) ? ((k < 3) ? JeA[3 * a + k] : JeQ[3 * a + k - 3]) : ((k < 3) ? 0.0 : JeA[3 * (a - 3) + k - 3]); };
+  EMPC_ROLLED for (int c = 0; c < ncols; ++c) {
+    double tmp[6];
+    EMPC_ROLLED for (int a = 0; a < 6; ++a) {
+      double s = 0;
+      EMPC_ROLLED for (int k = 0; k < 6; ++k) s += Je(a, k) * J[k * ncols + c];
+      tmp[a] = s;
+    }
+    EMPC_ROLLED for (int a = 0; a < 6; ++a) J[a * ncols + c] = tmp[a];
+  }
+  if (add_first) {
+    SE3 E; exp6(dx, E);
+    double Xs[36]; force_action_matrix(E, Xs);  // Ad(E^-1) = (X*)^T
+    EMPC_ROLLED for (int a = 0; a < 6; ++a)
+      EMPC_ROLLED for (int c = 0; c < 6; ++c) J[a * ncols + c] += Xs[6 * c + a];
+    EMPC_ROLLED for (int i = 6; i < D::NDX; ++i) J[i * ncols + i] += 1.0;
+  }
+}
+
+// Cost value and Gauss-Newton derivative blocks of one (stage of a) node, unscaled by the integrator: ACCUMULATES into
+// Lx (NDX), Lu (NU), Lxx (NDX x NDX), Lxu (NDX x NU), Luu (NU x NU) and returns sum_c w_c a_c(r_c).  nd / cw hold the
+// kinematics of x (cw.J, cw.ov: cw_world_kinematics); lam / lam_x / lam_u are the contact force and its Jacobians (only
+// read by a friction-cone cost).
+template <class D>
+__device__ __noinline__ double node_cost_derivs(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x,
+                                                const double* u, const NodeData<D>& nd, const ContactWork<D>& cw, const double* lam,
+                                                const double* lam_x, const double* lam_u, double* Lx, double* Lu, double* Lxx,
+                                                double* Lxu, double* Luu) {
+  constexpr int NV = D::NV, NDX = D::NDX, NU = D::NU;
+  double csum = 0;
+  const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
+  EMPC_ROLLED for (int c = c0; c < c1; ++c) {
+    const empc_cost_t cs = C.costs[c];
+    if (!cs.active) continue;
+    const double wt = cs.weight;
+    double r[NDX], Ar[NDX], Arr[NDX];
+    SE3 rMf;
+    if (cs.type == EMPC_COST_CONTACT_FRICTION_CONE) {
+      csum += wt * friction_cone_eval(C, cs, lam, r, Ar, Arr);
+      const double* A = C.pool + cs.ref_off;
+      // Rx = A df/dx (5 x NDX), Ru = A df/du (5 x NU)
+      double Rx[5][NDX], Ru[5][NU];
+      EMPC_ROLLED for (int a = 0; a < 5; ++a) {
+        EMPC_ROLLED for (int j = 0; j < NDX; ++j) Rx[a][j] = A[3 * a] * lam_x[j] + A[3 * a + 1] * lam_x[NDX + j] + A[3 * a + 2] * lam_x[2 * NDX + j];
+        EMPC_ROLLED for (int j = 0; j < NU; ++j) Ru[a][j] = A[3 * a] * lam_u[j] + A[3 * a + 1] * lam_u[NU + j] + A[3 * a + 2] * lam_u[2 * NU + j];
+      }
+      EMPC_ROLLED for (int i = 0; i < NDX; ++i) {
+        double s = 0;
+        EMPC_ROLLED for (int k = 0; k < 5; ++k) s += Rx[k][i] * Ar[k];
+        Lx[i] += wt * s;
+        EMPC_ROLLED for (int j = 0; j < NDX; ++j) {
+          double h = 0;
+          EMPC_ROLLED for (int k = 0; k < 5; ++k) h += Rx[k][i] * (Arr[k] * Rx[k][j]);
+          Lxx[i * NDX + j] += wt * h;
+        }
+        EMPC_ROLLED for (int j = 0; j < NU; ++j) {
+          double h = 0;
+          EMPC_ROLLED for (int k = 0; k < 5; ++k) h += Rx[k][i] * (Arr[k] * Ru[k][j]);
+          Lxu[i * NU + j] += wt * h;
+        }
+      }
+      EMPC_ROLLED for (int i = 0; i < NU; ++i) {
+        double s = 0;
+        EMPC_ROLLED for (int k = 0; k < 5; ++k) s += Ru[k][i] * Ar[k];
+        Lu[i] += wt * s;
+        EMPC_ROLLED for (int j = 0; j < NU; ++j) {
+          double h = 0;
+          EMPC_ROLLED for (int k = 0; k < 5; ++k) h += Ru[k][i] * (Arr[k] * Ru[k][j]);
+          Luu[i * NU + j] += wt * h;
+        }
+      }
+      continue;
+    }
+    csum += wt * cost_eval<D>(M, C, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
+    if (cs.type == EMPC_COST_STATE) {
+      // Rx = Jdiff(xref, x, second) = blockdiag(Jlog6(Mref^-1 M), I)
+      SE3 Mref, Mx, Dm;
+      q_to_se3(C.pool + cs.ref_off, Mref); q_to_se3(x, Mx); se3_inv_mul(Mref, Mx, Dm);
+      double Jl[36]; Jlog6(Dm, Jl);
+      EMPC_ROLLED for (int i = 0; i < 6; ++i) {
+        double s = 0;
+        EMPC_ROLLED for (int k = 0; k < 6; ++k) s += Jl[6 * k + i] * Ar[k];
+        Lx[i] += wt * s;
+        EMPC_ROLLED for (int j = 0; j < 6; ++j) {
+          double h = 0;
+          EMPC_ROLLED for (int k = 0; k < 6; ++k) h += Jl[6 * k + i] * (Arr[k] * Jl[6 * k + j]);
+          Lxx[i * NDX + j] += wt * h;
+        }
+      }
+      EMPC_ROLLED for (int i = 6; i < NDX; ++i) { Lx[i] += wt * Ar[i]; Lxx[i * NDX + i] += wt * Arr[i]; }
+    } else if (cs.type == EMPC_COST_CONTROL || cs.type == EMPC_COST_SQUASH_BARRIER) {
+      EMPC_ROLLED for (int i = 0; i < NU; ++i) { Lu[i] += wt * Ar[i]; Luu[i * NU + i] += wt * Arr[i]; }
+    } else {
+      // frame costs: Rx = [Rq | Rv] from the LOCAL frame Jacobian
+      const int f = cs.frame, jfc = M.frame_joint[f];
+      const int nres = (cs.type == EMPC_COST_FRAME_PLACEMENT || cs.type == EMPC_COST_FRAME_VELOCITY) ? 6 : 3;
+      SE3 oMf; cw_frame<D>(M, nd, f, oMf);
+      double Rx[6][NDX];
+      EMPC_ROLLED for (int a = 0; a < 6; ++a) EMPC_ROLLED for (int j = 0; j < NDX; ++j) Rx[a][j] = 0.0;
+      double Jl[36];
+      if (cs.type == EMPC_COST_FRAME_PLACEMENT) Jlog6(rMf, Jl);
+      else if (cs.type == EMPC_COST_FRAME_ROTATION) { double wv[3], th; log3(rMf.R, wv, th); Jlog3(th, wv, Jl); }
+      int ncols = NV;
+      EMPC_ROLLED for (int cc = 0; cc < NV; ++cc) {
+        const int k = cw_joint(cc);
+        if (k > jfc) continue;
+        double fj[6]; actinv_motion(oMf, cw.J[cc], fj);
+        if (cs.type == EMPC_COST_FRAME_PLACEMENT) {
+          EMPC_ROLLED for (int a = 0; a < 6; ++a) { double s = 0; EMPC_ROLLED for (int q = 0; q < 6; ++q) s += Jl[6 * a + q] * fj[q]; Rx[a][cc] = s; }
+        } else if (cs.type == EMPC_COST_FRAME_ROTATION) {
+          EMPC_ROLLED for (int a = 0; a < 3; ++a) Rx[a][cc] = Jl[3 * a] * fj[3] + Jl[3 * a + 1] * fj[4] + Jl[3 * a + 2] * fj[5];
+        } else if (cs.type == EMPC_COST_FRAME_TRANSLATION) {
+          EMPC_ROLLED for (int a = 0; a < 3; ++a) Rx[a][cc] = oMf.R[3 * a] * fj[0] + oMf.R[3 * a + 1] * fj[1] + oMf.R[3 * a + 2] * fj[2];
+        } else {  // FRAME_VELOCITY (LOCAL): d v_f / dq_c = oMf.actInv(V_parent(c) x J_c), d v_f / dv_c = fJ_c
+          if (k > 0) {
+            double cr[6], o[6];
+            cross_mm(cw.ov[k - 1], cw.J[cc], cr); actinv_motion(oMf, cr, o);
+            EMPC_ROLLED for (int a = 0; a < 6; ++a) Rx[a][cc] = o[a];
+          }
+          EMPC_ROLLED for (int a = 0; a < 6; ++a) Rx[a][NV + cc] = fj[a];
+          ncols = NDX;
+        }
+      }
+      EMPC_ROLLED for (int i = 0; i < ncols; ++i) {
+        double s = 0;
+        EMPC_ROLLED for (int k = 0; k < nres; ++k) s += Rx[k][i] * Ar[k];
+        Lx[i] += wt * s;
+        EMPC_ROLLED for (int j = 0; j < ncols; ++j) {
+          double h = 0;
+          EMPC_ROLLED for (int k = 0; k < nres; ++k) h += Rx[k][i] * (Arr[k] * Rx[k][j]);
+          Lxx[i * NDX + j] += wt * h;
+        }
+      }
+    }
+  }
+  return csum;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // calc + calcDiff of the contact nodes, one thread per node (early exit for every other node).  Runs after
 // node_diff_kernel and overwrites what the free-node kernels left for these nodes.
@@ -481,28 +626,8 @@ __global__ void __launch_bounds__(64) contact_node_kernel(Buffers bf, int force,
         lam_u[r * NU + j] = -s;
       }
   }
-  {
-    // JintegrateTransport: rows 0..5 <- Jexp6(dx[0:6]) rows 0..5; Jintegrate: += blockdiag(Ad(exp6(dx)^-1), I)
-    double JeA[9], JeQ[9];
-    Jexp6_blocks(nd.dx, JeA, JeQ);
-    auto Je = [&](int a, int k) -> double { return (a < 3) ? ((k < 3) ? JeA[3 * a + k] : JeQ[3 * a + k - 3]) : ((k < 3) ? 0.0 : JeA[3 * (a - 3) + k - 3]); };
-    EMPC_ROLLED for (int c = 0; c < NDX + NU; ++c) {
-      double* col = (c < NDX) ? Fx + c : Fu + (c - NDX);
-      const int ld = (c < NDX) ? NDX : NU;
-      double tmp[6];
-      EMPC_ROLLED for (int a = 0; a < 6; ++a) {
-        double s = 0;
-        EMPC_ROLLED for (int k = 0; k < 6; ++k) s += Je(a, k) * col[k * ld];
-        tmp[a] = s;
-      }
-      EMPC_ROLLED for (int a = 0; a < 6; ++a) col[a * ld] = tmp[a];
-    }
-    SE3 E; exp6(nd.dx, E);
-    double Xs[36]; force_action_matrix(E, Xs);  // Ad(E^-1) = (X*)^T
-    EMPC_ROLLED for (int a = 0; a < 6; ++a)
-      EMPC_ROLLED for (int c = 0; c < 6; ++c) Fx[a * NDX + c] += Xs[6 * c + a];
-    EMPC_ROLLED for (int i = 6; i < NDX; ++i) Fx[i * NDX + i] += 1.0;
-  }
+  jintegrate_apply_dev<D>(nd.dx, Fx, NDX, true);
+  jintegrate_apply_dev<D>(nd.dx, Fu, NU, false);
 
   // ---- costs: value and Gauss-Newton derivatives (CostModelSum::calc / calcDiff) ----
   EMPC_ROLLED for (int i = 0; i < NDX * NDX; ++i) Lxx[i] = 0.0;
@@ -510,112 +635,7 @@ __global__ void __launch_bounds__(64) contact_node_kernel(Buffers bf, int force,
   EMPC_ROLLED for (int i = 0; i < NU * NU; ++i) Luu[i] = 0.0;
   EMPC_ROLLED for (int i = 0; i < NDX; ++i) Lx[i] = 0.0;
   EMPC_ROLLED for (int i = 0; i < NU; ++i) Lu[i] = 0.0;
-  double csum = 0;
-  const int c0 = bf.ct.costset_begin[costset], c1 = bf.ct.costset_begin[costset + 1];
-  EMPC_ROLLED for (int c = c0; c < c1; ++c) {
-    const empc_cost_t cs = bf.ct.costs[c];
-    if (!cs.active) continue;
-    const double wt = cs.weight;
-    double r[NDX], Ar[NDX], Arr[NDX];
-    SE3 rMf;
-    if (cs.type == EMPC_COST_CONTACT_FRICTION_CONE) {
-      csum += wt * friction_cone_eval(bf.ct, cs, cw.lam, r, Ar, Arr);
-      const double* A = bf.ct.pool + cs.ref_off;
-      // Rx = A df/dx (5 x NDX), Ru = A df/du (5 x NU)
-      double Rx[5][NDX], Ru[5][NU];
-      EMPC_ROLLED for (int a = 0; a < 5; ++a) {
-        EMPC_ROLLED for (int j = 0; j < NDX; ++j) Rx[a][j] = A[3 * a] * lam_x[j] + A[3 * a + 1] * lam_x[NDX + j] + A[3 * a + 2] * lam_x[2 * NDX + j];
-        EMPC_ROLLED for (int j = 0; j < NU; ++j) Ru[a][j] = A[3 * a] * lam_u[j] + A[3 * a + 1] * lam_u[NU + j] + A[3 * a + 2] * lam_u[2 * NU + j];
-      }
-      EMPC_ROLLED for (int i = 0; i < NDX; ++i) {
-        double s = 0;
-        EMPC_ROLLED for (int k = 0; k < 5; ++k) s += Rx[k][i] * Ar[k];
-        Lx[i] += wt * s;
-        EMPC_ROLLED for (int j = 0; j < NDX; ++j) {
-          double h = 0;
-          EMPC_ROLLED for (int k = 0; k < 5; ++k) h += Rx[k][i] * (Arr[k] * Rx[k][j]);
-          Lxx[i * NDX + j] += wt * h;
-        }
-        EMPC_ROLLED for (int j = 0; j < NU; ++j) {
-          double h = 0;
-          EMPC_ROLLED for (int k = 0; k < 5; ++k) h += Rx[k][i] * (Arr[k] * Ru[k][j]);
-          Lxu[i * NU + j] += wt * h;
-        }
-      }
-      EMPC_ROLLED for (int i = 0; i < NU; ++i) {
-        double s = 0;
-        EMPC_ROLLED for (int k = 0; k < 5; ++k) s += Ru[k][i] * Ar[k];
-        Lu[i] += wt * s;
-        EMPC_ROLLED for (int j = 0; j < NU; ++j) {
-          double h = 0;
-          EMPC_ROLLED for (int k = 0; k < 5; ++k) h += Ru[k][i] * (Arr[k] * Ru[k][j]);
-          Luu[i * NU + j] += wt * h;
-        }
-      }
-      continue;
-    }
-    csum += wt * cost_eval<D>(M, bf.ct, cs, smooth, x, u, nd, r, Ar, Arr, rMf);
-    if (cs.type == EMPC_COST_STATE) {
-      // Rx = Jdiff(xref, x, second) = blockdiag(Jlog6(Mref^-1 M), I)
-      SE3 Mref, Mx, Dm;
-      q_to_se3(bf.ct.pool + cs.ref_off, Mref); q_to_se3(x, Mx); se3_inv_mul(Mref, Mx, Dm);
-      double Jl[36]; Jlog6(Dm, Jl);
-      EMPC_ROLLED for (int i = 0; i < 6; ++i) {
-        double s = 0;
-        EMPC_ROLLED for (int k = 0; k < 6; ++k) s += Jl[6 * k + i] * Ar[k];
-        Lx[i] += wt * s;
-        EMPC_ROLLED for (int j = 0; j < 6; ++j) {
-          double h = 0;
-          EMPC_ROLLED for (int k = 0; k < 6; ++k) h += Jl[6 * k + i] * (Arr[k] * Jl[6 * k + j]);
-          Lxx[i * NDX + j] += wt * h;
-        }
-      }
-      EMPC_ROLLED for (int i = 6; i < NDX; ++i) { Lx[i] += wt * Ar[i]; Lxx[i * NDX + i] += wt * Arr[i]; }
-    } else if (cs.type == EMPC_COST_CONTROL || cs.type == EMPC_COST_SQUASH_BARRIER) {
-      EMPC_ROLLED for (int i = 0; i < NU; ++i) { Lu[i] += wt * Ar[i]; Luu[i * NU + i] += wt * Arr[i]; }
-    } else {
-      // frame costs: Rx = [Rq | Rv] from the LOCAL frame Jacobian
-      const int f = cs.frame, jfc = M.frame_joint[f];
-      const int nres = (cs.type == EMPC_COST_FRAME_PLACEMENT || cs.type == EMPC_COST_FRAME_VELOCITY) ? 6 : 3;
-      SE3 oMf; cw_frame<D>(M, nd, f, oMf);
-      double Rx[6][NDX];
-      EMPC_ROLLED for (int a = 0; a < 6; ++a) EMPC_ROLLED for (int j = 0; j < NDX; ++j) Rx[a][j] = 0.0;
-      double Jl[36];
-      if (cs.type == EMPC_COST_FRAME_PLACEMENT) Jlog6(rMf, Jl);
-      else if (cs.type == EMPC_COST_FRAME_ROTATION) { double wv[3], th; log3(rMf.R, wv, th); Jlog3(th, wv, Jl); }
-      int ncols = NV;
-      EMPC_ROLLED for (int cc = 0; cc < NV; ++cc) {
-        const int k = cw_joint(cc);
-        if (k > jfc) continue;
-        double fj[6]; actinv_motion(oMf, cw.J[cc], fj);
-        if (cs.type == EMPC_COST_FRAME_PLACEMENT) {
-          EMPC_ROLLED for (int a = 0; a < 6; ++a) { double s = 0; EMPC_ROLLED for (int q = 0; q < 6; ++q) s += Jl[6 * a + q] * fj[q]; Rx[a][cc] = s; }
-        } else if (cs.type == EMPC_COST_FRAME_ROTATION) {
-          EMPC_ROLLED for (int a = 0; a < 3; ++a) Rx[a][cc] = Jl[3 * a] * fj[3] + Jl[3 * a + 1] * fj[4] + Jl[3 * a + 2] * fj[5];
-        } else if (cs.type == EMPC_COST_FRAME_TRANSLATION) {
-          EMPC_ROLLED for (int a = 0; a < 3; ++a) Rx[a][cc] = oMf.R[3 * a] * fj[0] + oMf.R[3 * a + 1] * fj[1] + oMf.R[3 * a + 2] * fj[2];
-        } else {  // FRAME_VELOCITY (LOCAL): d v_f / dq_c = oMf.actInv(V_parent(c) x J_c), d v_f / dv_c = fJ_c
-          if (k > 0) {
-            double cr[6], o[6];
-            cross_mm(cw.ov[k - 1], cw.J[cc], cr); actinv_motion(oMf, cr, o);
-            EMPC_ROLLED for (int a = 0; a < 6; ++a) Rx[a][cc] = o[a];
-          }
-          EMPC_ROLLED for (int a = 0; a < 6; ++a) Rx[a][NV + cc] = fj[a];
-          ncols = NDX;
-        }
-      }
-      EMPC_ROLLED for (int i = 0; i < ncols; ++i) {
-        double s = 0;
-        EMPC_ROLLED for (int k = 0; k < nres; ++k) s += Rx[k][i] * Ar[k];
-        Lx[i] += wt * s;
-        EMPC_ROLLED for (int j = 0; j < ncols; ++j) {
-          double h = 0;
-          EMPC_ROLLED for (int k = 0; k < nres; ++k) h += Rx[k][i] * (Arr[k] * Rx[k][j]);
-          Lxx[i * NDX + j] += wt * h;
-        }
-      }
-    }
-  }
+  const double csum = node_cost_derivs<D>(M, bf.ct, costset, smooth, x, u, nd, cw, cw.lam, lam_x, lam_u, Lx, Lu, Lxx, Lxu, Luu);
   bf.node_cost[n] = dt * csum;
   EMPC_ROLLED for (int i = 0; i < NDX * NDX; ++i) Lxx[i] *= dt;
   EMPC_ROLLED for (int i = 0; i < NDX * NU; ++i) Lxu[i] *= dt;

@@ -64,6 +64,8 @@ struct Buffers {
 
 #include "contact.cuh"
 
+#include "rk4.cuh"
+
 #include "backward.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ namespace empc {
 
 struct DevModel {
   int nj, na, nq, nv, nx, ndx, nu, nr, T, tile, use_squash, n_frames;
-  int oFx, oFu, oLxx, oLxu, oLuu, oLx, oLu, pad_;
+  int oFx, oFu, oLxx, oLxu, oLuu, oLx, oLu, integrator;  // integrator: EMPC_INTEGRATOR_EULER / _RK4 (rk4.cuh)
   double dt;
   double jR[EMPC_MAX_JOINTS][9], jp[EMPC_MAX_JOINTS][3], axis[EMPC_MAX_JOINTS][3];
   double Y[EMPC_MAX_JOINTS][36];  // body spatial inertia in the joint frame
@@ -559,7 +559,9 @@ EMPC_DI void node_dyn(const DevModel& M, double smooth, const double* x, const d
 
 // Value of one FRAME cost at state x (kinematics recomputed inside).  Deliberately not inlined: the world placements and
 // joint velocities (NodeData, ~1.3 KB) then live in this function's frame only, and only on the rare nodes with frame costs.
-template <class D>
+// (OVERLAY: the contact / RK4 code paths get their own instance, so that the register allocation and frame of the one
+//  the tuned kernels call do not depend on them)
+template <class D, bool OVERLAY = false>
 __device__ __noinline__ double frame_cost_value(const DevModel& M, const CostTables& C, const empc_cost_t& cs, double smooth, const double* x) {
   NodeData<D> nd;
   aba_kinematics<D, false>(M, x, nd);
@@ -584,10 +586,17 @@ EMPC_DI double friction_cone_eval(const CostTables& C, const empc_cost_t& cs, co
 
 // Cost half: dt * sum_c w_c a_c(r_c(x, u)) in the reference's cost order; needs the kinematics only when the cost set
 // holds frame costs.
-// CONTACT: the problem has contact stages, so a cost set may hold a friction-cone cost (its residual needs the contact
-// solve at (x, u): a call the other instantiation does not carry)
+// rk4.cuh: cost of a node under IntegratedActionModelRK4 (the four stage costs)
+template <class D>
+__device__ __noinline__ double rk4_node_cost(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x,
+                                             const double* u);
+// CONTACT: the overlay instantiation — the problem has contact stages, so a cost set may hold a friction-cone cost (its
+// residual needs the contact solve at (x, u)), or it integrates with RK4 (the node cost is the weighted sum of four stage
+// costs): calls the other instantiation does not carry.  raw: the cost sum without the integrator's dt.
 template <class D, bool CONTACT = false>
-EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x, const double* u) {
+EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costset, double smooth, const double* x, const double* u,
+                               bool raw = false) {
+  if (CONTACT && !raw && M.integrator == EMPC_INTEGRATOR_RK4) return rk4_node_cost<D>(M, C, costset, smooth, x, u);
   const int c0 = C.costset_begin[costset], c1 = C.costset_begin[costset + 1];
   double csum = 0;
   double gref[D::NX], gr[D::NDX];  // state costs that share a reference share the residual x (-) ref
@@ -595,7 +604,7 @@ EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costs
   for (int c = c0; c < c1; ++c) {
     const empc_cost_t cs = C.costs[c];
     if (!cs.active) continue;
-    if (is_frame_cost(cs.type)) { csum += cs.weight * frame_cost_value<D>(M, C, cs, smooth, x); continue; }
+    if (is_frame_cost(cs.type)) { csum += cs.weight * frame_cost_value<D, CONTACT>(M, C, cs, smooth, x); continue; }
     double Ar[D::NDX], Arr[D::NDX];
     if (!CONTACT && cs.type == EMPC_COST_CONTACT_FRICTION_CONE) continue;  // (empc_create refuses it without a contact)
     if (CONTACT && cs.type == EMPC_COST_CONTACT_FRICTION_CONE) {  // needs the contact force: the contact solve at (x, u)
@@ -628,7 +637,7 @@ EMPC_DI double node_cost_value(const DevModel& M, const CostTables& C, int costs
       csum += cs.weight * cost_eval<D>(M, C, cs, smooth, x, u, *no_kinematics, r, Ar, Arr, rMf);
     }
   }
-  return M.dt * csum;
+  return raw ? csum : M.dt * csum;
 }
 
 }  // namespace empc

@@ -45,7 +45,8 @@ struct RoCfg {
   static constexpr int SMEM_DOUBLES = 2 * OCPS * STAGE;
 };
 
-// CONTACT: the problem has contact stages; the nodes of those stages integrate the contact dynamics (contact.cuh)
+// CONTACT: the overlay instantiation — the problem has contact stages, whose nodes integrate the contact dynamics
+// (contact.cuh), or it uses the RK4 integrator (rk4.cuh)
 template <class D, int W, bool CONTACT = false>
 __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, const __grid_constant__ DevModel M) {
   constexpr int NX = D::NX, NDX = D::NDX, NU = D::NU;
@@ -174,9 +175,13 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
           __stcs(us_try + (size_t)t * NU + i, u[i]);
         }
         if (CONTACT) {
-          const int ci = bf.ct.costset_contact[bf.node_costset[(size_t)bf.ocp_map[b] * T1 + t]];
-          if (ci >= 0) node_dyn_contact<D>(M, bf.ct.contacts + ci, smooth, xt, u, xn);
-          else node_dyn<D, true>(M, smooth, xt, u, xn);
+          if (M.integrator == EMPC_INTEGRATOR_RK4) {
+            node_dyn_rk4<D>(M, smooth, xt, u, xn);
+          } else {
+            const int ci = bf.ct.costset_contact[bf.node_costset[(size_t)bf.ocp_map[b] * T1 + t]];
+            if (ci >= 0) node_dyn_contact<D>(M, bf.ct.contacts + ci, smooth, xt, u, xn);
+            else node_dyn<D, true>(M, smooth, xt, u, xn);
+          }
         } else {
           node_dyn<D, true>(M, smooth, xt, u, xn);
         }

@@ -57,7 +57,9 @@ struct empc_solver {
   long long* d_times = nullptr;   // n_node_maps controller times
   // contact dynamics (contact.cuh): has_contact = some cost set's model carries a contact; has_coupled = some cost set
   // holds a contact-force cost (backward_kernel<D, true>)
-  bool has_contact = false, has_coupled = false;
+  // rk4: IntegratedActionModelRK4 (rk4.cuh).  overlay = has_contact || rk4 selects the <.., true> instantiations of the
+  // rollout / decide / trial-cost kernels
+  bool has_contact = false, has_coupled = false, rk4 = false, overlay = false;
   int width_a = RO_WIDTH_A;  // stage-A width of the line search (rollout.cuh)
   // small batches (one wave of node_calc_kernel or less): node_cost_kernel runs beside node_calc_kernel on a second stream
   cudaStream_t side_stream = nullptr;
@@ -232,6 +234,10 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
       if (d->costset_contact[cs] >= 0) any_contact = true;
     }
   }
+  if (d->integrator != EMPC_INTEGRATOR_EULER && d->integrator != EMPC_INTEGRATOR_RK4) return fail(EMPC_ERR_INVALID, "bad integrator");
+  const bool is_rk4 = d->integrator == EMPC_INTEGRATOR_RK4;
+  if (is_rk4 && any_contact) return fail(EMPC_ERR_UNSUPPORTED, "IntegratedActionModelRK4 over contact dynamics is not supported");
+  if (is_rk4) { any_coupled = true; for (auto& c : coupled) c = 1; }  // the RK4 pull-back fills Lxu and the whole Luu of every node
   for (int cs = 0; cs < d->n_costsets; ++cs)
     for (int c = d->costset_begin[cs]; c < d->costset_begin[cs + 1]; ++c)
       if (d->costs[c].type == EMPC_COST_CONTACT_FRICTION_CONE) {
@@ -254,12 +260,12 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   h->width_a = ((long long)batch * RO_WIDTH_A_SMALL <= 32LL * 148 * 4) ? RO_WIDTH_A_SMALL : RO_WIDTH_A;
   if (const char* e = std::getenv("EMPC_RO_WIDTH_A")) { const int w = std::atoi(e); if (w == RO_WIDTH_A || w == RO_WIDTH_A_SMALL) h->width_a = w; }
   h->n_costs = d->n_costs; h->n_pool = d->n_pool; h->n_node_maps = d->n_node_maps; h->n_costsets = d->n_costsets;
-  h->has_contact = any_contact; h->has_coupled = any_coupled;
+  h->has_contact = any_contact; h->has_coupled = any_coupled; h->rk4 = is_rk4; h->overlay = any_contact || is_rk4;
 
   DevModel& M = h->hmodel;
   std::memset(&M, 0, sizeof(M));
   M.nj = r.n_joints; M.na = h->na; M.nq = h->nq; M.nv = h->nv; M.nx = h->nx; M.ndx = h->ndx; M.nu = h->nu; M.nr = h->nr;
-  M.T = d->T; M.use_squash = d->use_squash; M.n_frames = r.n_frames; M.dt = d->dt;
+  M.T = d->T; M.use_squash = d->use_squash; M.n_frames = r.n_frames; M.dt = d->dt; M.integrator = d->integrator;
   const int ndx = h->ndx, nu = h->nu;
   M.oFx = 0; M.oFu = ndx * ndx; M.oLxx = M.oFu + ndx * nu; M.oLxu = M.oLxx + ndx * ndx; M.oLuu = M.oLxu + ndx * nu;
   M.oLx = M.oLuu + nu * nu; M.oLu = M.oLx + ndx;
@@ -358,13 +364,15 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   if (d->n_pool) CKH(cudaMemcpyAsync(h->d_pool, d->pool, sizeof(double) * d->n_pool, cudaMemcpyHostToDevice, h->stream));
   CKH(cudaMemcpyAsync(h->d_costset_begin, d->costset_begin, sizeof(int) * (d->n_costsets + 1), cudaMemcpyHostToDevice, h->stream));
   CKH(cudaMemcpyAsync(h->d_node_costset, d->node_costset, sizeof(int) * d->n_node_maps * T1, cudaMemcpyHostToDevice, h->stream));
-  if (any_contact) {
+  if (h->overlay) {
     empc_contact_t* d_contacts = nullptr; int* d_cc = nullptr; unsigned char* d_cpl = nullptr;
-    CKH(dalloc(h, &d_contacts, (size_t)d->n_contacts));
+    std::vector<int> cc((size_t)d->n_costsets, -1);
+    if (any_contact) std::copy(d->costset_contact, d->costset_contact + d->n_costsets, cc.begin());
+    CKH(dalloc(h, &d_contacts, (size_t)std::max(1, d->n_contacts)));
     CKH(dalloc(h, &d_cc, (size_t)d->n_costsets));
     CKH(dalloc(h, &d_cpl, (size_t)d->n_costsets));
-    CKH(cudaMemcpyAsync(d_contacts, d->contacts, sizeof(empc_contact_t) * d->n_contacts, cudaMemcpyHostToDevice, h->stream));
-    CKH(cudaMemcpyAsync(d_cc, d->costset_contact, sizeof(int) * d->n_costsets, cudaMemcpyHostToDevice, h->stream));
+    if (any_contact) CKH(cudaMemcpyAsync(d_contacts, d->contacts, sizeof(empc_contact_t) * d->n_contacts, cudaMemcpyHostToDevice, h->stream));
+    CKH(cudaMemcpy(d_cc, cc.data(), sizeof(int) * d->n_costsets, cudaMemcpyHostToDevice));
     CKH(cudaMemcpyAsync(d_cpl, coupled.data(), (size_t)d->n_costsets, cudaMemcpyHostToDevice, h->stream));
     bf.ct.contacts = d_contacts; bf.ct.costset_contact = d_cc; bf.ct.costset_coupled = d_cpl;
   }
@@ -468,6 +476,7 @@ int empc_replicate_instances(empc_solver_t* h, int32_t n) {
   if (!h) return fail(EMPC_ERR_INVALID, "null");
   if (n < 1) return fail(EMPC_ERR_INVALID, "n_instances < 1");
   if (h->n_node_maps != 1) return fail(EMPC_ERR_INVALID, "instances are replicated from a problem with a single node map");
+  if (h->rk4) return fail(EMPC_ERR_UNSUPPORTED, "batched MPC instances with the RK4 integrator are not supported (cost sets are flagged per set, not per instance)");
   if (h->has_contact) return fail(EMPC_ERR_UNSUPPORTED, "MPC instances with contact stages are not supported (the reference's controllers refuse them, src/mpc-controllers/carrot-mpc.cpp:204-206)");
   if ((long long)n * std::max(h->n_pool, h->n_costs) > 0x7fffffffLL / 2) return fail(EMPC_ERR_INVALID, "replicated tables exceed the 32-bit offsets");
   CK(cudaSetDevice(h->device));
@@ -613,6 +622,11 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   const int T1 = h->T + 1;
   const long long n = (long long)bf.nb * T1;
   // the two thread-per-node halves are independent (different packet fields); when they do not fill the GPU they overlap
+  if (h->rk4) {  // IntegratedActionModelRK4: the whole node model is rk4_node_kernel (rk4.cuh)
+    rk4_node_kernel<D><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(bf, force, smooth, h->hmodel);
+    h->launches++;
+    return cudaGetLastError();
+  }
   const bool fork = h->side_stream && !gb && st == h->stream && n <= 148LL * NC_THREADS * EMPC_NC_BLOCKS;
   cudaError_t e;
   if (fork) {
@@ -658,7 +672,7 @@ static cudaError_t launch_rollout_w(empc_solver* h, const RoParams& P, const Buf
   using S = RoCfg<D, W>;
   const size_t smem = sizeof(double) * S::SMEM_DOUBLES;
   // one warp per block = 32/W OCPs x W step lengths
-  if (h->has_contact) rollout_kernel<D, W, true><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
+  if (h->overlay) rollout_kernel<D, W, true><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
   else rollout_kernel<D, W, false><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
   h->launches++;
   return cudaGetLastError();
@@ -677,7 +691,7 @@ static cudaError_t launch_rollout(empc_solver* h, int stage, int force, int feas
   if (!force) return cudaSuccess;
   const int width = (stage == 0) ? h->width_a : EMPC_N_ALPHAS - h->width_a;
   const long long n_thr = (long long)bf.nb * width * (h->T + 1);
-  if (h->has_contact) trial_cost_kernel<D, true><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
+  if (h->overlay) trial_cost_kernel<D, true><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
   else trial_cost_kernel<D, false><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
   h->launches++;
   const long long n_warps = (long long)bf.nb * width;
@@ -699,7 +713,7 @@ static cudaError_t launch_decide(empc_solver* h, int stage, const Buffers* gb = 
     const double eff = (double)T1 / ((double)rounds * n);
     if (eff >= best - 1e-12) { best = eff; threads = n; }
   }
-  if (h->has_contact) decide_kernel<D, true><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
+  if (h->overlay) decide_kernel<D, true><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
   else decide_kernel<D, false><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
   h->launches++;
   return cudaGetLastError();

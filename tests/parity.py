@@ -6,7 +6,9 @@ compiled with and without FMA contraction (liboracle.so / liboracle_nofma.so) an
 x0 (three sign patterns) give the yardstick d_self = max |o - o_alt| (four samples of the reference's own rounding sensitivity),
 and the GPU must stay within max(1e-9, 4 d_self) of the oracle (16 d_self where d_self > 1e-6: there a single sample of
 the sensitivity is only an order of magnitude).  The tolerance is therefore always bounded by a measured quantity: there
-is no unbounded tolerance.
+is no unbounded tolerance.  The samples of one OCP spread over two orders of magnitude on chaotic solves (1.5e-11 ..
+1.6e-9 on the gains of one synthetic OCP), so the tests of such problems ask for two more samples a few ulp away
+(`perturb`).
 
 Iteration path (`log` = the device iteration log, the stand-in for setCallbacks): every iteration's decisions (accepted step
 length, feasibility, regularisation, phase) must be identical and its cost within max(1e-9, 4 x the running maximum of the
