@@ -376,10 +376,13 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
       EMPC_BW_MARK(2);
       // Fx, Fu of this node are dead: the next node's fragments travel HBM -> registers while Quu is factorised
       if (t > 0) { load_F(t - 1); load_Lxx(t - 1); load_L(t - 1, pre, pre_fs); }
-      // ---- Cholesky of Quu, right-looking in registers: lane i holds row i; per pivot the diagonal entry and the scaled
-      // column travel by shuffles, so the dependent chain of a pivot is shuffle -> rsqrt -> multiply -> shuffle -> FMA (an
-      // FP64 operation has ~20 cycles of latency on B200: the left-looking form with its dot-product chains through shared
-      // memory cost ~50 % more per pivot).  L goes to shared memory row-wise and column-wise for the substitutions. ----
+      // ---- Quu = L D L^T (unit lower L, no square roots), right-looking in registers: lane i holds row i.  Per pivot the
+      // dependent chain is shuffle (pivot) -> reciprocal -> multiply -> FMA; the UNSCALED column entries A(c, j) the update
+      // needs travel by shuffles that do not wait for the reciprocal (an FP64 operation has ~20 cycles of latency on B200
+      // and co-resident warps' DMMAs stretch every dependent step: the LL^T form with its rsqrt -> multiply -> shuffle ->
+      // FMA chain per pivot and a multiply + FMA per substitution step cost ~0.7 k more cycles per node).  Positive pivots
+      // <=> Quu positive definite, the same failure test as the reference's LLT.  L goes to shared memory row-wise and
+      // column-wise for the substitutions, the reciprocal pivots beside it. ----
       int bad = 0;
       {
         const int i = lane < m ? lane : m - 1;
@@ -389,18 +392,21 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
 #pragma unroll
         for (int j = 0; j < m; ++j) {
           const double d = __shfl_sync(0xffffffffu, a[j], j);
+          double acj[m];
+#pragma unroll
+          for (int c = j + 1; c < m; ++c) acj[c] = __shfl_sync(0xffffffffu, a[j], c);  // A(c, j) = d L(c, j): independent of the reciprocal
           if (!(d > 0.0)) bad = 1;
-          const double dinv = rsqrt_h(d);
-          const double lij = (i == j) ? d * dinv : a[j] * dinv;
+          const double dinv = rcp_h(d);
+          const double lij = a[j] * dinv;
           a[j] = lij;
 #pragma unroll
-          for (int c = j + 1; c < m; ++c) { const double lcj = __shfl_sync(0xffffffffu, lij, c); a[c] = fma(-lij, lcj, a[c]); }
-          if (lane < m) sLT[j * LM + i] = lij;  // column j of L = row j of L^T (entries i < j are never read)
+          for (int c = j + 1; c < m; ++c) a[c] = fma(-lij, acj[c], a[c]);
+          if (lane < m) sLT[j * LM + i] = lij;  // column j of L = row j of L^T (entries i <= j are never read)
           if (lane == j) sLinv[j] = dinv;
         }
         if (lane < m) {
 #pragma unroll
-          for (int k = 0; k < LM; k += 2) *reinterpret_cast<double2*>(sL + i * LM + k) = make_double2(a[k], a[k + 1]);  // (entries k > i are never read)
+          for (int k = 0; k < LM; k += 2) *reinterpret_cast<double2*>(sL + i * LM + k) = make_double2(a[k], a[k + 1]);  // (entries k >= i are never read)
         }
         __syncwarp();
       EMPC_BW_MARK(3);
@@ -419,11 +425,11 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
         double linv[LM];
 #pragma unroll
         for (int k = 0; k < LM; k += 2) { const double2 v = *reinterpret_cast<const double2*>(sLinv + k); linv[k] = v.x; linv[k + 1] = v.y; }
-        // column-oriented substitutions: as soon as an entry is final it is subtracted from all the others, so the
-        // dependent chain is one multiply + one FMA per column; column kk of L is row kk of L^T (16-byte broadcasts)
+        // column-oriented substitutions with the unit-lower factor: as soon as an entry is final it is subtracted from all
+        // the others, so the dependent chain is ONE FMA per column (L y = b, then z = D^-1 y, then L^T x = z); column kk of
+        // L is row kk of L^T (16-byte broadcasts)
 #pragma unroll
         for (int kk = 0; kk < m; ++kk) {
-          rhs[kk] *= linv[kk];
 #pragma unroll
           for (int i = (kk + 1) & ~1; i < m; i += 2) {
             const double2 v = *reinterpret_cast<const double2*>(sLT + kk * LM + i);
@@ -432,8 +438,9 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
           }
         }
 #pragma unroll
+        for (int kk = 0; kk < m; ++kk) rhs[kk] *= linv[kk];
+#pragma unroll
         for (int kk = m - 1; kk >= 0; --kk) {
-          rhs[kk] *= linv[kk];
 #pragma unroll
           for (int i = 0; i < kk; i += 2) {
             const double2 v = *reinterpret_cast<const double2*>(sL + kk * LM + i);
