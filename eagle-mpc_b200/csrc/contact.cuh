@@ -536,8 +536,12 @@ __device__ __noinline__ double node_cost_derivs(const DevModel& M, const CostTab
 // ---------------------------------------------------------------------------------------------------------------------
 // calc + calcDiff of the contact nodes, one thread per node (early exit for every other node).  Runs after
 // node_diff_kernel and overwrites what the free-node kernels left for these nodes.
+#ifndef EMPC_CONTACT_THREADS
+#define EMPC_CONTACT_THREADS 128
+#define EMPC_CONTACT_MINB 8
+#endif
 template <class D>
-__global__ void __launch_bounds__(64) contact_node_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
+__global__ void __launch_bounds__(EMPC_CONTACT_THREADS, EMPC_CONTACT_MINB) contact_node_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
   constexpr int NV = D::NV, NDX = D::NDX, NU = D::NU, NX = D::NX, NR = D::NR;
   const long long nl0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int T1 = bf.T + 1;

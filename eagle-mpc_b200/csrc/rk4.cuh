@@ -76,8 +76,14 @@ __device__ __noinline__ double rk4_node_cost(const DevModel& M, const CostTables
 
 // ---------------------------------------------------------------------------------------------------------------------
 // calc + calcDiff of every node of an RK4 problem, one thread per node.
+// (latency-bound on its local-memory operands: 32 resident warps per SM at 64 registers ran 1.8x faster than 8 warps at
+//  255 registers, 785 vs 1415 ms for 1024 move_arm solves; more than that does not help)
+#ifndef EMPC_RK4_THREADS
+#define EMPC_RK4_THREADS 128
+#define EMPC_RK4_MINB 8
+#endif
 template <class D>
-__global__ void __launch_bounds__(64) rk4_node_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
+__global__ void __launch_bounds__(EMPC_RK4_THREADS, EMPC_RK4_MINB) rk4_node_kernel(Buffers bf, int force, double force_smooth, const __grid_constant__ DevModel M) {
   constexpr int NV = D::NV, NDX = D::NDX, NU = D::NU, NX = D::NX, NR = D::NR;
   const long long nl0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int T1 = bf.T + 1;

@@ -623,7 +623,7 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   const long long n = (long long)bf.nb * T1;
   // the two thread-per-node halves are independent (different packet fields); when they do not fill the GPU they overlap
   if (h->rk4) {  // IntegratedActionModelRK4: the whole node model is rk4_node_kernel (rk4.cuh)
-    rk4_node_kernel<D><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(bf, force, smooth, h->hmodel);
+    rk4_node_kernel<D><<<(unsigned)((n + EMPC_RK4_THREADS - 1) / EMPC_RK4_THREADS), EMPC_RK4_THREADS, 0, st>>>(bf, force, smooth, h->hmodel);
     h->launches++;
     return cudaGetLastError();
   }
@@ -650,7 +650,7 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   node_diff_kernel<D><<<(unsigned)groups, W::THREADS, smem, st>>>(bf, force, smooth, h->hmodel);
   h->launches++;
   if (h->has_contact) {  // the nodes of contact stages: calc + calcDiff again under the contact dynamics (contact.cuh)
-    contact_node_kernel<D><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(bf, force, smooth, h->hmodel);
+    contact_node_kernel<D><<<(unsigned)((n + EMPC_CONTACT_THREADS - 1) / EMPC_CONTACT_THREADS), EMPC_CONTACT_THREADS, 0, st>>>(bf, force, smooth, h->hmodel);
     h->launches++;
   }
   return cudaGetLastError();

@@ -91,9 +91,12 @@ class FlatProblem(abi.DescView):
         return _take_str(hlib().empc_host_flat_cost_names(self._p, costset)).splitlines()
 
     def __del__(self):
-        if getattr(self, "_p", None) and self._p.value:
-            hlib().empc_host_flat_free(self._p)
-            self._p = C.c_void_p()
+        try:
+            if getattr(self, "_p", None) and self._p.value:
+                hlib().empc_host_flat_free(self._p)
+                self._p = C.c_void_p()
+        except Exception:  # interpreter shutdown: the library handle is already gone
+            pass
 
 
 class Trajectory:
@@ -122,9 +125,12 @@ class Trajectory:
         return FlatProblem(p, self)
 
     def __del__(self):
-        if getattr(self, "_p", None) and self._p.value:
-            hlib().empc_host_trajectory_free(self._p)
-            self._p = C.c_void_p()
+        try:
+            if getattr(self, "_p", None) and self._p.value:
+                hlib().empc_host_trajectory_free(self._p)
+                self._p = C.c_void_p()
+        except Exception:  # interpreter shutdown: the library handle is already gone
+            pass
 
 
 class SolverSbFDDP:
@@ -154,6 +160,9 @@ class SolverSbFDDP:
         return xs, us, uss, cost[0], int(it[0]), bool(fe[0])
 
     def __del__(self):
-        if getattr(self, "_p", None) and self._p.value:
-            hlib().empc_host_solver_free(self._p)
-            self._p = C.c_void_p()
+        try:
+            if getattr(self, "_p", None) and self._p.value:
+                hlib().empc_host_solver_free(self._p)
+                self._p = C.c_void_p()
+        except Exception:  # interpreter shutdown: the library handle is already gone
+            pass
