@@ -108,7 +108,7 @@ class SolverParams(C.Structure):
         ("squash_quirk", C.c_int32),
         ("stop_criteria", C.c_int32),
         ("stop_test", C.c_int32),
-        ("reserved", C.c_int32),
+        ("solver_type", C.c_int32),
         ("convergence_init", C.c_double),
         ("convergence_stop", C.c_double),
         ("convergence_mult", C.c_double),
@@ -126,11 +126,18 @@ class SolverParams(C.Structure):
         ("th_stepdec", C.c_double),
         ("th_stepinc", C.c_double),
         ("th_stop_gaps", C.c_double),
+        ("th_stop", C.c_double),
+        ("boxqp_th_acceptstep", C.c_double),
+        ("boxqp_th_grad", C.c_double),
+        ("boxqp_reg", C.c_double),
+        ("boxqp_maxiter", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
 STOP_CRITERIA_COST_REDUCTION, STOP_CRITERIA_QU_NORM = 0, 1
 STOP_TEST_GAPS, STOP_TEST_FEASIBLE = 0, 1
+SOLVER_SBFDDP, SOLVER_BOXFDDP, SOLVER_BOXDDP = 0, 1, 2
 
 
 class IterRecord(C.Structure):

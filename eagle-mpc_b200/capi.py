@@ -75,6 +75,13 @@ def default_params():
     return p
 
 
+def box_params(solver_type=abi.SOLVER_BOXFDDP):
+    """Defaults of crocoddyl::SolverBoxFDDP / SolverBoxDDP (empc_box_params)."""
+    p = abi.SolverParams()
+    lib().empc_box_params(C.byref(p), solver_type)
+    return p
+
+
 def _ck(rc):
     if rc != 0:
         raise EmpcError(f"empc error {rc}: {lib().empc_last_error().decode()}")

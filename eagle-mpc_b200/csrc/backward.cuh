@@ -92,7 +92,122 @@ struct BwParams {
   double reg_max, reg_factor, th_gaptol;
   int force;  // phase hook: single attempt, xreg / is_feasible taken from the state as they are, no prologue
   int stop_qu_norm;  // EMPC_STOP_CRITERIA_QU_NORM: also leave sum_t ||Qu_t||^2 in the OCP state
+  // SolverBoxFDDP / SolverBoxDDP (backward_kernel<D, true, true>): crocoddyl::BoxQP(nu, maxiter, th_acceptstep, th_grad, reg)
+  int qp_maxiter;
+  double qp_th_acceptstep, qp_th_grad, qp_reg;
 };
+
+// crocoddyl::BoxQP::solve for one node, run by ONE lane (the problem is nu x nu: 4 .. 11 unknowns): projected Newton on
+//   min 1/2 x' H x + q' x,  u_lb - u <= x <= u_ub - u,  from the clamped warm start xinit (the k_[t] of the previous sweep).
+// Mirrors the oracle's box_qp (oracle/oracle.cpp) decision by decision: clamped = on a bound with the gradient pushing
+// outwards, converged when the gradient's infinity norm <= th_grad or nothing is free, Newton step on the free block through
+// its LLT, projected line search alpha = 1 .. 1/512 with the Armijo test.  Two exits the reference does not have, both at
+// iterates it would keep (bit for bit, or to the last few ulp) for the rest of its maxiter iterations: no step length was
+// accepted (the loop is deterministic: every further iteration repeats this one), and a Newton step below 1e-15 relative
+// (the iterate is the minimiser on its free set; the reference random-walks on the last bit from here).
+// Outputs: kout = -x, Hinv (m x LM, shared memory) = inverse of the free block of H scattered into the full matrix (zero rows
+// and columns for the clamped unknowns), q with its clamped entries zeroed.  Returns 1 when a free block is not positive
+// definite (the reference's "backward_error").
+template <int m, int LM>
+__device__ __noinline__ int bw_box_qp(const double* H, double* q, const double* u, const double* u_lb, const double* u_ub, const double* xinit,
+                                       double* kout, double* Hinv, const BwParams& P) {
+  double x[m], lo[m], hi[m], g[m], dx[m], xn[m], L[m * m], Ai[m * m];
+  int fidx[m], cidx[m];
+  int nf = 0, nc = 0, nf_inv = -1;
+  for (int i = 0; i < m; ++i) { lo[i] = u_lb[i] - u[i]; hi[i] = u_ub[i] - u[i]; x[i] = fmax(fmin(xinit[i], hi[i]), lo[i]); }
+  auto value = [&](const double* v) {
+    double a = 0, b2 = 0;
+    for (int i = 0; i < m; ++i) {
+      double r = 0;
+      for (int j = 0; j < m; ++j) r += H[i * LM + j] * v[j];
+      a += v[i] * r; b2 += q[i] * v[i];
+    }
+    return 0.5 * a + b2;
+  };
+  auto factor_free = [&]() -> bool {  // Hff (+ reg) = L L', Ai = (L L')^-1
+    for (int i = 0; i < nf; ++i)
+      for (int j = 0; j < nf; ++j) L[i * m + j] = H[fidx[i] * LM + fidx[j]] + ((i == j) ? P.qp_reg : 0.0);
+    for (int j = 0; j < nf; ++j) {
+      double d = L[j * m + j];
+      for (int k = 0; k < j; ++k) d -= L[j * m + k] * L[j * m + k];
+      if (!(d > 0.0)) return false;
+      d = sqrt(d);
+      L[j * m + j] = d;
+      for (int i = j + 1; i < nf; ++i) {
+        double s = L[i * m + j];
+        for (int k = 0; k < j; ++k) s -= L[i * m + k] * L[j * m + k];
+        L[i * m + j] = s / d;
+      }
+    }
+    for (int c = 0; c < nf; ++c) {  // column c of the inverse: L y = e_c, L' z = y
+      for (int i = 0; i < nf; ++i) {
+        double s = (i == c) ? 1.0 : 0.0;
+        for (int k = 0; k < i; ++k) s -= L[i * m + k] * Ai[k * m + c];
+        Ai[i * m + c] = s / L[i * m + i];
+      }
+      for (int i = nf - 1; i >= 0; --i) {
+        double s = Ai[i * m + c];
+        for (int k = i + 1; k < nf; ++k) s -= L[k * m + i] * Ai[k * m + c];
+        Ai[i * m + c] = s / L[i * m + i];
+      }
+    }
+    nf_inv = nf;
+    return true;
+  };
+  for (int it = 0; it < P.qp_maxiter; ++it) {
+    double gmax = 0;
+    for (int i = 0; i < m; ++i) {
+      double r = q[i];
+      for (int j = 0; j < m; ++j) r += H[i * LM + j] * x[j];
+      g[i] = r;
+      gmax = fmax(gmax, fabs(r));
+    }
+    nf = 0; nc = 0;
+    for (int j = 0; j < m; ++j) {
+      if ((x[j] == lo[j] && g[j] > 0.0) || (x[j] == hi[j] && g[j] < 0.0)) cidx[nc++] = j;
+      else fidx[nf++] = j;
+    }
+    if (gmax <= P.qp_th_grad || nf == 0) {
+      if ((it == 0 || nf_inv != nf) && !factor_free()) return 1;
+      break;
+    }
+    if (!factor_free()) return 1;
+    bool tiny = true;
+    for (int i = 0; i < m; ++i) dx[i] = 0.0;
+    for (int i = 0; i < nf; ++i) {
+      double r = 0.0;
+      for (int j = 0; j < nf; ++j) {
+        double rhs = -q[fidx[j]];
+        for (int c = 0; c < nc; ++c) rhs -= H[fidx[j] * LM + cidx[c]] * x[cidx[c]];
+        r += Ai[i * m + j] * rhs;
+      }
+      const double d = r - x[fidx[i]];
+      dx[fidx[i]] = d;
+      if (fabs(d) > 1e-15 * fmax(1.0, fabs(x[fidx[i]]))) tiny = false;
+    }
+    if (tiny) break;
+    const double fold = value(x);
+    bool moved = false;
+    for (int n = 0; n < EMPC_N_ALPHAS; ++n) {
+      const double a = 1.0 / (double)(1 << n);
+      double gd = 0;
+      for (int i = 0; i < m; ++i) { xn[i] = fmax(fmin(x[i] + a * dx[i], hi[i]), lo[i]); gd += g[i] * (x[i] - xn[i]); }
+      const double fnew = value(xn);
+      if (fold - fnew > P.qp_th_acceptstep * gd) {
+        for (int i = 0; i < m; ++i) x[i] = xn[i];
+        moved = true;
+        break;
+      }
+    }
+    if (!moved) break;
+  }
+  for (int i = 0; i < m * LM; ++i) Hinv[i] = 0.0;
+  for (int i = 0; i < nf; ++i)
+    for (int j = 0; j < nf; ++j) Hinv[fidx[i] * LM + fidx[j]] = Ai[i * m + j];
+  for (int i = 0; i < m; ++i) kout[i] = -x[i];
+  for (int c = 0; c < nc; ++c) q[cidx[c]] = 0.0;
+  return 0;
+}
 
 // optional phase timing (-DEMPC_BW_PROFILE): lane 0 of block 0 accumulates clock64() differences between the marks of a
 // node into bf.nodesc of the last OCP... (diagnostic builds only; scripts/diag/backward_phases.py)
@@ -120,7 +235,9 @@ EMPC_DI constexpr int bw_swz(int r) { return (r & 2) << 1; }
 
 // COUPLED: some cost set holds a contact-force cost, the only kind that couples x and u (contact.cuh): its nodes add the
 // Lxu block and the off-diagonal part of Luu that every other node leaves at zero
-template <class D, bool COUPLED = false>
+// BOX: SolverBoxFDDP / SolverBoxDDP::computeGains — when the candidate is feasible the gains of a node come from the box QP
+// on its Quu / Qu (bw_box_qp) instead of the LDL^T solves
+template <class D, bool COUPLED = false, bool BOX = false>
 __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_kernel(Buffers bf, BwParams P) {
   using S = BwCfg<D>;
   constexpr int n = S::n, m = S::m, LD = S::LD, LM = S::LM, PW = S::PW;
@@ -384,6 +501,34 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
       // <=> Quu positive definite, the same failure test as the reference's LLT.  L goes to shared memory row-wise and
       // column-wise for the substitutions, the reciprocal pivots beside it. ----
       int bad = 0;
+      bool boxed = false;
+      if constexpr (BOX) {
+        if (feasible) {  // uniform over the warp (one OCP); an infeasible candidate takes the plain gains below
+          boxed = true;
+          if (lane == 0) {
+            const size_t nodeu = (size_t)b * T + t;
+            bad = bw_box_qp<m, LM>(sQuu, Qu, bf.us + nodeu * m, bf.model->u_lb, bf.model->u_ub, bf.k + nodeu * m, kv, sL, P);
+          }
+          bad = __shfl_sync(0xffffffffu, bad, 0);
+          if (bad) { failed = 1; break; }
+          __syncwarp();
+          // K = Quu_inv Qxu^T, Quu_inv = the inverse of the free block (zero rows / columns for the clamped controls)
+          for (int c = lane; c < n; c += 32) {
+            double qc[m];
+#pragma unroll
+            for (int j = 0; j < m; ++j) qc[j] = sQux[j * LD + (c ^ bw_swz(j))];
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+              double s2 = 0.0;
+#pragma unroll
+              for (int j = 0; j < m; ++j) s2 = fma(sL[i * LM + j], qc[j], s2);
+              sK[i * LD + (c ^ bw_swz(i))] = s2;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (!boxed) {
       {
         const int i = lane < m ? lane : m - 1;
         double a[LM];
@@ -456,6 +601,7 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
           for (int i = 0; i < m; ++i) kv[i] = rhs[i];
         }
       }
+      }  // !boxed
       __syncwarp();
       EMPC_BW_MARK(4);
       if (lane < m) {  // Quuk = Quu k

@@ -89,6 +89,11 @@ __device__ __forceinline__ void decrease_reg(OcpState& st, const empc_solver_par
 // end of solveFDDP / solveDDP for one OCP: advance the SbFDDP outer schedule (src/sbfddp.cpp:205-222)
 __device__ __forceinline__ void end_inner_solve(OcpState& st, const empc_solver_params_t& P) {
   st.total_iters += st.iter + 1;
+  if (P.solver_type != EMPC_SOLVER_SBFDDP) {  // crocoddyl's SolverBoxFDDP / SolverBoxDDP: solve() is this one pass
+    st.phase = PHASE_DONE;
+    st.iters_out = st.total_iters - 1;
+    return;
+  }
   bool start_ddp = false;
   if (st.phase == PHASE_FDDP) {
     st.smooth_next *= P.smooth_mult;
@@ -307,6 +312,13 @@ __device__ __forceinline__ void init_ocp_state(OcpState& st, const empc_solver_p
   st.iter = 0; st.total_iters = 0; st.is_feasible = 0; st.was_feasible = 0; st.recalc = 1; st.bw_fail = 0;
   st.iters_out = 0; st.accepted = -1; st.pending = 0;
   st.qu2 = 0; st.d0_last = 0; st.d1_last = 0; st.log_count = 0; st.pad_ = 0;
+  if (P.solver_type != EMPC_SOLVER_SBFDDP) {
+    // crocoddyl::SolverBoxFDDP / SolverBoxDDP (src/mpc-controllers/carrot-mpc.cpp:236-241): one SolverFDDP::solve or
+    // SolverDDP::solve pass with th_stop_ = 5e-5 that honours the caller's feasibility flag (setCandidate)
+    st.th_stop = P.th_stop; st.is_feasible = is_feasible_arg;
+    st.phase = (P.solver_type == EMPC_SOLVER_BOXDDP) ? PHASE_DDP : PHASE_FDDP;
+    return;
+  }
   // solveFDDP(maxiter, false, ...) overrides the caller's flag (src/sbfddp.cpp:210,230)
   if (P.convergence_init >= P.convergence_stop) st.phase = PHASE_FDDP;
   else { st.phase = is_feasible_arg ? PHASE_DONE : PHASE_DDP; st.is_feasible = is_feasible_arg; }

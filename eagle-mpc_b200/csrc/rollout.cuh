@@ -28,6 +28,7 @@ struct RoParams {
   int force, force_feasible, force_ddp;
   double force_smooth;
   int a_begin;  // first step-length index of this launch (0: stage A, the width of stage A: stage B)
+  int box;      // SolverBoxFDDP / SolverBoxDDP::forwardPass: trial controls are clamped to [u_lb, u_ub] (overlay instantiation only)
 };
 
 // Step lengths tried by stage A; stage B covers the rest.  4 when the batch fills the GPU (one warp per sub-partition
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(32, 4) rollout_kernel(Buffers bf, RoParams P, 
 #pragma unroll
           for (int jj = 0; jj < NDX; ++jj) kd += in[S::oK + i * NDX + jj] * dx[jj];
           u[i] = in[S::oUs + i] - in[S::oKk + i] * alpha - kd;
+          if (CONTACT) { if (P.box) u[i] = fmin(fmax(u[i], M.u_lb[i]), M.u_ub[i]); }  // us_try.cwiseMax(u_lb).cwiseMin(u_ub)
           __stcs(us_try + (size_t)t * NU + i, u[i]);
         }
         if (CONTACT) {

@@ -152,6 +152,7 @@ static cudaError_t set_kernel_attributes() {
   if ((e = opt_in_smem(node_diff_kernel<D>, sizeof(double) * DiffCfg<D>::SMEM_DOUBLES)) != cudaSuccess) return e;
   if ((e = opt_in_smem(backward_kernel<D, false>, sizeof(double) * BwCfg<D>::TOTAL)) != cudaSuccess) return e;
   if ((e = opt_in_smem(backward_kernel<D, true>, sizeof(double) * BwCfg<D>::TOTAL)) != cudaSuccess) return e;
+  if ((e = opt_in_smem(backward_kernel<D, true, true>, sizeof(double) * BwCfg<D>::TOTAL)) != cudaSuccess) return e;
   if ((e = opt_in_smem(rollout_kernel<D, RO_WIDTH_A, false>, sizeof(double) * RoCfg<D, RO_WIDTH_A>::SMEM_DOUBLES)) != cudaSuccess) return e;
   if ((e = opt_in_smem(rollout_kernel<D, RO_WIDTH_A, true>, sizeof(double) * RoCfg<D, RO_WIDTH_A>::SMEM_DOUBLES)) != cudaSuccess) return e;
   if ((e = opt_in_smem(rollout_kernel<D, 8, true>, sizeof(double) * RoCfg<D, 8>::SMEM_DOUBLES)) != cudaSuccess) return e;
@@ -184,6 +185,14 @@ void empc_default_params(empc_solver_params_t* p) {
   p->reg_init = 1e-9; p->reg_min = 1e-9; p->reg_max = 1e9; p->reg_factor = 10;
   p->th_acceptstep = 0.1; p->th_acceptnegstep = 2; p->th_grad = 1e-12; p->th_gaptol = 1e-16;
   p->th_stepdec = 0.5; p->th_stepinc = 0.01; p->th_stop_gaps = 1.0;
+  p->solver_type = EMPC_SOLVER_SBFDDP;
+  p->th_stop = 5e-5; p->boxqp_maxiter = 100; p->boxqp_th_acceptstep = 0.1; p->boxqp_th_grad = 1e-5; p->boxqp_reg = 0.0;
+}
+
+void empc_box_params(empc_solver_params_t* p, int32_t solver_type) {
+  empc_default_params(p);
+  p->solver_type = solver_type;
+  p->stop_criteria = EMPC_STOP_CRITERIA_QU_NORM; p->stop_test = EMPC_STOP_TEST_FEASIBLE;  // upstream SolverFDDP / SolverDDP::solve
 }
 
 int empc_destroy(empc_solver_t* h) {
@@ -364,7 +373,7 @@ int empc_create(const empc_problem_desc_t* d, int32_t batch, int32_t device, emp
   if (d->n_pool) CKH(cudaMemcpyAsync(h->d_pool, d->pool, sizeof(double) * d->n_pool, cudaMemcpyHostToDevice, h->stream));
   CKH(cudaMemcpyAsync(h->d_costset_begin, d->costset_begin, sizeof(int) * (d->n_costsets + 1), cudaMemcpyHostToDevice, h->stream));
   CKH(cudaMemcpyAsync(h->d_node_costset, d->node_costset, sizeof(int) * d->n_node_maps * T1, cudaMemcpyHostToDevice, h->stream));
-  if (h->overlay) {
+  {  // overlay tables (contact / coupled-cost flags per cost set): also read by the Box solvers' kernel instantiations
     empc_contact_t* d_contacts = nullptr; int* d_cc = nullptr; unsigned char* d_cpl = nullptr;
     std::vector<int> cc((size_t)d->n_costsets, -1);
     if (any_contact) std::copy(d->costset_contact, d->costset_contact + d->n_costsets, cc.begin());
@@ -434,6 +443,9 @@ int empc_set_candidate(empc_solver_t* h, const double* xs, const double* us, int
 int empc_set_params(empc_solver_t* h, const empc_solver_params_t* p) {
   if (!h || !p) return fail(EMPC_ERR_INVALID, "null");
   if (p->maxiter < 1) return fail(EMPC_ERR_INVALID, "maxiter < 1");
+  if (p->solver_type != EMPC_SOLVER_SBFDDP && p->solver_type != EMPC_SOLVER_BOXFDDP && p->solver_type != EMPC_SOLVER_BOXDDP)
+    return fail(EMPC_ERR_INVALID, "solver_type is not one of EMPC_SOLVER_*");
+  if (p->solver_type != EMPC_SOLVER_SBFDDP && p->boxqp_maxiter < 1) return fail(EMPC_ERR_INVALID, "boxqp_maxiter < 1");
   h->P = *p;
   if (h->hmodel.barrier_weight != p->barrier_weight) {  // the device copy of the model only changes with this field
     h->hmodel.barrier_weight = p->barrier_weight;
@@ -655,14 +667,20 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   }
   return cudaGetLastError();
 }
+// the Box solvers run on the overlay instantiations of the rollout / decide / trial-cost kernels (the clamp of the trial
+// controls lives there), so that the kernels of the SbFDDP free path stay as they are
+static inline bool box_solver(const empc_solver* h) { return h->P.solver_type != EMPC_SOLVER_SBFDDP; }
+static inline bool use_overlay(const empc_solver* h) { return h->overlay || box_solver(h); }
 template <class D>
 static cudaError_t launch_backward(empc_solver* h, int force, const Buffers* gb = nullptr, cudaStream_t st = nullptr) {
   const Buffers& bf = gb ? *gb : h->bf;
   if (!st) st = h->stream;
   using S = BwCfg<D>;
   const size_t smem = sizeof(double) * S::TOTAL;
-  BwParams P{h->P.reg_max, h->P.reg_factor, h->P.th_gaptol, force, h->P.stop_criteria == EMPC_STOP_CRITERIA_QU_NORM};
-  if (h->has_coupled) backward_kernel<D, true><<<bf.nb, 32, smem, st>>>(bf, P);
+  BwParams P{h->P.reg_max, h->P.reg_factor, h->P.th_gaptol, force, h->P.stop_criteria == EMPC_STOP_CRITERIA_QU_NORM,
+             h->P.boxqp_maxiter, h->P.boxqp_th_acceptstep, h->P.boxqp_th_grad, h->P.boxqp_reg};
+  if (box_solver(h)) backward_kernel<D, true, true><<<bf.nb, 32, smem, st>>>(bf, P);  // SolverBoxFDDP / SolverBoxDDP gains
+  else if (h->has_coupled) backward_kernel<D, true><<<bf.nb, 32, smem, st>>>(bf, P);
   else backward_kernel<D, false><<<bf.nb, 32, smem, st>>>(bf, P);  // one warp per OCP
   h->launches++;
   return cudaGetLastError();
@@ -672,7 +690,7 @@ static cudaError_t launch_rollout_w(empc_solver* h, const RoParams& P, const Buf
   using S = RoCfg<D, W>;
   const size_t smem = sizeof(double) * S::SMEM_DOUBLES;
   // one warp per block = 32/W OCPs x W step lengths
-  if (h->overlay) rollout_kernel<D, W, true><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
+  if (use_overlay(h)) rollout_kernel<D, W, true><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
   else rollout_kernel<D, W, false><<<(bf.nb + S::OCPS - 1) / S::OCPS, 32, smem, st>>>(bf, P, h->hmodel);
   h->launches++;
   return cudaGetLastError();
@@ -683,7 +701,7 @@ static cudaError_t launch_rollout(empc_solver* h, int stage, int force, int feas
                                   cudaStream_t st = nullptr) {
   const Buffers& bf = gb ? *gb : h->bf;
   if (!st) st = h->stream;
-  RoParams P{force, feasible, ddp, smooth, stage == 0 ? 0 : h->width_a};
+  RoParams P{force, feasible, ddp, smooth, stage == 0 ? 0 : h->width_a, box_solver(h) ? 1 : 0};
   cudaError_t e = (stage == 0 && h->width_a == RO_WIDTH_A) ? launch_rollout_w<D, RO_WIDTH_A>(h, P, bf, st) : launch_rollout_w<D, 8>(h, P, bf, st);
   if (e != cudaSuccess) return e;
   // In a solve, decide_kernel evaluates the trial costs lazily in line-search order.  The tile-level parity hook wants
@@ -691,7 +709,7 @@ static cudaError_t launch_rollout(empc_solver* h, int stage, int force, int feas
   if (!force) return cudaSuccess;
   const int width = (stage == 0) ? h->width_a : EMPC_N_ALPHAS - h->width_a;
   const long long n_thr = (long long)bf.nb * width * (h->T + 1);
-  if (h->overlay) trial_cost_kernel<D, true><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
+  if (use_overlay(h)) trial_cost_kernel<D, true><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
   else trial_cost_kernel<D, false><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
   h->launches++;
   const long long n_warps = (long long)bf.nb * width;
@@ -713,7 +731,7 @@ static cudaError_t launch_decide(empc_solver* h, int stage, const Buffers* gb = 
     const double eff = (double)T1 / ((double)rounds * n);
     if (eff >= best - 1e-12) { best = eff; threads = n; }
   }
-  if (h->overlay) decide_kernel<D, true><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
+  if (use_overlay(h)) decide_kernel<D, true><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
   else decide_kernel<D, false><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
   h->launches++;
   return cudaGetLastError();

@@ -43,6 +43,8 @@ def hlib():
         L.empc_host_flat_cost_names.argtypes = [C.c_void_p, C.c_int32]
         L.empc_host_solver_create.restype = C.c_void_p
         L.empc_host_solver_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_int32]
+        L.empc_host_box_solver_create.restype = C.c_void_p
+        L.empc_host_box_solver_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_int32]
         L.empc_host_solver_free.argtypes = [C.c_void_p]
         L.empc_host_solver_handle.restype = C.c_void_p
         L.empc_host_solver_handle.argtypes = [C.c_void_p]
@@ -118,7 +120,12 @@ class Trajectory:
         """current stages (WeightedMpc merges the transition stages of the trajectory it is given, in place)"""
         return _take_str(hlib().empc_host_trajectory_stage_names(self._p)).split()
 
-    def createProblem(self, dt, squash=True, integrator="IntegratedActionModelEuler", add_barrier=True):
+    def createProblem(self, dt, squash=True, integrator="IntegratedActionModelEuler", add_barrier=None):
+        """add_barrier: SolverSbFDDP::barrierInit on the problem before flattening (default: exactly when squash is set — the
+        box solvers take the problem as createProblem leaves it).  The "barrier" cost lands in the stages' shared cost sums
+        and stays there, as it does in the reference (src/sbfddp.cpp:181-186 on the models of src/trajectory.cpp:102-143)."""
+        if add_barrier is None:
+            add_barrier = bool(squash)
         p = hlib().empc_host_flatten(self._p, int(dt), int(squash), integrator.encode(), int(add_barrier))
         if not p:
             raise EmpcError(_err())
@@ -147,6 +154,11 @@ class SolverSbFDDP:
     def set_convergence_init(self, c):
         hlib().empc_host_solver_set_convergence_init(self._p, c)
 
+    @property
+    def handle(self):
+        """the empc_solver_t* behind the facade (for the C-ABI getters of capi.py)"""
+        return C.c_void_p(hlib().empc_host_solver_handle(self._p))
+
     def solve(self, maxiter=100):
         if hlib().empc_host_solver_solve(self._p, maxiter):
             raise EmpcError(_err())
@@ -166,3 +178,21 @@ class SolverSbFDDP:
                 self._p = C.c_void_p()
         except Exception:  # interpreter shutdown: the library handle is already gone
             pass
+
+
+class SolverBoxFDDP(SolverSbFDDP):
+    """crocoddyl.SolverBoxFDDP on the problem created with squash = False (examples/python/trajectory.py:19-24), CUDA behind it."""
+    SOLVER_TYPE = abi.SOLVER_BOXFDDP
+
+    def __init__(self, trajectory, dt, integrator="IntegratedActionModelEuler", batch=1, device=0):
+        p = hlib().empc_host_box_solver_create(trajectory._p, int(dt), self.SOLVER_TYPE, integrator.encode(), batch, device)
+        if not p:
+            raise EmpcError(_err())
+        self._p = C.c_void_p(p)
+        self._traj = trajectory
+        self.batch = batch
+
+
+class SolverBoxDDP(SolverBoxFDDP):
+    """crocoddyl.SolverBoxDDP, same construction."""
+    SOLVER_TYPE = abi.SOLVER_BOXDDP

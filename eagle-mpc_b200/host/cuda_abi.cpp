@@ -39,6 +39,7 @@ const CudaAbi& cuda_abi() {
     try {
       bind(lib, "empc_last_error", abi.last_error);
       bind(lib, "empc_default_params", abi.default_params);
+      bind(lib, "empc_box_params", abi.box_params);
       bind(lib, "empc_create", abi.create);
       bind(lib, "empc_destroy", abi.destroy);
       bind(lib, "empc_set_x0", abi.set_x0);

@@ -12,6 +12,7 @@ namespace eagle_mpc {
 struct CudaAbi {
   decltype(&empc_last_error) last_error;
   decltype(&empc_default_params) default_params;
+  decltype(&empc_box_params) box_params;
   decltype(&empc_create) create;
   decltype(&empc_destroy) destroy;
   decltype(&empc_set_x0) set_x0;

@@ -333,7 +333,7 @@ class SolverSbFDDP {
  public:
   SolverSbFDDP(const std::shared_ptr<ShootingProblem>& problem, const std::shared_ptr<SquashingModelSmoothSat>& squashing_model,
                int batch = 1, int device = 0);
-  ~SolverSbFDDP();
+  virtual ~SolverSbFDDP();
   // crocoddyl::SolverAbstract::solve signature (include/eagle_mpc/sbfddp.hpp:43-47); regInit is ignored like upstream.
   bool solve(const std::vector<VectorXd>& init_xs = {}, const std::vector<VectorXd>& init_us = {}, std::size_t maxiter = 100,
              bool is_feasible = false, double regInit = 1e-9);
@@ -366,9 +366,17 @@ class SolverSbFDDP {
   void fetch(bool with_gains = true);     // device -> host mirrors (OCP 0)
   empc_solver_params_t& params() { return params_; }
 
+ protected:
+  // solver_type = EMPC_SOLVER_BOXFDDP / EMPC_SOLVER_BOXDDP: crocoddyl's box solvers on the same device path (no squashing model,
+  // no barrier cost, upstream stop rule; see SolverBoxFDDP / SolverBoxDDP below)
+  SolverSbFDDP(const std::shared_ptr<ShootingProblem>& problem, const std::shared_ptr<SquashingModelSmoothSat>& squashing_model,
+               int batch, int device, int solver_type);
+
  private:
+  void init();
   void barrierInit();
   void replayCallbacks();
+  std::size_t nu_ = 0;
   std::vector<std::shared_ptr<CallbackAbstract>> callbacks_;
   std::shared_ptr<ShootingProblem> problem_;
   std::shared_ptr<SquashingModelSmoothSat> squashing_model_;
@@ -376,11 +384,28 @@ class SolverSbFDDP {
   empc_solver_t* handle_ = nullptr;
   empc_solver_params_t params_;
   int batch_ = 1, device_ = 0;
+  int solver_type_ = EMPC_SOLVER_SBFDDP;
   std::vector<VectorXd> xs_, us_, us_squash_, k_;
   std::vector<std::vector<double>> K_;
   double cost_ = 0, stop_ = 0;
   std::size_t iter_ = 0;
   bool is_feasible_ = false;
+};
+
+// crocoddyl::SolverBoxFDDP / crocoddyl::SolverBoxDDP, the other two SolverTypes of the reference
+// (include/eagle_mpc/mpc-base.hpp:36-47; built at src/mpc-controllers/carrot-mpc.cpp:236-241, rail-mpc.cpp:118-123,
+// weighted-mpc.cpp:135-140 and by examples/python/trajectory.py:24 for problems created with squash = false).  Same surface
+// as SolverSbFDDP (solve, setCandidate, setCallbacks, get_xs / get_us / get_K / get_k ...), same device path: the box QP of
+// computeGains runs inside backward_kernel<D, true, true>, the rollouts clamp the trial controls.
+class SolverBoxFDDP : public SolverSbFDDP {
+ public:
+  explicit SolverBoxFDDP(const std::shared_ptr<ShootingProblem>& problem, int batch = 1, int device = 0)
+      : SolverSbFDDP(problem, nullptr, batch, device, EMPC_SOLVER_BOXFDDP) {}
+};
+class SolverBoxDDP : public SolverSbFDDP {
+ public:
+  explicit SolverBoxDDP(const std::shared_ptr<ShootingProblem>& problem, int batch = 1, int device = 0)
+      : SolverSbFDDP(problem, nullptr, batch, device, EMPC_SOLVER_BOXDDP) {}
 };
 
 }  // namespace eagle_mpc

@@ -114,6 +114,20 @@ void* empc_host_solver_create(void* t, int32_t dt_ms, int32_t squash, const char
     return hs.release();
   }, nullptr)
 }
+// trajectory.createProblem(dt, False, integrator) + crocoddyl.SolverBoxFDDP(problem) / SolverBoxDDP(problem)
+// (examples/python/trajectory.py:19-24); solver_type = EMPC_SOLVER_BOXFDDP or EMPC_SOLVER_BOXDDP
+void* empc_host_box_solver_create(void* t, int32_t dt_ms, int32_t solver_type, const char* integrator, int32_t batch, int32_t device) {
+  GUARD({
+    auto& tr = ((HostTrajectory*)t)->traj;
+    std::unique_ptr<HostSolver> hs(new HostSolver());
+    hs->traj = tr;
+    hs->problem = tr->createProblem((std::size_t)dt_ms, false, integrator);
+    if (solver_type == EMPC_SOLVER_BOXFDDP) hs->solver.reset(new SolverBoxFDDP(hs->problem, batch, device));
+    else if (solver_type == EMPC_SOLVER_BOXDDP) hs->solver.reset(new SolverBoxDDP(hs->problem, batch, device));
+    else throw std::invalid_argument("solver_type is not a box solver");
+    return hs.release();
+  }, nullptr)
+}
 void empc_host_solver_free(void* s) { delete (HostSolver*)s; }
 empc_solver_t* empc_host_solver_handle(void* s) { return ((HostSolver*)s)->solver->handle(); }
 int empc_host_solver_set_convergence_init(void* s, double c) { ((HostSolver*)s)->solver->set_convergence_init(c); return 0; }

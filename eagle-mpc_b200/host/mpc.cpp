@@ -47,8 +47,7 @@ void MpcAbstract::loadParams() {
 }
 
 void MpcAbstract::checkHotPathSupport() const {
-  if (params_.solver_type != SolverTypes::SolverSbFDDP)
-    throw std::runtime_error("only SolverSbFDDP is part of the B200 hot path (SolverBoxFDDP/BoxDDP: SURVEY.md §8f rank 4)");
+  // all three SolverTypes run on the device (SolverBoxFDDP / SolverBoxDDP: crocoddyl's box solvers, csrc/backward.cuh BOX)
 }
 
 std::shared_ptr<ActionModel> MpcAbstract::makeKnotModel(const std::shared_ptr<CostModelSum>& costs) const {
@@ -56,7 +55,8 @@ std::shared_ptr<ActionModel> MpcAbstract::makeKnotModel(const std::shared_ptr<Co
   iam->costs = costs;
   iam->dt = double(params_.dt) / 1000.;
   iam->rk4 = params_.integrator_type == "IntegratedActionModelRK4";  // src/mpc-controllers/carrot-mpc.cpp:211-222
-  iam->squash = true;
+  // src/mpc-controllers/carrot-mpc.cpp:188-193: the squashing actuation only under SolverSbFDDP
+  iam->squash = params_.solver_type == SolverTypes::SolverSbFDDP;
   iam->u_lb = platform_params_->u_lb; iam->u_ub = platform_params_->u_ub;
   return iam;
 }
@@ -70,13 +70,18 @@ void MpcAbstract::finishProblem() {
   problem_->platform = platform_params_;
   if (!defer_solver_) attachSolver();
   else {
-    sbfddp_barrier_init(*problem_, squash_->get_ns(), 1e-3);
+    if (params_.solver_type == SolverTypes::SolverSbFDDP) sbfddp_barrier_init(*problem_, squash_->get_ns(), 1e-3);
     flatten_problem(*problem_, flat_local_);
   }
 }
 
 void MpcAbstract::attachSolver() {
-  if (!solver_) solver_ = std::make_shared<SolverSbFDDP>(problem_, squash_, 1, 0);
+  if (solver_) return;
+  switch (params_.solver_type) {  // src/mpc-controllers/carrot-mpc.cpp:232-242
+    case SolverTypes::SolverSbFDDP: solver_ = std::make_shared<SolverSbFDDP>(problem_, squash_, 1, 0); break;
+    case SolverTypes::SolverBoxFDDP: solver_ = std::make_shared<SolverBoxFDDP>(problem_, 1, 0); break;
+    case SolverTypes::SolverBoxDDP: solver_ = std::make_shared<SolverBoxDDP>(problem_, 1, 0); break;
+  }
 }
 
 FlatProblem& MpcAbstract::flat() { return solver_ ? solver_->flat() : flat_local_; }

@@ -140,6 +140,13 @@ PYBIND11_MODULE(_eagle_mpc, m) {
       .def_property("stop_test", [](SolverSbFDDP& s) { return s.params().stop_test; }, [](SolverSbFDDP& s, int v) { s.params().stop_test = v; })
       .def_property_readonly("handle", [](const SolverSbFDDP& s) { return (std::uintptr_t)s.handle(); });
 
+  // crocoddyl.SolverBoxFDDP(problem) / crocoddyl.SolverBoxDDP(problem) of the reference's drivers (examples/python/trajectory.py:24,
+  // examples/python/mpc.py:26): same attributes as SolverSbFDDP, constructed from a problem created with squash = False
+  py::class_<SolverBoxFDDP, SolverSbFDDP, std::shared_ptr<SolverBoxFDDP>>(m, "SolverBoxFDDP")
+      .def(py::init<const std::shared_ptr<ShootingProblem>&, int, int>(), py::arg("problem"), py::arg("batch") = 1, py::arg("device") = 0);
+  py::class_<SolverBoxDDP, SolverSbFDDP, std::shared_ptr<SolverBoxDDP>>(m, "SolverBoxDDP")
+      .def(py::init<const std::shared_ptr<ShootingProblem>&, int, int>(), py::arg("problem"), py::arg("batch") = 1, py::arg("device") = 0);
+
   auto mpc_base = py::class_<MpcAbstract, std::shared_ptr<MpcAbstract>>(m, "MpcAbstract")
       .def("updateProblem", [](MpcAbstract& c, std::size_t t) { c.updateProblem(t); }, py::arg("current_time"))
       .def_property_readonly("robot_model", &MpcAbstract::get_robot_model)

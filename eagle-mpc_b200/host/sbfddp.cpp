@@ -16,12 +16,34 @@ static void ck(int rc, const char* what) {
 SolverSbFDDP::SolverSbFDDP(const std::shared_ptr<ShootingProblem>& problem,
                            const std::shared_ptr<SquashingModelSmoothSat>& squashing_model, int batch, int device)
     : problem_(problem), squashing_model_(squashing_model), batch_(batch), device_(device) {
-  cuda_abi().default_params(&params_);
-  barrierInit();
+  if (!squashing_model_) throw std::invalid_argument("SolverSbFDDP needs the squashing model (src/sbfddp.cpp:5)");
+  init();
+}
+
+SolverSbFDDP::SolverSbFDDP(const std::shared_ptr<ShootingProblem>& problem,
+                           const std::shared_ptr<SquashingModelSmoothSat>& squashing_model, int batch, int device, int solver_type)
+    : problem_(problem), squashing_model_(squashing_model), batch_(batch), device_(device), solver_type_(solver_type) {
+  init();
+}
+
+void SolverSbFDDP::init() {
+  if (solver_type_ == EMPC_SOLVER_SBFDDP) {
+    cuda_abi().default_params(&params_);
+    barrierInit();
+  } else {
+    // the box solvers take the problem as it is (createProblem(dt, squash = false, ...): plain actuation, control limits on
+    // every model, src/trajectory.cpp:96-100,131-132)
+    if (problem_->terminalModel->squash)
+      throw std::invalid_argument("SolverBoxFDDP / SolverBoxDDP: the problem was created with the squashing actuation (createProblem(dt, squash = false))");
+    cuda_abi().box_params(&params_, solver_type_);
+  }
   flatten_problem(*problem_, flat_);
   ck(cuda_abi().create(&flat_.desc, batch_, device_, &handle_), "empc_create");
+  ck(cuda_abi().set_params(handle_, &params_), "empc_set_params");
   const std::size_t T = problem_->get_T();
-  const std::size_t nx = (std::size_t)problem_->state->get_nx(), nu = squashing_model_->get_ns(), ndx = (std::size_t)problem_->state->get_ndx();
+  const std::size_t ndx = (std::size_t)problem_->state->get_ndx();
+  nu_ = squashing_model_ ? squashing_model_->get_ns() : (std::size_t)flat_.desc.n_rotors + ndx / 2 - 6;
+  const std::size_t nu = nu_;
   xs_.assign(T + 1, problem_->state->zero());
   us_.assign(T, VectorXd(nu, 0.0));
   us_squash_.assign(T, VectorXd(nu, 0.0));
@@ -59,7 +81,7 @@ void SolverSbFDDP::pushCosts(int first, int n) {
 void SolverSbFDDP::pushAllCosts() { pushCosts(0, (int)flat_.costs.size()); }
 
 void SolverSbFDDP::setCandidate(const std::vector<VectorXd>& xs_warm, const std::vector<VectorXd>& us_warm, bool is_feasible) {
-  const std::size_t T = problem_->get_T(), nx = (std::size_t)problem_->state->get_nx(), nu = squashing_model_->get_ns();
+  const std::size_t T = problem_->get_T(), nx = (std::size_t)problem_->state->get_nx(), nu = nu_;
   std::vector<double> xs, us;
   if (!xs_warm.empty()) {
     if (xs_warm.size() != T + 1)
@@ -79,7 +101,7 @@ void SolverSbFDDP::setCandidate(const std::vector<VectorXd>& xs_warm, const std:
 }
 
 void SolverSbFDDP::fetch(bool with_gains) {
-  const std::size_t T = problem_->get_T(), nx = (std::size_t)problem_->state->get_nx(), nu = squashing_model_->get_ns(),
+  const std::size_t T = problem_->get_T(), nx = (std::size_t)problem_->state->get_nx(), nu = nu_,
                     ndx = (std::size_t)problem_->state->get_ndx(), B = (std::size_t)batch_;
   std::vector<double> buf(B * (T + 1) * nx), ub(B * T * nu), sb(B * T * nu), c(B), s(B);
   std::vector<int32_t> it(B), fe(B);

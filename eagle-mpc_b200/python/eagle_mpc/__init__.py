@@ -7,6 +7,9 @@
     solver.setCallbacks([eagle_mpc.CallbackVerbose()])     # crocoddyl.CallbackVerbose() in the reference's scripts
     solver.solve([], [], maxiter=100)
 
+    problem = trajectory.createProblem(dt, False, "IntegratedActionModelEuler")   # useSquash = False
+    solver = eagle_mpc.SolverBoxFDDP(problem)               # crocoddyl.SolverBoxFDDP(problem) in the reference's scripts
+
 The extension module (_eagle_mpc, pybind11 over eagle-mpc_b200/host/) binds the CUDA library at run time; there is no CPU
 fallback: constructing a solver without a usable GPU raises RuntimeError."""
 import os as _os
@@ -15,7 +18,7 @@ _PKG = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__fil
 _os.environ.setdefault("EMPC_LIB", _os.path.join(_PKG, "lib", "libempc_b200.so"))
 
 from ._eagle_mpc import (CallbackVerbose, CarrotMpc, MpcAbstract, MultiCopterBaseParams, RailMpc, RobotModel,  # noqa: E402,F401
-                         ShootingProblem, SolverSbFDDP, SquashingModelSmoothSat, Stage, Trajectory, WeightedMpc,
+                         ShootingProblem, SolverBoxDDP, SolverBoxFDDP, SolverSbFDDP, SquashingModelSmoothSat, Stage, Trajectory, WeightedMpc,
                          set_robot_data_dir, set_yaml_dir)
 from . import utils  # noqa: E402,F401
 

@@ -152,6 +152,13 @@ typedef struct empc_problem_desc {
 enum { EMPC_STOP_CRITERIA_COST_REDUCTION = 0, EMPC_STOP_CRITERIA_QU_NORM = 1 };
 enum { EMPC_STOP_TEST_GAPS = 0, EMPC_STOP_TEST_FEASIBLE = 1 };
 
+/* Solver families of SolverTypes (include/eagle_mpc/mpc-base.hpp:36).  The Box solvers are crocoddyl's: ONE SolverFDDP::solve
+ * (BOXFDDP) or SolverDDP::solve (BOXDDP) pass on the problem built WITHOUT the squashing actuation (use_squash = 0, no
+ * barrier cost), where computeGains solves the box-constrained QP  min 1/2 du' Quu du + Qu' du,  u_lb <= us + du <= u_ub
+ * (projected Newton, crocoddyl::BoxQP) whenever the candidate is feasible, and the rollouts clamp us_try to [u_lb, u_ub].
+ * Their stop rule is upstream's: set stop_criteria = QU_NORM and stop_test = FEASIBLE (empc_box_params does). */
+enum { EMPC_SOLVER_SBFDDP = 0, EMPC_SOLVER_BOXFDDP = 1, EMPC_SOLVER_BOXDDP = 2 };
+
 /* Solver constants: eagle-mpc's (src/sbfddp.cpp:5-29) and crocoddyl SolverDDP/FDDP defaults. */
 typedef struct empc_solver_params {
   int32_t maxiter;          /* solve(maxiter), default 100 */
@@ -160,7 +167,8 @@ typedef struct empc_solver_params {
   int32_t stop_criteria;    /* set_stoppingCriteria (src/sbfddp.cpp:28): EMPC_STOP_CRITERIA_* */
   int32_t stop_test;        /* set_stoppingTest (src/sbfddp.cpp:29): EMPC_STOP_TEST_* (FDDP passes; the DDP clean-up always
                                uses stoppingTestFeasible, src/sbfddp.cpp:387) */
-  int32_t reserved;
+  int32_t solver_type;      /* EMPC_SOLVER_*: SolverSbFDDP (default) or crocoddyl's SolverBoxFDDP / SolverBoxDDP, the other two
+                               entries of SolverTypes (include/eagle_mpc/mpc-base.hpp:36-47, src/mpc-controllers/carrot-mpc.cpp:232-242) */
   double convergence_init;  /* 1e-2 */
   double convergence_stop;  /* 1e-3 */
   double convergence_mult;  /* 1e-1 */
@@ -178,10 +186,20 @@ typedef struct empc_solver_params {
   double th_stepdec;        /* 0.5 */
   double th_stepinc;        /* 0.01 */
   double th_stop_gaps;      /* 1.0 */
+  /* Box solvers only (crocoddyl SolverBoxFDDP / SolverBoxDDP constructors: th_stop_ = 5e-5, BoxQP(nu, 100, 0.1, 1e-5, 0)) */
+  double th_stop;           /* 5e-5 */
+  double boxqp_th_acceptstep; /* 0.1 */
+  double boxqp_th_grad;     /* 1e-5 */
+  double boxqp_reg;         /* 0 */
+  int32_t boxqp_maxiter;    /* 100 */
+  int32_t reserved;
 } empc_solver_params_t;
 
 /* Fills `p` with the reference defaults listed above. */
 void empc_default_params(empc_solver_params_t* p);
+/* Defaults of crocoddyl::SolverBoxFDDP / SolverBoxDDP (solver_type = EMPC_SOLVER_BOXFDDP or EMPC_SOLVER_BOXDDP): the reference
+ * defaults above with the upstream stop rule and th_stop_ = 5e-5. */
+void empc_box_params(empc_solver_params_t* p, int32_t solver_type);
 
 /* Derived dimensions of a problem. */
 typedef struct empc_dims {

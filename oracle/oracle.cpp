@@ -132,6 +132,102 @@ struct Solver {
     }
   }
 
+  // crocoddyl::BoxQP::solve (crocoddyl/core/solvers/box-qp.cpp; Tassa's projected Newton): minimise 1/2 x'Hx + q'x over
+  // lb <= x <= ub from the clamped warm start.  Per iteration: gradient g = q + Hx; a coordinate is CLAMPED when it sits on a
+  // bound with the gradient pushing outwards, FREE otherwise; converged when ||g||_inf <= th_grad or nothing is free; Newton
+  // step on the free block (LLT of Hff [+ reg]), dxf = Hff^-1 (-qf - Hfc xc) - xf; projected line search over alpha = 1, 1/2,
+  // ... 1/512 with the Armijo test  f(x) - f(xnew) > th_acceptstep g'(x - xnew).  Leaves x, the free / clamped index sets of
+  // the last iteration and Hff^-1 (of the last factorised free block) in qp_*; false = LLT failure ("backward_error").
+  std::vector<int> qp_free, qp_clamped;
+  std::vector<double> qp_Hff_inv, qp_x;
+  int qp_iters = 0;
+  // statistics of the box QPs since the last reset (test diagnostics): calls, calls whose LAST allowed iteration still moved
+  // the iterate by more than 1e-12 (the projected Newton iteration had not settled within maxiter), iterations until it
+  // settled summed over the calls, calls that clamped something
+  double qp_stats[4] = {0, 0, 0, 0};
+  bool box_qp(const double* H, const double* q, const double* lb, const double* ub, const double* xinit, int nx) {
+    std::vector<double> x(nx), g(nx), dx(nx), xnew(nx), Hff, Hfc, qf, xf, xc, dxf, Lf;
+    for (int i = 0; i < nx; ++i) x[i] = std::max(std::min(xinit[i], ub[i]), lb[i]);
+    auto value = [&](const std::vector<double>& v) {
+      double a = 0, b = 0;
+      for (int i = 0; i < nx; ++i) {
+        double r = 0;
+        for (int j = 0; j < nx; ++j) r += H[(size_t)i * nx + j] * v[j];
+        a += v[i] * r; b += q[i] * v[i];
+      }
+      return 0.5 * a + b;
+    };
+    auto factor_free = [&]() {  // Hff (+ reg) = L L', Hff_inv = (L L')^-1
+      const int nf = (int)qp_free.size();
+      Hff.assign((size_t)nf * nf, 0.0);
+      for (int i = 0; i < nf; ++i)
+        for (int j = 0; j < nf; ++j) Hff[(size_t)i * nf + j] = H[(size_t)qp_free[i] * nx + qp_free[j]];
+      if (P.boxqp_reg != 0.0) for (int i = 0; i < nf; ++i) Hff[(size_t)i * nf + i] += P.boxqp_reg;
+      Lf = Hff;
+      if (nf > 0 && !llt_inplace(Lf.data(), nf)) return false;
+      qp_Hff_inv.assign((size_t)nf * nf, 0.0);
+      for (int i = 0; i < nf; ++i) qp_Hff_inv[(size_t)i * nf + i] = 1.0;
+      if (nf > 0) llt_solve(Lf.data(), nf, qp_Hff_inv.data(), nf);
+      return true;
+    };
+    qp_iters = 0;
+    qp_stats[0] += 1;
+    int settled_at = -1; bool last_moved = false;
+    struct Tail { double* st; int* settled; bool* moved; std::vector<int>* cl; int* its;
+                  ~Tail() { st[2] += (*settled >= 0 ? *settled : *its); if (*moved) st[1] += 1; if (!cl->empty()) st[3] += 1; } } tail{qp_stats, &settled_at, &last_moved, &qp_clamped, &qp_iters};
+    for (int k = 0; k < P.boxqp_maxiter; ++k) {
+      qp_iters = k + 1;
+      last_moved = false;
+      qp_free.clear(); qp_clamped.clear();
+      double gmax = 0;
+      for (int i = 0; i < nx; ++i) {
+        double r = q[i];
+        for (int j = 0; j < nx; ++j) r += H[(size_t)i * nx + j] * x[j];
+        g[i] = r;
+        if (std::fabs(r) > gmax) gmax = std::fabs(r);
+      }
+      for (int j = 0; j < nx; ++j) {
+        if ((x[j] == lb[j] && g[j] > 0.0) || (x[j] == ub[j] && g[j] < 0.0)) qp_clamped.push_back(j);
+        else qp_free.push_back(j);
+      }
+      const int nf = (int)qp_free.size(), nc = (int)qp_clamped.size();
+      if (gmax <= P.boxqp_th_grad || nf == 0) {
+        // the inverse of the free Hessian is still needed by the caller (upstream computes it here only for k = 0 and otherwise
+        // hands out the previous iteration's; when the free set has changed size since, that would index a matrix of another
+        // shape, so it is recomputed)
+        if ((k == 0 || qp_Hff_inv.size() != (size_t)nf * nf) && !factor_free()) return false;
+        qp_x = x;
+        return true;
+      }
+      if (!factor_free()) return false;
+      dxf.assign(nf, 0.0);
+      for (int i = 0; i < nf; ++i) {
+        double r = -q[qp_free[i]];
+        for (int j = 0; j < nc; ++j) r -= H[(size_t)qp_free[i] * nx + qp_clamped[j]] * x[qp_clamped[j]];
+        dxf[i] = r;
+      }
+      llt_solve(Lf.data(), nf, dxf.data(), 1);
+      std::fill(dx.begin(), dx.end(), 0.0);
+      for (int i = 0; i < nf; ++i) dx[qp_free[i]] = dxf[i] - x[qp_free[i]];
+      const double fold = value(x);
+      for (int n = 0; n < EMPC_N_ALPHAS; ++n) {
+        const double a = alphas[n];
+        double gd = 0;
+        for (int i = 0; i < nx; ++i) { xnew[i] = std::max(std::min(x[i] + a * dx[i], ub[i]), lb[i]); gd += g[i] * (x[i] - xnew[i]); }
+        const double fnew = value(xnew);
+        if (fold - fnew > P.boxqp_th_acceptstep * gd) {
+          double mv = 0;
+          for (int i = 0; i < nx; ++i) mv = std::max(mv, std::fabs(xnew[i] - x[i]) / std::max(1.0, std::fabs(x[i])));
+          if (mv > 1e-12) { last_moved = true; settled_at = -1; } else if (settled_at < 0) settled_at = k;
+          x = xnew; break;
+        }
+      }
+      if (!last_moved && settled_at < 0) settled_at = k;
+    }
+    qp_x = x;
+    return true;
+  }
+
   // SolverDDP::backwardPass + computeGains; returns false on "backward_error"
   bool backward_pass() {
     const int ndx = m.ndx, nu = m.nu;
@@ -196,17 +292,40 @@ struct Solver {
         Qu_t[i] = Lu[i] + s;
         Quu[i * nu + i] += ureg;
       }
+      double* K_t = &K[(size_t)t * nu * ndx];
+      double* k_t = &k[(size_t)t * nu];
+      if (P.solver_type != EMPC_SOLVER_SBFDDP && is_feasible) {
+        // crocoddyl SolverBoxFDDP / SolverBoxDDP::computeGains (every model of the reference's problems has control limits:
+        // src/trajectory.cpp:131-132, src/mpc-controllers/carrot-mpc.cpp:220-221; an infeasible candidate takes the plain
+        // gains below): du = argmin 1/2 du' Quu du + Qu' du, u_lb - us <= du <= u_ub - us, warm-started at k_[t];
+        // K = Quu_inv Qxu^T with Quu_inv the inverse of the free block (zero rows / columns for the clamped controls);
+        // k = -du; the clamped entries of Qu are zeroed ("important for accounting the algorithm advancement")
+        std::vector<double> du_lb(nu), du_ub(nu);
+        for (int i = 0; i < nu; ++i) { du_lb[i] = desc.u_lb[i] - us[(size_t)t * nu + i]; du_ub[i] = desc.u_ub[i] - us[(size_t)t * nu + i]; }
+        if (!box_qp(Quu.data(), Qu_t, du_lb.data(), du_ub.data(), k_t, nu)) return false;
+        std::vector<double> Quu_inv((size_t)nu * nu, 0.0);
+        const int nf = (int)qp_free.size();
+        for (int i = 0; i < nf; ++i)
+          for (int j = 0; j < nf; ++j) Quu_inv[(size_t)qp_free[i] * nu + qp_free[j]] = qp_Hff_inv[(size_t)i * nf + j];
+        for (int i = 0; i < nu; ++i)
+          for (int j = 0; j < ndx; ++j) {
+            double sK = 0;
+            for (int l = 0; l < nu; ++l) sK += Quu_inv[(size_t)i * nu + l] * Qxu[j * nu + l];
+            K_t[i * ndx + j] = sK;
+          }
+        for (int i = 0; i < nu; ++i) k_t[i] = -qp_x[i];
+        for (int c : qp_clamped) Qu_t[c] = 0.0;
+      } else {
       // computeGains: LLT(Quu); K = Quu^-1 Qxu^T ; k = Quu^-1 Qu
       L = Quu;
       if (!llt_inplace(L.data(), nu)) return false;
-      double* K_t = &K[(size_t)t * nu * ndx];
-      double* k_t = &k[(size_t)t * nu];
       for (int i = 0; i < nu; ++i) {
         for (int j = 0; j < ndx; ++j) K_t[i * ndx + j] = Qxu[j * nu + i];
         k_t[i] = Qu_t[i];
       }
       llt_solve(L.data(), nu, K_t, ndx);
       llt_solve(L.data(), nu, k_t, 1);
+      }
       // value function
       double* Vx_t = &Vx[(size_t)t * ndx];
       double* Vxx_t = &Vxx[(size_t)t * ndx * ndx];
@@ -324,7 +443,10 @@ struct Solver {
     for (int i = 0; i < nu; ++i) {
       double kd = 0;
       for (int j = 0; j < ndx; ++j) kd += K[((size_t)t * nu + i) * ndx + j] * dxt[j];
-      us_try[(size_t)t * nu + i] = us[(size_t)t * nu + i] - k[(size_t)t * nu + i] * alpha - kd;
+      double ut = us[(size_t)t * nu + i] - k[(size_t)t * nu + i] * alpha - kd;
+      // SolverBoxFDDP / SolverBoxDDP::forwardPass: us_try = us_try.cwiseMax(u_lb).cwiseMin(u_ub)
+      if (P.solver_type != EMPC_SOLVER_SBFDDP) ut = std::min(std::max(ut, desc.u_lb[i]), desc.u_ub[i]);
+      us_try[(size_t)t * nu + i] = ut;
     }
     node_calc(m, ctx(), costset_of(t), &xs_try[(size_t)t * nx], &us_try[(size_t)t * nu], work[t], &evals[t]);
     std::memcpy(xnext, work[t].xnext, sizeof(double) * nx);
@@ -520,6 +642,19 @@ struct Solver {
   void solve(const double* xs_in, const double* us_in, int maxiter, bool feasible_arg) {
     std::memcpy(&xs_try[0], x0.data(), sizeof(double) * m.nx);
     set_candidate(xs_in, us_in, feasible_arg);
+    if (P.solver_type != EMPC_SOLVER_SBFDDP) {
+      // crocoddyl::SolverBoxFDDP / SolverBoxDDP (src/mpc-controllers/carrot-mpc.cpp:236-241): one upstream SolverFDDP::solve or
+      // SolverDDP::solve with th_stop_ = 5e-5, the caller's feasibility flag, box gains and clamped rollouts
+      smooth = smooth_model = P.smooth_init;
+      th_stop = P.th_stop;
+      total_iters = 0;
+      log.clear();
+      if (P.solver_type == EMPC_SOLVER_BOXFDDP) solve_fddp(maxiter, feasible_arg, P.reg_init);
+      else solve_ddp(maxiter, P.reg_init);
+      total_iters = iter + 1;
+      us_squash = us;  // no squashing function on this path
+      return;
+    }
     smooth = P.smooth_init;
     convergence = P.convergence_init;
     total_iters = 0;
@@ -565,6 +700,13 @@ void orc_default_params(empc_solver_params_t* p) {
   p->reg_init = 1e-9; p->reg_min = 1e-9; p->reg_max = 1e9; p->reg_factor = 10;
   p->th_acceptstep = 0.1; p->th_acceptnegstep = 2; p->th_grad = 1e-12; p->th_gaptol = 1e-16;
   p->th_stepdec = 0.5; p->th_stepinc = 0.01; p->th_stop_gaps = 1.0;
+  p->solver_type = EMPC_SOLVER_SBFDDP;
+  p->th_stop = 5e-5; p->boxqp_maxiter = 100; p->boxqp_th_acceptstep = 0.1; p->boxqp_th_grad = 1e-5; p->boxqp_reg = 0.0;
+}
+void orc_box_params(empc_solver_params_t* p, int32_t solver_type) {
+  orc_default_params(p);
+  p->solver_type = solver_type;
+  p->stop_criteria = EMPC_STOP_CRITERIA_QU_NORM; p->stop_test = EMPC_STOP_TEST_FEASIBLE;
 }
 
 void* orc_create(const empc_problem_desc_t* d) {
@@ -641,6 +783,8 @@ int orc_get(void* h, const char* name, double* out) {
   else if (n == "us_squash") copy_out(s->us_squash, out);
   else if (n == "K") copy_out(s->K, out);
   else if (n == "k") copy_out(s->k, out);
+  else if (n == "Qu") copy_out(s->Qu, out);
+  else if (n == "qp_stats") { std::memcpy(out, s->qp_stats, sizeof(s->qp_stats)); std::fill(s->qp_stats, s->qp_stats + 4, 0.0); }
   else if (n == "Vx") copy_out(s->Vx, out);
   else if (n == "Vxx") copy_out(s->Vxx, out);
   else if (n == "fs") copy_out(s->fs, out);

@@ -348,7 +348,11 @@ def _vec(v):
 class Problem:
     """trajectory YAML -> what SolverSbFDDP sees (robot, actuation, one cost dict per stage, node -> stage map)"""
 
-    def __init__(self, yaml_path, yaml_root, urdf_root, dt_ms, barrier_weight=1e-3, integrator="IntegratedActionModelEuler"):
+    def __init__(self, yaml_path, yaml_root, urdf_root, dt_ms, barrier_weight=1e-3, integrator="IntegratedActionModelEuler",
+                 use_squash=True):
+        # use_squash = False: the problem the reference hands to crocoddyl::SolverBoxFDDP (plain multicopter actuation, no
+        # barrier cost; src/trajectory.cpp:96-100, examples/python/trajectory.py:19-24)
+        self.use_squash = use_squash
         assert integrator in ("IntegratedActionModelEuler", "IntegratedActionModelRK4")   # src/factory/int-action.cpp:24-35
         self.rk4 = integrator == "IntegratedActionModelRK4"
         doc = pyyaml.safe_load(open(os.path.join(yaml_root, yaml_path)))["trajectory"]
@@ -399,7 +403,7 @@ class Problem:
             node_stage += [si] * n_knots
             # SolverSbFDDP::barrierInit (src/sbfddp.cpp:181-186): every RUNNING model gets "barrier" (one model object per
             # stage, src/trajectory.cpp:134: a last stage without running knots is the terminal model only and has none)
-            if n_knots > 0:
+            if n_knots > 0 and use_squash:
                 costs["barrier"] = {"type": "Barrier", "weight": barrier_weight, "active": True}
             self.stages.append({"name": st["name"], "duration": dur, "costs": dict(sorted(costs.items())), "contact": contact})
         self.T = len(node_stage)
@@ -460,6 +464,8 @@ class Problem:
 
     # ---- node model ----
     def squash(self, u, smooth):
+        if not self.use_squash:
+            return u
         a = (smooth * (self.u_ub - self.u_lb)) ** 2
         return 0.5 * (np.sqrt((u - self.u_lb) ** 2 + a) - np.sqrt((u - self.u_ub) ** 2 + a) + self.u_lb + self.u_ub)
 
@@ -609,11 +615,42 @@ class Problem:
 # Solver algebra, dense
 
 
-def riccati_sweep(nodes, terminal, fs, xreg, feasible):
-    """nodes[t]: dict with Fx, Fu, Lx, Lu, Lxx, Lxu, Luu; terminal: Lx, Lxx; fs[t]: gaps (T + 1).  Returns K, k, Vx, Vxx."""
+def box_qp(H, q, lb, ub, xinit, maxiter=100, th_acceptstep=0.1, th_grad=1e-5, reg=0.0):
+    """Projected-Newton box QP (Tassa, Mansard, Todorov 2014, as crocoddyl::BoxQP runs it): min 1/2 x'Hx + q'x, lb <= x <= ub.
+    Returns x, the free and clamped index arrays of the last active-set pass and the inverse of the free block of H."""
+    x = np.clip(np.asarray(xinit, dtype=float), lb, ub)
+    f = lambda v: 0.5 * v @ H @ v + q @ v
+    free = np.arange(x.size); clamped = np.array([], dtype=int); Hff_inv = None
+    for it in range(maxiter):
+        g = q + H @ x
+        on = ((x == lb) & (g > 0)) | ((x == ub) & (g < 0))
+        clamped, free = np.flatnonzero(on), np.flatnonzero(~on)
+        done = np.abs(g).max() <= th_grad or free.size == 0
+        if not done or it == 0 or Hff_inv.shape[0] != free.size:   # (a stale inverse of another free set is never handed out)
+            Hff = H[np.ix_(free, free)] + reg * np.eye(free.size)
+            np.linalg.cholesky(Hff) if free.size else None   # raises when not positive definite (the reference's backward_error)
+            Hff_inv = np.linalg.inv(Hff) if free.size else np.zeros((0, 0))
+        if done:
+            break
+        dx = np.zeros_like(x)
+        dx[free] = Hff_inv @ (-q[free] - H[np.ix_(free, clamped)] @ x[clamped]) - x[free]
+        fold = f(x)
+        for n in range(10):
+            xnew = np.clip(x + dx / 2.0 ** n, lb, ub)
+            if fold - f(xnew) > th_acceptstep * (g @ (x - xnew)):
+                x = xnew
+                break
+    return x, free, clamped, Hff_inv
+
+
+def riccati_sweep(nodes, terminal, fs, xreg, feasible, box=None):
+    """nodes[t]: dict with Fx, Fu, Lx, Lu, Lxx, Lxu, Luu; terminal: Lx, Lxx; fs[t]: gaps (T + 1).  Returns K, k, Vx, Vxx.
+    box = (us, u_lb, u_ub, k_prev): the gains of crocoddyl's SolverBoxFDDP / SolverBoxDDP for a feasible candidate — the box QP
+    on du with u_lb <= us + du <= u_ub warm-started at k_prev, feedback from the free block only, clamped entries of Qu
+    zeroed; then the sweep also returns the list of Qu."""
     T = len(nodes)
     ndx = terminal["Lx"].size
-    Vxx = [None] * (T + 1); Vx = [None] * (T + 1); K = [None] * T; k = [None] * T
+    Vxx = [None] * (T + 1); Vx = [None] * (T + 1); K = [None] * T; k = [None] * T; Qus = [None] * T
     Vxx[T] = terminal["Lxx"] + xreg * np.eye(ndx)
     Vx[T] = terminal["Lx"].copy()
     if not feasible:
@@ -626,18 +663,31 @@ def riccati_sweep(nodes, terminal, fs, xreg, feasible):
         Quu = n["Luu"] + Fu.T @ Vxx[t + 1] @ Fu + xreg * np.eye(Fu.shape[1])
         Qx = n["Lx"] + Fx.T @ Vx[t + 1]
         Qu = n["Lu"] + Fu.T @ Vx[t + 1]
-        K[t] = np.linalg.solve(Quu, Qxu.T)
-        k[t] = np.linalg.solve(Quu, Qu)
+        if box is not None and feasible:
+            us, u_lb, u_ub, k_prev = box
+            du, free, clamped, Hff_inv = box_qp(Quu, Qu, u_lb - us[t], u_ub - us[t], k_prev[t])
+            Quu_inv = np.zeros_like(Quu)
+            Quu_inv[np.ix_(free, free)] = Hff_inv
+            K[t] = Quu_inv @ Qxu.T
+            k[t] = -du
+            Qu = Qu.copy(); Qu[clamped] = 0.0
+            Qus[t] = Qu
+        else:
+            K[t] = np.linalg.solve(Quu, Qxu.T)
+            k[t] = np.linalg.solve(Quu, Qu)
         Vx[t] = Qx + K[t].T @ (Quu @ k[t]) - 2 * K[t].T @ Qu
         V = Qxx - Qxu @ K[t]
         Vxx[t] = 0.5 * (V + V.T) + xreg * np.eye(ndx)
         if not feasible:
             Vx[t] = Vx[t] + Vxx[t] @ fs[t]
+    if box is not None:
+        return K, k, Vx, Vxx, Qus
     return K, k, Vx, Vxx
 
 
-def rollout(prob, x0, xs, us, K, k, fs, alpha, smooth, feasible):
-    """SolverFDDP::forwardPass from x0 with step length alpha: returns xs_try, us_try, cost_try"""
+def rollout(prob, x0, xs, us, K, k, fs, alpha, smooth, feasible, clamp=None):
+    """SolverFDDP::forwardPass from x0 with step length alpha: returns xs_try, us_try, cost_try.
+    clamp = (u_lb, u_ub): SolverBoxFDDP::forwardPass clamps every trial control to its limits."""
     rob = prob.rob
     T = len(us)
     xs_try, us_try, cost = [], [], 0.0
@@ -649,6 +699,8 @@ def rollout(prob, x0, xs, us, K, k, fs, alpha, smooth, feasible):
             cost += prob.calc(prob.node_stage[T], xt, None, smooth, terminal=True)[1]
             break
         ut = us[t] - alpha * k[t] - K[t] @ diff(rob, xs[t], xt)
+        if clamp is not None:
+            ut = np.clip(ut, clamp[0], clamp[1])
         us_try.append(ut)
         xnext, c = prob.calc(prob.node_stage[t], xt, ut, smooth)
         cost += c

@@ -50,6 +50,13 @@ def default_params():
     return p
 
 
+def box_params(solver_type=abi.SOLVER_BOXFDDP):
+    """crocoddyl::SolverBoxFDDP / SolverBoxDDP defaults (orc_box_params)"""
+    p = abi.SolverParams()
+    lib.orc_box_params(C.byref(p), solver_type)
+    return p
+
+
 def solve_batch(holder, x0, nthreads=1, params=None):
     """(seconds, iterations per OCP, final costs) of the CPU oracle over a batch of initial states."""
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
@@ -95,7 +102,7 @@ class Oracle:
         T, nx, ndx, nu = self.T, self.nx, self.ndx, self.nu
         shapes = {
             "xs": (T + 1, nx), "us": (T, nu), "xs_try": (T + 1, nx), "us_try": (T, nu), "us_squash": (T, nu),
-            "K": (T, nu, ndx), "k": (T, nu), "Vx": (T + 1, ndx), "Vxx": (T + 1, ndx, ndx), "fs": (T + 1, ndx),
+            "K": (T, nu, ndx), "k": (T, nu), "Qu": (T, nu), "qp_stats": (4,), "Vx": (T + 1, ndx), "Vxx": (T + 1, ndx, ndx), "fs": (T + 1, ndx),
             "tiles": (T + 1, self.tile), "xnext": (T + 1, nx), "node_cost": (T + 1,), "cost": (1,),
             "cost_try": (1,), "stop": (1,), "xreg": (1,), "dgdq": (2,), "dv": (1,), "iter": (1,), "feasible": (1,),
         }

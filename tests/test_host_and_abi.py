@@ -33,7 +33,10 @@ def test_abi_exports_every_declared_symbol():
     assert not missing, missing
     p = capi.default_params()
     assert p.maxiter == 100 and p.convergence_init == 1e-2 and p.th_acceptnegstep == 2 and p.th_stop_gaps == 1.0
-    assert C.sizeof(abi.Cost) == 40 and C.sizeof(abi.SolverParams) == 24 + 17 * 8
+    assert C.sizeof(abi.Cost) == 40 and C.sizeof(abi.SolverParams) == 24 + 21 * 8 + 8
+    b = capi.box_params(abi.SOLVER_BOXDDP)   # crocoddyl::SolverBoxDDP: th_stop_ = 5e-5, BoxQP(nu, 100, 0.1, 1e-5, 0), upstream stop rule
+    assert b.solver_type == abi.SOLVER_BOXDDP and b.th_stop == 5e-5 and b.boxqp_maxiter == 100 and b.boxqp_th_grad == 1e-5
+    assert b.stop_criteria == abi.STOP_CRITERIA_QU_NORM and b.stop_test == abi.STOP_TEST_FEASIBLE and p.solver_type == abi.SOLVER_SBFDDP
 
 
 def test_no_gpu_means_loud_failure():
