@@ -210,7 +210,8 @@ def R_to_quat(R):
     R = np.ascontiguousarray(R, dtype=np.float64); q = np.zeros(4); lib.orc_R_to_quat(dp(R), dp(q)); return q
 
 
-def oracle_closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, record=False, t_start=0, xs_warm=None, us_warm=None):
+def oracle_closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, record=False, t_start=0, xs_warm=None, us_warm=None,
+                       params=None):
     """CPU twin of eagle-mpc_b200.mpc.closed_loop: same host-side CarrotMpc retargeting (created without a solver),
     oracle solves and oracle RK4 plant."""
     import time
@@ -223,7 +224,7 @@ def oracle_closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, rec
         costs, pool = mpc.cost_tables()
         lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), dp(pool))
 
-    p = default_params()
+    p = default_params() if params is None else params   # params: e.g. box_params(...) for a controller built on a Box solver
     mpc.updateProblem(int(t_start)); push()
     p.maxiter = 100; p.convergence_init = 1e-2
     o.set_params(p); o.set_x0(x_start)

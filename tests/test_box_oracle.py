@@ -150,3 +150,26 @@ def test_box_solve_properties(solver_type):
     assert all(r.phase == (0 if solver_type == abi.SOLVER_BOXFDDP else 1) for r in log)
     assert o.get("feasible") == 1.0 and log[-1].cost < log[0].cost
     assert np.array_equal(o.get("us_squash"), us)
+
+
+def box_mpc_yaml(tmp_path, solver="SolverBoxFDDP"):
+    """the flying arm's mpc.yaml with the solver entry switched (mpc_controller/solver, src/mpc-base.cpp:53)"""
+    src = open(os.path.join(YAML_ROOT, "hexacopter370_flying_arm_3/mpc/mpc.yaml")).read()
+    assert 'solver: "SolverSbFDDP"' in src
+    out = tmp_path / ("mpc_" + solver + ".yaml")
+    out.write_text(src.replace('solver: "SolverSbFDDP"', 'solver: "%s"' % solver))
+    return str(out)
+
+
+@pytest.mark.parametrize("solver", ["SolverBoxFDDP", "SolverBoxDDP"])
+def test_mpc_controller_with_a_box_solver_builds_the_unsquashed_problem(solver, tmp_path):
+    """src/mpc-controllers/carrot-mpc.cpp:188-193: the squashing actuation only under SolverSbFDDP; no barrier cost either
+    (barrierInit belongs to SolverSbFDDP)"""
+    mpcmod = importlib.import_module("eagle-mpc_b200.mpc")
+    tr = host.Trajectory("hexacopter370_flying_arm_3/trajectories/displacement.yaml")
+    xs = np.tile(np.array([0, 0, 0, 0, 0, 0, 1.0] + [0.0] * 12), (50, 1))
+    mpc = mpcmod.CarrotMpc(tr, xs, 20, box_mpc_yaml(tmp_path, solver), create_solver=False)
+    assert mpc.desc.use_squash == 0
+    assert abi.COST_SQUASH_BARRIER not in {c.type for c in mpc.cost_tables()[0]}
+    ref = mpcmod.CarrotMpc(tr, xs, 20, "hexacopter370_flying_arm_3/mpc/mpc.yaml", create_solver=False)
+    assert ref.desc.use_squash == 1 and abi.COST_SQUASH_BARRIER in {c.type for c in ref.cost_tables()[0]}

@@ -195,3 +195,27 @@ def test_box_front_ends():
     assert sb.iter == it and np.array_equal(np.asarray(sb.xs), xs) and np.array_equal(np.asarray(sb.us), us)
     with pytest.raises(Exception):
         eagle_mpc.SolverBoxFDDP(t2.createProblem(20, True, EULER))   # a squashed problem is not a box-solver problem
+
+
+def test_carrot_mpc_on_box_fddp_closed_loop(tmp_path):
+    """mpc.yaml with solver: "SolverBoxFDDP" (src/mpc-base.cpp:53, src/mpc-controllers/carrot-mpc.cpp:236-238): the controller builds
+    the unsquashed problem, owns a SolverBoxFDDP and steps the closed loop of examples/python/mpc.py like the oracle does"""
+    from test_box_oracle import box_mpc_yaml
+    mpcmod = importlib.import_module("eagle-mpc_b200.mpc")
+    traj = "hexacopter370_flying_arm_3/trajectories/displacement.yaml"
+    tr = host.Trajectory(traj)
+    fp = tr.createProblem(20, False, EULER)
+    po = ob.box_params(abi.SOLVER_BOXFDDP); po.maxiter = 100
+    o = ob.Oracle(fp); o.set_params(po); o.set_x0(fp.x0); o.solve()
+    xs, us = o.get("xs"), o.get("us")
+    yaml = box_mpc_yaml(tmp_path)
+    n_steps = 20
+    mpc_g = mpcmod.CarrotMpc(tr, xs, 20, yaml, create_solver=True)
+    lat_g, st_g, u_g, it_g = mpcmod.closed_loop(mpc_g, xs, us, xs[0], n_steps, record=True)
+    mpc_o = mpcmod.CarrotMpc(tr, xs, 20, yaml, create_solver=False)
+    lat_o, st_o, u_o, it_o = ob.oracle_closed_loop(mpc_o, xs, us, xs[0], n_steps, record=True, params=ob.box_params(abi.SOLVER_BOXFDDP))
+    assert it_g == it_o
+    lb, ub = limits(fp)
+    assert np.all(u_g >= lb) and np.all(u_g <= ub)
+    assert np.abs(u_g - u_o).max() <= 1e-7 * max(1.0, np.abs(u_o).max())
+    assert np.abs(st_g - st_o).max() <= 1e-8 * max(1.0, np.abs(st_o).max())
