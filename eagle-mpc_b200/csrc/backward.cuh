@@ -105,85 +105,99 @@ struct BwParams {
 // iterates it would keep (bit for bit, or to the last few ulp) for the rest of its maxiter iterations: no step length was
 // accepted (the loop is deterministic: every further iteration repeats this one), and a Newton step below 1e-15 relative
 // (the iterate is the minimiser on its free set; the reference random-walks on the last bit from here).
-// Outputs: kout = -x, Hinv (m x LM, shared memory) = inverse of the free block of H scattered into the full matrix (zero rows
-// and columns for the clamped unknowns), q with its clamped entries zeroed.  Returns 1 when a free block is not positive
-// definite (the reference's "backward_error").
+// The free block is never compacted: the factorisation runs on the full matrix with the rows / columns of the clamped
+// unknowns replaced by the identity (their factor entries are exact zeros, so the free entries come out bit-identical to the
+// compacted LLT) — every index is a compile-time constant, the iterate lives in registers and the factor in shared memory.
+// Outputs: kout = -x, Lsh (m x LM, shared memory) = that masked Cholesky factor for the FINAL active set, q with its clamped
+// entries zeroed.  Returns the bit mask of the clamped unknowns, or -1 when a free block is not positive definite (the
+// reference's "backward_error").
 template <int m, int LM>
 __device__ __noinline__ int bw_box_qp(const double* H, double* q, const double* u, const double* u_lb, const double* u_ub, const double* xinit,
-                                       double* kout, double* Hinv, const BwParams& P) {
-  double x[m], lo[m], hi[m], g[m], dx[m], xn[m], L[m * m], Ai[m * m];
-  int fidx[m], cidx[m];
-  int nf = 0, nc = 0, nf_inv = -1;
+                                       double* kout, double* Lsh, const BwParams& P) {
+  double x[m], lo[m], hi[m], g[m], dx[m], xn[m];
+  unsigned cl = 0u, cl_fact = ~0u;  // clamped set of this iteration; the set the factor in Lsh belongs to
+#pragma unroll
   for (int i = 0; i < m; ++i) { lo[i] = u_lb[i] - u[i]; hi[i] = u_ub[i] - u[i]; x[i] = fmax(fmin(xinit[i], hi[i]), lo[i]); }
-  auto value = [&](const double* v) {
+  auto value = [&](const double (&v)[m]) {
     double a = 0, b2 = 0;
+#pragma unroll
     for (int i = 0; i < m; ++i) {
       double r = 0;
+#pragma unroll
       for (int j = 0; j < m; ++j) r += H[i * LM + j] * v[j];
       a += v[i] * r; b2 += q[i] * v[i];
     }
     return 0.5 * a + b2;
   };
-  auto factor_free = [&]() -> bool {  // Hff (+ reg) = L L', Ai = (L L')^-1
-    for (int i = 0; i < nf; ++i)
-      for (int j = 0; j < nf; ++j) L[i * m + j] = H[fidx[i] * LM + fidx[j]] + ((i == j) ? P.qp_reg : 0.0);
-    for (int j = 0; j < nf; ++j) {
-      double d = L[j * m + j];
-      for (int k = 0; k < j; ++k) d -= L[j * m + k] * L[j * m + k];
+  auto factor = [&]() -> bool {  // masked Hff (+ reg) = L L'
+#pragma unroll
+    for (int j = 0; j < m; ++j) {
+      const bool cj = (cl >> j) & 1u;
+      double d = H[j * LM + j] + P.qp_reg;
+#pragma unroll
+      for (int k = 0; k < j; ++k) d -= Lsh[j * LM + k] * Lsh[j * LM + k];
+      if (cj) d = 1.0;
       if (!(d > 0.0)) return false;
       d = sqrt(d);
-      L[j * m + j] = d;
-      for (int i = j + 1; i < nf; ++i) {
-        double s = L[i * m + j];
-        for (int k = 0; k < j; ++k) s -= L[i * m + k] * L[j * m + k];
-        L[i * m + j] = s / d;
+      Lsh[j * LM + j] = d;
+#pragma unroll
+      for (int i = j + 1; i < m; ++i) {
+        double s2 = H[i * LM + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s2 -= Lsh[i * LM + k] * Lsh[j * LM + k];
+        Lsh[i * LM + j] = (cj || ((cl >> i) & 1u)) ? 0.0 : s2 / d;
       }
     }
-    for (int c = 0; c < nf; ++c) {  // column c of the inverse: L y = e_c, L' z = y
-      for (int i = 0; i < nf; ++i) {
-        double s = (i == c) ? 1.0 : 0.0;
-        for (int k = 0; k < i; ++k) s -= L[i * m + k] * Ai[k * m + c];
-        Ai[i * m + c] = s / L[i * m + i];
-      }
-      for (int i = nf - 1; i >= 0; --i) {
-        double s = Ai[i * m + c];
-        for (int k = i + 1; k < nf; ++k) s -= L[k * m + i] * Ai[k * m + c];
-        Ai[i * m + c] = s / L[i * m + i];
-      }
-    }
-    nf_inv = nf;
+    cl_fact = cl;
     return true;
   };
   for (int it = 0; it < P.qp_maxiter; ++it) {
     double gmax = 0;
+#pragma unroll
     for (int i = 0; i < m; ++i) {
       double r = q[i];
+#pragma unroll
       for (int j = 0; j < m; ++j) r += H[i * LM + j] * x[j];
       g[i] = r;
       gmax = fmax(gmax, fabs(r));
     }
-    nf = 0; nc = 0;
-    for (int j = 0; j < m; ++j) {
-      if ((x[j] == lo[j] && g[j] > 0.0) || (x[j] == hi[j] && g[j] < 0.0)) cidx[nc++] = j;
-      else fidx[nf++] = j;
-    }
-    if (gmax <= P.qp_th_grad || nf == 0) {
-      if ((it == 0 || nf_inv != nf) && !factor_free()) return 1;
+    cl = 0u;
+#pragma unroll
+    for (int j = 0; j < m; ++j)
+      if ((x[j] == lo[j] && g[j] > 0.0) || (x[j] == hi[j] && g[j] < 0.0)) cl |= 1u << j;
+    const bool none_free = cl == ((1u << m) - 1u);
+    if (gmax <= P.qp_th_grad || none_free) {
+      if (cl_fact != cl && !factor()) return -1;
       break;
     }
-    if (!factor_free()) return 1;
+    if (!factor()) return -1;
+    // dxf = Hff^-1 (-qf - Hfc xc) - xf through the masked factor (clamped rows: right-hand side 0, pivot 1)
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      double r = -q[i];
+#pragma unroll
+      for (int c = 0; c < m; ++c) if ((cl >> c) & 1u) r -= H[i * LM + c] * x[c];
+      dx[i] = ((cl >> i) & 1u) ? 0.0 : r;
+    }
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      double s2 = dx[i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) s2 -= Lsh[i * LM + k] * dx[k];
+      dx[i] = s2 / Lsh[i * LM + i];
+    }
+#pragma unroll
+    for (int i = m - 1; i >= 0; --i) {
+      double s2 = dx[i];
+#pragma unroll
+      for (int k = i + 1; k < m; ++k) s2 -= Lsh[k * LM + i] * dx[k];
+      dx[i] = s2 / Lsh[i * LM + i];
+    }
     bool tiny = true;
-    for (int i = 0; i < m; ++i) dx[i] = 0.0;
-    for (int i = 0; i < nf; ++i) {
-      double r = 0.0;
-      for (int j = 0; j < nf; ++j) {
-        double rhs = -q[fidx[j]];
-        for (int c = 0; c < nc; ++c) rhs -= H[fidx[j] * LM + cidx[c]] * x[cidx[c]];
-        r += Ai[i * m + j] * rhs;
-      }
-      const double d = r - x[fidx[i]];
-      dx[fidx[i]] = d;
-      if (fabs(d) > 1e-15 * fmax(1.0, fabs(x[fidx[i]]))) tiny = false;
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      dx[i] = ((cl >> i) & 1u) ? 0.0 : dx[i] - x[i];
+      if (fabs(dx[i]) > 1e-15 * fmax(1.0, fabs(x[i]))) tiny = false;
     }
     if (tiny) break;
     const double fold = value(x);
@@ -191,9 +205,11 @@ __device__ __noinline__ int bw_box_qp(const double* H, double* q, const double* 
     for (int n = 0; n < EMPC_N_ALPHAS; ++n) {
       const double a = 1.0 / (double)(1 << n);
       double gd = 0;
+#pragma unroll
       for (int i = 0; i < m; ++i) { xn[i] = fmax(fmin(x[i] + a * dx[i], hi[i]), lo[i]); gd += g[i] * (x[i] - xn[i]); }
       const double fnew = value(xn);
       if (fold - fnew > P.qp_th_acceptstep * gd) {
+#pragma unroll
         for (int i = 0; i < m; ++i) x[i] = xn[i];
         moved = true;
         break;
@@ -201,12 +217,9 @@ __device__ __noinline__ int bw_box_qp(const double* H, double* q, const double* 
     }
     if (!moved) break;
   }
-  for (int i = 0; i < m * LM; ++i) Hinv[i] = 0.0;
-  for (int i = 0; i < nf; ++i)
-    for (int j = 0; j < nf; ++j) Hinv[fidx[i] * LM + fidx[j]] = Ai[i * m + j];
-  for (int i = 0; i < m; ++i) kout[i] = -x[i];
-  for (int c = 0; c < nc; ++c) q[cidx[c]] = 0.0;
-  return 0;
+#pragma unroll
+  for (int i = 0; i < m; ++i) { kout[i] = -x[i]; if ((cl >> i) & 1u) q[i] = 0.0; }
+  return (int)cl;
 }
 
 // optional phase timing (-DEMPC_BW_PROFILE): lane 0 of block 0 accumulates clock64() differences between the marks of a
@@ -505,14 +518,38 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
       if constexpr (BOX) {
         if (feasible) {  // uniform over the warp (one OCP); an infeasible candidate takes the plain gains below
           boxed = true;
+          int qp = 0;
           if (lane == 0) {
             const size_t nodeu = (size_t)b * T + t;
-            bad = bw_box_qp<m, LM>(sQuu, Qu, bf.us + nodeu * m, bf.model->u_lb, bf.model->u_ub, bf.k + nodeu * m, kv, sL, P);
+            qp = bw_box_qp<m, LM>(sQuu, Qu, bf.us + nodeu * m, bf.model->u_lb, bf.model->u_ub, bf.k + nodeu * m, kv, sL, P);
           }
-          bad = __shfl_sync(0xffffffffu, bad, 0);
-          if (bad) { failed = 1; break; }
+          qp = __shfl_sync(0xffffffffu, qp, 0);
+          if (qp < 0) { failed = 1; break; }
           __syncwarp();
-          // K = Quu_inv Qxu^T, Quu_inv = the inverse of the free block (zero rows / columns for the clamped controls)
+          // Quu_inv = the inverse of the free block, zero rows / columns for the clamped controls: lane c solves
+          // L L' z = e_c through the masked factor lane 0 left in sL and writes column c into the (dead) L' area
+          if (lane < m) {
+            double z[m];
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+              double s2 = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+              for (int k = 0; k < i; ++k) s2 -= sL[i * LM + k] * z[k];
+              z[i] = s2 / sL[i * LM + i];
+            }
+#pragma unroll
+            for (int i = m - 1; i >= 0; --i) {
+              double s2 = z[i];
+#pragma unroll
+              for (int k = i + 1; k < m; ++k) s2 -= sL[k * LM + i] * z[k];
+              z[i] = s2 / sL[i * LM + i];
+            }
+            const bool ccl = (qp >> lane) & 1;
+#pragma unroll
+            for (int i = 0; i < m; ++i) sLT[i * LM + lane] = (ccl || ((qp >> i) & 1)) ? 0.0 : z[i];
+          }
+          __syncwarp();
+          // K = Quu_inv Qxu^T
           for (int c = lane; c < n; c += 32) {
             double qc[m];
 #pragma unroll
@@ -521,7 +558,7 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
             for (int i = 0; i < m; ++i) {
               double s2 = 0.0;
 #pragma unroll
-              for (int j = 0; j < m; ++j) s2 = fma(sL[i * LM + j], qc[j], s2);
+              for (int j = 0; j < m; ++j) s2 = fma(sLT[i * LM + j], qc[j], s2);
               sK[i * LD + (c ^ bw_swz(i))] = s2;
             }
           }

@@ -399,6 +399,9 @@ __global__ void __launch_bounds__(128) stream_refill_kernel(Buffers bf, StreamBu
   }
   for (int i = tid; i < T1 * NX; i += blockDim.x) bf.xs[(size_t)b * T1 * NX + i] = ((i % NX) == 6) ? 1.0 : 0.0;
   for (int i = tid; i < T * NU; i += blockDim.x) bf.us[(size_t)b * T * NU + i] = 0.0;
+  // Box solvers: k_[t] is the warm start of the node's box QP; a job is a fresh solver (k_ = 0), whichever slot it lands in
+  if (P.solver_type != EMPC_SOLVER_SBFDDP)
+    for (int i = tid; i < T * NU; i += blockDim.x) bf.k[(size_t)b * T * NU + i] = 0.0;
   if (tid == 0) {
     OcpState st;
     init_ocp_state(st, P, 0, 0.0);

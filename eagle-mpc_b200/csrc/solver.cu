@@ -667,8 +667,9 @@ static cudaError_t launch_calc_diff(empc_solver* h, int force, double smooth, co
   }
   return cudaGetLastError();
 }
-// the Box solvers run on the overlay instantiations of the rollout / decide / trial-cost kernels (the clamp of the trial
-// controls lives there), so that the kernels of the SbFDDP free path stay as they are
+// the Box solvers run on the overlay instantiation of the rollout kernel (the clamp of the trial controls lives there), so
+// that the rollout of the SbFDDP free path stays as it is; their node costs need nothing from the overlays, so decide_kernel
+// and trial_cost_kernel stay on the free instantiation (12x faster than the overlay one, which carries the contact solve)
 static inline bool box_solver(const empc_solver* h) { return h->P.solver_type != EMPC_SOLVER_SBFDDP; }
 static inline bool use_overlay(const empc_solver* h) { return h->overlay || box_solver(h); }
 template <class D>
@@ -709,7 +710,7 @@ static cudaError_t launch_rollout(empc_solver* h, int stage, int force, int feas
   if (!force) return cudaSuccess;
   const int width = (stage == 0) ? h->width_a : EMPC_N_ALPHAS - h->width_a;
   const long long n_thr = (long long)bf.nb * width * (h->T + 1);
-  if (use_overlay(h)) trial_cost_kernel<D, true><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
+  if (h->overlay) trial_cost_kernel<D, true><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
   else trial_cost_kernel<D, false><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(bf, P, width, h->hmodel);
   h->launches++;
   const long long n_warps = (long long)bf.nb * width;
@@ -731,7 +732,7 @@ static cudaError_t launch_decide(empc_solver* h, int stage, const Buffers* gb = 
     const double eff = (double)T1 / ((double)rounds * n);
     if (eff >= best - 1e-12) { best = eff; threads = n; }
   }
-  if (use_overlay(h)) decide_kernel<D, true><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
+  if (h->overlay) decide_kernel<D, true><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
   else decide_kernel<D, false><<<bf.nb, threads, 0, st>>>(bf, dp, h->hmodel);
   h->launches++;
   return cudaGetLastError();
