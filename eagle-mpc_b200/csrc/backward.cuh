@@ -108,7 +108,7 @@ struct BwParams {
 // The free block is never compacted: the factorisation runs on the full matrix with the rows / columns of the clamped
 // unknowns replaced by the identity (their factor entries are exact zeros, so the free entries come out bit-identical to the
 // compacted LLT) — every index is a compile-time constant, the iterate lives in registers and the factor in shared memory.
-// Outputs: kout = -x, Lsh (m x LM, shared memory) = that masked Cholesky factor for the FINAL active set, q with its clamped
+// Outputs: kout = -x, Lsh (m x LM, shared memory) = that masked Cholesky factor (diagonal inverted) for the FINAL active set, q with its clamped
 // entries zeroed.  Returns the bit mask of the clamped unknowns, or -1 when a free block is not positive definite (the
 // reference's "backward_error").
 template <int m, int LM>
@@ -138,14 +138,16 @@ __device__ __noinline__ int bw_box_qp(const double* H, double* q, const double* 
       for (int k = 0; k < j; ++k) d -= Lsh[j * LM + k] * Lsh[j * LM + k];
       if (cj) d = 1.0;
       if (!(d > 0.0)) return false;
-      d = sqrt(d);
-      Lsh[j * LM + j] = d;
+      // the diagonal of the factor is stored INVERTED (1 / L_jj): the substitutions multiply instead of dividing (an FP64
+      // division costs ~30 dependent instructions on this lane; the results move in the last bit only)
+      const double dinv = rsqrt_h(d);
+      Lsh[j * LM + j] = dinv;
 #pragma unroll
       for (int i = j + 1; i < m; ++i) {
         double s2 = H[i * LM + j];
 #pragma unroll
         for (int k = 0; k < j; ++k) s2 -= Lsh[i * LM + k] * Lsh[j * LM + k];
-        Lsh[i * LM + j] = (cj || ((cl >> i) & 1u)) ? 0.0 : s2 / d;
+        Lsh[i * LM + j] = (cj || ((cl >> i) & 1u)) ? 0.0 : s2 * dinv;
       }
     }
     cl_fact = cl;
@@ -184,14 +186,14 @@ __device__ __noinline__ int bw_box_qp(const double* H, double* q, const double* 
       double s2 = dx[i];
 #pragma unroll
       for (int k = 0; k < i; ++k) s2 -= Lsh[i * LM + k] * dx[k];
-      dx[i] = s2 / Lsh[i * LM + i];
+      dx[i] = s2 * Lsh[i * LM + i];
     }
 #pragma unroll
     for (int i = m - 1; i >= 0; --i) {
       double s2 = dx[i];
 #pragma unroll
       for (int k = i + 1; k < m; ++k) s2 -= Lsh[k * LM + i] * dx[k];
-      dx[i] = s2 / Lsh[i * LM + i];
+      dx[i] = s2 * Lsh[i * LM + i];
     }
     bool tiny = true;
 #pragma unroll
@@ -200,7 +202,11 @@ __device__ __noinline__ int bw_box_qp(const double* H, double* q, const double* 
       if (fabs(dx[i]) > 1e-15 * fmax(1.0, fabs(x[i]))) tiny = false;
     }
     if (tiny) break;
-    const double fold = value(x);
+    // f(x) = 1/2 x'Hx + q'x = 1/2 x'(g + q)  (g = q + Hx is already there)
+    double fold = 0.0;
+#pragma unroll
+    for (int i = 0; i < m; ++i) fold += x[i] * (g[i] + q[i]);
+    fold *= 0.5;
     bool moved = false;
     for (int n = 0; n < EMPC_N_ALPHAS; ++n) {
       const double a = 1.0 / (double)(1 << n);
@@ -535,14 +541,14 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
               double s2 = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
               for (int k = 0; k < i; ++k) s2 -= sL[i * LM + k] * z[k];
-              z[i] = s2 / sL[i * LM + i];
+              z[i] = s2 * sL[i * LM + i];   // (the factor's diagonal is stored inverted)
             }
 #pragma unroll
             for (int i = m - 1; i >= 0; --i) {
               double s2 = z[i];
 #pragma unroll
               for (int k = i + 1; k < m; ++k) s2 -= sL[k * LM + i] * z[k];
-              z[i] = s2 / sL[i * LM + i];
+              z[i] = s2 * sL[i * LM + i];
             }
             const bool ccl = (qp >> lane) & 1;
 #pragma unroll
