@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams
   constexpr int NX = D::NX, NU = D::NU;
   constexpr int CH = 512;  // nodes per chunk of the ordered cost sum
   const int b = bf.b0 + blockIdx.x;
-  __shared__ int s_acc, s_last, s_go, s_stop;
+  __shared__ int s_acc, s_last, s_go;
+  __shared__ int s_stop[2];  // one slot per parity of the step-length index: thread 0 may already write the flag of step n + 1
+                             // (a failed rollout has no barrier of its own) while slower threads still read the one of step n
   __shared__ double s_smooth;
   __shared__ double s_cost[CH];
   const empc_solver_params_t& P = dp.P;
@@ -219,10 +221,10 @@ __global__ void __launch_bounds__(256, 2) decide_kernel(Buffers bf, DecideParams
             }
           }
         }
-        s_stop = stop;
+        s_stop[n & 1] = stop;
       }
       __syncthreads();
-      if (s_stop) break;
+      if (s_stop[n & 1]) break;
     }
   }
   if (tid == 0 && mine) {

@@ -11,11 +11,14 @@ for l in open(src):
     m = re.match(r'\s*\.text\.(\S+):', l)
     if m: cur = m.group(1); bufs[cur] = []; continue
     if cur and re.match(r'\s+/\*[0-9a-f]{4,}\*/', l): bufs[cur].append(l.rstrip())
-want = {"node_calc_kernel": "node_calc", "node_cost_kernel": "node_cost", "node_diff_kernel": "node_diff", "backward_kernel": "backward",
-        "rollout_kernelINS_3DimILi3ELi6EEELi4": "rollout_w4", "decide_kernel": "decide"}
+# free-path instantiations (mangled template flags Lb0E...) + the Box-solver Riccati sweep and its box QP
+want = {"node_calc_kernel": "node_calc", "node_cost_kernel": "node_cost", "node_diff_kernel": "node_diff",
+        "backward_kernelINS_3DimILi3ELi6EEELb0ELb0E": "backward", "backward_kernelINS_3DimILi3ELi6EEELb1ELb1E": "backward_box",
+        "bw_box_qpILi9E": "bw_box_qp",
+        "rollout_kernelINS_3DimILi3ELi6EEELi4ELb0E": "rollout_w4", "decide_kernelINS_3DimILi3ELi6EEELb0E": "decide"}
 summary = []
 for name, lines in bufs.items():
-    if "3DimILi3ELi6" not in name: continue
+    if "3DimILi3ELi6" not in name and "bw_box_qpILi9E" not in name: continue
     for key, short in want.items():
         if key in name:
             ops = collections.Counter(re.sub(r'^(@!?U?P\d+\s+)?', '', re.sub(r'^\s+/\*[0-9a-f]+\*/\s+', '', x)).split()[0].split('.')[0].rstrip(';') for x in lines)

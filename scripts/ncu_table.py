@@ -1,3 +1,4 @@
+import os
 #!/usr/bin/env python3
 """profiles/ table + traffic JSON from an `ncu --set full` report holding one launch of each kernel family.
 usage: ncu_table.py <report.ncu-rep> <out.md> <out.json> <workload> <batch> <T>"""
@@ -48,5 +49,14 @@ open(out_md, "a").write("\nFP64 work per launch (hardware counters; DADD/DMUL/DF
                        "| kernel | G DADD | G DMUL | G DFMA | G DMMA FLOP | GFLOP per launch | kFLOP per node | TFLOP/s |\n|---|---|---|---|---|---|---|---|\n" + "\n".join(flines) + "\n")
 open(out_md, "a").write("\nWarp stall reasons (cycles a resident warp waits per instruction it issues, ncu `smsp__average_warps_issue_stalled_*_per_issue_active`; "
                        "top five besides the issue cycle itself):\n\n| kernel | ≈ cycles per issued instruction (top five + 1) | stalls |\n|---|---|---|\n" + "\n".join(slines) + "\n")
-json.dump({"workload": workload, "batch": batch, "T": T, "source": rep.split("/")[-1], "kernels": traffic}, open(out_json, "w"), indent=1)
+# stamped with the hash of the CUDA sources next to this script (the library under ncu was built from them): bench.py refuses
+# the numbers when the sources have changed since (bench.py source_hash)
+import hashlib
+_h = hashlib.sha256()
+_csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "eagle-mpc_b200", "csrc")
+for _f in sorted(os.listdir(_csrc)):
+    if _f.endswith((".cu", ".cuh")):
+        _h.update(open(os.path.join(_csrc, _f), "rb").read())
+json.dump({"workload": workload, "batch": batch, "T": T, "source": rep.split("/")[-1], "kernels": traffic, "source_hash": _h.hexdigest()[:16]},
+          open(out_json, "w"), indent=1)
 print(open(out_md).read())

@@ -28,5 +28,5 @@ print("box solve iters", g.iters().tolist(), "controls on a limit", int(((us == 
 PY
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 1 python /tmp/san_overlay.py 2>&1 | tail -8
 echo "memcheck rc=$?"
-timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 1 python /tmp/san_overlay.py 2>&1 | tail -6
+timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 1 python /tmp/san_overlay.py 2>&1 | tail -30
 echo "racecheck rc=$?"
