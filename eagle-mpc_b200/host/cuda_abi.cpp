@@ -39,7 +39,8 @@ const CudaAbi& cuda_abi() {
     try {
       bind(lib, "empc_last_error", abi.last_error);
       bind(lib, "empc_default_params", abi.default_params);
-      bind(lib, "empc_box_params", abi.box_params);
+      try { bind(lib, "empc_box_params", abi.box_params); }   // (a CUDA library older than the Box solvers: only they are refused)
+      catch (const std::exception&) { abi.box_params = nullptr; }
       bind(lib, "empc_create", abi.create);
       bind(lib, "empc_destroy", abi.destroy);
       bind(lib, "empc_set_x0", abi.set_x0);

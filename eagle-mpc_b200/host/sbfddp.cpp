@@ -35,6 +35,7 @@ void SolverSbFDDP::init() {
     // every model, src/trajectory.cpp:96-100,131-132)
     if (problem_->terminalModel->squash)
       throw std::invalid_argument("SolverBoxFDDP / SolverBoxDDP: the problem was created with the squashing actuation (createProblem(dt, squash = false))");
+    if (!cuda_abi().box_params) throw std::runtime_error("the loaded CUDA library has no Box solvers (empc_box_params is missing)");
     cuda_abi().box_params(&params_, solver_type_);
   }
   flatten_problem(*problem_, flat_);
