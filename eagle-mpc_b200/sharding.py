@@ -35,16 +35,19 @@ def scatter_rows(array_on_rank0, total, row_shape, dist, device="cpu", dtype=Non
             src = array_on_rank0.to(device=device, dtype=dtype)
         else:
             src = torch.as_tensor(np.ascontiguousarray(array_on_rank0), dtype=dtype, device=device)
-        reqs = []
+        # one batched group of sends (NCCL: a single ncclGroup, the transfers to all peers run concurrently over NVSwitch
+        # instead of one after the other); row slices of a contiguous array are contiguous: no staging copies
+        ops = []
         for r in range(1, world):
             rb, re = shard_range(total, r, world)
             if re > rb:
-                reqs.append(dist.isend(src[rb:re].contiguous(), dst=r))
+                ops.append(dist.P2POp(dist.isend, src[rb:re], r))
         out.copy_(src[b:e])
-        for q in reqs:
+        for q in (dist.batch_isend_irecv(ops) if ops else []):
             q.wait()
     elif e > b:
-        dist.recv(out, src=0)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, out, 0)]):
+            q.wait()
     return out
 
 
@@ -56,13 +59,15 @@ def gather_rows(local, total, dist, world=None, rank=None):
         out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         b, e = shard_range(total, 0, world)
         out[b:e].copy_(local)
+        ops = []   # every peer's shard lands straight in its rows of `out`, all receives in one batched group
         for r in range(1, world):
             rb, re = shard_range(total, r, world)
             if re > rb:
-                buf = torch.empty((re - rb,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-                dist.recv(buf, src=r)
-                out[rb:re].copy_(buf)
+                ops.append(dist.P2POp(dist.irecv, out[rb:re], r))
+        for q in (dist.batch_isend_irecv(ops) if ops else []):
+            q.wait()
         return out
     if local.shape[0] > 0:
-        dist.send(local.contiguous(), dst=0)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), 0)]):
+            q.wait()
     return None
