@@ -210,19 +210,35 @@ def R_to_quat(R):
     R = np.ascontiguousarray(R, dtype=np.float64); q = np.zeros(4); lib.orc_R_to_quat(dp(R), dp(q)); return q
 
 
+def closed_loop_bar(got_u, got_st, ref, yard, floor_u=1e-9, floor_st=1e-9):
+    """Closed-loop parity bar: the GPU loop (got_*) must stay within max(floor, 4 x the reference's own sensitivity) of the
+    oracle loop `ref` = (states, controls); the sensitivity is measured as the distance between `ref` and `yard`, the same
+    loop run by the oracle compiled without FMA contraction (the closed loop feeds every solve's rounding into the next
+    plant state, so the bar has to be a measured one).  Returns the four distances (u gpu, u self, x gpu, x self)."""
+    st_o, u_o = ref
+    st_y, u_y = yard
+    su, sx = max(1.0, np.abs(u_o).max()), max(1.0, np.abs(st_o).max())
+    du_self, dx_self = np.abs(u_y - u_o).max() / su, np.abs(st_y - st_o).max() / sx
+    du, dx = np.abs(got_u - u_o).max() / su, np.abs(got_st - st_o).max() / sx
+    assert du <= max(floor_u, 4 * du_self), ("controls", du, du_self)
+    assert dx <= max(floor_st, 4 * dx_self), ("states", dx, dx_self)
+    return du, du_self, dx, dx_self
+
+
 def oracle_closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, record=False, t_start=0, xs_warm=None, us_warm=None,
-                       params=None):
+                       params=None, nofma=False):
     """CPU twin of eagle-mpc_b200.mpc.closed_loop: same host-side CarrotMpc retargeting (created without a solver),
     oracle solves and oracle RK4 plant."""
     import time
     T = mpc.knots - 1
-    o = Oracle(mpc)
-    lib.orc_update_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Cost), C.c_int, C.c_int, abi.c_double_p]
-    lib.orc_plant_step.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, C.c_double, abi.c_double_p]
+    o = Oracle(mpc, nofma=nofma)   # nofma: the rounding yardstick of closed_loop_bar
+    L = o.lib
+    L.orc_update_costs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Cost), C.c_int, C.c_int, abi.c_double_p]
+    L.orc_plant_step.argtypes = [C.c_void_p, abi.c_double_p, abi.c_double_p, C.c_double, abi.c_double_p]
 
     def push():
         costs, pool = mpc.cost_tables()
-        lib.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), dp(pool))
+        L.orc_update_costs(o.p, 0, len(costs), costs, 0, len(pool), dp(pool))
 
     p = default_params() if params is None else params   # params: e.g. box_params(...) for a controller built on a Box solver
     mpc.updateProblem(int(t_start)); push()
@@ -242,7 +258,7 @@ def oracle_closed_loop(mpc, xs_traj, us_traj, x_start, n_steps, dt_sim_ms=2, rec
         lat.append(time.perf_counter() - t0)
         u = o.get("us_squash")[0].copy()
         xn = np.zeros_like(x)
-        lib.orc_plant_step(o.p, dp(np.ascontiguousarray(x)), dp(np.ascontiguousarray(u)), dt_sim_ms / 1000.0, dp(xn))
+        L.orc_plant_step(o.p, dp(np.ascontiguousarray(x)), dp(np.ascontiguousarray(u)), dt_sim_ms / 1000.0, dp(xn))
         x = xn
         t += dt_sim_ms
         if record:

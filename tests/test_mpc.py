@@ -65,8 +65,8 @@ def test_carrot_closed_loop_gpu_vs_oracle():
     mpc_o = mpcmod.CarrotMpc(tr, xs, 20, MPC, create_solver=False)
     lat_o, st_o, u_o, it_o = ob.oracle_closed_loop(mpc_o, xs, us, xs[0], n_steps, record=True)
     assert it_g == it_o
-    assert np.abs(u_g - u_o).max() <= 1e-7 * max(1.0, np.abs(u_o).max())
-    assert np.abs(st_g - st_o).max() <= 1e-8 * max(1.0, np.abs(st_o).max())
+    _l, st_y, u_y, it_y = ob.oracle_closed_loop(mpcmod.CarrotMpc(tr, xs, 20, MPC, create_solver=False), xs, us, xs[0], n_steps, record=True, nofma=True)
+    print("carrot closed loop: u gpu %.1e / self %.1e, x gpu %.1e / self %.1e" % ob.closed_loop_bar(u_g, st_g, (st_o, u_o), (st_y, u_y)))
     print("p50 latency gpu %.3f ms, oracle %.3f ms" % (1e3 * np.median(lat_g), 1e3 * np.median(lat_o)))
 
 
@@ -152,8 +152,8 @@ def _closed_loop_pair(make, xs, us, n_steps):
     mpc_o = make(False)
     lat_o, st_o, u_o, it_o = ob.oracle_closed_loop(mpc_o, xs, us, xs[0], n_steps, record=True)
     assert it_g == it_o
-    assert np.abs(u_g - u_o).max() <= 1e-7 * max(1.0, np.abs(u_o).max())
-    assert np.abs(st_g - st_o).max() <= 1e-8 * max(1.0, np.abs(st_o).max())
+    _l, st_y, u_y, it_y = ob.oracle_closed_loop(make(False), xs, us, xs[0], n_steps, record=True, nofma=True)
+    print("closed loop: u gpu %.1e / self %.1e, x gpu %.1e / self %.1e" % ob.closed_loop_bar(u_g, st_g, (st_o, u_o), (st_y, u_y)))
     return 1e3 * np.median(lat_g), 1e3 * np.median(lat_o)
 
 
@@ -425,8 +425,9 @@ def test_batched_device_closed_loop_rail():
         _lat, st_o, u_o, it_o = ob.oracle_closed_loop(mpc_o, xs, us, x0[b], n_steps, dt_sim_ms=dt_sim, record=True, t_start=t0,
                                                        xs_warm=xs_b[b], us_warm=us_b[b])
         assert list(it_g[:, b]) == it_o, (b, t0)
-        assert np.abs(u_g[:, b] - u_o).max() <= 1e-7 * max(1.0, np.abs(u_o).max()), (b, t0)
-        assert np.abs(st_g[:, b] - st_o).max() <= 1e-8 * max(1.0, np.abs(st_o).max()), (b, t0)
+        _l, st_y, u_y, it_y = ob.oracle_closed_loop(mpcmod.RailMpc(xs, 20, IRIS_MPC, create_solver=False), xs, us, x0[b], n_steps, dt_sim_ms=dt_sim,
+                                                    record=True, t_start=t0, xs_warm=xs_b[b], us_warm=us_b[b], nofma=True)
+        ob.closed_loop_bar(u_g[:, b], st_g[:, b], (st_o, u_o), (st_y, u_y))
 
 
 # ---- golden cost tables (tests/golden/mpc_cost_tables.json, written by tests/golden/make_golden_mpc.py) --------------------
