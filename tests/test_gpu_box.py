@@ -239,3 +239,31 @@ def test_box_stream_equals_plain_batch():
     assert np.array_equal(out["cost"], ref.cost()) and np.array_equal(out["xs"], ref.xs()) and np.array_equal(out["us"], ref.us())
     lb, ub = limits(fp)
     assert ((out["us"] == lb) | (out["us"] == ub)).any()
+
+
+@pytest.mark.parametrize("name,yaml,integ,maxiter", [("move_arm_rk4", "hexacopter370_flying_arm_3/trajectories/move_arm.yaml", "IntegratedActionModelRK4", 30),
+                                                      ("eagle_catch_contact", "hexacopter370_flying_arm_3/trajectories/eagle_catch.yaml", EULER, 12)])
+def test_box_over_the_other_overlays(name, yaml, integ, maxiter):
+    """SolverBoxFDDP on a problem that also uses an overlay node model — createProblem(dt, False, "IntegratedActionModelRK4"), or
+    a trajectory with a contact stage: the box sweep (which carries the Lxu / dense Luu terms those nodes produce) and the
+    clamped rollout (which calls their dynamics) against the oracle's iteration path"""
+    fp = host.Trajectory(yaml).createProblem(20, False, integ)
+    B = 2
+    x0 = np.tile(fp.x0, (B, 1))
+    x0[1] = wl.noisy_x0(fp.x0, 1, 5800)[0]
+    pg = capi.box_params(abi.SOLVER_BOXFDDP); pg.maxiter = maxiter
+    po = ob.box_params(abi.SOLVER_BOXFDDP); po.maxiter = maxiter
+    g = capi.BatchSolver(fp, B)
+    g.set_params(pg); g.enable_iteration_log(512)
+    g.set_x0(x0); g.set_candidate(None, None, False); g.solve()
+    got = {"xs": g.xs(), "us": g.us(), "K": g.K(), "k": g.k(), "cost": g.cost(), "us_squash": g.us_squash()}
+    iters, feas = g.iters(), g.feasible()
+    lb, ub = limits(fp)
+    assert np.all(got["us"] >= lb) and np.all(got["us"] <= ub)
+    worst = {}
+    for b in range(B):
+        for key, d_gpu, d_self in parity.check_ocp((name, b), fp, x0[b], {k_: v[b] for k_, v in got.items()}, iters[b], feas[b], params=po,
+                                                   log=g.iteration_log(b), perturb=1e-12 if "contact" in name else 0.0):
+            w = worst.setdefault(key, [0.0, 0.0])
+            w[0] = max(w[0], d_gpu); w[1] = max(w[1], d_self)
+    print(name, "box iters", iters.tolist(), {k_: f"gpu {v[0]:.1e} / self {v[1]:.1e}" for k_, v in worst.items()})
