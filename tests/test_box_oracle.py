@@ -173,3 +173,25 @@ def test_mpc_controller_with_a_box_solver_builds_the_unsquashed_problem(solver, 
     assert abi.COST_SQUASH_BARRIER not in {c.type for c in mpc.cost_tables()[0]}
     ref = mpcmod.CarrotMpc(tr, xs, 20, "hexacopter370_flying_arm_3/mpc/mpc.yaml", create_solver=False)
     assert ref.desc.use_squash == 1 and abi.COST_SQUASH_BARRIER in {c.type for c in ref.cost_tables()[0]}
+
+
+GB = np.load(os.path.join(ROOT, "tests", "golden", "twin_box.npz"))
+
+
+@pytest.mark.parametrize("ci", range(int(GB["n_cases"])))
+def test_oracle_box_sweep_equals_twin_golden(ci):
+    """the committed twin fixture of the box sweeps (scripts/make_twin_box_golden.py) against the oracle"""
+    key = f"c{ci}"
+    yaml, dt = str(GB[key + "_yaml"]), int(GB[key + "_dt"])
+    tail, xreg, smooth = int(GB["tail"]), float(GB["xreg"]), float(GB["smooth"])
+    fp = host.Trajectory(yaml).createProblem(dt, False, "IntegratedActionModelEuler")
+    xs, us = GB[key + "_xs"], GB[key + "_us"]
+    o = ob.Oracle(fp)
+    o.set_params(ob.box_params(abi.SOLVER_BOXFDDP))
+    o.set_x0(xs[0]); o.set_candidate(xs, us, True)
+    o.phase_calc_diff(smooth)
+    T0 = fp.T - tail
+    for sweep in range(2):
+        assert o.phase_backward(xreg, True)
+        for name, got in (("K", o.get("K")[T0:]), ("k", o.get("k")[T0:]), ("Vx", o.get("Vx")[T0:fp.T])):
+            assert rel_err(got, GB[f"{key}_s{sweep}_{name}"]) <= 1e-9, (yaml, sweep, name, rel_err(got, GB[f"{key}_s{sweep}_{name}"]))

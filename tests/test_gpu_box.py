@@ -5,6 +5,7 @@ bw_box_qp) and the rollouts clamp the trial controls.  Checker: the CPU oracle (
 numpy twin in tests/test_box_oracle.py).  Phase level: K, k, Vx of box sweeps (cold and warm-started) and clamped trials;
 solver level: the oracle's iteration path and solution on the YAML problems, plus the Python front-ends."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -267,3 +268,31 @@ def test_box_over_the_other_overlays(name, yaml, integ, maxiter):
             w = worst.setdefault(key, [0.0, 0.0])
             w[0] = max(w[0], d_gpu); w[1] = max(w[1], d_self)
     print(name, "box iters", iters.tolist(), {k_: f"gpu {v[0]:.1e} / self {v[1]:.1e}" for k_, v in worst.items()})
+
+
+GB = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "twin_box.npz"))
+
+
+@pytest.mark.parametrize("ci", range(int(GB["n_cases"])))
+def test_box_sweep_equals_twin_golden(ci):
+    """backward_kernel<D, true, true> against gains generated by the independent numpy twin (tests/golden/twin_box.npz, made by
+    scripts/make_twin_box_golden.py: complex-step node blocks, dense Riccati recursion, its own projected-Newton box QP) over
+    the last nodes of the horizon, cold and warm-started.  No oracle code runs here: the fixture is the checker."""
+    key = f"c{ci}"
+    yaml, dt = str(GB[key + "_yaml"]), int(GB[key + "_dt"])
+    tail, xreg, smooth = int(GB["tail"]), float(GB["xreg"]), float(GB["smooth"])
+    fp = host.Trajectory(yaml).createProblem(dt, False, EULER)
+    xs, us = GB[key + "_xs"], GB[key + "_us"]
+    g = capi.BatchSolver(fp, 2)
+    g.set_params(capi.box_params(abi.SOLVER_BOXFDDP))
+    g.set_x0(np.stack([xs[0], xs[0]])); g.set_candidate(np.stack([xs, xs]), np.stack([us, us]), True)
+    g.phase_calc_diff(smooth)
+    T0 = fp.T - tail
+    for sweep in range(2):
+        # (sweep 1 is warm-started by sweep 0's k, on the device as in the fixture; the nodes before the tail do not enter it)
+        assert np.all(g.phase_backward(xreg, True) == 1)
+        K, k, Vx = g.K()[1], g.k()[1], g.Vx()[1]
+        for name, got in (("K", K[T0:]), ("k", k[T0:]), ("Vx", Vx[T0:fp.T])):
+            ref = GB[f"{key}_s{sweep}_{name}"]
+            assert rel(got, ref) <= 1e-9, (yaml, sweep, name, rel(got, ref))
+        assert np.array_equal(np.all(K[T0:] == 0.0, axis=-1), np.all(GB[f"{key}_s{sweep}_K"] == 0.0, axis=-1)), "different active sets"
