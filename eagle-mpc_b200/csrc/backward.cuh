@@ -97,134 +97,129 @@ struct BwParams {
   double qp_th_acceptstep, qp_th_grad, qp_reg;
 };
 
-// crocoddyl::BoxQP::solve for one node, run by ONE lane (the problem is nu x nu: 4 .. 11 unknowns): projected Newton on
-//   min 1/2 x' H x + q' x,  u_lb - u <= x <= u_ub - u,  from the clamped warm start xinit (the k_[t] of the previous sweep).
-// Mirrors the oracle's box_qp (oracle/oracle.cpp) decision by decision: clamped = on a bound with the gradient pushing
-// outwards, converged when the gradient's infinity norm <= th_grad or nothing is free, Newton step on the free block through
-// its LLT, projected line search alpha = 1 .. 1/512 with the Armijo test.  Two exits the reference does not have, both at
+// crocoddyl::BoxQP::solve for one node, run by the WARP (the problem is nu x nu: 4 .. 11 unknowns; lane i owns unknown i):
+// projected Newton on  min 1/2 x' H x + q' x,  u_lb - u <= x <= u_ub - u,  from the clamped warm start (the k_[t] of the
+// previous sweep).  Mirrors the oracle's box_qp (oracle/oracle.cpp) decision by decision: clamped = on a bound with the
+// gradient pushing outwards, converged when the gradient's infinity norm <= th_grad or nothing is free, Newton step on the
+// free block, projected line search alpha = 1 .. 1/512 with the Armijo test.  Two exits the reference does not have, both at
 // iterates it would keep (bit for bit, or to the last few ulp) for the rest of its maxiter iterations: no step length was
 // accepted (the loop is deterministic: every further iteration repeats this one), and a Newton step below 1e-15 relative
 // (the iterate is the minimiser on its free set; the reference random-walks on the last bit from here).
 // The free block is never compacted: the factorisation runs on the full matrix with the rows / columns of the clamped
-// unknowns replaced by the identity (their factor entries are exact zeros, so the free entries come out bit-identical to the
-// compacted LLT) — every index is a compile-time constant, the iterate lives in registers and the factor in shared memory.
-// Outputs: kout = -x, Lsh (m x LM, shared memory) = that masked Cholesky factor (diagonal inverted) for the FINAL active set, q with its clamped
-// entries zeroed.  Returns the bit mask of the clamped unknowns, or -1 when a free block is not positive definite (the
-// reference's "backward_error").
+// unknowns replaced by the identity (their factor entries are exact zeros, so the free entries are those of the compacted
+// factorisation).  It is the sweep's own right-looking L D L^T by shuffles (lane i holds row i), the substitutions and the
+// matrix-vector products travel by shuffles too, sums are butterfly reductions (identical on every lane, so every decision
+// is warp-uniform).  A first version ran the QP on lane 0 alone: 21 k cycles per QP iteration, 49 k per node (clock64
+// counters) — one dependent FP64 chain with the sweep's registers spilled around it.
+// Leaves in shared memory what the gain solves of the sweep expect from a factorisation — L row-wise (sL), column-wise
+// (sLT), reciprocal pivots (sLinv) — for the masked matrix of the FINAL active set.  Returns the bit mask of the clamped
+// unknowns, or -1 when a free block is not positive definite (the reference's "backward_error"); xout = this lane's x.
 template <int m, int LM>
-__device__ __noinline__ int bw_box_qp(const double* H, double* q, const double* u, const double* u_lb, const double* u_ub, const double* xinit,
-                                       double* kout, double* Lsh, const BwParams& P) {
-  double x[m], lo[m], hi[m], g[m], dx[m], xn[m];
-  unsigned cl = 0u, cl_fact = ~0u;  // clamped set of this iteration; the set the factor in Lsh belongs to
+__device__ __noinline__ int bw_box_qp(const double* H, const double* q, const double* u, const double* u_lb, const double* u_ub, const double* xinit,
+                                       double* sL, double* sLT, double* sLinv, const BwParams& P, double& xout) {
+  constexpr unsigned FULL = 0xffffffffu, MM = (1u << m) - 1u;
+  const int lane = threadIdx.x, i = lane < m ? lane : m - 1;
+  const bool on = lane < m;
+  auto wmax = [&](double v) {
 #pragma unroll
-  for (int i = 0; i < m; ++i) { lo[i] = u_lb[i] - u[i]; hi[i] = u_ub[i] - u[i]; x[i] = fmax(fmin(xinit[i], hi[i]), lo[i]); }
-  auto value = [&](const double (&v)[m]) {
-    double a = 0, b2 = 0;
-#pragma unroll
-    for (int i = 0; i < m; ++i) {
-      double r = 0;
-#pragma unroll
-      for (int j = 0; j < m; ++j) r += H[i * LM + j] * v[j];
-      a += v[i] * r; b2 += q[i] * v[i];
-    }
-    return 0.5 * a + b2;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
   };
-  auto factor = [&]() -> bool {  // masked Hff (+ reg) = L L'
+  double h[m];  // row i of H
+#pragma unroll
+  for (int k = 0; k < m; ++k) h[k] = H[i * LM + k];
+  const double qi = q[i], lo = u_lb[i] - u[i], hi = u_ub[i] - u[i];
+  double xi = fmax(fmin(xinit[i], hi), lo), dinv_i = 1.0;
+  double a[m], lt[m];  // row i of the unit-lower factor (entries k < i) / column i of it (entries k > i)
+  unsigned cl = 0u, cl_fact = ~0u;
+  bool cli = false;
+  auto factor = [&]() -> bool {
+#pragma unroll
+    for (int k = 0; k < m; ++k) {
+      const bool masked = cli || ((cl >> k) & 1u);
+      a[k] = masked ? ((k == i) ? 1.0 : 0.0) : (h[k] + ((k == i) ? P.qp_reg : 0.0));
+    }
+    int bad = 0;
 #pragma unroll
     for (int j = 0; j < m; ++j) {
-      const bool cj = (cl >> j) & 1u;
-      double d = H[j * LM + j] + P.qp_reg;
+      const double d = __shfl_sync(FULL, a[j], j);
+      double acj[m];
 #pragma unroll
-      for (int k = 0; k < j; ++k) d -= Lsh[j * LM + k] * Lsh[j * LM + k];
-      if (cj) d = 1.0;
-      if (!(d > 0.0)) return false;
-      // the diagonal of the factor is stored INVERTED (1 / L_jj): the substitutions multiply instead of dividing (an FP64
-      // division costs ~30 dependent instructions on this lane; the results move in the last bit only)
-      const double dinv = rsqrt_h(d);
-      Lsh[j * LM + j] = dinv;
+      for (int c = j + 1; c < m; ++c) acj[c] = __shfl_sync(FULL, a[j], c);  // A(c, j) = d L(c, j)
+      if (!(d > 0.0)) bad = 1;
+      const double dinv = rcp_h(d);
+      const double lij = a[j] * dinv;
+      a[j] = lij;
 #pragma unroll
-      for (int i = j + 1; i < m; ++i) {
-        double s2 = H[i * LM + j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) s2 -= Lsh[i * LM + k] * Lsh[j * LM + k];
-        Lsh[i * LM + j] = (cj || ((cl >> i) & 1u)) ? 0.0 : s2 * dinv;
-      }
+      for (int c = j + 1; c < m; ++c) a[c] = fma(-lij, acj[c], a[c]);
+      if (on) sLT[j * LM + i] = lij;  // column j of L = row j of L^T (entries i <= j are never read)
+      if (j == i) dinv_i = dinv;
+      if (lane == j) sLinv[j] = dinv;
     }
+    if (on) {
+#pragma unroll
+      for (int k = 0; k < m; ++k) sL[i * LM + k] = a[k];  // (entries k >= i are never read)
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < m; ++k) lt[k] = sLT[i * LM + k];
     cl_fact = cl;
-    return true;
+    return !bad;  // uniform: every lane evaluates every pivot
   };
   for (int it = 0; it < P.qp_maxiter; ++it) {
-    double gmax = 0;
+    double gi = qi;
 #pragma unroll
-    for (int i = 0; i < m; ++i) {
-      double r = q[i];
-#pragma unroll
-      for (int j = 0; j < m; ++j) r += H[i * LM + j] * x[j];
-      g[i] = r;
-      gmax = fmax(gmax, fabs(r));
-    }
-    cl = 0u;
-#pragma unroll
-    for (int j = 0; j < m; ++j)
-      if ((x[j] == lo[j] && g[j] > 0.0) || (x[j] == hi[j] && g[j] < 0.0)) cl |= 1u << j;
-    const bool none_free = cl == ((1u << m) - 1u);
-    if (gmax <= P.qp_th_grad || none_free) {
+    for (int j = 0; j < m; ++j) gi = fma(h[j], __shfl_sync(FULL, xi, j), gi);
+    cli = (xi == lo && gi > 0.0) || (xi == hi && gi < 0.0);
+    cl = __ballot_sync(FULL, cli && on) & MM;
+    const double gmax = wmax(on ? fabs(gi) : 0.0);
+    if (gmax <= P.qp_th_grad || cl == MM) {
       if (cl_fact != cl && !factor()) return -1;
       break;
     }
     if (!factor()) return -1;
     // dxf = Hff^-1 (-qf - Hfc xc) - xf through the masked factor (clamped rows: right-hand side 0, pivot 1)
+    double r = -qi;
 #pragma unroll
-    for (int i = 0; i < m; ++i) {
-      double r = -q[i];
-#pragma unroll
-      for (int c = 0; c < m; ++c) if ((cl >> c) & 1u) r -= H[i * LM + c] * x[c];
-      dx[i] = ((cl >> i) & 1u) ? 0.0 : r;
+    for (int c = 0; c < m; ++c) {
+      const double xc = __shfl_sync(FULL, xi, c);
+      if ((cl >> c) & 1u) r = fma(-h[c], xc, r);
     }
+    double y = cli ? 0.0 : r;
 #pragma unroll
-    for (int i = 0; i < m; ++i) {
-      double s2 = dx[i];
-#pragma unroll
-      for (int k = 0; k < i; ++k) s2 -= Lsh[i * LM + k] * dx[k];
-      dx[i] = s2 * Lsh[i * LM + i];
+    for (int k = 0; k < m; ++k) {  // L y = r
+      const double yk = __shfl_sync(FULL, y, k);
+      if (i > k) y = fma(-a[k], yk, y);
     }
+    y *= dinv_i;
 #pragma unroll
-    for (int i = m - 1; i >= 0; --i) {
-      double s2 = dx[i];
-#pragma unroll
-      for (int k = i + 1; k < m; ++k) s2 -= Lsh[k * LM + i] * dx[k];
-      dx[i] = s2 * Lsh[i * LM + i];
+    for (int k = m - 1; k >= 0; --k) {  // L' w = D^-1 y
+      const double wk = __shfl_sync(FULL, y, k);
+      if (i < k) y = fma(-lt[k], wk, y);
     }
-    bool tiny = true;
+    const double dxi = (cli || !on) ? 0.0 : y - xi;
+    const bool big = fabs(dxi) > 1e-15 * fmax(1.0, fabs(xi));
+    if (__ballot_sync(FULL, big) == 0u) break;  // the Newton step no longer moves the iterate
+    auto wsum = [&](double v) {
 #pragma unroll
-    for (int i = 0; i < m; ++i) {
-      dx[i] = ((cl >> i) & 1u) ? 0.0 : dx[i] - x[i];
-      if (fabs(dx[i]) > 1e-15 * fmax(1.0, fabs(x[i]))) tiny = false;
-    }
-    if (tiny) break;
-    // f(x) = 1/2 x'Hx + q'x = 1/2 x'(g + q)  (g = q + Hx is already there)
-    double fold = 0.0;
-#pragma unroll
-    for (int i = 0; i < m; ++i) fold += x[i] * (g[i] + q[i]);
-    fold *= 0.5;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      return v;
+    };
+    const double fold = 0.5 * wsum(on ? xi * (gi + qi) : 0.0);  // f(x) = 1/2 x'Hx + q'x = 1/2 x'(g + q)
     bool moved = false;
     for (int n = 0; n < EMPC_N_ALPHAS; ++n) {
-      const double a = 1.0 / (double)(1 << n);
-      double gd = 0;
+      const double al = 1.0 / (double)(1 << n);
+      const double xn = fmax(fmin(xi + al * dxi, hi), lo);
+      double hx = 0.0;
 #pragma unroll
-      for (int i = 0; i < m; ++i) { xn[i] = fmax(fmin(x[i] + a * dx[i], hi[i]), lo[i]); gd += g[i] * (x[i] - xn[i]); }
-      const double fnew = value(xn);
-      if (fold - fnew > P.qp_th_acceptstep * gd) {
-#pragma unroll
-        for (int i = 0; i < m; ++i) x[i] = xn[i];
-        moved = true;
-        break;
-      }
+      for (int j = 0; j < m; ++j) hx = fma(h[j], __shfl_sync(FULL, xn, j), hx);
+      const double fnew = wsum(on ? xn * (0.5 * hx + qi) : 0.0);
+      const double gd = wsum(on ? gi * (xi - xn) : 0.0);
+      if (fold - fnew > P.qp_th_acceptstep * gd) { xi = xn; moved = true; break; }  // uniform: the sums are identical on every lane
     }
     if (!moved) break;
   }
-#pragma unroll
-  for (int i = 0; i < m; ++i) { kout[i] = -x[i]; if ((cl >> i) & 1u) q[i] = 0.0; }
+  xout = xi;
   return (int)cl;
 }
 
@@ -521,53 +516,23 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
       // column-wise for the substitutions, the reciprocal pivots beside it. ----
       int bad = 0;
       bool boxed = false;
+      double box_x = 0.0;
       if constexpr (BOX) {
         if (feasible) {  // uniform over the warp (one OCP); an infeasible candidate takes the plain gains below
           boxed = true;
-          int qp = 0;
-          if (lane == 0) {
-            const size_t nodeu = (size_t)b * T + t;
-            qp = bw_box_qp<m, LM>(sQuu, Qu, bf.us + nodeu * m, bf.model->u_lb, bf.model->u_ub, bf.k + nodeu * m, kv, sL, P);
-          }
-          qp = __shfl_sync(0xffffffffu, qp, 0);
+          const size_t nodeu = (size_t)b * T + t;
+          const int qp = bw_box_qp<m, LM>(sQuu, Qu, bf.us + nodeu * m, bf.model->u_lb, bf.model->u_ub, bf.k + nodeu * m, sL, sLT, sLinv, P, box_x);
           if (qp < 0) { failed = 1; break; }
+          // K = Quu_inv Qxu^T with Quu_inv = the inverse of the free block (zero rows / columns for the clamped controls): the
+          // gain solves below run on the masked factor the QP left behind, so the clamped rows of their right-hand sides (of
+          // Qxu^T) are zeroed; the clamped entries of Qu are zeroed for good ("important for accounting the algorithm
+          // advancement": expected improvement and stopping criterion see the projected gradient)
           __syncwarp();
-          // Quu_inv = the inverse of the free block, zero rows / columns for the clamped controls: lane c solves
-          // L L' z = e_c through the masked factor lane 0 left in sL and writes column c into the (dead) L' area
-          if (lane < m) {
-            double z[m];
+          for (int c = lane; c < LD; c += 32) {
 #pragma unroll
-            for (int i = 0; i < m; ++i) {
-              double s2 = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-              for (int k = 0; k < i; ++k) s2 -= sL[i * LM + k] * z[k];
-              z[i] = s2 * sL[i * LM + i];   // (the factor's diagonal is stored inverted)
-            }
-#pragma unroll
-            for (int i = m - 1; i >= 0; --i) {
-              double s2 = z[i];
-#pragma unroll
-              for (int k = i + 1; k < m; ++k) s2 -= sL[k * LM + i] * z[k];
-              z[i] = s2 * sL[i * LM + i];
-            }
-            const bool ccl = (qp >> lane) & 1;
-#pragma unroll
-            for (int i = 0; i < m; ++i) sLT[i * LM + lane] = (ccl || ((qp >> i) & 1)) ? 0.0 : z[i];
+            for (int cu = 0; cu < m; ++cu) if ((qp >> cu) & 1) sQux[cu * LD + c] = 0.0;
           }
-          __syncwarp();
-          // K = Quu_inv Qxu^T
-          for (int c = lane; c < n; c += 32) {
-            double qc[m];
-#pragma unroll
-            for (int j = 0; j < m; ++j) qc[j] = sQux[j * LD + (c ^ bw_swz(j))];
-#pragma unroll
-            for (int i = 0; i < m; ++i) {
-              double s2 = 0.0;
-#pragma unroll
-              for (int j = 0; j < m; ++j) s2 = fma(sLT[i * LM + j], qc[j], s2);
-              sK[i * LD + (c ^ bw_swz(i))] = s2;
-            }
-          }
+          if (lane < m && ((qp >> lane) & 1)) Qu[lane] = 0.0;
           __syncwarp();
         }
       }
@@ -600,6 +565,7 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
       EMPC_BW_MARK(3);
       }
       if (bad) { failed = 1; break; }  // uniform: every lane evaluates every pivot
+      }  // !boxed
       // ---- gains: K = Quu^-1 Qxu^T (one right-hand side per lane), k = Quu^-1 Qu ----
       for (int c = lane; c < n + 1; c += 32) {
         double rhs[m];
@@ -644,7 +610,12 @@ __global__ void __launch_bounds__(32) __maxnreg__(BwCfg<D>::MAXREG) backward_ker
           for (int i = 0; i < m; ++i) kv[i] = rhs[i];
         }
       }
-      }  // !boxed
+      if constexpr (BOX) {
+        if (boxed) {  // k = -du of the box QP (the column solved above for k belongs to the unconstrained step)
+          __syncwarp();
+          if (lane < m) kv[lane] = -box_x;
+        }
+      }
       __syncwarp();
       EMPC_BW_MARK(4);
       if (lane < m) {  // Quuk = Quu k

@@ -28,7 +28,8 @@ mg.solve(xs[0], xs[:T + 1], us[:T], maxiter=100, convergence_init=1e-2)
 p.maxiter = mg.iters; o.set_params(p)
 x = xs[0].copy(); t = 0
 lb = np.array(fp.desc.u_lb[:nu]); ub = np.array(fp.desc.u_ub[:nu])
-for step in range(20):
+for step in range(int(os.environ.get("NSTEPS", "20"))):
+    print("STEP", step, flush=True)
     mg.updateProblem(t); mo.updateProblem(t); push()
     o.set_x0(x); o.solve(o.get("xs"), o.get("us"))
     mg.solve(x, None, None, maxiter=mg.iters, convergence_init=1e-3)
