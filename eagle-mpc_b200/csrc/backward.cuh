@@ -134,6 +134,7 @@ __device__ __noinline__ int bw_box_qp(const double* H, const double* q, const do
   unsigned cl = 0u, cl_fact = ~0u;
   bool cli = false;
   auto factor = [&]() -> bool {
+    __syncwarp();  // the column loads of the previous factorisation (lt) are done before its shared-memory arrays are rewritten
 #pragma unroll
     for (int k = 0; k < m; ++k) {
       const bool masked = cli || ((cl >> k) & 1u);
